@@ -1,0 +1,263 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on CPU.
+
+TEST INFRASTRUCTURE.  Run in the build container only (the GPU box has no
+/root/reference):   python -m oracle.make_golden
+
+RNG injection: the reference draws noise with torch.normal (mobody_dynamics.py:220),
+member indices with np.random.choice (mobody_module.py:356) and buffer indices with
+np.random.randint (utils.py:128).  We patch those three callables around the reference
+call so the recorded eps / idx / ind are exactly what the reference consumed.
+Weights come from oracle.philox.recipe_fill (named by seed), so fixtures stay small.
+"""
+import os
+import sys
+import contextlib
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+from oracle import mobody_oracle as O  # noqa: E402
+
+HEALTHY = {  # state means inside each env's healthy set
+    "walker2d": lambda S: np.r_[1.25, 0.0, np.zeros(S - 2)],
+    "hopper": lambda S: np.r_[1.25, 0.0, np.zeros(S - 2)],
+    "halfcheetah": lambda S: np.zeros(S),
+    "ant": lambda S: np.r_[0.6, np.zeros(S - 1)],
+}
+ENV_NAME = {"walker2d": "walker2d-medium-v2", "hopper": "hopper-medium-v2",
+            "halfcheetah": "halfcheetah-medium-v2", "ant": "ant-medium-v2"}
+
+
+def _import_reference():
+    sys.path.insert(0, REF)
+    from algo.dynamics.mobody_module import MOBODYModule
+    from algo.dynamics.mobody_dynamics import MOBODYEnsembleDynamics
+    from algo.mb_utils.terminal_funs import get_termination_fn
+    from algo.offline_offline.mobody import MOBODY
+    from algo import utils as ref_utils
+    return MOBODYModule, MOBODYEnsembleDynamics, get_termination_fn, MOBODY, ref_utils
+
+
+class Inject:
+    """Patch torch.normal / np.random.choice / np.random.randint with scripted draws."""
+    def __init__(self, eps_fn=None, idx_fn=None, ind_list=None):
+        self.eps_fn, self.idx_fn, self.ind_list = eps_fn, idx_fn, list(ind_list or [])
+        self.calls = {"normal": 0, "choice": 0, "randint": 0}
+
+    def __enter__(self):
+        self._n, self._c, self._r = torch.normal, np.random.choice, np.random.randint
+        me = self
+
+        def normal(mean=None, std=None, **kw):
+            eps = me.eps_fn(me.calls["normal"], tuple(std.shape)); me.calls["normal"] += 1
+            return mean + eps * std
+
+        def choice(a, size=None, **kw):
+            idx = me.idx_fn(me.calls["choice"], int(size)); me.calls["choice"] += 1
+            return np.asarray(a)[idx]          # idx are *slots* into elites
+
+        def randint(low, high=None, size=None, **kw):
+            ind = me.ind_list[me.calls["randint"]]; me.calls["randint"] += 1
+            assert len(ind) == size and ind.max() < high
+            return ind
+        torch.normal, np.random.choice, np.random.randint = normal, choice, randint
+        return self
+
+    def __exit__(self, *a):
+        torch.normal, np.random.choice, np.random.randint = self._n, self._c, self._r
+
+
+def healthy(env, S, h0=None):
+    hs = HEALTHY[env](S).astype(np.float64)
+    if h0 is not None:
+        hs[0] = h0
+    return hs
+
+
+def build_reference_dynamics(S, A, seed, env, coef, h0=None, t3_gain=1.0):
+    MOBODYModule, MOBODYEnsembleDynamics, get_termination_fn, _, _ = _import_reference()
+    cfg = {"mopo": 0, "latent_reward": 0, "encoder_loss_coef": 1, "domain_loss_coef": 0, "cycle_loss_coef": 0}
+    with contextlib.redirect_stdout(None):
+        m = MOBODYModule(S, A, hidden_dims=256, num_ensemble=7, num_elites=5, device="cpu", config=cfg)
+    p = O.make_dynamics_params(S, A, seed, healthy_state=healthy(env, S, h0), t3_gain=t3_gain)
+    with torch.no_grad():
+        for name in O.dynamics_layer_shapes(S, A):
+            getattr(m, name).weight.copy_(p[name + ".weight"])
+            getattr(m, name).bias.copy_(p[name + ".bias"])
+    dyn = MOBODYEnsembleDynamics(cfg, m, None, None, get_termination_fn(ENV_NAME[env]), penalty_coef=coef)
+    return dyn, p
+
+
+def synth_obs(env, S, B, rng, spread=0.15):
+    return (HEALTHY[env](S)[None, :] + spread * rng.standard_normal((B, S))).astype(np.float32)
+
+
+def gen_step(env, S, A, B, seed, coef, use_trg=True):
+    rng = np.random.default_rng(seed)
+    dyn, _ = build_reference_dynamics(S, A, seed, env, coef)
+    obs = synth_obs(env, S, B, rng); act = rng.uniform(-1, 1, (B, A)).astype(np.float32)
+    eps = rng.standard_normal((7, B, S)).astype(np.float32)
+    slot = rng.integers(0, 5, B)
+    with Inject(lambda c, shp: torch.from_numpy(eps), lambda c, n: slot):
+        nobs, rew, term, info = dyn.step(torch.from_numpy(obs), torch.from_numpy(act), True, use_trg)
+    return dict(env=env, S=S, A=A, seed=seed, coef=np.float32(coef), use_trg=use_trg, obs=obs, act=act, eps=eps,
+                idx=slot.astype(np.int64), next_obs=nobs.numpy(), reward=rew.numpy(), terminal=term,
+                mean=info["samples"].numpy(), raw_reward=info["raw_reward"].numpy(), penalty=info["penalty"].numpy())
+
+
+def gen_termination():
+    _, _, get_termination_fn, _, _ = _import_reference()
+    rng = np.random.default_rng(7)
+    out = {}
+    for env, S in (("halfcheetah", 17), ("hopper", 11), ("walker2d", 17), ("ant", 27)):
+        x = synth_obs(env, S, 256, rng, 0.4)
+        # edge rows: exact thresholds, +-inf, nan, big magnitudes, far-negative dims
+        edges = [(0, 0, 0.7), (1, 0, 0.8), (2, 0, 2.0), (3, 0, 0.2), (4, 0, 1.0), (5, 1, 0.2), (6, 1, -0.2),
+                 (7, 1, 1.0), (8, 1, -1.0), (9, 2, 100.0), (10, 2, -100.0), (11, 3, np.inf), (12, 3, -np.inf),
+                 (13, 4, np.nan), (14, 2, -500.0), (15, 0, np.nextafter(np.float32(0.8), np.float32(1))),
+                 (16, 0, np.nextafter(np.float32(0.7), np.float32(1))), (17, S - 1, 150.0), (18, 0, np.nan)]
+        for r, c, v in edges:
+            x[r, c] = v
+        fn = get_termination_fn(ENV_NAME[env])
+        with np.errstate(invalid="ignore"):
+            out[env + "_x"] = x
+            out[env + "_done"] = fn(x, x[:, :1], x)
+    names = ["halfcheetahvel-x", "halfcheetah-medium-v2", "hopper-medium-v2", "antangle-v0", "ant-medium-v2",
+             "antmaze-umaze-v0", "walker2d-medium-v2", "pendulum", "humanoid-v2", "pen-human-v0", "door-human-v0"]
+    out["dispatch_names"] = np.array(names)
+    out["dispatch_fn"] = np.array([get_termination_fn(n).__name__ for n in names])
+    return out
+
+
+def build_reference_agent(S, A, seed, overrides=None):
+    _, _, _, MOBODY, _ = _import_reference()
+    cfg = dict(state_dim=S, action_dim=A, max_action=1.0, hidden_sizes=256, gamma=0.99, tau=0.005,
+               update_interval=2, actor_lr=3e-4, critic_lr=3e-4, gaussian_noise_std=1.0, weight=2.5,
+               penalty_type="none", penalty_coef=0.1, mopo=0, latent_reward=0, encoder_loss_coef=1,
+               domain_loss_coef=0, cycle_loss_coef=0, advantage=0, q_weighted=1, scale_Q=1, bc_coef=1.0,
+               fake_batch_scale=0.5, src_ratio=1, trg_ratio=1, filter_bad_rollout=1, env_filter=10.0,
+               src_rollout_length=1, trg_rollout_length=1, use_src_sa_to_get_target_next_state=1,
+               rollout_from_src=0, penalize_fake=0)
+    cfg.update(overrides or {})
+    pol = MOBODY(cfg, torch.device("cpu"))
+    ag = O.AgentState(S, A, seed)
+    pol.policy.load_state_dict(ag.policy)
+    pol.q_funcs.load_state_dict(ag.q)
+    pol.target_q_funcs.load_state_dict(ag.q_target)
+    return pol, ag, cfg
+
+
+def gen_rollout(env, S, A, B, T, seed, coef, env_filter, h0, t3_gain):
+    rng = np.random.default_rng(seed)
+    dyn, _ = build_reference_dynamics(S, A, seed, env, coef, h0, t3_gain)
+    pol, _, _ = build_reference_agent(S, A, seed, dict(env_filter=env_filter))
+    pol.dynamics = dyn
+    obs = synth_obs(env, S, B, rng, 0.2)
+    eps_full = rng.standard_normal((T, 7, B, S)).astype(np.float32)   # step t uses the first B_t rows
+    slot_full = rng.integers(0, 5, (T, B))
+    with Inject(lambda c, shp: torch.from_numpy(eps_full[c][:, :shp[1]].copy()), lambda c, n: slot_full[c][:n]), \
+            contextlib.redirect_stdout(None):
+        tr, info = pol.rollout(torch.from_numpy(obs), T, True)
+    d = dict(env=env, S=S, A=A, B=B, T=T, seed=seed, coef=np.float32(coef), env_filter=np.float32(env_filter),
+             h0=np.float64(h0), t3_gain=np.float64(t3_gain),
+             obs=obs, eps=eps_full, idx=slot_full.astype(np.int64), num_transitions=info["num_transitions"],
+             reward_mean=np.float64(info["reward_mean"]))
+    for k, v in tr.items():
+        d["out_" + k] = v.numpy()
+    return d
+
+
+def gen_buffer():
+    _, _, _, _, ref_utils = _import_reference()
+    rng = np.random.default_rng(3)
+    S, A, cap = 5, 2, 50
+    buf = ref_utils.ReplayBuffer(S, A, "cpu", max_size=cap)
+    batches = []
+    for M in (20, 25, 17, 50, 3):       # 20,45, wrap (12 spill), full-size batch, small
+        b = dict(obss=torch.from_numpy(rng.standard_normal((M, S)).astype(np.float32)),
+                 next_obss=torch.from_numpy(rng.standard_normal((M, S)).astype(np.float32)),
+                 actions=torch.from_numpy(rng.standard_normal((M, A)).astype(np.float32)),
+                 rewards=torch.from_numpy(rng.standard_normal((M, 1)).astype(np.float32)),
+                 terminals=torch.from_numpy((rng.random((M, 1)) < 0.3).astype(np.float32)))
+        batches.append(b)
+    out = {"S": S, "A": A, "cap": cap, "n_batches": len(batches)}
+    for i, b in enumerate(batches):
+        buf.add_batch(b)
+        for k, v in b.items():
+            out[f"b{i}_{k}"] = v.numpy()
+        out[f"after{i}_ptr"] = buf.ptr; out[f"after{i}_size"] = buf.size
+        for f in ("state", "action", "next_state", "reward", "not_done"):
+            out[f"after{i}_{f}"] = getattr(buf, f).numpy().copy()
+    ind = rng.integers(0, buf.size, 33)
+    with Inject(ind_list=[ind]):
+        smp = buf.sample(33)
+    out["ind"] = ind.astype(np.int64)
+    for f, v in zip(("state", "action", "next_state", "reward", "not_done"), smp):
+        out["sample_" + f] = v.numpy()
+    return out
+
+
+def gen_train(S, A, B, seed, n_steps=3):
+    """Steady-state MOBODY.train steps (no refresh: total_it starts at 1)."""
+    _, _, _, _, ref_utils = _import_reference()
+    rng = np.random.default_rng(seed)
+    pol, ag, cfg = build_reference_agent(S, A, seed)
+    n_src, n_tar, n_fake = 4000, 600, 900
+
+    def fill(buf, n):
+        buf.state[:n] = torch.from_numpy(rng.standard_normal((n, S)).astype(np.float32))
+        buf.action[:n] = torch.from_numpy(rng.uniform(-1, 1, (n, A)).astype(np.float32))
+        buf.next_state[:n] = torch.from_numpy(rng.standard_normal((n, S)).astype(np.float32))
+        buf.reward[:n] = torch.from_numpy(rng.standard_normal((n, 1)).astype(np.float32))
+        buf.not_done[:n] = torch.from_numpy((rng.random((n, 1)) > 0.1).astype(np.float32))
+        buf.size = n; buf.ptr = n
+    src = ref_utils.ReplayBuffer(S, A, "cpu", max_size=n_src); fill(src, n_src)
+    tar = ref_utils.ReplayBuffer(S, A, "cpu", max_size=n_tar); fill(tar, n_tar)
+    pol.fake_replay_buffer = ref_utils.ReplayBuffer(S, A, "cpu", max_size=n_fake); fill(pol.fake_replay_buffer, n_fake)
+    pol.total_it = 1
+    inds = []
+    for _ in range(n_steps):
+        inds += [rng.integers(0, n_src, B), rng.integers(0, n_tar, B), rng.integers(0, n_fake, int(0.5 * B))]
+    with Inject(ind_list=inds), contextlib.redirect_stdout(None):
+        for _ in range(n_steps):
+            pol.train(src, tar, B, None, None)
+    out = dict(S=S, A=A, B=B, seed=seed, n_steps=n_steps, n_src=n_src, n_tar=n_tar, n_fake=n_fake)
+    for nm, b in (("src", src), ("tar", tar), ("fake", pol.fake_replay_buffer)):
+        for f in ("state", "action", "next_state", "reward", "not_done"):
+            out[f"{nm}_{f}"] = getattr(b, f).numpy()[:b.size].copy()
+    for i, ind in enumerate(inds):
+        out[f"ind{i}"] = ind.astype(np.int64)
+    # post-step parameters: strided subsample + sums (full tensors would be ~1 MB)
+    for grp, sd in (("pi", pol.policy.state_dict()), ("q", pol.q_funcs.state_dict()),
+                    ("qt", pol.target_q_funcs.state_dict())):
+        for k, v in sd.items():
+            flat = v.numpy().reshape(-1)
+            out[f"post_{grp}_{k}_sub"] = flat[::37].copy()
+            out[f"post_{grp}_{k}_sum"] = np.float64(flat.astype(np.float64).sum())
+    return out
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0); np.random.seed(0)
+    torch.set_num_threads(1)
+    steps = [gen_step("walker2d", 17, 6, 64, 11, 5.0), gen_step("halfcheetah", 17, 6, 48, 12, 0.1),
+             gen_step("hopper", 11, 3, 40, 13, 5.0), gen_step("ant", 27, 8, 36, 14, 1.0),
+             gen_step("ant", 29, 8, 33, 15, 0.0), gen_step("walker2d", 17, 6, 32, 16, 5.0, use_trg=False)]
+    for i, d in enumerate(steps):
+        np.savez_compressed(os.path.join(OUT, f"step_{i}_{d['env']}_S{d['S']}A{d['A']}.npz"), **d)
+    np.savez_compressed(os.path.join(OUT, "termination.npz"), **gen_termination())
+    np.savez_compressed(os.path.join(OUT, "rollout_walker2d_T3.npz"), **gen_rollout("walker2d", 17, 6, 96, 3, 21, 5.0, 0.7803, 1.0, 6.0))
+    np.savez_compressed(os.path.join(OUT, "rollout_hopper_T5.npz"), **gen_rollout("hopper", 11, 3, 80, 5, 22, 1.0, 0.3233, 1.1, 3.0))
+    np.savez_compressed(os.path.join(OUT, "buffer.npz"), **gen_buffer())
+    np.savez_compressed(os.path.join(OUT, "train_S17A6_B32.npz"), **gen_train(17, 6, 32, 31))
+    np.savez_compressed(os.path.join(OUT, "train_S11A3_B16.npz"), **gen_train(11, 3, 16, 32, n_steps=2))
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()
