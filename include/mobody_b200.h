@@ -1,0 +1,146 @@
+/* mobody_b200 — C ABI of the B200-native MOBODY rollout / Q-weighted-BC hot path.
+ *
+ * Plain C: pointers and sizes only, no torch types.  Every pointer named "device" is a CUDA device
+ * pointer owned by the caller (PyTorch) and valid for the duration of the call; the library never
+ * allocates or frees.  All work is enqueued on `stream` (a cudaStream_t passed as void*) and is
+ * asynchronous with respect to the host.  Every entry point returns 0 on success and a negative
+ * code on failure; mobody_last_error() then holds a message (thread-local).  No exceptions cross
+ * the boundary.
+ *
+ * The reference (guoyihonggyh/MOBODY...) has no FFI: its hot path is Python calling torch eager
+ * ops.  Each export below names the reference Python interface it replaces; the Python-side
+ * binding (ctypes) lives in mobody_b200/_ffi.py and INTEGRATION.md shows how train_mobody.py
+ * binds to it.
+ */
+#ifndef MOBODY_B200_H
+#define MOBODY_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOBODY_ABI_VERSION 1
+#define MOBODY_E 7            /* ensemble members      (train_mobody.py:795) */
+#define MOBODY_H 256          /* hidden width          (train_mobody.py:794) */
+#define MOBODY_N_DYN_LAYERS 13
+
+/* error codes */
+#define MOBODY_OK 0
+#define MOBODY_ERR_ARG (-1)
+#define MOBODY_ERR_UNSUPPORTED (-2)
+#define MOBODY_ERR_CUDA (-3)
+
+/* termination kinds (algo/mb_utils/terminal_funs.py:10-121; dispatcher :123-149 is host side) */
+#define MOBODY_TERM_NEVER 0
+#define MOBODY_TERM_HALFCHEETAH 1
+#define MOBODY_TERM_HOPPER 2
+#define MOBODY_TERM_WALKER2D 3
+#define MOBODY_TERM_ANT 4
+#define MOBODY_TERM_HUMANOID 5
+#define MOBODY_TERM_PEN 6
+
+/* precision modes of the fused step */
+#define MOBODY_PREC_FP32 0    /* CUDA-core fp32 FMA; bit-faithful op order per row                  */
+#define MOBODY_PREC_BF16X2 1  /* tcgen05 bf16 hi+lo split (3 MMAs), ~1e-5 rel: inside the 1e-4 bound */
+#define MOBODY_PREC_BF16 2    /* tcgen05 single-pass bf16, stated looser bound 5e-3                   */
+
+/* compaction predicates */
+#define MOBODY_KEEP_U8_ZERO 0 /* keep rows with flag == 0      (non-terminal rows, mobody.py:635)   */
+#define MOBODY_KEEP_F32_LE 1  /* keep rows with value <= thr   (rollout filter, mobody.py:649)      */
+#define MOBODY_KEEP_F32_LT 2  /* keep rows with value <  thr   (dataset-step filter, mobody.py:468) */
+#define MOBODY_KEEP_U8_VALID 3 /* keep rows with flag != 0xFF  (rows a rollout step actually wrote) */
+
+/* Live parameters of MOBODYModule (algo/dynamics/mobody_module.py:97-184), device fp32:
+ * w[i] is weight [E,in,out], b[i] is bias [E,1,out], in the order
+ * zs1 zs2 zs3 za_src1 za_src2 za_trg1 za_trg2 transition1 transition2 transition3
+ * reward_model1 reward_model2 reward_model3. */
+typedef struct mobody_dyn_params {
+  const float* w[MOBODY_N_DYN_LAYERS];
+  const float* b[MOBODY_N_DYN_LAYERS];
+} mobody_dyn_params;
+
+/* Live parameters of an MLPNetwork (algo/offline_offline/mobody.py:35-48): nn.Linear layout,
+ * w[i] [out,in], b[i] [out], hidden 256. */
+typedef struct mobody_mlp_params {
+  const float* w[3];
+  const float* b[3];
+} mobody_mlp_params;
+
+/* One imagined transition for a batch of rows.
+ * Replaces MOBODYEnsembleDynamics.step (algo/dynamics/mobody_dynamics.py:193-265) and, when
+ * `policy` is non-NULL, the Policy forward that precedes it in MOBODY.rollout
+ * (algo/offline_offline/mobody.py:612).  Math: SURVEY.md Appendix A.1. */
+typedef struct mobody_step_desc {
+  int precision;             /* MOBODY_PREC_* */
+  int B, S, A;               /* B = row capacity (stride of eps / mean); obs is [B,S]             */
+  const int* n_rows_dev;     /* NULL, or device int: live row count (<= B)                        */
+  const long long* row_ids;  /* NULL, or device int64[B]: global row id per row (Philox counter)  */
+  const float* obs;          /* device [B,S]                                                      */
+  const float* act;          /* device [B,A], or NULL when `policy` computes it                   */
+  const mobody_mlp_params* policy; /* NULL or host struct of device pointers                      */
+  float max_action;
+  const mobody_dyn_params* dyn;    /* host struct of device pointers (fp32 path reads them live)  */
+  const void* dyn_pack;      /* device blob from mobody_dyn_pack (tensor-core precisions), or NULL */
+  const void* policy_pack;   /* device blob from mobody_mlp_pack (tensor-core precisions), or NULL */
+  int use_trg, use_penalty;  /* step(..., use_penalty, use_trg)                                   */
+  float penalty_coef;        /* dynamics._penalty_coef                                            */
+  int term_kind;             /* MOBODY_TERM_*                                                     */
+  const float* eps;          /* NULL -> Philox; else device [E,B,S] N(0,1) (parity mode)          */
+  const int64_t* idx;        /* NULL -> Philox pick among elites; else device int64[B] member ids */
+  const int64_t* elites;     /* device int64[n_elites]  (model.elites)                            */
+  int n_elites;
+  unsigned long long seed;   /* Philox key                                                        */
+  unsigned int step;         /* Philox counter word: rollout step                                 */
+  unsigned long long row0;   /* global row id of obs[0] when row_ids is NULL                      */
+  float* act_out;            /* NULL or device [B,A]                                              */
+  float* next_obs;           /* device [B,S]                                                      */
+  float* reward;             /* device [B]                                                        */
+  float* raw_reward;         /* NULL or device [B]   (info['raw_reward'])                         */
+  float* penalty;            /* device [B]           (info['penalty'])                            */
+  unsigned char* terminal;   /* device [B], 0/1      (terminal_fn(next_obs))                      */
+  float* mean;               /* device [E,B,S]       (info['samples']); always written            */
+} mobody_step_desc;
+
+int mobody_abi_version(void);
+const char* mobody_last_error(void);
+
+int mobody_step(const mobody_step_desc* d, void* stream);
+
+/* Policy.forward / select_action (mobody.py:60-72, 138-144): act_out[B,A] = tanh(MLP(obs))*max_action */
+int mobody_policy_forward(const float* obs, int B, int S, int A, const mobody_mlp_params* policy,
+                          float max_action, float* act_out, void* stream);
+
+/* terminal_fn(obs, act, next_obs) (terminal_funs.py:10-121) on device rows: out[n] in {0,1} */
+int mobody_termination(const float* next_obs, long long n, int S, int term_kind, unsigned char* out, void* stream);
+
+/* ---- replay buffer (algo/utils.py:13-193) on packed rows of row_width(S,A) floats:
+ *      [state(S) | action(A) | next_state(S) | reward | not_done | pad to a multiple of 4] ---- */
+int mobody_row_width(int S, int A);
+/* ReplayBuffer.sample (utils.py:127-148) with indices given: out[i,:] = rows[idx[i],:] */
+int mobody_gather_rows(const float* rows, const int64_t* idx, long long n, int row_width, float* out, void* stream);
+/* np.random.randint(0, size, n) replacement (utils.py:128): Philox4x32-10, key (seed,'indx'), counter (i, draw) */
+int mobody_philox_indices(int64_t* idx, long long n, unsigned long long seed, unsigned int draw,
+                          unsigned int size, void* stream);
+/* convert_D4RL / add_batch packing (utils.py:43-92, 173-193): d is `terminals` when done_is_terminal (stores 1-d) */
+int mobody_pack_rows(const float* s, const float* a, const float* ns, const float* r, const float* d,
+                     long long n, int S, int A, int done_is_terminal, float* out_rows, void* stream);
+/* ReplayBuffer.add_batch ring insert (utils.py:68-92): src row i -> dst row (ptr+i) % cap; n_dev optional device count */
+int mobody_ring_insert(const float* src_rows, long long n_cap, const int* n_dev, int row_width, long long ptr,
+                       long long cap, float* dst_rows, void* stream);
+
+/* ---- stable stream compaction (mobody.py:635-639, 648-651, 468) ----
+ * pos[0..count) = ascending indices i < n with keep(i); count_out is a device int.
+ * scratch: device int[mobody_compact_scratch_ints(n_cap)]. */
+long long mobody_compact_scratch_ints(long long n_cap);
+int mobody_compact(int keep_kind, const unsigned char* flags, const float* vals, float thr, long long n_cap,
+                   const int* n_dev, int* scratch, int* pos, int* count_out, void* stream);
+/* dst[j,0:w] = src[pos[j],0:w] for j < count (count = *m_dev if given else m_cap) */
+int mobody_gather_pos(const float* src, int w, int src_ld, const int* pos, const int* m_dev, long long m_cap,
+                      float* dst, int dst_ld, void* stream);
+int mobody_gather_pos_i64(const long long* src, const int* pos, const int* m_dev, long long m_cap,
+                          long long* dst, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOBODY_B200_H */

@@ -1,0 +1,134 @@
+"""ctypes binding of libmobody_b200.so (include/mobody_b200.h).
+
+The product has no CPU or eager-PyTorch fallback: if the shared library is missing or a CUDA
+device is not available, calls raise immediately.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmobody_b200.so")
+
+N_DYN_LAYERS = 13
+DYN_LAYER_NAMES = ("zs1", "zs2", "zs3", "za_src1", "za_src2", "za_trg1", "za_trg2",
+                   "transition1", "transition2", "transition3",
+                   "reward_model1", "reward_model2", "reward_model3")
+PREC = {"fp32": 0, "bf16x2": 1, "bf16": 2}
+KEEP_U8_ZERO, KEEP_F32_LE, KEEP_F32_LT, KEEP_U8_VALID = 0, 1, 2, 3
+
+
+class DynParams(C.Structure):
+    _fields_ = [("w", C.c_void_p * N_DYN_LAYERS), ("b", C.c_void_p * N_DYN_LAYERS)]
+
+
+class MlpParams(C.Structure):
+    _fields_ = [("w", C.c_void_p * 3), ("b", C.c_void_p * 3)]
+
+
+class StepDesc(C.Structure):
+    _fields_ = [
+        ("precision", C.c_int), ("B", C.c_int), ("S", C.c_int), ("A", C.c_int),
+        ("n_rows_dev", C.c_void_p), ("row_ids", C.c_void_p),
+        ("obs", C.c_void_p), ("act", C.c_void_p),
+        ("policy", C.POINTER(MlpParams)), ("max_action", C.c_float),
+        ("dyn", C.POINTER(DynParams)), ("dyn_pack", C.c_void_p), ("policy_pack", C.c_void_p),
+        ("use_trg", C.c_int), ("use_penalty", C.c_int), ("penalty_coef", C.c_float), ("term_kind", C.c_int),
+        ("eps", C.c_void_p), ("idx", C.c_void_p), ("elites", C.c_void_p), ("n_elites", C.c_int),
+        ("seed", C.c_ulonglong), ("step", C.c_uint), ("row0", C.c_ulonglong),
+        ("act_out", C.c_void_p), ("next_obs", C.c_void_p), ("reward", C.c_void_p), ("raw_reward", C.c_void_p),
+        ("penalty", C.c_void_p), ("terminal", C.c_void_p), ("mean", C.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    """Load the C-ABI library (built in-tree by build.py); raise loudly if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"mobody_b200: {LIB_PATH} is missing. Build it with `python __graft_entry__.py` "
+                "(nvcc, sm_100a). There is no CPU / eager fallback.")
+        L = C.CDLL(LIB_PATH)
+        L.mobody_last_error.restype = C.c_char_p
+        L.mobody_abi_version.restype = C.c_int
+        L.mobody_compact_scratch_ints.restype = C.c_longlong
+        L.mobody_compact_scratch_ints.argtypes = [C.c_longlong]
+        L.mobody_row_width.argtypes = [C.c_int, C.c_int]
+        L.mobody_step.argtypes = [C.POINTER(StepDesc), C.c_void_p]
+        L.mobody_policy_forward.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(MlpParams), C.c_float,
+                                            C.c_void_p, C.c_void_p]
+        L.mobody_termination.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.mobody_gather_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]
+        L.mobody_philox_indices.argtypes = [C.c_void_p, C.c_longlong, C.c_ulonglong, C.c_uint, C.c_uint, C.c_void_p]
+        L.mobody_pack_rows.argtypes = [C.c_void_p] * 5 + [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.mobody_ring_insert.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_longlong, C.c_longlong,
+                                         C.c_void_p, C.c_void_p]
+        L.mobody_compact.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_longlong, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mobody_gather_pos.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p,
+                                        C.c_int, C.c_void_p]
+        L.mobody_gather_pos_i64.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]
+        if L.mobody_abi_version() != 1:
+            raise RuntimeError("mobody_b200: ABI version mismatch between _ffi.py and libmobody_b200.so")
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError(f"mobody_b200 [{rc}]: {lib().mobody_last_error().decode()}")
+
+
+def stream_ptr(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("mobody_b200: expected a CUDA tensor (there is no CPU path)")
+    if not t.is_contiguous():
+        raise RuntimeError("mobody_b200: expected a contiguous tensor")
+    return t.data_ptr()
+
+
+def f32(t, device):
+    """Plumbing: make `t` a contiguous fp32 tensor on `device` (accepts numpy / CPU tensors)."""
+    if not torch.is_tensor(t):
+        t = torch.as_tensor(t)
+    return t.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+
+
+def dyn_params(model):
+    """DynParams of a MOBODYModule-like nn.Module (live parameter storage, no copies)."""
+    d = DynParams()
+    keep = []
+    for i, name in enumerate(DYN_LAYER_NAMES):
+        lay = getattr(model, name)
+        w, b = lay.weight.detach(), lay.bias.detach()
+        if w.dtype != torch.float32 or not w.is_cuda or not w.is_contiguous() or not b.is_contiguous():
+            raise RuntimeError(f"mobody_b200: {name} parameters must be contiguous fp32 CUDA tensors")
+        d.w[i], d.b[i] = w.data_ptr(), b.data_ptr()
+        keep += [w, b]
+    return d, keep
+
+
+def mlp_params(mlp):
+    """MlpParams of an MLPNetwork-like module with .network = Sequential(Linear,ReLU,Linear,ReLU,Linear)."""
+    net = mlp.network
+    m = MlpParams()
+    keep = []
+    for i, li in enumerate((0, 2, 4)):
+        w, b = net[li].weight.detach(), net[li].bias.detach()
+        if w.dtype != torch.float32 or not w.is_cuda or not w.is_contiguous():
+            raise RuntimeError("mobody_b200: MLP parameters must be contiguous fp32 CUDA tensors")
+        m.w[i], m.b[i] = w.data_ptr(), b.data_ptr()
+        keep += [w, b]
+    return m, keep

@@ -1,0 +1,161 @@
+// C-ABI entry points (include/mobody_b200.h).  Argument checking + kernel launches only.
+#include <stdio.h>
+#include <string.h>
+#include "../../include/mobody_b200.h"
+#include "common.cuh"
+
+// launchers implemented in the kernel translation units
+const char* mb_simt_step_launch(const StepArgs& a, const DynPtrs& dp, const MlpPtrs* pol, cudaStream_t st);
+const char* mb_simt_policy_launch(const float* obs, int B, int S, int A, const MlpPtrs& pol, float max_action,
+                                  float* act_out, cudaStream_t st);
+void mb_gather_rows_launch(const float* rows, const int64_t* idx, long long n, int rw, float* out, cudaStream_t st);
+void mb_philox_indices_launch(int64_t* idx, long long n, unsigned long long seed, unsigned int draw, unsigned int size, cudaStream_t st);
+void mb_pack_rows_launch(const float* s, const float* a, const float* ns, const float* r, const float* d, long long n,
+                         int S, int A, int rw, int done_is_terminal, float* out, cudaStream_t st);
+void mb_ring_insert_launch(const float* src, long long n_cap, const int* n_dev, int rw, long long ptr, long long cap,
+                           float* dst, cudaStream_t st);
+void mb_termination_launch(const float* x, long long n, int S, int kind, unsigned char* out, cudaStream_t st);
+void mb_compact_launch(int kind, const unsigned char* flags, const float* vals, float thr, long long n_cap, const int* n_dev,
+                       int* scratch, int* pos, int* count_out, cudaStream_t st);
+void mb_gather_pos_launch(const float* src, int w, int src_ld, const int* pos, const int* m_dev, long long m_cap,
+                          float* dst, int dst_ld, cudaStream_t st);
+void mb_gather_pos_i64_launch(const long long* src, const int* pos, const int* m_dev, long long m_cap, long long* dst, cudaStream_t st);
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+static int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return MOBODY_ERR_CUDA;
+  }
+  return MOBODY_OK;
+}
+
+static_assert(sizeof(mobody_dyn_params) == sizeof(DynPtrs), "DynPtrs layout");
+static_assert(sizeof(mobody_mlp_params) == sizeof(MlpPtrs), "MlpPtrs layout");
+static_assert(MOBODY_N_DYN_LAYERS == L_COUNT, "layer count");
+
+extern "C" {
+
+int mobody_abi_version(void) { return MOBODY_ABI_VERSION; }
+const char* mobody_last_error(void) { return g_err; }
+
+int mobody_step(const mobody_step_desc* d, void* stream) {
+  if (!d) return fail(MOBODY_ERR_ARG, "mobody_step: null descriptor");
+  if (d->B < 0 || d->S < 2 || d->A < 1) return fail(MOBODY_ERR_ARG, "mobody_step: bad B/S/A");
+  if (d->B == 0) return MOBODY_OK;
+  if (!d->obs || !d->dyn || !d->next_obs || !d->reward || !d->penalty || !d->terminal || !d->mean)
+    return fail(MOBODY_ERR_ARG, "mobody_step: obs, dyn, next_obs, reward, penalty, terminal and mean are required");
+  if (!d->act && !d->policy) return fail(MOBODY_ERR_ARG, "mobody_step: need act or policy");
+  if (!d->idx && (!d->elites || d->n_elites < 1)) return fail(MOBODY_ERR_ARG, "mobody_step: need idx or elites");
+  if (d->term_kind < 0 || d->term_kind > MOBODY_TERM_PEN) return fail(MOBODY_ERR_ARG, "mobody_step: bad term_kind");
+  if (d->term_kind == MOBODY_TERM_PEN && d->S < 27) return fail(MOBODY_ERR_ARG, "mobody_step: pen termination needs S >= 27");
+  StepArgs a;
+  memset(&a, 0, sizeof(a));
+  a.obs = d->obs; a.act = d->policy ? nullptr : d->act; a.eps = d->eps; a.idx = d->idx; a.elites = d->elites;
+  a.n_elites = d->n_elites; a.B = d->B; a.S = d->S; a.A = d->A; a.n_rows_dev = d->n_rows_dev; a.row_ids = d->row_ids;
+  a.use_trg = d->use_trg; a.use_penalty = d->use_penalty; a.term_kind = d->term_kind;
+  a.coef = d->penalty_coef; a.max_action = d->max_action; a.seed = d->seed; a.row0 = d->row0; a.step = d->step;
+  a.act_out = d->act_out; a.next_obs = d->next_obs; a.reward = d->reward; a.raw_reward = d->raw_reward;
+  a.penalty = d->penalty; a.terminal = d->terminal; a.mean = d->mean;
+  DynPtrs dp; memcpy(&dp, d->dyn, sizeof(dp));
+  for (int i = 0; i < L_COUNT; ++i)
+    if (!dp.w[i] || !dp.b[i]) return fail(MOBODY_ERR_ARG, "mobody_step: null dynamics parameter pointer");
+  MlpPtrs pol; const MlpPtrs* polp = nullptr;
+  if (d->policy) { memcpy(&pol, d->policy, sizeof(pol)); polp = &pol; }
+  const char* err = nullptr;
+  switch (d->precision) {
+    case MOBODY_PREC_FP32: err = mb_simt_step_launch(a, dp, polp, (cudaStream_t)stream); break;
+    default: return fail(MOBODY_ERR_UNSUPPORTED, "mobody_step: unknown precision mode");
+  }
+  if (err) return fail(MOBODY_ERR_UNSUPPORTED, err);
+  return check_launch("mobody_step");
+}
+
+int mobody_policy_forward(const float* obs, int B, int S, int A, const mobody_mlp_params* policy, float max_action,
+                          float* act_out, void* stream) {
+  if (B < 0 || !policy || (B > 0 && (!obs || !act_out))) return fail(MOBODY_ERR_ARG, "mobody_policy_forward: bad arguments");
+  MlpPtrs pol; memcpy(&pol, policy, sizeof(pol));
+  const char* err = mb_simt_policy_launch(obs, B, S, A, pol, max_action, act_out, (cudaStream_t)stream);
+  if (err) return fail(MOBODY_ERR_UNSUPPORTED, err);
+  return check_launch("mobody_policy_forward");
+}
+
+int mobody_termination(const float* next_obs, long long n, int S, int term_kind, unsigned char* out, void* stream) {
+  if (n < 0 || S < 1 || term_kind < 0 || term_kind > MOBODY_TERM_PEN) return fail(MOBODY_ERR_ARG, "mobody_termination: bad arguments");
+  if (term_kind == MOBODY_TERM_PEN && S < 27) return fail(MOBODY_ERR_ARG, "mobody_termination: pen needs S >= 27");
+  if ((term_kind == MOBODY_TERM_HOPPER || term_kind == MOBODY_TERM_WALKER2D) && S < 2)
+    return fail(MOBODY_ERR_ARG, "mobody_termination: hopper/walker2d need S >= 2");
+  if (n > 0 && (!next_obs || !out)) return fail(MOBODY_ERR_ARG, "mobody_termination: null pointer");
+  mb_termination_launch(next_obs, n, S, term_kind, out, (cudaStream_t)stream);
+  return check_launch("mobody_termination");
+}
+
+int mobody_row_width(int S, int A) { return (2 * S + A + 2 + 3) & ~3; }
+
+int mobody_gather_rows(const float* rows, const int64_t* idx, long long n, int row_width, float* out, void* stream) {
+  if (n < 0 || row_width <= 0 || (row_width & 3)) return fail(MOBODY_ERR_ARG, "mobody_gather_rows: row_width must be a positive multiple of 4");
+  if (n > 0 && (!rows || !idx || !out)) return fail(MOBODY_ERR_ARG, "mobody_gather_rows: null pointer");
+  mb_gather_rows_launch(rows, idx, n, row_width, out, (cudaStream_t)stream);
+  return check_launch("mobody_gather_rows");
+}
+
+int mobody_philox_indices(int64_t* idx, long long n, unsigned long long seed, unsigned int draw, unsigned int size, void* stream) {
+  if (n < 0 || size == 0 || (n > 0 && !idx)) return fail(MOBODY_ERR_ARG, "mobody_philox_indices: bad arguments (size must be > 0)");
+  mb_philox_indices_launch(idx, n, seed, draw, size, (cudaStream_t)stream);
+  return check_launch("mobody_philox_indices");
+}
+
+int mobody_pack_rows(const float* s, const float* a, const float* ns, const float* r, const float* d, long long n,
+                     int S, int A, int done_is_terminal, float* out_rows, void* stream) {
+  if (n < 0 || S < 1 || A < 1) return fail(MOBODY_ERR_ARG, "mobody_pack_rows: bad arguments");
+  if (n > 0 && (!s || !a || !ns || !r || !d || !out_rows)) return fail(MOBODY_ERR_ARG, "mobody_pack_rows: null pointer");
+  mb_pack_rows_launch(s, a, ns, r, d, n, S, A, mobody_row_width(S, A), done_is_terminal, out_rows, (cudaStream_t)stream);
+  return check_launch("mobody_pack_rows");
+}
+
+int mobody_ring_insert(const float* src_rows, long long n_cap, const int* n_dev, int row_width, long long ptr,
+                       long long cap, float* dst_rows, void* stream) {
+  if (n_cap < 0 || cap <= 0 || ptr < 0 || ptr >= cap || (row_width & 3) || row_width <= 0)
+    return fail(MOBODY_ERR_ARG, "mobody_ring_insert: bad arguments");
+  // the reference handles a single wrap only (utils.py:78-92); a longer batch is a shape error there
+  if (n_cap > cap) return fail(MOBODY_ERR_ARG, "mobody_ring_insert: batch larger than buffer capacity");
+  if (n_cap > 0 && (!src_rows || !dst_rows)) return fail(MOBODY_ERR_ARG, "mobody_ring_insert: null pointer");
+  mb_ring_insert_launch(src_rows, n_cap, n_dev, row_width, ptr, cap, dst_rows, (cudaStream_t)stream);
+  return check_launch("mobody_ring_insert");
+}
+
+long long mobody_compact_scratch_ints(long long n_cap) { return (n_cap + 1023) / 1024 + 1; }
+
+int mobody_compact(int keep_kind, const unsigned char* flags, const float* vals, float thr, long long n_cap,
+                   const int* n_dev, int* scratch, int* pos, int* count_out, void* stream) {
+  if (n_cap < 0 || n_cap > 0x7fffffffLL || !count_out) return fail(MOBODY_ERR_ARG, "mobody_compact: bad arguments");
+  const bool u8 = keep_kind == MOBODY_KEEP_U8_ZERO || keep_kind == MOBODY_KEEP_U8_VALID;
+  if (u8 ? (n_cap > 0 && !flags) : (n_cap > 0 && !vals))
+    return fail(MOBODY_ERR_ARG, "mobody_compact: predicate input missing");
+  if (keep_kind < 0 || keep_kind > MOBODY_KEEP_U8_VALID) return fail(MOBODY_ERR_ARG, "mobody_compact: bad keep_kind");
+  if (n_cap > 0 && (!scratch || !pos)) return fail(MOBODY_ERR_ARG, "mobody_compact: null pointer");
+  mb_compact_launch(keep_kind, flags, vals, thr, n_cap, n_dev, scratch, pos, count_out, (cudaStream_t)stream);
+  return check_launch("mobody_compact");
+}
+
+int mobody_gather_pos(const float* src, int w, int src_ld, const int* pos, const int* m_dev, long long m_cap,
+                      float* dst, int dst_ld, void* stream) {
+  if (m_cap < 0 || w < 1 || src_ld < w || dst_ld < w) return fail(MOBODY_ERR_ARG, "mobody_gather_pos: bad arguments");
+  if (m_cap > 0 && (!src || !pos || !dst)) return fail(MOBODY_ERR_ARG, "mobody_gather_pos: null pointer");
+  mb_gather_pos_launch(src, w, src_ld, pos, m_dev, m_cap, dst, dst_ld, (cudaStream_t)stream);
+  return check_launch("mobody_gather_pos");
+}
+
+int mobody_gather_pos_i64(const long long* src, const int* pos, const int* m_dev, long long m_cap, long long* dst, void* stream) {
+  if (m_cap < 0 || (m_cap > 0 && (!src || !pos || !dst))) return fail(MOBODY_ERR_ARG, "mobody_gather_pos_i64: bad arguments");
+  mb_gather_pos_i64_launch(src, pos, m_dev, m_cap, dst, (cudaStream_t)stream);
+  return check_launch("mobody_gather_pos_i64");
+}
+
+}  // extern "C"

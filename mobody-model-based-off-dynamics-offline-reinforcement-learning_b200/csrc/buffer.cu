@@ -1,0 +1,234 @@
+// Replay-buffer and rollout plumbing kernels: HBM-bound byte movers.
+//
+// Device-resident replacement for ReplayBuffer (reference algo/utils.py:13-193) and for the
+// host-side masking/concat in MOBODY.rollout (algo/offline_offline/mobody.py:624-653).
+// A transition is one packed row of RW = roundup4(2S+A+2) floats:
+//     [ state(S) | action(A) | next_state(S) | reward | not_done | 0-pad ]
+// so that sample() is a 128-bit-vectorised row gather and add_batch() a row scatter.
+#include "common.cuh"
+#include "philox.cuh"
+#include "term.cuh"
+
+namespace buf {
+
+constexpr int NT = 256;
+
+// out[i,:] = rows[idx[i],:]   (ReplayBuffer.sample, utils.py:127-148, with idx given)
+__global__ void gather_rows_kernel(const float4* __restrict__ rows, const int64_t* __restrict__ idx,
+                                   long long n, int rw4, float4* __restrict__ out) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = n * rw4;
+  for (; t < total; t += (long long)gridDim.x * blockDim.x) {
+    long long i = t / rw4; int c = (int)(t - i * rw4);
+    out[t] = __ldg(rows + (size_t)idx[i] * rw4 + c);
+  }
+}
+
+// idx[i] = mulhi(philox(i, draw), size)   (np.random.randint(0,size,n), utils.py:128)
+__global__ void philox_indices_kernel(int64_t* __restrict__ idx, long long n, unsigned long long seed,
+                                      unsigned int draw, unsigned int size) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i < n; i += (long long)gridDim.x * blockDim.x) {
+    Philox4 b = philox4x32_10((uint32_t)i, (uint32_t)((unsigned long long)i >> 32), draw, 0u, (uint32_t)seed, MB_STREAM_INDEX);
+    idx[i] = (int64_t)(((uint64_t)b.x * (uint64_t)size) >> 32);
+  }
+}
+
+// Pack separate [n,S],[n,A],[n,S],[n,1],[n,1] arrays into rows; done_is_terminal: store 1 - d (utils.py:73).
+__global__ void pack_rows_kernel(const float* __restrict__ s, const float* __restrict__ a, const float* __restrict__ ns,
+                                 const float* __restrict__ r, const float* __restrict__ d, long long n, int S, int A,
+                                 int rw, int done_is_terminal, float* __restrict__ out) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = n * rw;
+  for (; t < total; t += (long long)gridDim.x * blockDim.x) {
+    long long i = t / rw; int c = (int)(t - i * rw);
+    float v = 0.f;
+    if (c < S) v = s[i * S + c];
+    else if (c < S + A) v = a[i * A + (c - S)];
+    else if (c < 2 * S + A) v = ns[i * S + (c - S - A)];
+    else if (c == 2 * S + A) v = r[i];
+    else if (c == 2 * S + A + 1) v = done_is_terminal ? 1.0f - d[i] : d[i];
+    out[t] = v;
+  }
+}
+
+// Ring insert with the reference's single wrap (utils.py:43-92): src row i -> dst row (ptr + i) % cap.
+// n_dev (nullable) holds the live row count on device (rollout output) so no host sync is needed.
+__global__ void ring_insert_kernel(const float4* __restrict__ src, long long n_cap, const int* __restrict__ n_dev,
+                                   int rw4, long long ptr, long long cap, float4* __restrict__ dst) {
+  long long n = n_dev ? min((long long)*n_dev, n_cap) : n_cap;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = n * rw4;
+  for (; t < total; t += (long long)gridDim.x * blockDim.x) {
+    long long i = t / rw4; int c = (int)(t - i * rw4);
+    long long j = ptr + i; if (j >= cap) j -= cap;
+    dst[(size_t)j * rw4 + c] = src[t];
+  }
+}
+
+// terminal[i] = term_fn(next_obs[i,:])   (terminal_funs.py via mobody_dynamics.py:237)
+__global__ void termination_kernel(const float* __restrict__ x, long long n, int S, int kind, unsigned char* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (unsigned char)mb_terminal(kind, x + i * S, S);
+}
+
+// ---------------- stable stream compaction: keep[i] != 0 rows, original order ----------------
+// pass 1: per-block (1024 rows) counts; pass 2: exclusive scan of block counts (one CTA) + total;
+// pass 3: each block recomputes local ranks and emits pos[rank] = i.  n may live on device.
+constexpr int CB = 1024;
+
+__device__ __forceinline__ int block_exclusive_scan_1024(int flag, int* warp_sums, int& block_total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  unsigned bal = __ballot_sync(0xffffffffu, flag);
+  int local = __popc(bal & ((1u << lane) - 1u));
+  if (lane == 0) warp_sums[w] = __popc(bal);
+  __syncthreads();
+  if (w == 0) {
+    int v = warp_sums[lane], x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    warp_sums[lane] = x - v;
+    if (lane == 31) warp_sums[32] = x;
+  }
+  __syncthreads();
+  block_total = warp_sums[32];
+  return warp_sums[w] + local;
+}
+
+// keep predicate kinds
+enum { KEEP_U8_ZERO = 0,   // keep where flags_u8[i] == 0   (non-terminal rows, mobody.py:635)
+       KEEP_F32_LE = 1,    // keep where vals[i] <= thr     (rollout filter, mobody.py:649)
+       KEEP_F32_LT = 2,    // keep where vals[i] <  thr     (dataset-(s,a) filter, mobody.py:468)
+       KEEP_U8_VALID = 3 };// keep where flags_u8[i] != 0xFF (rows a rollout step actually wrote)
+
+__device__ __forceinline__ int keep_pred(int kind, const unsigned char* f, const float* v, float thr, long long i) {
+  if (kind == KEEP_U8_ZERO) return f[i] == 0;
+  if (kind == KEEP_U8_VALID) return f[i] != 0xFF;
+  if (kind == KEEP_F32_LE) return v[i] <= thr;
+  return v[i] < thr;
+}
+
+__global__ void __launch_bounds__(CB) compact_count_kernel(int kind, const unsigned char* __restrict__ f, const float* __restrict__ v,
+                                                          float thr, long long n_cap, const int* __restrict__ n_dev,
+                                                          int* __restrict__ block_counts) {
+  __shared__ int ws[33];
+  long long n = n_dev ? min((long long)*n_dev, n_cap) : n_cap;
+  long long i = (long long)blockIdx.x * CB + threadIdx.x;
+  int flag = (i < n) ? keep_pred(kind, f, v, thr, i) : 0;
+  int tot; block_exclusive_scan_1024(flag, ws, tot);
+  if (threadIdx.x == 0) block_counts[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(1024) compact_scan_kernel(int* __restrict__ block_counts, int nblocks, int* __restrict__ total_out) {
+  __shared__ int ws[33];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nblocks; base += 1024) {
+    int i = base + threadIdx.x;
+    int v = (i < nblocks) ? block_counts[i] : 0;
+    // inclusive scan of v over the CTA
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) ws[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      int s = ws[lane], t = s;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += y; }
+      ws[lane] = t - s;
+      if (lane == 31) ws[32] = t;
+    }
+    __syncthreads();
+    int excl = carry + ws[w] + x - v;
+    if (i < nblocks) block_counts[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 0) carry += ws[32];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total_out = carry;
+}
+
+__global__ void __launch_bounds__(CB) compact_emit_kernel(int kind, const unsigned char* __restrict__ f, const float* __restrict__ v,
+                                                         float thr, long long n_cap, const int* __restrict__ n_dev,
+                                                         const int* __restrict__ block_offsets, int* __restrict__ pos) {
+  __shared__ int ws[33];
+  long long n = n_dev ? min((long long)*n_dev, n_cap) : n_cap;
+  long long i = (long long)blockIdx.x * CB + threadIdx.x;
+  int flag = (i < n) ? keep_pred(kind, f, v, thr, i) : 0;
+  int tot; int rank = block_exclusive_scan_1024(flag, ws, tot);
+  if (flag) pos[block_offsets[blockIdx.x] + rank] = (int)i;
+}
+
+// dst[j, 0:w] = src[pos[j], 0:w] for j < *m_dev  (row gather by int32 positions; generic width)
+__global__ void gather_pos_kernel(const float* __restrict__ src, int w, int src_ld, const int* __restrict__ pos,
+                                  const int* __restrict__ m_dev, long long m_cap, float* __restrict__ dst, int dst_ld) {
+  long long m = m_dev ? min((long long)*m_dev, m_cap) : m_cap;
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = m * w;
+  for (; t < total; t += (long long)gridDim.x * blockDim.x) {
+    long long j = t / w; int c = (int)(t - j * w);
+    dst[j * dst_ld + c] = src[(size_t)pos[j] * src_ld + c];
+  }
+}
+__global__ void gather_pos_i64_kernel(const long long* __restrict__ src, const int* __restrict__ pos,
+                                      const int* __restrict__ m_dev, long long m_cap, long long* __restrict__ dst) {
+  long long m = m_dev ? min((long long)*m_dev, m_cap) : m_cap;
+  long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; j < m; j += (long long)gridDim.x * blockDim.x) dst[j] = src[pos[j]];
+}
+
+}  // namespace buf
+
+static inline int grid_for(long long work, int nt, int max_blocks = 148 * 16) {
+  long long g = (work + nt - 1) / nt;
+  if (g < 1) g = 1;
+  if (g > max_blocks) g = max_blocks;
+  return (int)g;
+}
+
+// ---- host launchers ----
+void mb_gather_rows_launch(const float* rows, const int64_t* idx, long long n, int rw, float* out, cudaStream_t st) {
+  if (n <= 0) return;
+  buf::gather_rows_kernel<<<grid_for(n * (rw / 4), buf::NT), buf::NT, 0, st>>>(
+      reinterpret_cast<const float4*>(rows), idx, n, rw / 4, reinterpret_cast<float4*>(out));
+}
+void mb_philox_indices_launch(int64_t* idx, long long n, unsigned long long seed, unsigned int draw, unsigned int size, cudaStream_t st) {
+  if (n <= 0) return;
+  buf::philox_indices_kernel<<<grid_for(n, buf::NT), buf::NT, 0, st>>>(idx, n, seed, draw, size);
+}
+void mb_pack_rows_launch(const float* s, const float* a, const float* ns, const float* r, const float* d, long long n,
+                         int S, int A, int rw, int done_is_terminal, float* out, cudaStream_t st) {
+  if (n <= 0) return;
+  buf::pack_rows_kernel<<<grid_for(n * rw, buf::NT), buf::NT, 0, st>>>(s, a, ns, r, d, n, S, A, rw, done_is_terminal, out);
+}
+void mb_ring_insert_launch(const float* src, long long n_cap, const int* n_dev, int rw, long long ptr, long long cap,
+                           float* dst, cudaStream_t st) {
+  if (n_cap <= 0) return;
+  buf::ring_insert_kernel<<<grid_for(n_cap * (rw / 4), buf::NT), buf::NT, 0, st>>>(
+      reinterpret_cast<const float4*>(src), n_cap, n_dev, rw / 4, ptr, cap, reinterpret_cast<float4*>(dst));
+}
+void mb_termination_launch(const float* x, long long n, int S, int kind, unsigned char* out, cudaStream_t st) {
+  if (n <= 0) return;
+  buf::termination_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, n, S, kind, out);
+}
+// scratch: int[ceil(n_cap/1024) + 1]
+void mb_compact_launch(int kind, const unsigned char* flags, const float* vals, float thr, long long n_cap, const int* n_dev,
+                       int* scratch, int* pos, int* count_out, cudaStream_t st) {
+  if (n_cap <= 0) { cudaMemsetAsync(count_out, 0, sizeof(int), st); return; }
+  int nb = (int)((n_cap + buf::CB - 1) / buf::CB);
+  buf::compact_count_kernel<<<nb, buf::CB, 0, st>>>(kind, flags, vals, thr, n_cap, n_dev, scratch);
+  buf::compact_scan_kernel<<<1, 1024, 0, st>>>(scratch, nb, count_out);
+  buf::compact_emit_kernel<<<nb, buf::CB, 0, st>>>(kind, flags, vals, thr, n_cap, n_dev, scratch, pos);
+}
+void mb_gather_pos_launch(const float* src, int w, int src_ld, const int* pos, const int* m_dev, long long m_cap,
+                          float* dst, int dst_ld, cudaStream_t st) {
+  if (m_cap <= 0) return;
+  buf::gather_pos_kernel<<<grid_for(m_cap * w, buf::NT), buf::NT, 0, st>>>(src, w, src_ld, pos, m_dev, m_cap, dst, dst_ld);
+}
+void mb_gather_pos_i64_launch(const long long* src, const int* pos, const int* m_dev, long long m_cap, long long* dst, cudaStream_t st) {
+  if (m_cap <= 0) return;
+  buf::gather_pos_i64_kernel<<<grid_for(m_cap, buf::NT), buf::NT, 0, st>>>(src, pos, m_dev, m_cap, dst);
+}

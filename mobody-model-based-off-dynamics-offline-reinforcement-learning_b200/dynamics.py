@@ -1,0 +1,129 @@
+"""MOBODYEnsembleDynamics.step as one fused CUDA launch.
+
+Mirror of algo/dynamics/mobody_dynamics.py:83-265 (identity StandardScaler + ``step``).  The model
+fitting half of that class (``train``/``learn``/``validate``, :300-1270) is out of scope
+(SURVEY.md §2 #3): this class drops in for the *rollout* use of the dynamics object.
+"""
+import ctypes as C
+from typing import Callable, Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _ffi
+from .terminal_funs import TerminationFn
+
+
+class StandardScaler(object):
+    """Identity scaler: the reference's transform/inverse_transform return their input
+    (mobody_dynamics.py:111-131) and load_scaler ends with mu=0, std=1 (:153-154)."""
+
+    def __init__(self, mu=None, std=None):
+        self.mu, self.std = mu, std
+
+    def transform(self, data):
+        return data
+
+    def inverse_transform(self, data):
+        return data
+
+    def transform_tensor(self, data):
+        return data
+
+
+class StepWorkspace:
+    """Output tensors of one step; torch owns the memory, the C side only fills it."""
+
+    def __init__(self, B, S, A, device, want_act=False):
+        f = dict(dtype=torch.float32, device=device)
+        self.next_obs = torch.empty(B, S, **f)
+        self.reward = torch.empty(B, 1, **f)
+        self.raw_reward = torch.empty(B, 1, **f)
+        self.penalty = torch.empty(B, 1, **f)
+        self.terminal = torch.empty(B, dtype=torch.uint8, device=device)
+        self.mean = torch.empty(7, B, S, **f)
+        self.act = torch.empty(B, A, **f) if want_act else None
+
+
+class MOBODYEnsembleDynamics(object):
+    def __init__(self, config, model, optim=None, scaler=None,
+                 terminal_fn: Optional[Callable] = None, penalty_coef: float = 0.0,
+                 uncertainty_mode: str = "pairwise-diff", precision: Optional[str] = None, seed: int = 0) -> None:
+        if uncertainty_mode != "pairwise-diff":
+            # 'aleatoric' / 'ensemble_std' (mobody_dynamics.py:241-252) are unreachable from train_mobody.py
+            raise NotImplementedError("mobody_b200 implements the default 'pairwise-diff' uncertainty mode")
+        if not isinstance(terminal_fn, TerminationFn):
+            raise TypeError("terminal_fn must come from mobody_b200.get_termination_fn (device predicate)")
+        self.model, self.optim = model, optim
+        self.terminal_fn = terminal_fn
+        self._penalty_coef = penalty_coef
+        self._uncertainty_mode = uncertainty_mode
+        self.obs_scaler, self.action_scaler = StandardScaler(), StandardScaler()
+        self.config = config
+        self.encoder_loss_coef = config.get("encoder_loss_coef", 1) if config else 1
+        self.domain_loss_coef = config.get("domain_loss_coef", 0) if config else 0
+        self.cycle_loss_coef = config.get("cycle_loss_coef", 0) if config else 0
+        self.encode_trg_diff = getattr(model, "encode_trg_diff", 0)
+        self.precision = precision or (config or {}).get("b200_precision", "fp32")
+        self.seed = int(seed)
+        self._draw = 0        # Philox step counter for stand-alone step() calls in production mode
+
+    # ------------------------------------------------------------------
+    def launch_step(self, obs, act, ws: StepWorkspace, *, policy=None, max_action=1.0, use_penalty=True,
+                    use_trg=True, eps=None, idx=None, n_rows_dev=None, row_ids=None, step=0, row0=0):
+        """Enqueue the fused step on the current stream; no host synchronisation.
+        obs [B,S] (B = capacity), act [B,A] or None with ``policy`` (an MLPNetwork-like module)."""
+        dev = obs.device
+        B, S = obs.shape
+        A = self.model.action_dim
+        d = _ffi.StepDesc()
+        d.precision = _ffi.PREC[self.precision]
+        d.B, d.S, d.A = B, S, A
+        d.n_rows_dev, d.row_ids = _ffi.ptr(n_rows_dev), _ffi.ptr(row_ids)
+        d.obs, d.act = _ffi.ptr(obs), _ffi.ptr(act)
+        keep = []
+        if policy is not None:
+            mp, k = _ffi.mlp_params(policy); keep += k
+            d.policy = C.pointer(mp)
+        d.max_action = float(max_action)
+        dp, k = _ffi.dyn_params(self.model); keep += k
+        d.dyn = C.pointer(dp)
+        d.use_trg, d.use_penalty = int(bool(use_trg)), int(bool(use_penalty))
+        d.penalty_coef = float(self._penalty_coef)
+        d.term_kind = self.terminal_fn.kind
+        elites = self.model.elites.data
+        if elites.dtype != torch.int64 or not elites.is_cuda:
+            elites = elites.to(device=dev, dtype=torch.int64)
+        keep.append(elites)
+        d.eps, d.idx, d.elites, d.n_elites = _ffi.ptr(eps), _ffi.ptr(idx), _ffi.ptr(elites), elites.numel()
+        d.seed, d.step, d.row0 = self.seed, int(step), int(row0)
+        d.act_out = _ffi.ptr(ws.act)
+        d.next_obs, d.reward, d.raw_reward = _ffi.ptr(ws.next_obs), _ffi.ptr(ws.reward), _ffi.ptr(ws.raw_reward)
+        d.penalty, d.terminal, d.mean = _ffi.ptr(ws.penalty), _ffi.ptr(ws.terminal), _ffi.ptr(ws.mean)
+        _ffi.check(_ffi.lib().mobody_step(C.byref(d), _ffi.stream_ptr(dev)))
+        return ws
+
+    @torch.no_grad()
+    def step(self, obs, action, use_penalty=True, use_trg=True, *, eps=None, idx=None
+             ) -> Tuple[torch.Tensor, torch.Tensor, np.ndarray, Dict]:
+        """Reference signature (mobody_dynamics.py:193-265):
+        -> (next_obs Tensor[B,S], reward Tensor[B,1], terminal np.bool_[B,1] on host, info).
+        ``eps`` [7,B,S] / ``idx`` [B] inject the noise and member indices the reference would draw
+        from torch.normal / np.random.choice; when omitted they come from Philox (seed, draw)."""
+        self.model.inference()
+        dev = self.model.elites.device
+        obs = _ffi.f32(obs, dev)
+        action = _ffi.f32(action, dev).reshape(obs.shape[0], -1)
+        B, S = obs.shape
+        if eps is not None:
+            eps = _ffi.f32(eps, dev)
+            assert tuple(eps.shape) == (7, B, S)
+        if idx is not None:
+            idx = torch.as_tensor(np.asarray(idx) if not torch.is_tensor(idx) else idx).to(device=dev, dtype=torch.int64).contiguous()
+        ws = StepWorkspace(B, S, action.shape[1], dev)
+        if B > 0:
+            self.launch_step(obs, action, ws, use_penalty=use_penalty, use_trg=use_trg, eps=eps, idx=idx, step=self._draw)
+        self._draw += 1
+        info = {"samples": ws.mean, "raw_reward": ws.raw_reward, "penalty": ws.penalty}
+        terminal = ws.terminal.bool()[:, None].cpu().numpy()      # the one D2H the reference API demands (:237)
+        return ws.next_obs, ws.reward, terminal, info

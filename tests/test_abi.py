@@ -1,0 +1,78 @@
+"""CPU-side checks of the C-ABI boundary: the library builds, loads and exports every declared symbol."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "mobody_b200.h")
+
+
+@pytest.fixture(scope="module")
+def libpath():
+    import __graft_entry__ as g
+    g.build()
+    from mobody_b200 import _ffi
+    assert os.path.exists(_ffi.LIB_PATH)
+    return _ffi.LIB_PATH
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"^\s*(?:const\s+)?(?:int|long long|char\s*\*|const char\s*\*)\s+(mobody_\w+)\s*\(", src, flags=re.M)
+    assert len(names) >= 12
+    return names
+
+
+def test_every_declared_symbol_is_exported(libpath):
+    lib = ctypes.CDLL(libpath)
+    for name in declared_functions():
+        assert hasattr(lib, name), f"{name} declared in include/mobody_b200.h but not exported"
+
+
+def test_abi_version_and_pure_host_calls(libpath):
+    from mobody_b200 import _ffi
+    L = _ffi.lib()
+    assert L.mobody_abi_version() == 1
+    assert L.mobody_row_width(17, 6) == 44 and L.mobody_row_width(11, 3) == 28 and L.mobody_row_width(27, 8) == 64
+    assert L.mobody_compact_scratch_ints(1) == 2 and L.mobody_compact_scratch_ints(1025) == 3
+
+
+def test_argument_errors_are_reported_not_raised_across_abi(libpath):
+    from mobody_b200 import _ffi
+    L = _ffi.lib()
+    assert L.mobody_step(None, None) == -1 and b"null descriptor" in L.mobody_last_error()
+    assert L.mobody_gather_rows(None, None, 4, 7, None, None) == -1     # row width not a multiple of 4
+    assert L.mobody_ring_insert(None, 10, None, 44, 0, 5, None, None) == -1   # batch larger than capacity
+    assert L.mobody_termination(None, 1, 17, 99, None, None) == -1
+    with pytest.raises(RuntimeError, match="mobody_b200"):
+        _ffi.check(-1)
+
+
+def test_struct_mirrors_match_header_sizes(libpath):
+    from mobody_b200 import _ffi
+    assert ctypes.sizeof(_ffi.DynParams) == 2 * 13 * 8 and ctypes.sizeof(_ffi.MlpParams) == 6 * 8
+
+
+def test_no_cpu_path():
+    """Product classes refuse CPU devices instead of silently falling back."""
+    import torch
+    import mobody_b200 as mb
+    with pytest.raises(RuntimeError):
+        mb.ReplayBuffer(3, 2, "cpu", max_size=8)
+    with pytest.raises(RuntimeError):
+        mb._ffi.ptr(torch.zeros(2))
+
+
+def test_termination_dispatch_order():
+    import mobody_b200 as mb
+    kinds = {n: mb.get_termination_fn(n).kind for n in
+             ["halfcheetahvel-x", "halfcheetah-medium-v2", "hopper-medium-v2", "antangle", "antmaze-umaze-v0",
+              "walker2d-medium-v2", "pendulum", "humanoid", "pen-human-v0", "door-human"]}
+    assert kinds == {"halfcheetahvel-x": 0, "halfcheetah-medium-v2": 1, "hopper-medium-v2": 2, "antangle": 4,
+                     "antmaze-umaze-v0": 4, "walker2d-medium-v2": 3, "pendulum": 0, "humanoid": 5, "pen-human-v0": 6,
+                     "door-human": 0}
+    with pytest.raises(TypeError):
+        mb.get_termination_fn("unknown")

@@ -1,0 +1,107 @@
+"""GPU parity of the byte/index kernels: bit-exact against reference-generated goldens and the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def test_termination_bit_exact(golden_dir):
+    import mobody_b200 as mb
+    g = np.load(os.path.join(golden_dir, "termination.npz"))
+    task = {"walker2d": "walker2d-medium-v2", "hopper": "hopper-medium-v2", "halfcheetah": "halfcheetah-medium-v2", "ant": "ant-medium-v2"}
+    for env in task:
+        fn = mb.get_termination_fn(task[env])
+        x = g[env + "_x"]
+        done = fn(x, x[:, :1], x)                              # numpy in -> numpy bool [B,1], like the reference
+        assert done.dtype == np.bool_ and np.array_equal(done, g[env + "_done"]), env
+        dev = fn(torch.from_numpy(x).cuda(), torch.from_numpy(x[:, :1]).cuda(), torch.from_numpy(x).cuda())
+        assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), g[env + "_done"])
+    never = mb.get_termination_fn("pendulum")
+    assert not never(np.zeros((5, 3), np.float32), np.zeros((5, 1), np.float32), np.full((5, 3), np.nan, np.float32)).any()
+
+
+def test_ring_buffer_matches_reference(golden_dir):
+    import mobody_b200 as mb
+    g = np.load(os.path.join(golden_dir, "buffer.npz"))
+    S, A, cap = int(g["S"]), int(g["A"]), int(g["cap"])
+    buf = mb.ReplayBuffer(S, A, "cuda", max_size=cap)
+    buf.add_batch(None)
+    for i in range(int(g["n_batches"])):
+        buf.add_batch({k: torch.from_numpy(g[f"b{i}_{k}"]) for k in ("obss", "next_obss", "actions", "rewards", "terminals")})
+        assert (buf.ptr, buf.size) == (int(g[f"after{i}_ptr"]), int(g[f"after{i}_size"]))
+        for f in ("state", "action", "next_state", "reward", "not_done"):
+            assert np.array_equal(getattr(buf, f).cpu().numpy(), g[f"after{i}_{f}"]), (i, f)
+    smp = buf.sample(33, ind=g["ind"])
+    for f, v in zip(("state", "action", "next_state", "reward", "not_done"), smp):
+        assert v.is_cuda and np.array_equal(v.cpu().numpy(), g["sample_" + f])
+    with pytest.raises(ValueError):
+        buf.add_batch({k: torch.zeros(cap + 1, w) for k, w in (("obss", S), ("next_obss", S), ("actions", A), ("rewards", 1), ("terminals", 1))})
+    # direct field pokes used by train_mobody.py:551 and mobody.py:381
+    before = buf.reward.clone()
+    buf.reward -= 1.0
+    assert torch.equal(buf.reward, before - 1.0)
+    buf.reward = torch.zeros(cap, 1)
+    assert float(buf.reward.abs().sum()) == 0.0
+    st_all = buf.sample_all(False)
+    assert not st_all[0].is_cuda and st_all[0].shape == (buf.size, S)
+
+
+def test_philox_indices_bit_exact_and_empty():
+    import mobody_b200 as mb
+    from oracle.philox import buffer_indices
+    buf = mb.ReplayBuffer(3, 2, "cuda", max_size=5000, seed=99)
+    with pytest.raises(ValueError):
+        buf.sample(4)
+    buf.size = 4321
+    for draw in range(3):
+        got = buf.draw_indices(1000).cpu().numpy()
+        assert np.array_equal(got, buffer_indices(99, draw, 1000, 4321))
+    assert buf.draw_indices(0).numel() == 0
+
+
+def test_convert_d4rl_and_sample_shapes():
+    import mobody_b200 as mb
+    rng = np.random.default_rng(0)
+    n, S, A = 777, 17, 6
+    ds = dict(observations=rng.standard_normal((n, S)).astype(np.float32), actions=rng.standard_normal((n, A)).astype(np.float32),
+              next_observations=rng.standard_normal((n, S)).astype(np.float32), rewards=rng.standard_normal(n).astype(np.float32),
+              terminals=(rng.random(n) < 0.1))
+    buf = mb.ReplayBuffer(S, A, "cuda")
+    buf.convert_D4RL(ds)
+    assert buf.size == n
+    ind = rng.integers(0, n, 50)
+    s, a, ns, r, nd = buf.sample(50, ind=ind)
+    assert np.array_equal(s.cpu().numpy(), ds["observations"][ind]) and np.array_equal(a.cpu().numpy(), ds["actions"][ind])
+    assert np.array_equal(ns.cpu().numpy(), ds["next_observations"][ind]) and np.array_equal(r.cpu().numpy()[:, 0], ds["rewards"][ind])
+    assert np.array_equal(nd.cpu().numpy()[:, 0], 1.0 - ds["terminals"][ind].astype(np.float32))
+    assert r.shape == (50, 1) and nd.shape == (50, 1)
+
+
+@pytest.mark.parametrize("n", [0, 1, 1023, 1024, 1025, 70000, 2_500_000])
+def test_compaction_stable_and_exact(n):
+    from mobody_b200 import _ffi
+    L, st = _ffi.lib(), _ffi.stream_ptr()
+    rng = np.random.default_rng(n)
+    flags = (rng.random(n) < 0.3).astype(np.uint8)
+    vals = rng.standard_normal(n).astype(np.float32)
+    if n > 10:
+        vals[3] = np.nan; vals[5] = 0.25
+    f, v = torch.from_numpy(flags).cuda(), torch.from_numpy(vals).cuda()
+    pos = torch.empty(max(n, 1), dtype=torch.int32, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+    scr = torch.empty(int(L.mobody_compact_scratch_ints(n)), dtype=torch.int32, device="cuda")
+    with np.errstate(invalid="ignore"):
+        cases = [(_ffi.KEEP_U8_ZERO, np.flatnonzero(flags == 0)), (_ffi.KEEP_F32_LE, np.flatnonzero(vals <= 0.25)),
+                 (_ffi.KEEP_F32_LT, np.flatnonzero(vals < 0.25)), (_ffi.KEEP_U8_VALID, np.flatnonzero(flags != 255))]
+    for kind, want in cases:
+        _ffi.check(L.mobody_compact(kind, _ffi.ptr(f), _ffi.ptr(v), 0.25, n, None, _ffi.ptr(scr), _ffi.ptr(pos), _ffi.ptr(cnt), st))
+        c = int(cnt.item())
+        assert c == len(want) and np.array_equal(pos[:c].cpu().numpy(), want)
+    if n >= 1025:   # live count on the device bounds the scan
+        live = torch.tensor([1000], dtype=torch.int32, device="cuda")
+        _ffi.check(L.mobody_compact(_ffi.KEEP_U8_ZERO, _ffi.ptr(f), None, 0.0, n, _ffi.ptr(live), _ffi.ptr(scr), _ffi.ptr(pos), _ffi.ptr(cnt), st))
+        want = np.flatnonzero(flags[:1000] == 0)
+        assert int(cnt.item()) == len(want) and np.array_equal(pos[:len(want)].cpu().numpy(), want)
