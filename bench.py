@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""Benchmark of the MOBODY model-rollout hot path (BASELINE.json metric: model-rollout transitions/sec).
+
+Workload at N=1: BASELINE.json configs[1] — halfcheetah-gravity shaped (obs 17 / act 6), 100 000 start
+states, rollout_length=1, 7-member ensemble, policy forward fused in.  At N>1 every rank rolls its own
+100 000 start states (weak scaling) and the synthetic transitions are all-gathered over NCCL.
+
+One "step" = one full rollout of the start states (policy + 7-member dynamics + reward ensemble +
+penalty + termination + penalty filter), exactly what MOBODY.rollout does per refresh.
+
+  value   : transitions/s with the start states already in HBM (CUDA events around each rollout,
+            L2 flushed between iterations, max over ranks)
+  e2e     : the same through the public API MOBODY.rollout() with HOST buffers: pinned-host -> device
+            copy of the start states and device -> host copy of the returned transition dict inside
+            the timed region
+  roofline: tensor-core roofline of the fused step kernel (algorithmic FLOP / measured kernel time)
+  cpu_baseline: the oracle (CPU restatement of the reference, torch CPU) timed on this box's host cores
+
+`--impl reference` times the reference's CPU path (oracle port; the reference is Python and does not
+travel to the GPU box) with all host threads on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+S, A, B_PER_GPU, T = 17, 6, 100_000, 1
+ENV, TASK, COEF, ENV_FILTER = "halfcheetah", "halfcheetah-medium-v2", 5.0, 10.0
+METRIC, UNIT = "model-rollout transitions/sec", "transitions/s"
+
+
+def flop_per_transition(S, A, H=256, E=7):
+    """2*[E*(dyn+rew)+policy] with dead columns counted (not credited as skipped)."""
+    dyn = S * H + H * H + 32 * H + (16 + A) * 32 + 32 * 32 + 16 * H + H * H + H * S
+    rew = (2 * S + A) * H + H * H + 2 * H
+    pol = S * H + H * H + H * A
+    return 2 * (E * (dyn + rew) + pol)
+
+
+def synth_obs(n, seed):
+    rng = np.random.default_rng(seed)
+    return (0.3 * rng.standard_normal((n, S))).astype(np.float32)   # halfcheetah healthy set: |x| < 100
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p, "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self._halt = gpu, [], threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._halt.wait(0.1)
+
+    def stop(self):
+        self._halt.set(); self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def cpu_rollout_rate(n_rows, threads, repeats=1):
+    """Oracle (CPU restatement of MOBODY.rollout, proven equal to the reference) on host cores."""
+    from oracle import mobody_oracle as M
+    torch.set_num_threads(threads)
+    p = M.make_dynamics_params(S, A, 1)
+    ag = M.AgentState(S, A, 1)
+    obs = torch.from_numpy(synth_obs(n_rows, 0))
+    g = torch.Generator().manual_seed(0)
+    elites = p["elites"].numpy()
+    best = None
+    for _ in range(repeats + 1):            # first pass is warm-up
+        t0 = time.perf_counter()
+        eps = [lambda n: torch.randn(7, n, S, generator=g)]
+        idx = [lambda n: elites[np.random.randint(0, len(elites), n)]]
+        _, info = M.rollout(p, ag.policy, 1.0, obs, T, eps, idx, M.termination_kind(TASK), COEF, ENV_FILTER, True)
+        dt = time.perf_counter() - t0
+        best = dt if best is None or _ == 0 else min(best, dt)
+        if _ == 0:
+            best = None
+    return info["num_transitions"] / best, best
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n = 20_000                               # bounded sample: ~1-2 s per step on 8+ cores
+    rate, dt = cpu_rollout_rate(n, cores, repeats=max(args.steps, 1))   # includes one warm-up pass
+    val = rate
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"halfcheetah-gravity S{S}/A{A} rollout_length={T}, {B_PER_GPU} start states (BASELINE configs[1])",
+                       "sample": f"{n} of {B_PER_GPU} start states per step"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"oracle.rollout on {n} start states, best of {max(args.steps, 1)} after 1 warm-up, torch threads={cores}"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("MOBODY_PRECISION", "auto"))
+    ap.add_argument("--rows", type=int, default=B_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+    W = max(args.warmup, 3)
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    import __graft_entry__ as G
+    if rank == 0 or not os.path.exists(os.path.join(G.PKG, "libmobody_b200.so")):
+        G.build()
+    if dist is not None:
+        dist.barrier()
+    import mobody_b200 as mb
+    from mobody_b200 import _ffi
+    from helpers import cuda_agent, cuda_dynamics
+    enabled = list(getattr(_ffi, "ENABLED_PRECISIONS", ("fp32",)))
+    prec = args.precision if args.precision != "auto" else ("bf16x2" if "bf16x2" in enabled else "fp32")
+    dyn, _ = cuda_dynamics(S, A, 1, ENV, COEF, precision=prec)
+    ag, _ = cuda_agent(S, A, 1, env_filter=ENV_FILTER)
+    ag.dynamics = dyn
+    Bn = args.rows
+    obs_host = torch.from_numpy(synth_obs(Bn, 100 + rank)).pin_memory()
+    obs_dev = obs_host.to(dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+
+    def one_rollout_device():
+        out, info = ag.rollout_device(obs_dev, T, row0=rank * Bn)
+        return out, info
+
+    gather_buf = None
+
+    def exchange(out, info):
+        """NCCL all-gather of the packed synthetic transitions (padded slabs + counts)."""
+        nonlocal gather_buf
+        if dist is None:
+            return
+        w = 2 * S + A + 3
+        slab = torch.zeros(Bn * T, w, dtype=torch.float32, device=dev)
+        m = out["obss"].shape[0]
+        slab[:m] = torch.cat([out["obss"], out["actions"], out["next_obss"], out["rewards"], out["terminals"], out["penalty"]], 1)
+        if gather_buf is None:
+            gather_buf = torch.empty(world * Bn * T, w, dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(gather_buf, slab)
+
+    # ---- device-resident timing ----
+    for _ in range(W):
+        o, i = one_rollout_device(); exchange(o, i)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    sampler = ClockSampler(local_rank); sampler.start()
+    evs, n_trans = [], 0
+    torch.cuda.synchronize()
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.zero_()                                     # L2 flush, outside the timed event pair
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        o, i = one_rollout_device(); exchange(o, i)
+        e1.record()
+        evs.append((e0, e1)); n_trans += i["num_transitions"]
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    wall = time.perf_counter() - wall0
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+
+    # ---- step-kernel-only timing for the roofline (same stream, events directly around the launch) ----
+    from mobody_b200.dynamics import StepWorkspace
+    ws = StepWorkspace(Bn, S, A, dev, want_act=True)
+    kt = []
+    for it in range(W + args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dyn.launch_step(obs_dev, None, ws, policy=ag.policy.network, max_action=1.0, step=it, row0=rank * Bn)
+        e1.record()
+        kt.append((e0, e1))
+    torch.cuda.synchronize()
+    k_ms = float(np.mean([a.elapsed_time(b) for a, b in kt[W:]]))
+
+    # ---- end-to-end through the public API with host buffers ----
+    def one_rollout_e2e():
+        x = obs_host.to(dev, non_blocking=True)
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):
+            tr, info = ag.rollout(x, T)
+        return tr, info
+    for _ in range(2):
+        one_rollout_e2e()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter(); e2e_trans = 0; d2h = 0
+    for _ in range(args.steps):
+        tr, info = one_rollout_e2e(); e2e_trans += info["num_transitions"]
+        d2h = sum(v.numel() * v.element_size() for v in tr.values())
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+
+    t = torch.tensor([dev_ms, e2e_s, float(n_trans), float(e2e_trans), k_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = t.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dev_ms, e2e_s, k_ms = float(mx[0]), float(mx[1]), float(mx[4])
+        n_trans, e2e_trans = float(sm[2]), float(sm[3])
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    pk, pk_src = peaks()
+    flop = flop_per_transition(S, A)
+    split = {"fp32": 1, "bf16": 1, "bf16x2": 3}[prec]
+    ach = flop * Bn / (k_ms * 1e-3) / 1e12
+    peak = pk["bf16_tflops"]                               # kernel timed alone -> burst figure
+    value = n_trans / (dev_ms * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"fp32": "f32", "bf16x2": "bf16x2 (hi+lo split, fp32-parity)", "bf16": "bf16"}[prec], "data": "synthetic",
+        "config": {"workload": f"halfcheetah-gravity S{S}/A{A} rollout_length={T}, {Bn} start states per GPU (BASELINE configs[1])",
+                   "ensemble": 7, "hidden": 256, "precision": prec, "l2": "flushed between timed iterations (256 MiB memset)",
+                   "parallelism": f"dp{world} (start states sharded; NCCL all-gather of transitions)" if world > 1 else "single GPU"},
+        "e2e": {"value": e2e_trans / e2e_s, "unit": UNIT, "h2d_bytes_per_step": Bn * S * 4, "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": args.steps * (T * 1 + (T - 1) * 5 + 3 + 6),
+        "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                     "traffic": None, "kernel": "fused rollout step", "kernel_ms": k_ms, "peak_source": pk_src + " bf16 burst",
+                     "mma_passes_per_gemm": split, "frac_of_mma_issued": ach * split / peak,
+                     "flop_per_transition": flop},
+        "clocks": clocks, "wall_s": wall,
+    }
+    if not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n = 20_000
+        rate, dt = cpu_rollout_rate(n, cores, repeats=2)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"oracle.rollout (CPU restatement of MOBODY.rollout) on {n} of {Bn} start states, "
+                                          f"best of 2 after 1 warm-up, torch threads={cores}"}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

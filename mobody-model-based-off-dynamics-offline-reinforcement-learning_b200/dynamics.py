@@ -113,7 +113,7 @@ class MOBODYEnsembleDynamics(object):
         self.model.inference()
         dev = self.model.elites.device
         obs = _ffi.f32(obs, dev)
-        action = _ffi.f32(action, dev).reshape(obs.shape[0], -1)
+        action = _ffi.f32(action, dev).reshape(obs.shape[0], self.model.action_dim)
         B, S = obs.shape
         if eps is not None:
             eps = _ffi.f32(eps, dev)
