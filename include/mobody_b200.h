@@ -140,6 +140,10 @@ int mobody_gather_pos(const float* src, int w, int src_ld, const int* pos, const
 int mobody_gather_pos_i64(const long long* src, const int* pos, const int* m_dev, long long m_cap,
                           long long* dst, void* stream);
 
+/* Test hook: D[128,N] = A[128,K] * B[N,K]^T on one CTA through the same tcgen05 operand layout,
+ * descriptors and TMEM read-back as the rollout kernel (nsplit 1 = bf16, 2 = bf16 hi+lo split). */
+int mobody_selftest_umma(const float* A, const float* B, int K, int N, int nsplit, float* D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

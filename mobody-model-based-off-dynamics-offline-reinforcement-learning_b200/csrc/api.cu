@@ -21,6 +21,8 @@ void mb_gather_pos_launch(const float* src, int w, int src_ld, const int* pos, c
                           float* dst, int dst_ld, cudaStream_t st);
 void mb_gather_pos_i64_launch(const long long* src, const int* pos, const int* m_dev, long long m_cap, long long* dst, cudaStream_t st);
 
+const char* mb_umma_selftest_launch(const float* A, const float* B, int K, int N, int nsplit, float* D, cudaStream_t st);
+
 static thread_local char g_err[512] = "";
 
 static int fail(int code, const char* msg) {
@@ -156,6 +158,13 @@ int mobody_gather_pos_i64(const long long* src, const int* pos, const int* m_dev
   if (m_cap < 0 || (m_cap > 0 && (!src || !pos || !dst))) return fail(MOBODY_ERR_ARG, "mobody_gather_pos_i64: bad arguments");
   mb_gather_pos_i64_launch(src, pos, m_dev, m_cap, dst, (cudaStream_t)stream);
   return check_launch("mobody_gather_pos_i64");
+}
+
+int mobody_selftest_umma(const float* A, const float* B, int K, int N, int nsplit, float* D, void* stream) {
+  if (!A || !B || !D) return fail(MOBODY_ERR_ARG, "mobody_selftest_umma: null pointer");
+  const char* err = mb_umma_selftest_launch(A, B, K, N, nsplit, D, (cudaStream_t)stream);
+  if (err) return fail(MOBODY_ERR_ARG, err);
+  return check_launch("mobody_selftest_umma");
 }
 
 }  // extern "C"
