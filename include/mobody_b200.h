@@ -140,6 +140,15 @@ int mobody_gather_pos(const float* src, int w, int src_ld, const int* pos, const
 int mobody_gather_pos_i64(const long long* src, const int* pos, const int* m_dev, long long m_cap,
                           long long* dst, void* stream);
 
+/* ---- tensor-core weight images (precision MOBODY_PREC_BF16X2 / MOBODY_PREC_BF16) ----
+ * The reference keeps weights as fp32 nn.Parameters (mobody_module.py:371-391, mobody.py:35-48); the
+ * tcgen05 path consumes them as bf16 planes in the UMMA shared-memory layout.  Re-pack whenever the
+ * parameters change (after dynamics.load / every policy optimiser step that precedes a rollout). */
+long long mobody_dyn_pack_bytes(int S, int A, int precision);
+int mobody_dyn_pack(const mobody_dyn_params* dyn, int S, int A, int precision, void* blob, void* stream);
+long long mobody_mlp_pack_bytes(int din, int dout, int precision);
+int mobody_mlp_pack(const mobody_mlp_params* mlp, int din, int dout, int precision, void* blob, void* stream);
+
 /* Test hook: D[128,N] = A[128,K] * B[N,K]^T on one CTA through the same tcgen05 operand layout,
  * descriptors and TMEM read-back as the rollout kernel (nsplit 1 = bf16, 2 = bf16 hi+lo split). */
 int mobody_selftest_umma(const float* A, const float* B, int K, int N, int nsplit, float* D, void* stream);

@@ -16,6 +16,7 @@ DYN_LAYER_NAMES = ("zs1", "zs2", "zs3", "za_src1", "za_src2", "za_trg1", "za_trg
                    "transition1", "transition2", "transition3",
                    "reward_model1", "reward_model2", "reward_model3")
 PREC = {"fp32": 0, "bf16x2": 1, "bf16": 2}
+ENABLED_PRECISIONS = ("fp32", "bf16x2", "bf16")
 KEEP_U8_ZERO, KEEP_F32_LE, KEEP_F32_LT, KEEP_U8_VALID = 0, 1, 2, 3
 
 
@@ -73,6 +74,12 @@ def lib():
         L.mobody_gather_pos.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p,
                                         C.c_int, C.c_void_p]
         L.mobody_gather_pos_i64.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]
+        L.mobody_dyn_pack_bytes.restype = C.c_longlong
+        L.mobody_dyn_pack_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.mobody_dyn_pack.argtypes = [C.POINTER(DynParams), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.mobody_mlp_pack_bytes.restype = C.c_longlong
+        L.mobody_mlp_pack_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.mobody_mlp_pack.argtypes = [C.POINTER(MlpParams), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.mobody_selftest_umma.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         if L.mobody_abi_version() != 1:
             raise RuntimeError("mobody_b200: ABI version mismatch between _ffi.py and libmobody_b200.so")
@@ -119,6 +126,11 @@ def dyn_params(model):
         d.w[i], d.b[i] = w.data_ptr(), b.data_ptr()
         keep += [w, b]
     return d, keep
+
+
+def params_version(tensors):
+    """Cheap change detector for packed weight images: storage pointers + in-place version counters."""
+    return tuple((t.data_ptr(), t._version) for t in tensors)
 
 
 def mlp_params(mlp):

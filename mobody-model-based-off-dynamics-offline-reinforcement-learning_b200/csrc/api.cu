@@ -3,6 +3,7 @@
 #include <string.h>
 #include "../../include/mobody_b200.h"
 #include "common.cuh"
+#include "tc_layout.h"
 
 // launchers implemented in the kernel translation units
 const char* mb_simt_step_launch(const StepArgs& a, const DynPtrs& dp, const MlpPtrs* pol, cudaStream_t st);
@@ -21,6 +22,9 @@ void mb_gather_pos_launch(const float* src, int w, int src_ld, const int* pos, c
                           float* dst, int dst_ld, cudaStream_t st);
 void mb_gather_pos_i64_launch(const long long* src, const int* pos, const int* m_dev, long long m_cap, long long* dst, cudaStream_t st);
 
+const char* mb_tc_dyn_pack(const DynPtrs& dp, int S, int A, int ns, unsigned char* blob, cudaStream_t st);
+const char* mb_tc_mlp_pack(const MlpPtrs& mp, int din, int dout, int ns, unsigned char* blob, cudaStream_t st);
+const char* mb_tc_step_launch(const StepArgs& a, const unsigned char* dynb, const unsigned char* polb, int ns, cudaStream_t st);
 const char* mb_umma_selftest_launch(const float* A, const float* B, int K, int N, int nsplit, float* D, cudaStream_t st);
 
 static thread_local char g_err[512] = "";
@@ -73,6 +77,13 @@ int mobody_step(const mobody_step_desc* d, void* stream) {
   const char* err = nullptr;
   switch (d->precision) {
     case MOBODY_PREC_FP32: err = mb_simt_step_launch(a, dp, polp, (cudaStream_t)stream); break;
+    case MOBODY_PREC_BF16X2:
+    case MOBODY_PREC_BF16:
+      if (!d->dyn_pack) return fail(MOBODY_ERR_ARG, "mobody_step: tensor-core precision needs dyn_pack (mobody_dyn_pack)");
+      if (d->policy && !d->policy_pack) return fail(MOBODY_ERR_ARG, "mobody_step: fused policy needs policy_pack (mobody_mlp_pack)");
+      err = mb_tc_step_launch(a, (const unsigned char*)d->dyn_pack, d->policy ? (const unsigned char*)d->policy_pack : nullptr,
+                              d->precision == MOBODY_PREC_BF16X2 ? 2 : 1, (cudaStream_t)stream);
+      break;
     default: return fail(MOBODY_ERR_UNSUPPORTED, "mobody_step: unknown precision mode");
   }
   if (err) return fail(MOBODY_ERR_UNSUPPORTED, err);
@@ -158,6 +169,40 @@ int mobody_gather_pos_i64(const long long* src, const int* pos, const int* m_dev
   if (m_cap < 0 || (m_cap > 0 && (!src || !pos || !dst))) return fail(MOBODY_ERR_ARG, "mobody_gather_pos_i64: bad arguments");
   mb_gather_pos_i64_launch(src, pos, m_dev, m_cap, dst, (cudaStream_t)stream);
   return check_launch("mobody_gather_pos_i64");
+}
+
+static int nsplit_of(int precision) { return precision == MOBODY_PREC_BF16X2 ? 2 : precision == MOBODY_PREC_BF16 ? 1 : 0; }
+
+long long mobody_dyn_pack_bytes(int S, int A, int precision) {
+  int ns = nsplit_of(precision);
+  if (!ns || S < 2 || A < 1) return 0;
+  return (long long)tc_dyn_layout(S, A, ns).total_bytes;
+}
+
+int mobody_dyn_pack(const mobody_dyn_params* dyn, int S, int A, int precision, void* blob, void* stream) {
+  int ns = nsplit_of(precision);
+  if (!ns || !dyn || !blob || S < 2 || A < 1) return fail(MOBODY_ERR_ARG, "mobody_dyn_pack: bad arguments");
+  DynPtrs dp; memcpy(&dp, dyn, sizeof(dp));
+  for (int i = 0; i < L_COUNT; ++i)
+    if (!dp.w[i] || !dp.b[i]) return fail(MOBODY_ERR_ARG, "mobody_dyn_pack: null parameter pointer");
+  const char* err = mb_tc_dyn_pack(dp, S, A, ns, (unsigned char*)blob, (cudaStream_t)stream);
+  if (err) return fail(MOBODY_ERR_ARG, err);
+  return check_launch("mobody_dyn_pack");
+}
+
+long long mobody_mlp_pack_bytes(int din, int dout, int precision) {
+  int ns = nsplit_of(precision);
+  if (!ns || din < 1 || dout < 1) return 0;
+  return (long long)tc_mlp_layout(din, dout, ns).total_bytes;
+}
+
+int mobody_mlp_pack(const mobody_mlp_params* mlp, int din, int dout, int precision, void* blob, void* stream) {
+  int ns = nsplit_of(precision);
+  if (!ns || !mlp || !blob || din < 1 || dout < 1) return fail(MOBODY_ERR_ARG, "mobody_mlp_pack: bad arguments");
+  MlpPtrs mp; memcpy(&mp, mlp, sizeof(mp));
+  const char* err = mb_tc_mlp_pack(mp, din, dout, ns, (unsigned char*)blob, (cudaStream_t)stream);
+  if (err) return fail(MOBODY_ERR_ARG, err);
+  return check_launch("mobody_mlp_pack");
 }
 
 int mobody_selftest_umma(const float* A, const float* B, int K, int N, int nsplit, float* D, void* stream) {

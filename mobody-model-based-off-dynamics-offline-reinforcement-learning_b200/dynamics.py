@@ -67,6 +67,33 @@ class MOBODYEnsembleDynamics(object):
         self.precision = precision or (config or {}).get("b200_precision", "fp32")
         self.seed = int(seed)
         self._draw = 0        # Philox step counter for stand-alone step() calls in production mode
+        self._dyn_pack = None  # (version key, blob) of the tensor-core weight image
+        self._pol_pack = {}    # id(policy module) -> (version key, blob)
+
+    # ------------------------------------------------------------------
+    def _packed_dynamics(self, dp, keep):
+        """bf16-plane UMMA image of the ensemble weights; re-packed when any parameter changed."""
+        key = (self.precision,) + _ffi.params_version(keep)
+        if self._dyn_pack is None or self._dyn_pack[0] != key:
+            S, A, prec = self.model.obs_dim, self.model.action_dim, _ffi.PREC[self.precision]
+            dev = keep[0].device
+            n = int(_ffi.lib().mobody_dyn_pack_bytes(S, A, prec))
+            blob = torch.empty(n, dtype=torch.uint8, device=dev)
+            _ffi.check(_ffi.lib().mobody_dyn_pack(C.byref(dp), S, A, prec, _ffi.ptr(blob), _ffi.stream_ptr(dev)))
+            self._dyn_pack = (key, blob)
+        return self._dyn_pack[1]
+
+    def _packed_policy(self, policy, mp, keep):
+        key = (self.precision,) + _ffi.params_version(keep)
+        ent = self._pol_pack.get(id(policy))
+        if ent is None or ent[0] != key:
+            S, A, prec = self.model.obs_dim, self.model.action_dim, _ffi.PREC[self.precision]
+            dev = keep[0].device
+            n = int(_ffi.lib().mobody_mlp_pack_bytes(S, A, prec))
+            blob = ent[1] if ent is not None and ent[1].numel() == n else torch.empty(n, dtype=torch.uint8, device=dev)
+            _ffi.check(_ffi.lib().mobody_mlp_pack(C.byref(mp), S, A, prec, _ffi.ptr(blob), _ffi.stream_ptr(dev)))
+            self._pol_pack[id(policy)] = (key, blob)
+        return self._pol_pack[id(policy)][1]
 
     # ------------------------------------------------------------------
     def launch_step(self, obs, act, ws: StepWorkspace, *, policy=None, max_action=1.0, use_penalty=True,
@@ -82,12 +109,19 @@ class MOBODYEnsembleDynamics(object):
         d.n_rows_dev, d.row_ids = _ffi.ptr(n_rows_dev), _ffi.ptr(row_ids)
         d.obs, d.act = _ffi.ptr(obs), _ffi.ptr(act)
         keep = []
+        tensor_core = self.precision != "fp32"
         if policy is not None:
             mp, k = _ffi.mlp_params(policy); keep += k
             d.policy = C.pointer(mp)
+            if tensor_core:
+                d.policy_pack = _ffi.ptr(self._packed_policy(policy, mp, k))
+                if ws.act is None:
+                    ws.act = torch.empty(B, A, dtype=torch.float32, device=dev)
         d.max_action = float(max_action)
         dp, k = _ffi.dyn_params(self.model); keep += k
         d.dyn = C.pointer(dp)
+        if tensor_core:
+            d.dyn_pack = _ffi.ptr(self._packed_dynamics(dp, k))
         d.use_trg, d.use_penalty = int(bool(use_trg)), int(bool(use_penalty))
         d.penalty_coef = float(self._penalty_coef)
         d.term_kind = self.terminal_fn.kind

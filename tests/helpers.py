@@ -48,5 +48,11 @@ def cuda_agent(S, A, seed, **overrides):
 
 
 def rel_err(a, b):
+    """max |a-b| / (|b| + scale) with scale = mean|b| of the tensor: the "relative" error of north_star,
+    with an absolute floor tied to the tensor's own magnitude so that elements that happen to be ~0
+    (e.g. joint angles around zero next to a torso height of 1.25) are judged at the tensor's scale."""
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
-    return float(np.max(np.abs(a - b) / (np.abs(b) + 1e-3)))
+    if b.size == 0:
+        return 0.0
+    scale = float(np.mean(np.abs(b))) + 1e-12
+    return float(np.max(np.abs(a - b) / (np.abs(b) + scale)))

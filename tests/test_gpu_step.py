@@ -15,7 +15,7 @@ from helpers import cuda_dynamics, rel_err
 from oracle import mobody_oracle as M
 
 pytestmark = pytest.mark.gpu
-TOL = {"fp32": 1e-4, "bf16x2": 1e-4, "bf16": 5e-3}
+TOL = {"fp32": 1e-4, "bf16x2": 1e-4, "bf16": 2e-2}   # bf16: stated looser bound (single-pass bf16 GEMMs)
 
 
 def precisions():
