@@ -152,6 +152,8 @@ int mobody_mlp_pack(const mobody_mlp_params* mlp, int din, int dout, int precisi
 /* Test hook: D[128,N] = A[128,K] * B[N,K]^T on one CTA through the same tcgen05 operand layout,
  * descriptors and TMEM read-back as the rollout kernel (nsplit 1 = bf16, 2 = bf16 hi+lo split). */
 int mobody_selftest_umma(const float* A, const float* B, int K, int N, int nsplit, float* D, void* stream);
+/* Same for the CTA pair (tcgen05.mma.cta_group::2): D[256,N] = A[256,K] * B[N,K]^T on a 2-CTA cluster. */
+int mobody_selftest_umma2(const float* A, const float* B, int K, int N, int nsplit, float* D, void* stream);
 
 #ifdef __cplusplus
 }

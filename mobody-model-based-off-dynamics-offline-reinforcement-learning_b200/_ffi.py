@@ -81,6 +81,7 @@ def lib():
         L.mobody_mlp_pack_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
         L.mobody_mlp_pack.argtypes = [C.POINTER(MlpParams), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.mobody_selftest_umma.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.mobody_selftest_umma2.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         if L.mobody_abi_version() != 1:
             raise RuntimeError("mobody_b200: ABI version mismatch between _ffi.py and libmobody_b200.so")
         _lib = L

@@ -27,6 +27,8 @@ const char* mb_tc_mlp_pack(const MlpPtrs& mp, int din, int dout, int ns, unsigne
 const char* mb_tc_step_launch(const StepArgs& a, const unsigned char* dynb, const unsigned char* polb, int ns, cudaStream_t st);
 const char* mb_umma_selftest_launch(const float* A, const float* B, int K, int N, int nsplit, float* D, cudaStream_t st);
 
+const char* mb_umma2_selftest_launch(const float* A, const float* B, int K, int N, int nsplit, float* D, cudaStream_t st);
+
 static thread_local char g_err[512] = "";
 
 static int fail(int code, const char* msg) {
@@ -210,6 +212,13 @@ int mobody_selftest_umma(const float* A, const float* B, int K, int N, int nspli
   const char* err = mb_umma_selftest_launch(A, B, K, N, nsplit, D, (cudaStream_t)stream);
   if (err) return fail(MOBODY_ERR_ARG, err);
   return check_launch("mobody_selftest_umma");
+}
+
+int mobody_selftest_umma2(const float* A, const float* B, int K, int N, int nsplit, float* D, void* stream) {
+  if (!A || !B || !D) return fail(MOBODY_ERR_ARG, "mobody_selftest_umma2: null pointer");
+  const char* err = mb_umma2_selftest_launch(A, B, K, N, nsplit, D, (cudaStream_t)stream);
+  if (err) return fail(MOBODY_ERR_ARG, err);
+  return check_launch("mobody_selftest_umma2");
 }
 
 }  // extern "C"

@@ -27,8 +27,11 @@
 
 namespace tcs {
 
-constexpr int NTHREADS = 384;      // warp 0 producer, 1 MMA issuer, 2 TMEM allocator, 3 idle, 4..11 epilogue
-constexpr int EPI_WARP0 = 4;
+constexpr int EPI_WARPS = 16;      // warps 0..15: epilogue, 4 groups x 4 TMEM lane quadrants
+constexpr int NGROUPS = EPI_WARPS / 4;
+constexpr int PROD_WARP = 16;      // weight producer (+ TMEM alloc/dealloc)
+constexpr int MMA_WARP = 17;       // MMA issuer
+constexpr int NTHREADS = 32 * (EPI_WARPS + 2);
 constexpr int TM = 128;
 constexpr uint32_t MAIN_PLANE = 65536;   // 128 rows x 256 k x bf16
 constexpr int MAX_NST = 12;
@@ -59,6 +62,8 @@ __device__ __forceinline__ void store8(unsigned char* base, uint32_t plane_strid
   }
 }
 
+template <int NS> __device__ __forceinline__ float swish_ns(float x) { return NS == 1 ? tc::swish_tanh(x) : tc::swish_ex2_rcp(x); }
+
 template <int NS>
 __device__ __forceinline__ void store1(unsigned char* base, uint32_t plane_stride, uint32_t off, float v) {
   __nv_bfloat16 h = __float2bfloat16_rn(v);
@@ -66,7 +71,7 @@ __device__ __forceinline__ void store1(unsigned char* base, uint32_t plane_strid
   if (NS == 2) *reinterpret_cast<__nv_bfloat16*>(base + plane_stride + off) = __float2bfloat16_rn(v - __bfloat162float(h));
 }
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // epilogue warps only
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory"); }   // epilogue warps only
 
 template <int NS>
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -81,24 +86,24 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
   unsigned char* A_main = smem;
   unsigned char* A_small = A_main + NS * MAIN_PLANE;
   unsigned char* wst = A_small + NS * cfg.small_plane;
-  float* red = reinterpret_cast<float*>(wst + (size_t)cfg.nst * cfg.stage_bytes);      // [2][2][128]
-  Bars* bars = reinterpret_cast<Bars*>(red + 512);
+  float* red = reinterpret_cast<float*>(wst + (size_t)cfg.nst * cfg.stage_bytes);      // [2][NGROUPS][128]
+  Bars* bars = reinterpret_cast<Bars*>(red + 2 * NGROUPS * 128);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     for (int i = 0; i < cfg.nst; ++i) { tc::mbar_init(&bars->w_full[i], 1); tc::mbar_init(&bars->w_empty[i], 1); }
     for (int i = 0; i < 8; ++i) tc::mbar_init(&bars->a_ready[i], 4);       // 4 warps own each 32-column chunk
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&bars->d_full[i], 1); tc::mbar_init(&bars->d_empty[i], 8); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&bars->d_full[i], 1); tc::mbar_init(&bars->d_empty[i], EPI_WARPS); }
     tc::mbar_fence_init();
   }
-  if (warp == 2) tc::tmem_alloc(&bars->tmem_slot, 512);
+  if (warp == PROD_WARP) tc::tmem_alloc(&bars->tmem_slot, 512);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
   const uint32_t tmem = bars->tmem_slot;
 
-  if (warp == 0) {
+  if (warp == PROD_WARP) {
     // ================= weight producer: L2 -> SMEM ring, one K step (all planes) per stage =================
     if (tc::elect_one()) {
       int stage = 0; uint32_t phase = 0;
@@ -114,7 +119,7 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == MMA_WARP) {
     // ================= MMA issuer =================
     if (tc::elect_one()) {
       int stage = 0; uint32_t wphase = 0, aph = 0;
@@ -152,9 +157,9 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
         tc::umma_commit(&bars->d_full[buf]);
       }
     }
-  } else if (warp >= EPI_WARP0) {
+  } else {
     // ================= epilogue warps =================
-    const int q = warp & 3, group = (warp - EPI_WARP0) >> 2;
+    const int q = warp & 3, group = warp >> 2;
     const int r = q * 32 + lane;
     const bool valid = (row0 + r) < live;
     const size_t grow = (size_t)row0 + r;                     // row in this launch's arrays
@@ -177,19 +182,19 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
     };
     auto bias_of = [&](int l) { const TcLayer L = sched.L[l]; return (L.blob ? pol_bias : dyn_bias) + L.b_off; };
 
-    // 256-wide hidden layer: act(x + b) -> A_main planes, chunk by chunk
+    // 256-wide hidden layer: act(x + b) -> A_main planes, chunk by chunk (group g owns chunks g, g+4)
     auto epi_act256 = [&](int l, bool relu) {
       const float* bias = bias_of(l);
-      wait_d(l);
       const uint32_t t0 = lane_addr + (uint32_t)(l & 1) * 256u;
+      float4 bv[8];                                            // bias of the first chunk: fetched before the wait
+#pragma unroll
+      for (int i = 0; i < 8; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(bias + group * 32) + i);
+      wait_d(l);
 #pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        const int c = cc * 2 + group;
+      for (int cc = 0; cc < 8 / NGROUPS; ++cc) {
+        const int c = cc * NGROUPS + group;
         uint32_t x[32];
         tc::tmem_ld32(t0 + (uint32_t)c * 32u, x);
-        float4 bv[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(bias + c * 32) + i);
         tc::tmem_ld_wait();
 #pragma unroll
         for (int kg = 0; kg < 4; ++kg) {
@@ -199,11 +204,15 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
             const float4 b4 = bv[kg * 2 + (i >> 2)];
             const float bb = (i & 3) == 0 ? b4.x : (i & 3) == 1 ? b4.y : (i & 3) == 2 ? b4.z : b4.w;
             const float t = __uint_as_float(x[kg * 8 + i]) + bb;
-            v[i] = relu ? fmaxf(t, 0.f) : mb_swish(t);
+            v[i] = relu ? fmaxf(t, 0.f) : swish_ns<NS>(t);
           }
           store8<NS>(A_main, MAIN_PLANE, (uint32_t)(c * 4 + kg) * 2048u + (uint32_t)r * 16u, v);
         }
         signal_a(c);
+        if (cc + 1 < 8 / NGROUPS) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(bias + (c + NGROUPS) * 32) + i);
+        }
       }
       release_d(l);
     };
@@ -297,7 +306,7 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
           for (int kg = 0; kg < 4; ++kg) {
             float v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = mb_swish(__uint_as_float(x[kg * 8 + i]) + __ldg(bias + kg * 8 + i));
+            for (int i = 0; i < 8; ++i) v[i] = swish_ns<NS>(__uint_as_float(x[kg * 8 + i]) + __ldg(bias + kg * 8 + i));
             store8<NS>(A_main, MAIN_PLANE, (uint32_t)kg * 2048u + (uint32_t)r * 16u, v);
           }
           signal_a(0);
@@ -330,7 +339,7 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
         const float* bias = bias_of(l);
         const int np = sched.L[l].n;
         wait_d(l);
-        for (int c = group; c * 32 < np; c += 2) {
+        for (int c = group; c * 32 < np; c += NGROUPS) {
           uint32_t x[32];
           if (np - c * 32 >= 32) tc::tmem_ld32(lane_addr + (uint32_t)(l & 1) * 256u + (uint32_t)c * 32u, x);
           else {
@@ -398,7 +407,7 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
       tc::fence_proxy_async_smem();
     }
     epi_bar();
-    for (int c = group; c * 32 < (int)cfg.sas_kp; c += 2) { __syncwarp(); if (lane == 0) tc::mbar_arrive(&bars->a_ready[c]); }
+    for (int c = group; c * 32 < (int)cfg.sas_kp; c += NGROUPS) { __syncwarp(); if (lane == 0) tc::mbar_arrive(&bars->a_ready[c]); }
 
     // ---------------- reward head, all 7 members (mobody_module.py:295-302; mean over members :236) ----------------
 #pragma unroll 1
@@ -412,19 +421,30 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
         const uint32_t t0 = lane_addr + (uint32_t)(l & 1) * 256u;
         float part = 0.f;
 #pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
-          const int c = cc * 2 + group;
+        for (int cc = 0; cc < 8 / NGROUPS; ++cc) {
+          const int c = cc * NGROUPS + group;
           uint32_t x[32];
           tc::tmem_ld32(t0 + (uint32_t)c * 32u, x);
           tc::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            part = fmaf(mb_swish(__uint_as_float(x[j]) + __ldg(bias + c * 32 + j)), __ldg(w3 + c * 32 + j), part);
+          for (int i = 0; i < 8; ++i) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c * 32) + i);
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(w3 + c * 32) + i);
+            part = fmaf(swish_ns<NS>(__uint_as_float(x[4 * i + 0]) + b4.x), w4.x, part);
+            part = fmaf(swish_ns<NS>(__uint_as_float(x[4 * i + 1]) + b4.y), w4.y, part);
+            part = fmaf(swish_ns<NS>(__uint_as_float(x[4 * i + 2]) + b4.z), w4.z, part);
+            part = fmaf(swish_ns<NS>(__uint_as_float(x[4 * i + 3]) + b4.w), w4.w, part);
+          }
         }
         release_d(l);
-        red[((e & 1) * 2 + group) * 128 + r] = part;
+        red[((e & 1) * NGROUPS + group) * 128 + r] = part;
         epi_bar();
-        if (group == 0) racc += red[((e & 1) * 2 + 0) * 128 + r] + red[((e & 1) * 2 + 1) * 128 + r] + __ldg(w3 + 256);
+        if (group == 0) {
+          float sum = 0.f;
+#pragma unroll
+          for (int g2 = 0; g2 < NGROUPS; ++g2) sum += red[((e & 1) * NGROUPS + g2) * 128 + r];
+          racc += sum + __ldg(w3 + 256);
+        }
       }
     }
     if (group == 0 && valid) {
@@ -437,7 +457,7 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
 
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 2) tc::tmem_dealloc(tmem, 512);
+  if (warp == PROD_WARP) tc::tmem_dealloc(tmem, 512);
 }
 
 // ---------------- weight packing: fp32 [K][N] (any strides) -> bf16 planes in UMMA B layout ----------------
@@ -552,7 +572,7 @@ const char* mb_tc_step_launch(const StepArgs& a, const unsigned char* dynb, cons
   cfg.stage_bytes = (uint32_t)ns * 256u * 32u;
   cfg.dyn_bias_base = (uint32_t)DL.bias_base; cfg.member_b_floats = DL.member_b_floats; cfg.r3_b_off = DL.b_off[PK_COUNT];
   cfg.has_policy = has_policy ? 1 : 0;
-  const size_t fixed = (size_t)ns * tcs::MAIN_PLANE + (size_t)ns * cfg.small_plane + 512 * sizeof(float) + sizeof(tcs::Bars) + 128;
+  const size_t fixed = (size_t)ns * tcs::MAIN_PLANE + (size_t)ns * cfg.small_plane + 2 * tcs::NGROUPS * 128 * sizeof(float) + sizeof(tcs::Bars) + 128;
   const size_t budget = 227 * 1024;
   if (fixed + 2 * cfg.stage_bytes > budget) return "tensor-core step kernel: shared memory budget exceeded for this (S, A)";
   int nst = (int)((budget - fixed) / cfg.stage_bytes);

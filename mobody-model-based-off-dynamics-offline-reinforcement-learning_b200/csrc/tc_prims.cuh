@@ -110,6 +110,55 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---------------- CTA pair (cta_group::2) variants ----------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(rank) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait_cluster(bar, parity)) {}
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// commit of the pair's MMAs: arrives on the barrier at this offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit2(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+// D[tmem, 256 rows over the CTA pair] (+)= A * B^T : A rows 0-127 from CTA0 / 128-255 from CTA1 (same smem offset),
+// B rows n < N/2 from CTA0 / n >= N/2 from CTA1.  Issued by one thread of the leader CTA.
+__device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -120,18 +169,36 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-// ---------------- bf16 split helpers ----------------
-// hi = rn_bf16(v); lo = rn_bf16(v - hi).  hi+lo carries ~16 significand bits of v.
+// ---------------- bf16 split helpers (integer pipe only: no F2FP / XU traffic) ----------------
+// hi = bf16(v) rounded half-away (add 0x8000 to the magnitude bits, keep the top 16);
+// lo = bf16(v - hi), same rounding.  hi+lo carries ~16 significand bits of v (error <= 2^-17 |v|).
+// Packing two values into one 32-bit word is a byte permute (low half = first value).
 __device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);          // .x = v0 (low half), .y = v1 (high half)
-  hi = *reinterpret_cast<uint32_t*>(&h);
-  float h0 = __uint_as_float(hi << 16), h1 = __uint_as_float(hi & 0xFFFF0000u);
-  __nv_bfloat162 l = __floats2bfloat162_rn(v0 - h0, v1 - h1);
-  lo = *reinterpret_cast<uint32_t*>(&l);
+  const uint32_t h0 = (__float_as_uint(v0) + 0x8000u) & 0xFFFF0000u;
+  const uint32_t h1 = (__float_as_uint(v1) + 0x8000u) & 0xFFFF0000u;
+  const uint32_t l0 = __float_as_uint(v0 - __uint_as_float(h0)) + 0x8000u;
+  const uint32_t l1 = __float_as_uint(v1 - __uint_as_float(h1)) + 0x8000u;
+  hi = __byte_perm(h0, h1, 0x7632);
+  lo = __byte_perm(l0, l1, 0x7632);
 }
 __device__ __forceinline__ uint32_t pack_bf16(float v0, float v1) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
-  return *reinterpret_cast<uint32_t*>(&h);
+  return __byte_perm(__float_as_uint(v0) + 0x8000u, __float_as_uint(v1) + 0x8000u, 0x7632);
+}
+
+// ---------------- swish on the SFU with flush-to-zero forms (one MUFU each, no range fix-ups) ----------------
+// exact mode: x / (1 + 2^(-x log2 e)) with ex2.approx.ftz (2 ulp) and rcp.approx.ftz (1 ulp)
+__device__ __forceinline__ float swish_ex2_rcp(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
+}
+// loose mode (single-pass bf16 only): 0.5x (1 + tanh(0.5x)), one MUFU; tanh.approx error 2^-11 < bf16 ulp
+__device__ __forceinline__ float swish_tanh(float x) {
+  const float hx = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(hx));
+  return fmaf(hx, t, hx);
 }
 
 }  // namespace tc
