@@ -29,6 +29,8 @@ const char* mb_umma_selftest_launch(const float* A, const float* B, int K, int N
 
 const char* mb_umma2_selftest_launch(const float* A, const float* B, int K, int N, int nsplit, float* D, cudaStream_t st);
 
+void mb_tc_set_trace(long long* buf);
+
 static thread_local char g_err[512] = "";
 
 static int fail(int code, const char* msg) {
@@ -220,5 +222,8 @@ int mobody_selftest_umma2(const float* A, const float* B, int K, int N, int nspl
   if (err) return fail(MOBODY_ERR_ARG, err);
   return check_launch("mobody_selftest_umma2");
 }
+
+/* debug hook (not in the public header): device int64[80*8] receiving per-layer clock64 stamps of CTA 0 */
+int mobody_debug_set_trace(void* buf) { mb_tc_set_trace((long long*)buf); return MOBODY_OK; }
 
 }  // extern "C"

@@ -40,6 +40,15 @@ __device__ __forceinline__ void philox_normal4(const Philox4& b, float out[4]) {
   sincosf(t1, &s, &c); out[2] = r1 * c; out[3] = r1 * s;
 }
 
+// one N(0,1): word w (0..3) of the block, same values as philox_normal4()[w]
+__device__ __forceinline__ float philox_normal1(const Philox4& b, int w) {
+  const float two_pi = 6.283185307179586f;
+  const uint32_t xa = (w & 2) ? b.z : b.x, xb = (w & 2) ? b.w : b.y;
+  // SFU forms (lg2/sin/cos.approx): |error| ~1e-6 on the sample, far below the noise it models
+  const float r = sqrtf(-2.0f * __logf(philox_u01(xa))), t = two_pi * philox_u01(xb);
+  return (w & 1) ? r * __sinf(t) : r * __cosf(t);
+}
+
 __device__ __forceinline__ Philox4 philox_noise_block(unsigned long long seed, unsigned int step,
                                                      unsigned long long row, unsigned int block) {
   return philox4x32_10((uint32_t)row, (uint32_t)(row >> 32), step, block, (uint32_t)seed, MB_STREAM_NOISE);

@@ -12,10 +12,13 @@
 //    (cp.async.bulk + mbarrier complete_tx) through an NST-deep ring;
 //  * one elected thread issues tcgen05.mma (128 x N x 16 per instruction), accumulators live in
 //    TMEM (two 256-column buffers, ping-pong across layers);
-//  * 8 epilogue warps read TMEM (tcgen05.ld), apply bias + swish/relu, split to bf16 planes and write
-//    the next layer's A operand in place in SMEM, 32 columns at a time; the next layer's MMAs start
-//    as soon as the first 32-column chunk is announced (mbarrier per chunk), so tensor pipe and
-//    epilogue overlap inside a single row tile.
+//  * 16 epilogue warps (4 groups x 4 TMEM lane quadrants) read TMEM (tcgen05.ld, one chunk ahead), apply
+//    bias + swish/relu, split to bf16 planes with integer ops and write the next layer's A operand in
+//    place in SMEM.  All groups work on the same 32-column chunk (8 columns per warp), so chunks are
+//    announced in order (one mbarrier per chunk) and the next layer's MMAs trail the epilogue by one chunk:
+//    tensor pipe and epilogue overlap inside a single row tile.
+//  A CTA-pair (cta_group::2) variant of this kernel lives on branch `cta-pair`: correct but slower here
+//  (the chain is latency-, not SMEM-bandwidth-bound); see DESIGN.md.
 //
 // Precision: NS = 1 -> single bf16 pass (stated bound 5e-3); NS = 2 -> bf16 hi+lo split of both
 // operands, 3 MMAs per K step (hi*hi + lo*hi + hi*lo), ~2^-16 per product: inside the 1e-4 bound.
@@ -24,14 +27,12 @@
 #include "term.cuh"
 #include "tc_prims.cuh"
 #include "tc_layout.h"
+#include <stdlib.h>
 
 namespace tcs {
 
-constexpr int EPI_WARPS = 16;      // warps 0..15: epilogue, 4 groups x 4 TMEM lane quadrants
-constexpr int NGROUPS = EPI_WARPS / 4;
-constexpr int PROD_WARP = 16;      // weight producer (+ TMEM alloc/dealloc)
-constexpr int MMA_WARP = 17;       // MMA issuer
-constexpr int NTHREADS = 32 * (EPI_WARPS + 2);
+template <int W> __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(32 * W) : "memory"); }   // epilogue warps only
+
 constexpr int TM = 128;
 constexpr uint32_t MAIN_PLANE = 65536;   // 128 rows x 256 k x bf16
 constexpr int MAX_NST = 12;
@@ -41,6 +42,7 @@ struct Cfg {
   uint32_t stage_bytes, small_plane, sa_off, obs_kp, sas_kp;
   uint32_t dyn_bias_base, pol_bias_base, member_b_floats, r3_b_off;
   int has_policy;
+  long long* trace;     // debug: per-layer clock64 timestamps of CTA 0 ([layer][8]); nullptr in production
 };
 
 struct Bars {
@@ -64,19 +66,19 @@ __device__ __forceinline__ void store8(unsigned char* base, uint32_t plane_strid
 
 template <int NS> __device__ __forceinline__ float swish_ns(float x) { return NS == 1 ? tc::swish_tanh(x) : tc::swish_ex2_rcp(x); }
 
-template <int NS>
-__device__ __forceinline__ void store1(unsigned char* base, uint32_t plane_stride, uint32_t off, float v) {
-  __nv_bfloat16 h = __float2bfloat16_rn(v);
-  *reinterpret_cast<__nv_bfloat16*>(base + off) = h;
-  if (NS == 2) *reinterpret_cast<__nv_bfloat16*>(base + plane_stride + off) = __float2bfloat16_rn(v - __bfloat162float(h));
-}
+template <int CW> __device__ __forceinline__ void tmem_ldw(uint32_t taddr, uint32_t (&x)[CW]);
+template <> __device__ __forceinline__ void tmem_ldw<8>(uint32_t taddr, uint32_t (&x)[8]) { tc::tmem_ld8(taddr, x); }
+template <> __device__ __forceinline__ void tmem_ldw<16>(uint32_t taddr, uint32_t (&x)[16]) { tc::tmem_ld16(taddr, x); }
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory"); }   // epilogue warps only
-
-template <int NS>
-__global__ void __launch_bounds__(NTHREADS, 1)
+// NG groups of 4 epilogue warps (one warp per TMEM lane quadrant).  Every 32-column accumulator chunk is
+// processed by ALL groups at once (group g takes columns [g*CW, (g+1)*CW) of the chunk, CW = 32/NG), so
+// chunks complete in order and the next layer's MMAs trail the epilogue by one chunk.
+template <int NS, int NG>
+__global__ void __launch_bounds__(32 * (4 * NG + 2), 1)
 step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const unsigned char* __restrict__ polb,
                const __grid_constant__ TcSched sched, const Cfg cfg) {
+  constexpr int EPI_WARPS = 4 * NG, PROD_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1;
+  constexpr int CW = 32 / NG, KGW = CW / 8;
   extern __shared__ __align__(128) unsigned char smem[];
   const int S = a.S, A = a.A, B = a.B;
   const int live = a.n_rows_dev ? min(*a.n_rows_dev, B) : B;
@@ -86,14 +88,14 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
   unsigned char* A_main = smem;
   unsigned char* A_small = A_main + NS * MAIN_PLANE;
   unsigned char* wst = A_small + NS * cfg.small_plane;
-  float* red = reinterpret_cast<float*>(wst + (size_t)cfg.nst * cfg.stage_bytes);      // [2][NGROUPS][128]
-  Bars* bars = reinterpret_cast<Bars*>(red + 2 * NGROUPS * 128);
+  float* red = reinterpret_cast<float*>(wst + (size_t)cfg.nst * cfg.stage_bytes);      // [2][4][128]
+  Bars* bars = reinterpret_cast<Bars*>(red + 2 * 4 * 128);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
     for (int i = 0; i < cfg.nst; ++i) { tc::mbar_init(&bars->w_full[i], 1); tc::mbar_init(&bars->w_empty[i], 1); }
-    for (int i = 0; i < 8; ++i) tc::mbar_init(&bars->a_ready[i], 4);       // 4 warps own each 32-column chunk
+    for (int i = 0; i < 8; ++i) tc::mbar_init(&bars->a_ready[i], EPI_WARPS);   // every epilogue warp announces every chunk
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&bars->d_full[i], 1); tc::mbar_init(&bars->d_empty[i], EPI_WARPS); }
     tc::mbar_fence_init();
   }
@@ -130,6 +132,7 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
         const uint32_t dcol = tmem + (uint32_t)buf * 256u;
         if (li >= 2) tc::mbar_wait(&bars->d_empty[buf], (uint32_t)(((li >> 1) - 1) & 1));
         tc::tc_fence_after();
+        if (cfg.trace && blockIdx.x == 0) cfg.trace[li * 8 + 0] = clock64();
         uint32_t abase, aplane;
         if (L.a_region == REG_MAIN) { abase = main0; aplane = MAIN_PLANE; }
         else { aplane = cfg.small_plane; abase = small0 + (L.a_region == REG_SA ? cfg.sa_off : 0u); }
@@ -145,6 +148,7 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
           tc::tc_fence_after();
           const uint32_t ao = abase + (uint32_t)s * 4096u, bo = wst0 + (uint32_t)stage * cfg.stage_bytes;
           const uint64_t ah = tc::make_smem_desc(ao, 2048, 128), bh = tc::make_smem_desc(bo, blbo, 128);
+          if (cfg.trace && blockIdx.x == 0 && s == 0) cfg.trace[li * 8 + 1] = clock64();
           tc::umma_bf16(dcol, ah, bh, idesc, s > 0 ? 1u : 0u);
           if (NS == 2) {
             const uint64_t al = tc::make_smem_desc(ao + aplane, 2048, 128), bl = tc::make_smem_desc(bo + bplane, blbo, 128);
@@ -155,6 +159,7 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
           if (++stage == cfg.nst) { stage = 0; wphase ^= 1u; }
         }
         tc::umma_commit(&bars->d_full[buf]);
+        if (cfg.trace && blockIdx.x == 0) cfg.trace[li * 8 + 2] = clock64();
       }
     }
   } else {
@@ -163,16 +168,22 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
     const int r = q * 32 + lane;
     const bool valid = (row0 + r) < live;
     const size_t grow = (size_t)row0 + r;                     // row in this launch's arrays
-    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(group * CW);
     const float* dyn_bias = reinterpret_cast<const float*>(dynb + cfg.dyn_bias_base);
     const float* pol_bias = reinterpret_cast<const float*>(polb + cfg.pol_bias_base);
     const uint32_t sp = cfg.small_plane;
+    const int col0 = group * CW;                              // this warp's first column inside a 32-column chunk
     int li = 0;
-    float zs[16];
+    float zs[CW];
     float racc = 0.f, pen = 0.f;
 
-    auto wait_d = [&](int l) { tc::mbar_wait(&bars->d_full[l & 1], (uint32_t)((l >> 1) & 1)); tc::tc_fence_after(); };
+    const bool tracer = cfg.trace && blockIdx.x == 0 && lane == 0 && q == 0 && group < 2;
+    auto wait_d = [&](int l) {
+      tc::mbar_wait(&bars->d_full[l & 1], (uint32_t)((l >> 1) & 1)); tc::tc_fence_after();
+      if (tracer) cfg.trace[l * 8 + 3 + 2 * group] = clock64();
+    };
     auto release_d = [&](int l) {
+      if (tracer) cfg.trace[l * 8 + 4 + 2 * group] = clock64();
       tc::tc_fence_before(); __syncwarp();
       if (lane == 0) tc::mbar_arrive(&bars->d_empty[l & 1]);
     };
@@ -181,60 +192,63 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
       if (lane == 0) tc::mbar_arrive(&bars->a_ready[c]);
     };
     auto bias_of = [&](int l) { const TcLayer L = sched.L[l]; return (L.blob ? pol_bias : dyn_bias) + L.b_off; };
+    auto ldbias = [&](const float* b, float (&bv)[CW]) {
+#pragma unroll
+      for (int i = 0; i < CW / 4; ++i) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(b) + i);
+        bv[4 * i] = t.x; bv[4 * i + 1] = t.y; bv[4 * i + 2] = t.z; bv[4 * i + 3] = t.w;
+      }
+    };
 
-    // 256-wide hidden layer: act(x + b) -> A_main planes, chunk by chunk (group g owns chunks g, g+4)
+    // 256-wide hidden layer: act(x + b) -> A_main planes; chunks complete in order, TMEM loads one chunk ahead
     auto epi_act256 = [&](int l, bool relu) {
-      const float* bias = bias_of(l);
+      const float* bias = bias_of(l) + col0;
       const uint32_t t0 = lane_addr + (uint32_t)(l & 1) * 256u;
-      float4 bv[8];                                            // bias of the first chunk: fetched before the wait
-#pragma unroll
-      for (int i = 0; i < 8; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(bias + group * 32) + i);
+      float bv[CW];
+      ldbias(bias, bv);
       wait_d(l);
+      uint32_t x[CW], xn[CW];
+      tmem_ldw<CW>(t0, x);
 #pragma unroll 1
-      for (int cc = 0; cc < 8 / NGROUPS; ++cc) {
-        const int c = cc * NGROUPS + group;
-        uint32_t x[32];
-        tc::tmem_ld32(t0 + (uint32_t)c * 32u, x);
+      for (int c = 0; c < 8; ++c) {
         tc::tmem_ld_wait();
+        if (c + 1 < 8) tmem_ldw<CW>(t0 + (uint32_t)(c + 1) * 32u, xn);
 #pragma unroll
-        for (int kg = 0; kg < 4; ++kg) {
+        for (int kg = 0; kg < KGW; ++kg) {
           float v[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const float4 b4 = bv[kg * 2 + (i >> 2)];
-            const float bb = (i & 3) == 0 ? b4.x : (i & 3) == 1 ? b4.y : (i & 3) == 2 ? b4.z : b4.w;
-            const float t = __uint_as_float(x[kg * 8 + i]) + bb;
+            const float t = __uint_as_float(x[kg * 8 + i]) + bv[kg * 8 + i];
             v[i] = relu ? fmaxf(t, 0.f) : swish_ns<NS>(t);
           }
-          store8<NS>(A_main, MAIN_PLANE, (uint32_t)(c * 4 + kg) * 2048u + (uint32_t)r * 16u, v);
+          store8<NS>(A_main, MAIN_PLANE, (uint32_t)(c * 4 + group * KGW + kg) * 2048u + (uint32_t)r * 16u, v);
         }
         signal_a(c);
-        if (cc + 1 < 8 / NGROUPS) {
+        if (c + 1 < 8) {
+          ldbias(bias + (c + 1) * 32, bv);
+          tc::tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 8; ++i) bv[i] = __ldg(reinterpret_cast<const float4*>(bias + (c + NGROUPS) * 32) + i);
+          for (int i = 0; i < CW; ++i) x[i] = xn[i];
         }
       }
       release_d(l);
     };
 
     // ---------------- prologue: obs (and given actions) -> bf16 operand planes ----------------
-    if (group == 0) {
+    {
       const float* orow = a.obs + grow * S;
-      for (int kg = 0; kg < (int)cfg.obs_kp / 8; ++kg) {
+      for (int kg = group; kg < (int)cfg.obs_kp / 8; kg += NG) {
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) { int j = kg * 8 + i; v[i] = (valid && j < S) ? __ldg(orow + j) : 0.f; }
         store8<NS>(A_small, sp, (uint32_t)kg * 2048u + (uint32_t)r * 16u, v);
       }
-      if (!cfg.has_policy) {
+      if (!cfg.has_policy && group < 2) {
         const float* arow = a.act + grow * A;
+        float v[8];
 #pragma unroll
-        for (int kg = 0; kg < 2; ++kg) {
-          float v[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) { int j = kg * 8 + i; v[i] = (valid && j < A) ? __ldg(arow + j) : 0.f; }
-          store8<NS>(A_small, sp, cfg.sa_off + (uint32_t)(2 + kg) * 2048u + (uint32_t)r * 16u, v);
-        }
+        for (int i = 0; i < 8; ++i) { int j = group * 8 + i; v[i] = (valid && j < A) ? __ldg(arow + j) : 0.f; }
+        store8<NS>(A_small, sp, cfg.sa_off + (uint32_t)(2 + group) * 2048u + (uint32_t)r * 16u, v);
       }
       signal_a(0);
     }
@@ -247,21 +261,20 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
         const int l = li++;
         const float* bias = bias_of(l);
         wait_d(l);
-        if (group == 0) {
-          uint32_t x[16];
-          tc::tmem_ld16(lane_addr + (uint32_t)(l & 1) * 256u, x);
+        if (col0 < 16) {
+          uint32_t x[CW];
+          tmem_ldw<CW>(lane_addr + (uint32_t)(l & 1) * 256u, x);
           tc::tmem_ld_wait();
-          float act[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) act[j] = (j < A) ? tanhf(__uint_as_float(x[j]) + __ldg(bias + j)) * a.max_action : 0.f;
-          if (valid && a.act_out)
-            for (int j = 0; j < A; ++j) a.act_out[grow * A + j] = act[j];
-#pragma unroll
-          for (int kg = 0; kg < 2; ++kg) {
+          for (int kg = 0; kg < KGW; ++kg) {
             float v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = act[kg * 8 + i];
-            store8<NS>(A_small, sp, cfg.sa_off + (uint32_t)(2 + kg) * 2048u + (uint32_t)r * 16u, v);
+            for (int i = 0; i < 8; ++i) {
+              const int j = col0 + kg * 8 + i;
+              v[i] = (j < A) ? tanhf(__uint_as_float(x[kg * 8 + i]) + __ldg(bias + j)) * a.max_action : 0.f;
+              if (valid && j < A && a.act_out) a.act_out[grow * A + j] = v[i];
+            }
+            store8<NS>(A_small, sp, cfg.sa_off + (uint32_t)(2 + group * KGW + kg) * 2048u + (uint32_t)r * 16u, v);
           }
         }
         release_d(l);
@@ -277,59 +290,59 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
         const int l = li++;
         const float* bias = bias_of(l);
         wait_d(l);
-        if (group == 0) {
-          uint32_t x[16];
-          tc::tmem_ld16(lane_addr + (uint32_t)(l & 1) * 256u, x);
+        if (col0 < 16) {
+          uint32_t x[CW];
+          tmem_ldw<CW>(lane_addr + (uint32_t)(l & 1) * 256u, x);
           tc::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) zs[j] = __uint_as_float(x[j]) + __ldg(bias + j);
+          for (int j = 0; j < CW; ++j) zs[j] = __uint_as_float(x[j]) + __ldg(bias + col0 + j);
 #pragma unroll
-          for (int kg = 0; kg < 2; ++kg) {
+          for (int kg = 0; kg < KGW; ++kg) {
             float v[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = zs[kg * 8 + i];
-            store8<NS>(A_small, sp, cfg.sa_off + (uint32_t)kg * 2048u + (uint32_t)r * 16u, v);
+            store8<NS>(A_small, sp, cfg.sa_off + (uint32_t)(group * KGW + kg) * 2048u + (uint32_t)r * 16u, v);
           }
-          signal_a(0);
         }
+        signal_a(0);
         release_d(l);
       }
       {                                                         // za1: swish -> 32-wide operand (aliases A_main)
         const int l = li++;
         const float* bias = bias_of(l);
         wait_d(l);
-        if (group == 0) {
-          uint32_t x[32];
-          tc::tmem_ld32(lane_addr + (uint32_t)(l & 1) * 256u, x);
+        {
+          uint32_t x[CW];
+          tmem_ldw<CW>(lane_addr + (uint32_t)(l & 1) * 256u, x);
           tc::tmem_ld_wait();
 #pragma unroll
-          for (int kg = 0; kg < 4; ++kg) {
+          for (int kg = 0; kg < KGW; ++kg) {
             float v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = swish_ns<NS>(__uint_as_float(x[kg * 8 + i]) + __ldg(bias + kg * 8 + i));
-            store8<NS>(A_main, MAIN_PLANE, (uint32_t)kg * 2048u + (uint32_t)r * 16u, v);
+            for (int i = 0; i < 8; ++i) v[i] = swish_ns<NS>(__uint_as_float(x[kg * 8 + i]) + __ldg(bias + col0 + kg * 8 + i));
+            store8<NS>(A_main, MAIN_PLANE, (uint32_t)(group * KGW + kg) * 2048u + (uint32_t)r * 16u, v);
           }
-          signal_a(0);
         }
+        signal_a(0);
         release_d(l);
       }
       {                                                         // za2 mu half: z = zs + za -> 16-wide operand
         const int l = li++;
         const float* bias = bias_of(l);
         wait_d(l);
-        if (group == 0) {
-          uint32_t x[16];
-          tc::tmem_ld16(lane_addr + (uint32_t)(l & 1) * 256u, x);
+        if (col0 < 16) {
+          uint32_t x[CW];
+          tmem_ldw<CW>(lane_addr + (uint32_t)(l & 1) * 256u, x);
           tc::tmem_ld_wait();
 #pragma unroll
-          for (int kg = 0; kg < 2; ++kg) {
+          for (int kg = 0; kg < KGW; ++kg) {
             float v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = zs[kg * 8 + i] + (__uint_as_float(x[kg * 8 + i]) + __ldg(bias + kg * 8 + i));
-            store8<NS>(A_main, MAIN_PLANE, (uint32_t)kg * 2048u + (uint32_t)r * 16u, v);
+            for (int i = 0; i < 8; ++i) v[i] = zs[kg * 8 + i] + (__uint_as_float(x[kg * 8 + i]) + __ldg(bias + col0 + kg * 8 + i));
+            store8<NS>(A_main, MAIN_PLANE, (uint32_t)(group * KGW + kg) * 2048u + (uint32_t)r * 16u, v);
           }
-          signal_a(0);
         }
+        signal_a(0);
         release_d(l);
       }
       epi_act256(li++, false);                                  // transition1
@@ -339,20 +352,14 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
         const float* bias = bias_of(l);
         const int np = sched.L[l].n;
         wait_d(l);
-        for (int c = group; c * 32 < np; c += NGROUPS) {
-          uint32_t x[32];
-          if (np - c * 32 >= 32) tc::tmem_ld32(lane_addr + (uint32_t)(l & 1) * 256u + (uint32_t)c * 32u, x);
-          else {
-            uint32_t y[16];
-            tc::tmem_ld16(lane_addr + (uint32_t)(l & 1) * 256u + (uint32_t)c * 32u, y);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) { x[j] = y[j]; x[16 + j] = 0u; }
-          }
+        for (int c = 0; c * 32 + col0 < np; ++c) {
+          uint32_t x[CW];
+          tmem_ldw<CW>(lane_addr + (uint32_t)(l & 1) * 256u + (uint32_t)c * 32u, x);
           tc::tmem_ld_wait();
           if (valid) {
             float* mrow = a.mean + ((size_t)e * B + grow) * S;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { int col = c * 32 + j; if (col < S) mrow[col] = __uint_as_float(x[j]) + __ldg(bias + col); }
+            for (int j = 0; j < CW; ++j) { const int col = c * 32 + col0 + j; if (col < S) mrow[col] = __uint_as_float(x[j]) + __ldg(bias + col); }
           }
         }
         release_d(l);
@@ -360,54 +367,114 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
     }
 
     // ---------------- ensemble statistics, noise, pick, penalty, termination ----------------
-    epi_bar();   // mean columns >= 32 were written by the other group's thread of this row
-    if (group == 0) {
-      int member = 0;
-      float d2[MB_E];
-#pragma unroll
-      for (int e = 0; e < MB_E; ++e) d2[e] = 0.f;
-      const unsigned long long gid = a.row_ids ? (unsigned long long)a.row_ids[valid ? grow : 0] : a.row0 + grow;
-      if (valid) {
-        member = a.idx ? (int)a.idx[grow] : (int)a.elites[philox_elite_slot(a.seed, a.step, gid, a.n_elites)];
-        float nrm[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int j = 0; j < S; ++j) {
-          if (!a.eps && (j & 3) == 0) philox_normal4(philox_noise_block(a.seed, a.step, gid, (unsigned)(j >> 2)), nrm);
+    // All epilogue warps take part: the NG threads of a row split its dims in blocks of 4 (block b -> group b % NG).
+    // A_main is free here (every dynamics MMA has completed) and serves as fp32 scratch.
+    // Element-wise over the tile's contiguous [128 x S] block of every member (coalesced loads; there is no
+    // L1 to speak of next to ~227 KB of shared memory), all epilogue threads in flight at once.  Per-row sums of
+    // squared deviations go through shared memory in member batches and are added in a fixed order (deterministic).
+    constexpr int NEPI = 32 * EPI_WARPS;
+    const int n_el = TM * S;
+    float* nobs_s = reinterpret_cast<float*>(A_main);                 // [128*S]   next_obs of the tile
+    int* member_s = reinterpret_cast<int*>(nobs_s + n_el);            // [128]     picked member per row
+    float* dsq_s = reinterpret_cast<float*>(member_s + TM) + TM;      // [batch][128*S] squared deviations
+    const int scratch_floats = (int)(NS * MAIN_PLANE / 4) - n_el - 2 * TM;
+    const int mbatch = min(MB_E, scratch_floats / n_el);
+    const int etid = tid;                                             // epilogue threads are 0 .. NEPI-1
+    if (tracer && group == 0) cfg.trace[79 * 8 + 0] = clock64();
+    if (etid < TM) {
+      int mem = 0;
+      if (row0 + etid < live) {
+        const size_t gr = (size_t)row0 + etid;
+        const unsigned long long gid = a.row_ids ? (unsigned long long)a.row_ids[gr] : a.row0 + gr;
+        mem = a.idx ? (int)a.idx[gr] : (int)a.elites[philox_elite_slot(a.seed, a.step, gid, a.n_elites)];
+      }
+      member_s[etid] = mem;
+    }
+    epi_bar<EPI_WARPS>();   // every mean column of this tile has been written; member_s is visible
+    if (tracer && group == 0) cfg.trace[79 * 8 + 1] = clock64();
+    float row_pmax = 0.f;
+    for (int e0 = 0; e0 < MB_E; e0 += mbatch) {
+#pragma unroll 2
+      for (int i = etid; i < n_el; i += NEPI) {
+        const int rr = i / S, j = i - rr * S;
+        const size_t gr = (size_t)row0 + rr;
+        if (row0 + rr < live) {
           float mv[MB_E], sum = 0.f;
 #pragma unroll
-          for (int e = 0; e < MB_E; ++e) { mv[e] = a.mean[((size_t)e * B + grow) * S + j]; sum += mv[e]; }
+          for (int e = 0; e < MB_E; ++e) { mv[e] = a.mean[((size_t)e * B + row0) * S + i]; sum += mv[e]; }
           const float mbar = sum / (float)MB_E;
+          const int member = member_s[rr];
           float ss = 0.f, mk = 0.f;
 #pragma unroll
           for (int e = 0; e < MB_E; ++e) {
-            const float d = mv[e] - mbar; ss = fmaf(d, d, ss);
-            if (j < S - 1) d2[e] = fmaf(d, d, d2[e]);            // quirk: last state dim excluded (:246)
+            const float d = mv[e] - mbar, dd = d * d;
+            ss += dd;
+            if (e >= e0 && e < e0 + mbatch) dsq_s[(e - e0) * n_el + i] = (j < S - 1) ? dd : 0.f;   // quirk: last dim excluded (:246)
             if (e == member) mk = mv[e];
           }
-          const float sd = sqrtf(ss / (float)(MB_E - 1));
-          const float ep = a.eps ? a.eps[((size_t)member * B + grow) * S + j] : nrm[j & 3];
-          a.next_obs[grow * S + j] = mk + ep * sd;
+          if (e0 == 0) {
+            const float sd = sqrtf(ss / (float)(MB_E - 1));
+            float ep;
+            if (a.eps) ep = a.eps[((size_t)member * B + gr) * S + j];
+            else {
+              const unsigned long long gid = a.row_ids ? (unsigned long long)a.row_ids[gr] : a.row0 + gr;
+              ep = philox_normal1(philox_noise_block(a.seed, a.step, gid, (unsigned)(j >> 2)), j & 3);
+            }
+            const float nv = mk + ep * sd;
+            a.next_obs[(size_t)row0 * S + i] = nv;
+            nobs_s[i] = nv;
+          }
         }
-        float pmax = 0.f;
-#pragma unroll
-        for (int e = 0; e < MB_E; ++e) pmax = fmaxf(pmax, sqrtf(d2[e]));
-        pen = pmax;
-        a.terminal[grow] = (unsigned char)mb_terminal(a.term_kind, a.next_obs + grow * S, S);
       }
-      // sas = [obs, act, next_obs, 0-pad] operand of the reward head (mobody_module.py:296)
-      const float* actp = cfg.has_policy ? a.act_out : a.act;
-      for (int k = 0; k < (int)cfg.sas_kp; ++k) {
-        float v = 0.f;
-        if (valid) {
-          if (k < S) v = __ldg(a.obs + grow * S + k);
-          else if (k < S + A) v = actp[grow * A + (k - S)];
-          else if (k < 2 * S + A) v = a.next_obs[grow * S + (k - S - A)];
+      epi_bar<EPI_WARPS>();
+      // (row, member) sums in a fixed order; group g takes members g, g+NG, ... of its row r
+      if (valid) {
+        for (int e = group; e < mbatch && e0 + e < MB_E; e += NG) {
+          const float* p = dsq_s + e * n_el + r * S;
+          float v0 = 0.f, v1 = 0.f;
+          int j = 0;
+          for (; j + 2 <= S - 1; j += 2) { v0 += p[j]; v1 += p[j + 1]; }
+          if (j < S - 1) v0 += p[j];
+          row_pmax = fmaxf(row_pmax, sqrtf(v0 + v1));
         }
-        store1<NS>(A_small, sp, (uint32_t)(k >> 3) * 2048u + (uint32_t)r * 16u + (uint32_t)(k & 7) * 2u, v);
+      }
+      if (e0 + mbatch < MB_E) epi_bar<EPI_WARPS>();   // dsq_s is rewritten by the next batch
+    }
+    if (tracer && group == 0) cfg.trace[79 * 8 + 2] = clock64();
+    red[group * 128 + r] = row_pmax;
+    if (group == 0 && valid) a.terminal[grow] = (unsigned char)mb_terminal(a.term_kind, nobs_s + r * S, S);
+    epi_bar<EPI_WARPS>();
+    if (tracer && group == 0) cfg.trace[79 * 8 + 3] = clock64();
+    if (group == 0 && valid) {
+      float pm = 0.f;
+#pragma unroll
+      for (int g2 = 0; g2 < NG; ++g2) pm = fmaxf(pm, red[g2 * 128 + r]);
+      pen = pm;
+    }
+    if (tracer && group == 0) cfg.trace[79 * 8 + 4] = clock64();
+    {   // sas = [obs, act, next_obs, 0-pad] operand of the reward head (mobody_module.py:296); aliases obs/sa planes
+      const float* actp = cfg.has_policy ? a.act_out : a.act;
+      for (int kg = group; kg < (int)cfg.sas_kp / 8; kg += NG) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int k = kg * 8 + i;
+          float t = 0.f;
+          if (valid) {
+            if (k < S) t = __ldg(a.obs + grow * S + k);
+            else if (k < S + A) t = actp[grow * A + (k - S)];
+            else if (k < 2 * S + A) t = nobs_s[r * S + (k - S - A)];
+          }
+          v[i] = t;
+        }
+        store8<NS>(A_small, sp, (uint32_t)kg * 2048u + (uint32_t)r * 16u, v);
       }
       tc::fence_proxy_async_smem();
     }
-    epi_bar();
-    for (int c = group; c * 32 < (int)cfg.sas_kp; c += NGROUPS) { __syncwarp(); if (lane == 0) tc::mbar_arrive(&bars->a_ready[c]); }
+    if (tracer && group == 0) cfg.trace[79 * 8 + 5] = clock64();
+    epi_bar<EPI_WARPS>();   // every sas plane is written (and nobs_s is no longer needed) before any chunk is announced
+    if (tracer && group == 0) cfg.trace[79 * 8 + 6] = clock64();
+    for (int c = 0; c * 32 < (int)cfg.sas_kp; ++c) { __syncwarp(); if (lane == 0) tc::mbar_arrive(&bars->a_ready[c]); }
 
     // ---------------- reward head, all 7 members (mobody_module.py:295-302; mean over members :236) ----------------
 #pragma unroll 1
@@ -415,34 +482,35 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
       epi_act256(li++, false);                                  // reward_model1
       {                                                         // reward_model2 -> swish -> dot reward_model3[:,0]
         const int l = li++;
-        const float* bias = bias_of(l);
+        const float* bias = bias_of(l) + col0;
         const float* w3 = dyn_bias + (size_t)e * cfg.member_b_floats + cfg.r3_b_off;
-        wait_d(l);
         const uint32_t t0 = lane_addr + (uint32_t)(l & 1) * 256u;
         float part = 0.f;
+        wait_d(l);
+        uint32_t x[CW], xn[CW];
+        tmem_ldw<CW>(t0, x);
 #pragma unroll 1
-        for (int cc = 0; cc < 8 / NGROUPS; ++cc) {
-          const int c = cc * NGROUPS + group;
-          uint32_t x[32];
-          tc::tmem_ld32(t0 + (uint32_t)c * 32u, x);
+        for (int c = 0; c < 8; ++c) {
           tc::tmem_ld_wait();
+          if (c + 1 < 8) tmem_ldw<CW>(t0 + (uint32_t)(c + 1) * 32u, xn);
+          float bv[CW], wv[CW];
+          ldbias(bias + c * 32, bv);
+          ldbias(w3 + col0 + c * 32, wv);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c * 32) + i);
-            const float4 w4 = __ldg(reinterpret_cast<const float4*>(w3 + c * 32) + i);
-            part = fmaf(swish_ns<NS>(__uint_as_float(x[4 * i + 0]) + b4.x), w4.x, part);
-            part = fmaf(swish_ns<NS>(__uint_as_float(x[4 * i + 1]) + b4.y), w4.y, part);
-            part = fmaf(swish_ns<NS>(__uint_as_float(x[4 * i + 2]) + b4.z), w4.z, part);
-            part = fmaf(swish_ns<NS>(__uint_as_float(x[4 * i + 3]) + b4.w), w4.w, part);
+          for (int i = 0; i < CW; ++i) part = fmaf(swish_ns<NS>(__uint_as_float(x[i]) + bv[i]), wv[i], part);
+          if (c + 1 < 8) {
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < CW; ++i) x[i] = xn[i];
           }
         }
         release_d(l);
-        red[((e & 1) * NGROUPS + group) * 128 + r] = part;
-        epi_bar();
+        red[((e & 1) * NG + group) * 128 + r] = part;
+        epi_bar<EPI_WARPS>();
         if (group == 0) {
           float sum = 0.f;
 #pragma unroll
-          for (int g2 = 0; g2 < NGROUPS; ++g2) sum += red[((e & 1) * NGROUPS + g2) * 128 + r];
+          for (int g2 = 0; g2 < NG; ++g2) sum += red[((e & 1) * NG + g2) * 128 + r];
           racc += sum + __ldg(w3 + 256);
         }
       }
@@ -522,6 +590,9 @@ const char* mb_tc_mlp_pack(const MlpPtrs& mp, int din, int dout, int ns, unsigne
   return nullptr;
 }
 
+static long long* g_tc_trace = nullptr;
+void mb_tc_set_trace(long long* buf) { g_tc_trace = buf; }
+
 const char* mb_tc_step_launch(const StepArgs& a, const unsigned char* dynb, const unsigned char* polb, int ns, cudaStream_t st) {
   if (a.B <= 0) return nullptr;
   const int S = a.S, A = a.A;
@@ -572,17 +643,21 @@ const char* mb_tc_step_launch(const StepArgs& a, const unsigned char* dynb, cons
   cfg.stage_bytes = (uint32_t)ns * 256u * 32u;
   cfg.dyn_bias_base = (uint32_t)DL.bias_base; cfg.member_b_floats = DL.member_b_floats; cfg.r3_b_off = DL.b_off[PK_COUNT];
   cfg.has_policy = has_policy ? 1 : 0;
-  const size_t fixed = (size_t)ns * tcs::MAIN_PLANE + (size_t)ns * cfg.small_plane + 2 * tcs::NGROUPS * 128 * sizeof(float) + sizeof(tcs::Bars) + 128;
+  cfg.trace = g_tc_trace;
+  const size_t fixed = (size_t)ns * tcs::MAIN_PLANE + (size_t)ns * cfg.small_plane + 2 * 4 * 128 * sizeof(float) + sizeof(tcs::Bars) + 128;
   const size_t budget = 227 * 1024;
   if (fixed + 2 * cfg.stage_bytes > budget) return "tensor-core step kernel: shared memory budget exceeded for this (S, A)";
   int nst = (int)((budget - fixed) / cfg.stage_bytes);
   if (nst > tcs::MAX_NST) nst = tcs::MAX_NST;
   cfg.nst = nst;
   const size_t bytes = fixed + (size_t)nst * cfg.stage_bytes;
-  auto kern = ns == 2 ? tcs::step_tc_kernel<2> : tcs::step_tc_kernel<1>;
+  static int ng = 0;
+  if (!ng) { const char* e = getenv("MOBODY_TC_GROUPS"); ng = (e && atoi(e) == 2) ? 2 : 4; }
+  auto kern = ns == 2 ? (ng == 2 ? tcs::step_tc_kernel<2, 2> : tcs::step_tc_kernel<2, 4>)
+                      : (ng == 2 ? tcs::step_tc_kernel<1, 2> : tcs::step_tc_kernel<1, 4>);
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
     return "cudaFuncSetAttribute(step_tc_kernel) failed";
   const int grid = (a.B + tcs::TM - 1) / tcs::TM;
-  kern<<<grid, tcs::NTHREADS, bytes, st>>>(a, dynb, polb ? polb : dynb, sc, cfg);
+  kern<<<grid, 32 * (4 * ng + 2), bytes, st>>>(a, dynb, polb ? polb : dynb, sc, cfg);
   return nullptr;
 }
