@@ -140,6 +140,29 @@ int mobody_gather_pos(const float* src, int w, int src_ld, const int* pos, const
 int mobody_gather_pos_i64(const long long* src, const int* pos, const int* m_dev, long long m_cap,
                           long long* dst, void* stream);
 
+/* ---- steady-state train step: twin-critic TD update + Polyak + Q-weighted BC actor update ----
+ * Replaces MOBODY.update_q_functions / update_target / update_policy / bc_loss and the three
+ * torch.optim.Adam steps inside MOBODY.train (algo/offline_offline/mobody.py:183-208, 246-276, 314-345,
+ * 541-573; math in SURVEY.md Appendix A.3; defaults advantage=0, scale_Q=1, q_weighted=1).
+ * `rows` is the concatenated batch [N, row_width] (src, tar, fake order; the first n_true rows are the
+ * src+tar rows of the BC term).  Parameters and Adam moments are updated IN PLACE in the live
+ * nn.Parameter storage.  scalars_out (device float[16]):
+ *   [0] q_loss [1] mean q1 [2] policy loss [3] bc loss [4] mean q(s,pi(s)) [5] mean|q(s,pi(s))|
+ *   [6] mean exp_adv [7] min exp_adv [8] max exp_adv [9] p_w [10] mean|q(s_t,a_t)| */
+typedef struct mobody_mlp_state { float* w[3]; float* b[3]; } mobody_mlp_state;   /* writable twin of mobody_mlp_params */
+typedef struct mobody_train_desc {
+  const float* rows; int N, n_true, S, A, row_width;
+  mobody_mlp_state policy, q1, q2, q1_target, q2_target;        /* parameters (updated in place)            */
+  mobody_mlp_state policy_m, policy_v, q1_m, q1_v, q2_m, q2_v;  /* Adam first / second moments              */
+  int t_q, t_pi;                 /* optimiser step counts AFTER this step (1-based), for bias correction    */
+  float gamma, tau, critic_lr, actor_lr, weight, bc_coef, max_action;
+  int nsplit;                    /* row splits of the weight-gradient GEMMs (1 for small batches)           */
+  void* workspace; long long workspace_bytes;   /* device scratch >= mobody_train_workspace_bytes(...)       */
+  float* scalars_out;            /* device float[16]                                                        */
+} mobody_train_desc;
+long long mobody_train_workspace_bytes(int N, int S, int A, int nsplit);
+int mobody_train_step(const mobody_train_desc* d, void* stream);
+
 /* ---- tensor-core weight images (precision MOBODY_PREC_BF16X2 / MOBODY_PREC_BF16) ----
  * The reference keeps weights as fp32 nn.Parameters (mobody_module.py:371-391, mobody.py:35-48); the
  * tcgen05 path consumes them as bf16 planes in the UMMA shared-memory layout.  Re-pack whenever the

@@ -43,6 +43,22 @@ class StepDesc(C.Structure):
     ]
 
 
+class MlpState(C.Structure):
+    _fields_ = [("w", C.c_void_p * 3), ("b", C.c_void_p * 3)]
+
+
+class TrainDesc(C.Structure):
+    _fields_ = [
+        ("rows", C.c_void_p), ("N", C.c_int), ("n_true", C.c_int), ("S", C.c_int), ("A", C.c_int), ("row_width", C.c_int),
+        ("policy", MlpState), ("q1", MlpState), ("q2", MlpState), ("q1_target", MlpState), ("q2_target", MlpState),
+        ("policy_m", MlpState), ("policy_v", MlpState), ("q1_m", MlpState), ("q1_v", MlpState), ("q2_m", MlpState), ("q2_v", MlpState),
+        ("t_q", C.c_int), ("t_pi", C.c_int),
+        ("gamma", C.c_float), ("tau", C.c_float), ("critic_lr", C.c_float), ("actor_lr", C.c_float), ("weight", C.c_float),
+        ("bc_coef", C.c_float), ("max_action", C.c_float),
+        ("nsplit", C.c_int), ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong), ("scalars_out", C.c_void_p),
+    ]
+
+
 _lib = None
 
 
@@ -80,6 +96,9 @@ def lib():
         L.mobody_mlp_pack_bytes.restype = C.c_longlong
         L.mobody_mlp_pack_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
         L.mobody_mlp_pack.argtypes = [C.POINTER(MlpParams), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.mobody_train_workspace_bytes.restype = C.c_longlong
+        L.mobody_train_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+        L.mobody_train_step.argtypes = [C.POINTER(TrainDesc), C.c_void_p]
         L.mobody_selftest_umma.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.mobody_selftest_umma2.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         if L.mobody_abi_version() != 1:
@@ -127,6 +146,23 @@ def dyn_params(model):
         d.w[i], d.b[i] = w.data_ptr(), b.data_ptr()
         keep += [w, b]
     return d, keep
+
+
+def mlp_state(tensors):
+    """MlpState from [w0, b0, w1, b1, w2, b2] contiguous fp32 CUDA tensors (parameters or Adam moments)."""
+    st = MlpState()
+    for i in range(3):
+        w, b = tensors[2 * i], tensors[2 * i + 1]
+        if w.dtype != torch.float32 or not w.is_cuda or not w.is_contiguous() or not b.is_contiguous():
+            raise RuntimeError("mobody_b200: train-step tensors must be contiguous fp32 CUDA tensors")
+        st.w[i], st.b[i] = w.data_ptr(), b.data_ptr()
+    return st
+
+
+def mlp_tensors(mlp):
+    """[w0, b0, w1, b1, w2, b2] parameter tensors (detached views of the live storage) of an MLPNetwork."""
+    net = mlp.network
+    return [t.detach() for li in (0, 2, 4) for t in (net[li].weight, net[li].bias)]
 
 
 def params_version(tensors):

@@ -30,6 +30,8 @@ const char* mb_umma_selftest_launch(const float* A, const float* B, int K, int N
 const char* mb_umma2_selftest_launch(const float* A, const float* B, int K, int N, int nsplit, float* D, cudaStream_t st);
 
 void mb_tc_set_trace(long long* buf);
+long long mb_train_workspace_bytes(int N, int S, int A, int nsplit);
+const char* mb_train_step_launch(const mobody_train_desc& d, cudaStream_t st);
 
 static thread_local char g_err[512] = "";
 
@@ -173,6 +175,25 @@ int mobody_gather_pos_i64(const long long* src, const int* pos, const int* m_dev
   if (m_cap < 0 || (m_cap > 0 && (!src || !pos || !dst))) return fail(MOBODY_ERR_ARG, "mobody_gather_pos_i64: bad arguments");
   mb_gather_pos_i64_launch(src, pos, m_dev, m_cap, dst, (cudaStream_t)stream);
   return check_launch("mobody_gather_pos_i64");
+}
+
+long long mobody_train_workspace_bytes(int N, int S, int A, int nsplit) {
+  if (N < 1 || S < 1 || A < 1 || nsplit < 1) return 0;
+  return mb_train_workspace_bytes(N, S, A, nsplit);
+}
+
+int mobody_train_step(const mobody_train_desc* d, void* stream) {
+  if (!d || !d->rows) return fail(MOBODY_ERR_ARG, "mobody_train_step: null descriptor / rows");
+  if (d->row_width != mobody_row_width(d->S, d->A)) return fail(MOBODY_ERR_ARG, "mobody_train_step: row_width does not match (S, A)");
+  const mobody_mlp_state* all[11] = {&d->policy, &d->q1, &d->q2, &d->q1_target, &d->q2_target, &d->policy_m, &d->policy_v,
+                                     &d->q1_m, &d->q1_v, &d->q2_m, &d->q2_v};
+  for (int i = 0; i < 11; ++i)
+    for (int j = 0; j < 3; ++j)
+      if (!all[i]->w[j] || !all[i]->b[j]) return fail(MOBODY_ERR_ARG, "mobody_train_step: null parameter / moment pointer");
+  if (d->t_q < 1 || d->t_pi < 1) return fail(MOBODY_ERR_ARG, "mobody_train_step: optimiser step counts are 1-based");
+  const char* err = mb_train_step_launch(*d, (cudaStream_t)stream);
+  if (err) return fail(MOBODY_ERR_UNSUPPORTED, err);
+  return check_launch("mobody_train_step");
 }
 
 static int nsplit_of(int precision) { return precision == MOBODY_PREC_BF16X2 ? 2 : precision == MOBODY_PREC_BF16 ? 1 : 0; }

@@ -14,139 +14,9 @@
 #include "common.cuh"
 #include "philox.cuh"
 #include "term.cuh"
+#include "simt_layers.cuh"
 
 namespace simt {
-
-constexpr int TM = 64;     // rows per CTA
-constexpr int NT = 256;    // threads per CTA
-constexpr int KC = 16;     // weight rows staged per chunk
-constexpr int H = MB_H;
-
-enum { ACT_NONE = 0, ACT_SWISH = 1, ACT_RELU = 2, ACT_TANH = 3 };
-
-__device__ __forceinline__ float apply_act(float v, int act, float scale) {
-  if (act == ACT_SWISH) return mb_swish(v);
-  if (act == ACT_RELU) return fmaxf(v, 0.0f);
-  if (act == ACT_TANH) return tanhf(v) * scale;
-  return v;
-}
-
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
-  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
-
-// Stage W rows [k0, k0+KC) x 256 columns into Wst[KC][256]; rows >= K are zero-filled.
-template <bool WT>
-__device__ __forceinline__ void stage_w(float* Wst, const float* __restrict__ Wg, int K, int k0) {
-  const int tid = threadIdx.x;
-  if (!WT) {   // Wg is [K][256] row-major: 16-byte async copies
-#pragma unroll
-    for (int i = 0; i < (KC * H / 4) / NT; ++i) {
-      int f = tid + NT * i;
-      int row = f >> 6, c4 = f & 63;
-      bool ok = (k0 + row) < K;
-      const float* src = ok ? (Wg + (size_t)(k0 + row) * H + c4 * 4) : Wg;
-      cp_async16(Wst + row * H + c4 * 4, src, ok ? 16 : 0);
-    }
-  } else {     // Wg is nn.Linear [256][K]: thread n copies K-run of column n (rows may be unaligned)
-    const float* src = Wg + (size_t)tid * K + k0;
-#pragma unroll
-    for (int kk = 0; kk < KC; ++kk) Wst[kk * H + tid] = (k0 + kk < K) ? __ldg(src + kk) : 0.0f;
-  }
-  cp_async_commit();
-}
-
-// Y[TM][256] = act(X[TM][K] * W + b).  X columns in [K, roundup16(K)) must be zero; ldx % 4 == 0.
-template <bool WT>
-__device__ void big_layer(const float* __restrict__ Xs, int ldx, int K, const float* __restrict__ Wg,
-                          const float* __restrict__ bias, float* __restrict__ Ys, float* Wst, int act) {
-  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-  float acc[8][8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
-  const int nchunks = (K + KC - 1) / KC;
-  stage_w<WT>(Wst, Wg, K, 0);
-  for (int c = 0; c < nchunks; ++c) {
-    float* cur = Wst + (c & 1) * (KC * H);
-    if (c + 1 < nchunks) { stage_w<WT>(Wst + ((c + 1) & 1) * (KC * H), Wg, K, (c + 1) * KC); cp_async_wait<1>(); }
-    else cp_async_wait<0>();
-    __syncthreads();
-    const float* xrow = Xs + (size_t)(ty * 8) * ldx + c * KC;
-#pragma unroll
-    for (int kk = 0; kk < KC; kk += 4) {
-      float4 xv[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) xv[i] = *reinterpret_cast<const float4*>(xrow + (size_t)i * ldx + kk);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float4 w0 = *reinterpret_cast<const float4*>(cur + (kk + q) * H + tx * 4);
-        float4 w1 = *reinterpret_cast<const float4*>(cur + (kk + q) * H + 128 + tx * 4);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float x = q == 0 ? xv[i].x : q == 1 ? xv[i].y : q == 2 ? xv[i].z : xv[i].w;
-          acc[i][0] = fmaf(x, w0.x, acc[i][0]); acc[i][1] = fmaf(x, w0.y, acc[i][1]);
-          acc[i][2] = fmaf(x, w0.z, acc[i][2]); acc[i][3] = fmaf(x, w0.w, acc[i][3]);
-          acc[i][4] = fmaf(x, w1.x, acc[i][4]); acc[i][5] = fmaf(x, w1.y, acc[i][5]);
-          acc[i][6] = fmaf(x, w1.z, acc[i][6]); acc[i][7] = fmaf(x, w1.w, acc[i][7]);
-        }
-      }
-    }
-    __syncthreads();
-  }
-  float4 b0 = *reinterpret_cast<const float4*>(bias + tx * 4);
-  float4 b1 = *reinterpret_cast<const float4*>(bias + 128 + tx * 4);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float4 o0, o1;
-    o0.x = apply_act(acc[i][0] + b0.x, act, 1.f); o0.y = apply_act(acc[i][1] + b0.y, act, 1.f);
-    o0.z = apply_act(acc[i][2] + b0.z, act, 1.f); o0.w = apply_act(acc[i][3] + b0.w, act, 1.f);
-    o1.x = apply_act(acc[i][4] + b1.x, act, 1.f); o1.y = apply_act(acc[i][5] + b1.y, act, 1.f);
-    o1.z = apply_act(acc[i][6] + b1.z, act, 1.f); o1.w = apply_act(acc[i][7] + b1.w, act, 1.f);
-    *reinterpret_cast<float4*>(Ys + (size_t)(ty * 8 + i) * H + tx * 4) = o0;
-    *reinterpret_cast<float4*>(Ys + (size_t)(ty * 8 + i) * H + 128 + tx * 4) = o1;
-  }
-  __syncthreads();
-}
-
-// Narrow layers (N <= 32 or so): one thread per (row, column).  W is [K][ldw] (or [N][K] if WT).
-template <bool WT>
-__device__ void small_layer(const float* __restrict__ Xs, int ldx, int K, const float* __restrict__ Wg, int ldw,
-                            const float* __restrict__ bias, int N, float* __restrict__ Ys, int ldy, int act,
-                            float scale) {
-  for (int idx = threadIdx.x; idx < TM * N; idx += NT) {
-    int r = idx / N, n = idx - r * N;
-    const float* x = Xs + (size_t)r * ldx;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int k = 0;
-    if (!WT) {
-      const float* w = Wg + n;
-      for (; k + 4 <= K; k += 4) {
-        a0 = fmaf(x[k], __ldg(w + (size_t)k * ldw), a0);
-        a1 = fmaf(x[k + 1], __ldg(w + (size_t)(k + 1) * ldw), a1);
-        a2 = fmaf(x[k + 2], __ldg(w + (size_t)(k + 2) * ldw), a2);
-        a3 = fmaf(x[k + 3], __ldg(w + (size_t)(k + 3) * ldw), a3);
-      }
-      for (; k < K; ++k) a0 = fmaf(x[k], __ldg(w + (size_t)k * ldw), a0);
-    } else {
-      const float* w = Wg + (size_t)n * ldw;
-      for (; k + 4 <= K; k += 4) {
-        a0 = fmaf(x[k], __ldg(w + k), a0); a1 = fmaf(x[k + 1], __ldg(w + k + 1), a1);
-        a2 = fmaf(x[k + 2], __ldg(w + k + 2), a2); a3 = fmaf(x[k + 3], __ldg(w + k + 3), a3);
-      }
-      for (; k < K; ++k) a0 = fmaf(x[k], __ldg(w + k), a0);
-    }
-    float v = ((a0 + a1) + (a2 + a3)) + __ldg(bias + n);
-    Ys[(size_t)r * ldy + n] = apply_act(v, act, scale);
-  }
-  __syncthreads();
-}
-
-__host__ __device__ inline int rup16(int x) { return (x + 15) & ~15; }
 
 struct Smem {   // carve-up of dynamic shared memory (floats)
   float *X0, *X1, *Wst, *obs, *act, *nobs, *sas, *sa, *g, *zs, *z, *racc, *pen;

@@ -1,0 +1,538 @@
+// Steady-state MOBODY.train step as fused fp32 forward/backward MLP kernels.
+//
+// Replaces, on packed batch rows [N, RW] = [state | action | next_state | reward | not_done | pad]
+// (rows ordered src, tar, fake; the first n_true rows are the "true" src+tar rows):
+//   update_q_functions + q backward          algo/offline_offline/mobody.py:189-208, 546-548
+//   update_target (Polyak, every step)        :183-187, 552
+//   update_policy + bc_loss + pi backward     :314-345, 246-276, 571-573
+//   torch.optim.Adam (lr, betas .9/.999, eps 1e-8) :127-131
+// Math: SURVEY.md Appendix A.3.  All networks are MLPNetwork (Linear-ReLU-Linear-ReLU-Linear, :35-48).
+//
+// A CTA owns a tile of 64 rows; hidden activations stay in shared memory for the whole
+// forward + backward-data chain of that tile (simt_layers.cuh).  Only what the weight-gradient
+// GEMMs need (H1, H2, dH1, dH2 per network) goes to HBM.  Weight gradients are row-reductions done
+// by a tiled GEMM over the whole batch (deterministic, no atomics), optionally split over row
+// ranges whose partials are summed inside the fused Adam(+Polyak) kernel.
+#include "simt_layers.cuh"
+#include "../../include/mobody_b200.h"
+#include <math.h>
+
+namespace trn {
+using namespace simt;
+
+struct CriticArgs {
+  const float* X; int N, S, A, rw;
+  MlpPtrs pi, q[2], qt[2];
+  float gamma, max_action;
+  float* Hq[2][2];     // [net][layer] relu activations of Q_k(s,a), [N][256]
+  float* Dq[2][2];     // [net][layer] dLoss/d(pre-activation), [N][256]
+  float* d3[2];        // [net] dLoss/dq_k, [N]
+  float* part;         // [n_tiles][4]: sum (q1-y)^2, sum (q2-y)^2, sum q1, sum q2
+};
+
+struct ActorArgs {
+  const float* X; int N, n_true, S, A, rw;
+  MlpPtrs pi, q[2];
+  float max_action;
+  float* Hp[2];        // relu activations of pi(s), [N][256]
+  float* api;          // pi(s), [N][A]
+  float* qpi;          // min_k Q_k(s, pi(s)), [N]
+  float* ga;           // d qpi / d action, [N][A]
+  float* qhat;         // min_k Q_k(s_t, a_t), [n_true]
+};
+
+__device__ __forceinline__ void store_tile(const float* __restrict__ Xs, float* __restrict__ g, int row0, int rows) {
+  // [64][256] smem tile -> global [N][256], 128-bit stores
+  for (int i = threadIdx.x; i < rows * (H / 4); i += NT) {
+    int r = i / (H / 4), c = i - r * (H / 4);
+    reinterpret_cast<float4*>(g + (size_t)(row0 + r) * H)[c] = reinterpret_cast<const float4*>(Xs + r * H)[c];
+  }
+}
+__device__ __forceinline__ void load_tile(float* __restrict__ Xs, const float* __restrict__ g, int row0, int rows) {
+  for (int i = threadIdx.x; i < TM * (H / 4); i += NT) {
+    int r = i / (H / 4), c = i - r * (H / 4);
+    reinterpret_cast<float4*>(Xs + r * H)[c] = r < rows ? reinterpret_cast<const float4*>(g + (size_t)(row0 + r) * H)[c]
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// out[r] = X1[r,:] . w + b   (last Linear of a Q network, one output)
+__device__ __forceinline__ void q_head(const float* __restrict__ X1, const float* __restrict__ w, const float* __restrict__ b,
+                                       float* __restrict__ out) {
+  const int r = threadIdx.x >> 2, q = threadIdx.x & 3;
+  const float* x = X1 + r * H;
+  float s = 0.f;
+  for (int k = q; k < H; k += 4) s = fmaf(x[k], __ldg(w + k), s);
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  if (q == 0) out[r] = s + __ldg(b);
+  __syncthreads();
+}
+
+// relu backward of the last Linear (one output): X1[r][n] = X1[r][n] > 0 ? g[r] * w[n] : 0   (in place)
+__device__ __forceinline__ void head_backward(float* __restrict__ X1, const float* __restrict__ w, const float* __restrict__ g) {
+  for (int i = threadIdx.x; i < TM * H; i += NT) {
+    int r = i >> 8, n = i & 255;
+    X1[i] = X1[i] > 0.f ? g[r] * __ldg(w + n) : 0.f;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(NT, 1) critic_kernel(CriticArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const int S = a.S, A = a.A, ldi = rup16(S + A);
+  float* X0 = sm; float* X1 = X0 + TM * H; float* Wst = X1 + TM * H;
+  float* in_s = Wst + 2 * KC * H;          // [64][ldi]  [s, a, 0]
+  float* in2_s = in_s + TM * ldi;          // [64][ldi]  [s', pi(s'), 0]
+  float* rew = in2_s + TM * ldi; float* nd = rew + TM; float* y = nd + TM;
+  float* qa = y + TM; float* qb = qa + TM; float* g3 = qb + TM; float* redbuf = g3 + TM;   // redbuf[8]
+  const int tid = threadIdx.x, row0 = blockIdx.x * TM, rows = min(TM, a.N - row0);
+  for (int i = tid; i < TM * ldi; i += NT) {
+    int r = i / ldi, j = i - r * ldi;
+    const float* x = a.X + (size_t)(row0 + r) * a.rw;
+    in_s[i] = (r < rows && j < S + A) ? x[j] : 0.f;
+    in2_s[i] = (r < rows && j < S) ? x[S + A + j] : 0.f;
+  }
+  if (tid < TM) {
+    const float* x = a.X + (size_t)(row0 + tid) * a.rw;
+    rew[tid] = tid < rows ? x[2 * S + A] : 0.f;
+    nd[tid] = tid < rows ? x[2 * S + A + 1] : 0.f;
+  }
+  __syncthreads();
+  // ---- TD target: y = r + nd * gamma * min_k Q'_k(s', pi(s'))   (no grad, :190-195) ----
+  big_layer<true>(in2_s, ldi, S, a.pi.w[0], a.pi.b[0], X0, Wst, ACT_RELU);
+  big_layer<true>(X0, H, H, a.pi.w[1], a.pi.b[1], X1, Wst, ACT_RELU);
+  small_layer<true>(X1, H, H, a.pi.w[2], H, a.pi.b[2], A, in2_s + S, ldi, ACT_TANH, a.max_action);
+  for (int k = 0; k < 2; ++k) {
+    big_layer<true>(in2_s, ldi, S + A, a.qt[k].w[0], a.qt[k].b[0], X0, Wst, ACT_RELU);
+    big_layer<true>(X0, H, H, a.qt[k].w[1], a.qt[k].b[1], X1, Wst, ACT_RELU);
+    q_head(X1, a.qt[k].w[2], a.qt[k].b[2], k == 0 ? qa : qb);
+  }
+  if (tid < TM) y[tid] = rew[tid] + nd[tid] * a.gamma * fminf(qa[tid], qb[tid]);
+  __syncthreads();
+  // ---- Q_k(s,a): forward, mse gradient, backward to the pre-activations (:196, 207) ----
+  float lsum[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k = 0; k < 2; ++k) {
+    big_layer<true>(in_s, ldi, S + A, a.q[k].w[0], a.q[k].b[0], X0, Wst, ACT_RELU);
+    store_tile(X0, a.Hq[k][0], row0, rows);
+    big_layer<true>(X0, H, H, a.q[k].w[1], a.q[k].b[1], X1, Wst, ACT_RELU);
+    store_tile(X1, a.Hq[k][1], row0, rows);
+    q_head(X1, a.q[k].w[2], a.q[k].b[2], qa);
+    if (tid < TM) {
+      const float d = tid < rows ? qa[tid] - y[tid] : 0.f;
+      g3[tid] = 2.0f * d / (float)a.N;                      // d mean((q-y)^2) / dq
+      if (tid < rows) a.d3[k][row0 + tid] = g3[tid];
+      lsum[k] = d * d; lsum[2 + k] = tid < rows ? qa[tid] : 0.f;
+    }
+    __syncthreads();
+    head_backward(X1, a.q[k].w[2], g3);                     // dH2 (masked)
+    store_tile(X1, a.Dq[k][1], row0, rows);
+    big_layer<false>(X1, H, H, a.q[k].w[1], nullptr, X0, Wst, ACT_MASK);   // dH1 = (dH2 W2) * 1[H1>0], in place on H1
+    store_tile(X0, a.Dq[k][0], row0, rows);
+    __syncthreads();
+  }
+  // tile partial sums in a fixed order (deterministic): threads 0..63 hold one row each
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float v = tid < TM ? lsum[c] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (tid < TM && (tid & 31) == 0) redbuf[(tid >> 5) * 4 + c] = v;
+  }
+  __syncthreads();
+  if (tid < 4) a.part[blockIdx.x * 4 + tid] = redbuf[tid] + redbuf[4 + tid];
+}
+
+__global__ void __launch_bounds__(NT, 1) actor_kernel(ActorArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const int S = a.S, A = a.A, ldi = rup16(S + A);
+  float* X0 = sm; float* X1 = X0 + TM * H; float* Wst = X1 + TM * H;
+  float* in_s = Wst + 2 * KC * H;          // [s, a_t, 0]
+  float* sap_s = in_s + TM * ldi;          // [s, pi(s), 0]
+  float* qv = sap_s + TM * ldi;            // [2][64]
+  float* ones = qv + 2 * TM;               // [64] upstream gradient 1
+  float* gak = ones + TM;                  // [2][64][A]
+  const int tid = threadIdx.x, row0 = blockIdx.x * TM, rows = min(TM, a.N - row0);
+  for (int i = tid; i < TM * ldi; i += NT) {
+    int r = i / ldi, j = i - r * ldi;
+    const float* x = a.X + (size_t)(row0 + r) * a.rw;
+    const float v = (r < rows && j < S + A) ? x[j] : 0.f;
+    in_s[i] = v;
+    sap_s[i] = j < S ? v : 0.f;
+  }
+  if (tid < TM) ones[tid] = 1.0f;
+  __syncthreads();
+  // ---- pi(s) (:315) ----
+  big_layer<true>(in_s, ldi, S, a.pi.w[0], a.pi.b[0], X0, Wst, ACT_RELU);
+  store_tile(X0, a.Hp[0], row0, rows);
+  big_layer<true>(X0, H, H, a.pi.w[1], a.pi.b[1], X1, Wst, ACT_RELU);
+  store_tile(X1, a.Hp[1], row0, rows);
+  small_layer<true>(X1, H, H, a.pi.w[2], H, a.pi.b[2], A, sap_s + S, ldi, ACT_TANH, a.max_action);
+  for (int i = tid; i < rows * A; i += NT) { int r = i / A, j = i - r * A; a.api[(size_t)(row0 + r) * A + j] = sap_s[r * ldi + S + j]; }
+  // ---- Q_k(s, pi(s)) and d q_k / d action (Q frozen, :316-317, 555-556) ----
+  for (int k = 0; k < 2; ++k) {
+    big_layer<true>(sap_s, ldi, S + A, a.q[k].w[0], a.q[k].b[0], X0, Wst, ACT_RELU);
+    big_layer<true>(X0, H, H, a.q[k].w[1], a.q[k].b[1], X1, Wst, ACT_RELU);
+    q_head(X1, a.q[k].w[2], a.q[k].b[2], qv + k * TM);
+    head_backward(X1, a.q[k].w[2], ones);
+    big_layer<false>(X1, H, H, a.q[k].w[1], nullptr, X0, Wst, ACT_MASK);
+    // d q / d a_j = sum_n dH1[n] * W1[n][S+j]
+    small_layer<false>(X0, H, H, a.q[k].w[0] + S, S + A, nullptr, A, gak + k * TM * A, A, ACT_NONE, 1.f);
+  }
+  for (int i = tid; i < rows * A; i += NT) {
+    int r = i / A;
+    const int sel = qv[r] <= qv[TM + r] ? 0 : 1;            // torch.min(q1, q2): gradient follows the smaller one
+    a.ga[(size_t)row0 * A + i] = gak[sel * TM * A + i];
+  }
+  if (tid < rows) a.qpi[row0 + tid] = fminf(qv[tid], qv[TM + tid]);
+  __syncthreads();
+  // ---- q_hat = min_k Q_k(s_t, a_t) on the true rows (no grad, :249-251) ----
+  if (row0 < a.n_true) {
+    for (int k = 0; k < 2; ++k) {
+      big_layer<true>(in_s, ldi, S + A, a.q[k].w[0], a.q[k].b[0], X0, Wst, ACT_RELU);
+      big_layer<true>(X0, H, H, a.q[k].w[1], a.q[k].b[1], X1, Wst, ACT_RELU);
+      q_head(X1, a.q[k].w[2], a.q[k].b[2], qv + k * TM);
+    }
+    if (tid < rows && row0 + tid < a.n_true) a.qhat[row0 + tid] = fminf(qv[tid], qv[TM + tid]);
+  }
+}
+
+// Scalars of the actor loss (single CTA, fixed-order reductions):
+//   out[0] = mean|qpi| (N rows)  out[1] = mean qpi  out[2] = mean|qhat| (n_true rows)
+//   out[3] = p_w = weight / mean|qpi|   out[4] = bc loss  out[5] = policy loss
+//   out[6..8] = mean / min / max of exp_adv   out[9] = q loss   out[10] = mean q1   (critic tile partials)
+struct ActorScalarArgs {
+  const float* qpi; const float* qhat; const float* api; const float* X; const float* part; int ntiles;
+  int N, n_true, S, A, rw; float weight, bc_coef; float* out;
+};
+__device__ float block_sum(float v, float* sh) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  float t = 0.f;
+  if (w == 0) {
+    t = lane < (int)(blockDim.x >> 5) ? sh[lane] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) sh[32] = t;
+  }
+  __syncthreads();
+  return sh[32];
+}
+__device__ float block_minmax(float v, float* sh, bool is_max) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { float u = __shfl_xor_sync(0xffffffffu, v, o); v = is_max ? fmaxf(v, u) : fminf(v, u); }
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    float t = lane < (int)(blockDim.x >> 5) ? sh[lane] : sh[0];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { float u = __shfl_xor_sync(0xffffffffu, t, o); t = is_max ? fmaxf(t, u) : fminf(t, u); }
+    if (lane == 0) sh[32] = t;
+  }
+  __syncthreads();
+  return sh[32];
+}
+__global__ void __launch_bounds__(1024) actor_scalar_kernel(ActorScalarArgs a) {
+  __shared__ float sh[33];
+  float s_abs = 0.f, s_q = 0.f;
+  for (int i = threadIdx.x; i < a.N; i += blockDim.x) { float q = a.qpi[i]; s_abs += fabsf(q); s_q += q; }
+  const float mean_abs = block_sum(s_abs, sh) / (float)a.N;
+  const float mean_q = block_sum(s_q, sh) / (float)a.N;
+  float s_h = 0.f;
+  for (int i = threadIdx.x; i < a.n_true; i += blockDim.x) s_h += fabsf(a.qhat[i]);
+  const float mean_h = block_sum(s_h, sh) / (float)a.n_true;
+  float s_w = 0.f, w_min = 3.4e38f, w_max = -3.4e38f, s_bc = 0.f;
+  for (int i = threadIdx.x; i < a.n_true; i += blockDim.x) {
+    const float w = fminf(expf(3.0f * (a.qhat[i] / mean_h)), 100.0f);      // :252-258
+    s_w += w; w_min = fminf(w_min, w); w_max = fmaxf(w_max, w);
+    const float* x = a.X + (size_t)i * a.rw + a.S;
+    float e = 0.f;
+    for (int j = 0; j < a.A; ++j) { float d = a.api[(size_t)i * a.A + j] - x[j]; e += d * d; }
+    s_bc += w * e;
+  }
+  const float mean_w = block_sum(s_w, sh) / (float)a.n_true;
+  const float bc = block_sum(s_bc, sh) / (float)((size_t)a.n_true * a.A);   // mean over rows AND action dims (:271)
+  const float wmn = block_minmax(w_min, sh, false), wmx = block_minmax(w_max, sh, true);
+  if (threadIdx.x == 0) {
+    float l = 0.f, q1s = 0.f;
+    for (int t = 0; t < a.ntiles; ++t) { l += a.part[t * 4] + a.part[t * 4 + 1]; q1s += a.part[t * 4 + 2]; }
+    a.out[0] = l / (float)a.N; a.out[1] = q1s / (float)a.N;                 // mse(q1,y) + mse(q2,y) (:207)
+    const float pw = a.weight / mean_abs;                                   // :318
+    a.out[2] = pw * (-mean_q) + a.bc_coef * bc;                             // :321, 330
+    a.out[3] = bc; a.out[4] = mean_q; a.out[5] = mean_abs;
+    a.out[6] = mean_w; a.out[7] = wmn; a.out[8] = wmx; a.out[9] = pw; a.out[10] = mean_h;
+  }
+}
+
+// d loss / d (pre-tanh policy output) for every row: [N][A]
+struct ActorGradArgs {
+  const float* scal; const float* ga; const float* api; const float* qhat; const float* X;
+  int N, n_true, S, A, rw; float bc_coef, max_action; float* d3p;
+};
+__global__ void actor_grad_kernel(ActorGradArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.N * a.A) return;
+  const int r = i / a.A, j = i - r * a.A;
+  const float pw = a.scal[9], mean_h = a.scal[10];
+  const float ap = a.api[i];
+  float g = -pw / (float)a.N * a.ga[i];                                     // d [pw * mean(-q)] / d a
+  if (r < a.n_true) {
+    const float w = fminf(expf(3.0f * (a.qhat[r] / mean_h)), 100.0f);
+    const float at = a.X[(size_t)r * a.rw + a.S + j];
+    g += a.bc_coef * w * 2.0f * (ap - at) / (float)((size_t)a.n_true * a.A);
+  }
+  const float t = ap / a.max_action;                                        // tanh(u)
+  a.d3p[i] = g * a.max_action * (1.0f - t * t);
+}
+
+// Policy backward to the pre-activations: dH2 = (d3p W3) * 1[H2>0], dH1 = (dH2 W2) * 1[H1>0]
+struct PolicyBwdArgs { const float* d3p; int N, A; MlpPtrs pi; const float* Hp[2]; float* Dp[2]; };
+__global__ void __launch_bounds__(NT, 1) policy_bwd_kernel(PolicyBwdArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  float* X0 = sm; float* X1 = X0 + TM * H; float* Wst = X1 + TM * H;
+  const int lda = rup16(a.A);
+  float* d3 = Wst + 2 * KC * H;            // [64][lda]
+  const int tid = threadIdx.x, row0 = blockIdx.x * TM, rows = min(TM, a.N - row0);
+  for (int i = tid; i < TM * lda; i += NT) {
+    int r = i / lda, j = i - r * lda;
+    d3[i] = (r < rows && j < a.A) ? a.d3p[(size_t)(row0 + r) * a.A + j] : 0.f;
+  }
+  load_tile(X1, a.Hp[1], row0, rows);
+  load_tile(X0, a.Hp[0], row0, rows);
+  __syncthreads();
+  big_layer<false>(d3, lda, a.A, a.pi.w[2], nullptr, X1, Wst, ACT_MASK);    // W3 is [A][256]: dH2[r][i] = sum_j d3[r][j] W3[j][i]
+  store_tile(X1, a.Dp[1], row0, rows);
+  big_layer<false>(X1, H, H, a.pi.w[1], nullptr, X0, Wst, ACT_MASK);
+  store_tile(X0, a.Dp[0], row0, rows);
+}
+
+// ---------------- weight gradients: dW[o][i] = sum_r D[r][o] X[r][i], db[o] = sum_r D[r][o] ----------------
+struct WgradJob { const float* D; int ldD; const float* X; int ldX; float* dW; float* db; int O, I; };
+struct WgradArgs { WgradJob job[6]; int njobs, N, nsplit; };
+constexpr int WT_O = 64, WT_I = 64, WT_R = 32;
+__global__ void __launch_bounds__(256) wgrad_kernel(WgradArgs a) {
+  const WgradJob jb = a.job[blockIdx.z];
+  const int tiles_i = (jb.I + WT_I - 1) / WT_I, tiles_o = (jb.O + WT_O - 1) / WT_O;
+  if ((int)blockIdx.x >= tiles_i * tiles_o) return;
+  const int o0 = (blockIdx.x / tiles_i) * WT_O, i0 = (blockIdx.x % tiles_i) * WT_I;
+  const int split = blockIdx.y;
+  const int rbeg = (int)((long long)a.N * split / a.nsplit), rend = (int)((long long)a.N * (split + 1) / a.nsplit);
+  __shared__ float Ds[WT_R][WT_O + 1], Xs[WT_R][WT_I + 1];
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;     // 16 x 16 threads, 4 x 4 outputs each
+  float acc[4][4] = {}, bacc[4] = {};
+  for (int r0 = rbeg; r0 < rend; r0 += WT_R) {
+    for (int t = tid; t < WT_R * WT_O; t += 256) {
+      int rr = t / WT_O, c = t - rr * WT_O;
+      Ds[rr][c] = (r0 + rr < rend && o0 + c < jb.O) ? jb.D[(size_t)(r0 + rr) * jb.ldD + o0 + c] : 0.f;
+    }
+    for (int t = tid; t < WT_R * WT_I; t += 256) {
+      int rr = t / WT_I, c = t - rr * WT_I;
+      Xs[rr][c] = (r0 + rr < rend && i0 + c < jb.I) ? jb.X[(size_t)(r0 + rr) * jb.ldX + i0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int rr = 0; rr < WT_R; ++rr) {
+      float d[4], x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { d[u] = Ds[rr][ty * 4 + u]; x[u] = Xs[rr][tx * 4 + u]; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        bacc[u] += d[u];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(d[u], x[v], acc[u][v]);
+      }
+    }
+    __syncthreads();
+  }
+  const size_t poff = (size_t)split * jb.O * jb.I;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int o = o0 + ty * 4 + u;
+    if (o >= jb.O) continue;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) { const int i = i0 + tx * 4 + v; if (i < jb.I) jb.dW[poff + (size_t)o * jb.I + i] = acc[u][v]; }
+    if (i0 == 0 && tx == 0) jb.db[(size_t)split * jb.O + o] = bacc[u];
+  }
+}
+
+// ---------------- fused Adam (+ Polyak target update) over a table of tensors ----------------
+struct AdamJob { float* p; const float* g; float* m; float* v; float* tgt; int n; };
+struct AdamArgs { AdamJob job[12]; int njobs, nsplit; float lr_over_bc1, inv_sqrt_bc2, b1, b2, eps, tau; };
+__global__ void adam_kernel(AdamArgs a) {
+  const AdamJob jb = a.job[blockIdx.y];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < jb.n; i += gridDim.x * blockDim.x) {
+    float g = 0.f;
+    for (int s = 0; s < a.nsplit; ++s) g += jb.g[(size_t)s * jb.n + i];      // fixed order over the row splits
+    const float m = a.b1 * jb.m[i] + (1.0f - a.b1) * g;
+    const float v = a.b2 * jb.v[i] + (1.0f - a.b2) * g * g;
+    jb.m[i] = m; jb.v[i] = v;
+    const float denom = sqrtf(v) * a.inv_sqrt_bc2 + a.eps;
+    const float p = jb.p[i] - a.lr_over_bc1 * (m / denom);
+    jb.p[i] = p;
+    if (jb.tgt) jb.tgt[i] = a.tau * p + (1.0f - a.tau) * jb.tgt[i];          // :183-187, uses the updated Q
+  }
+}
+
+}  // namespace trn
+
+// ---------------- host launchers ----------------
+static size_t tile_smem(int S, int A, int extra_floats) {
+  return (2 * (size_t)simt::TM * simt::H + 2 * simt::KC * simt::H + 2 * (size_t)simt::TM * simt::rup16(S + A) + extra_floats) * sizeof(float);
+}
+template <typename K> static const char* set_smem(K kern, size_t bytes) {
+  if (bytes > 227 * 1024) return "train step: shared memory budget exceeded for this (S, A)";
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return "cudaFuncSetAttribute failed";
+  return nullptr;
+}
+
+const char* mb_train_critic_launch(const trn::CriticArgs& a, cudaStream_t st) {
+  size_t bytes = tile_smem(a.S, a.A, 6 * simt::TM + 8);
+  if (const char* e = set_smem(trn::critic_kernel, bytes)) return e;
+  trn::critic_kernel<<<(a.N + simt::TM - 1) / simt::TM, simt::NT, bytes, st>>>(a);
+  return nullptr;
+}
+const char* mb_train_actor_launch(const trn::ActorArgs& a, cudaStream_t st) {
+  size_t bytes = tile_smem(a.S, a.A, 3 * simt::TM + 2 * simt::TM * a.A);
+  if (const char* e = set_smem(trn::actor_kernel, bytes)) return e;
+  trn::actor_kernel<<<(a.N + simt::TM - 1) / simt::TM, simt::NT, bytes, st>>>(a);
+  return nullptr;
+}
+const char* mb_train_actor_scalars_launch(const trn::ActorScalarArgs& a, cudaStream_t st) {
+  trn::actor_scalar_kernel<<<1, 1024, 0, st>>>(a);
+  return nullptr;
+}
+const char* mb_train_actor_grad_launch(const trn::ActorGradArgs& a, cudaStream_t st) {
+  int n = a.N * a.A;
+  trn::actor_grad_kernel<<<(n + 255) / 256, 256, 0, st>>>(a);
+  return nullptr;
+}
+const char* mb_train_policy_bwd_launch(const trn::PolicyBwdArgs& a, cudaStream_t st) {
+  size_t bytes = (2 * (size_t)simt::TM * simt::H + 2 * simt::KC * simt::H + (size_t)simt::TM * simt::rup16(a.A)) * sizeof(float);
+  if (const char* e = set_smem(trn::policy_bwd_kernel, bytes)) return e;
+  trn::policy_bwd_kernel<<<(a.N + simt::TM - 1) / simt::TM, simt::NT, bytes, st>>>(a);
+  return nullptr;
+}
+const char* mb_train_wgrad_launch(const trn::WgradArgs& a, cudaStream_t st) {
+  int maxt = 1;
+  for (int j = 0; j < a.njobs; ++j) {
+    int t = ((a.job[j].O + trn::WT_O - 1) / trn::WT_O) * ((a.job[j].I + trn::WT_I - 1) / trn::WT_I);
+    if (t > maxt) maxt = t;
+  }
+  trn::wgrad_kernel<<<dim3(maxt, a.nsplit, a.njobs), 256, 0, st>>>(a);
+  return nullptr;
+}
+const char* mb_train_adam_launch(const trn::AdamArgs& a, cudaStream_t st) {
+  int maxn = 1;
+  for (int j = 0; j < a.njobs; ++j) if (a.job[j].n > maxn) maxn = a.job[j].n;
+  int gx = (maxn + 255) / 256; if (gx > 64) gx = 64;
+  trn::adam_kernel<<<dim3(gx, a.njobs), 256, 0, st>>>(a);
+  return nullptr;
+}
+
+// ---------------- whole train step (C ABI: mobody_train_step) ----------------
+struct TrainWs {   // float offsets into the workspace
+  size_t Hq[2][2], Dq[2][2], d3[2], part, Hp[2], Dp[2], api, qpi, ga, qhat, d3p, scal, gq[2][6], gp[6], total;
+  int ntiles;
+};
+static TrainWs train_ws(int N, int S, int A, int nsplit) {
+  TrainWs w{}; size_t o = 0;
+  auto take = [&](size_t n) { size_t r = o; o += (n + 3) & ~(size_t)3; return r; };
+  const size_t act = (size_t)N * 256;
+  w.ntiles = (N + 63) / 64;
+  for (int k = 0; k < 2; ++k) for (int l = 0; l < 2; ++l) { w.Hq[k][l] = take(act); w.Dq[k][l] = take(act); }
+  for (int k = 0; k < 2; ++k) w.d3[k] = take(N);
+  w.part = take((size_t)w.ntiles * 4);
+  for (int l = 0; l < 2; ++l) { w.Hp[l] = take(act); w.Dp[l] = take(act); }
+  w.api = take((size_t)N * A); w.qpi = take(N); w.ga = take((size_t)N * A); w.qhat = take(N); w.d3p = take((size_t)N * A);
+  w.scal = take(16);
+  const size_t qn[6] = {(size_t)256 * (S + A), 256, 256 * 256, 256, 256, 1};       // w1 b1 w2 b2 w3 b3
+  const size_t pn[6] = {(size_t)256 * S, 256, 256 * 256, 256, (size_t)A * 256, (size_t)A};
+  for (int k = 0; k < 2; ++k) for (int t = 0; t < 6; ++t) w.gq[k][t] = take(qn[t] * nsplit);
+  for (int t = 0; t < 6; ++t) w.gp[t] = take(pn[t] * nsplit);
+  w.total = o;
+  return w;
+}
+long long mb_train_workspace_bytes(int N, int S, int A, int nsplit) { return (long long)train_ws(N, S, A, nsplit).total * 4; }
+
+static MlpPtrs as_ptrs(const mobody_mlp_state& s) { MlpPtrs p; for (int i = 0; i < 3; ++i) { p.w[i] = s.w[i]; p.b[i] = s.b[i]; } return p; }
+
+const char* mb_train_step_launch(const mobody_train_desc& d, cudaStream_t st) {
+  const int N = d.N, S = d.S, A = d.A, ns = d.nsplit;
+  if (N < 1 || d.n_true < 1 || d.n_true > N || S < 1 || S > 64 || A < 1 || A > 32 || ns < 1 || ns > 64) return "train step: bad N/n_true/S/A/nsplit";
+  const TrainWs w = train_ws(N, S, A, ns);
+  if (!d.workspace || d.workspace_bytes < (long long)w.total * 4) return "train step: workspace too small";
+  float* ws = (float*)d.workspace;
+  const mobody_mlp_state* qs[2] = {&d.q1, &d.q2};
+  const mobody_mlp_state* qts[2] = {&d.q1_target, &d.q2_target};
+  const mobody_mlp_state* qm[2] = {&d.q1_m, &d.q2_m};
+  const mobody_mlp_state* qv[2] = {&d.q1_v, &d.q2_v};
+  // ---- critic: TD target, forward, backward-data ----
+  trn::CriticArgs c{};
+  c.X = d.rows; c.N = N; c.S = S; c.A = A; c.rw = d.row_width; c.pi = as_ptrs(d.policy);
+  for (int k = 0; k < 2; ++k) {
+    c.q[k] = as_ptrs(*qs[k]); c.qt[k] = as_ptrs(*qts[k]);
+    for (int l = 0; l < 2; ++l) { c.Hq[k][l] = ws + w.Hq[k][l]; c.Dq[k][l] = ws + w.Dq[k][l]; }
+    c.d3[k] = ws + w.d3[k];
+  }
+  c.gamma = d.gamma; c.max_action = d.max_action; c.part = ws + w.part;
+  if (const char* e = mb_train_critic_launch(c, st)) return e;
+  // ---- critic weight gradients + Adam + Polyak ----
+  trn::WgradArgs g{}; g.N = N; g.nsplit = ns; g.njobs = 6;
+  for (int k = 0; k < 2; ++k) {
+    g.job[3 * k + 0] = {c.Dq[k][0], 256, d.rows, d.row_width, ws + w.gq[k][0], ws + w.gq[k][1], 256, S + A};
+    g.job[3 * k + 1] = {c.Dq[k][1], 256, c.Hq[k][0], 256, ws + w.gq[k][2], ws + w.gq[k][3], 256, 256};
+    g.job[3 * k + 2] = {c.d3[k], 1, c.Hq[k][1], 256, ws + w.gq[k][4], ws + w.gq[k][5], 1, 256};
+  }
+  if (const char* e = mb_train_wgrad_launch(g, st)) return e;
+  trn::AdamArgs ad{}; ad.nsplit = ns; ad.b1 = 0.9f; ad.b2 = 0.999f; ad.eps = 1e-8f; ad.tau = d.tau; ad.njobs = 12;
+  {
+    const double bc1 = 1.0 - pow(0.9, (double)d.t_q), bc2 = 1.0 - pow(0.999, (double)d.t_q);
+    ad.lr_over_bc1 = (float)(d.critic_lr / bc1); ad.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+    const int qn[6] = {256 * (S + A), 256, 256 * 256, 256, 256, 1};
+    for (int k = 0; k < 2; ++k)
+      for (int t = 0; t < 6; ++t) {
+        const int li = t >> 1; const bool isw = (t & 1) == 0;
+        ad.job[6 * k + t] = {isw ? qs[k]->w[li] : qs[k]->b[li], ws + w.gq[k][t], isw ? qm[k]->w[li] : qm[k]->b[li],
+                             isw ? qv[k]->w[li] : qv[k]->b[li], isw ? qts[k]->w[li] : qts[k]->b[li], qn[t]};
+      }
+  }
+  if (const char* e = mb_train_adam_launch(ad, st)) return e;
+  // ---- actor: forward through the UPDATED, frozen Q; loss scalars; backward ----
+  trn::ActorArgs ac{};
+  ac.X = d.rows; ac.N = N; ac.n_true = d.n_true; ac.S = S; ac.A = A; ac.rw = d.row_width; ac.pi = as_ptrs(d.policy);
+  ac.q[0] = as_ptrs(d.q1); ac.q[1] = as_ptrs(d.q2); ac.max_action = d.max_action;
+  ac.Hp[0] = ws + w.Hp[0]; ac.Hp[1] = ws + w.Hp[1]; ac.api = ws + w.api; ac.qpi = ws + w.qpi; ac.ga = ws + w.ga; ac.qhat = ws + w.qhat;
+  if (const char* e = mb_train_actor_launch(ac, st)) return e;
+  trn::ActorScalarArgs sc{ac.qpi, ac.qhat, ac.api, d.rows, ws + w.part, w.ntiles, N, d.n_true, S, A, d.row_width, d.weight, d.bc_coef, ws + w.scal};
+  if (const char* e = mb_train_actor_scalars_launch(sc, st)) return e;
+  trn::ActorGradArgs ag{ws + w.scal, ac.ga, ac.api, ac.qhat, d.rows, N, d.n_true, S, A, d.row_width, d.bc_coef, d.max_action, ws + w.d3p};
+  if (const char* e = mb_train_actor_grad_launch(ag, st)) return e;
+  trn::PolicyBwdArgs pb{}; pb.d3p = ws + w.d3p; pb.N = N; pb.A = A; pb.pi = ac.pi;
+  pb.Hp[0] = ac.Hp[0]; pb.Hp[1] = ac.Hp[1]; pb.Dp[0] = ws + w.Dp[0]; pb.Dp[1] = ws + w.Dp[1];
+  if (const char* e = mb_train_policy_bwd_launch(pb, st)) return e;
+  trn::WgradArgs gp{}; gp.N = N; gp.nsplit = ns; gp.njobs = 3;
+  gp.job[0] = {pb.Dp[0], 256, d.rows, d.row_width, ws + w.gp[0], ws + w.gp[1], 256, S};
+  gp.job[1] = {pb.Dp[1], 256, ac.Hp[0], 256, ws + w.gp[2], ws + w.gp[3], 256, 256};
+  gp.job[2] = {pb.d3p, A, ac.Hp[1], 256, ws + w.gp[4], ws + w.gp[5], A, 256};
+  if (const char* e = mb_train_wgrad_launch(gp, st)) return e;
+  trn::AdamArgs ap{}; ap.nsplit = ns; ap.b1 = 0.9f; ap.b2 = 0.999f; ap.eps = 1e-8f; ap.tau = 0.f; ap.njobs = 6;
+  {
+    const double bc1 = 1.0 - pow(0.9, (double)d.t_pi), bc2 = 1.0 - pow(0.999, (double)d.t_pi);
+    ap.lr_over_bc1 = (float)(d.actor_lr / bc1); ap.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+    const int pn[6] = {256 * S, 256, 256 * 256, 256, A * 256, A};
+    for (int t = 0; t < 6; ++t) {
+      const int li = t >> 1; const bool isw = (t & 1) == 0;
+      ap.job[t] = {isw ? d.policy.w[li] : d.policy.b[li], ws + w.gp[t], isw ? d.policy_m.w[li] : d.policy_m.b[li],
+                   isw ? d.policy_v.w[li] : d.policy_v.b[li], nullptr, pn[t]};
+    }
+  }
+  if (const char* e = mb_train_adam_launch(ap, st)) return e;
+  if (d.scalars_out) cudaMemcpyAsync(d.scalars_out, ws + w.scal, 16 * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  return nullptr;
+}

@@ -84,7 +84,7 @@ class MOBODYEnsembleDynamics(object):
         return self._dyn_pack[1]
 
     def _packed_policy(self, policy, mp, keep):
-        key = (self.precision,) + _ffi.params_version(keep)
+        key = (self.precision, getattr(policy, "_b200_epoch", 0)) + _ffi.params_version(keep)
         ent = self._pol_pack.get(id(policy))
         if ent is None or ent[0] != key:
             S, A, prec = self.model.obs_dim, self.model.action_dim, _ffi.PREC[self.precision]

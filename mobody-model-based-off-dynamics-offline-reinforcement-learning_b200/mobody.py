@@ -82,6 +82,14 @@ class MOBODY(object):
         self.v_func = ValueFunc(S, A).to(self.device)
         self.policy = Policy(S, A, config["max_action"]).to(self.device)
         self.dynamics = None                                     # injected by the caller (train_mobody.py:888)
+        # Adam moments of the fused train step (torch.optim.Adam equivalents of mobody.py:127-131)
+        z = lambda mlp: [torch.zeros_like(t) for t in _ffi.mlp_tensors(mlp)]      # noqa: E731
+        self._adam = {"pi": (z(self.policy.network), z(self.policy.network)),
+                      "q1": (z(self.q_funcs.network1), z(self.q_funcs.network1)),
+                      "q2": (z(self.q_funcs.network2), z(self.q_funcs.network2))}
+        self._t_q = self._t_pi = 0
+        self._train_ws = None
+        self._scalars = torch.zeros(16, dtype=torch.float32, device=self.device)
 
     def select_action(self, state, policy, cuda=False):          # mobody.py:138-144
         with torch.no_grad():
@@ -169,6 +177,111 @@ class MOBODY(object):
             print("filtered rollout", info["kept"], info["num_transitions"])     # mobody.py:653
         return {k: v.cpu() for k, v in out.items()}, {"num_transitions": info["num_transitions"],
                                                       "reward_mean": info["reward_mean"]}
+
+    # ------------------------------------------------------------------ train step
+    def train_on_rows(self, rows, n_true):
+        """One fused critic + Polyak + actor update on packed batch rows [N, RW] (device, rows ordered
+        src, tar, fake; the first ``n_true`` rows are the src+tar rows of the BC term).  Asynchronous:
+        losses land in ``self._scalars`` (device).  mobody.py:541-573."""
+        cfg = self.config
+        if cfg.get("advantage", 0) or not cfg.get("scale_Q", 1) or not cfg.get("q_weighted", 1):
+            raise NotImplementedError("mobody_b200 implements the default advantage=0, scale_Q=1, q_weighted=1 update")
+        S, A = cfg["state_dim"], cfg["action_dim"]
+        N = rows.shape[0]
+        nsplit = 1 if N <= 1024 else min(16, N // 512)
+        lib = _ffi.lib()
+        need = int(lib.mobody_train_workspace_bytes(N, S, A, nsplit))
+        if self._train_ws is None or self._train_ws.numel() < need:
+            self._train_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        self._t_q += 1; self._t_pi += 1
+        d = _ffi.TrainDesc()
+        d.rows, d.N, d.n_true, d.S, d.A, d.row_width = _ffi.ptr(rows), N, int(n_true), S, A, rows.shape[1]
+        qt = self.target_q_funcs
+        d.policy = _ffi.mlp_state(_ffi.mlp_tensors(self.policy.network))
+        d.q1, d.q2 = _ffi.mlp_state(_ffi.mlp_tensors(self.q_funcs.network1)), _ffi.mlp_state(_ffi.mlp_tensors(self.q_funcs.network2))
+        d.q1_target, d.q2_target = _ffi.mlp_state(_ffi.mlp_tensors(qt.network1)), _ffi.mlp_state(_ffi.mlp_tensors(qt.network2))
+        d.policy_m, d.policy_v = _ffi.mlp_state(self._adam["pi"][0]), _ffi.mlp_state(self._adam["pi"][1])
+        d.q1_m, d.q1_v = _ffi.mlp_state(self._adam["q1"][0]), _ffi.mlp_state(self._adam["q1"][1])
+        d.q2_m, d.q2_v = _ffi.mlp_state(self._adam["q2"][0]), _ffi.mlp_state(self._adam["q2"][1])
+        d.t_q, d.t_pi = self._t_q, self._t_pi
+        d.gamma, d.tau = float(self.discount), float(self.tau)
+        d.critic_lr, d.actor_lr = float(cfg["critic_lr"]), float(cfg["actor_lr"])
+        d.weight, d.bc_coef, d.max_action = float(cfg["weight"]), float(cfg.get("bc_coef", 1.0)), float(cfg["max_action"])
+        d.nsplit, d.workspace, d.workspace_bytes = nsplit, _ffi.ptr(self._train_ws), self._train_ws.numel()
+        d.scalars_out = _ffi.ptr(self._scalars)
+        _ffi.check(lib.mobody_train_step(C.byref(d), _ffi.stream_ptr(self.device)))
+        # parameters were updated in place behind autograd's version counters: bump the epoch that the
+        # tensor-core weight images (dynamics._packed_policy) are keyed on
+        self.policy.network._b200_epoch = getattr(self.policy.network, "_b200_epoch", 0) + 1
+        return self._scalars
+
+    def loss_scalars(self):
+        """Host copy of the last step's diagnostics (one D2H sync; call sparingly)."""
+        v = self._scalars.cpu().tolist()
+        return dict(q_loss=v[0], q1_mean=v[1], pi_loss=v[2], bc_loss=v[3], q_policy=v[4], q_abs_mean=v[5],
+                    w_mean=v[6], w_min=v[7], w_max=v[8], p_w=v[9])
+
+    def train(self, src_replay_buffer, tar_replay_buffer, batch_size=128, writer=None, wandbrun=None, *, _inject=None):
+        """Reference signature (mobody.py:347-578).  ``_inject`` optionally supplies the buffer indices the
+        reference would draw with np.random.randint, as a dict {src, tar, fake, src_init, tar_init}."""
+        cfg = self.config
+        self.total_it += 1
+        self.src_replay_buffer, self.tar_replay_buffer = src_replay_buffer, tar_replay_buffer
+        if self.penalty_type == "dara":
+            raise NotImplementedError("the DARA classifier prologue (mobody.py:146-181, 354-381) is outside the hot path "
+                                      "built so far (SURVEY.md section 8f rank 1); use penalty_type 'par' or 'none'")
+        inj = _inject or {}
+        S, A = cfg["state_dim"], cfg["action_dim"]
+        n_src, n_tar = int(cfg["src_ratio"] * batch_size), int(cfg["trg_ratio"] * batch_size)
+        n_fake = int(cfg["fake_batch_scale"] * batch_size) if cfg["fake_batch_scale"] != 0 else 0
+        RW = src_replay_buffer.RW
+        rows = torch.empty(n_src + n_tar + n_fake, RW, dtype=torch.float32, device=self.device)
+        src_replay_buffer.sample_rows(n_src, inj.get("src"), out=rows[:n_src])                        # :399
+        tar_replay_buffer.sample_rows(n_tar, inj.get("tar"), out=rows[n_src:n_src + n_tar])           # :400
+        if self.penalty_type == "par":                                                                # :428-434
+            s, a_, ns = rows[:n_src, :S].contiguous(), rows[:n_src, S:S + A].contiguous(), rows[:n_src, S + A:2 * S + A]
+            pred, _, _, _ = self.dynamics.step(s, a_)
+            rows[:n_src, 2 * S + A] -= cfg["penalty_coef"] * ((ns - pred) ** 2).mean(1)
+        if (self.total_it - 1) % 5000 == 0:                                                           # :441-475 refresh
+            self.refresh_fake_buffer(src_replay_buffer, tar_replay_buffer, inj)
+        if n_fake:
+            self.fake_replay_buffer.sample_rows(n_fake, inj.get("fake"), out=rows[n_src + n_tar:])    # :524
+        self.train_on_rows(rows, n_src + n_tar)
+        if self.total_it % 1000 == 0 and cfg.get("q_weighted", 1):                                    # :269-270
+            v = self.loss_scalars()
+            print(v["w_mean"], v["w_min"], v["w_max"])
+        if writer is not None and self.total_it % 5000 == 0:                                          # :203-205, 272-274, 332-344
+            v = self.loss_scalars()
+            writer.add_scalar("train/q1", v["q1_mean"], self.total_it)
+            writer.add_scalar("train/exp_adv", v["w_mean"], self.total_it)
+            writer.add_scalar("train/bc_loss", v["bc_loss"], self.total_it)
+            writer.add_scalar("train/q_policy", v["q_policy"], self.total_it)
+            writer.add_scalar("train/policy_loss", v["pi_loss"], self.total_it)
+            if wandbrun is not None:
+                wandbrun.log({"train/q1": v["q1_mean"], "train/q_policy": v["q_policy"], "train/policy_loss": v["pi_loss"]},
+                             step=self.total_it)
+
+    def refresh_fake_buffer(self, src_buf, tar_buf, inj=None):
+        """Synthetic-data refresh (mobody.py:441-475): two policy rollouts through the learned target dynamics and one
+        dynamics step on dataset (s, a) pairs, all inserted into the fake buffer without leaving the device."""
+        cfg, inj = self.config, inj or {}
+        S, A = cfg["state_dim"], cfg["action_dim"]
+        src_rows = src_buf.sample_rows(50000, inj.get("src_init"))                                    # :442 (sizes hard-coded there)
+        tar_rows = tar_buf.sample_rows(2000, inj.get("tar_init"))                                     # :443
+        for init, T in ((src_rows[:, :S].contiguous(), cfg["src_rollout_length"]), (tar_rows[:, :S].contiguous(), cfg["trg_rollout_length"])):
+            out, info = self.rollout_device(init, T)                                                  # :444, 453
+            if cfg.get("filter_bad_rollout", 1) and out is not None:
+                print("filtered rollout", info["kept"], info["num_transitions"])                     # :653
+            self.fake_replay_buffer.add_batch(out)
+        if cfg.get("use_src_sa_to_get_target_next_state", 1):                                         # :460-475
+            s, a_ = src_rows[:, :S].contiguous(), src_rows[:, S:S + A].contiguous()
+            ws = StepWorkspace(s.shape[0], S, A, self.device)
+            self.dynamics.launch_step(s, a_, ws)
+            keep = (ws.penalty < cfg["env_filter"]).squeeze(1)                                        # strict < here (quirk 5)
+            self.fake_replay_buffer.add_batch({"obss": s[keep], "next_obss": ws.next_obs[keep], "actions": a_[keep],
+                                               "rewards": ws.reward[keep], "terminals": ws.terminal[keep].float()[:, None]})
+        if cfg.get("rollout_from_src", 0):
+            raise NotImplementedError("rollout_from_src (mobody.py:479-513) needs the DARA classifier (SURVEY.md section 8f)")
 
     # ------------------------------------------------------------------ checkpoints
     def save(self, filename):                                    # mobody.py:584-588 (optimizer files: see train step)
