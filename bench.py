@@ -111,6 +111,58 @@ def cpu_rollout_rate(n_rows, threads, repeats=1):
     return info["num_transitions"] / best, best
 
 
+def synth_buffer_dict(n, seed):
+    rng = np.random.default_rng(seed)
+    return dict(observations=synth_obs(n, seed), actions=rng.uniform(-1, 1, (n, A)).astype(np.float32),
+                next_observations=synth_obs(n, seed + 1), rewards=rng.standard_normal(n).astype(np.float32),
+                terminals=np.zeros(n, bool))
+
+
+def cpu_train_rate(batch, threads, steps=5):
+    """Oracle steady-state MOBODY.train step (3 buffer gathers + critic + Polyak + actor) on host cores."""
+    from oracle import mobody_oracle as M
+    torch.set_num_threads(threads)
+    ag = M.AgentState(S, A, 1)
+    bufs = []
+    for n, sd in ((200_000, 1), (20_000, 2), (50_000, 3)):
+        d = synth_buffer_dict(n, sd)
+        b = M.RingBuffer(S, A, n)
+        b.state[:] = torch.from_numpy(d["observations"]); b.action[:] = torch.from_numpy(d["actions"])
+        b.next_state[:] = torch.from_numpy(d["next_observations"]); b.reward[:, 0] = torch.from_numpy(d["rewards"]); b.not_done[:] = 1.0
+        b.size = n; bufs.append(b)
+    cfg = dict(gamma=0.99, tau=0.005, actor_lr=3e-4, critic_lr=3e-4, weight=2.5, bc_coef=1.0, max_action=1.0)
+    ns = (batch, batch, batch // 2)
+    t0 = None
+    for it in range(steps + 2):
+        if it == 2:
+            t0 = time.perf_counter()
+        parts = [b.gather(np.random.randint(0, b.size, n)) for b, n in zip(bufs, ns)]
+        M.train_step(ag, tuple(torch.cat([p[c] for p in parts], 0) for c in range(5)), 2 * batch, cfg)
+    return steps / (time.perf_counter() - t0)
+
+
+def gpu_train_rate(mb, dev, batch, steps=300):
+    """MOBODY.train steady state through the public API: device-resident buffers, Philox indices, fused step."""
+    from helpers import cuda_agent
+    ag, _ = cuda_agent(S, A, 2, penalty_type="none")
+    src, tar = mb.ReplayBuffer(S, A, dev), mb.ReplayBuffer(S, A, dev)
+    src.convert_D4RL(synth_buffer_dict(200_000, 1)); tar.convert_D4RL(synth_buffer_dict(20_000, 2))
+    ag.fake_replay_buffer.convert_D4RL(synth_buffer_dict(50_000, 3))
+    ag.total_it = 1                               # steady state: the 5000-step refresh is measured by the rollout metric
+    for _ in range(20):
+        ag.train(src, tar, batch)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+        ag.train(src, tar, batch)
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    return steps / (e0.elapsed_time(e1) * 1e-3), steps / wall
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -276,8 +328,15 @@ def main():
                      "flop_per_transition": flop},
         "clocks": clocks, "wall_s": wall,
     }
+    # second BASELINE metric: Q-weighted BC updates/sec (one update = one steady-state MOBODY.train step)
+    upd_dev, upd_wall = gpu_train_rate(mb, dev, 128)
+    line["train"] = {"metric": "Q-weighted BC updates/sec", "value": upd_wall, "unit": "updates/s", "device_only": upd_dev,
+                     "config": {"workload": f"MOBODY.train steady state, batch 128 (128 src + 128 tar + 64 fake rows), S{S}/A{A}",
+                                "launches_per_update": 12, "dtype": "f32"}}
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
+        line["train"]["cpu_baseline"] = {"value": cpu_train_rate(128, cores), "unit": "updates/s", "cores": cores, "kind": "port",
+                                         "sample": "oracle.train_step incl. 3 buffer gathers, 5 steps after 2 warm-up"}
         n = 20_000
         rate, dt = cpu_rollout_rate(n, cores, repeats=2)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",

@@ -40,44 +40,54 @@ __device__ __forceinline__ void stage_w(float* Wst, const float* __restrict__ Wg
       const float* src = ok ? (Wg + (size_t)(k0 + row) * H + c4 * 4) : Wg;
       cp_async16(Wst + row * H + c4 * 4, src, ok ? 16 : 0);
     }
-  } else {     // Wg is nn.Linear [256][K]: thread n copies K-run of column n (rows may be unaligned)
+  } else {     // Wg is nn.Linear [256][K]: thread n copies the K-run of output n (4-byte async copies, rows may be unaligned)
     const float* src = Wg + (size_t)tid * K + k0;
 #pragma unroll
-    for (int kk = 0; kk < KC; ++kk) Wst[kk * H + tid] = (k0 + kk < K) ? __ldg(src + kk) : 0.0f;
+    for (int kk = 0; kk < KC; ++kk) {
+      const bool ok = (k0 + kk) < K;
+      unsigned d = (unsigned)__cvta_generic_to_shared(Wst + kk * H + tid);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(ok ? src + kk : Wg), "r"(ok ? 4 : 0));
+    }
   }
   cp_async_commit();
 }
 
 // Y[TM][256] = act(X[TM][K] * W + b).  X columns in [K, roundup16(K)) must be zero; ldx % 4 == 0.
 // act == ACT_MASK: Y = (X W) where Y's previous content is > 0, else 0 (relu backward, in place on Ys); bias unused.
-template <bool WT>
+// RPT = rows per thread; the CTA's row tile is 8 * RPT rows (64 by default, 16 for small batches).
+// NSTG = depth of the weight-chunk ring in Wst (NSTG * KC * 256 floats); NSTG - 1 chunks are prefetched ahead.
+template <bool WT, int RPT = 8, int NSTG = 2>
 __device__ void big_layer(const float* __restrict__ Xs, int ldx, int K, const float* __restrict__ Wg,
                           const float* __restrict__ bias, float* __restrict__ Ys, float* Wst, int act) {
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-  float acc[8][8];
+  float acc[RPT][8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < RPT; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
   const int nchunks = (K + KC - 1) / KC;
-  stage_w<WT>(Wst, Wg, K, 0);
+#pragma unroll
+  for (int p = 0; p < NSTG - 1; ++p) {                       // prologue: one commit group per chunk, possibly empty
+    if (p < nchunks) stage_w<WT>(Wst + p * (KC * H), Wg, K, p * KC); else cp_async_commit();
+  }
   for (int c = 0; c < nchunks; ++c) {
-    float* cur = Wst + (c & 1) * (KC * H);
-    if (c + 1 < nchunks) { stage_w<WT>(Wst + ((c + 1) & 1) * (KC * H), Wg, K, (c + 1) * KC); cp_async_wait<1>(); }
-    else cp_async_wait<0>();
+    float* cur = Wst + (c % NSTG) * (KC * H);
+    if (c + NSTG - 1 < nchunks) stage_w<WT>(Wst + ((c + NSTG - 1) % NSTG) * (KC * H), Wg, K, (c + NSTG - 1) * KC);
+    else cp_async_commit();
+    cp_async_wait<NSTG - 1>();                               // chunk c has landed (groups retire in order)
     __syncthreads();
-    const float* xrow = Xs + (size_t)(ty * 8) * ldx + c * KC;
+    const float* xrow = Xs + (size_t)(ty * RPT) * ldx + c * KC;
 #pragma unroll
     for (int kk = 0; kk < KC; kk += 4) {
-      float4 xv[8];
+      float4 xv[RPT];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) xv[i] = *reinterpret_cast<const float4*>(xrow + (size_t)i * ldx + kk);
+      for (int i = 0; i < RPT; ++i) xv[i] = *reinterpret_cast<const float4*>(xrow + (size_t)i * ldx + kk);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         float4 w0 = *reinterpret_cast<const float4*>(cur + (kk + q) * H + tx * 4);
         float4 w1 = *reinterpret_cast<const float4*>(cur + (kk + q) * H + 128 + tx * 4);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < RPT; ++i) {
           float x = q == 0 ? xv[i].x : q == 1 ? xv[i].y : q == 2 ? xv[i].z : xv[i].w;
           acc[i][0] = fmaf(x, w0.x, acc[i][0]); acc[i][1] = fmaf(x, w0.y, acc[i][1]);
           acc[i][2] = fmaf(x, w0.z, acc[i][2]); acc[i][3] = fmaf(x, w0.w, acc[i][3]);
@@ -90,9 +100,9 @@ __device__ void big_layer(const float* __restrict__ Xs, int ldx, int K, const fl
   }
   if (act == ACT_MASK) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4* p0 = reinterpret_cast<float4*>(Ys + (size_t)(ty * 8 + i) * H + tx * 4);
-      float4* p1 = reinterpret_cast<float4*>(Ys + (size_t)(ty * 8 + i) * H + 128 + tx * 4);
+    for (int i = 0; i < RPT; ++i) {
+      float4* p0 = reinterpret_cast<float4*>(Ys + (size_t)(ty * RPT + i) * H + tx * 4);
+      float4* p1 = reinterpret_cast<float4*>(Ys + (size_t)(ty * RPT + i) * H + 128 + tx * 4);
       const float4 m0 = *p0, m1 = *p1;
       *p0 = make_float4(m0.x > 0.f ? acc[i][0] : 0.f, m0.y > 0.f ? acc[i][1] : 0.f, m0.z > 0.f ? acc[i][2] : 0.f, m0.w > 0.f ? acc[i][3] : 0.f);
       *p1 = make_float4(m1.x > 0.f ? acc[i][4] : 0.f, m1.y > 0.f ? acc[i][5] : 0.f, m1.z > 0.f ? acc[i][6] : 0.f, m1.w > 0.f ? acc[i][7] : 0.f);
@@ -103,24 +113,24 @@ __device__ void big_layer(const float* __restrict__ Xs, int ldx, int K, const fl
   float4 b0 = *reinterpret_cast<const float4*>(bias + tx * 4);
   float4 b1 = *reinterpret_cast<const float4*>(bias + 128 + tx * 4);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
+  for (int i = 0; i < RPT; ++i) {
     float4 o0, o1;
     o0.x = apply_act(acc[i][0] + b0.x, act, 1.f); o0.y = apply_act(acc[i][1] + b0.y, act, 1.f);
     o0.z = apply_act(acc[i][2] + b0.z, act, 1.f); o0.w = apply_act(acc[i][3] + b0.w, act, 1.f);
     o1.x = apply_act(acc[i][4] + b1.x, act, 1.f); o1.y = apply_act(acc[i][5] + b1.y, act, 1.f);
     o1.z = apply_act(acc[i][6] + b1.z, act, 1.f); o1.w = apply_act(acc[i][7] + b1.w, act, 1.f);
-    *reinterpret_cast<float4*>(Ys + (size_t)(ty * 8 + i) * H + tx * 4) = o0;
-    *reinterpret_cast<float4*>(Ys + (size_t)(ty * 8 + i) * H + 128 + tx * 4) = o1;
+    *reinterpret_cast<float4*>(Ys + (size_t)(ty * RPT + i) * H + tx * 4) = o0;
+    *reinterpret_cast<float4*>(Ys + (size_t)(ty * RPT + i) * H + 128 + tx * 4) = o1;
   }
   __syncthreads();
 }
 
 // Narrow layers (N <= 32 or so): one thread per (row, column).  W is [K][ldw] (or [N][K] if WT).
-template <bool WT>
+template <bool WT, int RPT = 8>
 __device__ void small_layer(const float* __restrict__ Xs, int ldx, int K, const float* __restrict__ Wg, int ldw,
                             const float* __restrict__ bias, int N, float* __restrict__ Ys, int ldy, int act,
                             float scale) {
-  for (int idx = threadIdx.x; idx < TM * N; idx += NT) {
+  for (int idx = threadIdx.x; idx < 8 * RPT * N; idx += NT) {
     int r = idx / N, n = idx - r * N;
     const float* x = Xs + (size_t)r * ldx;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;

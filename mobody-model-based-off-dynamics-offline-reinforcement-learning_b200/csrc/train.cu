@@ -41,6 +41,7 @@ struct ActorArgs {
   float* qhat;         // min_k Q_k(s_t, a_t), [n_true]
 };
 
+template <int TMv>
 __device__ __forceinline__ void store_tile(const float* __restrict__ Xs, float* __restrict__ g, int row0, int rows) {
   // [64][256] smem tile -> global [N][256], 128-bit stores
   for (int i = threadIdx.x; i < rows * (H / 4); i += NT) {
@@ -48,8 +49,9 @@ __device__ __forceinline__ void store_tile(const float* __restrict__ Xs, float* 
     reinterpret_cast<float4*>(g + (size_t)(row0 + r) * H)[c] = reinterpret_cast<const float4*>(Xs + r * H)[c];
   }
 }
+template <int TMv>
 __device__ __forceinline__ void load_tile(float* __restrict__ Xs, const float* __restrict__ g, int row0, int rows) {
-  for (int i = threadIdx.x; i < TM * (H / 4); i += NT) {
+  for (int i = threadIdx.x; i < TMv * (H / 4); i += NT) {
     int r = i / (H / 4), c = i - r * (H / 4);
     reinterpret_cast<float4*>(Xs + r * H)[c] = r < rows ? reinterpret_cast<const float4*>(g + (size_t)(row0 + r) * H)[c]
                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -57,32 +59,37 @@ __device__ __forceinline__ void load_tile(float* __restrict__ Xs, const float* _
 }
 
 // out[r] = X1[r,:] . w + b   (last Linear of a Q network, one output)
+template <int TMv>
 __device__ __forceinline__ void q_head(const float* __restrict__ X1, const float* __restrict__ w, const float* __restrict__ b,
                                        float* __restrict__ out) {
-  const int r = threadIdx.x >> 2, q = threadIdx.x & 3;
+  constexpr int TPR = NT / TMv;                               // threads per row (4 for 64 rows, 16 for 16 rows)
+  const int r = threadIdx.x / TPR, q = threadIdx.x % TPR;
   const float* x = X1 + r * H;
   float s = 0.f;
-  for (int k = q; k < H; k += 4) s = fmaf(x[k], __ldg(w + k), s);
-  s += __shfl_xor_sync(0xffffffffu, s, 1);
-  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  for (int k = q; k < H; k += TPR) s = fmaf(x[k], __ldg(w + k), s);
+#pragma unroll
+  for (int o = 1; o < TPR; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if (q == 0) out[r] = s + __ldg(b);
   __syncthreads();
 }
 
 // relu backward of the last Linear (one output): X1[r][n] = X1[r][n] > 0 ? g[r] * w[n] : 0   (in place)
+template <int TMv>
 __device__ __forceinline__ void head_backward(float* __restrict__ X1, const float* __restrict__ w, const float* __restrict__ g) {
-  for (int i = threadIdx.x; i < TM * H; i += NT) {
+  for (int i = threadIdx.x; i < TMv * H; i += NT) {
     int r = i >> 8, n = i & 255;
     X1[i] = X1[i] > 0.f ? g[r] * __ldg(w + n) : 0.f;
   }
   __syncthreads();
 }
 
+template <int RPT>
 __global__ void __launch_bounds__(NT, 1) critic_kernel(CriticArgs a) {
+  constexpr int TM = 8 * RPT;
   extern __shared__ __align__(16) float sm[];
   const int S = a.S, A = a.A, ldi = rup16(S + A);
   float* X0 = sm; float* X1 = X0 + TM * H; float* Wst = X1 + TM * H;
-  float* in_s = Wst + 2 * KC * H;          // [64][ldi]  [s, a, 0]
+  float* in_s = Wst + (RPT == 8 ? 2 : 6) * KC * H;   // [TM][ldi]  [s, a, 0]
   float* in2_s = in_s + TM * ldi;          // [64][ldi]  [s', pi(s'), 0]
   float* rew = in2_s + TM * ldi; float* nd = rew + TM; float* y = nd + TM;
   float* qa = y + TM; float* qb = qa + TM; float* g3 = qb + TM; float* redbuf = g3 + TM;   // redbuf[8]
@@ -100,24 +107,24 @@ __global__ void __launch_bounds__(NT, 1) critic_kernel(CriticArgs a) {
   }
   __syncthreads();
   // ---- TD target: y = r + nd * gamma * min_k Q'_k(s', pi(s'))   (no grad, :190-195) ----
-  big_layer<true>(in2_s, ldi, S, a.pi.w[0], a.pi.b[0], X0, Wst, ACT_RELU);
-  big_layer<true>(X0, H, H, a.pi.w[1], a.pi.b[1], X1, Wst, ACT_RELU);
-  small_layer<true>(X1, H, H, a.pi.w[2], H, a.pi.b[2], A, in2_s + S, ldi, ACT_TANH, a.max_action);
+  big_layer<true, RPT, (RPT == 8 ? 2 : 6)>(in2_s, ldi, S, a.pi.w[0], a.pi.b[0], X0, Wst, ACT_RELU);
+  big_layer<true, RPT, (RPT == 8 ? 2 : 6)>(X0, H, H, a.pi.w[1], a.pi.b[1], X1, Wst, ACT_RELU);
+  small_layer<true, RPT>(X1, H, H, a.pi.w[2], H, a.pi.b[2], A, in2_s + S, ldi, ACT_TANH, a.max_action);
   for (int k = 0; k < 2; ++k) {
-    big_layer<true>(in2_s, ldi, S + A, a.qt[k].w[0], a.qt[k].b[0], X0, Wst, ACT_RELU);
-    big_layer<true>(X0, H, H, a.qt[k].w[1], a.qt[k].b[1], X1, Wst, ACT_RELU);
-    q_head(X1, a.qt[k].w[2], a.qt[k].b[2], k == 0 ? qa : qb);
+    big_layer<true, RPT, (RPT == 8 ? 2 : 6)>(in2_s, ldi, S + A, a.qt[k].w[0], a.qt[k].b[0], X0, Wst, ACT_RELU);
+    big_layer<true, RPT, (RPT == 8 ? 2 : 6)>(X0, H, H, a.qt[k].w[1], a.qt[k].b[1], X1, Wst, ACT_RELU);
+    q_head<TM>(X1, a.qt[k].w[2], a.qt[k].b[2], k == 0 ? qa : qb);
   }
   if (tid < TM) y[tid] = rew[tid] + nd[tid] * a.gamma * fminf(qa[tid], qb[tid]);
   __syncthreads();
   // ---- Q_k(s,a): forward, mse gradient, backward to the pre-activations (:196, 207) ----
   float lsum[4] = {0.f, 0.f, 0.f, 0.f};
   for (int k = 0; k < 2; ++k) {
-    big_layer<true>(in_s, ldi, S + A, a.q[k].w[0], a.q[k].b[0], X0, Wst, ACT_RELU);
-    store_tile(X0, a.Hq[k][0], row0, rows);
-    big_layer<true>(X0, H, H, a.q[k].w[1], a.q[k].b[1], X1, Wst, ACT_RELU);
-    store_tile(X1, a.Hq[k][1], row0, rows);
-    q_head(X1, a.q[k].w[2], a.q[k].b[2], qa);
+    big_layer<true, RPT, (RPT == 8 ? 2 : 6)>(in_s, ldi, S + A, a.q[k].w[0], a.q[k].b[0], X0, Wst, ACT_RELU);
+    store_tile<TM>(X0, a.Hq[k][0], row0, rows);
+    big_layer<true, RPT, (RPT == 8 ? 2 : 6)>(X0, H, H, a.q[k].w[1], a.q[k].b[1], X1, Wst, ACT_RELU);
+    store_tile<TM>(X1, a.Hq[k][1], row0, rows);
+    q_head<TM>(X1, a.q[k].w[2], a.q[k].b[2], qa);
     if (tid < TM) {
       const float d = tid < rows ? qa[tid] - y[tid] : 0.f;
       g3[tid] = 2.0f * d / (float)a.N;                      // d mean((q-y)^2) / dq
@@ -125,13 +132,15 @@ __global__ void __launch_bounds__(NT, 1) critic_kernel(CriticArgs a) {
       lsum[k] = d * d; lsum[2 + k] = tid < rows ? qa[tid] : 0.f;
     }
     __syncthreads();
-    head_backward(X1, a.q[k].w[2], g3);                     // dH2 (masked)
-    store_tile(X1, a.Dq[k][1], row0, rows);
-    big_layer<false>(X1, H, H, a.q[k].w[1], nullptr, X0, Wst, ACT_MASK);   // dH1 = (dH2 W2) * 1[H1>0], in place on H1
-    store_tile(X0, a.Dq[k][0], row0, rows);
+    head_backward<TM>(X1, a.q[k].w[2], g3);                     // dH2 (masked)
+    store_tile<TM>(X1, a.Dq[k][1], row0, rows);
+    big_layer<false, RPT, (RPT == 8 ? 2 : 6)>(X1, H, H, a.q[k].w[1], nullptr, X0, Wst, ACT_MASK);   // dH1 = (dH2 W2) * 1[H1>0], in place on H1
+    store_tile<TM>(X0, a.Dq[k][0], row0, rows);
     __syncthreads();
   }
-  // tile partial sums in a fixed order (deterministic): threads 0..63 hold one row each
+  // tile partial sums in a fixed order (deterministic): threads 0..TM-1 hold one row each
+  if (tid < 8) redbuf[tid] = 0.f;
+  __syncthreads();
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     float v = tid < TM ? lsum[c] : 0.f;
@@ -143,11 +152,13 @@ __global__ void __launch_bounds__(NT, 1) critic_kernel(CriticArgs a) {
   if (tid < 4) a.part[blockIdx.x * 4 + tid] = redbuf[tid] + redbuf[4 + tid];
 }
 
+template <int RPT>
 __global__ void __launch_bounds__(NT, 1) actor_kernel(ActorArgs a) {
+  constexpr int TM = 8 * RPT;
   extern __shared__ __align__(16) float sm[];
   const int S = a.S, A = a.A, ldi = rup16(S + A);
   float* X0 = sm; float* X1 = X0 + TM * H; float* Wst = X1 + TM * H;
-  float* in_s = Wst + 2 * KC * H;          // [s, a_t, 0]
+  float* in_s = Wst + (RPT == 8 ? 2 : 6) * KC * H;   // [s, a_t, 0]
   float* sap_s = in_s + TM * ldi;          // [s, pi(s), 0]
   float* qv = sap_s + TM * ldi;            // [2][64]
   float* ones = qv + 2 * TM;               // [64] upstream gradient 1
@@ -163,21 +174,21 @@ __global__ void __launch_bounds__(NT, 1) actor_kernel(ActorArgs a) {
   if (tid < TM) ones[tid] = 1.0f;
   __syncthreads();
   // ---- pi(s) (:315) ----
-  big_layer<true>(in_s, ldi, S, a.pi.w[0], a.pi.b[0], X0, Wst, ACT_RELU);
-  store_tile(X0, a.Hp[0], row0, rows);
-  big_layer<true>(X0, H, H, a.pi.w[1], a.pi.b[1], X1, Wst, ACT_RELU);
-  store_tile(X1, a.Hp[1], row0, rows);
-  small_layer<true>(X1, H, H, a.pi.w[2], H, a.pi.b[2], A, sap_s + S, ldi, ACT_TANH, a.max_action);
+  big_layer<true, RPT, (RPT == 8 ? 2 : 6)>(in_s, ldi, S, a.pi.w[0], a.pi.b[0], X0, Wst, ACT_RELU);
+  store_tile<TM>(X0, a.Hp[0], row0, rows);
+  big_layer<true, RPT, (RPT == 8 ? 2 : 6)>(X0, H, H, a.pi.w[1], a.pi.b[1], X1, Wst, ACT_RELU);
+  store_tile<TM>(X1, a.Hp[1], row0, rows);
+  small_layer<true, RPT>(X1, H, H, a.pi.w[2], H, a.pi.b[2], A, sap_s + S, ldi, ACT_TANH, a.max_action);
   for (int i = tid; i < rows * A; i += NT) { int r = i / A, j = i - r * A; a.api[(size_t)(row0 + r) * A + j] = sap_s[r * ldi + S + j]; }
   // ---- Q_k(s, pi(s)) and d q_k / d action (Q frozen, :316-317, 555-556) ----
   for (int k = 0; k < 2; ++k) {
-    big_layer<true>(sap_s, ldi, S + A, a.q[k].w[0], a.q[k].b[0], X0, Wst, ACT_RELU);
-    big_layer<true>(X0, H, H, a.q[k].w[1], a.q[k].b[1], X1, Wst, ACT_RELU);
-    q_head(X1, a.q[k].w[2], a.q[k].b[2], qv + k * TM);
-    head_backward(X1, a.q[k].w[2], ones);
-    big_layer<false>(X1, H, H, a.q[k].w[1], nullptr, X0, Wst, ACT_MASK);
+    big_layer<true, RPT, (RPT == 8 ? 2 : 6)>(sap_s, ldi, S + A, a.q[k].w[0], a.q[k].b[0], X0, Wst, ACT_RELU);
+    big_layer<true, RPT, (RPT == 8 ? 2 : 6)>(X0, H, H, a.q[k].w[1], a.q[k].b[1], X1, Wst, ACT_RELU);
+    q_head<TM>(X1, a.q[k].w[2], a.q[k].b[2], qv + k * TM);
+    head_backward<TM>(X1, a.q[k].w[2], ones);
+    big_layer<false, RPT, (RPT == 8 ? 2 : 6)>(X1, H, H, a.q[k].w[1], nullptr, X0, Wst, ACT_MASK);
     // d q / d a_j = sum_n dH1[n] * W1[n][S+j]
-    small_layer<false>(X0, H, H, a.q[k].w[0] + S, S + A, nullptr, A, gak + k * TM * A, A, ACT_NONE, 1.f);
+    small_layer<false, RPT>(X0, H, H, a.q[k].w[0] + S, S + A, nullptr, A, gak + k * TM * A, A, ACT_NONE, 1.f);
   }
   for (int i = tid; i < rows * A; i += NT) {
     int r = i / A;
@@ -189,9 +200,9 @@ __global__ void __launch_bounds__(NT, 1) actor_kernel(ActorArgs a) {
   // ---- q_hat = min_k Q_k(s_t, a_t) on the true rows (no grad, :249-251) ----
   if (row0 < a.n_true) {
     for (int k = 0; k < 2; ++k) {
-      big_layer<true>(in_s, ldi, S + A, a.q[k].w[0], a.q[k].b[0], X0, Wst, ACT_RELU);
-      big_layer<true>(X0, H, H, a.q[k].w[1], a.q[k].b[1], X1, Wst, ACT_RELU);
-      q_head(X1, a.q[k].w[2], a.q[k].b[2], qv + k * TM);
+      big_layer<true, RPT, (RPT == 8 ? 2 : 6)>(in_s, ldi, S + A, a.q[k].w[0], a.q[k].b[0], X0, Wst, ACT_RELU);
+      big_layer<true, RPT, (RPT == 8 ? 2 : 6)>(X0, H, H, a.q[k].w[1], a.q[k].b[1], X1, Wst, ACT_RELU);
+      q_head<TM>(X1, a.q[k].w[2], a.q[k].b[2], qv + k * TM);
     }
     if (tid < rows && row0 + tid < a.n_true) a.qhat[row0 + tid] = fminf(qv[tid], qv[TM + tid]);
   }
@@ -293,23 +304,25 @@ __global__ void actor_grad_kernel(ActorGradArgs a) {
 
 // Policy backward to the pre-activations: dH2 = (d3p W3) * 1[H2>0], dH1 = (dH2 W2) * 1[H1>0]
 struct PolicyBwdArgs { const float* d3p; int N, A; MlpPtrs pi; const float* Hp[2]; float* Dp[2]; };
+template <int RPT>
 __global__ void __launch_bounds__(NT, 1) policy_bwd_kernel(PolicyBwdArgs a) {
+  constexpr int TM = 8 * RPT;
   extern __shared__ __align__(16) float sm[];
   float* X0 = sm; float* X1 = X0 + TM * H; float* Wst = X1 + TM * H;
   const int lda = rup16(a.A);
-  float* d3 = Wst + 2 * KC * H;            // [64][lda]
+  float* d3 = Wst + (RPT == 8 ? 2 : 6) * KC * H;     // [TM][lda]
   const int tid = threadIdx.x, row0 = blockIdx.x * TM, rows = min(TM, a.N - row0);
   for (int i = tid; i < TM * lda; i += NT) {
     int r = i / lda, j = i - r * lda;
     d3[i] = (r < rows && j < a.A) ? a.d3p[(size_t)(row0 + r) * a.A + j] : 0.f;
   }
-  load_tile(X1, a.Hp[1], row0, rows);
-  load_tile(X0, a.Hp[0], row0, rows);
+  load_tile<TM>(X1, a.Hp[1], row0, rows);
+  load_tile<TM>(X0, a.Hp[0], row0, rows);
   __syncthreads();
-  big_layer<false>(d3, lda, a.A, a.pi.w[2], nullptr, X1, Wst, ACT_MASK);    // W3 is [A][256]: dH2[r][i] = sum_j d3[r][j] W3[j][i]
-  store_tile(X1, a.Dp[1], row0, rows);
-  big_layer<false>(X1, H, H, a.pi.w[1], nullptr, X0, Wst, ACT_MASK);
-  store_tile(X0, a.Dp[0], row0, rows);
+  big_layer<false, RPT, (RPT == 8 ? 2 : 6)>(d3, lda, a.A, a.pi.w[2], nullptr, X1, Wst, ACT_MASK);    // W3 is [A][256]: dH2[r][i] = sum_j d3[r][j] W3[j][i]
+  store_tile<TM>(X1, a.Dp[1], row0, rows);
+  big_layer<false, RPT, (RPT == 8 ? 2 : 6)>(X1, H, H, a.pi.w[1], nullptr, X0, Wst, ACT_MASK);
+  store_tile<TM>(X0, a.Dp[0], row0, rows);
 }
 
 // ---------------- weight gradients: dW[o][i] = sum_r D[r][o] X[r][i], db[o] = sum_r D[r][o] ----------------
@@ -382,9 +395,11 @@ __global__ void adam_kernel(AdamArgs a) {
 }  // namespace trn
 
 // ---------------- host launchers ----------------
-static size_t tile_smem(int S, int A, int extra_floats) {
-  return (2 * (size_t)simt::TM * simt::H + 2 * simt::KC * simt::H + 2 * (size_t)simt::TM * simt::rup16(S + A) + extra_floats) * sizeof(float);
+static size_t tile_smem(int tm, int S, int A, int extra_floats) {
+  return (2 * (size_t)tm * simt::H + (size_t)(tm == 64 ? 2 : 6) * simt::KC * simt::H + 2 * (size_t)tm * simt::rup16(S + A) + extra_floats) * sizeof(float);
 }
+// Row tile: 64 rows per CTA for large batches; 16 for small ones so that a 320-row batch still spreads over 20 SMs.
+static int pick_tm(int N) { return N >= 148 * 32 ? 64 : 16; }
 template <typename K> static const char* set_smem(K kern, size_t bytes) {
   if (bytes > 227 * 1024) return "train step: shared memory budget exceeded for this (S, A)";
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return "cudaFuncSetAttribute failed";
@@ -392,15 +407,19 @@ template <typename K> static const char* set_smem(K kern, size_t bytes) {
 }
 
 const char* mb_train_critic_launch(const trn::CriticArgs& a, cudaStream_t st) {
-  size_t bytes = tile_smem(a.S, a.A, 6 * simt::TM + 8);
-  if (const char* e = set_smem(trn::critic_kernel, bytes)) return e;
-  trn::critic_kernel<<<(a.N + simt::TM - 1) / simt::TM, simt::NT, bytes, st>>>(a);
+  const int tm = pick_tm(a.N);
+  size_t bytes = tile_smem(tm, a.S, a.A, 6 * tm + 8);
+  auto kern = tm == 64 ? trn::critic_kernel<8> : trn::critic_kernel<2>;
+  if (const char* e = set_smem(kern, bytes)) return e;
+  kern<<<(a.N + tm - 1) / tm, simt::NT, bytes, st>>>(a);
   return nullptr;
 }
 const char* mb_train_actor_launch(const trn::ActorArgs& a, cudaStream_t st) {
-  size_t bytes = tile_smem(a.S, a.A, 3 * simt::TM + 2 * simt::TM * a.A);
-  if (const char* e = set_smem(trn::actor_kernel, bytes)) return e;
-  trn::actor_kernel<<<(a.N + simt::TM - 1) / simt::TM, simt::NT, bytes, st>>>(a);
+  const int tm = pick_tm(a.N);
+  size_t bytes = tile_smem(tm, a.S, a.A, 3 * tm + 2 * tm * a.A);
+  auto kern = tm == 64 ? trn::actor_kernel<8> : trn::actor_kernel<2>;
+  if (const char* e = set_smem(kern, bytes)) return e;
+  kern<<<(a.N + tm - 1) / tm, simt::NT, bytes, st>>>(a);
   return nullptr;
 }
 const char* mb_train_actor_scalars_launch(const trn::ActorScalarArgs& a, cudaStream_t st) {
@@ -413,9 +432,11 @@ const char* mb_train_actor_grad_launch(const trn::ActorGradArgs& a, cudaStream_t
   return nullptr;
 }
 const char* mb_train_policy_bwd_launch(const trn::PolicyBwdArgs& a, cudaStream_t st) {
-  size_t bytes = (2 * (size_t)simt::TM * simt::H + 2 * simt::KC * simt::H + (size_t)simt::TM * simt::rup16(a.A)) * sizeof(float);
-  if (const char* e = set_smem(trn::policy_bwd_kernel, bytes)) return e;
-  trn::policy_bwd_kernel<<<(a.N + simt::TM - 1) / simt::TM, simt::NT, bytes, st>>>(a);
+  const int tm = pick_tm(a.N);
+  size_t bytes = (2 * (size_t)tm * simt::H + (size_t)(tm == 64 ? 2 : 6) * simt::KC * simt::H + (size_t)tm * simt::rup16(a.A)) * sizeof(float);
+  auto kern = tm == 64 ? trn::policy_bwd_kernel<8> : trn::policy_bwd_kernel<2>;
+  if (const char* e = set_smem(kern, bytes)) return e;
+  kern<<<(a.N + tm - 1) / tm, simt::NT, bytes, st>>>(a);
   return nullptr;
 }
 const char* mb_train_wgrad_launch(const trn::WgradArgs& a, cudaStream_t st) {
@@ -444,7 +465,7 @@ static TrainWs train_ws(int N, int S, int A, int nsplit) {
   TrainWs w{}; size_t o = 0;
   auto take = [&](size_t n) { size_t r = o; o += (n + 3) & ~(size_t)3; return r; };
   const size_t act = (size_t)N * 256;
-  w.ntiles = (N + 63) / 64;
+  w.ntiles = (N + 15) / 16;                          // upper bound over both row-tile sizes
   for (int k = 0; k < 2; ++k) for (int l = 0; l < 2; ++l) { w.Hq[k][l] = take(act); w.Dq[k][l] = take(act); }
   for (int k = 0; k < 2; ++k) w.d3[k] = take(N);
   w.part = take((size_t)w.ntiles * 4);
@@ -509,7 +530,7 @@ const char* mb_train_step_launch(const mobody_train_desc& d, cudaStream_t st) {
   ac.q[0] = as_ptrs(d.q1); ac.q[1] = as_ptrs(d.q2); ac.max_action = d.max_action;
   ac.Hp[0] = ws + w.Hp[0]; ac.Hp[1] = ws + w.Hp[1]; ac.api = ws + w.api; ac.qpi = ws + w.qpi; ac.ga = ws + w.ga; ac.qhat = ws + w.qhat;
   if (const char* e = mb_train_actor_launch(ac, st)) return e;
-  trn::ActorScalarArgs sc{ac.qpi, ac.qhat, ac.api, d.rows, ws + w.part, w.ntiles, N, d.n_true, S, A, d.row_width, d.weight, d.bc_coef, ws + w.scal};
+  trn::ActorScalarArgs sc{ac.qpi, ac.qhat, ac.api, d.rows, ws + w.part, (N + pick_tm(N) - 1) / pick_tm(N), N, d.n_true, S, A, d.row_width, d.weight, d.bc_coef, ws + w.scal};
   if (const char* e = mb_train_actor_scalars_launch(sc, st)) return e;
   trn::ActorGradArgs ag{ws + w.scal, ac.ga, ac.api, ac.qhat, d.rows, N, d.n_true, S, A, d.row_width, d.bc_coef, d.max_action, ws + w.d3p};
   if (const char* e = mb_train_actor_grad_launch(ag, st)) return e;
