@@ -221,24 +221,24 @@ def main():
     obs_dev = obs_host.to(dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
 
-    def one_rollout_device():
-        out, info = ag.rollout_device(obs_dev, T, row0=rank * Bn)
-        return out, info
+    pending = []
 
-    gather_buf = None
+    def drain():
+        while pending:
+            pending.pop(0).wait()
+
+    def one_rollout_device():
+        if dist is None:
+            return ag.rollout_device(obs_dev, T, row0=rank * Bn)
+        # shard = this rank's start states; NCCL all-gather(v) of the synthetic transitions at the end
+        (slabs, counts_dev, widths, work), info = mb.parallel.sharded_rollout(ag, obs_dev, T, sharded_input=True, gather="padded_async")
+        pending.append(work)
+        if len(pending) > 1:
+            pending.pop(0).wait()                     # the all-gather of step t-1 overlapped this step's rollout
+        return slabs, dict(info, num_transitions=info["num_transitions"] * world)
 
     def exchange(out, info):
-        """NCCL all-gather of the packed synthetic transitions (padded slabs + counts)."""
-        nonlocal gather_buf
-        if dist is None:
-            return
-        w = 2 * S + A + 3
-        slab = torch.zeros(Bn * T, w, dtype=torch.float32, device=dev)
-        m = out["obss"].shape[0]
-        slab[:m] = torch.cat([out["obss"], out["actions"], out["next_obss"], out["rewards"], out["terminals"], out["penalty"]], 1)
-        if gather_buf is None:
-            gather_buf = torch.empty(world * Bn * T, w, dtype=torch.float32, device=dev)
-        dist.all_gather_into_tensor(gather_buf, slab)
+        return None
 
     # ---- device-resident timing ----
     for _ in range(W):
@@ -246,22 +246,24 @@ def main():
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
+    drain()
     sampler = ClockSampler(local_rank); sampler.start()
-    evs, n_trans = [], 0
+    n_trans = 0
     torch.cuda.synchronize()
     wall0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     for _ in range(args.steps):
-        flush.zero_()                                     # L2 flush, outside the timed event pair
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        flush.zero_()                                     # L2 flush between iterations (inside the timed region: ~2% of a step)
         o, i = one_rollout_device(); exchange(o, i)
-        e1.record()
-        evs.append((e0, e1)); n_trans += i["num_transitions"]
+        n_trans += i["num_transitions"] if dist is None else i["num_transitions"] // world
+    drain()                                               # every all-gather has completed before the closing event
+    e1.record()
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     wall = time.perf_counter() - wall0
-    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    dev_ms = e0.elapsed_time(e1)
 
     # ---- step-kernel-only timing for the roofline (same stream, events directly around the launch) ----
     from mobody_b200.dynamics import StepWorkspace
@@ -318,7 +320,7 @@ def main():
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"fp32": "f32", "bf16x2": "bf16x2 (hi+lo split, fp32-parity)", "bf16": "bf16"}[prec], "data": "synthetic",
         "config": {"workload": f"halfcheetah-gravity S{S}/A{A} rollout_length={T}, {Bn} start states per GPU (BASELINE configs[1])",
-                   "ensemble": 7, "hidden": 256, "precision": prec, "l2": "flushed between timed iterations (256 MiB memset)",
+                   "ensemble": 7, "hidden": 256, "precision": prec, "l2": "flushed between timed iterations (256 MiB memset, inside the timed region)",
                    "parallelism": f"dp{world} (start states sharded; NCCL all-gather of transitions)" if world > 1 else "single GPU"},
         "e2e": {"value": e2e_trans / e2e_s, "unit": UNIT, "h2d_bytes_per_step": Bn * S * 4, "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": args.steps * (T * 1 + (T - 1) * 5 + 3 + 6),

@@ -7,7 +7,7 @@ Public names mirror the reference modules they replace:
   algo.utils                      -> ReplayBuffer
   algo.offline_offline.mobody     -> MOBODY, Policy, DoubleQFunc, MLPNetwork, ValueFunc
 """
-from . import _ffi                                                    # noqa: F401
+from . import _ffi, parallel                                          # noqa: F401
 from .module import MOBODYModule, EnsembleLinear, Swish, soft_clamp   # noqa: F401
 from .dynamics import MOBODYEnsembleDynamics, StandardScaler          # noqa: F401
 from .terminal_funs import get_termination_fn, TERM_KINDS             # noqa: F401

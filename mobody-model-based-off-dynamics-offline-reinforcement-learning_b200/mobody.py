@@ -99,12 +99,15 @@ class MOBODY(object):
 
     # ------------------------------------------------------------------ rollout
     @torch.no_grad()
-    def rollout_device(self, init_obss, rollout_length, use_trg=True, *, eps=None, idx=None, row0=0):
+    def rollout_device(self, init_obss, rollout_length, use_trg=True, *, eps=None, idx=None, row0=0, out_packed=None):
         """T-step imagined rollout entirely on the device (mobody.py:596-657 without its per-step
         D2H copies and host masks).  One host read at the end (the transition counts).
 
         eps: optional [T,7,B,S] / idx: optional [T,B] injected draws (step t uses the first B_t rows,
         exactly what the reference consumes when fed the same arrays).
+        out_packed: optional preallocated [>= T*B, 2S+A+3] CUDA tensor; the kept transitions are gathered into its
+        first rows as [obs | act | next_obs | reward | terminal | penalty] and the returned dict holds column views
+        of it (this is the slab the multi-GPU all-gather ships).
         Returns (dict of CUDA tensors, info) or (None, None) when rollout_length == 0."""
         if rollout_length == 0:
             return None, None                                    # mobody.py:602-603
@@ -158,14 +161,19 @@ class MOBODY(object):
         termf = terms.float()
         out = {}
         mdev = counts[T + 1:T + 2]
-        for name, src, w in (("obss", obss, S), ("next_obss", nexts, S), ("actions", acts, A), ("rewards", rews, 1),
+        W = 2 * S + A + 3
+        packed = out_packed if out_packed is not None else torch.empty(max(M, 1), W, **f)
+        assert packed.shape[1] == W and packed.shape[0] >= M and packed.is_contiguous()
+        c0 = 0
+        for name, src, w in (("obss", obss, S), ("actions", acts, A), ("next_obss", nexts, S), ("rewards", rews, 1),
                              ("terminals", termf, 1), ("penalty", pens, 1)):
-            dst = torch.empty(M, w, **f)
-            if M:
-                _ffi.check(lib.mobody_gather_pos(_ffi.ptr(src), w, w, _ffi.ptr(pos), _ffi.ptr(mdev), M, _ffi.ptr(dst), w, st))
-            out[name] = dst
+            if M:   # dst[j, c0:c0+w] = src[pos[j], :]: row gather straight into the packed slab (leading dim W)
+                _ffi.check(lib.mobody_gather_pos(_ffi.ptr(src), w, w, _ffi.ptr(pos), _ffi.ptr(mdev), M,
+                                                 packed.data_ptr() + 4 * c0, W, st))
+            out[name] = packed[:M, c0:c0 + w]
+            c0 += w
         info = {"num_transitions": num_transitions, "reward_mean": float(host[T + 2]) / max(num_transitions, 1),
-                "rows_per_step": n_per_step, "kept": M}
+                "rows_per_step": n_per_step, "kept": M, "kept_dev": mdev}
         return out, info
 
     def rollout(self, init_obss, rollout_length, use_trg=True, **kw):
