@@ -36,6 +36,8 @@ template <int W> __device__ __forceinline__ void epi_bar() { asm volatile("bar.s
 constexpr int TM = 128;
 constexpr uint32_t MAIN_PLANE = 65536;   // 128 rows x 256 k x bf16
 constexpr int MAX_NST = 12;
+constexpr int NB = 4;                    // bias ring slots (one layer's bias each)
+constexpr int BSLOT = 528;               // floats per slot: 256 bias + reward_model3 vector (272) behind reward_model2's bias
 
 struct Cfg {
   int nst;
@@ -46,7 +48,7 @@ struct Cfg {
 };
 
 struct Bars {
-  uint64_t w_full[MAX_NST], w_empty[MAX_NST], a_ready[8], d_full[2], d_empty[2];
+  uint64_t w_full[MAX_NST], w_empty[MAX_NST], a_ready[8], d_full[2], d_empty[2], b_full[NB], b_empty[NB];
   uint32_t tmem_slot, pad;
 };
 
@@ -89,7 +91,8 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
   unsigned char* A_small = A_main + NS * MAIN_PLANE;
   unsigned char* wst = A_small + NS * cfg.small_plane;
   float* red = reinterpret_cast<float*>(wst + (size_t)cfg.nst * cfg.stage_bytes);      // [2][4][128]
-  Bars* bars = reinterpret_cast<Bars*>(red + 2 * 4 * 128);
+  float* bias_s = red + 2 * 4 * 128;                                                   // [NB][BSLOT]
+  Bars* bars = reinterpret_cast<Bars*>(bias_s + NB * BSLOT);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -97,6 +100,7 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
     for (int i = 0; i < cfg.nst; ++i) { tc::mbar_init(&bars->w_full[i], 1); tc::mbar_init(&bars->w_empty[i], 1); }
     for (int i = 0; i < 8; ++i) tc::mbar_init(&bars->a_ready[i], EPI_WARPS);   // every epilogue warp announces every chunk
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&bars->d_full[i], 1); tc::mbar_init(&bars->d_empty[i], EPI_WARPS); }
+    for (int i = 0; i < NB; ++i) { tc::mbar_init(&bars->b_full[i], 1); tc::mbar_init(&bars->b_empty[i], EPI_WARPS); }
     tc::mbar_fence_init();
   }
   if (warp == PROD_WARP) tc::tmem_alloc(&bars->tmem_slot, 512);
@@ -113,6 +117,14 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
         const TcLayer L = sched.L[li];
         const unsigned char* src = (L.blob ? polb : dynb) + L.w_off;
         const uint32_t bytes = (uint32_t)NS * L.n * 32u;
+        {   // this layer's bias (and reward_model3's vector right behind reward_model2's bias) -> bias ring slot li % NB
+          const int slot = li & (NB - 1);
+          const float* bsrc = reinterpret_cast<const float*>(L.blob ? polb + cfg.pol_bias_base : dynb + cfg.dyn_bias_base) + L.b_off;
+          const uint32_t bb = (L.kind == EPI_REWARD ? (uint32_t)BSLOT : (uint32_t)L.n) * 4u;
+          tc::mbar_wait(&bars->b_empty[slot], (uint32_t)(((li / NB) & 1) ^ 1));
+          tc::mbar_arrive_expect_tx(&bars->b_full[slot], bb);
+          tc::bulk_g2s(bias_s + slot * BSLOT, bsrc, bb, &bars->b_full[slot]);
+        }
         for (int s = 0; s < L.ksteps; ++s) {
           tc::mbar_wait(&bars->w_empty[stage], phase ^ 1u);
           tc::mbar_arrive_expect_tx(&bars->w_full[stage], bytes);
@@ -169,8 +181,6 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
     const bool valid = (row0 + r) < live;
     const size_t grow = (size_t)row0 + r;                     // row in this launch's arrays
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(group * CW);
-    const float* dyn_bias = reinterpret_cast<const float*>(dynb + cfg.dyn_bias_base);
-    const float* pol_bias = reinterpret_cast<const float*>(polb + cfg.pol_bias_base);
     const uint32_t sp = cfg.small_plane;
     const int col0 = group * CW;                              // this warp's first column inside a 32-column chunk
     int li = 0;
@@ -191,11 +201,16 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
       tc::fence_proxy_async_smem(); __syncwarp();
       if (lane == 0) tc::mbar_arrive(&bars->a_ready[c]);
     };
-    auto bias_of = [&](int l) { const TcLayer L = sched.L[l]; return (L.blob ? pol_bias : dyn_bias) + L.b_off; };
+    // biases are staged per layer by the producer warp (bias ring); every epilogue warp acquires and releases every layer
+    auto bias_of = [&](int l) -> const float* {
+      tc::mbar_wait(&bars->b_full[l & (NB - 1)], (uint32_t)((l / NB) & 1));
+      return bias_s + (l & (NB - 1)) * BSLOT;
+    };
+    auto bias_done = [&](int l) { __syncwarp(); if (lane == 0) tc::mbar_arrive(&bars->b_empty[l & (NB - 1)]); };
     auto ldbias = [&](const float* b, float (&bv)[CW]) {
 #pragma unroll
       for (int i = 0; i < CW / 4; ++i) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(b) + i);
+        const float4 t = *(reinterpret_cast<const float4*>(b) + i);
         bv[4 * i] = t.x; bv[4 * i + 1] = t.y; bv[4 * i + 2] = t.z; bv[4 * i + 3] = t.w;
       }
     };
@@ -204,13 +219,13 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
     auto epi_act256 = [&](int l, bool relu) {
       const float* bias = bias_of(l) + col0;
       const uint32_t t0 = lane_addr + (uint32_t)(l & 1) * 256u;
-      float bv[CW];
-      ldbias(bias, bv);
       wait_d(l);
       uint32_t x[CW], xn[CW];
       tmem_ldw<CW>(t0, x);
 #pragma unroll 1
       for (int c = 0; c < 8; ++c) {
+        float bv[CW];
+        ldbias(bias + c * 32, bv);
         tc::tmem_ld_wait();
         if (c + 1 < 8) tmem_ldw<CW>(t0 + (uint32_t)(c + 1) * 32u, xn);
 #pragma unroll
@@ -225,13 +240,13 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
         }
         signal_a(c);
         if (c + 1 < 8) {
-          ldbias(bias + (c + 1) * 32, bv);
           tc::tmem_ld_wait();
 #pragma unroll
           for (int i = 0; i < CW; ++i) x[i] = xn[i];
         }
       }
       release_d(l);
+      bias_done(l);
     };
 
     // ---------------- prologue: obs (and given actions) -> bf16 operand planes ----------------
@@ -271,13 +286,14 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int j = col0 + kg * 8 + i;
-              v[i] = (j < A) ? tanhf(__uint_as_float(x[kg * 8 + i]) + __ldg(bias + j)) * a.max_action : 0.f;
+              v[i] = (j < A) ? tanhf(__uint_as_float(x[kg * 8 + i]) + bias[j]) * a.max_action : 0.f;
               if (valid && j < A && a.act_out) a.act_out[grow * A + j] = v[i];
             }
             store8<NS>(A_small, sp, cfg.sa_off + (uint32_t)(2 + group * KGW + kg) * 2048u + (uint32_t)r * 16u, v);
           }
         }
         release_d(l);
+        bias_done(l);
       }
     }
 
@@ -295,7 +311,7 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
           tmem_ldw<CW>(lane_addr + (uint32_t)(l & 1) * 256u, x);
           tc::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < CW; ++j) zs[j] = __uint_as_float(x[j]) + __ldg(bias + col0 + j);
+          for (int j = 0; j < CW; ++j) zs[j] = __uint_as_float(x[j]) + bias[col0 + j];
 #pragma unroll
           for (int kg = 0; kg < KGW; ++kg) {
             float v[8];
@@ -306,6 +322,7 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
         }
         signal_a(0);
         release_d(l);
+        bias_done(l);
       }
       {                                                         // za1: swish -> 32-wide operand (aliases A_main)
         const int l = li++;
@@ -319,12 +336,13 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
           for (int kg = 0; kg < KGW; ++kg) {
             float v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = swish_ns<NS>(__uint_as_float(x[kg * 8 + i]) + __ldg(bias + col0 + kg * 8 + i));
+            for (int i = 0; i < 8; ++i) v[i] = swish_ns<NS>(__uint_as_float(x[kg * 8 + i]) + bias[col0 + kg * 8 + i]);
             store8<NS>(A_main, MAIN_PLANE, (uint32_t)(group * KGW + kg) * 2048u + (uint32_t)r * 16u, v);
           }
         }
         signal_a(0);
         release_d(l);
+        bias_done(l);
       }
       {                                                         // za2 mu half: z = zs + za -> 16-wide operand
         const int l = li++;
@@ -338,12 +356,13 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
           for (int kg = 0; kg < KGW; ++kg) {
             float v[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = zs[kg * 8 + i] + (__uint_as_float(x[kg * 8 + i]) + __ldg(bias + col0 + kg * 8 + i));
+            for (int i = 0; i < 8; ++i) v[i] = zs[kg * 8 + i] + (__uint_as_float(x[kg * 8 + i]) + bias[col0 + kg * 8 + i]);
             store8<NS>(A_main, MAIN_PLANE, (uint32_t)(group * KGW + kg) * 2048u + (uint32_t)r * 16u, v);
           }
         }
         signal_a(0);
         release_d(l);
+        bias_done(l);
       }
       epi_act256(li++, false);                                  // transition1
       epi_act256(li++, false);                                  // transition2
@@ -359,10 +378,11 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
           if (valid) {
             float* mrow = a.mean + ((size_t)e * B + grow) * S;
 #pragma unroll
-            for (int j = 0; j < CW; ++j) { const int col = c * 32 + col0 + j; if (col < S) mrow[col] = __uint_as_float(x[j]) + __ldg(bias + col); }
+            for (int j = 0; j < CW; ++j) { const int col = c * 32 + col0 + j; if (col < S) mrow[col] = __uint_as_float(x[j]) + bias[col]; }
           }
         }
         release_d(l);
+        bias_done(l);
       }
     }
 
@@ -482,8 +502,9 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
       epi_act256(li++, false);                                  // reward_model1
       {                                                         // reward_model2 -> swish -> dot reward_model3[:,0]
         const int l = li++;
-        const float* bias = bias_of(l) + col0;
-        const float* w3 = dyn_bias + (size_t)e * cfg.member_b_floats + cfg.r3_b_off;
+        const float* bslot = bias_of(l);
+        const float* bias = bslot + col0;
+        const float* w3 = bslot + 256;                              // reward_model3[:,0] (256) and its bias at [256]
         const uint32_t t0 = lane_addr + (uint32_t)(l & 1) * 256u;
         float part = 0.f;
         wait_d(l);
@@ -504,14 +525,16 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
             for (int i = 0; i < CW; ++i) x[i] = xn[i];
           }
         }
+        const float b3 = w3[256];
         release_d(l);
+        bias_done(l);
         red[((e & 1) * NG + group) * 128 + r] = part;
         epi_bar<EPI_WARPS>();
         if (group == 0) {
           float sum = 0.f;
 #pragma unroll
           for (int g2 = 0; g2 < NG; ++g2) sum += red[((e & 1) * NG + g2) * 128 + r];
-          racc += sum + __ldg(w3 + 256);
+          racc += sum + b3;
         }
       }
     }
@@ -644,7 +667,7 @@ const char* mb_tc_step_launch(const StepArgs& a, const unsigned char* dynb, cons
   cfg.dyn_bias_base = (uint32_t)DL.bias_base; cfg.member_b_floats = DL.member_b_floats; cfg.r3_b_off = DL.b_off[PK_COUNT];
   cfg.has_policy = has_policy ? 1 : 0;
   cfg.trace = g_tc_trace;
-  const size_t fixed = (size_t)ns * tcs::MAIN_PLANE + (size_t)ns * cfg.small_plane + 2 * 4 * 128 * sizeof(float) + sizeof(tcs::Bars) + 128;
+  const size_t fixed = (size_t)ns * tcs::MAIN_PLANE + (size_t)ns * cfg.small_plane + (2 * 4 * 128 + tcs::NB * tcs::BSLOT) * sizeof(float) + sizeof(tcs::Bars) + 128;
   const size_t budget = 227 * 1024;
   if (fixed + 2 * cfg.stage_bytes > budget) return "tensor-core step kernel: shared memory budget exceeded for this (S, A)";
   int nst = (int)((budget - fixed) / cfg.stage_bytes);

@@ -56,6 +56,29 @@ def test_struct_mirrors_match_header_sizes(libpath):
     assert ctypes.sizeof(_ffi.DynParams) == 2 * 13 * 8 and ctypes.sizeof(_ffi.MlpParams) == 6 * 8
 
 
+def test_struct_layouts_match_header_via_gcc(libpath, tmp_path):
+    """Compile include/mobody_b200.h with gcc and compare sizeof/offsetof with the ctypes mirrors field by field."""
+    import subprocess
+    from mobody_b200 import _ffi
+    structs = {"mobody_step_desc": _ffi.StepDesc, "mobody_train_desc": _ffi.TrainDesc,
+               "mobody_dyn_params": _ffi.DynParams, "mobody_mlp_params": _ffi.MlpParams, "mobody_mlp_state": _ffi.MlpState}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void){']
+    for cname, ct in structs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in ct._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ['return 0;}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c11", "-o", str(exe), str(src)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, ct in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(ct), cname
+        for fname, _ in ct._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(ct, fname).offset, f"{cname}.{fname}"
+
+
 def test_no_cpu_path():
     """Product classes refuse CPU devices instead of silently falling back."""
     import torch
