@@ -140,6 +140,39 @@ int mobody_gather_pos(const float* src, int w, int src_ld, const int* pos, const
 int mobody_gather_pos_i64(const long long* src, const int* pos, const int* m_dev, long long m_cap,
                           long long* dst, void* stream);
 
+/* ---- whole model rollout: MOBODY.rollout (algo/offline_offline/mobody.py:596-657) as ONE host call ----
+ * T fused steps (policy forward + dynamics step) with device-side compaction of the non-terminal rows between
+ * steps (:635-639), concatenation over steps and the penalty filter `penalty <= env_filter` (:641-653) — no host
+ * round trip inside the rollout.  `step` is the template of every step: its obs is the start states [B,S], its
+ * policy must be set, and its per-step fields (obs/act_out/next_obs/reward/penalty/terminal/row_ids/n_rows_dev/
+ * step/eps/idx) are overridden from the workspace below.  Everything is caller-allocated device memory.
+ * Outputs: packed[j,:] = [obs(S) | act(A) | next_obs(S) | reward | terminal(0/1) | penalty] for the kept
+ * transitions j < counts[T+1] in the reference's order (step-major, rows ascending); counts[t] = live rows entering
+ * step t (t < T); stats[0] = sum of rewards over all produced transitions, stats[1] = their number
+ * (info['reward_mean'] = stats[0] / stats[1], info['num_transitions'] = stats[1]). */
+typedef struct mobody_rollout_desc {
+  mobody_step_desc step;
+  int T;                      /* rollout_length (1 <= T <= 200)                                        */
+  int filter_bad_rollout;     /* config['filter_bad_rollout']                                          */
+  float env_filter;           /* config['env_filter']                                                  */
+  const float* eps_all;       /* NULL -> Philox; else device [T,E,B,S]                                 */
+  const int64_t* idx_all;     /* NULL -> Philox; else device int64 [T,B]                               */
+  float* obss;                /* device [T,B,S]; obss[0] is filled from step.obs unless they alias     */
+  float* acts;                /* device [T,B,A]                                                        */
+  float* nexts;               /* device [T,B,S]                                                        */
+  float* rews;                /* device [T,B]                                                          */
+  float* pens;                /* device [T,B]                                                          */
+  unsigned char* terms;       /* device [T,B]   0/1, 0xFF = slot never produced                        */
+  long long* row_ids;         /* device int64 [T,B] global row ids (Philox counters)                   */
+  int* counts;                /* device int [T+2]                                                      */
+  int* pos;                   /* device int [T*B]                                                      */
+  int* scratch;               /* device int [mobody_compact_scratch_ints(T*B)]                         */
+  double* stats;              /* device double [2 + 2*148] (first 2 are the result) ...                */
+  unsigned int* ticket;       /* ... and one device unsigned, zero-initialised once by the caller      */
+  float* packed;              /* device [T*B, 2S+A+3]                                                  */
+} mobody_rollout_desc;
+int mobody_rollout(const mobody_rollout_desc* d, void* stream);
+
 /* ---- steady-state train step: twin-critic TD update + Polyak + Q-weighted BC actor update ----
  * Replaces MOBODY.update_q_functions / update_target / update_policy / bc_loss and the three
  * torch.optim.Adam steps inside MOBODY.train (algo/offline_offline/mobody.py:183-208, 246-276, 314-345,

@@ -43,6 +43,16 @@ class StepDesc(C.Structure):
     ]
 
 
+class RolloutDesc(C.Structure):
+    _fields_ = [
+        ("step", StepDesc), ("T", C.c_int), ("filter_bad_rollout", C.c_int), ("env_filter", C.c_float),
+        ("eps_all", C.c_void_p), ("idx_all", C.c_void_p),
+        ("obss", C.c_void_p), ("acts", C.c_void_p), ("nexts", C.c_void_p), ("rews", C.c_void_p), ("pens", C.c_void_p),
+        ("terms", C.c_void_p), ("row_ids", C.c_void_p), ("counts", C.c_void_p), ("pos", C.c_void_p), ("scratch", C.c_void_p),
+        ("stats", C.c_void_p), ("ticket", C.c_void_p), ("packed", C.c_void_p),
+    ]
+
+
 class MlpState(C.Structure):
     _fields_ = [("w", C.c_void_p * 3), ("b", C.c_void_p * 3)]
 
@@ -77,6 +87,7 @@ def lib():
         L.mobody_compact_scratch_ints.argtypes = [C.c_longlong]
         L.mobody_row_width.argtypes = [C.c_int, C.c_int]
         L.mobody_step.argtypes = [C.POINTER(StepDesc), C.c_void_p]
+        L.mobody_rollout.argtypes = [C.POINTER(RolloutDesc), C.c_void_p]
         L.mobody_policy_forward.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(MlpParams), C.c_float,
                                             C.c_void_p, C.c_void_p]
         L.mobody_termination.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p]

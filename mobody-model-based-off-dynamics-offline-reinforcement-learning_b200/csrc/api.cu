@@ -22,6 +22,16 @@ void mb_gather_pos_launch(const float* src, int w, int src_ld, const int* pos, c
                           float* dst, int dst_ld, cudaStream_t st);
 void mb_gather_pos_i64_launch(const long long* src, const int* pos, const int* m_dev, long long m_cap, long long* dst, cudaStream_t st);
 
+void mb_rollout_init_launch(long long* row_ids, unsigned long long row0, int B, int T, float* pens, unsigned char* terms,
+                            int* counts, cudaStream_t st);
+void mb_rollout_advance_launch(const float* nexts, const long long* ids_prev, int S, const int* pos, const int* m_dev,
+                               long long m_cap, float* obs_next, long long* ids_next, cudaStream_t st);
+void mb_rollout_pack_launch(const float* obss, const float* acts, const float* nexts, const float* rews, const unsigned char* terms,
+                            const float* pens, int S, int A, const int* pos, const int* m_dev, long long m_cap, float* packed,
+                            cudaStream_t st);
+void mb_rollout_stats_launch(const float* rews, const unsigned char* terms, long long n, double* partial, unsigned int* ticket,
+                             double* stats, cudaStream_t st);
+
 const char* mb_tc_dyn_pack(const DynPtrs& dp, int S, int A, int ns, unsigned char* blob, cudaStream_t st);
 const char* mb_tc_mlp_pack(const MlpPtrs& mp, int din, int dout, int ns, unsigned char* blob, cudaStream_t st);
 const char* mb_tc_step_launch(const StepArgs& a, const unsigned char* dynb, const unsigned char* polb, int ns, cudaStream_t st);
@@ -175,6 +185,46 @@ int mobody_gather_pos_i64(const long long* src, const int* pos, const int* m_dev
   if (m_cap < 0 || (m_cap > 0 && (!src || !pos || !dst))) return fail(MOBODY_ERR_ARG, "mobody_gather_pos_i64: bad arguments");
   mb_gather_pos_i64_launch(src, pos, m_dev, m_cap, dst, (cudaStream_t)stream);
   return check_launch("mobody_gather_pos_i64");
+}
+
+int mobody_rollout(const mobody_rollout_desc* d, void* stream) {
+  if (!d) return fail(MOBODY_ERR_ARG, "mobody_rollout: null descriptor");
+  const mobody_step_desc& s0 = d->step;
+  const int B = s0.B, S = s0.S, A = s0.A, T = d->T;
+  if (T < 1 || T > 200 || B < 0 || (long long)T * B > 0x7fffffffLL) return fail(MOBODY_ERR_ARG, "mobody_rollout: bad T / B");
+  if (B == 0) return MOBODY_OK;
+  if (!s0.policy) return fail(MOBODY_ERR_ARG, "mobody_rollout: the step template needs a policy (actions come from pi(s))");
+  if (!s0.obs || !d->obss || !d->acts || !d->nexts || !d->rews || !d->pens || !d->terms || !d->row_ids || !d->counts || !d->pos ||
+      !d->scratch || !d->stats || !d->ticket || !d->packed)
+    return fail(MOBODY_ERR_ARG, "mobody_rollout: null workspace pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (s0.obs != d->obss &&
+      cudaMemcpyAsync(d->obss, s0.obs, (size_t)B * S * sizeof(float), cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+    return fail(MOBODY_ERR_CUDA, "mobody_rollout: copy of the start states failed");
+  mb_rollout_init_launch(d->row_ids, s0.row0, B, T, d->pens, d->terms, d->counts, st);
+  for (int t = 0; t < T; ++t) {
+    mobody_step_desc s = s0;
+    const size_t o = (size_t)t * B;
+    s.obs = d->obss + o * S; s.act = nullptr; s.act_out = d->acts + o * A; s.next_obs = d->nexts + o * S;
+    s.reward = d->rews + o; s.penalty = d->pens + o; s.terminal = d->terms + o;
+    s.row_ids = d->row_ids + o; s.n_rows_dev = d->counts + t; s.step = s0.step + (unsigned)t;
+    s.eps = d->eps_all ? d->eps_all + (size_t)t * MOBODY_E * B * S : nullptr;
+    s.idx = d->idx_all ? d->idx_all + o : nullptr;
+    if (int rc = mobody_step(&s, stream)) return rc;
+    if (t + 1 < T) {   // nonterm_mask compaction (mobody.py:635-639): stable order, counts stay on the device
+      mb_compact_launch(MOBODY_KEEP_U8_ZERO, s.terminal, nullptr, 0.f, B, d->counts + t, d->scratch, d->pos, d->counts + t + 1, st);
+      mb_rollout_advance_launch(s.next_obs, s.row_ids, S, d->pos, d->counts + t + 1, B, d->obss + (o + B) * S, d->row_ids + o + B, st);
+    }
+  }
+  // concat over steps + penalty filter (mobody.py:641-653): one stable compaction over the T*B slots
+  if (d->filter_bad_rollout)
+    mb_compact_launch(MOBODY_KEEP_F32_LE, nullptr, d->pens, d->env_filter, (long long)T * B, nullptr, d->scratch, d->pos, d->counts + T + 1, st);
+  else
+    mb_compact_launch(MOBODY_KEEP_U8_VALID, d->terms, nullptr, 0.f, (long long)T * B, nullptr, d->scratch, d->pos, d->counts + T + 1, st);
+  mb_rollout_pack_launch(d->obss, d->acts, d->nexts, d->rews, d->terms, d->pens, S, A, d->pos, d->counts + T + 1, (long long)T * B,
+                         d->packed, st);
+  mb_rollout_stats_launch(d->rews, d->terms, (long long)T * B, d->stats + 2, d->ticket, d->stats, st);
+  return check_launch("mobody_rollout");
 }
 
 long long mobody_train_workspace_bytes(int N, int S, int A, int nsplit) {

@@ -180,6 +180,88 @@ __global__ void gather_pos_i64_kernel(const long long* __restrict__ src, const i
   for (; j < m; j += (long long)gridDim.x * blockDim.x) dst[j] = src[pos[j]];
 }
 
+// ---------------- whole-rollout plumbing (MOBODY.rollout, mobody.py:596-657) ----------------
+// init: row ids of step 0, "never produced" markers for the rows of steps >= 1 (penalty +inf fails every `<=`
+// filter, terminal 0xFF marks a slot no step wrote), live-row counts.
+__global__ void rollout_init_kernel(long long* __restrict__ row_ids, unsigned long long row0, int B, int T,
+                                    float* __restrict__ pens, unsigned char* __restrict__ terms, int* __restrict__ counts) {
+  const long long total = (long long)T * B;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    if (i < B) row_ids[i] = (long long)(row0 + (unsigned long long)i);
+    else { pens[i] = __int_as_float(0x7f800000); terms[i] = 0xFF; }
+  }
+  if (blockIdx.x == 0 && threadIdx.x <= T + 1) counts[threadIdx.x] = threadIdx.x == 0 ? B : 0;
+}
+
+// next step's inputs: obs[j,:] = next_obs[pos[j],:], row_ids[j] = row_ids_prev[pos[j]] for j < *m_dev (mobody.py:635-639)
+__global__ void rollout_advance_kernel(const float* __restrict__ nexts, const long long* __restrict__ ids_prev, int S,
+                                       const int* __restrict__ pos, const int* __restrict__ m_dev, long long m_cap,
+                                       float* __restrict__ obs_next, long long* __restrict__ ids_next) {
+  const long long m = min((long long)*m_dev, m_cap);
+  const long long total = m * (S + 1);
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long j = t / (S + 1); const int c = (int)(t - j * (S + 1));
+    const size_t p = (size_t)pos[j];
+    if (c < S) obs_next[j * S + c] = nexts[p * S + c];
+    else ids_next[j] = ids_prev[p];
+  }
+}
+
+// packed[j,:] = [obs | act | next_obs | reward | terminal | penalty] of slot pos[j], j < *m_dev  (mobody.py:641-653)
+__global__ void rollout_pack_kernel(const float* __restrict__ obss, const float* __restrict__ acts, const float* __restrict__ nexts,
+                                    const float* __restrict__ rews, const unsigned char* __restrict__ terms,
+                                    const float* __restrict__ pens, int S, int A, const int* __restrict__ pos,
+                                    const int* __restrict__ m_dev, long long m_cap, float* __restrict__ packed) {
+  const int W = 2 * S + A + 3;
+  const long long m = min((long long)*m_dev, m_cap);
+  const long long total = m * W;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long j = t / W; const int c = (int)(t - j * W);
+    const size_t p = (size_t)pos[j];
+    float v;
+    if (c < S) v = obss[p * S + c];
+    else if (c < S + A) v = acts[p * A + (c - S)];
+    else if (c < 2 * S + A) v = nexts[p * S + (c - S - A)];
+    else if (c == 2 * S + A) v = rews[p];
+    else if (c == 2 * S + A + 1) v = (float)terms[p];
+    else v = pens[p];
+    packed[t] = v;
+  }
+}
+
+// stats[0] = sum of rewards over every produced slot (terminal != 0xFF), stats[1] = number of produced slots.
+// Fixed-order reduction: per-block partials, the last block to finish adds them in block order (deterministic).
+constexpr int SB = 256;
+__global__ void __launch_bounds__(SB) rollout_stats_kernel(const float* __restrict__ rews, const unsigned char* __restrict__ terms,
+                                                          long long n, double* __restrict__ partial, unsigned int* __restrict__ ticket,
+                                                          double* __restrict__ stats) {
+  __shared__ double sh[2][SB];
+  __shared__ bool last;
+  double s = 0.0, c = 0.0;
+  const long long per = (n + gridDim.x - 1) / gridDim.x;
+  const long long lo = (long long)blockIdx.x * per, hi = min(n, lo + per);
+  for (long long i = lo + threadIdx.x; i < hi; i += SB) if (terms[i] != 0xFF) { s += (double)rews[i]; c += 1.0; }
+  sh[0][threadIdx.x] = s; sh[1][threadIdx.x] = c;
+  __syncthreads();
+  for (int o = SB / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) { sh[0][threadIdx.x] += sh[0][threadIdx.x + o]; sh[1][threadIdx.x] += sh[1][threadIdx.x + o]; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    partial[2 * blockIdx.x] = sh[0][0]; partial[2 * blockIdx.x + 1] = sh[1][0];
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double ts = 0.0, tc = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) { ts += partial[2 * b]; tc += partial[2 * b + 1]; }
+    stats[0] = ts; stats[1] = tc;
+    *ticket = 0u;                      // re-armed for the next call on this stream
+  }
+}
+
 }  // namespace buf
 
 static inline int grid_for(long long work, int nt, int max_blocks = 148 * 16) {
@@ -231,4 +313,28 @@ void mb_gather_pos_launch(const float* src, int w, int src_ld, const int* pos, c
 void mb_gather_pos_i64_launch(const long long* src, const int* pos, const int* m_dev, long long m_cap, long long* dst, cudaStream_t st) {
   if (m_cap <= 0) return;
   buf::gather_pos_i64_kernel<<<grid_for(m_cap, buf::NT), buf::NT, 0, st>>>(src, pos, m_dev, m_cap, dst);
+}
+
+// ---- whole-rollout plumbing ----
+void mb_rollout_init_launch(long long* row_ids, unsigned long long row0, int B, int T, float* pens, unsigned char* terms,
+                            int* counts, cudaStream_t st) {
+  buf::rollout_init_kernel<<<grid_for((long long)T * B, buf::NT), buf::NT, 0, st>>>(row_ids, row0, B, T, pens, terms, counts);
+}
+void mb_rollout_advance_launch(const float* nexts, const long long* ids_prev, int S, const int* pos, const int* m_dev,
+                               long long m_cap, float* obs_next, long long* ids_next, cudaStream_t st) {
+  if (m_cap <= 0) return;
+  buf::rollout_advance_kernel<<<grid_for(m_cap * (S + 1), buf::NT), buf::NT, 0, st>>>(nexts, ids_prev, S, pos, m_dev, m_cap, obs_next, ids_next);
+}
+void mb_rollout_pack_launch(const float* obss, const float* acts, const float* nexts, const float* rews, const unsigned char* terms,
+                            const float* pens, int S, int A, const int* pos, const int* m_dev, long long m_cap, float* packed,
+                            cudaStream_t st) {
+  if (m_cap <= 0) return;
+  buf::rollout_pack_kernel<<<grid_for(m_cap * (2 * S + A + 3), buf::NT), buf::NT, 0, st>>>(obss, acts, nexts, rews, terms, pens, S, A,
+                                                                                          pos, m_dev, m_cap, packed);
+}
+// scratch: double[2 * MB_STATS_BLOCKS] partials followed by one unsigned ticket (zero-initialised once by the caller)
+void mb_rollout_stats_launch(const float* rews, const unsigned char* terms, long long n, double* partial, unsigned int* ticket,
+                             double* stats, cudaStream_t st) {
+  int nb = (int)((n + 4095) / 4096); if (nb < 1) nb = 1; if (nb > 148) nb = 148;
+  buf::rollout_stats_kernel<<<nb, buf::SB, 0, st>>>(rews, terms, n, partial, ticket, stats);
 }

@@ -66,7 +66,8 @@ __device__ __forceinline__ void store8(unsigned char* base, uint32_t plane_strid
   }
 }
 
-template <int NS> __device__ __forceinline__ float swish_ns(float x) { return NS == 1 ? tc::swish_tanh(x) : tc::swish_ex2_rcp(x); }
+// argument is the PRE-SCALED pre-activation (see tc_swish_scales); result carries the mode's output scale
+template <int NS> __device__ __forceinline__ float swish_ns(float t) { return NS == 1 ? tc::swish_pre_tanh(t) : tc::swish_pre_ex2_rcp(t); }
 
 template <int CW> __device__ __forceinline__ void tmem_ldw(uint32_t taddr, uint32_t (&x)[CW]);
 template <> __device__ __forceinline__ void tmem_ldw<8>(uint32_t taddr, uint32_t (&x)[8]) { tc::tmem_ld8(taddr, x); }
@@ -553,7 +554,7 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
 
 // ---------------- weight packing: fp32 [K][N] (any strides) -> bf16 planes in UMMA B layout ----------------
 __global__ void pack_weight_kernel(const float* __restrict__ W, long long stride_k, long long stride_n, int K, int N, int Kp,
-                                   int Np, int ns, __nv_bfloat16* __restrict__ out) {
+                                   int Np, int ns, float scale, __nv_bfloat16* __restrict__ out) {
   const long long total = (long long)(Kp / 16) * ns * 2 * Np * 8;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     int j = (int)(t & 7); long long u = t >> 3;
@@ -561,22 +562,22 @@ __global__ void pack_weight_kernel(const float* __restrict__ W, long long stride
     int g = (int)(u & 1); u >>= 1;
     int p = (int)(u % ns); int s = (int)(u / ns);
     int k = s * 16 + g * 8 + j;
-    float v = (k < K && n < N) ? W[k * stride_k + n * stride_n] : 0.f;
+    float v = (k < K && n < N) ? W[k * stride_k + n * stride_n] * scale : 0.f;
     __nv_bfloat16 h = __float2bfloat16_rn(v);
     out[t] = (p == 0) ? h : __float2bfloat16_rn(v - __bfloat162float(h));
   }
 }
-__global__ void pack_bias_kernel(const float* __restrict__ b, long long stride, int N, int Np, float* __restrict__ out) {
+__global__ void pack_bias_kernel(const float* __restrict__ b, long long stride, int N, int Np, float scale, float* __restrict__ out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < Np) out[i] = (i < N) ? b[i * stride] : 0.f;
+  if (i < Np) out[i] = (i < N) ? b[i * stride] * scale : 0.f;
 }
 
 }  // namespace tcs
 
-static inline void launch_pack_w(const float* W, long long sk, long long sn, const TcGeom& g, int ns, unsigned char* out, cudaStream_t st) {
+static inline void launch_pack_w(const float* W, long long sk, long long sn, const TcGeom& g, int ns, float scale, unsigned char* out, cudaStream_t st) {
   long long total = (long long)(g.Kp / 16) * ns * 2 * g.Np * 8;
   int grid = (int)((total + 255) / 256); if (grid > 1184) grid = 1184;
-  tcs::pack_weight_kernel<<<grid, 256, 0, st>>>(W, sk, sn, g.K, g.N, g.Kp, g.Np, ns, reinterpret_cast<__nv_bfloat16*>(out));
+  tcs::pack_weight_kernel<<<grid, 256, 0, st>>>(W, sk, sn, g.K, g.N, g.Kp, g.Np, ns, scale, reinterpret_cast<__nv_bfloat16*>(out));
 }
 
 // mobody_dyn_pack: all 7 members x 12 MMA layers + biases + reward_model3 vector
@@ -585,19 +586,23 @@ const char* mb_tc_dyn_pack(const DynPtrs& dp, int S, int A, int ns, unsigned cha
   const TcDynLayout L = tc_dyn_layout(S, A, ns);
   static const int src[PK_COUNT] = {L_ZS1, L_ZS2, L_ZS3, L_ZASRC1, L_ZASRC2, L_ZATRG1, L_ZATRG2, L_T1, L_T2, L_T3, L_R1, L_R2};
   float* bias = reinterpret_cast<float*>(blob + L.bias_base);
+  double so, si;
+  tc_swish_scales(ns, &so, &si);
   for (int e = 0; e < MB_E; ++e)
     for (int i = 0; i < PK_COUNT; ++i) {
+      const float wscale = (float)((tc_out_is_swish(i) ? so : 1.0) * (tc_in_is_swish(i) ? si : 1.0));
+      const float bscale = (float)(tc_out_is_swish(i) ? so : 1.0);
       const TcGeom g = tc_dyn_geom(i, S, A);
       const int nfull = (i == PK_ZS3 || i == PK_ZASRC2 || i == PK_ZATRG2) ? 32 : g.N;     // mu half of 32 columns
       const float* W = dp.w[src[i]] + (size_t)e * g.K * nfull;
-      launch_pack_w(W, nfull, 1, g, ns, blob + (size_t)e * L.member_w_bytes + L.w_off[i], st);
-      tcs::pack_bias_kernel<<<(g.Np + 127) / 128, 128, 0, st>>>(dp.b[src[i]] + (size_t)e * nfull, 1, g.N, g.Np,
+      launch_pack_w(W, nfull, 1, g, ns, wscale, blob + (size_t)e * L.member_w_bytes + L.w_off[i], st);
+      tcs::pack_bias_kernel<<<(g.Np + 127) / 128, 128, 0, st>>>(dp.b[src[i]] + (size_t)e * nfull, 1, g.N, g.Np, bscale,
                                                                 bias + (size_t)e * L.member_b_floats + L.b_off[i]);
     }
   for (int e = 0; e < MB_E; ++e) {   // reward_model3: column 0 of [256][2] and bias[0]
     float* o = bias + (size_t)e * L.member_b_floats + L.b_off[PK_COUNT];
-    tcs::pack_bias_kernel<<<2, 128, 0, st>>>(dp.w[L_R3] + (size_t)e * MB_H * 2, 2, MB_H, MB_H, o);
-    tcs::pack_bias_kernel<<<1, 32, 0, st>>>(dp.b[L_R3] + (size_t)e * 2, 1, 1, 16, o + MB_H);
+    tcs::pack_bias_kernel<<<2, 128, 0, st>>>(dp.w[L_R3] + (size_t)e * MB_H * 2, 2, MB_H, MB_H, (float)si, o);   // consumes reward_model2's swish
+    tcs::pack_bias_kernel<<<1, 32, 0, st>>>(dp.b[L_R3] + (size_t)e * 2, 1, 1, 16, 1.0f, o + MB_H);
   }
   return nullptr;
 }
@@ -607,8 +612,8 @@ const char* mb_tc_mlp_pack(const MlpPtrs& mp, int din, int dout, int ns, unsigne
   const TcMlpLayout L = tc_mlp_layout(din, dout, ns);
   float* bias = reinterpret_cast<float*>(blob + L.bias_base);
   for (int i = 0; i < 3; ++i) {   // nn.Linear weight is [out][in]: stride_k = 1, stride_n = K
-    launch_pack_w(mp.w[i], 1, L.g[i].K, L.g[i], ns, blob + L.w_off[i], st);
-    tcs::pack_bias_kernel<<<(L.g[i].Np + 127) / 128, 128, 0, st>>>(mp.b[i], 1, L.g[i].N, L.g[i].Np, bias + L.b_off[i]);
+    launch_pack_w(mp.w[i], 1, L.g[i].K, L.g[i], ns, 1.0f, blob + L.w_off[i], st);
+    tcs::pack_bias_kernel<<<(L.g[i].Np + 127) / 128, 128, 0, st>>>(mp.b[i], 1, L.g[i].N, L.g[i].Np, 1.0f, bias + L.b_off[i]);
   }
   return nullptr;
 }

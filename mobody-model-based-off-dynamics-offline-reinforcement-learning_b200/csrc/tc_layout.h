@@ -63,6 +63,21 @@ static inline __host__ __device__ TcGeom tc_dyn_geom(int layer, int S, int A) {
 }
 static inline __host__ __device__ size_t tc_layer_bytes(const TcGeom& g, int ns) { return (size_t)(g.Kp / 16) * ns * g.Np * 32; }
 
+// Swish layers are packed PRE-SCALED so the epilogue needs no multiply in front of the SFU op:
+//   exact mode (ns = 2): accumulator holds t = -log2(e) x, epilogue returns t / (1 + 2^t) = -log2(e) swish(x)
+//   loose mode (ns = 1): accumulator holds t = x / 2,      epilogue returns t + t tanh(t) = swish(x)
+// `so` multiplies W and b of a layer whose output goes through swish, `si` multiplies W of a layer whose INPUT is
+// such an epilogue result (si * so_epilogue_factor = 1: -ln 2 in exact mode, 1 in loose mode).
+static inline __host__ __device__ void tc_swish_scales(int ns, double* so, double* si) {
+  if (ns == 2) { *so = -1.4426950408889634; *si = -0.6931471805599453; } else { *so = 0.5; *si = 1.0; }
+}
+static inline __host__ __device__ bool tc_out_is_swish(int pk) {
+  return pk == PK_ZS1 || pk == PK_ZS2 || pk == PK_ZASRC1 || pk == PK_ZATRG1 || pk == PK_T1 || pk == PK_T2 || pk == PK_R1 || pk == PK_R2;
+}
+static inline __host__ __device__ bool tc_in_is_swish(int pk) {
+  return pk == PK_ZS2 || pk == PK_ZS3 || pk == PK_ZASRC2 || pk == PK_ZATRG2 || pk == PK_T2 || pk == PK_T3 || pk == PK_R2;
+}
+
 #define TC_R3_FLOATS 272   // reward_model3 column 0 (256) + its bias at [256], padded
 
 struct TcDynLayout {

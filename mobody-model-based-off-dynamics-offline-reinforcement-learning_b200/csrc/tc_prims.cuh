@@ -176,15 +176,15 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ---------------- bf16 split helpers (integer pipe only: no F2FP / XU traffic) ----------------
-// hi = bf16(v) rounded half-away (add 0x8000 to the magnitude bits, keep the top 16);
-// lo = bf16(v - hi), same rounding.  hi+lo carries ~16 significand bits of v (error <= 2^-17 |v|).
+// hi = top 16 bits of v (truncation; exact, so v - hi is exact in fp32 and has the sign of v),
+// lo = bf16(v - hi) rounded half-away.  hi+lo carries ~16 significand bits of v (error <= 2^-16 |v|);
+// the rounding of lo is unbiased, the truncation of hi is fully compensated by lo.
 // Packing two values into one 32-bit word is a byte permute (low half = first value).
 __device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
-  const uint32_t h0 = (__float_as_uint(v0) + 0x8000u) & 0xFFFF0000u;
-  const uint32_t h1 = (__float_as_uint(v1) + 0x8000u) & 0xFFFF0000u;
-  const uint32_t l0 = __float_as_uint(v0 - __uint_as_float(h0)) + 0x8000u;
-  const uint32_t l1 = __float_as_uint(v1 - __uint_as_float(h1)) + 0x8000u;
-  hi = __byte_perm(h0, h1, 0x7632);
+  const uint32_t u0 = __float_as_uint(v0), u1 = __float_as_uint(v1);
+  hi = __byte_perm(u0, u1, 0x7632);
+  const uint32_t l0 = __float_as_uint(v0 - __uint_as_float(u0 & 0xFFFF0000u)) + 0x8000u;
+  const uint32_t l1 = __float_as_uint(v1 - __uint_as_float(u1 & 0xFFFF0000u)) + 0x8000u;
   lo = __byte_perm(l0, l1, 0x7632);
 }
 __device__ __forceinline__ uint32_t pack_bf16(float v0, float v1) {
@@ -192,19 +192,20 @@ __device__ __forceinline__ uint32_t pack_bf16(float v0, float v1) {
 }
 
 // ---------------- swish on the SFU with flush-to-zero forms (one MUFU each, no range fix-ups) ----------------
-// exact mode: x / (1 + 2^(-x log2 e)) with ex2.approx.ftz (2 ulp) and rcp.approx.ftz (1 ulp)
-__device__ __forceinline__ float swish_ex2_rcp(float x) {
+// The weight packer pre-scales every swish layer (tc_layout.h: tc_swish_scales), so the accumulator already holds
+//   exact mode : t = -x log2(e)  ->  t / (1 + 2^t) = -log2(e) swish(x)   (the consumer's weights carry the -ln 2);
+//                ex2.approx.ftz (2 ulp) and rcp.approx.ftz (1 ulp)
+//   loose mode : t = x / 2       ->  t + t tanh(t) = swish(x); single-pass bf16 only: tanh.approx error 2^-11 < bf16 ulp
+__device__ __forceinline__ float swish_pre_ex2_rcp(float t) {
   float e, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
-  return x * r;
+  return t * r;
 }
-// loose mode (single-pass bf16 only): 0.5x (1 + tanh(0.5x)), one MUFU; tanh.approx error 2^-11 < bf16 ulp
-__device__ __forceinline__ float swish_tanh(float x) {
-  const float hx = 0.5f * x;
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(hx));
-  return fmaf(hx, t, hx);
+__device__ __forceinline__ float swish_pre_tanh(float t) {
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(t));
+  return fmaf(t, th, t);
 }
 
 }  // namespace tc

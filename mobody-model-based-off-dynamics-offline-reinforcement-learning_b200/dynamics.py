@@ -96,29 +96,21 @@ class MOBODYEnsembleDynamics(object):
         return self._pol_pack[id(policy)][1]
 
     # ------------------------------------------------------------------
-    def launch_step(self, obs, act, ws: StepWorkspace, *, policy=None, max_action=1.0, use_penalty=True,
-                    use_trg=True, eps=None, idx=None, n_rows_dev=None, row_ids=None, step=0, row0=0):
-        """Enqueue the fused step on the current stream; no host synchronisation.
-        obs [B,S] (B = capacity), act [B,A] or None with ``policy`` (an MLPNetwork-like module)."""
-        dev = obs.device
-        B, S = obs.shape
+    def fill_step_desc(self, d, B, S, dev, *, policy=None, max_action=1.0, use_penalty=True, use_trg=True):
+        """Fill the call-invariant half of a mobody_step_desc (shapes, parameter pointers, packed weight images,
+        penalty/termination/elite settings).  Returns the tensors/structs that must outlive the launch."""
         A = self.model.action_dim
-        d = _ffi.StepDesc()
         d.precision = _ffi.PREC[self.precision]
         d.B, d.S, d.A = B, S, A
-        d.n_rows_dev, d.row_ids = _ffi.ptr(n_rows_dev), _ffi.ptr(row_ids)
-        d.obs, d.act = _ffi.ptr(obs), _ffi.ptr(act)
         keep = []
         tensor_core = self.precision != "fp32"
         if policy is not None:
-            mp, k = _ffi.mlp_params(policy); keep += k
+            mp, k = _ffi.mlp_params(policy); keep += k; keep.append(mp)
             d.policy = C.pointer(mp)
             if tensor_core:
                 d.policy_pack = _ffi.ptr(self._packed_policy(policy, mp, k))
-                if ws.act is None:
-                    ws.act = torch.empty(B, A, dtype=torch.float32, device=dev)
         d.max_action = float(max_action)
-        dp, k = _ffi.dyn_params(self.model); keep += k
+        dp, k = _ffi.dyn_params(self.model); keep += k; keep.append(dp)
         d.dyn = C.pointer(dp)
         if tensor_core:
             d.dyn_pack = _ffi.ptr(self._packed_dynamics(dp, k))
@@ -129,8 +121,25 @@ class MOBODYEnsembleDynamics(object):
         if elites.dtype != torch.int64 or not elites.is_cuda:
             elites = elites.to(device=dev, dtype=torch.int64)
         keep.append(elites)
-        d.eps, d.idx, d.elites, d.n_elites = _ffi.ptr(eps), _ffi.ptr(idx), _ffi.ptr(elites), elites.numel()
-        d.seed, d.step, d.row0 = self.seed, int(step), int(row0)
+        d.elites, d.n_elites = _ffi.ptr(elites), elites.numel()
+        d.seed = self.seed
+        return keep
+
+    def launch_step(self, obs, act, ws: StepWorkspace, *, policy=None, max_action=1.0, use_penalty=True,
+                    use_trg=True, eps=None, idx=None, n_rows_dev=None, row_ids=None, step=0, row0=0):
+        """Enqueue the fused step on the current stream; no host synchronisation.
+        obs [B,S] (B = capacity), act [B,A] or None with ``policy`` (an MLPNetwork-like module)."""
+        dev = obs.device
+        B, S = obs.shape
+        A = self.model.action_dim
+        d = _ffi.StepDesc()
+        keep = self.fill_step_desc(d, B, S, dev, policy=policy, max_action=max_action, use_penalty=use_penalty, use_trg=use_trg)  # noqa: F841
+        if policy is not None and ws.act is None:
+            ws.act = torch.empty(B, A, dtype=torch.float32, device=dev)
+        d.n_rows_dev, d.row_ids = _ffi.ptr(n_rows_dev), _ffi.ptr(row_ids)
+        d.obs, d.act = _ffi.ptr(obs), _ffi.ptr(act)
+        d.eps, d.idx = _ffi.ptr(eps), _ffi.ptr(idx)
+        d.step, d.row0 = int(step), int(row0)
         d.act_out = _ffi.ptr(ws.act)
         d.next_obs, d.reward, d.raw_reward = _ffi.ptr(ws.next_obs), _ffi.ptr(ws.reward), _ffi.ptr(ws.raw_reward)
         d.penalty, d.terminal, d.mean = _ffi.ptr(ws.penalty), _ffi.ptr(ws.terminal), _ffi.ptr(ws.mean)

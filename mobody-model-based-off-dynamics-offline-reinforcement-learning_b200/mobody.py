@@ -90,6 +90,8 @@ class MOBODY(object):
         self._t_q = self._t_pi = 0
         self._train_ws = None
         self._scalars = torch.zeros(16, dtype=torch.float32, device=self.device)
+        self._roll_ws = {}                                       # (T, B, S, A) -> rollout scratch
+        self._host_slabs, self._host_turn = [None, None], 0      # pinned staging of rollout() results
 
     def select_action(self, state, policy, cuda=False):          # mobody.py:138-144
         with torch.no_grad():
@@ -98,16 +100,40 @@ class MOBODY(object):
             return action.squeeze() if cuda else action.squeeze().cpu().numpy()
 
     # ------------------------------------------------------------------ rollout
-    @torch.no_grad()
-    def rollout_device(self, init_obss, rollout_length, use_trg=True, *, eps=None, idx=None, row0=0, out_packed=None):
-        """T-step imagined rollout entirely on the device (mobody.py:596-657 without its per-step
-        D2H copies and host masks).  One host read at the end (the transition counts).
+    def _rollout_workspace(self, T, B, S, A):
+        """Device scratch of mobody_rollout for (T, B): allocated once and reused (the result slab is not part of it)."""
+        key = (T, B, S, A)
+        ws = self._roll_ws.get(key)
+        if ws is None:
+            dev, f = self.device, dict(dtype=torch.float32, device=self.device)
+            ws = dict(obss=torch.empty(T, B, S, **f), acts=torch.empty(T, B, A, **f), nexts=torch.empty(T, B, S, **f),
+                      rews=torch.empty(T, B, 1, **f), pens=torch.empty(T, B, 1, **f), raw=torch.empty(B, 1, **f),
+                      terms=torch.empty(T, B, dtype=torch.uint8, device=dev), mean=torch.empty(7, B, S, **f),
+                      row_ids=torch.empty(T, B, dtype=torch.int64, device=dev),
+                      counts=torch.zeros(T + 2, dtype=torch.int32, device=dev),
+                      pos=torch.empty(max(T * B, 1), dtype=torch.int32, device=dev),
+                      scratch=torch.empty(int(_ffi.lib().mobody_compact_scratch_ints(T * B)), dtype=torch.int32, device=dev),
+                      stats=torch.zeros(2 + 2 * 148, dtype=torch.float64, device=dev),
+                      ticket=torch.zeros(1, dtype=torch.int32, device=dev))
+            if len(self._roll_ws) >= 4:                       # a handful of shapes per run (50 000 / 2 000 starts)
+                self._roll_ws.pop(next(iter(self._roll_ws)))
+            self._roll_ws[key] = ws
+        return ws
 
-        eps: optional [T,7,B,S] / idx: optional [T,B] injected draws (step t uses the first B_t rows,
-        exactly what the reference consumes when fed the same arrays).
-        out_packed: optional preallocated [>= T*B, 2S+A+3] CUDA tensor; the kept transitions are gathered into its
-        first rows as [obs | act | next_obs | reward | terminal | penalty] and the returned dict holds column views
-        of it (this is the slab the multi-GPU all-gather ships).
+    @torch.no_grad()
+    def rollout_device(self, init_obss, rollout_length, use_trg=True, *, eps=None, idx=None, row0=0, out_packed=None,
+                       sync=True):
+        """T-step imagined rollout entirely on the device (mobody.py:596-657 without its per-step D2H copies and
+        host masks): ONE C-ABI call (mobody_rollout) enqueues the T fused steps, the compactions between them, the
+        concatenation + penalty filter and the packing of the kept transitions.
+
+        eps: optional [T,7,B,S] / idx: optional [T,B] injected draws (step t uses the first B_t rows, exactly what
+        the reference consumes when fed the same arrays).
+        out_packed: optional preallocated [>= T*B, 2S+A+3] CUDA tensor receiving the kept transitions as rows
+        [obs | act | next_obs | reward | terminal | penalty] (the slab the multi-GPU all-gather ships).
+        sync=True: one host read at the end (row counts + reward sum); the returned dict holds [M, .] column views of
+        the slab.  sync=False: nothing is read back; the dict holds capacity-sized views (rows >= kept are
+        unspecified) and info carries device tensors only (``kept_dev``, ``counts_dev``, ``stats_dev``).
         Returns (dict of CUDA tensors, info) or (None, None) when rollout_length == 0."""
         if rollout_length == 0:
             return None, None                                    # mobody.py:602-603
@@ -115,76 +141,75 @@ class MOBODY(object):
         init_obss = _ffi.f32(init_obss, dev)
         B, S = init_obss.shape
         A = self.config["action_dim"]
-        lib, st = _ffi.lib(), _ffi.stream_ptr(dev)
-        f = dict(dtype=torch.float32, device=dev)
-        obss = torch.empty(T, B, S, **f); obss[0].copy_(init_obss)
-        nexts, acts = torch.empty(T, B, S, **f), torch.empty(T, B, A, **f)
-        rews, raws = torch.empty(T, B, 1, **f), torch.empty(B, 1, **f)
-        pens = torch.full((T, B, 1), float("inf"), **f)          # rows never written fail every `<=` filter
-        terms = torch.full((T, B), 0xFF, dtype=torch.uint8, device=dev)   # 0xFF = row not produced
-        mean = torch.empty(7, B, S, **f)
-        row_ids = torch.empty(T, B, dtype=torch.int64, device=dev)
-        row_ids[0] = torch.arange(row0, row0 + B, device=dev)
-        counts = torch.zeros(T + 2, dtype=torch.int32, device=dev); counts[0] = B   # [B_0..B_T, M]
-        pos = torch.empty(max(T * B, 1), dtype=torch.int32, device=dev)
-        scratch = torch.empty(int(lib.mobody_compact_scratch_ints(T * B)), dtype=torch.int32, device=dev)
+        W = 2 * S + A + 3
+        ws = self._rollout_workspace(T, B, S, A)
+        packed = out_packed if out_packed is not None else torch.empty(max(T * B, 1), W, dtype=torch.float32, device=dev)
+        assert packed.shape[1] == W and packed.shape[0] >= T * B and packed.is_contiguous()
         if eps is not None:
             eps = _ffi.f32(eps, dev); assert tuple(eps.shape) == (T, 7, B, S)
         if idx is not None:
             idx = torch.as_tensor(np.asarray(idx) if not torch.is_tensor(idx) else idx).to(device=dev, dtype=torch.int64).contiguous()
-        ws = StepWorkspace.__new__(StepWorkspace)
-        for t in range(T):
-            ws.next_obs, ws.reward, ws.raw_reward, ws.penalty = nexts[t], rews[t], raws, pens[t]
-            ws.terminal, ws.mean, ws.act = terms[t], mean, acts[t]
-            dyn.launch_step(obss[t], None, ws, policy=self.policy.network, max_action=self.policy.max_action,
-                            use_trg=use_trg, eps=None if eps is None else eps[t], idx=None if idx is None else idx[t],
-                            n_rows_dev=counts[t:t + 1], row_ids=row_ids[t], step=t)
-            if t + 1 < T:   # nonterm_mask compaction (mobody.py:635-639), stable order, no host round trip
-                _ffi.check(lib.mobody_compact(_ffi.KEEP_U8_ZERO, _ffi.ptr(terms[t]), None, 0.0, B, _ffi.ptr(counts[t:t + 1]),
-                                              _ffi.ptr(scratch), _ffi.ptr(pos), _ffi.ptr(counts[t + 1:t + 2]), st))
-                _ffi.check(lib.mobody_gather_pos(_ffi.ptr(nexts[t]), S, S, _ffi.ptr(pos), _ffi.ptr(counts[t + 1:t + 2]), B,
-                                                 _ffi.ptr(obss[t + 1]), S, st))
-                _ffi.check(lib.mobody_gather_pos_i64(_ffi.ptr(row_ids[t]), _ffi.ptr(pos), _ffi.ptr(counts[t + 1:t + 2]), B,
-                                                     _ffi.ptr(row_ids[t + 1]), st))
-        # concat over steps + penalty filter (mobody.py:641-653): one stable compaction over T*B slots
-        if self.config.get("filter_bad_rollout", 1):
-            kind, flags, vals, thr = _ffi.KEEP_F32_LE, None, pens, float(self.config["env_filter"])
+        counts = ws["counts"]
+        if B > 0:
+            d = _ffi.RolloutDesc()
+            keep = dyn.fill_step_desc(d.step, B, S, dev, policy=self.policy.network, max_action=self.policy.max_action,  # noqa: F841
+                                      use_trg=use_trg)
+            d.step.obs, d.step.mean, d.step.raw_reward = _ffi.ptr(init_obss), _ffi.ptr(ws["mean"]), _ffi.ptr(ws["raw"])
+            d.step.step, d.step.row0 = 0, int(row0)
+            d.T, d.filter_bad_rollout = T, int(bool(self.config.get("filter_bad_rollout", 1)))
+            d.env_filter = float(self.config.get("env_filter", 0.0))
+            d.eps_all, d.idx_all = _ffi.ptr(eps), _ffi.ptr(idx)
+            for k in ("obss", "acts", "nexts", "rews", "pens", "terms", "row_ids", "counts", "pos", "scratch", "stats", "ticket"):
+                setattr(d, k, _ffi.ptr(ws[k]))
+            d.packed = _ffi.ptr(packed)
+            _ffi.check(_ffi.lib().mobody_rollout(C.byref(d), _ffi.stream_ptr(dev)))
         else:
-            kind, flags, vals, thr = _ffi.KEEP_U8_VALID, terms, None, 0.0
-        _ffi.check(lib.mobody_compact(kind, _ffi.ptr(flags), _ffi.ptr(vals), thr, T * B, None, _ffi.ptr(scratch),
-                                      _ffi.ptr(pos), _ffi.ptr(counts[T + 1:T + 2]), st))
-        valid = terms != 0xFF
-        rew_sum = torch.where(valid, rews.view(T, B), torch.zeros((), **f)).double().sum()
-        host = torch.cat([counts.double(), rew_sum.view(1)]).cpu()       # the single host read
-        n_per_step = [int(v) for v in host[:T]]
-        M, num_transitions = int(host[T + 1]), int(sum(n_per_step))
-        termf = terms.float()
-        out = {}
+            counts.zero_(); ws["stats"][:2].zero_()
         mdev = counts[T + 1:T + 2]
-        W = 2 * S + A + 3
-        packed = out_packed if out_packed is not None else torch.empty(max(M, 1), W, **f)
-        assert packed.shape[1] == W and packed.shape[0] >= M and packed.is_contiguous()
-        c0 = 0
-        for name, src, w in (("obss", obss, S), ("actions", acts, A), ("next_obss", nexts, S), ("rewards", rews, 1),
-                             ("terminals", termf, 1), ("penalty", pens, 1)):
-            if M:   # dst[j, c0:c0+w] = src[pos[j], :]: row gather straight into the packed slab (leading dim W)
-                _ffi.check(lib.mobody_gather_pos(_ffi.ptr(src), w, w, _ffi.ptr(pos), _ffi.ptr(mdev), M,
-                                                 packed.data_ptr() + 4 * c0, W, st))
+        if sync:
+            host = torch.cat([counts.double(), ws["stats"][:2]]).cpu()       # the single host read
+            n_per_step = [int(v) for v in host[:T]]
+            M, num_transitions, rew_sum = int(host[T + 1]), int(host[T + 3]), float(host[T + 2])
+            info = {"num_transitions": num_transitions, "reward_mean": rew_sum / max(num_transitions, 1),
+                    "rows_per_step": n_per_step, "kept": M, "kept_dev": mdev}
+        else:
+            M = T * B
+            info = {"kept_dev": mdev, "counts_dev": counts, "stats_dev": ws["stats"][:2], "capacity": T * B}
+        out, c0 = {}, 0
+        for name, w in (("obss", S), ("actions", A), ("next_obss", S), ("rewards", 1), ("terminals", 1), ("penalty", 1)):
             out[name] = packed[:M, c0:c0 + w]
             c0 += w
-        info = {"num_transitions": num_transitions, "reward_mean": float(host[T + 2]) / max(num_transitions, 1),
-                "rows_per_step": n_per_step, "kept": M, "kept_dev": mdev}
+        info["packed"] = packed
         return out, info
 
+    def _host_slab(self, rows, W):
+        """Pinned staging slab for rollout() results, double-buffered: the CPU tensors a rollout() call returns stay
+        valid until the second-next rollout() call (the reference's only consumer, add_batch, copies immediately)."""
+        self._host_turn ^= 1
+        slab = self._host_slabs[self._host_turn]
+        if slab is None or slab.shape[0] < rows or slab.shape[1] != W:
+            slab = torch.empty(max(rows, 1), W, dtype=torch.float32, pin_memory=True)
+            self._host_slabs[self._host_turn] = slab
+        return slab
+
     def rollout(self, init_obss, rollout_length, use_trg=True, **kw):
-        """Reference signature and return convention (mobody.py:596-657): dict of CPU tensors + info."""
+        """Reference signature and return convention (mobody.py:596-657): dict of CPU tensors + info.
+        One D2H copy of the kept rows into a pinned staging slab; the dict values are column views of it."""
         out, info = self.rollout_device(init_obss, rollout_length, use_trg, **kw)
         if out is None:
             return None, None
         if self.config.get("filter_bad_rollout", 1):
             print("filtered rollout", info["kept"], info["num_transitions"])     # mobody.py:653
-        return {k: v.cpu() for k, v in out.items()}, {"num_transitions": info["num_transitions"],
-                                                      "reward_mean": info["reward_mean"]}
+        M, packed = info["kept"], info["packed"]
+        host = self._host_slab(M, packed.shape[1])[:M]
+        host.copy_(packed[:M], non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        S, A = self.config["state_dim"], self.config["action_dim"]
+        res, c0 = {}, 0
+        for name, w in (("obss", S), ("actions", A), ("next_obss", S), ("rewards", 1), ("terminals", 1), ("penalty", 1)):
+            res[name] = host[:, c0:c0 + w]
+            c0 += w
+        return res, {"num_transitions": info["num_transitions"], "reward_mean": info["reward_mean"]}
 
     # ------------------------------------------------------------------ train step
     def train_on_rows(self, rows, n_true):

@@ -105,9 +105,10 @@ def sharded_rollout(agent, init_obss, rollout_length, use_trg=True, *, group=Non
         return unpack_transitions(allp, widths), {"num_transitions": n, "reward_mean": float(stats[1].item()) / max(n, 1),
                                                   "kept": int(sum(counts)), "kept_per_rank": counts}
     slab = torch.empty(cap + 1, W, dtype=torch.float32, device=local.device)
-    out, info = agent.rollout_device(local, T, use_trg, row0=lo, out_packed=slab[:cap])
-    slab[cap, 0] = info["kept_dev"].float()[0]                       # in-band row count (exact below 2^24 rows)
-    slab[cap, 1] = float(info["num_transitions"]); slab[cap, 2] = float(info["reward_mean"] * info["num_transitions"])
+    out, info = agent.rollout_device(local, T, use_trg, row0=lo, out_packed=slab[:cap], sync=False)   # nothing read back
+    # in-band header row: kept rows (exact below 2^24), produced transitions, reward sum — written on the stream
+    slab[cap, 0:1] = info["kept_dev"].float()
+    slab[cap, 1:3] = info["stats_dev"].flip(0).float()
     widths = [S, probe_w, S, 1, 1, 1]
     if gather == "padded_async":
         slabs, counts_dev, work = allgather_slabs(slab, group, async_op=True)
