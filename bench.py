@@ -213,6 +213,7 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("MOBODY_PRECISION", "auto"))
     ap.add_argument("--rows", type=int, default=B_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the updates/sec measurement (short ncu runs)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -342,7 +343,7 @@ def main():
         loose = float(np.mean([a.elapsed_time(b) for a, b in lt[W:]]))
     # second BASELINE metric: Q-weighted BC updates/sec (one update = one steady-state MOBODY.train step)
     upd_dev = upd_wall = None
-    if rank == 0:
+    if rank == 0 and not args.no_train:
         upd_dev, upd_wall = gpu_train_rate(mb, dev, 128)
     clocks = sampler.stop()
 
@@ -381,13 +382,15 @@ def main():
         la = flop * Bn / (loose * 1e-3) / 1e12
         line["roofline"]["bf16_single_pass"] = {"kernel_ms": loose, "achieved": la, "frac": la / peak, "transitions_per_s": Bn / (loose * 1e-3),
                                                 "tolerance": "5e-3 relative (stated looser bound of north_star for bf16 GEMMs)"}
-    line["train"] = {"metric": "Q-weighted BC updates/sec", "value": upd_wall, "unit": "updates/s", "device_only": upd_dev,
-                     "config": {"workload": f"MOBODY.train steady state, batch 128 (128 src + 128 tar + 64 fake rows), S{S}/A{A}",
-                                "launches_per_update": 12, "dtype": "f32"}}
+    if upd_wall is not None:
+        line["train"] = {"metric": "Q-weighted BC updates/sec", "value": upd_wall, "unit": "updates/s", "device_only": upd_dev,
+                         "config": {"workload": f"MOBODY.train steady state, batch 128 (128 src + 128 tar + 64 fake rows), S{S}/A{A}",
+                                    "launches_per_update": 12, "dtype": "f32"}}
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        line["train"]["cpu_baseline"] = {"value": cpu_train_rate(128, cores), "unit": "updates/s", "cores": cores, "kind": "port",
-                                         "sample": "oracle.train_step incl. 3 buffer gathers, 5 steps after 2 warm-up"}
+        if upd_wall is not None:
+            line["train"]["cpu_baseline"] = {"value": cpu_train_rate(128, cores), "unit": "updates/s", "cores": cores, "kind": "port",
+                                             "sample": "oracle.train_step incl. 3 buffer gathers, 5 steps after 2 warm-up"}
         n = 20_000
         rate, dt = cpu_rollout_rate(n, cores, repeats=2)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",

@@ -69,6 +69,35 @@ __device__ __forceinline__ void store8(unsigned char* base, uint32_t plane_strid
 // argument is the PRE-SCALED pre-activation (see tc_swish_scales); result carries the mode's output scale
 template <int NS> __device__ __forceinline__ float swish_ns(float t) { return NS == 1 ? tc::swish_pre_tanh(t) : tc::swish_pre_ex2_rcp(t); }
 
+// v[i] = act(x[i] + b[i]) for 8 accumulator columns.  Swish layers arrive pre-scaled (tc_swish_scales); the SFU ops
+// are volatile so they stay batched: 8 independent MUFUs in flight per warp, then the dependent ones.
+template <int NS>
+__device__ __forceinline__ void act8(const uint32_t* x, const float* b, float (&v)[8], bool relu) {
+  float t[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t[i] = __uint_as_float(x[i]) + b[i];
+  if (relu) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaxf(t[i], 0.f);
+  } else if (NS == 1) {
+    float th[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) asm volatile("tanh.approx.f32 %0, %1;" : "=f"(th[i]) : "f"(t[i]));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaf(t[i], th[i], t[i]);
+  } else {
+    float e[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[i]) : "f"(t[i]));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) e[i] += 1.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(e[i]) : "f"(e[i]));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = t[i] * e[i];
+  }
+}
+
 template <int CW> __device__ __forceinline__ void tmem_ldw(uint32_t taddr, uint32_t (&x)[CW]);
 template <> __device__ __forceinline__ void tmem_ldw<8>(uint32_t taddr, uint32_t (&x)[8]) { tc::tmem_ld8(taddr, x); }
 template <> __device__ __forceinline__ void tmem_ldw<16>(uint32_t taddr, uint32_t (&x)[16]) { tc::tmem_ld16(taddr, x); }
@@ -216,35 +245,34 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
       }
     };
 
-    // 256-wide hidden layer: act(x + b) -> A_main planes; chunks complete in order, TMEM loads one chunk ahead
+    // 256-wide hidden layer: act(x + b) -> A_main planes; chunks complete in order, TMEM loads one chunk ahead.
+    // Two register sets alternate (no copies); the SFU ops of a chunk are issued back to back (act8) so their
+    // latency overlaps inside one warp instead of relying on the other three warps of the scheduler.
     auto epi_act256 = [&](int l, bool relu) {
       const float* bias = bias_of(l) + col0;
       const uint32_t t0 = lane_addr + (uint32_t)(l & 1) * 256u;
       wait_d(l);
-      uint32_t x[CW], xn[CW];
-      tmem_ldw<CW>(t0, x);
-#pragma unroll 1
-      for (int c = 0; c < 8; ++c) {
+      uint32_t xa[CW], xb[CW];
+      auto chunk = [&](int c, const uint32_t (&x)[CW]) {
         float bv[CW];
         ldbias(bias + c * 32, bv);
-        tc::tmem_ld_wait();
-        if (c + 1 < 8) tmem_ldw<CW>(t0 + (uint32_t)(c + 1) * 32u, xn);
 #pragma unroll
         for (int kg = 0; kg < KGW; ++kg) {
           float v[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float t = __uint_as_float(x[kg * 8 + i]) + bv[kg * 8 + i];
-            v[i] = relu ? fmaxf(t, 0.f) : swish_ns<NS>(t);
-          }
+          act8<NS>(&x[kg * 8], &bv[kg * 8], v, relu);
           store8<NS>(A_main, MAIN_PLANE, (uint32_t)(c * 4 + group * KGW + kg) * 2048u + (uint32_t)r * 16u, v);
         }
         signal_a(c);
-        if (c + 1 < 8) {
-          tc::tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < CW; ++i) x[i] = xn[i];
-        }
+      };
+      tmem_ldw<CW>(t0, xa);
+#pragma unroll 1
+      for (int c = 0; c < 8; c += 2) {
+        tc::tmem_ld_wait();
+        tmem_ldw<CW>(t0 + (uint32_t)(c + 1) * 32u, xb);
+        chunk(c, xa);
+        tc::tmem_ld_wait();
+        if (c + 2 < 8) tmem_ldw<CW>(t0 + (uint32_t)(c + 2) * 32u, xa);
+        chunk(c + 1, xb);
       }
       release_d(l);
       bias_done(l);
