@@ -310,10 +310,9 @@ def main():
 
     # ---- end-to-end through the public API with host buffers ----
     def one_rollout_e2e():
-        x = obs_host.to(dev, non_blocking=True)
         import contextlib, io
         with contextlib.redirect_stdout(io.StringIO()):
-            tr, info = ag.rollout(x, T)
+            tr, info = ag.rollout(obs_host, T)      # pinned HOST start states in, CPU tensors out (H2D + D2H inside)
         return tr, info
     for _ in range(2):
         one_rollout_e2e()

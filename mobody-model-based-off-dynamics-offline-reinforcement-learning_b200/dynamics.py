@@ -69,6 +69,7 @@ class MOBODYEnsembleDynamics(object):
         self._draw = 0        # Philox step counter for stand-alone step() calls in production mode
         self._dyn_pack = None  # (version key, blob) of the tensor-core weight image
         self._pol_pack = {}    # id(policy module) -> (version key, blob)
+        self._param_cache = {}  # (kind, id(module)) -> (parameters, data_ptrs, pointer struct, keep-alive list)
 
     # ------------------------------------------------------------------
     def _packed_dynamics(self, dp, keep):
@@ -96,6 +97,17 @@ class MOBODYEnsembleDynamics(object):
         return self._pol_pack[id(policy)][1]
 
     # ------------------------------------------------------------------
+    def _cached_params(self, kind, module, build):
+        """Pointer struct of a module's live parameters, rebuilt only when a parameter's storage moved (building it
+        costs ~0.1 ms of host time for the 26 ensemble tensors; the check costs a few microseconds)."""
+        ptrs = [p.data_ptr() for p in module.parameters()]
+        ent = self._param_cache.get((kind, id(module)))
+        if ent is not None and ent[0] == ptrs:
+            return ent[1], ent[2]
+        struct, keep = build(module)
+        self._param_cache[(kind, id(module))] = (ptrs, struct, keep)
+        return struct, keep
+
     def fill_step_desc(self, d, B, S, dev, *, policy=None, max_action=1.0, use_penalty=True, use_trg=True):
         """Fill the call-invariant half of a mobody_step_desc (shapes, parameter pointers, packed weight images,
         penalty/termination/elite settings).  Returns the tensors/structs that must outlive the launch."""
@@ -105,12 +117,12 @@ class MOBODYEnsembleDynamics(object):
         keep = []
         tensor_core = self.precision != "fp32"
         if policy is not None:
-            mp, k = _ffi.mlp_params(policy); keep += k; keep.append(mp)
+            mp, k = self._cached_params("pol", policy, _ffi.mlp_params); keep += k; keep.append(mp)
             d.policy = C.pointer(mp)
             if tensor_core:
                 d.policy_pack = _ffi.ptr(self._packed_policy(policy, mp, k))
         d.max_action = float(max_action)
-        dp, k = _ffi.dyn_params(self.model); keep += k; keep.append(dp)
+        dp, k = self._cached_params("dyn", self.model, _ffi.dyn_params); keep += k; keep.append(dp)
         d.dyn = C.pointer(dp)
         if tensor_core:
             d.dyn_pack = _ffi.ptr(self._packed_dynamics(dp, k))

@@ -92,6 +92,7 @@ class MOBODY(object):
         self._scalars = torch.zeros(16, dtype=torch.float32, device=self.device)
         self._roll_ws = {}                                       # (T, B, S, A) -> rollout scratch
         self._host_slabs, self._host_turn = [None, None], 0      # pinned staging of rollout() results
+        self._pipe_streams, self._pipe_hdr = None, None          # side streams / pinned header of the pipelined rollout()
 
     def select_action(self, state, policy, cuda=False):          # mobody.py:138-144
         with torch.no_grad():
@@ -100,9 +101,10 @@ class MOBODY(object):
             return action.squeeze() if cuda else action.squeeze().cpu().numpy()
 
     # ------------------------------------------------------------------ rollout
-    def _rollout_workspace(self, T, B, S, A):
-        """Device scratch of mobody_rollout for (T, B): allocated once and reused (the result slab is not part of it)."""
-        key = (T, B, S, A)
+    def _rollout_workspace(self, T, B, S, A, slot=0):
+        """Device scratch of mobody_rollout for (T, B): allocated once and reused (the result slab is not part of it).
+        ``slot`` separates workspaces of rollouts that are in flight at the same time on different streams."""
+        key = (T, B, S, A, slot)
         ws = self._roll_ws.get(key)
         if ws is None:
             dev, f = self.device, dict(dtype=torch.float32, device=self.device)
@@ -115,14 +117,14 @@ class MOBODY(object):
                       scratch=torch.empty(int(_ffi.lib().mobody_compact_scratch_ints(T * B)), dtype=torch.int32, device=dev),
                       stats=torch.zeros(2 + 2 * 148, dtype=torch.float64, device=dev),
                       ticket=torch.zeros(1, dtype=torch.int32, device=dev))
-            if len(self._roll_ws) >= 4:                       # a handful of shapes per run (50 000 / 2 000 starts)
+            if len(self._roll_ws) >= 8:                       # a handful of shapes per run (50 000 / 2 000 starts)
                 self._roll_ws.pop(next(iter(self._roll_ws)))
             self._roll_ws[key] = ws
         return ws
 
     @torch.no_grad()
     def rollout_device(self, init_obss, rollout_length, use_trg=True, *, eps=None, idx=None, row0=0, out_packed=None,
-                       sync=True):
+                       sync=True, ws_slot=0):
         """T-step imagined rollout entirely on the device (mobody.py:596-657 without its per-step D2H copies and
         host masks): ONE C-ABI call (mobody_rollout) enqueues the T fused steps, the compactions between them, the
         concatenation + penalty filter and the packing of the kept transitions.
@@ -142,7 +144,7 @@ class MOBODY(object):
         B, S = init_obss.shape
         A = self.config["action_dim"]
         W = 2 * S + A + 3
-        ws = self._rollout_workspace(T, B, S, A)
+        ws = self._rollout_workspace(T, B, S, A, ws_slot)
         packed = out_packed if out_packed is not None else torch.empty(max(T * B, 1), W, dtype=torch.float32, device=dev)
         assert packed.shape[1] == W and packed.shape[0] >= T * B and packed.is_contiguous()
         if eps is not None:
@@ -192,24 +194,79 @@ class MOBODY(object):
             self._host_slabs[self._host_turn] = slab
         return slab
 
+    PIPE_ROWS = 2 * 148 * 128     # start states per pipelined chunk: two full waves of 128-row tiles on 148 SMs
+
     def rollout(self, init_obss, rollout_length, use_trg=True, **kw):
         """Reference signature and return convention (mobody.py:596-657): dict of CPU tensors + info.
-        One D2H copy of the kept rows into a pinned staging slab; the dict values are column views of it."""
-        out, info = self.rollout_device(init_obss, rollout_length, use_trg, **kw)
-        if out is None:
+        The kept rows are copied D2H once, into a pinned staging slab; the dict values are column views of it.
+        One-step rollouts of many start states are pipelined in chunks on two side streams (H2D of chunk c+1 and D2H
+        of chunk c-1 overlap the kernels of chunk c); rows are independent and Philox is keyed on the global row id,
+        so the result is identical to the unchunked call (row order included)."""
+        T = int(rollout_length)
+        if T == 0:
             return None, None
-        if self.config.get("filter_bad_rollout", 1):
-            print("filtered rollout", info["kept"], info["num_transitions"])     # mobody.py:653
-        M, packed = info["kept"], info["packed"]
-        host = self._host_slab(M, packed.shape[1])[:M]
-        host.copy_(packed[:M], non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
         S, A = self.config["state_dim"], self.config["action_dim"]
+        W = 2 * S + A + 3
+        B = int(init_obss.shape[0])
+        if T == 1 and B >= 2 * self.PIPE_ROWS and not kw:
+            res_host, n_tr, rsum, M = self._rollout_pipelined(init_obss, use_trg, S, A, W)
+        else:
+            out, info = self.rollout_device(init_obss, T, use_trg, **kw)
+            M, packed = info["kept"], info["packed"]
+            res_host = self._host_slab(M, W)[:M]
+            res_host.copy_(packed[:M], non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            n_tr, rsum = info["num_transitions"], info["reward_mean"] * info["num_transitions"]
+        if self.config.get("filter_bad_rollout", 1):
+            print("filtered rollout", M, n_tr)                                   # mobody.py:653
         res, c0 = {}, 0
         for name, w in (("obss", S), ("actions", A), ("next_obss", S), ("rewards", 1), ("terminals", 1), ("penalty", 1)):
-            res[name] = host[:, c0:c0 + w]
+            res[name] = res_host[:, c0:c0 + w]
             c0 += w
-        return res, {"num_transitions": info["num_transitions"], "reward_mean": info["reward_mean"]}
+        return res, {"num_transitions": n_tr, "reward_mean": rsum / max(n_tr, 1)}
+
+    def _rollout_pipelined(self, init_obss, use_trg, S, A, W):
+        dev = self.device
+        if not torch.is_tensor(init_obss):
+            init_obss = torch.as_tensor(np.asarray(init_obss, dtype=np.float32))
+        B = init_obss.shape[0]
+        bounds = list(range(0, B, self.PIPE_ROWS)) + [B]
+        if bounds[-1] - bounds[-2] < self.PIPE_ROWS // 4 and len(bounds) > 2:
+            bounds.pop(-2)                                        # fold a short tail into the previous chunk
+        n = len(bounds) - 1
+        if self._pipe_streams is None:
+            self._pipe_streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)]   # 2 compute + 1 D2H
+        if self._pipe_hdr is None or self._pipe_hdr.shape[0] < n:
+            self._pipe_hdr = torch.empty(max(n, 8), 4, dtype=torch.float64, pin_memory=True)
+        cur = torch.cuda.current_stream(dev)
+        # (re)build the packed weight images on the caller's stream, before the side streams fork from it
+        self.dynamics.fill_step_desc(_ffi.StepDesc(), 1, S, dev, policy=self.policy.network, max_action=self.policy.max_action,
+                                     use_trg=use_trg)
+        ready = torch.cuda.Event(); ready.record(cur)
+        host = self._host_slab(B, W)
+        chunks = []
+        for c in range(n):
+            st = self._pipe_streams[c & 1]
+            lo, hi = bounds[c], bounds[c + 1]
+            with torch.cuda.stream(st):
+                st.wait_event(ready)
+                x = init_obss[lo:hi].to(device=dev, dtype=torch.float32, non_blocking=True)
+                out, info = self.rollout_device(x, 1, use_trg, row0=lo, sync=False, ws_slot=1 + (c & 1))
+                # [kept, produced, reward sum] of this chunk -> pinned header row (8-byte D2H, stream ordered)
+                self._pipe_hdr[c, 0:1].copy_(info["kept_dev"].double(), non_blocking=True)
+                self._pipe_hdr[c, 1:3].copy_(info["stats_dev"].flip(0), non_blocking=True)
+                ev = torch.cuda.Event(); ev.record(st)
+            chunks.append((st, ev, info["packed"], x))
+        off, n_tr, rsum = 0, 0, 0.0
+        for c, (st, ev, packed, _x) in enumerate(chunks):
+            ev.synchronize()                                      # chunk c is done; later chunks keep the GPU busy
+            m = int(self._pipe_hdr[c, 0]); n_tr += int(self._pipe_hdr[c, 1]); rsum += float(self._pipe_hdr[c, 2])
+            with torch.cuda.stream(self._pipe_streams[2]):     # dedicated copy stream: never queued behind a later chunk's kernels
+                host[off:off + m].copy_(packed[:m], non_blocking=True)
+            off += m
+        for st in self._pipe_streams:
+            st.synchronize()
+        return host[:off], n_tr, rsum, off
 
     # ------------------------------------------------------------------ train step
     def train_on_rows(self, rows, n_true):

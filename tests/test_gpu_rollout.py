@@ -69,3 +69,27 @@ def test_rollout_production_mode_shard_invariant(golden_dir):
         return m[np.lexsort(m.T[::-1])]
     both = {k: torch.cat([a[k], b[k]], 0) for k in a}
     assert np.array_equal(canon(full), canon(both))
+
+
+@pytest.mark.parametrize("precision", ["bf16x2", "fp32"])
+def test_pipelined_host_rollout_equals_single_pass(precision, capsys):
+    """rollout() with HOST start states pipelines one-step rollouts in chunks on side streams; the returned CPU
+    tensors must be bit-identical (values and row order) to the unchunked device rollout, filter included."""
+    S, A = 11, 3
+    dyn, _ = cuda_dynamics(S, A, 3, "hopper", 5.0, precision=precision)
+    ag, _ = cuda_agent(S, A, 3, env_filter=1e9)
+    ag.dynamics = dyn
+    ag.PIPE_ROWS = 4096 if precision == "fp32" else ag.PIPE_ROWS
+    B = 2 * ag.PIPE_ROWS + 1500                             # three chunks (a short tail is folded only below 1/4 chunk)
+    rng = np.random.default_rng(5)
+    obs = (np.r_[1.25, np.zeros(S - 1)][None] + 0.2 * rng.standard_normal((B, S))).astype(np.float32)
+    host_in = torch.from_numpy(obs).pin_memory()
+    probe, _ = ag.rollout_device(torch.from_numpy(obs).cuda(), 1)
+    ag.config["env_filter"] = float(probe["penalty"].median())     # a filter that really drops rows
+    tr, info = ag.rollout(host_in, 1)
+    ref, ri = ag.rollout_device(torch.from_numpy(obs).cuda(), 1)
+    assert 0 < ri["kept"] < B and info["num_transitions"] == ri["num_transitions"] == B
+    assert abs(info["reward_mean"] - ri["reward_mean"]) < 1e-5 * abs(ri["reward_mean"]) + 1e-7
+    for k in ("obss", "actions", "next_obss", "rewards", "terminals", "penalty"):
+        assert not tr[k].is_cuda and tuple(tr[k].shape) == tuple(ref[k].shape), k
+        assert torch.equal(tr[k], ref[k].cpu()), k
