@@ -125,6 +125,106 @@ __device__ void big_layer(const float* __restrict__ Xs, int ldx, int K, const fl
   __syncthreads();
 }
 
+// ---------------- warp-level tensor-core version of big_layer (train step) ----------------
+// Same contract as big_layer (Xs/Ys fp32 tiles in shared memory, live fp32 weights in global memory), but the
+// contraction runs on mma.sync m16n8k8 TF32 with both operands split on the fly into hi + lo ("3xTF32":
+// lo*hi + hi*lo + hi*hi, 22 significand bits per operand, fp32 accumulate) — fp32-class accuracy (~3e-7 relative),
+// which the train step needs: Q values of a fresh critic are small differences of O(1) terms and feed exp(3 q/mean|q|).
+// Why warp-level MMA here and tcgen05 in the rollout: the train step at batch 128 is 320 rows in 16-row tiles, a
+// latency-bound chain of ~13 dependent 256x256 layers per kernel; a 16-row tile is exactly one m16 fragment and every
+// weight is used once per CTA, so weights go straight from L2 into B fragments (nn.Linear's [out][in] layout IS the
+// "col" operand layout) with no shared-memory staging, and a layer takes a few us instead of ~23 us on the FMA pipe.
+// Warp w owns output columns [32w, 32w+32) (4 n-tiles) of every 16-row m-tile.
+__device__ __forceinline__ void mma_tf32_1688(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// hi = top 19 bits (exactly a TF32 value), lo = v - hi (exact in fp32; the MMA reads its top 19 bits)
+__device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(v) & 0xFFFFE000u;
+  lo = __float_as_uint(v - __uint_as_float(hi));
+}
+
+template <bool WT, int RPT = 8>
+__device__ void big_layer_mma(const float* __restrict__ Xs, int ldx, int K, const float* __restrict__ Wg,
+                              const float* __restrict__ bias, float* __restrict__ Ys, int act) {
+  constexpr int MT = RPT / 2;                                  // 16-row m-tiles of the 8*RPT-row tile
+  static_assert(RPT % 2 == 0, "row tile must be a multiple of 16 rows");
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int n0 = warp * 32;
+  float acc[MT][4][4];
+#pragma unroll
+  for (int m = 0; m < MT; ++m)
+#pragma unroll
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[m][n][j] = 0.f;
+  const int ksteps = (K + 7) >> 3;                             // k8 steps; Xs columns up to roundup16(K) are readable
+  // raw fp32 B values of one k8 step: [n-tile][k = t, t+4] for column n0 + 8 nt + g
+  auto load_b = [&](int s, float (&raw)[4][2]) {
+    const int kb = s * 8 + t;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int n = n0 + nt * 8 + g;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int k = kb + 4 * j;
+        raw[nt][j] = (k < K) ? (WT ? __ldg(Wg + (size_t)n * K + k) : __ldg(Wg + (size_t)k * H + n)) : 0.f;
+      }
+    }
+  };
+  constexpr int PF = 4;                                        // k8 steps of weights in flight
+  float rb[PF][4][2];
+#pragma unroll
+  for (int p = 0; p < PF; ++p) if (p < ksteps) load_b(p, rb[p]);
+#pragma unroll PF
+  for (int s = 0; s < ksteps; ++s) {
+    float (&raw)[4][2] = rb[s % PF];
+    uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      split_tf32(raw[nt][0], bh[nt][0], bl[nt][0]);
+      split_tf32(raw[nt][1], bh[nt][1], bl[nt][1]);
+    }
+    if (s + PF < ksteps) load_b(s + PF, rb[s % PF]);
+    const int kb = s * 8 + t;
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      const float* x0 = Xs + (size_t)(m * 16 + g) * ldx + kb;
+      const float* x1 = x0 + (size_t)8 * ldx;
+      uint32_t ah[4], al[4];
+      split_tf32(x0[0], ah[0], al[0]); split_tf32(x1[0], ah[1], al[1]);
+      split_tf32(x0[4], ah[2], al[2]); split_tf32(x1[4], ah[3], al[3]);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        mma_tf32_1688(acc[m][nt], al, bh[nt][0], bh[nt][1]);
+        mma_tf32_1688(acc[m][nt], ah, bl[nt][0], bl[nt][1]);
+        mma_tf32_1688(acc[m][nt], ah, bh[nt][0], bh[nt][1]);
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int m = 0; m < MT; ++m)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int c = n0 + nt * 8 + 2 * t;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        float2* p = reinterpret_cast<float2*>(Ys + (size_t)(m * 16 + g + 8 * hh) * H + c);
+        const float a0 = acc[m][nt][2 * hh], a1 = acc[m][nt][2 * hh + 1];
+        if (act == ACT_MASK) {
+          const float2 old = *p;
+          *p = make_float2(old.x > 0.f ? a0 : 0.f, old.y > 0.f ? a1 : 0.f);
+        } else {
+          *p = make_float2(apply_act(a0 + __ldg(bias + c), act, 1.f), apply_act(a1 + __ldg(bias + c + 1), act, 1.f));
+        }
+      }
+    }
+  __syncthreads();
+}
+
 // Narrow layers (N <= 32 or so): one thread per (row, column).  W is [K][ldw] (or [N][K] if WT).
 template <bool WT, int RPT = 8>
 __device__ void small_layer(const float* __restrict__ Xs, int ldx, int K, const float* __restrict__ Wg, int ldw,

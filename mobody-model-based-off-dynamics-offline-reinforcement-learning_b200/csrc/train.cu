@@ -107,12 +107,12 @@ __global__ void __launch_bounds__(NT, 1) critic_kernel(CriticArgs a) {
   }
   __syncthreads();
   // ---- TD target: y = r + nd * gamma * min_k Q'_k(s', pi(s'))   (no grad, :190-195) ----
-  big_layer<true, RPT, (RPT == 8 ? 2 : 6)>(in2_s, ldi, S, a.pi.w[0], a.pi.b[0], X0, Wst, ACT_RELU);
-  big_layer<true, RPT, (RPT == 8 ? 2 : 6)>(X0, H, H, a.pi.w[1], a.pi.b[1], X1, Wst, ACT_RELU);
+  big_layer_mma<true, RPT>(in2_s, ldi, S, a.pi.w[0], a.pi.b[0], X0, ACT_RELU);
+  big_layer_mma<true, RPT>(X0, H, H, a.pi.w[1], a.pi.b[1], X1, ACT_RELU);
   small_layer<true, RPT>(X1, H, H, a.pi.w[2], H, a.pi.b[2], A, in2_s + S, ldi, ACT_TANH, a.max_action);
   for (int k = 0; k < 2; ++k) {
-    big_layer<true, RPT, (RPT == 8 ? 2 : 6)>(in2_s, ldi, S + A, a.qt[k].w[0], a.qt[k].b[0], X0, Wst, ACT_RELU);
-    big_layer<true, RPT, (RPT == 8 ? 2 : 6)>(X0, H, H, a.qt[k].w[1], a.qt[k].b[1], X1, Wst, ACT_RELU);
+    big_layer_mma<true, RPT>(in2_s, ldi, S + A, a.qt[k].w[0], a.qt[k].b[0], X0, ACT_RELU);
+    big_layer_mma<true, RPT>(X0, H, H, a.qt[k].w[1], a.qt[k].b[1], X1, ACT_RELU);
     q_head<TM>(X1, a.qt[k].w[2], a.qt[k].b[2], k == 0 ? qa : qb);
   }
   if (tid < TM) y[tid] = rew[tid] + nd[tid] * a.gamma * fminf(qa[tid], qb[tid]);
@@ -120,9 +120,9 @@ __global__ void __launch_bounds__(NT, 1) critic_kernel(CriticArgs a) {
   // ---- Q_k(s,a): forward, mse gradient, backward to the pre-activations (:196, 207) ----
   float lsum[4] = {0.f, 0.f, 0.f, 0.f};
   for (int k = 0; k < 2; ++k) {
-    big_layer<true, RPT, (RPT == 8 ? 2 : 6)>(in_s, ldi, S + A, a.q[k].w[0], a.q[k].b[0], X0, Wst, ACT_RELU);
+    big_layer_mma<true, RPT>(in_s, ldi, S + A, a.q[k].w[0], a.q[k].b[0], X0, ACT_RELU);
     store_tile<TM>(X0, a.Hq[k][0], row0, rows);
-    big_layer<true, RPT, (RPT == 8 ? 2 : 6)>(X0, H, H, a.q[k].w[1], a.q[k].b[1], X1, Wst, ACT_RELU);
+    big_layer_mma<true, RPT>(X0, H, H, a.q[k].w[1], a.q[k].b[1], X1, ACT_RELU);
     store_tile<TM>(X1, a.Hq[k][1], row0, rows);
     q_head<TM>(X1, a.q[k].w[2], a.q[k].b[2], qa);
     if (tid < TM) {
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(NT, 1) critic_kernel(CriticArgs a) {
     __syncthreads();
     head_backward<TM>(X1, a.q[k].w[2], g3);                     // dH2 (masked)
     store_tile<TM>(X1, a.Dq[k][1], row0, rows);
-    big_layer<false, RPT, (RPT == 8 ? 2 : 6)>(X1, H, H, a.q[k].w[1], nullptr, X0, Wst, ACT_MASK);   // dH1 = (dH2 W2) * 1[H1>0], in place on H1
+    big_layer_mma<false, RPT>(X1, H, H, a.q[k].w[1], nullptr, X0, ACT_MASK);   // dH1 = (dH2 W2) * 1[H1>0], in place on H1
     store_tile<TM>(X0, a.Dq[k][0], row0, rows);
     __syncthreads();
   }
@@ -174,19 +174,19 @@ __global__ void __launch_bounds__(NT, 1) actor_kernel(ActorArgs a) {
   if (tid < TM) ones[tid] = 1.0f;
   __syncthreads();
   // ---- pi(s) (:315) ----
-  big_layer<true, RPT, (RPT == 8 ? 2 : 6)>(in_s, ldi, S, a.pi.w[0], a.pi.b[0], X0, Wst, ACT_RELU);
+  big_layer_mma<true, RPT>(in_s, ldi, S, a.pi.w[0], a.pi.b[0], X0, ACT_RELU);
   store_tile<TM>(X0, a.Hp[0], row0, rows);
-  big_layer<true, RPT, (RPT == 8 ? 2 : 6)>(X0, H, H, a.pi.w[1], a.pi.b[1], X1, Wst, ACT_RELU);
+  big_layer_mma<true, RPT>(X0, H, H, a.pi.w[1], a.pi.b[1], X1, ACT_RELU);
   store_tile<TM>(X1, a.Hp[1], row0, rows);
   small_layer<true, RPT>(X1, H, H, a.pi.w[2], H, a.pi.b[2], A, sap_s + S, ldi, ACT_TANH, a.max_action);
   for (int i = tid; i < rows * A; i += NT) { int r = i / A, j = i - r * A; a.api[(size_t)(row0 + r) * A + j] = sap_s[r * ldi + S + j]; }
   // ---- Q_k(s, pi(s)) and d q_k / d action (Q frozen, :316-317, 555-556) ----
   for (int k = 0; k < 2; ++k) {
-    big_layer<true, RPT, (RPT == 8 ? 2 : 6)>(sap_s, ldi, S + A, a.q[k].w[0], a.q[k].b[0], X0, Wst, ACT_RELU);
-    big_layer<true, RPT, (RPT == 8 ? 2 : 6)>(X0, H, H, a.q[k].w[1], a.q[k].b[1], X1, Wst, ACT_RELU);
+    big_layer_mma<true, RPT>(sap_s, ldi, S + A, a.q[k].w[0], a.q[k].b[0], X0, ACT_RELU);
+    big_layer_mma<true, RPT>(X0, H, H, a.q[k].w[1], a.q[k].b[1], X1, ACT_RELU);
     q_head<TM>(X1, a.q[k].w[2], a.q[k].b[2], qv + k * TM);
     head_backward<TM>(X1, a.q[k].w[2], ones);
-    big_layer<false, RPT, (RPT == 8 ? 2 : 6)>(X1, H, H, a.q[k].w[1], nullptr, X0, Wst, ACT_MASK);
+    big_layer_mma<false, RPT>(X1, H, H, a.q[k].w[1], nullptr, X0, ACT_MASK);
     // d q / d a_j = sum_n dH1[n] * W1[n][S+j]
     small_layer<false, RPT>(X0, H, H, a.q[k].w[0] + S, S + A, nullptr, A, gak + k * TM * A, A, ACT_NONE, 1.f);
   }
@@ -200,8 +200,8 @@ __global__ void __launch_bounds__(NT, 1) actor_kernel(ActorArgs a) {
   // ---- q_hat = min_k Q_k(s_t, a_t) on the true rows (no grad, :249-251) ----
   if (row0 < a.n_true) {
     for (int k = 0; k < 2; ++k) {
-      big_layer<true, RPT, (RPT == 8 ? 2 : 6)>(in_s, ldi, S + A, a.q[k].w[0], a.q[k].b[0], X0, Wst, ACT_RELU);
-      big_layer<true, RPT, (RPT == 8 ? 2 : 6)>(X0, H, H, a.q[k].w[1], a.q[k].b[1], X1, Wst, ACT_RELU);
+      big_layer_mma<true, RPT>(in_s, ldi, S + A, a.q[k].w[0], a.q[k].b[0], X0, ACT_RELU);
+      big_layer_mma<true, RPT>(X0, H, H, a.q[k].w[1], a.q[k].b[1], X1, ACT_RELU);
       q_head<TM>(X1, a.q[k].w[2], a.q[k].b[2], qv + k * TM);
     }
     if (tid < rows && row0 + tid < a.n_true) a.qhat[row0 + tid] = fminf(qv[tid], qv[TM + tid]);
@@ -319,9 +319,9 @@ __global__ void __launch_bounds__(NT, 1) policy_bwd_kernel(PolicyBwdArgs a) {
   load_tile<TM>(X1, a.Hp[1], row0, rows);
   load_tile<TM>(X0, a.Hp[0], row0, rows);
   __syncthreads();
-  big_layer<false, RPT, (RPT == 8 ? 2 : 6)>(d3, lda, a.A, a.pi.w[2], nullptr, X1, Wst, ACT_MASK);    // W3 is [A][256]: dH2[r][i] = sum_j d3[r][j] W3[j][i]
+  big_layer_mma<false, RPT>(d3, lda, a.A, a.pi.w[2], nullptr, X1, ACT_MASK);    // W3 is [A][256]: dH2[r][i] = sum_j d3[r][j] W3[j][i]
   store_tile<TM>(X1, a.Dp[1], row0, rows);
-  big_layer<false, RPT, (RPT == 8 ? 2 : 6)>(X1, H, H, a.pi.w[1], nullptr, X0, Wst, ACT_MASK);
+  big_layer_mma<false, RPT>(X1, H, H, a.pi.w[1], nullptr, X0, ACT_MASK);
   store_tile<TM>(X0, a.Dp[0], row0, rows);
 }
 
