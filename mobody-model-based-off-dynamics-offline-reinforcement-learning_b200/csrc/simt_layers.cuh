@@ -146,6 +146,11 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
   lo = __float_as_uint(v - __uint_as_float(hi));
 }
 
+// Operand slots are permuted so that every global / shared load is a 128-bit vector (the contraction does not care
+// which actual k sits in which k-slot as long as A and B agree, and the epilogue knows which column an n-slot is):
+//   k16 block, thread (g, t): actual k = kb + 4t + i, i = 0..3; MMA #0 takes i = 0 (slot t) and 1 (slot t+4), MMA #1
+//   takes i = 2, 3.  A: one LDS.128 per row.  B, nn.Linear [out][in] (WT): one LDG.128 per n-tile along k.
+//   B, [k][256] row-major (!WT): n-slot g of tile nt is column n0 + 4g + nt, one LDG.128 along n per actual k.
 template <bool WT, int RPT = 8>
 __device__ void big_layer_mma(const float* __restrict__ Xs, int ldx, int K, const float* __restrict__ Wg,
                               const float* __restrict__ bias, float* __restrict__ Ys, int act) {
@@ -160,68 +165,82 @@ __device__ void big_layer_mma(const float* __restrict__ Xs, int ldx, int K, cons
     for (int n = 0; n < 4; ++n)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[m][n][j] = 0.f;
-  const int ksteps = (K + 7) >> 3;                             // k8 steps; Xs columns up to roundup16(K) are readable
-  // raw fp32 B values of one k8 step: [n-tile][k = t, t+4] for column n0 + 8 nt + g
-  auto load_b = [&](int s, float (&raw)[4][2]) {
-    const int kb = s * 8 + t;
+  const int kblocks = (K + 15) >> 4;                           // Xs columns up to roundup16(K) are readable (zero or finite)
+  const bool vec = WT ? ((K & 3) == 0) : true;                 // rows of an odd-K nn.Linear weight are not 16-byte aligned
+  // raw fp32 B values of one k16 block: raw[nt][i] = B[actual k = kb + 4t + i][n-slot g of tile nt]
+  auto load_b = [&](int blk, float (&raw)[4][4]) {
+    const int k0 = blk * 16 + 4 * t;
+    if (WT) {
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      const int n = n0 + nt * 8 + g;
+      for (int nt = 0; nt < 4; ++nt) {
+        const float* w = Wg + (size_t)(n0 + nt * 8 + g) * K + k0;
+        if (vec && k0 + 3 < K) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(w));
+          raw[nt][0] = v.x; raw[nt][1] = v.y; raw[nt][2] = v.z; raw[nt][3] = v.w;
+        } else {
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int k = kb + 4 * j;
-        raw[nt][j] = (k < K) ? (WT ? __ldg(Wg + (size_t)n * K + k) : __ldg(Wg + (size_t)k * H + n)) : 0.f;
+          for (int i = 0; i < 4; ++i) raw[nt][i] = (k0 + i < K) ? __ldg(w + i) : 0.f;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k0 + i < K) v = __ldg(reinterpret_cast<const float4*>(Wg + (size_t)(k0 + i) * H + n0 + 4 * g));
+        raw[0][i] = v.x; raw[1][i] = v.y; raw[2][i] = v.z; raw[3][i] = v.w;
       }
     }
   };
-  constexpr int PF = 4;                                        // k8 steps of weights in flight
-  float rb[PF][4][2];
+  constexpr int PF = (RPT <= 2) ? 3 : 2;                       // k16 blocks of weights in flight
+  float rb[PF][4][4];
 #pragma unroll
-  for (int p = 0; p < PF; ++p) if (p < ksteps) load_b(p, rb[p]);
-#pragma unroll PF
-  for (int s = 0; s < ksteps; ++s) {
-    float (&raw)[4][2] = rb[s % PF];
-    uint32_t bh[4][2], bl[4][2];
+  for (int p = 0; p < PF; ++p) if (p < kblocks) load_b(p, rb[p]);
+  auto consume = [&](int blk, float (&raw)[4][4]) {
+    uint32_t bh[4][4], bl[4][4];
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      split_tf32(raw[nt][0], bh[nt][0], bl[nt][0]);
-      split_tf32(raw[nt][1], bh[nt][1], bl[nt][1]);
-    }
-    if (s + PF < ksteps) load_b(s + PF, rb[s % PF]);
-    const int kb = s * 8 + t;
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) split_tf32(raw[nt][i], bh[nt][i], bl[nt][i]);
+    if (blk + PF < kblocks) load_b(blk + PF, raw);             // refill this slot: PF blocks of weights stay in flight
+    const int k0 = blk * 16 + 4 * t;
 #pragma unroll
     for (int m = 0; m < MT; ++m) {
-      const float* x0 = Xs + (size_t)(m * 16 + g) * ldx + kb;
-      const float* x1 = x0 + (size_t)8 * ldx;
-      uint32_t ah[4], al[4];
-      split_tf32(x0[0], ah[0], al[0]); split_tf32(x1[0], ah[1], al[1]);
-      split_tf32(x0[4], ah[2], al[2]); split_tf32(x1[4], ah[3], al[3]);
+      const float4 x0 = *reinterpret_cast<const float4*>(Xs + (size_t)(m * 16 + g) * ldx + k0);
+      const float4 x1 = *reinterpret_cast<const float4*>(Xs + (size_t)(m * 16 + g + 8) * ldx + k0);
+      const float xr0[4] = {x0.x, x0.y, x0.z, x0.w}, xr1[4] = {x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        mma_tf32_1688(acc[m][nt], al, bh[nt][0], bh[nt][1]);
-        mma_tf32_1688(acc[m][nt], ah, bl[nt][0], bl[nt][1]);
-        mma_tf32_1688(acc[m][nt], ah, bh[nt][0], bh[nt][1]);
+      for (int h2 = 0; h2 < 2; ++h2) {                          // the two k8 MMAs of the block: i = 2 h2, 2 h2 + 1
+        uint32_t ah[4], al[4];
+        split_tf32(xr0[2 * h2], ah[0], al[0]); split_tf32(xr1[2 * h2], ah[1], al[1]);
+        split_tf32(xr0[2 * h2 + 1], ah[2], al[2]); split_tf32(xr1[2 * h2 + 1], ah[3], al[3]);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          mma_tf32_1688(acc[m][nt], al, bh[nt][2 * h2], bh[nt][2 * h2 + 1]);
+          mma_tf32_1688(acc[m][nt], ah, bl[nt][2 * h2], bl[nt][2 * h2 + 1]);
+          mma_tf32_1688(acc[m][nt], ah, bh[nt][2 * h2], bh[nt][2 * h2 + 1]);
+        }
       }
     }
+  };
+  for (int blk = 0; blk < kblocks; blk += PF) {
+#pragma unroll
+    for (int p = 0; p < PF; ++p)
+      if (blk + p < kblocks) consume(blk + p, rb[p]);          // static slot index: rb stays in registers
   }
   __syncthreads();
 #pragma unroll
   for (int m = 0; m < MT; ++m)
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      const int c = n0 + nt * 8 + 2 * t;
+    for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        float2* p = reinterpret_cast<float2*>(Ys + (size_t)(m * 16 + g + 8 * hh) * H + c);
-        const float a0 = acc[m][nt][2 * hh], a1 = acc[m][nt][2 * hh + 1];
-        if (act == ACT_MASK) {
-          const float2 old = *p;
-          *p = make_float2(old.x > 0.f ? a0 : 0.f, old.y > 0.f ? a1 : 0.f);
-        } else {
-          *p = make_float2(apply_act(a0 + __ldg(bias + c), act, 1.f), apply_act(a1 + __ldg(bias + c + 1), act, 1.f));
-        }
+      for (int j = 0; j < 4; ++j) {                             // C fragment: row g + 8 (j >> 1), n-slot 2t + (j & 1)
+        const int slot = 2 * t + (j & 1);
+        const int c = WT ? (n0 + nt * 8 + slot) : (n0 + 4 * slot + nt);
+        float* p = Ys + (size_t)(m * 16 + g + 8 * (j >> 1)) * H + c;
+        const float a = acc[m][nt][j];
+        if (act == ACT_MASK) *p = (*p > 0.f) ? a : 0.f;
+        else *p = apply_act(a + __ldg(bias + c), act, 1.f);
       }
-    }
   __syncthreads();
 }
 

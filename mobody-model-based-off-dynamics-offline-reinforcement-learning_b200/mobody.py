@@ -278,7 +278,7 @@ class MOBODY(object):
             raise NotImplementedError("mobody_b200 implements the default advantage=0, scale_Q=1, q_weighted=1 update")
         S, A = cfg["state_dim"], cfg["action_dim"]
         N = rows.shape[0]
-        nsplit = 1 if N <= 1024 else min(16, N // 512)
+        nsplit = max(1, min(16, (N + 63) // 64))    # row splits of the weight-gradient GEMMs (partials summed in Adam, fixed order)
         lib = _ffi.lib()
         need = int(lib.mobody_train_workspace_bytes(N, S, A, nsplit))
         if self._train_ws is None or self._train_ws.numel() < need:
