@@ -1,6 +1,7 @@
 // C-ABI entry points (include/mobody_b200.h).  Argument checking + kernel launches only.
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include "../../include/mobody_b200.h"
 #include "common.cuh"
 #include "tc_layout.h"
@@ -35,6 +36,8 @@ void mb_rollout_stats_launch(const float* rews, const unsigned char* terms, long
 const char* mb_tc_dyn_pack(const DynPtrs& dp, int S, int A, int ns, unsigned char* blob, cudaStream_t st);
 const char* mb_tc_mlp_pack(const MlpPtrs& mp, int din, int dout, int ns, unsigned char* blob, cudaStream_t st);
 const char* mb_tc_step_launch(const StepArgs& a, const unsigned char* dynb, const unsigned char* polb, int ns, cudaStream_t st);
+int mb_tc_use_pair();
+const char* mb_tc_pair_step_launch(const StepArgs& a, const unsigned char* dynb, const unsigned char* polb, int ns, cudaStream_t st);
 const char* mb_umma_selftest_launch(const float* A, const float* B, int K, int N, int nsplit, float* D, cudaStream_t st);
 
 const char* mb_umma2_selftest_launch(const float* A, const float* B, int K, int N, int nsplit, float* D, cudaStream_t st);
@@ -97,8 +100,11 @@ int mobody_step(const mobody_step_desc* d, void* stream) {
     case MOBODY_PREC_BF16:
       if (!d->dyn_pack) return fail(MOBODY_ERR_ARG, "mobody_step: tensor-core precision needs dyn_pack (mobody_dyn_pack)");
       if (d->policy && !d->policy_pack) return fail(MOBODY_ERR_ARG, "mobody_step: fused policy needs policy_pack (mobody_mlp_pack)");
-      err = mb_tc_step_launch(a, (const unsigned char*)d->dyn_pack, d->policy ? (const unsigned char*)d->policy_pack : nullptr,
-                              d->precision == MOBODY_PREC_BF16X2 ? 2 : 1, (cudaStream_t)stream);
+      {   // default: one CTA per 128-row tile; MOBODY_TC_PAIR=1 selects the experimental CTA-pair kernel (two tiles in flight)
+        auto launch = mb_tc_use_pair() ? mb_tc_pair_step_launch : mb_tc_step_launch;   // the packed images are laid out for it
+        err = launch(a, (const unsigned char*)d->dyn_pack, d->policy ? (const unsigned char*)d->policy_pack : nullptr,
+                     d->precision == MOBODY_PREC_BF16X2 ? 2 : 1, (cudaStream_t)stream);
+      }
       break;
     default: return fail(MOBODY_ERR_UNSUPPORTED, "mobody_step: unknown precision mode");
   }

@@ -27,11 +27,12 @@
 #include "term.cuh"
 #include "tc_prims.cuh"
 #include "tc_layout.h"
+#include "tc_epi.cuh"
 #include <stdlib.h>
 
 namespace tcs {
+using namespace tce;
 
-template <int W> __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(32 * W) : "memory"); }   // epilogue warps only
 
 constexpr int TM = 128;
 constexpr uint32_t MAIN_PLANE = 65536;   // 128 rows x 256 k x bf16
@@ -51,56 +52,6 @@ struct Bars {
   uint64_t w_full[MAX_NST], w_empty[MAX_NST], a_ready[8], d_full[2], d_empty[2], b_full[NB], b_empty[NB];
   uint32_t tmem_slot, pad;
 };
-
-template <int NS>
-__device__ __forceinline__ void store8(unsigned char* base, uint32_t plane_stride, uint32_t off, const float (&v)[8]) {
-  if (NS == 2) {
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) tc::split2(v[2 * i], v[2 * i + 1], h[i], l[i]);
-    *reinterpret_cast<uint4*>(base + off) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4*>(base + plane_stride + off) = make_uint4(l[0], l[1], l[2], l[3]);
-  } else {
-    *reinterpret_cast<uint4*>(base + off) = make_uint4(tc::pack_bf16(v[0], v[1]), tc::pack_bf16(v[2], v[3]),
-                                                       tc::pack_bf16(v[4], v[5]), tc::pack_bf16(v[6], v[7]));
-  }
-}
-
-// argument is the PRE-SCALED pre-activation (see tc_swish_scales); result carries the mode's output scale
-template <int NS> __device__ __forceinline__ float swish_ns(float t) { return NS == 1 ? tc::swish_pre_tanh(t) : tc::swish_pre_ex2_rcp(t); }
-
-// v[i] = act(x[i] + b[i]) for 8 accumulator columns.  Swish layers arrive pre-scaled (tc_swish_scales); the SFU ops
-// are volatile so they stay batched: 8 independent MUFUs in flight per warp, then the dependent ones.
-template <int NS>
-__device__ __forceinline__ void act8(const uint32_t* x, const float* b, float (&v)[8], bool relu) {
-  float t[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) t[i] = __uint_as_float(x[i]) + b[i];
-  if (relu) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = fmaxf(t[i], 0.f);
-  } else if (NS == 1) {
-    float th[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) asm volatile("tanh.approx.f32 %0, %1;" : "=f"(th[i]) : "f"(t[i]));
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = fmaf(t[i], th[i], t[i]);
-  } else {
-    float e[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[i]) : "f"(t[i]));
-#pragma unroll
-    for (int i = 0; i < 8; ++i) e[i] += 1.0f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(e[i]) : "f"(e[i]));
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = t[i] * e[i];
-  }
-}
-
-template <int CW> __device__ __forceinline__ void tmem_ldw(uint32_t taddr, uint32_t (&x)[CW]);
-template <> __device__ __forceinline__ void tmem_ldw<8>(uint32_t taddr, uint32_t (&x)[8]) { tc::tmem_ld8(taddr, x); }
-template <> __device__ __forceinline__ void tmem_ldw<16>(uint32_t taddr, uint32_t (&x)[16]) { tc::tmem_ld16(taddr, x); }
 
 // NG groups of 4 epilogue warps (one warp per TMEM lane quadrant).  Every 32-column accumulator chunk is
 // processed by ALL groups at once (group g takes columns [g*CW, (g+1)*CW) of the chunk, CW = 32/NG), so
@@ -581,14 +532,25 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
 }
 
 // ---------------- weight packing: fp32 [K][N] (any strides) -> bf16 planes in UMMA B layout ----------------
+// pair = 0: [kstep s][plane p][kgroup g][n < Np][8 k]            (one CTA stages the whole K step with one bulk copy)
+// pair = 1: [kstep s][half h][plane p][kgroup g][n_local < Np/2][8 k]   (CTA h of a pair stages its half with one bulk copy)
 __global__ void pack_weight_kernel(const float* __restrict__ W, long long stride_k, long long stride_n, int K, int N, int Kp,
-                                   int Np, int ns, float scale, __nv_bfloat16* __restrict__ out) {
+                                   int Np, int ns, int pair, float scale, __nv_bfloat16* __restrict__ out) {
   const long long total = (long long)(Kp / 16) * ns * 2 * Np * 8;
+  const int nh = Np / 2;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     int j = (int)(t & 7); long long u = t >> 3;
-    int n = (int)(u % Np); u /= Np;
-    int g = (int)(u & 1); u >>= 1;
-    int p = (int)(u % ns); int s = (int)(u / ns);
+    int n, g, p, s;
+    if (!pair) {
+      n = (int)(u % Np); u /= Np;
+      g = (int)(u & 1); u >>= 1;
+      p = (int)(u % ns); s = (int)(u / ns);
+    } else {
+      const int nl = (int)(u % nh); u /= nh;
+      g = (int)(u & 1); u >>= 1;
+      p = (int)(u % ns); u /= ns;
+      n = (int)(u & 1) * nh + nl; s = (int)(u >> 1);
+    }
     int k = s * 16 + g * 8 + j;
     float v = (k < K && n < N) ? W[k * stride_k + n * stride_n] * scale : 0.f;
     __nv_bfloat16 h = __float2bfloat16_rn(v);
@@ -602,10 +564,18 @@ __global__ void pack_bias_kernel(const float* __restrict__ b, long long stride, 
 
 }  // namespace tcs
 
+// Which kernel the packed images feed: the one-CTA-per-tile kernel (default) or the experimental CTA-pair kernel
+// (MOBODY_TC_PAIR=1; correct, but its software cross-CTA hand-offs are slower than what it saves — see DESIGN.md).
+int mb_tc_use_pair() {
+  static int pair = -1;
+  if (pair < 0) { const char* e = getenv("MOBODY_TC_PAIR"); pair = (e && atoi(e) == 1) ? 1 : 0; }
+  return pair;
+}
+
 static inline void launch_pack_w(const float* W, long long sk, long long sn, const TcGeom& g, int ns, float scale, unsigned char* out, cudaStream_t st) {
   long long total = (long long)(g.Kp / 16) * ns * 2 * g.Np * 8;
   int grid = (int)((total + 255) / 256); if (grid > 1184) grid = 1184;
-  tcs::pack_weight_kernel<<<grid, 256, 0, st>>>(W, sk, sn, g.K, g.N, g.Kp, g.Np, ns, scale, reinterpret_cast<__nv_bfloat16*>(out));
+  tcs::pack_weight_kernel<<<grid, 256, 0, st>>>(W, sk, sn, g.K, g.N, g.Kp, g.Np, ns, mb_tc_use_pair(), scale, reinterpret_cast<__nv_bfloat16*>(out));
 }
 
 // mobody_dyn_pack: all 7 members x 12 MMA layers + biases + reward_model3 vector
@@ -648,6 +618,7 @@ const char* mb_tc_mlp_pack(const MlpPtrs& mp, int din, int dout, int ns, unsigne
 
 static long long* g_tc_trace = nullptr;
 void mb_tc_set_trace(long long* buf) { g_tc_trace = buf; }
+long long* mb_tc_get_trace() { return g_tc_trace; }
 
 const char* mb_tc_step_launch(const StepArgs& a, const unsigned char* dynb, const unsigned char* polb, int ns, cudaStream_t st) {
   if (a.B <= 0) return nullptr;

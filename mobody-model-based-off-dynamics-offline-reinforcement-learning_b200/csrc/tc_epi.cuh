@@ -1,0 +1,61 @@
+// Epilogue helpers shared by the tensor-core rollout kernels (step_tc.cu: one CTA per 128-row tile;
+// step_pair.cu: CTA pair, two interleaved tiles): activation math on accumulator columns, bf16 hi/lo
+// operand stores in the UMMA K-major layout, TMEM loads, the epilogue-only named barrier.
+#pragma once
+#include "tc_prims.cuh"
+
+namespace tce {
+
+template <int W> __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(32 * W) : "memory"); }   // epilogue warps only
+
+template <int NS>
+__device__ __forceinline__ void store8(unsigned char* base, uint32_t plane_stride, uint32_t off, const float (&v)[8]) {
+  if (NS == 2) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) tc::split2(v[2 * i], v[2 * i + 1], h[i], l[i]);
+    *reinterpret_cast<uint4*>(base + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(base + plane_stride + off) = make_uint4(l[0], l[1], l[2], l[3]);
+  } else {
+    *reinterpret_cast<uint4*>(base + off) = make_uint4(tc::pack_bf16(v[0], v[1]), tc::pack_bf16(v[2], v[3]),
+                                                       tc::pack_bf16(v[4], v[5]), tc::pack_bf16(v[6], v[7]));
+  }
+}
+
+// argument is the PRE-SCALED pre-activation (see tc_swish_scales); result carries the mode's output scale
+template <int NS> __device__ __forceinline__ float swish_ns(float t) { return NS == 1 ? tc::swish_pre_tanh(t) : tc::swish_pre_ex2_rcp(t); }
+
+// v[i] = act(x[i] + b[i]) for 8 accumulator columns.  Swish layers arrive pre-scaled (tc_swish_scales); the SFU ops
+// are volatile so they stay batched: 8 independent MUFUs in flight per warp, then the dependent ones.
+template <int NS>
+__device__ __forceinline__ void act8(const uint32_t* x, const float* b, float (&v)[8], bool relu) {
+  float t[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t[i] = __uint_as_float(x[i]) + b[i];
+  if (relu) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaxf(t[i], 0.f);
+  } else if (NS == 1) {
+    float th[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) asm volatile("tanh.approx.f32 %0, %1;" : "=f"(th[i]) : "f"(t[i]));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaf(t[i], th[i], t[i]);
+  } else {
+    float e[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[i]) : "f"(t[i]));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) e[i] += 1.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) asm volatile("rcp.approx.ftz.f32 %0, %1;" : "=f"(e[i]) : "f"(e[i]));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = t[i] * e[i];
+  }
+}
+
+template <int CW> __device__ __forceinline__ void tmem_ldw(uint32_t taddr, uint32_t (&x)[CW]);
+template <> __device__ __forceinline__ void tmem_ldw<8>(uint32_t taddr, uint32_t (&x)[8]) { tc::tmem_ld8(taddr, x); }
+template <> __device__ __forceinline__ void tmem_ldw<16>(uint32_t taddr, uint32_t (&x)[16]) { tc::tmem_ld16(taddr, x); }
+
+}  // namespace tce
