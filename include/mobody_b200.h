@@ -196,6 +196,31 @@ typedef struct mobody_train_desc {
 long long mobody_train_workspace_bytes(int N, int S, int A, int nsplit);
 int mobody_train_step(const mobody_train_desc* d, void* stream);
 
+/* ---- DARA domain classifier ----
+ * mobody_classifier_step replaces the forward / double-softmax cross-entropy / backward / Adam of
+ * MOBODY.update_classifier (algo/offline_offline/mobody.py:146-181) for Classifier (:11-33): `rows` [N,row_width]
+ * is the concatenated (src, tar) and permuted batch, label[i] in {0,1} its domain.  noise_* inject the draws of
+ * torch.randn_like (parity) or are NULL (Philox keyed on (seed, draw, row, column)); noise_std = gaussian_noise_std.
+ * scalars_out: [0] loss_sa, [1] loss_sas.  Parameters and Adam moments are updated in place. */
+typedef struct mobody_classifier_desc {
+  const float* rows; int N, S, A, row_width;
+  const int* label;                              /* device int32 [N]                                        */
+  const float* noise_sas; const float* noise_sa; /* device [N,2S+A] / [N,S+A] or NULL                       */
+  float noise_std; unsigned long long seed; unsigned int draw;
+  mobody_mlp_state sas, sa, sas_m, sas_v, sa_m, sa_v;   /* sas_classifier / sa_classifier parameters + Adam moments */
+  int t;                                         /* optimiser step count AFTER this step (1-based)          */
+  float lr;                                      /* config['actor_lr'] (mobody.py:135)                      */
+  int nsplit;
+  void* workspace; long long workspace_bytes;    /* >= mobody_classifier_workspace_bytes(N, S, A, nsplit)   */
+  float* scalars_out;                            /* device float[2]                                         */
+} mobody_classifier_desc;
+long long mobody_classifier_workspace_bytes(int N, int S, int A, int nsplit);
+int mobody_classifier_step(const mobody_classifier_desc* d, void* stream);
+/* One-off source-reward relabel (mobody.py:364-378) on packed buffer rows, in place:
+ * reward += penalty_coef * clamp(log p_sas(tar)/p_sas(src) - log p_sa(tar)/p_sa(src), -10, 10); penalty_out optional [n]. */
+int mobody_dara_relabel(float* rows, long long n, int S, int A, int row_width, const mobody_mlp_params* sas,
+                        const mobody_mlp_params* sa, float penalty_coef, float* penalty_out, void* stream);
+
 /* ---- tensor-core weight images (precision MOBODY_PREC_BF16X2 / MOBODY_PREC_BF16) ----
  * The reference keeps weights as fp32 nn.Parameters (mobody_module.py:371-391, mobody.py:35-48); the
  * tcgen05 path consumes them as bf16 planes in the UMMA shared-memory layout.  Re-pack whenever the

@@ -12,7 +12,7 @@ from .module import MOBODYModule, EnsembleLinear, Swish, soft_clamp   # noqa: F4
 from .dynamics import MOBODYEnsembleDynamics, StandardScaler          # noqa: F401
 from .terminal_funs import get_termination_fn, TERM_KINDS             # noqa: F401
 from .buffer import ReplayBuffer                                      # noqa: F401
-from .mobody import MOBODY, Policy, DoubleQFunc, MLPNetwork, ValueFunc  # noqa: F401
+from .mobody import MOBODY, Policy, DoubleQFunc, MLPNetwork, ValueFunc, Classifier  # noqa: F401
 
 __all__ = ["MOBODYModule", "EnsembleLinear", "Swish", "MOBODYEnsembleDynamics", "StandardScaler",
-           "get_termination_fn", "ReplayBuffer", "MOBODY", "Policy", "DoubleQFunc", "MLPNetwork", "ValueFunc"]
+           "get_termination_fn", "ReplayBuffer", "MOBODY", "Policy", "DoubleQFunc", "MLPNetwork", "ValueFunc", "Classifier"]

@@ -69,6 +69,17 @@ class TrainDesc(C.Structure):
     ]
 
 
+class ClassifierDesc(C.Structure):
+    _fields_ = [
+        ("rows", C.c_void_p), ("N", C.c_int), ("S", C.c_int), ("A", C.c_int), ("row_width", C.c_int),
+        ("label", C.c_void_p), ("noise_sas", C.c_void_p), ("noise_sa", C.c_void_p),
+        ("noise_std", C.c_float), ("seed", C.c_ulonglong), ("draw", C.c_uint),
+        ("sas", MlpState), ("sa", MlpState), ("sas_m", MlpState), ("sas_v", MlpState), ("sa_m", MlpState), ("sa_v", MlpState),
+        ("t", C.c_int), ("lr", C.c_float), ("nsplit", C.c_int),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong), ("scalars_out", C.c_void_p),
+    ]
+
+
 _lib = None
 
 
@@ -110,6 +121,11 @@ def lib():
         L.mobody_train_workspace_bytes.restype = C.c_longlong
         L.mobody_train_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
         L.mobody_train_step.argtypes = [C.POINTER(TrainDesc), C.c_void_p]
+        L.mobody_classifier_workspace_bytes.restype = C.c_longlong
+        L.mobody_classifier_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+        L.mobody_classifier_step.argtypes = [C.POINTER(ClassifierDesc), C.c_void_p]
+        L.mobody_dara_relabel.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.POINTER(MlpParams),
+                                          C.POINTER(MlpParams), C.c_float, C.c_void_p, C.c_void_p]
         L.mobody_selftest_umma.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.mobody_selftest_umma2.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         if L.mobody_abi_version() != 1:

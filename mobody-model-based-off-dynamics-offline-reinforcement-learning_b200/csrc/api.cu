@@ -46,6 +46,11 @@ void mb_tc_set_trace(long long* buf);
 long long mb_train_workspace_bytes(int N, int S, int A, int nsplit);
 const char* mb_train_step_launch(const mobody_train_desc& d, cudaStream_t st);
 
+long long mb_classifier_workspace_bytes(int N, int S, int A, int nsplit);
+const char* mb_classifier_step_launch(const mobody_classifier_desc& d, cudaStream_t st);
+const char* mb_dara_relabel_launch(float* rows, long long n, int S, int A, int rw, const MlpPtrs& sas, const MlpPtrs& sa,
+                                   float coef, float* pen_out, cudaStream_t st);
+
 static thread_local char g_err[512] = "";
 
 static int fail(int code, const char* msg) {
@@ -250,6 +255,34 @@ int mobody_train_step(const mobody_train_desc* d, void* stream) {
   const char* err = mb_train_step_launch(*d, (cudaStream_t)stream);
   if (err) return fail(MOBODY_ERR_UNSUPPORTED, err);
   return check_launch("mobody_train_step");
+}
+
+long long mobody_classifier_workspace_bytes(int N, int S, int A, int nsplit) {
+  if (N < 1 || S < 1 || A < 1 || nsplit < 1) return 0;
+  return mb_classifier_workspace_bytes(N, S, A, nsplit);
+}
+
+int mobody_classifier_step(const mobody_classifier_desc* d, void* stream) {
+  if (!d || !d->rows || !d->label) return fail(MOBODY_ERR_ARG, "mobody_classifier_step: null descriptor / rows / label");
+  if (d->row_width != mobody_row_width(d->S, d->A)) return fail(MOBODY_ERR_ARG, "mobody_classifier_step: row_width does not match (S, A)");
+  const mobody_mlp_state* all[6] = {&d->sas, &d->sa, &d->sas_m, &d->sas_v, &d->sa_m, &d->sa_v};
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < 3; ++j)
+      if (!all[i]->w[j] || !all[i]->b[j]) return fail(MOBODY_ERR_ARG, "mobody_classifier_step: null parameter / moment pointer");
+  if (d->t < 1) return fail(MOBODY_ERR_ARG, "mobody_classifier_step: optimiser step count is 1-based");
+  const char* err = mb_classifier_step_launch(*d, (cudaStream_t)stream);
+  if (err) return fail(MOBODY_ERR_UNSUPPORTED, err);
+  return check_launch("mobody_classifier_step");
+}
+
+int mobody_dara_relabel(float* rows, long long n, int S, int A, int row_width, const mobody_mlp_params* sas,
+                        const mobody_mlp_params* sa, float penalty_coef, float* penalty_out, void* stream) {
+  if (n < 0 || !sas || !sa || (n > 0 && !rows)) return fail(MOBODY_ERR_ARG, "mobody_dara_relabel: bad arguments");
+  if (row_width != mobody_row_width(S, A)) return fail(MOBODY_ERR_ARG, "mobody_dara_relabel: row_width does not match (S, A)");
+  MlpPtrs p0, p1; memcpy(&p0, sas, sizeof(p0)); memcpy(&p1, sa, sizeof(p1));
+  const char* err = mb_dara_relabel_launch(rows, n, S, A, row_width, p0, p1, penalty_coef, penalty_out, (cudaStream_t)stream);
+  if (err) return fail(MOBODY_ERR_UNSUPPORTED, err);
+  return check_launch("mobody_dara_relabel");
 }
 
 static int nsplit_of(int precision) { return precision == MOBODY_PREC_BF16X2 ? 2 : precision == MOBODY_PREC_BF16 ? 1 : 0; }

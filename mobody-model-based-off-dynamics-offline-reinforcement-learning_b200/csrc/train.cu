@@ -14,6 +14,7 @@
 // by a tiled GEMM over the whole batch (deterministic, no atomics), optionally split over row
 // ranges whose partials are summed inside the fused Adam(+Polyak) kernel.
 #include "simt_layers.cuh"
+#include "philox.cuh"
 #include "../../include/mobody_b200.h"
 #include <math.h>
 
@@ -392,6 +393,157 @@ __global__ void adam_kernel(AdamArgs a) {
   }
 }
 
+// ---------------- DARA domain classifier (mobody.py:11-33, 146-181, 364-378) ----------------
+// Two MLPNetworks in -> 256 -> 256 -> 2: sas_classifier on [s, a, s'] and sa_classifier on [s, a], trained on
+// noise-perturbed inputs with cross_entropy applied to the SOFTMAXED outputs (the reference's double softmax).
+#define MB_STREAM_CLSN 0x636C736Eu
+struct ClsArgs {
+  const float* X; int N, S, A, rw;
+  const int* label;
+  const float* noise[2];     // [N][2S+A], [N][S+A] injected N(0,1) or nullptr -> Philox(seed, draw)
+  float std; unsigned long long seed; unsigned int draw;
+  MlpPtrs net[2];            // 0 = sas_classifier, 1 = sa_classifier
+  float* Xn[2];              // noisy inputs [N][ld_k] (weight-gradient operand of layer 1)
+  float* Hc[2][2];           // relu activations [N][256]
+  float* Dc[2][2];           // dLoss/d(pre-activation) [N][256]
+  float* d3[2];              // dLoss/d(logit) [N][2]
+  float* part;               // [n_tiles][2] cross-entropy sums (sas, sa)
+};
+
+__device__ __forceinline__ void softmax2(float z0, float z1, float& p0, float& p1) {
+  const float m = fmaxf(z0, z1), e0 = expf(z0 - m), e1 = expf(z1 - m), inv = 1.0f / (e0 + e1);
+  p0 = e0 * inv; p1 = e1 * inv;
+}
+
+template <int RPT>
+__global__ void __launch_bounds__(NT, 1) classifier_kernel(ClsArgs a) {
+  constexpr int TM = 8 * RPT;
+  extern __shared__ __align__(16) float sm[];
+  const int S = a.S, A = a.A;
+  float* X0 = sm; float* X1 = X0 + TM * H;
+  float* in_s = X1 + TM * H;                       // [TM][ld], ld <= rup16(2S+A)
+  float* z_s = in_s + TM * rup16(2 * S + A);       // [TM][2] logits
+  float* g_s = z_s + 2 * TM;                       // [TM][2] dLoss/dlogit
+  float* redbuf = g_s + 2 * TM;                    // [8]
+  const int tid = threadIdx.x, row0 = blockIdx.x * TM, rows = min(TM, a.N - row0);
+  float lsum[2] = {0.f, 0.f};
+  for (int k = 0; k < 2; ++k) {
+    const int K = k == 0 ? 2 * S + A : S + A, ld = rup16(K);
+    for (int i = tid; i < TM * ld; i += NT) {
+      const int r = i / ld, j = i - r * ld;
+      float v = 0.f;
+      if (r < rows && j < K) {
+        const size_t gr = (size_t)row0 + r;
+        v = a.X[gr * a.rw + j];                                              // [s | a | s'] are the first 2S+A columns of a row
+        if (a.std != 0.f) {
+          float nz;
+          if (a.noise[k]) nz = a.noise[k][gr * K + j];
+          else nz = philox_normal1(philox4x32_10((uint32_t)gr, ((uint32_t)k << 16) | (uint32_t)(j >> 2), a.draw, 0u,
+                                                 (uint32_t)a.seed, MB_STREAM_CLSN), j & 3);
+          v += nz * a.std;                                                     // sas += randn_like(sas) * std (:24-25, 30-31)
+        }
+        a.Xn[k][gr * ld + j] = v;
+      } else if (r < rows) a.Xn[k][((size_t)row0 + r) * ld + j] = 0.f;
+      in_s[i] = v;
+    }
+    __syncthreads();
+    big_layer_mma<true, RPT>(in_s, ld, K, a.net[k].w[0], a.net[k].b[0], X0, ACT_RELU);
+    store_tile<TM>(X0, a.Hc[k][0], row0, rows);
+    big_layer_mma<true, RPT>(X0, H, H, a.net[k].w[1], a.net[k].b[1], X1, ACT_RELU);
+    store_tile<TM>(X1, a.Hc[k][1], row0, rows);
+    small_layer<true, RPT>(X1, H, H, a.net[k].w[2], H, a.net[k].b[2], 2, z_s, 2, ACT_NONE, 1.f);
+    if (tid < TM) {
+      float g0 = 0.f, g1 = 0.f;
+      if (tid < rows) {
+        float p0, p1, q0, q1;
+        softmax2(z_s[2 * tid], z_s[2 * tid + 1], p0, p1);                      // Softmax inside Classifier.forward (:26, 32)
+        softmax2(p0, p1, q0, q1);                                              // F.cross_entropy softmaxes again (:170-171)
+        const int y = a.label[row0 + tid];
+        lsum[k] = -logf(y ? q1 : q0);
+        const float invn = 1.0f / (float)a.N;
+        const float dp0 = (q0 - (y == 0 ? 1.f : 0.f)) * invn, dp1 = (q1 - (y == 1 ? 1.f : 0.f)) * invn;   // dL/dp
+        const float dot = dp0 * p0 + dp1 * p1;
+        g0 = p0 * (dp0 - dot); g1 = p1 * (dp1 - dot);                          // through the inner softmax
+        a.d3[k][(size_t)(row0 + tid) * 2] = g0; a.d3[k][(size_t)(row0 + tid) * 2 + 1] = g1;
+      }
+      g_s[2 * tid] = g0; g_s[2 * tid + 1] = g1;
+    }
+    __syncthreads();
+    {   // relu backward of the 2-output head: dH2[r][n] = H2 > 0 ? g0 W3[0][n] + g1 W3[1][n] : 0
+      const float* w3 = a.net[k].w[2];
+      for (int i = tid; i < TM * H; i += NT) {
+        const int r = i >> 8, n = i & 255;
+        X1[i] = X1[i] > 0.f ? g_s[2 * r] * __ldg(w3 + n) + g_s[2 * r + 1] * __ldg(w3 + H + n) : 0.f;
+      }
+      __syncthreads();
+    }
+    store_tile<TM>(X1, a.Dc[k][1], row0, rows);
+    big_layer_mma<false, RPT>(X1, H, H, a.net[k].w[1], nullptr, X0, ACT_MASK);
+    store_tile<TM>(X0, a.Dc[k][0], row0, rows);
+    __syncthreads();
+  }
+  if (tid < 8) redbuf[tid] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    float v = tid < TM ? lsum[c] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (tid < TM && (tid & 31) == 0) redbuf[(tid >> 5) * 2 + c] = v;
+  }
+  __syncthreads();
+  if (tid < 2) a.part[blockIdx.x * 2 + tid] = redbuf[tid] + redbuf[2 + tid] + redbuf[4 + tid] + redbuf[6 + tid];
+}
+
+__global__ void cls_scalar_kernel(const float* __restrict__ part, int ntiles, int N, float* __restrict__ out) {
+  if (threadIdx.x < 2) {
+    float s = 0.f;
+    for (int t = 0; t < ntiles; ++t) s += part[t * 2 + threadIdx.x];
+    out[1 - threadIdx.x] = s / (float)N;                                      // out[0] = loss_sa, out[1] = loss_sas
+  }
+}
+
+// reward relabel (mobody.py:364-378): rows[i].reward += coef * clamp(log-ratio of the twice-softmaxed outputs, -10, 10)
+struct RelabelArgs { float* X; long long n; int S, A, rw; MlpPtrs net[2]; float coef; float* pen_out; };
+__global__ void __launch_bounds__(NT, 1) dara_relabel_kernel(RelabelArgs a) {
+  constexpr int RPT = 8, TM = 64;
+  extern __shared__ __align__(16) float sm[];
+  const int S = a.S, A = a.A;
+  float* X0 = sm; float* X1 = X0 + TM * H;
+  float* in_s = X1 + TM * H;
+  float* z_s = in_s + TM * rup16(2 * S + A);       // [2][TM][2]
+  const int tid = threadIdx.x;
+  for (long long row0 = (long long)blockIdx.x * TM; row0 < a.n; row0 += (long long)gridDim.x * TM) {
+    const int rows = (int)min((long long)TM, a.n - row0);
+    for (int k = 0; k < 2; ++k) {
+      const int K = k == 0 ? 2 * S + A : S + A, ld = rup16(K);
+      for (int i = tid; i < TM * ld; i += NT) {
+        const int r = i / ld, j = i - r * ld;
+        in_s[i] = (r < rows && j < K) ? a.X[(size_t)(row0 + r) * a.rw + j] : 0.f;
+      }
+      __syncthreads();
+      big_layer_mma<true, RPT>(in_s, ld, K, a.net[k].w[0], a.net[k].b[0], X0, ACT_RELU);
+      big_layer_mma<true, RPT>(X0, H, H, a.net[k].w[1], a.net[k].b[1], X1, ACT_RELU);
+      small_layer<true, RPT>(X1, H, H, a.net[k].w[2], H, a.net[k].b[2], 2, z_s + k * 2 * TM, 2, ACT_NONE, 1.f);
+    }
+    if (tid < rows) {
+      float lp[2][2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        float p0, p1, q0, q1;
+        softmax2(z_s[k * 2 * TM + 2 * tid], z_s[k * 2 * TM + 2 * tid + 1], p0, p1);
+        softmax2(p0, p1, q0, q1);
+        lp[k][0] = logf(q0 + 1e-10f); lp[k][1] = logf(q1 + 1e-10f);
+      }
+      float pen = lp[0][1] - lp[1][1] - lp[0][0] + lp[1][0];                   // sas_lp[1] - sa_lp[1] - sas_lp[0] + sa_lp[0]
+      pen = fminf(fmaxf(pen, -10.f), 10.f);
+      a.X[(size_t)(row0 + tid) * a.rw + 2 * S + A] += a.coef * pen;
+      if (a.pen_out) a.pen_out[row0 + tid] = pen;
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace trn
 
 // ---------------- host launchers ----------------
@@ -555,5 +707,88 @@ const char* mb_train_step_launch(const mobody_train_desc& d, cudaStream_t st) {
   }
   if (const char* e = mb_train_adam_launch(ap, st)) return e;
   if (d.scalars_out) cudaMemcpyAsync(d.scalars_out, ws + w.scal, 16 * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  return nullptr;
+}
+
+// ---------------- DARA classifier step / relabel (C ABI: mobody_classifier_step, mobody_dara_relabel) ----------------
+struct ClsWs { size_t Xn[2], Hc[2][2], Dc[2][2], d3[2], part, scal, g[2][6], total; int ntiles; };
+static ClsWs cls_ws(int N, int S, int A, int nsplit) {
+  ClsWs w{}; size_t o = 0;
+  auto take = [&](size_t n) { size_t r = o; o += (n + 3) & ~(size_t)3; return r; };
+  const int K[2] = {2 * S + A, S + A};
+  w.ntiles = (N + 15) / 16;
+  for (int k = 0; k < 2; ++k) {
+    w.Xn[k] = take((size_t)N * simt::rup16(K[k]));
+    for (int l = 0; l < 2; ++l) { w.Hc[k][l] = take((size_t)N * 256); w.Dc[k][l] = take((size_t)N * 256); }
+    w.d3[k] = take((size_t)N * 2);
+  }
+  w.part = take((size_t)w.ntiles * 2); w.scal = take(16);
+  for (int k = 0; k < 2; ++k) {
+    const size_t n6[6] = {(size_t)256 * K[k], 256, 256 * 256, 256, 2 * 256, 2};
+    for (int t = 0; t < 6; ++t) w.g[k][t] = take(n6[t] * nsplit);
+  }
+  w.total = o;
+  return w;
+}
+long long mb_classifier_workspace_bytes(int N, int S, int A, int nsplit) { return (long long)cls_ws(N, S, A, nsplit).total * 4; }
+
+const char* mb_classifier_step_launch(const mobody_classifier_desc& d, cudaStream_t st) {
+  const int N = d.N, S = d.S, A = d.A, ns = d.nsplit;
+  if (N < 1 || S < 1 || S > 64 || A < 1 || A > 32 || ns < 1 || ns > 64) return "classifier step: bad N/S/A/nsplit";
+  const ClsWs w = cls_ws(N, S, A, ns);
+  if (!d.workspace || d.workspace_bytes < (long long)w.total * 4) return "classifier step: workspace too small";
+  float* ws = (float*)d.workspace;
+  const mobody_mlp_state* nets[2] = {&d.sas, &d.sa};
+  const mobody_mlp_state* ms[2] = {&d.sas_m, &d.sa_m};
+  const mobody_mlp_state* vs[2] = {&d.sas_v, &d.sa_v};
+  trn::ClsArgs c{};
+  c.X = d.rows; c.N = N; c.S = S; c.A = A; c.rw = d.row_width; c.label = d.label;
+  c.noise[0] = d.noise_sas; c.noise[1] = d.noise_sa; c.std = d.noise_std; c.seed = d.seed; c.draw = d.draw;
+  for (int k = 0; k < 2; ++k) {
+    c.net[k] = as_ptrs(*nets[k]); c.Xn[k] = ws + w.Xn[k]; c.d3[k] = ws + w.d3[k];
+    for (int l = 0; l < 2; ++l) { c.Hc[k][l] = ws + w.Hc[k][l]; c.Dc[k][l] = ws + w.Dc[k][l]; }
+  }
+  c.part = ws + w.part;
+  const int tm = pick_tm(N);
+  const size_t bytes = (2 * (size_t)tm * simt::H + (size_t)tm * simt::rup16(2 * S + A) + 4 * tm + 8) * sizeof(float);
+  auto kern = tm == 64 ? trn::classifier_kernel<8> : trn::classifier_kernel<2>;
+  if (const char* e = set_smem(kern, bytes)) return e;
+  const int ntiles = (N + tm - 1) / tm;
+  kern<<<ntiles, simt::NT, bytes, st>>>(c);
+  trn::cls_scalar_kernel<<<1, 32, 0, st>>>(c.part, ntiles, N, ws + w.scal);
+  const int K[2] = {2 * S + A, S + A};
+  trn::WgradArgs g{}; g.N = N; g.nsplit = ns; g.njobs = 6;
+  for (int k = 0; k < 2; ++k) {
+    g.job[3 * k + 0] = {c.Dc[k][0], 256, c.Xn[k], simt::rup16(K[k]), ws + w.g[k][0], ws + w.g[k][1], 256, K[k]};
+    g.job[3 * k + 1] = {c.Dc[k][1], 256, c.Hc[k][0], 256, ws + w.g[k][2], ws + w.g[k][3], 256, 256};
+    g.job[3 * k + 2] = {c.d3[k], 2, c.Hc[k][1], 256, ws + w.g[k][4], ws + w.g[k][5], 2, 256};
+  }
+  if (const char* e = mb_train_wgrad_launch(g, st)) return e;
+  trn::AdamArgs ad{}; ad.nsplit = ns; ad.b1 = 0.9f; ad.b2 = 0.999f; ad.eps = 1e-8f; ad.tau = 0.f; ad.njobs = 12;
+  const double bc1 = 1.0 - pow(0.9, (double)d.t), bc2 = 1.0 - pow(0.999, (double)d.t);
+  ad.lr_over_bc1 = (float)(d.lr / bc1); ad.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+  for (int k = 0; k < 2; ++k) {
+    const int n6[6] = {256 * K[k], 256, 256 * 256, 256, 2 * 256, 2};
+    for (int t = 0; t < 6; ++t) {
+      const int li = t >> 1; const bool isw = (t & 1) == 0;
+      ad.job[6 * k + t] = {isw ? nets[k]->w[li] : nets[k]->b[li], ws + w.g[k][t], isw ? ms[k]->w[li] : ms[k]->b[li],
+                           isw ? vs[k]->w[li] : vs[k]->b[li], nullptr, n6[t]};
+    }
+  }
+  if (const char* e = mb_train_adam_launch(ad, st)) return e;
+  if (d.scalars_out) cudaMemcpyAsync(d.scalars_out, ws + w.scal, 2 * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  return nullptr;
+}
+
+const char* mb_dara_relabel_launch(float* rows, long long n, int S, int A, int rw, const MlpPtrs& sas, const MlpPtrs& sa,
+                                   float coef, float* pen_out, cudaStream_t st) {
+  if (n <= 0) return nullptr;
+  if (S < 1 || S > 64 || A < 1 || A > 32) return "dara relabel: bad S/A";
+  trn::RelabelArgs a{rows, n, S, A, rw, {sas, sa}, coef, pen_out};
+  const size_t bytes = (2 * (size_t)64 * simt::H + (size_t)64 * simt::rup16(2 * S + A) + 4 * 64) * sizeof(float);
+  if (const char* e = set_smem(trn::dara_relabel_kernel, bytes)) return e;
+  long long tiles = (n + 63) / 64;
+  int grid = (int)(tiles < 148 * 4 ? tiles : 148 * 4);
+  trn::dara_relabel_kernel<<<grid, simt::NT, bytes, st>>>(a);
   return nullptr;
 }

@@ -62,6 +62,14 @@ class DoubleQFunc(nn.Module):                                  # mobody.py:74-83
         self.network2 = MLPNetwork(state_dim + action_dim, 1, hidden_size)
 
 
+class Classifier(nn.Module):                                   # mobody.py:11-33 (domain classifier of DARA / DARC)
+    def __init__(self, state_dim, action_dim, hidden_size=256, gaussian_noise_std=1.0):
+        super().__init__()
+        self.action_dim, self.gaussian_noise_std = action_dim, gaussian_noise_std
+        self.sa_classifier = MLPNetwork(state_dim + action_dim, 2, hidden_size)
+        self.sas_classifier = MLPNetwork(2 * state_dim + action_dim, 2, hidden_size)
+
+
 class MOBODY(object):
     def __init__(self, config, device, target_entropy=None):   # mobody.py:91-135
         self.config, self.device = config, torch.device(device)
@@ -81,13 +89,17 @@ class MOBODY(object):
             p.requires_grad = False
         self.v_func = ValueFunc(S, A).to(self.device)
         self.policy = Policy(S, A, config["max_action"]).to(self.device)
+        self.classifier = Classifier(S, A, 256, config.get("gaussian_noise_std", 1.0)).to(self.device)   # :134
         self.dynamics = None                                     # injected by the caller (train_mobody.py:888)
         # Adam moments of the fused train step (torch.optim.Adam equivalents of mobody.py:127-131)
         z = lambda mlp: [torch.zeros_like(t) for t in _ffi.mlp_tensors(mlp)]      # noqa: E731
         self._adam = {"pi": (z(self.policy.network), z(self.policy.network)),
                       "q1": (z(self.q_funcs.network1), z(self.q_funcs.network1)),
                       "q2": (z(self.q_funcs.network2), z(self.q_funcs.network2))}
-        self._t_q = self._t_pi = 0
+        self._adam["sas"] = (z(self.classifier.sas_classifier), z(self.classifier.sas_classifier))
+        self._adam["sa"] = (z(self.classifier.sa_classifier), z(self.classifier.sa_classifier))
+        self._t_q = self._t_pi = self._t_cls = 0
+        self._cls_ws, self._cls_scalars = None, torch.zeros(2, dtype=torch.float32, device=self.device)
         self._train_ws = None
         self._scalars = torch.zeros(16, dtype=torch.float32, device=self.device)
         self._roll_ws = {}                                       # (T, B, S, A) -> rollout scratch
@@ -268,6 +280,71 @@ class MOBODY(object):
             st.synchronize()
         return host[:off], n_tr, rsum, off
 
+    # ------------------------------------------------------------------ DARA domain classifier
+    def classifier_step_on_rows(self, rows, label, *, noise_sas=None, noise_sa=None):
+        """One fused classifier update (forward on noise-perturbed inputs, cross-entropy on the softmaxed outputs,
+        backward, Adam) on packed batch rows [N, RW] with int32 domain labels [N].  Asynchronous; the two losses land
+        in ``self._cls_scalars`` = [loss_sa, loss_sas] (device).  mobody.py:11-33, 146-181."""
+        cfg = self.config
+        S, A = cfg["state_dim"], cfg["action_dim"]
+        N = rows.shape[0]
+        nsplit = max(1, min(16, (N + 63) // 64))
+        lib = _ffi.lib()
+        need = int(lib.mobody_classifier_workspace_bytes(N, S, A, nsplit))
+        if self._cls_ws is None or self._cls_ws.numel() < need:
+            self._cls_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        self._t_cls += 1
+        d = _ffi.ClassifierDesc()
+        d.rows, d.N, d.S, d.A, d.row_width = _ffi.ptr(rows), N, S, A, rows.shape[1]
+        d.label = _ffi.ptr(label)
+        d.noise_sas = _ffi.ptr(None if noise_sas is None else _ffi.f32(noise_sas, self.device))
+        d.noise_sa = _ffi.ptr(None if noise_sa is None else _ffi.f32(noise_sa, self.device))
+        d.noise_std, d.seed, d.draw = float(self.classifier.gaussian_noise_std), int(cfg.get("seed", 0)), self._t_cls
+        cl = self.classifier
+        d.sas, d.sa = _ffi.mlp_state(_ffi.mlp_tensors(cl.sas_classifier)), _ffi.mlp_state(_ffi.mlp_tensors(cl.sa_classifier))
+        d.sas_m, d.sas_v = _ffi.mlp_state(self._adam["sas"][0]), _ffi.mlp_state(self._adam["sas"][1])
+        d.sa_m, d.sa_v = _ffi.mlp_state(self._adam["sa"][0]), _ffi.mlp_state(self._adam["sa"][1])
+        d.t, d.lr, d.nsplit = self._t_cls, float(cfg["actor_lr"]), nsplit           # Adam(lr=actor_lr), mobody.py:135
+        d.workspace, d.workspace_bytes, d.scalars_out = _ffi.ptr(self._cls_ws), self._cls_ws.numel(), _ffi.ptr(self._cls_scalars)
+        _ffi.check(lib.mobody_classifier_step(C.byref(d), _ffi.stream_ptr(self.device)))
+        return self._cls_scalars
+
+    def update_classifier(self, src_replay_buffer, tar_replay_buffer, batch_size, writer=None, *, _inject=None):
+        """Reference signature (mobody.py:146-181) -> (loss_sa, loss_sas) as 0-d device tensors.
+        ``_inject`` optionally scripts the draws of np.random.randint / torch.randperm / torch.randn_like:
+        {src, tar, perm, noise_sas, noise_sa}."""
+        if self.config.get("penalize_fake", 0):
+            raise NotImplementedError("penalize_fake=1 mixes batch sizes the reference's own labels do not cover (mobody.py:149-162)")
+        inj = _inject or {}
+        B = int(batch_size)
+        RW = src_replay_buffer.RW
+        rows = torch.empty(2 * B, RW, dtype=torch.float32, device=self.device)
+        src_replay_buffer.sample_rows(B, inj.get("src"), out=rows[:B])
+        tar_replay_buffer.sample_rows(B, inj.get("tar"), out=rows[B:])
+        perm = inj.get("perm")
+        perm = torch.randperm(2 * B, device=self.device) if perm is None else torch.as_tensor(np.asarray(perm)).to(self.device)
+        rows = rows[perm]                                                            # :164-166
+        label = (perm >= B).to(torch.int32).contiguous()                             # zeros for src, ones for tar (:162)
+        sc = self.classifier_step_on_rows(rows, label, noise_sas=inj.get("noise_sas"), noise_sa=inj.get("noise_sa"))
+        if writer is not None and self.total_it % 5000 == 0:                         # :176-179
+            v = sc.cpu().tolist()
+            writer.add_scalar("train/sas classifier loss", v[1], global_step=self.total_it)
+            writer.add_scalar("train/sa classifier loss", v[0], global_step=self.total_it)
+        return sc[0], sc[1]
+
+    @torch.no_grad()
+    def dara_relabel(self, src_replay_buffer, penalty_out=None):
+        """One-off relabel of the source rewards with the trained classifier (mobody.py:364-378), in place on the
+        device-resident buffer rows: reward += penalty_coef * clamp(log-ratio, -10, 10)."""
+        cl = self.classifier
+        sas, k0 = _ffi.mlp_params(cl.sas_classifier)
+        sa, k1 = _ffi.mlp_params(cl.sa_classifier)
+        buf = src_replay_buffer
+        _ffi.check(_ffi.lib().mobody_dara_relabel(_ffi.ptr(buf._rows), buf.size, buf.S, buf.A, buf.RW, C.byref(sas), C.byref(sa),
+                                                  float(self.config["penalty_coef"]), _ffi.ptr(penalty_out),
+                                                  _ffi.stream_ptr(self.device)))
+        del k0, k1
+
     # ------------------------------------------------------------------ train step
     def train_on_rows(self, rows, n_true):
         """One fused critic + Polyak + actor update on packed batch rows [N, RW] (device, rows ordered
@@ -317,9 +394,12 @@ class MOBODY(object):
         cfg = self.config
         self.total_it += 1
         self.src_replay_buffer, self.tar_replay_buffer = src_replay_buffer, tar_replay_buffer
-        if self.penalty_type == "dara":
-            raise NotImplementedError("the DARA classifier prologue (mobody.py:146-181, 354-381) is outside the hot path "
-                                      "built so far (SURVEY.md section 8f rank 1); use penalty_type 'par' or 'none'")
+        if self.penalty_type == "dara" and self.total_it == 1:                                        # :354-378
+            for it in range(10 * 500):
+                loss_sa, loss_sas = self.update_classifier(src_replay_buffer, tar_replay_buffer, batch_size, writer)
+                if it % 2000 == 0:
+                    print(loss_sa, loss_sas)
+            self.dara_relabel(src_replay_buffer)
         inj = _inject or {}
         S, A = cfg["state_dim"], cfg["action_dim"]
         n_src, n_tar = int(cfg["src_ratio"] * batch_size), int(cfg["trg_ratio"] * batch_size)

@@ -240,6 +240,81 @@ def gen_train(S, A, B, seed, n_steps=3):
     return out
 
 
+def gen_classifier(S, A, B, seed, n_steps=3):
+    """update_classifier steps of the UNMODIFIED reference (mobody.py:146-181) with scripted buffer indices
+    (np.random.randint), permutation (torch.randperm) and noise (torch.randn_like); then the reward relabel of
+    mobody.py:364-378 computed with the reference Classifier.forward on the whole source buffer."""
+    _, _, _, _, ref_utils = _import_reference()
+    rng = np.random.default_rng(seed)
+    pol, ag, cfg = build_reference_agent(S, A, seed, {"penalty_type": "dara", "penalty_coef": 0.7})
+    cl = O.ClassifierState(S, A, seed)
+    pol.classifier.load_state_dict(cl.params)
+    n_src, n_tar = 1500, 400
+
+    def fill(buf, n, shift):
+        buf.state[:n] = torch.from_numpy(rng.standard_normal((n, S)).astype(np.float32))
+        buf.action[:n] = torch.from_numpy(rng.uniform(-1, 1, (n, A)).astype(np.float32))
+        buf.next_state[:n] = torch.from_numpy((rng.standard_normal((n, S)) + shift).astype(np.float32))
+        buf.reward[:n] = torch.from_numpy(rng.standard_normal((n, 1)).astype(np.float32))
+        buf.not_done[:n] = 1.0
+        buf.size = n; buf.ptr = n
+    src = ref_utils.ReplayBuffer(S, A, "cpu", max_size=n_src); fill(src, n_src, 0.0)
+    tar = ref_utils.ReplayBuffer(S, A, "cpu", max_size=n_tar); fill(tar, n_tar, 0.5)
+    inds, perms, noises = [], [], []
+    for _ in range(n_steps):
+        inds += [rng.integers(0, n_src, B), rng.integers(0, n_tar, B)]
+        perms.append(rng.permutation(2 * B))
+        noises += [rng.standard_normal((2 * B, 2 * S + A)).astype(np.float32), rng.standard_normal((2 * B, S + A)).astype(np.float32)]
+    calls = {"perm": 0, "randn": 0}
+    _rp, _rl = torch.randperm, torch.randn_like
+
+    def randperm(n, **kw):
+        r = torch.from_numpy(perms[calls["perm"]].astype(np.int64)); calls["perm"] += 1
+        assert r.numel() == n
+        return r
+
+    def randn_like(x, **kw):
+        r = torch.from_numpy(noises[calls["randn"]]); calls["randn"] += 1
+        assert tuple(r.shape) == tuple(x.shape)
+        return r
+    losses = []
+    torch.randperm, torch.randn_like = randperm, randn_like
+    try:
+        with Inject(ind_list=inds), contextlib.redirect_stdout(None), contextlib.redirect_stderr(None):
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                for _ in range(n_steps):
+                    lsa, lsas = pol.update_classifier(src, tar, B)
+                    losses.append([float(lsa), float(lsas)])
+                # reward relabel, mobody.py:364-378, through the reference's own forward
+                with torch.no_grad():
+                    sas_logits, sa_logits = pol.classifier(src.state[:n_src], src.action[:n_src], src.next_state[:n_src], with_noise=False)
+                    sas_probs, sa_probs = torch.softmax(sas_logits, -1), torch.softmax(sa_logits, -1)
+                    sas_lp, sa_lp = torch.log(sas_probs + 1e-10), torch.log(sa_probs + 1e-10)
+                    pen = (sas_lp[:, 1:] - sa_lp[:, 1:] - sas_lp[:, :1] + sa_lp[:, :1]).clamp(-10, 10)
+                    new_reward = src.reward[:n_src] + cfg["penalty_coef"] * pen
+    finally:
+        torch.randperm, torch.randn_like = _rp, _rl
+    out = dict(S=S, A=A, B=B, seed=seed, n_steps=n_steps, n_src=n_src, n_tar=n_tar, penalty_coef=np.float32(cfg["penalty_coef"]),
+               std=np.float32(cfg["gaussian_noise_std"]), lr=np.float32(cfg["actor_lr"]), losses=np.asarray(losses, np.float64),
+               reward_penalty=pen.numpy(), new_reward=new_reward.numpy())
+    for nm, b in (("src", src), ("tar", tar)):
+        for f in ("state", "action", "next_state", "reward", "not_done"):
+            out[f"{nm}_{f}"] = getattr(b, f).numpy()[:b.size].copy()
+    for i, ind in enumerate(inds):
+        out[f"ind{i}"] = ind.astype(np.int64)
+    for i, pm in enumerate(perms):
+        out[f"perm{i}"] = pm.astype(np.int64)
+    for i, nz in enumerate(noises):
+        out[f"noise{i}"] = nz
+    for k, v in pol.classifier.state_dict().items():
+        flat = v.numpy().reshape(-1)
+        out[f"post_{k}_sub"] = flat[::29].copy()
+        out[f"post_{k}_sum"] = np.float64(flat.astype(np.float64).sum())
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0); np.random.seed(0)
@@ -255,6 +330,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "buffer.npz"), **gen_buffer())
     np.savez_compressed(os.path.join(OUT, "train_S17A6_B32.npz"), **gen_train(17, 6, 32, 31))
     np.savez_compressed(os.path.join(OUT, "train_S11A3_B16.npz"), **gen_train(11, 3, 16, 32, n_steps=2))
+    np.savez_compressed(os.path.join(OUT, "classifier_S17A6_B32.npz"), **gen_classifier(17, 6, 32, 41))
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

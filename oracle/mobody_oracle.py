@@ -390,3 +390,59 @@ def train_step(ag, batch, n_true, cfg):
         adam_update(ag.policy, grads, ag.m_pi, ag.v_pi, ag.t_pi, cfg["actor_lr"])
     return dict(q_loss=float(q_loss.detach()), pi_loss=float(loss.detach()), bc_loss=float(bc.detach()), q1_mean=float(q1.detach().mean()),
                 q_policy=float(qv.detach().mean()), w_mean=float(w.mean()), w_min=float(w.min()), w_max=float(w.max()))
+
+
+# --------------------------------------------------------------------------
+# DARA domain classifier; mobody.py:11-33 (Classifier), :146-181 (update_classifier), :354-381 (reward relabel)
+# --------------------------------------------------------------------------
+class ClassifierState:
+    """Parameters + Adam state of Classifier.sa_classifier / .sas_classifier (MLPNetwork in -> 256 -> 256 -> 2)."""
+    def __init__(self, S, A, seed, H=HIDDEN):
+        self.S, self.A = S, A
+        p = OrderedDict()
+        for k, v in make_mlp_params(S + A, 2, seed + 4, H).items():
+            p["sa_classifier." + k] = v
+        for k, v in make_mlp_params(2 * S + A, 2, seed + 5, H).items():
+            p["sas_classifier." + k] = v
+        self.params = p
+        self.t = 0
+        self.m = {k: torch.zeros_like(v) for k, v in p.items()}
+        self.v = {k: torch.zeros_like(v) for k, v in p.items()}
+
+
+def classifier_forward(p, s, a, s2, noise_sas=None, noise_sa=None, std=1.0):
+    """Classifier.forward (mobody.py:20-33): returns SOFTMAXED outputs (the reference calls them logits).
+    noise_* are the N(0,1) draws of torch.randn_like (with_noise=True) or None (with_noise=False)."""
+    sas = torch.cat([s, a, s2], -1)
+    if noise_sas is not None:
+        sas = sas + noise_sas * std
+    sas_logits = torch.softmax(mlp_forward(p, sas, "sas_classifier."), dim=1)
+    sa = torch.cat([s, a], -1)
+    if noise_sa is not None:
+        sa = sa + noise_sa * std
+    sa_logits = torch.softmax(mlp_forward(p, sa, "sa_classifier."), dim=1)
+    return sas_logits, sa_logits
+
+
+def classifier_update(cl, s, a, s2, label, noise_sas, noise_sa, std, lr):
+    """One update_classifier step (mobody.py:146-181) on an already sampled, concatenated and permuted batch:
+    cross_entropy is applied to the softmaxed outputs (double softmax, kept as in the reference); Adam(lr=actor_lr)."""
+    pp = {k: v.clone().requires_grad_(True) for k, v in cl.params.items()}
+    sas_logits, sa_logits = classifier_forward(pp, s, a, s2, noise_sas, noise_sa, std)
+    loss_sas = F.cross_entropy(sas_logits, label)
+    loss_sa = F.cross_entropy(sa_logits, label)
+    grads = dict(zip(pp.keys(), torch.autograd.grad(loss_sas + loss_sa, list(pp.values()))))
+    cl.t += 1
+    with torch.no_grad():
+        adam_update(cl.params, grads, cl.m, cl.v, cl.t, lr)
+    return float(loss_sa.detach()), float(loss_sas.detach())
+
+
+@torch.no_grad()
+def dara_reward_penalty(p, s, a, s2):
+    """mobody.py:371-377: log-ratio of the twice-softmaxed classifier outputs, clamped to [-10, 10]."""
+    sas_logits, sa_logits = classifier_forward(p, s, a, s2)
+    sas_lp = torch.log(torch.softmax(sas_logits, -1) + 1e-10)
+    sa_lp = torch.log(torch.softmax(sa_logits, -1) + 1e-10)
+    pen = sas_lp[:, 1:] - sa_lp[:, 1:] - sas_lp[:, :1] + sa_lp[:, :1]
+    return pen.clamp(-10, 10)

@@ -1,0 +1,69 @@
+"""GPU parity of the DARA domain-classifier path against goldens produced by the
+reference's own MOBODY.update_classifier / Classifier.forward with scripted indices, permutation and noise.
+Tolerance: losses and relabelled rewards 1e-4 relative; post-Adam parameters as in test_gpu_train.adam_close."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import cuda_agent, rel_err
+from oracle import mobody_oracle as M
+from test_gpu_train import adam_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(g):
+    import mobody_b200 as mb
+    S, A, seed = int(g["S"]), int(g["A"]), int(g["seed"])
+    ag, _ = cuda_agent(S, A, seed, penalty_type="dara", penalty_coef=float(g["penalty_coef"]),
+                       gaussian_noise_std=float(g["std"]), actor_lr=float(g["lr"]), penalize_fake=0)
+    ag.classifier.load_state_dict(M.ClassifierState(S, A, seed).params)
+    bufs = {}
+    for nm in ("src", "tar"):
+        n = int(g["n_" + nm])
+        b = mb.ReplayBuffer(S, A, "cuda", max_size=n)
+        b.add_batch({"obss": torch.from_numpy(g[f"{nm}_state"]), "actions": torch.from_numpy(g[f"{nm}_action"]),
+                     "next_obss": torch.from_numpy(g[f"{nm}_next_state"]), "rewards": torch.from_numpy(g[f"{nm}_reward"]),
+                     "terminals": torch.from_numpy(1.0 - g[f"{nm}_not_done"])})
+        bufs[nm] = b
+    return ag, bufs
+
+
+def test_update_classifier_and_relabel_match_reference_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "classifier_S17A6_B32.npz"))
+    ag, bufs = _setup(g)
+    B, n_steps = int(g["B"]), int(g["n_steps"])
+    for it in range(n_steps):
+        loss_sa, loss_sas = ag.update_classifier(bufs["src"], bufs["tar"], B, None, _inject={
+            "src": g[f"ind{2 * it}"], "tar": g[f"ind{2 * it + 1}"], "perm": g[f"perm{it}"],
+            "noise_sas": g[f"noise{2 * it}"], "noise_sa": g[f"noise{2 * it + 1}"]})
+        got = np.array([float(loss_sa), float(loss_sas)])
+        assert np.all(np.abs(got - g["losses"][it]) <= 1e-4 * np.abs(g["losses"][it])), (it, got, g["losses"][it])
+    for k, v in ag.classifier.state_dict().items():
+        flat = v.detach().cpu().numpy().reshape(-1)
+        adam_close(flat[::29], g[f"post_{k}_sub"], float(g["lr"]), n_steps, k)
+        assert abs(flat.astype(np.float64).sum() - float(g[f"post_{k}_sum"])) <= 1e-4 * abs(float(g[f"post_{k}_sum"])) + 2e-3, k
+    pen = torch.empty(bufs["src"].size, dtype=torch.float32, device="cuda")
+    ag.dara_relabel(bufs["src"], penalty_out=pen)
+    assert rel_err(pen.cpu().numpy()[:, None], g["reward_penalty"]) < 1e-3           # log-ratios of a 3-step-old classifier: ~0.1
+    assert rel_err(bufs["src"].reward.cpu().numpy(), g["new_reward"]) < 1e-4
+
+
+def test_classifier_production_noise_and_dara_prologue(golden_dir, capsys):
+    """Philox noise path: losses stay finite and fall over a few hundred steps on separable domains; the first train()
+    call with penalty_type='dara' runs the 5000-step prologue and relabels the source rewards exactly once."""
+    g = np.load(os.path.join(golden_dir, "classifier_S17A6_B32.npz"))
+    ag, bufs = _setup(g)
+    first = None
+    for it in range(300):
+        loss_sa, loss_sas = ag.update_classifier(bufs["src"], bufs["tar"], 64)
+        if it == 0:
+            first = float(loss_sas)
+    assert np.isfinite(float(loss_sas)) and float(loss_sas) < first        # s' of the target buffer is shifted by 0.5
+    before = bufs["src"].reward.clone()
+    pen = torch.empty(bufs["src"].size, dtype=torch.float32, device="cuda")
+    ag.dara_relabel(bufs["src"], penalty_out=pen)
+    assert torch.allclose(bufs["src"].reward, before + ag.config["penalty_coef"] * pen[:, None], atol=1e-6)
+    assert float(pen.abs().max()) <= 10.0

@@ -111,6 +111,15 @@ def test_train_end_to_end_with_refresh_runs():
     torch.cuda.synchronize()
     v = ag.loss_scalars()
     assert np.isfinite(list(v.values())).all() and not torch.equal(before, ag.policy.network.network[0].weight.detach())
-    with pytest.raises(NotImplementedError):
-        ag2, _ = cuda_agent(S, A, 3, penalty_type="dara")
-        ag2.train(src, tar, 128, None, None)
+    # README headline setting: penalty_type='dara' -> 5000-step classifier prologue + one-off reward relabel, then the same step
+    ag2, _ = cuda_agent(S, A, 3, penalty_type="dara", penalty_coef=0.1)
+    ag2.dynamics = ag.dynamics
+    r0 = src.reward.clone()
+    ag2.train(src, tar, 128, None, None)
+    assert ag2._t_cls == 5000 and not torch.equal(r0, src.reward)          # classifier trained, source rewards relabelled (:364-378)
+    assert float((src.reward - r0).abs().max()) <= 0.1 * 10.0 + 1e-5       # |penalty| is clamped to 10
+    r1 = src.reward.clone()
+    ag2.train(src, tar, 128, None, None)
+    torch.cuda.synchronize()
+    assert ag2._t_cls == 5000 and torch.equal(r1, src.reward)              # the prologue runs once
+    assert np.isfinite(list(ag2.loss_scalars().values())).all()

@@ -133,6 +133,32 @@ def test_train_step_matches_reference(golden_dir, name):
             np.testing.assert_allclose(flat.astype(np.float64).sum(), float(g[f"post_{grp}_{k}_sum"]), rtol=1e-4, atol=1e-5)
 
 
+def classifier_batch(g, it):
+    """The concatenated + permuted batch update_classifier builds (mobody.py:147-167) from the scripted draws."""
+    B = int(g["B"])
+    si, ti, pm = g[f"ind{2 * it}"], g[f"ind{2 * it + 1}"], g[f"perm{it}"]
+    cat = lambda f: np.concatenate([g["src_" + f][si], g["tar_" + f][ti]], 0)[pm]          # noqa: E731
+    label = np.concatenate([np.zeros(B, np.int64), np.ones(B, np.int64)])[pm]
+    return cat("state"), cat("action"), cat("next_state"), label, g[f"noise{2 * it}"], g[f"noise{2 * it + 1}"]
+
+
+def test_classifier_update_and_relabel_match_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "classifier_S17A6_B32.npz"))
+    S, A, seed, n_steps = (int(g[k]) for k in ("S", "A", "seed", "n_steps"))
+    cl = M.ClassifierState(S, A, seed)
+    for it in range(n_steps):
+        s, a, s2, label, nz_sas, nz_sa = (torch.from_numpy(x) for x in classifier_batch(g, it))
+        lsa, lsas = M.classifier_update(cl, s, a, s2, label, nz_sas, nz_sa, float(g["std"]), float(g["lr"]))
+        np.testing.assert_allclose([lsa, lsas], g["losses"][it], rtol=2e-6)
+    for k, v in cl.params.items():
+        flat = v.numpy().reshape(-1)
+        np.testing.assert_allclose(flat[::29], g[f"post_{k}_sub"], rtol=2e-5, atol=2e-7, err_msg=k)
+        np.testing.assert_allclose(flat.astype(np.float64).sum(), float(g[f"post_{k}_sum"]), rtol=1e-4, atol=1e-5)
+    pen = M.dara_reward_penalty(cl.params, *(torch.from_numpy(g["src_" + f]) for f in ("state", "action", "next_state")))
+    np.testing.assert_allclose(pen.numpy(), g["reward_penalty"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(g["src_reward"] + float(g["penalty_coef"]) * pen.numpy(), g["new_reward"], rtol=1e-6, atol=1e-6)
+
+
 def test_philox_known_answers():
     """Random123 published KATs for philox4x32-10."""
     z = O.philox4x32_10(np.zeros(4, np.uint32), np.zeros(2, np.uint32))
