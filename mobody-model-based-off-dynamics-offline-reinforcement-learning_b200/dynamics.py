@@ -31,6 +31,20 @@ class StandardScaler(object):
         return data
 
 
+    # checkpoint side files of the reference (mobody_dynamics.py:133-154): mu.npy / std.npy are written and read,
+    # and the loaded values are then overwritten by mu = 0, std = 1 — i.e. an identity scaler either way
+    def save_scaler(self, save_path):
+        import os
+        np.save(os.path.join(save_path, "mu.npy"), np.asarray(0.0 if self.mu is None else self.mu))
+        np.save(os.path.join(save_path, "std.npy"), np.asarray(1.0 if self.std is None else self.std))
+
+    def load_scaler(self, load_path):
+        import os
+        np.load(os.path.join(load_path, "mu.npy"), allow_pickle=True)
+        np.load(os.path.join(load_path, "std.npy"), allow_pickle=True)
+        self.mu, self.std = 0, 1
+
+
 class StepWorkspace:
     """Output tensors of one step; torch owns the memory, the C side only fills it."""
 
@@ -157,6 +171,18 @@ class MOBODYEnsembleDynamics(object):
         d.penalty, d.terminal, d.mean = _ffi.ptr(ws.penalty), _ffi.ptr(ws.terminal), _ffi.ptr(ws.mean)
         _ffi.check(_ffi.lib().mobody_step(C.byref(d), _ffi.stream_ptr(dev)))
         return ws
+
+    # ------------------------------------------------------------------ checkpoints (mobody_dynamics.py:1158-1166)
+    def save(self, save_path: str) -> None:
+        import os
+        torch.save(self.model.state_dict(), os.path.join(save_path, "dynamics.pth"))
+        self.obs_scaler.save_scaler(save_path)
+
+    def load(self, load_path: str) -> None:
+        import os
+        self.model.load_state_dict(torch.load(os.path.join(load_path, "dynamics.pth"), map_location=self.model.elites.device))
+        self.obs_scaler.load_scaler(load_path)
+        self._dyn_pack = None                                     # packed tensor-core image is rebuilt on the next step
 
     @torch.no_grad()
     def step(self, obs, action, use_penalty=True, use_trg=True, *, eps=None, idx=None

@@ -413,7 +413,7 @@ class MOBODY(object):
             pred, _, _, _ = self.dynamics.step(s, a_)
             rows[:n_src, 2 * S + A] -= cfg["penalty_coef"] * ((ns - pred) ** 2).mean(1)
         if (self.total_it - 1) % 5000 == 0:                                                           # :441-475 refresh
-            self.refresh_fake_buffer(src_replay_buffer, tar_replay_buffer, inj)
+            self.refresh_fake_buffer(src_replay_buffer, tar_replay_buffer, inj, batch_size)
         if n_fake:
             self.fake_replay_buffer.sample_rows(n_fake, inj.get("fake"), out=rows[n_src + n_tar:])    # :524
         self.train_on_rows(rows, n_src + n_tar)
@@ -431,7 +431,7 @@ class MOBODY(object):
                 wandbrun.log({"train/q1": v["q1_mean"], "train/q_policy": v["q_policy"], "train/policy_loss": v["pi_loss"]},
                              step=self.total_it)
 
-    def refresh_fake_buffer(self, src_buf, tar_buf, inj=None):
+    def refresh_fake_buffer(self, src_buf, tar_buf, inj=None, batch_size=128):
         """Synthetic-data refresh (mobody.py:441-475): two policy rollouts through the learned target dynamics and one
         dynamics step on dataset (s, a) pairs, all inserted into the fake buffer without leaving the device."""
         cfg, inj = self.config, inj or {}
@@ -450,8 +450,23 @@ class MOBODY(object):
             keep = (ws.penalty < cfg["env_filter"]).squeeze(1)                                        # strict < here (quirk 5)
             self.fake_replay_buffer.add_batch({"obss": s[keep], "next_obss": ws.next_obs[keep], "actions": a_[keep],
                                                "rewards": ws.reward[keep], "terminals": ws.terminal[keep].float()[:, None]})
-        if cfg.get("rollout_from_src", 0):
-            raise NotImplementedError("rollout_from_src (mobody.py:479-513) needs the DARA classifier (SURVEY.md section 8f)")
+        if cfg.get("rollout_from_src", 0):                                                            # :477-510
+            if self.penalty_type != "dara":
+                self.update_classifier(src_buf, tar_buf, batch_size)
+            starts = torch.cat([src_buf.sample_rows(50000, inj.get("src_init2"))[:, :S],
+                                tar_buf.sample_rows(100, inj.get("tar_init2"))[:, :S]], 0).contiguous()
+            out, info = self.rollout_device(starts, cfg["rollout_from_src_length"], use_trg=False)   # source-dynamics heads
+            if out is not None:
+                if cfg.get("filter_bad_rollout", 1):
+                    print("filtered rollout", info["kept"], info["num_transitions"])
+                rows = self.fake_replay_buffer._pack(out["obss"], out["actions"], out["next_obss"], out["rewards"],
+                                                     out["terminals"], True)
+                cl = self.classifier                                                                  # :498-505 reward penalty
+                sas, k0 = _ffi.mlp_params(cl.sas_classifier)
+                sa, k1 = _ffi.mlp_params(cl.sa_classifier)
+                _ffi.check(_ffi.lib().mobody_dara_relabel(_ffi.ptr(rows), rows.shape[0], S, A, rows.shape[1], C.byref(sas),
+                                                          C.byref(sa), float(cfg["penalty_coef"]), None, _ffi.stream_ptr(self.device)))
+                self.fake_replay_buffer.add_packed(rows, rows.shape[0])
 
     # ------------------------------------------------------------------ checkpoints
     def save(self, filename):                                    # mobody.py:584-588 (optimizer files: see train step)

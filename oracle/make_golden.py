@@ -315,6 +315,26 @@ def gen_classifier(S, A, B, seed, n_steps=3):
     return out
 
 
+def gen_checkpoint_keys():
+    """Key -> shape of every checkpoint file the reference writes for this path: dynamics.pth
+    (MOBODYModule.state_dict, mobody_dynamics.py:1158-1160), <name>_actor / <name>_critic (mobody.py:584-588) and the
+    classifier (for completeness)."""
+    MOBODYModule, _, _, _, _ = _import_reference()
+    cfg = {"mopo": 0, "latent_reward": 0, "encoder_loss_coef": 1, "domain_loss_coef": 0, "cycle_loss_coef": 0}
+    out = {}
+    for S, A in ((17, 6), (11, 3)):
+        with contextlib.redirect_stdout(None):
+            m = MOBODYModule(S, A, hidden_dims=256, num_ensemble=7, num_elites=5, device="cpu", config=cfg)
+        pol, _, _ = build_reference_agent(S, A, 1)
+        out[f"S{S}A{A}"] = {
+            "dynamics.pth": {k: list(v.shape) for k, v in m.state_dict().items()},
+            "_actor": {k: list(v.shape) for k, v in pol.policy.state_dict().items()},
+            "_critic": {k: list(v.shape) for k, v in pol.q_funcs.state_dict().items()},
+            "classifier": {k: list(v.shape) for k, v in pol.classifier.state_dict().items()},
+        }
+    return out
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0); np.random.seed(0)
@@ -331,6 +351,9 @@ def main():
     np.savez_compressed(os.path.join(OUT, "train_S17A6_B32.npz"), **gen_train(17, 6, 32, 31))
     np.savez_compressed(os.path.join(OUT, "train_S11A3_B16.npz"), **gen_train(11, 3, 16, 32, n_steps=2))
     np.savez_compressed(os.path.join(OUT, "classifier_S17A6_B32.npz"), **gen_classifier(17, 6, 32, 41))
+    import json
+    with open(os.path.join(OUT, "checkpoint_keys.json"), "w") as f:
+        json.dump(gen_checkpoint_keys(), f, indent=0, sort_keys=True)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

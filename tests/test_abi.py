@@ -100,3 +100,22 @@ def test_termination_dispatch_order():
                      "door-human": 0}
     with pytest.raises(TypeError):
         mb.get_termination_fn("unknown")
+
+
+def test_checkpoint_formats_match_the_reference(golden_dir, tmp_path):
+    """dynamics.pth / _actor / _critic written by the reference load unchanged — the mirror
+    modules expose exactly the reference's state_dict keys and shapes (golden list generated from the reference)."""
+    import json
+    import torch
+    import mobody_b200 as mb
+    want = json.load(open(os.path.join(golden_dir, "checkpoint_keys.json")))
+    for tag, (S, A) in (("S17A6", (17, 6)), ("S11A3", (11, 3))):
+        m = mb.MOBODYModule(S, A, 256, 7, 5, device="cpu", config={"mopo": 0, "latent_reward": 0})
+        assert {k: list(v.shape) for k, v in m.state_dict().items()} == want[tag]["dynamics.pth"]
+        assert {k: list(v.shape) for k, v in mb.Policy(S, A, 1.0).state_dict().items()} == want[tag]["_actor"]
+        assert {k: list(v.shape) for k, v in mb.DoubleQFunc(S, A).state_dict().items()} == want[tag]["_critic"]
+        assert {k: list(v.shape) for k, v in mb.Classifier(S, A).state_dict().items()} == want[tag]["classifier"]
+    # the identity scaler writes / reads the reference's mu.npy / std.npy side files (mobody_dynamics.py:133-154)
+    sc = mb.StandardScaler()
+    sc.save_scaler(str(tmp_path)); sc.load_scaler(str(tmp_path))
+    assert sc.mu == 0 and sc.std == 1 and sorted(os.listdir(tmp_path)) == ["mu.npy", "std.npy"]

@@ -123,3 +123,8 @@ def test_train_end_to_end_with_refresh_runs():
     torch.cuda.synchronize()
     assert ag2._t_cls == 5000 and torch.equal(r1, src.reward)              # the prologue runs once
     assert np.isfinite(list(ag2.loss_scalars().values())).all()
+    # rollout_from_src (mobody.py:477-510): source-head rollout from 50 000 + 100 starts, classifier-penalised rewards
+    ag3, _ = cuda_agent(S, A, 3, penalty_type="par", penalty_coef=0.1, rollout_from_src=1, rollout_from_src_length=1)
+    ag3.dynamics = ag.dynamics
+    ag3.train(src, tar, 128, None, None)
+    assert ag3._t_cls == 1 and ag3.fake_replay_buffer.size == 50000 + 2000 + 50000 + 50100
