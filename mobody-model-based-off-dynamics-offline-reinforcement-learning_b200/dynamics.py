@@ -78,7 +78,12 @@ class MOBODYEnsembleDynamics(object):
         self.domain_loss_coef = config.get("domain_loss_coef", 0) if config else 0
         self.cycle_loss_coef = config.get("cycle_loss_coef", 0) if config else 0
         self.encode_trg_diff = getattr(model, "encode_trg_diff", 0)
-        self.precision = precision or (config or {}).get("b200_precision", "fp32")
+        # 'auto' (default): the tcgen05 kernel in its fp32-parity mode (bf16 hi+lo split, inside the 1e-4 bound) whenever
+        # it supports the shapes, else the fp32 CUDA-core kernel (any S <= 128)
+        self.precision = precision or (config or {}).get("b200_precision", "auto")
+        if self.precision == "auto":
+            S_, A_ = getattr(model, "obs_dim", 0), getattr(model, "action_dim", 0)
+            self.precision = "bf16x2" if (2 <= S_ <= 64 and 1 <= A_ <= 16) else "fp32"
         self.seed = int(seed)
         self._draw = 0        # Philox step counter for stand-alone step() calls in production mode
         self._dyn_pack = None  # (version key, blob) of the tensor-core weight image
