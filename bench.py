@@ -134,10 +134,12 @@ def cpu_rollout_rate(n_rows, threads, repeats=1):
     return info["num_transitions"] / best, best
 
 
-def synth_buffer_dict(n, seed):
+def synth_buffer_dict(n, seed, s_dim=None, a_dim=None):
+    s_dim, a_dim = s_dim or S, a_dim or A
     rng = np.random.default_rng(seed)
-    return dict(observations=synth_obs(n, seed), actions=rng.uniform(-1, 1, (n, A)).astype(np.float32),
-                next_observations=synth_obs(n, seed + 1), rewards=rng.standard_normal(n).astype(np.float32),
+    obs = lambda sd: (0.3 * np.random.default_rng(sd).standard_normal((n, s_dim))).astype(np.float32)   # noqa: E731
+    return dict(observations=obs(seed), actions=rng.uniform(-1, 1, (n, a_dim)).astype(np.float32),
+                next_observations=obs(seed + 1), rewards=rng.standard_normal(n).astype(np.float32),
                 terminals=np.zeros(n, bool))
 
 
@@ -164,13 +166,14 @@ def cpu_train_rate(batch, threads, steps=5):
     return steps / (time.perf_counter() - t0)
 
 
-def gpu_train_rate(mb, dev, batch, steps=300):
+def gpu_train_rate(mb, dev, batch, steps=300, s_dim=None, a_dim=None):
     """MOBODY.train steady state through the public API: device-resident buffers, Philox indices, fused step."""
     from helpers import cuda_agent
-    ag, _ = cuda_agent(S, A, 2, penalty_type="none")
-    src, tar = mb.ReplayBuffer(S, A, dev), mb.ReplayBuffer(S, A, dev)
-    src.convert_D4RL(synth_buffer_dict(200_000, 1)); tar.convert_D4RL(synth_buffer_dict(20_000, 2))
-    ag.fake_replay_buffer.convert_D4RL(synth_buffer_dict(50_000, 3))
+    s_dim, a_dim = s_dim or S, a_dim or A
+    ag, _ = cuda_agent(s_dim, a_dim, 2, penalty_type="none")
+    src, tar = mb.ReplayBuffer(s_dim, a_dim, dev), mb.ReplayBuffer(s_dim, a_dim, dev)
+    src.convert_D4RL(synth_buffer_dict(200_000, 1, s_dim, a_dim)); tar.convert_D4RL(synth_buffer_dict(20_000, 2, s_dim, a_dim))
+    ag.fake_replay_buffer.convert_D4RL(synth_buffer_dict(50_000, 3, s_dim, a_dim))
     ag.total_it = 1                               # steady state: the 5000-step refresh is measured by the rollout metric
     for _ in range(20):
         ag.train(src, tar, batch)
@@ -342,8 +345,10 @@ def main():
         loose = float(np.mean([a.elapsed_time(b) for a, b in lt[W:]]))
     # second BASELINE metric: Q-weighted BC updates/sec (one update = one steady-state MOBODY.train step)
     upd_dev = upd_wall = None
+    big_dev = big_wall = None
     if rank == 0 and not args.no_train:
         upd_dev, upd_wall = gpu_train_rate(mb, dev, 128)
+        big_dev, big_wall = gpu_train_rate(mb, dev, 4096, steps=40, s_dim=27, a_dim=8)     # BASELINE configs[3]: ant-shaped, batch 4096
     clocks = sampler.stop()
 
     t = torch.tensor([dev_ms, e2e_s, float(n_trans), float(e2e_trans), k_ms], dtype=torch.float64, device=dev)
@@ -384,7 +389,9 @@ def main():
     if upd_wall is not None:
         line["train"] = {"metric": "Q-weighted BC updates/sec", "value": upd_wall, "unit": "updates/s", "device_only": upd_dev,
                          "config": {"workload": f"MOBODY.train steady state, batch 128 (128 src + 128 tar + 64 fake rows), S{S}/A{A}",
-                                    "launches_per_update": 12, "dtype": "f32"}}
+                                    "launches_per_update": 12, "dtype": "f32 (3xTF32 tensor-core MMA for the 256-wide layers, fp32 elsewhere)"},
+                         "batch4096_S27A8": {"value": big_wall, "device_only": big_dev, "unit": "updates/s",
+                                             "workload": "MOBODY.train steady state, batch 4096 (4096 src + 4096 tar + 2048 fake rows), S27/A8 (BASELINE configs[3])"}}
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         if upd_wall is not None:

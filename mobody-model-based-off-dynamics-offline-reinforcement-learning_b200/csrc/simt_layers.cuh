@@ -140,10 +140,12 @@ __device__ __forceinline__ void mma_tf32_1688(float (&c)[4], const uint32_t (&a)
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// hi = top 19 bits (exactly a TF32 value), lo = v - hi (exact in fp32; the MMA reads its top 19 bits)
+// hi = top 19 bits (exactly a TF32 value), lo = v - hi (exact in fp32).  The MMA reads only the top 19 bits of an
+// operand, so lo gets half an ulp of TF32 added to its magnitude first: round-to-nearest instead of truncation
+// (unbiased; the truncation of hi is fully compensated by lo).
 __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
   hi = __float_as_uint(v) & 0xFFFFE000u;
-  lo = __float_as_uint(v - __uint_as_float(hi));
+  lo = __float_as_uint(v - __uint_as_float(hi)) + 0x1000u;
 }
 
 // Operand slots are permuted so that every global / shared load is a 128-bit vector (the contraction does not care
