@@ -23,7 +23,7 @@ struct Smem {   // carve-up of dynamic shared memory (floats)
   int ld_obs, ld_sas, ld_sa;
 };
 
-__host__ __device__ inline size_t smem_floats(int S, int A) {
+__host__ __device__ inline size_t smem_floats(int S, int A, int TM) {
   size_t n = 2 * (size_t)TM * H + 2 * KC * H;
   n += (size_t)TM * rup16(S);                 // obs (padded, zero tail)
   n += (size_t)TM * A;                        // act
@@ -36,7 +36,7 @@ __host__ __device__ inline size_t smem_floats(int S, int A) {
   return n;
 }
 
-__device__ inline Smem carve(float* base, int S, int A) {
+__device__ inline Smem carve(float* base, int S, int A, int TM) {
   Smem m; float* p = base;
   m.X0 = p; p += TM * H; m.X1 = p; p += TM * H; m.Wst = p; p += 2 * KC * H;
   m.ld_obs = rup16(S); m.obs = p; p += TM * m.ld_obs;
@@ -47,14 +47,18 @@ __device__ inline Smem carve(float* base, int S, int A) {
   return m;
 }
 
+// RPT rows per thread: the row tile is 8 * RPT rows (64 by default; 32 for wide observations, S > 64, whose
+// [obs | act | next_obs] operands would not fit next to two 64-row activation tiles).
+template <int RPT>
 __global__ void __launch_bounds__(NT, 1)
 step_kernel(StepArgs a, DynPtrs dp, MlpPtrs pol, int has_policy) {
+  constexpr int TM = 8 * RPT, TPR = NT / TM;        // rows per CTA, threads per row in the per-row phases
   extern __shared__ __align__(16) float smem_f[];
   const int S = a.S, A = a.A, B = a.B;
   const int live = a.n_rows_dev ? min(*a.n_rows_dev, B) : B;
   const int row0 = blockIdx.x * TM;
   if (row0 >= live) return;                   // whole CTA exits together
-  Smem m = carve(smem_f, S, A);
+  Smem m = carve(smem_f, S, A, TM);
   const int tid = threadIdx.x;
   const int rows = min(TM, live - row0);
 
@@ -70,9 +74,9 @@ step_kernel(StepArgs a, DynPtrs dp, MlpPtrs pol, int has_policy) {
     }
   __syncthreads();
   if (has_policy) {   // Policy.forward: relu MLP, tanh * max_action  (mobody.py:35-72)
-    big_layer<true>(m.obs, m.ld_obs, S, pol.w[0], pol.b[0], m.X0, m.Wst, ACT_RELU);
-    big_layer<true>(m.X0, H, H, pol.w[1], pol.b[1], m.X1, m.Wst, ACT_RELU);
-    small_layer<true>(m.X1, H, H, pol.w[2], H, pol.b[2], A, m.act, A, ACT_TANH, a.max_action);
+    big_layer<true, RPT>(m.obs, m.ld_obs, S, pol.w[0], pol.b[0], m.X0, m.Wst, ACT_RELU);
+    big_layer<true, RPT>(m.X0, H, H, pol.w[1], pol.b[1], m.X1, m.Wst, ACT_RELU);
+    small_layer<true, RPT>(m.X1, H, H, pol.w[2], H, pol.b[2], A, m.act, A, ACT_TANH, a.max_action);
   }
   if (a.act_out)
     for (int i = tid; i < rows * A; i += NT) a.act_out[(size_t)row0 * A + i] = m.act[i];
@@ -87,30 +91,30 @@ step_kernel(StepArgs a, DynPtrs dp, MlpPtrs pol, int has_policy) {
   const int za1 = a.use_trg ? L_ZATRG1 : L_ZASRC1, za2 = a.use_trg ? L_ZATRG2 : L_ZASRC2;
   // ---- 7 members: forward_trg / forward_src (mobody_module.py:315-330) ----
   for (int e = 0; e < MB_E; ++e) {
-    big_layer<false>(m.obs, m.ld_obs, S, dp.w[L_ZS1] + (size_t)e * S * H, dp.b[L_ZS1] + e * H, m.X0, m.Wst, ACT_SWISH);
-    big_layer<false>(m.X0, H, H, dp.w[L_ZS2] + (size_t)e * H * H, dp.b[L_ZS2] + e * H, m.X1, m.Wst, ACT_SWISH);
+    big_layer<false, RPT>(m.obs, m.ld_obs, S, dp.w[L_ZS1] + (size_t)e * S * H, dp.b[L_ZS1] + e * H, m.X0, m.Wst, ACT_SWISH);
+    big_layer<false, RPT>(m.X0, H, H, dp.w[L_ZS2] + (size_t)e * H * H, dp.b[L_ZS2] + e * H, m.X1, m.Wst, ACT_SWISH);
     // zs3: only the mu half (first 16 of 32 columns) is used at inference (:223-225, 237-243)
-    small_layer<false>(m.X1, H, H, dp.w[L_ZS3] + (size_t)e * H * 2 * MB_LATENT, 2 * MB_LATENT,
+    small_layer<false, RPT>(m.X1, H, H, dp.w[L_ZS3] + (size_t)e * H * 2 * MB_LATENT, 2 * MB_LATENT,
                        dp.b[L_ZS3] + e * 2 * MB_LATENT, MB_LATENT, m.zs, MB_LATENT, ACT_NONE, 1.f);
     for (int i = tid; i < TM * MB_LATENT; i += NT) m.sa[(i >> 4) * m.ld_sa + (i & 15)] = m.zs[i];
     __syncthreads();
-    small_layer<false>(m.sa, m.ld_sa, MB_LATENT + A, dp.w[za1] + (size_t)e * (MB_LATENT + A) * MB_ZAH, MB_ZAH,
+    small_layer<false, RPT>(m.sa, m.ld_sa, MB_LATENT + A, dp.w[za1] + (size_t)e * (MB_LATENT + A) * MB_ZAH, MB_ZAH,
                        dp.b[za1] + e * MB_ZAH, MB_ZAH, m.g, MB_ZAH, ACT_SWISH, 1.f);
-    small_layer<false>(m.g, MB_ZAH, MB_ZAH, dp.w[za2] + (size_t)e * MB_ZAH * 2 * MB_LATENT, 2 * MB_LATENT,
+    small_layer<false, RPT>(m.g, MB_ZAH, MB_ZAH, dp.w[za2] + (size_t)e * MB_ZAH * 2 * MB_LATENT, 2 * MB_LATENT,
                        dp.b[za2] + e * 2 * MB_LATENT, MB_LATENT, m.z, MB_LATENT, ACT_NONE, 1.f);
     for (int i = tid; i < TM * MB_LATENT; i += NT) m.z[i] = m.zs[i] + m.z[i];      // z_ns = zs + za
     __syncthreads();
-    big_layer<false>(m.z, MB_LATENT, MB_LATENT, dp.w[L_T1] + (size_t)e * MB_LATENT * H, dp.b[L_T1] + e * H, m.X0, m.Wst, ACT_SWISH);
-    big_layer<false>(m.X0, H, H, dp.w[L_T2] + (size_t)e * H * H, dp.b[L_T2] + e * H, m.X1, m.Wst, ACT_SWISH);
+    big_layer<false, RPT>(m.z, MB_LATENT, MB_LATENT, dp.w[L_T1] + (size_t)e * MB_LATENT * H, dp.b[L_T1] + e * H, m.X0, m.Wst, ACT_SWISH);
+    big_layer<false, RPT>(m.X0, H, H, dp.w[L_T2] + (size_t)e * H * H, dp.b[L_T2] + e * H, m.X1, m.Wst, ACT_SWISH);
     // transition3 -> mean[e] ; staged through nobs then written to global (info['samples'])
-    small_layer<false>(m.X1, H, H, dp.w[L_T3] + (size_t)e * H * S, S, dp.b[L_T3] + e * S, S, m.nobs, S, ACT_NONE, 1.f);
+    small_layer<false, RPT>(m.X1, H, H, dp.w[L_T3] + (size_t)e * H * S, S, dp.b[L_T3] + e * S, S, m.nobs, S, ACT_NONE, 1.f);
     for (int i = tid; i < rows * S; i += NT) a.mean[((size_t)e * B + row0) * S + i] = m.nobs[i];
     __syncthreads();
   }
 
   // ---- ensemble statistics, noise, pick, penalty (mobody_dynamics.py:218-259) ----
   {
-    const int r = tid >> 2, q = tid & 3;     // 4 threads per row; thread q owns dim blocks q, q+4, ...
+    const int r = tid / TPR, q = tid % TPR;  // TPR threads per row; thread q owns dim blocks q, q+TPR, ...
     float d2[MB_E];
 #pragma unroll
     for (int e = 0; e < MB_E; ++e) d2[e] = 0.f;
@@ -120,7 +124,7 @@ step_kernel(StepArgs a, DynPtrs dp, MlpPtrs pol, int has_policy) {
                                                 : a.row0 + (unsigned long long)(row0 + r);
       if (a.idx) member = (int)a.idx[row0 + r];
       else member = (int)a.elites[philox_elite_slot(a.seed, a.step, grow, a.n_elites)];
-      for (int blk = q; blk * 4 < S; blk += 4) {
+      for (int blk = q; blk * 4 < S; blk += TPR) {
         float nrm[4] = {0.f, 0.f, 0.f, 0.f};
         if (!a.eps) philox_normal4(philox_noise_block(a.seed, a.step, grow, (unsigned)blk), nrm);
 #pragma unroll
@@ -147,8 +151,8 @@ step_kernel(StepArgs a, DynPtrs dp, MlpPtrs pol, int has_policy) {
 #pragma unroll
     for (int e = 0; e < MB_E; ++e) {
       float v = d2[e];
-      v += __shfl_xor_sync(0xffffffffu, v, 1);
-      v += __shfl_xor_sync(0xffffffffu, v, 2);
+#pragma unroll
+      for (int o = 1; o < TPR; o <<= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       pmax = fmaxf(pmax, sqrtf(v));
     }
     if (q == 0) { m.pen[r] = pmax; m.racc[r] = 0.f; }
@@ -171,17 +175,17 @@ step_kernel(StepArgs a, DynPtrs dp, MlpPtrs pol, int has_policy) {
 
   // ---- reward head, all 7 members (mobody_module.py:295-302; mean over members :236) ----
   for (int e = 0; e < MB_E; ++e) {
-    big_layer<false>(m.sas, m.ld_sas, 2 * S + A, dp.w[L_R1] + (size_t)e * (2 * S + A) * H, dp.b[L_R1] + e * H, m.X0, m.Wst, ACT_SWISH);
-    big_layer<false>(m.X0, H, H, dp.w[L_R2] + (size_t)e * H * H, dp.b[L_R2] + e * H, m.X1, m.Wst, ACT_SWISH);
+    big_layer<false, RPT>(m.sas, m.ld_sas, 2 * S + A, dp.w[L_R1] + (size_t)e * (2 * S + A) * H, dp.b[L_R1] + e * H, m.X0, m.Wst, ACT_SWISH);
+    big_layer<false, RPT>(m.X0, H, H, dp.w[L_R2] + (size_t)e * H * H, dp.b[L_R2] + e * H, m.X1, m.Wst, ACT_SWISH);
     // reward_model3 column 0 (mu); column 1 (logvar) is discarded by step() (:235)
     {
-      const int r = tid >> 2, q = tid & 3;
+      const int r = tid / TPR, q = tid % TPR;
       const float* w = dp.w[L_R3] + (size_t)e * H * 2;
       const float* x = m.X1 + r * H;
       float s = 0.f;
-      for (int k = q; k < H; k += 4) s = fmaf(x[k], __ldg(w + 2 * k), s);
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      for (int k = q; k < H; k += TPR) s = fmaf(x[k], __ldg(w + 2 * k), s);
+#pragma unroll
+      for (int o = 1; o < TPR; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       if (q == 0) m.racc[r] += s + __ldg(dp.b[L_R3] + e * 2);
     }
     __syncthreads();
@@ -197,6 +201,7 @@ step_kernel(StepArgs a, DynPtrs dp, MlpPtrs pol, int has_policy) {
 // Policy forward only: select_action (mobody.py:138-144).
 __global__ void __launch_bounds__(NT, 1)
 policy_kernel(const float* __restrict__ obs, int B, int S, int A, MlpPtrs pol, float max_action, float* __restrict__ act_out) {
+  constexpr int RPT = 8;
   extern __shared__ __align__(16) float smem_f[];
   float* X0 = smem_f; float* X1 = X0 + TM * H; float* Wst = X1 + TM * H;
   const int ld = rup16(S);
@@ -207,9 +212,9 @@ policy_kernel(const float* __restrict__ obs, int B, int S, int A, MlpPtrs pol, f
     o[i] = (r < rows && j < S) ? obs[(size_t)(row0 + r) * S + j] : 0.0f;
   }
   __syncthreads();
-  big_layer<true>(o, ld, S, pol.w[0], pol.b[0], X0, Wst, ACT_RELU);
-  big_layer<true>(X0, H, H, pol.w[1], pol.b[1], X1, Wst, ACT_RELU);
-  small_layer<true>(X1, H, H, pol.w[2], H, pol.b[2], A, act, A, ACT_TANH, max_action);
+  big_layer<true, RPT>(o, ld, S, pol.w[0], pol.b[0], X0, Wst, ACT_RELU);
+  big_layer<true, RPT>(X0, H, H, pol.w[1], pol.b[1], X1, Wst, ACT_RELU);
+  small_layer<true, RPT>(X1, H, H, pol.w[2], H, pol.b[2], A, act, A, ACT_TANH, max_action);
   for (int i = tid; i < rows * A; i += NT) act_out[(size_t)row0 * A + i] = act[i];
 }
 
@@ -218,18 +223,16 @@ policy_kernel(const float* __restrict__ obs, int B, int S, int A, MlpPtrs pol, f
 // ---- host launchers (called from api.cu) ----
 const char* mb_simt_step_launch(const StepArgs& a, const DynPtrs& dp, const MlpPtrs* pol, cudaStream_t st) {
   if (a.B <= 0) return nullptr;
-  if (a.S < 2 || a.S > 64 || a.A < 1 || a.A > 32) return "fp32 step kernel supports 2 <= S <= 64, 1 <= A <= 32";
-  size_t bytes = simt::smem_floats(a.S, a.A) * sizeof(float);
+  if (a.S < 2 || a.S > 128 || a.A < 1 || a.A > 32) return "fp32 step kernel supports 2 <= S <= 128, 1 <= A <= 32";
+  const int tm = a.S <= 64 ? 64 : 32;                       // wide observations: 32-row tiles (shared-memory budget)
+  size_t bytes = simt::smem_floats(a.S, a.A, tm) * sizeof(float);
   if (bytes > 227 * 1024) return "fp32 step kernel: shared memory budget exceeded for this (S, A)";
-  static size_t configured = 0;
-  if (bytes > configured) {
-    if (cudaFuncSetAttribute(simt::step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
-      return "cudaFuncSetAttribute(step_kernel) failed";
-    configured = bytes;
-  }
+  auto kern = tm == 64 ? simt::step_kernel<8> : simt::step_kernel<4>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+    return "cudaFuncSetAttribute(step_kernel) failed";
   MlpPtrs none{};
-  int grid = (a.B + simt::TM - 1) / simt::TM;
-  simt::step_kernel<<<grid, simt::NT, bytes, st>>>(a, dp, pol ? *pol : none, pol ? 1 : 0);
+  int grid = (a.B + tm - 1) / tm;
+  kern<<<grid, simt::NT, bytes, st>>>(a, dp, pol ? *pol : none, pol ? 1 : 0);
   return nullptr;
 }
 

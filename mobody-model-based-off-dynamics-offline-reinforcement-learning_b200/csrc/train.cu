@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(NT, 1) critic_kernel(CriticArgs a) {
   extern __shared__ __align__(16) float sm[];
   const int S = a.S, A = a.A, ldi = rup16(S + A);
   float* X0 = sm; float* X1 = X0 + TM * H; float* Wst = X1 + TM * H;
-  float* in_s = Wst + (RPT == 8 ? 2 : 6) * KC * H;   // [TM][ldi]  [s, a, 0]
+  float* in_s = Wst;                                     // [TM][ldi]  [s, a, 0]
   float* in2_s = in_s + TM * ldi;          // [64][ldi]  [s', pi(s'), 0]
   float* rew = in2_s + TM * ldi; float* nd = rew + TM; float* y = nd + TM;
   float* qa = y + TM; float* qb = qa + TM; float* g3 = qb + TM; float* redbuf = g3 + TM;   // redbuf[8]
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(NT, 1) actor_kernel(ActorArgs a) {
   extern __shared__ __align__(16) float sm[];
   const int S = a.S, A = a.A, ldi = rup16(S + A);
   float* X0 = sm; float* X1 = X0 + TM * H; float* Wst = X1 + TM * H;
-  float* in_s = Wst + (RPT == 8 ? 2 : 6) * KC * H;   // [s, a_t, 0]
+  float* in_s = Wst;                                     // [s, a_t, 0]
   float* sap_s = in_s + TM * ldi;          // [s, pi(s), 0]
   float* qv = sap_s + TM * ldi;            // [2][64]
   float* ones = qv + 2 * TM;               // [64] upstream gradient 1
@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(NT, 1) policy_bwd_kernel(PolicyBwdArgs a) {
   extern __shared__ __align__(16) float sm[];
   float* X0 = sm; float* X1 = X0 + TM * H; float* Wst = X1 + TM * H;
   const int lda = rup16(a.A);
-  float* d3 = Wst + (RPT == 8 ? 2 : 6) * KC * H;     // [TM][lda]
+  float* d3 = Wst;                                       // [TM][lda]
   const int tid = threadIdx.x, row0 = blockIdx.x * TM, rows = min(TM, a.N - row0);
   for (int i = tid; i < TM * lda; i += NT) {
     int r = i / lda, j = i - r * lda;
@@ -548,7 +548,7 @@ __global__ void __launch_bounds__(NT, 1) dara_relabel_kernel(RelabelArgs a) {
 
 // ---------------- host launchers ----------------
 static size_t tile_smem(int tm, int S, int A, int extra_floats) {
-  return (2 * (size_t)tm * simt::H + (size_t)(tm == 64 ? 2 : 6) * simt::KC * simt::H + 2 * (size_t)tm * simt::rup16(S + A) + extra_floats) * sizeof(float);
+  return (2 * (size_t)tm * simt::H + 2 * (size_t)tm * simt::rup16(S + A) + extra_floats) * sizeof(float);
 }
 // Row tile: 64 rows per CTA for large batches; 16 for small ones so that a 320-row batch still spreads over 20 SMs.
 static int pick_tm(int N) { return N >= 148 * 32 ? 64 : 16; }
@@ -585,7 +585,7 @@ const char* mb_train_actor_grad_launch(const trn::ActorGradArgs& a, cudaStream_t
 }
 const char* mb_train_policy_bwd_launch(const trn::PolicyBwdArgs& a, cudaStream_t st) {
   const int tm = pick_tm(a.N);
-  size_t bytes = (2 * (size_t)tm * simt::H + (size_t)(tm == 64 ? 2 : 6) * simt::KC * simt::H + (size_t)tm * simt::rup16(a.A)) * sizeof(float);
+  size_t bytes = (2 * (size_t)tm * simt::H + (size_t)tm * simt::rup16(a.A)) * sizeof(float);
   auto kern = tm == 64 ? trn::policy_bwd_kernel<8> : trn::policy_bwd_kernel<2>;
   if (const char* e = set_smem(kern, bytes)) return e;
   kern<<<(a.N + tm - 1) / tm, simt::NT, bytes, st>>>(a);
@@ -637,7 +637,7 @@ static MlpPtrs as_ptrs(const mobody_mlp_state& s) { MlpPtrs p; for (int i = 0; i
 
 const char* mb_train_step_launch(const mobody_train_desc& d, cudaStream_t st) {
   const int N = d.N, S = d.S, A = d.A, ns = d.nsplit;
-  if (N < 1 || d.n_true < 1 || d.n_true > N || S < 1 || S > 64 || A < 1 || A > 32 || ns < 1 || ns > 64) return "train step: bad N/n_true/S/A/nsplit";
+  if (N < 1 || d.n_true < 1 || d.n_true > N || S < 1 || S > 128 || A < 1 || A > 32 || ns < 1 || ns > 64) return "train step: bad N/n_true/S/A/nsplit";
   const TrainWs w = train_ws(N, S, A, ns);
   if (!d.workspace || d.workspace_bytes < (long long)w.total * 4) return "train step: workspace too small";
   float* ws = (float*)d.workspace;
@@ -734,7 +734,7 @@ long long mb_classifier_workspace_bytes(int N, int S, int A, int nsplit) { retur
 
 const char* mb_classifier_step_launch(const mobody_classifier_desc& d, cudaStream_t st) {
   const int N = d.N, S = d.S, A = d.A, ns = d.nsplit;
-  if (N < 1 || S < 1 || S > 64 || A < 1 || A > 32 || ns < 1 || ns > 64) return "classifier step: bad N/S/A/nsplit";
+  if (N < 1 || S < 1 || S > 128 || A < 1 || A > 32 || ns < 1 || ns > 64) return "classifier step: bad N/S/A/nsplit";
   const ClsWs w = cls_ws(N, S, A, ns);
   if (!d.workspace || d.workspace_bytes < (long long)w.total * 4) return "classifier step: workspace too small";
   float* ws = (float*)d.workspace;
@@ -783,7 +783,7 @@ const char* mb_classifier_step_launch(const mobody_classifier_desc& d, cudaStrea
 const char* mb_dara_relabel_launch(float* rows, long long n, int S, int A, int rw, const MlpPtrs& sas, const MlpPtrs& sa,
                                    float coef, float* pen_out, cudaStream_t st) {
   if (n <= 0) return nullptr;
-  if (S < 1 || S > 64 || A < 1 || A > 32) return "dara relabel: bad S/A";
+  if (S < 1 || S > 128 || A < 1 || A > 32) return "dara relabel: bad S/A";
   trn::RelabelArgs a{rows, n, S, A, rw, {sas, sa}, coef, pen_out};
   const size_t bytes = (2 * (size_t)64 * simt::H + (size_t)64 * simt::rup16(2 * S + A) + 4 * 64) * sizeof(float);
   if (const char* e = set_smem(trn::dara_relabel_kernel, bytes)) return e;
