@@ -21,10 +21,15 @@
 namespace trn {
 using namespace simt;
 
+// The chains of one update are independent per network until they meet (TD target, min over the twin critics), so
+// each phase runs the networks side by side: blockIdx.y selects the role, blockIdx.x the row tile.
 struct CriticArgs {
   const float* X; int N, S, A, rw;
   MlpPtrs pi, q[2], qt[2];
   float gamma, max_action;
+  float* a2;           // pi(s'), [N][A]                                  (phase 1 role 0 -> phase 2)
+  float* qk[2];        // Q_k(s, a), [N]                                  (phase 1 roles 1, 2 -> phase 3)
+  float* qtk[2];       // Q'_k(s', pi(s')), [N]                           (phase 2 -> phase 3)
   float* Hq[2][2];     // [net][layer] relu activations of Q_k(s,a), [N][256]
   float* Dq[2][2];     // [net][layer] dLoss/d(pre-activation), [N][256]
   float* d3[2];        // [net] dLoss/dq_k, [N]
@@ -37,9 +42,9 @@ struct ActorArgs {
   float max_action;
   float* Hp[2];        // relu activations of pi(s), [N][256]
   float* api;          // pi(s), [N][A]
-  float* qpi;          // min_k Q_k(s, pi(s)), [N]
-  float* ga;           // d qpi / d action, [N][A]
-  float* qhat;         // min_k Q_k(s_t, a_t), [n_true]
+  float* qv[2];        // Q_k(s, pi(s)), [N]
+  float* gak[2];       // d Q_k / d action, [N][A]
+  float* qh[2];        // Q_k(s_t, a_t), [n_true]
 };
 
 template <int TMv>
@@ -84,129 +89,162 @@ __device__ __forceinline__ void head_backward(float* __restrict__ X1, const floa
   __syncthreads();
 }
 
+// ---- critic phase 1: role 0 = pi(s') (:190), roles 1, 2 = Q_k(s, a) forward with stored activations (:196) ----
 template <int RPT>
-__global__ void __launch_bounds__(NT, 1) critic_kernel(CriticArgs a) {
+__global__ void __launch_bounds__(NT, 1) critic_fwd_kernel(CriticArgs a) {
   constexpr int TM = 8 * RPT;
   extern __shared__ __align__(16) float sm[];
   const int S = a.S, A = a.A, ldi = rup16(S + A);
-  float* X0 = sm; float* X1 = X0 + TM * H; float* Wst = X1 + TM * H;
-  float* in_s = Wst;                                     // [TM][ldi]  [s, a, 0]
-  float* in2_s = in_s + TM * ldi;          // [64][ldi]  [s', pi(s'), 0]
-  float* rew = in2_s + TM * ldi; float* nd = rew + TM; float* y = nd + TM;
-  float* qa = y + TM; float* qb = qa + TM; float* g3 = qb + TM; float* redbuf = g3 + TM;   // redbuf[8]
-  const int tid = threadIdx.x, row0 = blockIdx.x * TM, rows = min(TM, a.N - row0);
+  float* X0 = sm; float* X1 = X0 + TM * H; float* in_s = X1 + TM * H; float* qa = in_s + TM * ldi;
+  const int tid = threadIdx.x, row0 = blockIdx.x * TM, rows = min(TM, a.N - row0), role = blockIdx.y;
   for (int i = tid; i < TM * ldi; i += NT) {
-    int r = i / ldi, j = i - r * ldi;
+    const int r = i / ldi, j = i - r * ldi;
     const float* x = a.X + (size_t)(row0 + r) * a.rw;
-    in_s[i] = (r < rows && j < S + A) ? x[j] : 0.f;
-    in2_s[i] = (r < rows && j < S) ? x[S + A + j] : 0.f;
-  }
-  if (tid < TM) {
-    const float* x = a.X + (size_t)(row0 + tid) * a.rw;
-    rew[tid] = tid < rows ? x[2 * S + A] : 0.f;
-    nd[tid] = tid < rows ? x[2 * S + A + 1] : 0.f;
+    in_s[i] = role == 0 ? ((r < rows && j < S) ? x[S + A + j] : 0.f)        // [s', 0]
+                        : ((r < rows && j < S + A) ? x[j] : 0.f);            // [s, a, 0]
   }
   __syncthreads();
-  // ---- TD target: y = r + nd * gamma * min_k Q'_k(s', pi(s'))   (no grad, :190-195) ----
-  big_layer_mma<true, RPT>(in2_s, ldi, S, a.pi.w[0], a.pi.b[0], X0, ACT_RELU);
-  big_layer_mma<true, RPT>(X0, H, H, a.pi.w[1], a.pi.b[1], X1, ACT_RELU);
-  small_layer<true, RPT>(X1, H, H, a.pi.w[2], H, a.pi.b[2], A, in2_s + S, ldi, ACT_TANH, a.max_action);
-  for (int k = 0; k < 2; ++k) {
-    big_layer_mma<true, RPT>(in2_s, ldi, S + A, a.qt[k].w[0], a.qt[k].b[0], X0, ACT_RELU);
-    big_layer_mma<true, RPT>(X0, H, H, a.qt[k].w[1], a.qt[k].b[1], X1, ACT_RELU);
-    q_head<TM>(X1, a.qt[k].w[2], a.qt[k].b[2], k == 0 ? qa : qb);
-  }
-  if (tid < TM) y[tid] = rew[tid] + nd[tid] * a.gamma * fminf(qa[tid], qb[tid]);
-  __syncthreads();
-  // ---- Q_k(s,a): forward, mse gradient, backward to the pre-activations (:196, 207) ----
-  float lsum[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int k = 0; k < 2; ++k) {
+  if (role == 0) {
+    big_layer_mma<true, RPT>(in_s, ldi, S, a.pi.w[0], a.pi.b[0], X0, ACT_RELU);
+    big_layer_mma<true, RPT>(X0, H, H, a.pi.w[1], a.pi.b[1], X1, ACT_RELU);
+    small_layer<true, RPT>(X1, H, H, a.pi.w[2], H, a.pi.b[2], A, in_s, ldi, ACT_TANH, a.max_action);
+    for (int i = tid; i < rows * A; i += NT) { const int r = i / A, j = i - r * A; a.a2[(size_t)(row0 + r) * A + j] = in_s[r * ldi + j]; }
+  } else {
+    const int k = role - 1;
     big_layer_mma<true, RPT>(in_s, ldi, S + A, a.q[k].w[0], a.q[k].b[0], X0, ACT_RELU);
     store_tile<TM>(X0, a.Hq[k][0], row0, rows);
     big_layer_mma<true, RPT>(X0, H, H, a.q[k].w[1], a.q[k].b[1], X1, ACT_RELU);
     store_tile<TM>(X1, a.Hq[k][1], row0, rows);
     q_head<TM>(X1, a.q[k].w[2], a.q[k].b[2], qa);
-    if (tid < TM) {
-      const float d = tid < rows ? qa[tid] - y[tid] : 0.f;
-      g3[tid] = 2.0f * d / (float)a.N;                      // d mean((q-y)^2) / dq
-      if (tid < rows) a.d3[k][row0 + tid] = g3[tid];
-      lsum[k] = d * d; lsum[2 + k] = tid < rows ? qa[tid] : 0.f;
-    }
-    __syncthreads();
-    head_backward<TM>(X1, a.q[k].w[2], g3);                     // dH2 (masked)
-    store_tile<TM>(X1, a.Dq[k][1], row0, rows);
-    big_layer_mma<false, RPT>(X1, H, H, a.q[k].w[1], nullptr, X0, ACT_MASK);   // dH1 = (dH2 W2) * 1[H1>0], in place on H1
-    store_tile<TM>(X0, a.Dq[k][0], row0, rows);
-    __syncthreads();
+    if (tid < rows) a.qk[k][row0 + tid] = qa[tid];
   }
-  // tile partial sums in a fixed order (deterministic): threads 0..TM-1 hold one row each
-  if (tid < 8) redbuf[tid] = 0.f;
-  __syncthreads();
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    float v = tid < TM ? lsum[c] : 0.f;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (tid < TM && (tid & 31) == 0) redbuf[(tid >> 5) * 4 + c] = v;
-  }
-  __syncthreads();
-  if (tid < 4) a.part[blockIdx.x * 4 + tid] = redbuf[tid] + redbuf[4 + tid];
 }
 
+// ---- critic phase 2: role k = Q'_k(s', pi(s')) (no grad, :191-193) ----
 template <int RPT>
-__global__ void __launch_bounds__(NT, 1) actor_kernel(ActorArgs a) {
+__global__ void __launch_bounds__(NT, 1) critic_tgt_kernel(CriticArgs a) {
   constexpr int TM = 8 * RPT;
   extern __shared__ __align__(16) float sm[];
   const int S = a.S, A = a.A, ldi = rup16(S + A);
-  float* X0 = sm; float* X1 = X0 + TM * H; float* Wst = X1 + TM * H;
-  float* in_s = Wst;                                     // [s, a_t, 0]
-  float* sap_s = in_s + TM * ldi;          // [s, pi(s), 0]
-  float* qv = sap_s + TM * ldi;            // [2][64]
-  float* ones = qv + 2 * TM;               // [64] upstream gradient 1
-  float* gak = ones + TM;                  // [2][64][A]
-  const int tid = threadIdx.x, row0 = blockIdx.x * TM, rows = min(TM, a.N - row0);
+  float* X0 = sm; float* X1 = X0 + TM * H; float* in_s = X1 + TM * H; float* qa = in_s + TM * ldi;
+  const int tid = threadIdx.x, row0 = blockIdx.x * TM, rows = min(TM, a.N - row0), k = blockIdx.y;
   for (int i = tid; i < TM * ldi; i += NT) {
-    int r = i / ldi, j = i - r * ldi;
-    const float* x = a.X + (size_t)(row0 + r) * a.rw;
-    const float v = (r < rows && j < S + A) ? x[j] : 0.f;
+    const int r = i / ldi, j = i - r * ldi;
+    float v = 0.f;
+    if (r < rows) {
+      if (j < S) v = a.X[(size_t)(row0 + r) * a.rw + S + A + j];
+      else if (j < S + A) v = a.a2[(size_t)(row0 + r) * A + (j - S)];
+    }
     in_s[i] = v;
-    sap_s[i] = j < S ? v : 0.f;
+  }
+  __syncthreads();
+  big_layer_mma<true, RPT>(in_s, ldi, S + A, a.qt[k].w[0], a.qt[k].b[0], X0, ACT_RELU);
+  big_layer_mma<true, RPT>(X0, H, H, a.qt[k].w[1], a.qt[k].b[1], X1, ACT_RELU);
+  q_head<TM>(X1, a.qt[k].w[2], a.qt[k].b[2], qa);
+  if (tid < rows) a.qtk[k][row0 + tid] = qa[tid];
+}
+
+// ---- critic phase 3: role k = TD target, mse gradient of Q_k and backward to the pre-activations (:194-207) ----
+template <int RPT>
+__global__ void __launch_bounds__(NT, 1) critic_bwd_kernel(CriticArgs a) {
+  constexpr int TM = 8 * RPT;
+  extern __shared__ __align__(16) float sm[];
+  const int S = a.S, A = a.A;
+  float* X0 = sm; float* X1 = X0 + TM * H; float* g3 = X1 + TM * H; float* redbuf = g3 + TM;   // redbuf[4]
+  const int tid = threadIdx.x, row0 = blockIdx.x * TM, rows = min(TM, a.N - row0), k = blockIdx.y;
+  load_tile<TM>(X0, a.Hq[k][0], row0, rows);
+  load_tile<TM>(X1, a.Hq[k][1], row0, rows);
+  float l0 = 0.f, l1 = 0.f;
+  if (tid < TM) {
+    float d = 0.f, q = 0.f;
+    if (tid < rows) {
+      const float* x = a.X + (size_t)(row0 + tid) * a.rw;
+      const float y = x[2 * S + A] + x[2 * S + A + 1] * a.gamma * fminf(a.qtk[0][row0 + tid], a.qtk[1][row0 + tid]);
+      q = a.qk[k][row0 + tid];
+      d = q - y;
+      a.d3[k][row0 + tid] = 2.0f * d / (float)a.N;
+    }
+    g3[tid] = 2.0f * d / (float)a.N;                          // d mean((q-y)^2) / dq
+    l0 = d * d; l1 = q;
+  }
+  __syncthreads();
+  head_backward<TM>(X1, a.q[k].w[2], g3);                     // dH2 (masked)
+  store_tile<TM>(X1, a.Dq[k][1], row0, rows);
+  big_layer_mma<false, RPT>(X1, H, H, a.q[k].w[1], nullptr, X0, ACT_MASK);   // dH1 = (dH2 W2) * 1[H1>0], in place on H1
+  store_tile<TM>(X0, a.Dq[k][0], row0, rows);
+  // tile partial sums in a fixed order (deterministic): threads 0..TM-1 hold one row each
+  if (tid < 4) redbuf[tid] = 0.f;
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    float v = tid < TM ? (c == 0 ? l0 : l1) : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (tid < TM && (tid & 31) == 0) redbuf[(tid >> 5) * 2 + c] = v;
+  }
+  __syncthreads();
+  if (tid < 2) a.part[blockIdx.x * 4 + 2 * tid + k] = redbuf[tid] + redbuf[2 + tid];     // [0..1] = sq err of Q1, Q2; [2..3] = sum q
+}
+
+// ---- actor phase 1: role 0 = pi(s) with stored activations (:315); roles 1, 2 = q_hat_k = Q_k(s_t, a_t) on true rows (:249-251) ----
+template <int RPT>
+__global__ void __launch_bounds__(NT, 1) actor_fwd_kernel(ActorArgs a) {
+  constexpr int TM = 8 * RPT;
+  extern __shared__ __align__(16) float sm[];
+  const int S = a.S, A = a.A, ldi = rup16(S + A);
+  float* X0 = sm; float* X1 = X0 + TM * H; float* in_s = X1 + TM * H; float* qa = in_s + TM * ldi;
+  const int tid = threadIdx.x, row0 = blockIdx.x * TM, rows = min(TM, a.N - row0), role = blockIdx.y;
+  if (role != 0 && row0 >= a.n_true) return;
+  for (int i = tid; i < TM * ldi; i += NT) {
+    const int r = i / ldi, j = i - r * ldi;
+    in_s[i] = (r < rows && j < (role == 0 ? S : S + A)) ? a.X[(size_t)(row0 + r) * a.rw + j] : 0.f;
+  }
+  __syncthreads();
+  if (role == 0) {
+    big_layer_mma<true, RPT>(in_s, ldi, S, a.pi.w[0], a.pi.b[0], X0, ACT_RELU);
+    store_tile<TM>(X0, a.Hp[0], row0, rows);
+    big_layer_mma<true, RPT>(X0, H, H, a.pi.w[1], a.pi.b[1], X1, ACT_RELU);
+    store_tile<TM>(X1, a.Hp[1], row0, rows);
+    small_layer<true, RPT>(X1, H, H, a.pi.w[2], H, a.pi.b[2], A, in_s, ldi, ACT_TANH, a.max_action);
+    for (int i = tid; i < rows * A; i += NT) { const int r = i / A, j = i - r * A; a.api[(size_t)(row0 + r) * A + j] = in_s[r * ldi + j]; }
+  } else {
+    const int k = role - 1;
+    big_layer_mma<true, RPT>(in_s, ldi, S + A, a.q[k].w[0], a.q[k].b[0], X0, ACT_RELU);
+    big_layer_mma<true, RPT>(X0, H, H, a.q[k].w[1], a.q[k].b[1], X1, ACT_RELU);
+    q_head<TM>(X1, a.q[k].w[2], a.q[k].b[2], qa);
+    if (tid < rows && row0 + tid < a.n_true) a.qh[k][row0 + tid] = qa[tid];
+  }
+}
+
+// ---- actor phase 2: role k = Q_k(s, pi(s)) and d Q_k / d action with Q frozen (:316-317, 555-556) ----
+template <int RPT>
+__global__ void __launch_bounds__(NT, 1) actor_q_kernel(ActorArgs a) {
+  constexpr int TM = 8 * RPT;
+  extern __shared__ __align__(16) float sm[];
+  const int S = a.S, A = a.A, ldi = rup16(S + A);
+  float* X0 = sm; float* X1 = X0 + TM * H; float* sap_s = X1 + TM * H;
+  float* qa = sap_s + TM * ldi; float* ones = qa + TM; float* gk = ones + TM;      // gk [TM][A]
+  const int tid = threadIdx.x, row0 = blockIdx.x * TM, rows = min(TM, a.N - row0), k = blockIdx.y;
+  for (int i = tid; i < TM * ldi; i += NT) {
+    const int r = i / ldi, j = i - r * ldi;
+    float v = 0.f;
+    if (r < rows) {
+      if (j < S) v = a.X[(size_t)(row0 + r) * a.rw + j];
+      else if (j < S + A) v = a.api[(size_t)(row0 + r) * A + (j - S)];
+    }
+    sap_s[i] = v;
   }
   if (tid < TM) ones[tid] = 1.0f;
   __syncthreads();
-  // ---- pi(s) (:315) ----
-  big_layer_mma<true, RPT>(in_s, ldi, S, a.pi.w[0], a.pi.b[0], X0, ACT_RELU);
-  store_tile<TM>(X0, a.Hp[0], row0, rows);
-  big_layer_mma<true, RPT>(X0, H, H, a.pi.w[1], a.pi.b[1], X1, ACT_RELU);
-  store_tile<TM>(X1, a.Hp[1], row0, rows);
-  small_layer<true, RPT>(X1, H, H, a.pi.w[2], H, a.pi.b[2], A, sap_s + S, ldi, ACT_TANH, a.max_action);
-  for (int i = tid; i < rows * A; i += NT) { int r = i / A, j = i - r * A; a.api[(size_t)(row0 + r) * A + j] = sap_s[r * ldi + S + j]; }
-  // ---- Q_k(s, pi(s)) and d q_k / d action (Q frozen, :316-317, 555-556) ----
-  for (int k = 0; k < 2; ++k) {
-    big_layer_mma<true, RPT>(sap_s, ldi, S + A, a.q[k].w[0], a.q[k].b[0], X0, ACT_RELU);
-    big_layer_mma<true, RPT>(X0, H, H, a.q[k].w[1], a.q[k].b[1], X1, ACT_RELU);
-    q_head<TM>(X1, a.q[k].w[2], a.q[k].b[2], qv + k * TM);
-    head_backward<TM>(X1, a.q[k].w[2], ones);
-    big_layer_mma<false, RPT>(X1, H, H, a.q[k].w[1], nullptr, X0, ACT_MASK);
-    // d q / d a_j = sum_n dH1[n] * W1[n][S+j]
-    small_layer<false, RPT>(X0, H, H, a.q[k].w[0] + S, S + A, nullptr, A, gak + k * TM * A, A, ACT_NONE, 1.f);
-  }
-  for (int i = tid; i < rows * A; i += NT) {
-    int r = i / A;
-    const int sel = qv[r] <= qv[TM + r] ? 0 : 1;            // torch.min(q1, q2): gradient follows the smaller one
-    a.ga[(size_t)row0 * A + i] = gak[sel * TM * A + i];
-  }
-  if (tid < rows) a.qpi[row0 + tid] = fminf(qv[tid], qv[TM + tid]);
-  __syncthreads();
-  // ---- q_hat = min_k Q_k(s_t, a_t) on the true rows (no grad, :249-251) ----
-  if (row0 < a.n_true) {
-    for (int k = 0; k < 2; ++k) {
-      big_layer_mma<true, RPT>(in_s, ldi, S + A, a.q[k].w[0], a.q[k].b[0], X0, ACT_RELU);
-      big_layer_mma<true, RPT>(X0, H, H, a.q[k].w[1], a.q[k].b[1], X1, ACT_RELU);
-      q_head<TM>(X1, a.q[k].w[2], a.q[k].b[2], qv + k * TM);
-    }
-    if (tid < rows && row0 + tid < a.n_true) a.qhat[row0 + tid] = fminf(qv[tid], qv[TM + tid]);
-  }
+  big_layer_mma<true, RPT>(sap_s, ldi, S + A, a.q[k].w[0], a.q[k].b[0], X0, ACT_RELU);
+  big_layer_mma<true, RPT>(X0, H, H, a.q[k].w[1], a.q[k].b[1], X1, ACT_RELU);
+  q_head<TM>(X1, a.q[k].w[2], a.q[k].b[2], qa);
+  head_backward<TM>(X1, a.q[k].w[2], ones);
+  big_layer_mma<false, RPT>(X1, H, H, a.q[k].w[1], nullptr, X0, ACT_MASK);
+  // d q / d a_j = sum_n dH1[n] * W1[n][S+j]
+  small_layer<false, RPT>(X0, H, H, a.q[k].w[0] + S, S + A, nullptr, A, gk, A, ACT_NONE, 1.f);
+  for (int i = tid; i < rows * A; i += NT) a.gak[k][(size_t)row0 * A + i] = gk[i];
+  if (tid < rows) a.qv[k][row0 + tid] = qa[tid];
 }
 
 // Scalars of the actor loss (single CTA, fixed-order reductions):
@@ -214,7 +252,7 @@ __global__ void __launch_bounds__(NT, 1) actor_kernel(ActorArgs a) {
 //   out[3] = p_w = weight / mean|qpi|   out[4] = bc loss  out[5] = policy loss
 //   out[6..8] = mean / min / max of exp_adv   out[9] = q loss   out[10] = mean q1   (critic tile partials)
 struct ActorScalarArgs {
-  const float* qpi; const float* qhat; const float* api; const float* X; const float* part; int ntiles;
+  const float* qv[2]; const float* qh[2]; const float* api; const float* X; const float* part; int ntiles;   // twin outputs; min taken here
   int N, n_true, S, A, rw; float weight, bc_coef; float* out;
 };
 __device__ float block_sum(float v, float* sh) {
@@ -253,15 +291,15 @@ __device__ float block_minmax(float v, float* sh, bool is_max) {
 __global__ void __launch_bounds__(1024) actor_scalar_kernel(ActorScalarArgs a) {
   __shared__ float sh[33];
   float s_abs = 0.f, s_q = 0.f;
-  for (int i = threadIdx.x; i < a.N; i += blockDim.x) { float q = a.qpi[i]; s_abs += fabsf(q); s_q += q; }
+  for (int i = threadIdx.x; i < a.N; i += blockDim.x) { float q = fminf(a.qv[0][i], a.qv[1][i]); s_abs += fabsf(q); s_q += q; }
   const float mean_abs = block_sum(s_abs, sh) / (float)a.N;
   const float mean_q = block_sum(s_q, sh) / (float)a.N;
   float s_h = 0.f;
-  for (int i = threadIdx.x; i < a.n_true; i += blockDim.x) s_h += fabsf(a.qhat[i]);
+  for (int i = threadIdx.x; i < a.n_true; i += blockDim.x) s_h += fabsf(fminf(a.qh[0][i], a.qh[1][i]));
   const float mean_h = block_sum(s_h, sh) / (float)a.n_true;
   float s_w = 0.f, w_min = 3.4e38f, w_max = -3.4e38f, s_bc = 0.f;
   for (int i = threadIdx.x; i < a.n_true; i += blockDim.x) {
-    const float w = fminf(expf(3.0f * (a.qhat[i] / mean_h)), 100.0f);      // :252-258
+    const float w = fminf(expf(3.0f * (fminf(a.qh[0][i], a.qh[1][i]) / mean_h)), 100.0f);      // :252-258
     s_w += w; w_min = fminf(w_min, w); w_max = fmaxf(w_max, w);
     const float* x = a.X + (size_t)i * a.rw + a.S;
     float e = 0.f;
@@ -284,7 +322,7 @@ __global__ void __launch_bounds__(1024) actor_scalar_kernel(ActorScalarArgs a) {
 
 // d loss / d (pre-tanh policy output) for every row: [N][A]
 struct ActorGradArgs {
-  const float* scal; const float* ga; const float* api; const float* qhat; const float* X;
+  const float* scal; const float* gak[2]; const float* qv[2]; const float* api; const float* qh[2]; const float* X;
   int N, n_true, S, A, rw; float bc_coef, max_action; float* d3p;
 };
 __global__ void actor_grad_kernel(ActorGradArgs a) {
@@ -293,9 +331,10 @@ __global__ void actor_grad_kernel(ActorGradArgs a) {
   const int r = i / a.A, j = i - r * a.A;
   const float pw = a.scal[9], mean_h = a.scal[10];
   const float ap = a.api[i];
-  float g = -pw / (float)a.N * a.ga[i];                                     // d [pw * mean(-q)] / d a
+  const float ga = a.qv[0][r] <= a.qv[1][r] ? a.gak[0][i] : a.gak[1][i];   // torch.min(q1, q2): gradient follows the smaller one
+  float g = -pw / (float)a.N * ga;                                          // d [pw * mean(-q)] / d a
   if (r < a.n_true) {
-    const float w = fminf(expf(3.0f * (a.qhat[r] / mean_h)), 100.0f);
+    const float w = fminf(expf(3.0f * (fminf(a.qh[0][r], a.qh[1][r]) / mean_h)), 100.0f);
     const float at = a.X[(size_t)r * a.rw + a.S + j];
     g += a.bc_coef * w * 2.0f * (ap - at) / (float)((size_t)a.n_true * a.A);
   }
@@ -559,19 +598,28 @@ template <typename K> static const char* set_smem(K kern, size_t bytes) {
 }
 
 const char* mb_train_critic_launch(const trn::CriticArgs& a, cudaStream_t st) {
-  const int tm = pick_tm(a.N);
-  size_t bytes = tile_smem(tm, a.S, a.A, 6 * tm + 8);
-  auto kern = tm == 64 ? trn::critic_kernel<8> : trn::critic_kernel<2>;
-  if (const char* e = set_smem(kern, bytes)) return e;
-  kern<<<(a.N + tm - 1) / tm, simt::NT, bytes, st>>>(a);
+  const int tm = pick_tm(a.N), ntiles = (a.N + tm - 1) / tm;
+  const size_t bytes = (2 * (size_t)tm * simt::H + (size_t)tm * simt::rup16(a.S + a.A) + 2 * tm + 8) * sizeof(float);
+  auto k1 = tm == 64 ? trn::critic_fwd_kernel<8> : trn::critic_fwd_kernel<2>;
+  auto k2 = tm == 64 ? trn::critic_tgt_kernel<8> : trn::critic_tgt_kernel<2>;
+  auto k3 = tm == 64 ? trn::critic_bwd_kernel<8> : trn::critic_bwd_kernel<2>;
+  if (const char* e = set_smem(k1, bytes)) return e;
+  if (const char* e = set_smem(k2, bytes)) return e;
+  if (const char* e = set_smem(k3, bytes)) return e;
+  k1<<<dim3(ntiles, 3), simt::NT, bytes, st>>>(a);
+  k2<<<dim3(ntiles, 2), simt::NT, bytes, st>>>(a);
+  k3<<<dim3(ntiles, 2), simt::NT, bytes, st>>>(a);
   return nullptr;
 }
 const char* mb_train_actor_launch(const trn::ActorArgs& a, cudaStream_t st) {
-  const int tm = pick_tm(a.N);
-  size_t bytes = tile_smem(tm, a.S, a.A, 3 * tm + 2 * tm * a.A);
-  auto kern = tm == 64 ? trn::actor_kernel<8> : trn::actor_kernel<2>;
-  if (const char* e = set_smem(kern, bytes)) return e;
-  kern<<<(a.N + tm - 1) / tm, simt::NT, bytes, st>>>(a);
+  const int tm = pick_tm(a.N), ntiles = (a.N + tm - 1) / tm;
+  const size_t bytes = (2 * (size_t)tm * simt::H + (size_t)tm * simt::rup16(a.S + a.A) + 2 * tm + (size_t)tm * a.A + 8) * sizeof(float);
+  auto k1 = tm == 64 ? trn::actor_fwd_kernel<8> : trn::actor_fwd_kernel<2>;
+  auto k2 = tm == 64 ? trn::actor_q_kernel<8> : trn::actor_q_kernel<2>;
+  if (const char* e = set_smem(k1, bytes)) return e;
+  if (const char* e = set_smem(k2, bytes)) return e;
+  k1<<<dim3(ntiles, 3), simt::NT, bytes, st>>>(a);
+  k2<<<dim3(ntiles, 2), simt::NT, bytes, st>>>(a);
   return nullptr;
 }
 const char* mb_train_actor_scalars_launch(const trn::ActorScalarArgs& a, cudaStream_t st) {
@@ -610,7 +658,7 @@ const char* mb_train_adam_launch(const trn::AdamArgs& a, cudaStream_t st) {
 
 // ---------------- whole train step (C ABI: mobody_train_step) ----------------
 struct TrainWs {   // float offsets into the workspace
-  size_t Hq[2][2], Dq[2][2], d3[2], part, Hp[2], Dp[2], api, qpi, ga, qhat, d3p, scal, gq[2][6], gp[6], total;
+  size_t Hq[2][2], Dq[2][2], d3[2], part, Hp[2], Dp[2], api, a2, qk[2], qtk[2], qv[2], qh[2], gak[2], d3p, scal, gq[2][6], gp[6], total;
   int ntiles;
 };
 static TrainWs train_ws(int N, int S, int A, int nsplit) {
@@ -622,7 +670,8 @@ static TrainWs train_ws(int N, int S, int A, int nsplit) {
   for (int k = 0; k < 2; ++k) w.d3[k] = take(N);
   w.part = take((size_t)w.ntiles * 4);
   for (int l = 0; l < 2; ++l) { w.Hp[l] = take(act); w.Dp[l] = take(act); }
-  w.api = take((size_t)N * A); w.qpi = take(N); w.ga = take((size_t)N * A); w.qhat = take(N); w.d3p = take((size_t)N * A);
+  w.api = take((size_t)N * A); w.a2 = take((size_t)N * A); w.d3p = take((size_t)N * A);
+  for (int k = 0; k < 2; ++k) { w.qk[k] = take(N); w.qtk[k] = take(N); w.qv[k] = take(N); w.qh[k] = take(N); w.gak[k] = take((size_t)N * A); }
   w.scal = take(16);
   const size_t qn[6] = {(size_t)256 * (S + A), 256, 256 * 256, 256, 256, 1};       // w1 b1 w2 b2 w3 b3
   const size_t pn[6] = {(size_t)256 * S, 256, 256 * 256, 256, (size_t)A * 256, (size_t)A};
@@ -653,7 +702,8 @@ const char* mb_train_step_launch(const mobody_train_desc& d, cudaStream_t st) {
     for (int l = 0; l < 2; ++l) { c.Hq[k][l] = ws + w.Hq[k][l]; c.Dq[k][l] = ws + w.Dq[k][l]; }
     c.d3[k] = ws + w.d3[k];
   }
-  c.gamma = d.gamma; c.max_action = d.max_action; c.part = ws + w.part;
+  c.gamma = d.gamma; c.max_action = d.max_action; c.part = ws + w.part; c.a2 = ws + w.a2;
+  for (int k = 0; k < 2; ++k) { c.qk[k] = ws + w.qk[k]; c.qtk[k] = ws + w.qtk[k]; }
   if (const char* e = mb_train_critic_launch(c, st)) return e;
   // ---- critic weight gradients + Adam + Polyak ----
   trn::WgradArgs g{}; g.N = N; g.nsplit = ns; g.njobs = 6;
@@ -680,11 +730,12 @@ const char* mb_train_step_launch(const mobody_train_desc& d, cudaStream_t st) {
   trn::ActorArgs ac{};
   ac.X = d.rows; ac.N = N; ac.n_true = d.n_true; ac.S = S; ac.A = A; ac.rw = d.row_width; ac.pi = as_ptrs(d.policy);
   ac.q[0] = as_ptrs(d.q1); ac.q[1] = as_ptrs(d.q2); ac.max_action = d.max_action;
-  ac.Hp[0] = ws + w.Hp[0]; ac.Hp[1] = ws + w.Hp[1]; ac.api = ws + w.api; ac.qpi = ws + w.qpi; ac.ga = ws + w.ga; ac.qhat = ws + w.qhat;
+  ac.Hp[0] = ws + w.Hp[0]; ac.Hp[1] = ws + w.Hp[1]; ac.api = ws + w.api;
+  for (int k = 0; k < 2; ++k) { ac.qv[k] = ws + w.qv[k]; ac.qh[k] = ws + w.qh[k]; ac.gak[k] = ws + w.gak[k]; }
   if (const char* e = mb_train_actor_launch(ac, st)) return e;
-  trn::ActorScalarArgs sc{ac.qpi, ac.qhat, ac.api, d.rows, ws + w.part, (N + pick_tm(N) - 1) / pick_tm(N), N, d.n_true, S, A, d.row_width, d.weight, d.bc_coef, ws + w.scal};
+  trn::ActorScalarArgs sc{{ac.qv[0], ac.qv[1]}, {ac.qh[0], ac.qh[1]}, ac.api, d.rows, ws + w.part, (N + pick_tm(N) - 1) / pick_tm(N), N, d.n_true, S, A, d.row_width, d.weight, d.bc_coef, ws + w.scal};
   if (const char* e = mb_train_actor_scalars_launch(sc, st)) return e;
-  trn::ActorGradArgs ag{ws + w.scal, ac.ga, ac.api, ac.qhat, d.rows, N, d.n_true, S, A, d.row_width, d.bc_coef, d.max_action, ws + w.d3p};
+  trn::ActorGradArgs ag{ws + w.scal, {ac.gak[0], ac.gak[1]}, {ac.qv[0], ac.qv[1]}, ac.api, {ac.qh[0], ac.qh[1]}, d.rows, N, d.n_true, S, A, d.row_width, d.bc_coef, d.max_action, ws + w.d3p};
   if (const char* e = mb_train_actor_grad_launch(ag, st)) return e;
   trn::PolicyBwdArgs pb{}; pb.d3p = ws + w.d3p; pb.N = N; pb.A = A; pb.pi = ac.pi;
   pb.Hp[0] = ac.Hp[0]; pb.Hp[1] = ac.Hp[1]; pb.Dp[0] = ws + w.Dp[0]; pb.Dp[1] = ws + w.Dp[1];
