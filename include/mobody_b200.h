@@ -121,6 +121,12 @@ int mobody_gather_rows(const float* rows, const int64_t* idx, long long n, int r
 /* np.random.randint(0, size, n) replacement (utils.py:128): Philox4x32-10, key (seed,'indx'), counter (i, draw) */
 int mobody_philox_indices(int64_t* idx, long long n, unsigned long long seed, unsigned int draw,
                           unsigned int size, void* stream);
+/* Fused draw + gather of up to 4 buffer samples in one launch (the three ReplayBuffer.sample calls of one
+ * MOBODY.train step, mobody.py:399-400, 524): out[i,:] = rows[philox_index(i, draw, seed) , :], i < n. */
+typedef struct mobody_sample_job {
+  const float* rows; long long n; unsigned int size; unsigned int draw; unsigned long long seed; float* out;
+} mobody_sample_job;
+int mobody_sample_rows(const mobody_sample_job* jobs, int njobs, int row_width, void* stream);
 /* convert_D4RL / add_batch packing (utils.py:43-92, 173-193): d is `terminals` when done_is_terminal (stores 1-d) */
 int mobody_pack_rows(const float* s, const float* a, const float* ns, const float* r, const float* d,
                      long long n, int S, int A, int done_is_terminal, float* out_rows, void* stream);

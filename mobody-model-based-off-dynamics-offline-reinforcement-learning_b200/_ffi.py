@@ -53,6 +53,11 @@ class RolloutDesc(C.Structure):
     ]
 
 
+class SampleJob(C.Structure):
+    _fields_ = [("rows", C.c_void_p), ("n", C.c_longlong), ("size", C.c_uint), ("draw", C.c_uint), ("seed", C.c_ulonglong),
+                ("out", C.c_void_p)]
+
+
 class MlpState(C.Structure):
     _fields_ = [("w", C.c_void_p * 3), ("b", C.c_void_p * 3)]
 
@@ -104,6 +109,7 @@ def lib():
         L.mobody_termination.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.mobody_gather_rows.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]
         L.mobody_philox_indices.argtypes = [C.c_void_p, C.c_longlong, C.c_ulonglong, C.c_uint, C.c_uint, C.c_void_p]
+        L.mobody_sample_rows.argtypes = [C.POINTER(SampleJob), C.c_int, C.c_int, C.c_void_p]
         L.mobody_pack_rows.argtypes = [C.c_void_p] * 5 + [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.mobody_ring_insert.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_longlong, C.c_longlong,
                                          C.c_void_p, C.c_void_p]

@@ -12,6 +12,7 @@ const char* mb_simt_policy_launch(const float* obs, int B, int S, int A, const M
                                   float* act_out, cudaStream_t st);
 void mb_gather_rows_launch(const float* rows, const int64_t* idx, long long n, int rw, float* out, cudaStream_t st);
 void mb_philox_indices_launch(int64_t* idx, long long n, unsigned long long seed, unsigned int draw, unsigned int size, cudaStream_t st);
+void mb_sample_rows_launch(const mobody_sample_job* jobs, int njobs, int rw, cudaStream_t st);
 void mb_pack_rows_launch(const float* s, const float* a, const float* ns, const float* r, const float* d, long long n,
                          int S, int A, int rw, int done_is_terminal, float* out, cudaStream_t st);
 void mb_ring_insert_launch(const float* src, long long n_cap, const int* n_dev, int rw, long long ptr, long long cap,
@@ -149,6 +150,15 @@ int mobody_philox_indices(int64_t* idx, long long n, unsigned long long seed, un
   if (n < 0 || size == 0 || (n > 0 && !idx)) return fail(MOBODY_ERR_ARG, "mobody_philox_indices: bad arguments (size must be > 0)");
   mb_philox_indices_launch(idx, n, seed, draw, size, (cudaStream_t)stream);
   return check_launch("mobody_philox_indices");
+}
+
+int mobody_sample_rows(const mobody_sample_job* jobs, int njobs, int row_width, void* stream) {
+  if (!jobs || njobs < 1 || njobs > 4 || row_width <= 0 || (row_width & 3)) return fail(MOBODY_ERR_ARG, "mobody_sample_rows: bad arguments");
+  for (int b = 0; b < njobs; ++b)
+    if (jobs[b].n < 0 || (jobs[b].n > 0 && (!jobs[b].rows || !jobs[b].out || jobs[b].size == 0)))
+      return fail(MOBODY_ERR_ARG, "mobody_sample_rows: null pointer or empty buffer");
+  mb_sample_rows_launch(jobs, njobs, row_width, (cudaStream_t)stream);
+  return check_launch("mobody_sample_rows");
 }
 
 int mobody_pack_rows(const float* s, const float* a, const float* ns, const float* r, const float* d, long long n,

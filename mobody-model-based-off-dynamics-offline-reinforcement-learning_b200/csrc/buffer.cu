@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "philox.cuh"
 #include "term.cuh"
+#include "../../include/mobody_b200.h"
 
 namespace buf {
 
@@ -31,6 +32,20 @@ __global__ void philox_indices_kernel(int64_t* __restrict__ idx, long long n, un
   for (; i < n; i += (long long)gridDim.x * blockDim.x) {
     Philox4 b = philox4x32_10((uint32_t)i, (uint32_t)((unsigned long long)i >> 32), draw, 0u, (uint32_t)seed, MB_STREAM_INDEX);
     idx[i] = (int64_t)(((uint64_t)b.x * (uint64_t)size) >> 32);
+  }
+}
+
+// Fused Philox index draw + row gather for up to 4 buffers in one launch (blockIdx.y = job): the three buffer samples of
+// one MOBODY.train step (mobody.py:399-400, 524).  Indices are exactly those of philox_indices_kernel.
+struct SampleJobs { const float4* rows[4]; float4* out[4]; long long n[4]; unsigned int size[4], draw[4]; unsigned long long seed[4]; };
+__global__ void sample_rows_kernel(SampleJobs j, int rw4) {
+  const int b = blockIdx.y;
+  const long long total = j.n[b] * rw4;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long i = t / rw4; const int c = (int)(t - i * rw4);
+    Philox4 p = philox4x32_10((uint32_t)i, (uint32_t)((unsigned long long)i >> 32), j.draw[b], 0u, (uint32_t)j.seed[b], MB_STREAM_INDEX);
+    const size_t src = (size_t)(((uint64_t)p.x * (uint64_t)j.size[b]) >> 32);
+    j.out[b][t] = __ldg(j.rows[b] + src * rw4 + c);
   }
 }
 
@@ -337,4 +352,16 @@ void mb_rollout_stats_launch(const float* rews, const unsigned char* terms, long
                              double* stats, cudaStream_t st) {
   int nb = (int)((n + 4095) / 4096); if (nb < 1) nb = 1; if (nb > 148) nb = 148;
   buf::rollout_stats_kernel<<<nb, buf::SB, 0, st>>>(rews, terms, n, partial, ticket, stats);
+}
+
+void mb_sample_rows_launch(const mobody_sample_job* jobs, int njobs, int rw, cudaStream_t st) {
+  buf::SampleJobs j{};
+  long long maxn = 0;
+  for (int b = 0; b < njobs; ++b) {
+    j.rows[b] = reinterpret_cast<const float4*>(jobs[b].rows); j.out[b] = reinterpret_cast<float4*>(jobs[b].out);
+    j.n[b] = jobs[b].n; j.size[b] = jobs[b].size; j.draw[b] = jobs[b].draw; j.seed[b] = jobs[b].seed;
+    if (jobs[b].n > maxn) maxn = jobs[b].n;
+  }
+  if (maxn <= 0) return;
+  buf::sample_rows_kernel<<<dim3(grid_for(maxn * (rw / 4), buf::NT), njobs), buf::NT, 0, st>>>(j, rw / 4);
 }

@@ -406,6 +406,20 @@ class MOBODY(object):
         n_fake = int(cfg["fake_batch_scale"] * batch_size) if cfg["fake_batch_scale"] != 0 else 0
         RW = src_replay_buffer.RW
         rows = torch.empty(n_src + n_tar + n_fake, RW, dtype=torch.float32, device=self.device)
+        refresh = (self.total_it - 1) % 5000 == 0
+        fused = (not inj and not refresh and self.penalty_type != "par" and n_fake and
+                 all(b.index_source == "philox" and b.size > 0 for b in (src_replay_buffer, tar_replay_buffer, self.fake_replay_buffer)))
+        if fused:   # the three buffer samples of this step (:399, 400, 524) as ONE launch: Philox draw + 128-bit row gather
+            jobs = (_ffi.SampleJob * 3)()
+            for jb, (b, n, lo) in zip(jobs, ((src_replay_buffer, n_src, 0), (tar_replay_buffer, n_tar, n_src),
+                                             (self.fake_replay_buffer, n_fake, n_src + n_tar))):
+                jb.rows, jb.n, jb.size, jb.draw, jb.seed = _ffi.ptr(b._rows), n, b.size, b._draw, b.seed
+                jb.out = rows.data_ptr() + 4 * RW * lo
+                b._draw += 1
+            _ffi.check(_ffi.lib().mobody_sample_rows(jobs, 3, RW, _ffi.stream_ptr(self.device)))
+            self.train_on_rows(rows, n_src + n_tar)
+            self._train_side_effects(writer, wandbrun)
+            return
         src_replay_buffer.sample_rows(n_src, inj.get("src"), out=rows[:n_src])                        # :399
         tar_replay_buffer.sample_rows(n_tar, inj.get("tar"), out=rows[n_src:n_src + n_tar])           # :400
         if self.penalty_type == "par":                                                                # :428-434
@@ -417,6 +431,10 @@ class MOBODY(object):
         if n_fake:
             self.fake_replay_buffer.sample_rows(n_fake, inj.get("fake"), out=rows[n_src + n_tar:])    # :524
         self.train_on_rows(rows, n_src + n_tar)
+        self._train_side_effects(writer, wandbrun)
+
+    def _train_side_effects(self, writer, wandbrun):
+        cfg = self.config
         if self.total_it % 1000 == 0 and cfg.get("q_weighted", 1):                                    # :269-270
             v = self.loss_scalars()
             print(v["w_mean"], v["w_min"], v["w_max"])

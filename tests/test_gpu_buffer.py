@@ -105,3 +105,30 @@ def test_compaction_stable_and_exact(n):
         _ffi.check(L.mobody_compact(_ffi.KEEP_U8_ZERO, _ffi.ptr(f), None, 0.0, n, _ffi.ptr(live), _ffi.ptr(scr), _ffi.ptr(pos), _ffi.ptr(cnt), st))
         want = np.flatnonzero(flags[:1000] == 0)
         assert int(cnt.item()) == len(want) and np.array_equal(pos[:len(want)].cpu().numpy(), want)
+
+
+def test_fused_sample_rows_equals_separate_draw_and_gather():
+    """mobody_sample_rows (one launch for the three buffer samples of a train step) draws the same Philox indices and
+    gathers the same rows as philox_indices + gather_rows per buffer."""
+    import mobody_b200 as mb
+    from mobody_b200 import _ffi
+    S, A = 17, 6
+    rng = np.random.default_rng(0)
+    bufs, sizes, ns = [], (5000, 700, 1234), (128, 128, 64)
+    for n, sd in zip(sizes, (1, 2, 3)):
+        b = mb.ReplayBuffer(S, A, "cuda", max_size=n, seed=sd)
+        b.add_batch({"obss": rng.standard_normal((n, S)).astype(np.float32), "actions": rng.uniform(-1, 1, (n, A)).astype(np.float32),
+                     "next_obss": rng.standard_normal((n, S)).astype(np.float32), "rewards": rng.standard_normal((n, 1)).astype(np.float32),
+                     "terminals": np.zeros((n, 1), np.float32)})
+        b._draw = 7 + sd
+        bufs.append(b)
+    RW = bufs[0].RW
+    rows = torch.empty(sum(ns), RW, dtype=torch.float32, device="cuda")
+    jobs = (_ffi.SampleJob * 3)()
+    lo = 0
+    for jb, b, n in zip(jobs, bufs, ns):
+        jb.rows, jb.n, jb.size, jb.draw, jb.seed, jb.out = _ffi.ptr(b._rows), n, b.size, b._draw, b.seed, rows.data_ptr() + 4 * RW * lo
+        lo += n
+    _ffi.check(_ffi.lib().mobody_sample_rows(jobs, 3, RW, _ffi.stream_ptr(torch.device("cuda"))))
+    want = torch.cat([b.sample_rows(n) for b, n in zip(bufs, ns)], 0)
+    assert torch.equal(rows, want)
