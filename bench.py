@@ -377,7 +377,9 @@ def main():
         "e2e": {"value": e2e_trans / e2e_s, "unit": UNIT, "h2d_bytes_per_step": Bn * S * 4, "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": args.steps * (T + (T - 1) * 4 + 1 + 3 + 2),   # per rollout: init, T steps, (T-1) x (3 compact + advance), 3 compact, pack, stats
         "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                     "traffic": None, "kernel": "fused rollout step", "kernel_ms": k_ms, "peak_source": pk_src + " bf16 burst",
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01f_step_tc_ncu_full_selected.csv);
+                     # algorithmic I/O is 240 B x 100 000 = 24.0 MB (part of the outputs is still in L2 when the kernel ends)
+                     "traffic": 21497856 if (Bn == 100_000 and prec == "bf16x2") else None, "kernel": "fused rollout step", "kernel_ms": k_ms, "peak_source": pk_src + " bf16 burst",
                      "mma_passes_per_gemm": split, "frac_of_mma_issued": ach * split / peak,
                      "flop_per_transition": flop},
         "clocks": clocks, "wall_s": wall,
@@ -389,7 +391,7 @@ def main():
     if upd_wall is not None:
         line["train"] = {"metric": "Q-weighted BC updates/sec", "value": upd_wall, "unit": "updates/s", "device_only": upd_dev,
                          "config": {"workload": f"MOBODY.train steady state, batch 128 (128 src + 128 tar + 64 fake rows), S{S}/A{A}",
-                                    "launches_per_update": 12, "dtype": "f32 (3xTF32 tensor-core MMA for the 256-wide layers, fp32 elsewhere)"},
+                                    "launches_per_update": 13, "dtype": "f32 (3xTF32 tensor-core MMA for the 256-wide layers, fp32 elsewhere)"},
                          "batch4096_S27A8": {"value": big_wall, "device_only": big_dev, "unit": "updates/s",
                                              "workload": "MOBODY.train steady state, batch 4096 (4096 src + 4096 tar + 2048 fake rows), S27/A8 (BASELINE configs[3])"}}
     if not args.no_cpu_baseline:
