@@ -193,14 +193,14 @@ def run_reference(args, rank):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    n = 20_000                               # bounded sample: ~1-2 s per step on 8+ cores
+    n = B_PER_GPU                            # one full rollout of the workload per step: ~1.3 s on 16 cores
     rate, dt = cpu_rollout_rate(n, cores, repeats=max(args.steps, 1))   # includes one warm-up pass
     val = rate
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"halfcheetah-gravity S{S}/A{A} rollout_length={T}, {B_PER_GPU} start states (BASELINE configs[1])",
-                       "sample": f"{n} of {B_PER_GPU} start states per step"},
+                       "sample": f"{n} of {B_PER_GPU} start states per step (the full workload)"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"oracle.rollout on {n} start states, best of {max(args.steps, 1)} after 1 warm-up, torch threads={cores}"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -399,11 +399,11 @@ def main():
         if upd_wall is not None:
             line["train"]["cpu_baseline"] = {"value": cpu_train_rate(128, cores), "unit": "updates/s", "cores": cores, "kind": "port",
                                              "sample": "oracle.train_step incl. 3 buffer gathers, 5 steps after 2 warm-up"}
-        n = 20_000
-        rate, dt = cpu_rollout_rate(n, cores, repeats=2)
+        n = min(Bn, 100_000)                   # the whole workload (~1.3 s per pass on 16 cores), best of 3 after a warm-up
+        rate, dt = cpu_rollout_rate(n, cores, repeats=3)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"oracle.rollout (CPU restatement of MOBODY.rollout) on {n} of {Bn} start states, "
-                                          f"best of 2 after 1 warm-up, torch threads={cores}"}
+                                          f"best of 3 after 1 warm-up, torch threads={cores}"}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
