@@ -38,6 +38,7 @@ const char* mb_tc_dyn_pack(const DynPtrs& dp, int S, int A, int ns, unsigned cha
 const char* mb_tc_mlp_pack(const MlpPtrs& mp, int din, int dout, int ns, unsigned char* blob, cudaStream_t st);
 const char* mb_tc_step_launch(const StepArgs& a, const unsigned char* dynb, const unsigned char* polb, int ns, cudaStream_t st);
 int mb_tc_use_pair();
+const char* mb_tc_duo_step_launch(const StepArgs& a, const unsigned char* dynb, const unsigned char* polb, cudaStream_t st, bool* launched);
 const char* mb_tc_pair_step_launch(const StepArgs& a, const unsigned char* dynb, const unsigned char* polb, int ns, cudaStream_t st);
 const char* mb_umma_selftest_launch(const float* A, const float* B, int K, int N, int nsplit, float* D, cudaStream_t st);
 
@@ -108,6 +109,18 @@ int mobody_step(const mobody_step_desc* d, void* stream) {
       if (d->policy && !d->policy_pack) return fail(MOBODY_ERR_ARG, "mobody_step: fused policy needs policy_pack (mobody_mlp_pack)");
       {   // default: one CTA per 128-row tile; MOBODY_TC_PAIR=1 selects the experimental CTA-pair kernel (two tiles in flight)
         auto launch = mb_tc_use_pair() ? mb_tc_pair_step_launch : mb_tc_step_launch;   // the packed images are laid out for it
+        if (d->precision == MOBODY_PREC_BF16 && !mb_tc_use_pair()) {
+          // single bf16 plane: two row tiles fit in one SM -> the two-tiles-in-flight kernel (MOBODY_TC_DUO=0 disables it)
+          static int duo = -1;
+          if (duo < 0) { const char* e = getenv("MOBODY_TC_DUO"); duo = (e && atoi(e) == 0) ? 0 : 1; }
+          if (duo) {
+            bool launched = false;
+            err = mb_tc_duo_step_launch(a, (const unsigned char*)d->dyn_pack, d->policy ? (const unsigned char*)d->policy_pack : nullptr,
+                                        (cudaStream_t)stream, &launched);
+            if (err) return fail(MOBODY_ERR_UNSUPPORTED, err);
+            if (launched) return check_launch("mobody_step");
+          }
+        }
         err = launch(a, (const unsigned char*)d->dyn_pack, d->policy ? (const unsigned char*)d->policy_pack : nullptr,
                      d->precision == MOBODY_PREC_BF16X2 ? 2 : 1, (cudaStream_t)stream);
       }
