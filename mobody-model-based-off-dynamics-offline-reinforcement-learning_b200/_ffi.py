@@ -15,8 +15,8 @@ N_DYN_LAYERS = 13
 DYN_LAYER_NAMES = ("zs1", "zs2", "zs3", "za_src1", "za_src2", "za_trg1", "za_trg2",
                    "transition1", "transition2", "transition3",
                    "reward_model1", "reward_model2", "reward_model3")
-PREC = {"fp32": 0, "bf16x2": 1, "bf16": 2}
-ENABLED_PRECISIONS = ("fp32", "bf16x2", "bf16")
+PREC = {"fp32": 0, "bf16x2": 1, "bf16": 2, "fp16": 3}
+ENABLED_PRECISIONS = ("fp32", "bf16x2", "bf16", "fp16")
 KEEP_U8_ZERO, KEEP_F32_LE, KEEP_F32_LT, KEEP_U8_VALID = 0, 1, 2, 3
 
 

@@ -34,11 +34,11 @@ void mb_rollout_pack_launch(const float* obss, const float* acts, const float* n
 void mb_rollout_stats_launch(const float* rews, const unsigned char* terms, long long n, double* partial, unsigned int* ticket,
                              double* stats, cudaStream_t st);
 
-const char* mb_tc_dyn_pack(const DynPtrs& dp, int S, int A, int ns, unsigned char* blob, cudaStream_t st);
-const char* mb_tc_mlp_pack(const MlpPtrs& mp, int din, int dout, int ns, unsigned char* blob, cudaStream_t st);
+const char* mb_tc_dyn_pack(const DynPtrs& dp, int S, int A, int ns, int fp16, unsigned char* blob, cudaStream_t st);
+const char* mb_tc_mlp_pack(const MlpPtrs& mp, int din, int dout, int ns, int fp16, unsigned char* blob, cudaStream_t st);
 const char* mb_tc_step_launch(const StepArgs& a, const unsigned char* dynb, const unsigned char* polb, int ns, cudaStream_t st);
 int mb_tc_use_pair();
-const char* mb_tc_duo_step_launch(const StepArgs& a, const unsigned char* dynb, const unsigned char* polb, cudaStream_t st, bool* launched);
+const char* mb_tc_duo_step_launch(const StepArgs& a, const unsigned char* dynb, const unsigned char* polb, int fp16, cudaStream_t st, bool* launched);
 const char* mb_tc_pair_step_launch(const StepArgs& a, const unsigned char* dynb, const unsigned char* polb, int ns, cudaStream_t st);
 const char* mb_umma_selftest_launch(const float* A, const float* B, int K, int N, int nsplit, float* D, cudaStream_t st);
 
@@ -103,6 +103,15 @@ int mobody_step(const mobody_step_desc* d, void* stream) {
   const char* err = nullptr;
   switch (d->precision) {
     case MOBODY_PREC_FP32: err = mb_simt_step_launch(a, dp, polp, (cudaStream_t)stream); break;
+    case MOBODY_PREC_FP16: {
+      if (!d->dyn_pack) return fail(MOBODY_ERR_ARG, "mobody_step: tensor-core precision needs dyn_pack (mobody_dyn_pack)");
+      if (d->policy && !d->policy_pack) return fail(MOBODY_ERR_ARG, "mobody_step: fused policy needs policy_pack (mobody_mlp_pack)");
+      if (mb_tc_use_pair()) return fail(MOBODY_ERR_UNSUPPORTED, "mobody_step: the fp16 mode is not available with MOBODY_TC_PAIR=1");
+      bool launched = false;
+      err = mb_tc_duo_step_launch(a, (const unsigned char*)d->dyn_pack, d->policy ? (const unsigned char*)d->policy_pack : nullptr, 1,
+                                  (cudaStream_t)stream, &launched);
+      if (!err && !launched) err = "fp16 mode: two row tiles do not fit in shared memory for this (S, A); use bf16 or bf16x2";
+    } break;
     case MOBODY_PREC_BF16X2:
     case MOBODY_PREC_BF16:
       if (!d->dyn_pack) return fail(MOBODY_ERR_ARG, "mobody_step: tensor-core precision needs dyn_pack (mobody_dyn_pack)");
@@ -115,7 +124,7 @@ int mobody_step(const mobody_step_desc* d, void* stream) {
           if (duo < 0) { const char* e = getenv("MOBODY_TC_DUO"); duo = (e && atoi(e) == 0) ? 0 : 1; }
           if (duo) {
             bool launched = false;
-            err = mb_tc_duo_step_launch(a, (const unsigned char*)d->dyn_pack, d->policy ? (const unsigned char*)d->policy_pack : nullptr,
+            err = mb_tc_duo_step_launch(a, (const unsigned char*)d->dyn_pack, d->policy ? (const unsigned char*)d->policy_pack : nullptr, 0,
                                         (cudaStream_t)stream, &launched);
             if (err) return fail(MOBODY_ERR_UNSUPPORTED, err);
             if (launched) return check_launch("mobody_step");
@@ -308,7 +317,7 @@ int mobody_dara_relabel(float* rows, long long n, int S, int A, int row_width, c
   return check_launch("mobody_dara_relabel");
 }
 
-static int nsplit_of(int precision) { return precision == MOBODY_PREC_BF16X2 ? 2 : precision == MOBODY_PREC_BF16 ? 1 : 0; }
+static int nsplit_of(int precision) { return precision == MOBODY_PREC_BF16X2 ? 2 : (precision == MOBODY_PREC_BF16 || precision == MOBODY_PREC_FP16) ? 1 : 0; }
 
 long long mobody_dyn_pack_bytes(int S, int A, int precision) {
   int ns = nsplit_of(precision);
@@ -322,7 +331,7 @@ int mobody_dyn_pack(const mobody_dyn_params* dyn, int S, int A, int precision, v
   DynPtrs dp; memcpy(&dp, dyn, sizeof(dp));
   for (int i = 0; i < L_COUNT; ++i)
     if (!dp.w[i] || !dp.b[i]) return fail(MOBODY_ERR_ARG, "mobody_dyn_pack: null parameter pointer");
-  const char* err = mb_tc_dyn_pack(dp, S, A, ns, (unsigned char*)blob, (cudaStream_t)stream);
+  const char* err = mb_tc_dyn_pack(dp, S, A, ns, precision == MOBODY_PREC_FP16, (unsigned char*)blob, (cudaStream_t)stream);
   if (err) return fail(MOBODY_ERR_ARG, err);
   return check_launch("mobody_dyn_pack");
 }
@@ -337,7 +346,7 @@ int mobody_mlp_pack(const mobody_mlp_params* mlp, int din, int dout, int precisi
   int ns = nsplit_of(precision);
   if (!ns || !mlp || !blob || din < 1 || dout < 1) return fail(MOBODY_ERR_ARG, "mobody_mlp_pack: bad arguments");
   MlpPtrs mp; memcpy(&mp, mlp, sizeof(mp));
-  const char* err = mb_tc_mlp_pack(mp, din, dout, ns, (unsigned char*)blob, (cudaStream_t)stream);
+  const char* err = mb_tc_mlp_pack(mp, din, dout, ns, precision == MOBODY_PREC_FP16, (unsigned char*)blob, (cudaStream_t)stream);
   if (err) return fail(MOBODY_ERR_ARG, err);
   return check_launch("mobody_mlp_pack");
 }

@@ -35,6 +35,7 @@ struct Cfg {
   uint32_t stage_bytes, small_plane, sa_off, obs_kp, sas_kp;
   uint32_t dyn_bias_base, pol_bias_base;
   int has_policy, first_dyn;
+  long long* trace;     // debug: clock64 stamps of CTA 0, [(layer * 2 + tile)][8]; nullptr in production
 };
 
 struct Bars {
@@ -43,6 +44,8 @@ struct Bars {
   uint32_t tmem_slot, pad;
 };
 
+// F16: fp16 operands and the packed-half epilogue (tc_epi.cuh) instead of bf16 operands and fp32 epilogue math.
+template <bool F16>
 __global__ void __launch_bounds__(NTHREADS, 1)
 step_duo_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const unsigned char* __restrict__ polb,
                 const __grid_constant__ TcSched sched, const Cfg cfg) {
@@ -93,11 +96,15 @@ step_duo_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const 
           tc::mbar_arrive_expect_tx(&bars->b_full[slot], bb);
           tc::bulk_g2s(bias_s + slot * BSLOT, bsrc, bb, &bars->b_full[slot]);
         }
+        // a unit's MMAs wait for the tile's whole previous epilogue, so nothing hides the ring's load -> MMA -> commit ->
+        // reload round trip here: narrow layers put as many K steps as fit into one stage (one copy, one round trip)
+        const int kps = max(1, min((int)L.ksteps, (int)(cfg.stage_bytes / bytes)));
         for (int u = 0; u < 2; ++u)
-          for (int s = 0; s < L.ksteps; ++s) {
+          for (int s = 0; s < L.ksteps; s += kps) {
+            const uint32_t nb = (uint32_t)min(kps, (int)L.ksteps - s) * bytes;
             tc::mbar_wait(&bars->w_empty[stage], phase ^ 1u);
-            tc::mbar_arrive_expect_tx(&bars->w_full[stage], bytes);
-            tc::bulk_g2s(wst + (size_t)stage * cfg.stage_bytes, src + (size_t)s * bytes, bytes, &bars->w_full[stage]);
+            tc::mbar_arrive_expect_tx(&bars->w_full[stage], nb);
+            tc::bulk_g2s(wst + (size_t)stage * cfg.stage_bytes, src + (size_t)s * bytes, nb, &bars->w_full[stage]);
             if (++stage == cfg.nst) { stage = 0; phase ^= 1u; }
           }
       }
@@ -109,26 +116,38 @@ step_duo_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const 
       const uint32_t wst0 = tc::smem_u32(wst);
       for (int li = 0; li < sched.n_layers; ++li) {
         const TcLayer L = sched.L[li];
-        const uint32_t idesc = tc::make_idesc_bf16(128, L.n);
+        const uint32_t idesc = F16 ? tc::make_idesc_f16(128, L.n) : tc::make_idesc_bf16(128, L.n);
         const uint32_t blbo = (uint32_t)L.n * 16u;
+        const int kps = max(1, min((int)L.ksteps, (int)(cfg.stage_bytes / ((uint32_t)L.n * 32u))));     // K steps per ring stage (see the producer)
         for (int u = 0; u < 2; ++u) {
           const uint32_t dcol = tmem + (uint32_t)u * 256u;
           if (li >= 1) tc::mbar_wait(&bars->d_empty[u], (uint32_t)((li - 1) & 1));      // accumulator of this tile drained
           if (L.a_wait) { tc::mbar_wait(&bars->a_ready[u], aph[u]); aph[u] ^= 1u; }       // operand written by the last epilogue
           tc::tc_fence_after();
+          if (cfg.trace && blockIdx.x == 0) cfg.trace[(li * 2 + u) * 8 + 0] = clock64();
           uint32_t abase;
           if (L.a_region == REG_MAIN) abase = tc::smem_u32(main_of(u));
           else abase = tc::smem_u32(small_of(u)) + (L.a_region == REG_SA ? cfg.sa_off : 0u);
-          for (int s = 0; s < L.ksteps; ++s) {
+          // one barrier wait and one commit per ring STAGE; inside a stage only descriptor increments and MMAs (the issuing
+          // thread's serial latency per K step, ~230 cycles with a wait in it, exceeds the 128 cycles the MMA itself takes)
+          const uint32_t kb16 = ((uint32_t)L.n * 32u) >> 4;
+          const uint64_t b_tmpl = tc::make_smem_desc(0, blbo, 128);
+          uint64_t ad = tc::make_smem_desc(abase, 2048, 128);
+          uint32_t acc = 0u;
+          for (int s0 = 0; s0 < L.ksteps; s0 += kps) {
             tc::mbar_wait(&bars->w_full[stage], wphase);
             tc::tc_fence_after();
-            const uint64_t ad = tc::make_smem_desc(abase + (uint32_t)s * 4096u, 2048, 128);
-            const uint64_t bd = tc::make_smem_desc(wst0 + (uint32_t)stage * cfg.stage_bytes, blbo, 128);
-            tc::umma_bf16(dcol, ad, bd, idesc, s > 0 ? 1u : 0u);
+            uint64_t bd = b_tmpl + (uint64_t)((wst0 + (uint32_t)stage * cfg.stage_bytes) >> 4);
+            const int ne = min(kps, (int)L.ksteps - s0);
+            for (int j = 0; j < ne; ++j) {
+              tc::umma_bf16(dcol, ad, bd, idesc, acc);
+              acc = 1u; ad += 256u; bd += kb16;                          // next K step: 4096 bytes of A, one K step of B
+            }
             tc::umma_commit(&bars->w_empty[stage]);
             if (++stage == cfg.nst) { stage = 0; wphase ^= 1u; }
           }
           tc::umma_commit(&bars->d_full[u]);
+          if (cfg.trace && blockIdx.x == 0) cfg.trace[(li * 2 + u) * 8 + 2] = clock64();
         }
       }
     }
@@ -143,8 +162,15 @@ step_duo_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const 
     float racc[2] = {0.f, 0.f}, pen[2] = {0.f, 0.f};
 
     auto row0_of = [&](int u) { return (size_t)cta_row0 + (size_t)u * TM; };
-    auto wait_d = [&](int u, int l) { tc::mbar_wait(&bars->d_full[u], (uint32_t)(l & 1)); tc::tc_fence_after(); };
+    const bool tracer = cfg.trace && blockIdx.x == 0 && warp == 0 && lane == 0;
+    auto wait_d = [&](int u, int l) {
+      if (tracer) cfg.trace[(l * 2 + u) * 8 + 3] = clock64();
+      tc::mbar_wait(&bars->d_full[u], (uint32_t)(l & 1)); tc::tc_fence_after();
+      if (tracer) cfg.trace[(l * 2 + u) * 8 + 4] = clock64();
+    };
+    int cur_l = 0;
     auto release_d = [&](int u) {
+      if (tracer) cfg.trace[(cur_l * 2 + u) * 8 + 5] = clock64();
       tc::tc_fence_before(); __syncwarp();
       if (lane == 0) tc::mbar_arrive(&bars->d_empty[u]);
     };
@@ -157,33 +183,49 @@ step_duo_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const 
       return bias_s + (l & (NB - 1)) * BSLOT;
     };
     auto bias_done = [&](int l) { __syncwarp(); if (lane == 0) tc::mbar_arrive(&bars->b_empty[l & (NB - 1)]); };
+    auto put8 = [&](unsigned char* base, uint32_t off, const float (&v)[8]) {      // 8 fp32 values -> one 16-byte operand word group
+      if (F16) store8_f16(base, off, v); else store8<NS>(base, 0u, off, v);
+    };
     auto ld8s = [&](const float* b, float (&bv)[8]) {
       const float4 t0 = *reinterpret_cast<const float4*>(b), t1 = *(reinterpret_cast<const float4*>(b) + 1);
       bv[0] = t0.x; bv[1] = t0.y; bv[2] = t0.z; bv[3] = t0.w; bv[4] = t1.x; bv[5] = t1.y; bv[6] = t1.z; bv[7] = t1.w;
     };
 
-    // 256-wide hidden layer of tile u: act(x + b) -> A_main[u]; 8 chunks of 32 columns, 8 columns per warp
+    // 256-wide hidden layer of tile u: act(x + b) -> A_main[u].  Nothing trails this epilogue chunk by chunk (the tile's
+    // next MMA waits for the whole unit), so warp group g simply owns the 64-column slab [64 g, 64 g + 64): four TMEM
+    // loads of 16 columns, double buffered, 16 independent activations in flight per warp.
     auto epi_act256 = [&](int l, int u, bool relu) {
-      const float* bias = bias_of(l) + col0;
-      const uint32_t t0 = lane_base + (uint32_t)u * 256u + (uint32_t)col0;
+      const float* bias = bias_of(l) + group * 64;
+      const uint32_t t0 = lane_base + (uint32_t)u * 256u + (uint32_t)(group * 64);
       unsigned char* Am = main_of(u);
       wait_d(u, l);
-      uint32_t xa[8], xb[8];
-      auto chunk = [&](int c, const uint32_t (&x)[8]) {
-        float bv[8], v[8];
-        ld8s(bias + c * 32, bv);
-        act8<NS>(x, bv, v, relu);
-        store8<NS>(Am, MAIN_PLANE, (uint32_t)(c * 4 + group) * 2048u + (uint32_t)r * 16u, v);
+      uint32_t xa[16], xb[16];
+      auto slab = [&](int c, const uint32_t (&x)[16]) {            // columns 64 g + 16 c .. + 15 = k-groups 8 g + 2 c, + 1
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          float bv[8];
+          ld8s(bias + c * 16 + h * 8, bv);
+          const uint32_t off = (uint32_t)(group * 8 + c * 2 + h) * 2048u + (uint32_t)r * 16u;
+          if (F16) {
+            uint32_t o[4];
+            act8_f16(&x[h * 8], bv, o, relu);
+            *reinterpret_cast<uint4*>(Am + off) = make_uint4(o[0], o[1], o[2], o[3]);
+          } else {
+            float v[8];
+            act8<NS>(&x[h * 8], bv, v, relu);
+            store8<NS>(Am, MAIN_PLANE, off, v);
+          }
+        }
       };
-      tc::tmem_ld8(t0, xa);
+      tc::tmem_ld16(t0, xa);
 #pragma unroll 1
-      for (int c = 0; c < 8; c += 2) {
+      for (int c = 0; c < 4; c += 2) {
         tc::tmem_ld_wait();
-        tc::tmem_ld8(t0 + (uint32_t)(c + 1) * 32u, xb);
-        chunk(c, xa);
+        tc::tmem_ld16(t0 + (uint32_t)(c + 1) * 16u, xb);
+        slab(c, xa);
         tc::tmem_ld_wait();
-        if (c + 2 < 8) tc::tmem_ld8(t0 + (uint32_t)(c + 2) * 32u, xa);
-        chunk(c + 1, xb);
+        if (c + 2 < 4) tc::tmem_ld16(t0 + (uint32_t)(c + 2) * 16u, xa);
+        slab(c + 1, xb);
       }
       signal_a(u);
       release_d(u);
@@ -200,14 +242,14 @@ step_duo_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const 
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) { int j = kg * 8 + i; v[i] = (valid && j < S) ? __ldg(orow + j) : 0.f; }
-        store8<NS>(As, sp, (uint32_t)kg * 2048u + (uint32_t)r * 16u, v);
+        put8(As, (uint32_t)kg * 2048u + (uint32_t)r * 16u, v);
       }
       if (!cfg.has_policy && group < 2) {
         const float* arow = a.act + grow * A;
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) { int j = group * 8 + i; v[i] = (valid && j < A) ? __ldg(arow + j) : 0.f; }
-        store8<NS>(As, sp, cfg.sa_off + (uint32_t)(2 + group) * 2048u + (uint32_t)r * 16u, v);
+        put8(As, cfg.sa_off + (uint32_t)(2 + group) * 2048u + (uint32_t)r * 16u, v);
       }
       signal_a(u);
     }
@@ -307,7 +349,7 @@ step_duo_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const 
             }
             v[i] = t;
           }
-          store8<NS>(As, sp, (uint32_t)kg * 2048u + (uint32_t)r * 16u, v);
+          put8(As, (uint32_t)kg * 2048u + (uint32_t)r * 16u, v);
         }
         tc::fence_proxy_async_smem();
       }
@@ -320,6 +362,7 @@ step_duo_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const 
 #pragma unroll 1
     for (int l = 0; l < sched.n_layers; ++l) {
       const int kind = sched.L[l].kind, n = sched.L[l].n;
+      cur_l = l;
       const int e = (l >= cfg.first_dyn && kind != EPI_REWARD) ? (l - cfg.first_dyn) >> 3 : 0;
 #pragma unroll 1
       for (int u = 0; u < 2; ++u) {
@@ -342,7 +385,7 @@ step_duo_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const 
                 v[i] = (j < A) ? tanhf(__uint_as_float(x[i]) + bias[j]) * a.max_action : 0.f;
                 if (valid && j < A && a.act_out) a.act_out[grow * A + j] = v[i];
               }
-              store8<NS>(small_of(u), sp, cfg.sa_off + (uint32_t)(2 + group) * 2048u + (uint32_t)r * 16u, v);
+              put8(small_of(u), cfg.sa_off + (uint32_t)(2 + group) * 2048u + (uint32_t)r * 16u, v);
             }
             release_d(u); bias_done(l);
           } break;
@@ -355,7 +398,7 @@ step_duo_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const 
               float v[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) { zs[u][i] = __uint_as_float(x[i]) + bias[col0 + i]; v[i] = zs[u][i]; }
-              store8<NS>(small_of(u), sp, cfg.sa_off + (uint32_t)group * 2048u + (uint32_t)r * 16u, v);
+              put8(small_of(u), cfg.sa_off + (uint32_t)group * 2048u + (uint32_t)r * 16u, v);
             }
             signal_a(u);
             release_d(u); bias_done(l);
@@ -368,7 +411,7 @@ step_duo_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const 
               tc::tmem_ld8(tbase + (uint32_t)col0, x); tc::tmem_ld_wait();
               float v[8];
               act8<NS>(x, bias + col0, v, false);
-              store8<NS>(main_of(u), MAIN_PLANE, (uint32_t)group * 2048u + (uint32_t)r * 16u, v);
+              put8(main_of(u), (uint32_t)group * 2048u + (uint32_t)r * 16u, v);
             }
             signal_a(u);
             release_d(u); bias_done(l);
@@ -382,7 +425,7 @@ step_duo_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const 
               float v[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) v[i] = zs[u][i] + (__uint_as_float(x[i]) + bias[col0 + i]);
-              store8<NS>(main_of(u), MAIN_PLANE, (uint32_t)group * 2048u + (uint32_t)r * 16u, v);
+              put8(main_of(u), (uint32_t)group * 2048u + (uint32_t)r * 16u, v);
             }
             signal_a(u);
             release_d(u); bias_done(l);
@@ -404,28 +447,36 @@ step_duo_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const 
           } break;
           case EPI_REWARD: {                                    // reward_model2 -> swish -> dot reward_model3[:,0]
             const float* bslot = bias_of(l);
-            const float* bias = bslot + col0;
-            const float* w3 = bslot + 256 + col0;
-            const uint32_t t0 = tbase + (uint32_t)col0;
+            const float* bias = bslot + group * 64;
+            const float* w3 = bslot + 256 + group * 64;
+            const uint32_t t0 = tbase + (uint32_t)(group * 64);
             float part = 0.f;
             wait_d(u, l);
-            uint32_t xa[8], xb[8];
-            auto chunk = [&](int c, const uint32_t (&x)[8]) {
-              float bv[8], wv[8], v[8];
-              ld8s(bias + c * 32, bv); ld8s(w3 + c * 32, wv);
-              act8<NS>(x, bv, v, false);
+            uint32_t xa[16], xb[16];
+            auto slab = [&](int c, const uint32_t (&x)[16]) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) part = fmaf(v[i], wv[i], part);
+              for (int h = 0; h < 2; ++h) {
+                float bv[8], wv[8], v[8];
+                ld8s(bias + c * 16 + h * 8, bv); ld8s(w3 + c * 16 + h * 8, wv);
+                if (F16) {
+                  uint32_t o[4];
+                  act8_f16(&x[h * 8], bv, o, false);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) unpack_f16x2(o[i], v[2 * i], v[2 * i + 1]);
+                } else act8<NS>(&x[h * 8], bv, v, false);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) part = fmaf(v[i], wv[i], part);
+              }
             };
-            tc::tmem_ld8(t0, xa);
+            tc::tmem_ld16(t0, xa);
 #pragma unroll 1
-            for (int c = 0; c < 8; c += 2) {
+            for (int c = 0; c < 4; c += 2) {
               tc::tmem_ld_wait();
-              tc::tmem_ld8(t0 + (uint32_t)(c + 1) * 32u, xb);
-              chunk(c, xa);
+              tc::tmem_ld16(t0 + (uint32_t)(c + 1) * 16u, xb);
+              slab(c, xa);
               tc::tmem_ld_wait();
-              if (c + 2 < 8) tc::tmem_ld8(t0 + (uint32_t)(c + 2) * 32u, xa);
-              chunk(c + 1, xb);
+              if (c + 2 < 4) tc::tmem_ld16(t0 + (uint32_t)(c + 2) * 16u, xa);
+              slab(c + 1, xb);
             }
             const float b3 = bslot[512];
             release_d(u); bias_done(l);
@@ -463,8 +514,10 @@ step_duo_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const 
 
 }  // namespace tcd
 
-// Single-pass bf16 only.  Returns "" (empty string) when this (S, A) does not fit two tiles, so the caller falls back.
-const char* mb_tc_duo_step_launch(const StepArgs& a, const unsigned char* dynb, const unsigned char* polb, cudaStream_t st, bool* launched) {
+long long* mb_tc_get_trace();
+
+// Single-pass modes only.  Returns "" (empty string) when this (S, A) does not fit two tiles, so the caller falls back.
+const char* mb_tc_duo_step_launch(const StepArgs& a, const unsigned char* dynb, const unsigned char* polb, int fp16, cudaStream_t st, bool* launched) {
   *launched = false;
   if (a.B <= 0) { *launched = true; return nullptr; }
   const int S = a.S, A = a.A, ns = 1;
@@ -513,21 +566,25 @@ const char* mb_tc_duo_step_launch(const StepArgs& a, const unsigned char* dynb, 
   cfg.sa_off = (cfg.obs_kp / 8) * 2048u;
   uint32_t small = cfg.sa_off + 4 * 2048u, sasb = (cfg.sas_kp / 8) * 2048u;
   cfg.small_plane = small > sasb ? small : sasb;
-  cfg.stage_bytes = 256u * 32u;
   cfg.dyn_bias_base = (uint32_t)DL.bias_base;
   cfg.has_policy = has_policy ? 1 : 0;
+  cfg.trace = mb_tc_get_trace();
   const size_t fixed = 2 * ((size_t)tcd::MAIN_PLANE + (size_t)cfg.small_plane) +
                        (2 * 4 * tcd::TM + tcd::NB * tcd::BSLOT) * sizeof(float) + sizeof(tcd::Bars) + 128;
   const size_t budget = 227 * 1024;
+  // ring stage: 16 KB (two K steps of a 256-wide layer, every K step of a narrow one) when three of them fit, else 8 KB
+  cfg.stage_bytes = 2u * 256u * 32u;
+  if (fixed + 3 * cfg.stage_bytes > budget) cfg.stage_bytes = 256u * 32u;
   if (fixed + 3 * cfg.stage_bytes > budget) return nullptr;    // two tiles do not fit for this (S, A): caller falls back
   int nst = (int)((budget - fixed) / cfg.stage_bytes);
   if (nst > tcd::MAX_NST) nst = tcd::MAX_NST;
   cfg.nst = nst;
   const size_t bytes = fixed + (size_t)nst * cfg.stage_bytes;
-  if (cudaFuncSetAttribute(tcd::step_duo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+  auto kern = fp16 ? tcd::step_duo_kernel<true> : tcd::step_duo_kernel<false>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
     return "cudaFuncSetAttribute(step_duo_kernel) failed";
   const int grid = (a.B + 2 * tcd::TM - 1) / (2 * tcd::TM);
-  tcd::step_duo_kernel<<<grid, tcd::NTHREADS, bytes, st>>>(a, dynb, polb ? polb : dynb, sc, cfg);
+  kern<<<grid, tcd::NTHREADS, bytes, st>>>(a, dynb, polb ? polb : dynb, sc, cfg);
   *launched = true;
   return nullptr;
 }

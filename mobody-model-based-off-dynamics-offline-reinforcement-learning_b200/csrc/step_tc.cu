@@ -20,7 +20,7 @@
 //  A CTA-pair (cta_group::2) variant of this kernel lives on branch `cta-pair`: correct but slower here
 //  (the chain is latency-, not SMEM-bandwidth-bound); see DESIGN.md.
 //
-// Precision: NS = 1 -> single bf16 pass (stated bound 5e-3); NS = 2 -> bf16 hi+lo split of both
+// Precision: NS = 1 -> single bf16 pass (bound 2e-2; the fp16 single-pass mode lives in step_duo.cu); NS = 2 -> bf16 hi+lo split of both
 // operands, 3 MMAs per K step (hi*hi + lo*hi + hi*lo), ~2^-16 per product: inside the 1e-4 bound.
 #include "common.cuh"
 #include "philox.cuh"
@@ -28,6 +28,7 @@
 #include "tc_prims.cuh"
 #include "tc_layout.h"
 #include "tc_epi.cuh"
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace tcs {
@@ -535,7 +536,7 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
 // pair = 0: [kstep s][plane p][kgroup g][n < Np][8 k]            (one CTA stages the whole K step with one bulk copy)
 // pair = 1: [kstep s][half h][plane p][kgroup g][n_local < Np/2][8 k]   (CTA h of a pair stages its half with one bulk copy)
 __global__ void pack_weight_kernel(const float* __restrict__ W, long long stride_k, long long stride_n, int K, int N, int Kp,
-                                   int Np, int ns, int pair, float scale, __nv_bfloat16* __restrict__ out) {
+                                   int Np, int ns, int pair, int fp16, float scale, __nv_bfloat16* __restrict__ out) {
   const long long total = (long long)(Kp / 16) * ns * 2 * Np * 8;
   const int nh = Np / 2;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
@@ -553,6 +554,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ W, long long stride
     }
     int k = s * 16 + g * 8 + j;
     float v = (k < K && n < N) ? W[k * stride_k + n * stride_n] * scale : 0.f;
+    if (fp16) { reinterpret_cast<__half*>(out)[t] = __float2half_rn(v); continue; }     // single fp16 plane (ns == 1)
     __nv_bfloat16 h = __float2bfloat16_rn(v);
     out[t] = (p == 0) ? h : __float2bfloat16_rn(v - __bfloat162float(h));
   }
@@ -572,14 +574,15 @@ int mb_tc_use_pair() {
   return pair;
 }
 
-static inline void launch_pack_w(const float* W, long long sk, long long sn, const TcGeom& g, int ns, float scale, unsigned char* out, cudaStream_t st) {
+static inline void launch_pack_w(const float* W, long long sk, long long sn, const TcGeom& g, int ns, int fp16, float scale, unsigned char* out, cudaStream_t st) {
   long long total = (long long)(g.Kp / 16) * ns * 2 * g.Np * 8;
   int grid = (int)((total + 255) / 256); if (grid > 1184) grid = 1184;
-  tcs::pack_weight_kernel<<<grid, 256, 0, st>>>(W, sk, sn, g.K, g.N, g.Kp, g.Np, ns, mb_tc_use_pair(), scale, reinterpret_cast<__nv_bfloat16*>(out));
+  tcs::pack_weight_kernel<<<grid, 256, 0, st>>>(W, sk, sn, g.K, g.N, g.Kp, g.Np, ns, mb_tc_use_pair(), fp16, scale, reinterpret_cast<__nv_bfloat16*>(out));
 }
 
 // mobody_dyn_pack: all 7 members x 12 MMA layers + biases + reward_model3 vector
-const char* mb_tc_dyn_pack(const DynPtrs& dp, int S, int A, int ns, unsigned char* blob, cudaStream_t st) {
+const char* mb_tc_dyn_pack(const DynPtrs& dp, int S, int A, int ns, int fp16, unsigned char* blob, cudaStream_t st) {
+  if (fp16 && ns != 1) return "dyn_pack: fp16 is a single-plane format";
   if (ns != 1 && ns != 2) return "dyn_pack: nsplit must be 1 or 2";
   const TcDynLayout L = tc_dyn_layout(S, A, ns);
   static const int src[PK_COUNT] = {L_ZS1, L_ZS2, L_ZS3, L_ZASRC1, L_ZASRC2, L_ZATRG1, L_ZATRG2, L_T1, L_T2, L_T3, L_R1, L_R2};
@@ -593,7 +596,7 @@ const char* mb_tc_dyn_pack(const DynPtrs& dp, int S, int A, int ns, unsigned cha
       const TcGeom g = tc_dyn_geom(i, S, A);
       const int nfull = (i == PK_ZS3 || i == PK_ZASRC2 || i == PK_ZATRG2) ? 32 : g.N;     // mu half of 32 columns
       const float* W = dp.w[src[i]] + (size_t)e * g.K * nfull;
-      launch_pack_w(W, nfull, 1, g, ns, wscale, blob + (size_t)e * L.member_w_bytes + L.w_off[i], st);
+      launch_pack_w(W, nfull, 1, g, ns, fp16, wscale, blob + (size_t)e * L.member_w_bytes + L.w_off[i], st);
       tcs::pack_bias_kernel<<<(g.Np + 127) / 128, 128, 0, st>>>(dp.b[src[i]] + (size_t)e * nfull, 1, g.N, g.Np, bscale,
                                                                 bias + (size_t)e * L.member_b_floats + L.b_off[i]);
     }
@@ -605,12 +608,12 @@ const char* mb_tc_dyn_pack(const DynPtrs& dp, int S, int A, int ns, unsigned cha
   return nullptr;
 }
 
-const char* mb_tc_mlp_pack(const MlpPtrs& mp, int din, int dout, int ns, unsigned char* blob, cudaStream_t st) {
+const char* mb_tc_mlp_pack(const MlpPtrs& mp, int din, int dout, int ns, int fp16, unsigned char* blob, cudaStream_t st) {
   if (ns != 1 && ns != 2) return "mlp_pack: nsplit must be 1 or 2";
   const TcMlpLayout L = tc_mlp_layout(din, dout, ns);
   float* bias = reinterpret_cast<float*>(blob + L.bias_base);
   for (int i = 0; i < 3; ++i) {   // nn.Linear weight is [out][in]: stride_k = 1, stride_n = K
-    launch_pack_w(mp.w[i], 1, L.g[i].K, L.g[i], ns, 1.0f, blob + L.w_off[i], st);
+    launch_pack_w(mp.w[i], 1, L.g[i].K, L.g[i], ns, fp16, 1.0f, blob + L.w_off[i], st);
     tcs::pack_bias_kernel<<<(L.g[i].Np + 127) / 128, 128, 0, st>>>(mp.b[i], 1, L.g[i].N, L.g[i].Np, 1.0f, bias + L.b_off[i]);
   }
   return nullptr;

@@ -1,4 +1,5 @@
-"""Debug aid: per-unit timeline (clock64) of pair 0 of the CTA-pair step kernel."""
+"""Debug aid: per-(layer, tile) timeline (clock64) of CTA 0 of the two-tile step kernels: the CTA-pair kernel
+(MOBODY_TC_PAIR=1, precision bf16x2) or the two-tiles-per-CTA kernel (precision fp16 / bf16)."""
 import sys, os, ctypes
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -8,7 +9,7 @@ from mobody_b200 import _ffi
 from mobody_b200.dynamics import StepWorkspace
 
 prec = sys.argv[1] if len(sys.argv) > 1 else "bf16x2"
-B = int(sys.argv[2]) if len(sys.argv) > 2 else 256 * 74
+B = int(sys.argv[2]) if len(sys.argv) > 2 else 256 * 148
 S, A = 17, 6
 dyn, p = cuda_dynamics(S, A, 1, "halfcheetah", 5.0, precision=prec)
 ag, _ = cuda_agent(S, A, 1)
