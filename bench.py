@@ -13,7 +13,8 @@ penalty + termination + penalty filter), exactly what MOBODY.rollout does per re
   e2e     : the same through the public API MOBODY.rollout() with HOST buffers: pinned-host -> device
             copy of the start states and device -> host copy of the returned transition dict inside
             the timed region
-  roofline: tensor-core roofline of the fused step kernel (algorithmic FLOP / measured kernel time)
+  roofline: tensor-core roofline of the fused step kernel (algorithmic FLOP / measured kernel time) in the headline
+            fp32-parity mode (bf16 hi+lo split); the single-pass fp16 / bf16 modes (looser stated bounds) are timed too
   cpu_baseline: the oracle (CPU restatement of the reference, torch CPU) timed on this box's host cores
 
 `--impl reference` times the reference's CPU path (oracle port; the reference is Python and does not

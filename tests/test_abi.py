@@ -47,6 +47,21 @@ def test_argument_errors_are_reported_not_raised_across_abi(libpath):
     assert L.mobody_gather_rows(None, None, 4, 7, None, None) == -1     # row width not a multiple of 4
     assert L.mobody_ring_insert(None, 10, None, 44, 0, 5, None, None) == -1   # batch larger than capacity
     assert L.mobody_termination(None, 1, 17, 99, None, None) == -1
+    # whole-rollout / classifier / sampling entry points: descriptor validation happens before any launch
+    assert L.mobody_rollout(None, None) == -1 and b"null descriptor" in L.mobody_last_error()
+    rd = _ffi.RolloutDesc()
+    rd.T, rd.step.B, rd.step.S, rd.step.A = 0, 4, 17, 6
+    assert L.mobody_rollout(ctypes.byref(rd), None) == -1 and b"bad T" in L.mobody_last_error()
+    rd.T = 2
+    assert L.mobody_rollout(ctypes.byref(rd), None) == -1 and b"policy" in L.mobody_last_error()
+    assert L.mobody_classifier_step(None, None) == -1
+    assert L.mobody_dara_relabel(None, 5, 17, 6, 44, None, None, 1.0, None, None) == -1
+    assert L.mobody_sample_rows(None, 3, 44, None) == -1
+    sj = (_ffi.SampleJob * 1)()
+    sj[0].n, sj[0].size = 4, 0
+    assert L.mobody_sample_rows(sj, 1, 44, None) == -1 and b"empty buffer" in L.mobody_last_error()
+    assert L.mobody_dyn_pack_bytes(17, 6, 3) == L.mobody_dyn_pack_bytes(17, 6, 2) > 0      # fp16 and bf16 images have the same size
+    assert L.mobody_dyn_pack_bytes(17, 6, 0) == 0                                           # fp32 mode has no packed image
     with pytest.raises(RuntimeError, match="mobody_b200"):
         _ffi.check(-1)
 
