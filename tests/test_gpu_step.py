@@ -133,3 +133,19 @@ def test_policy_forward_matches_oracle():
         assert got.shape == (B, A) and rel_err(got, want) < 1e-4
         a1 = ag.select_action(x[:1].numpy(), ag.policy)            # numpy in, numpy out, squeezed (mobody.py:138-144)
         assert isinstance(a1, np.ndarray) and a1.shape == (A,)
+
+
+@pytest.mark.parametrize("env_var", ["MOBODY_TC_PAIR=1", "MOBODY_TC_DUO=0"])
+def test_alternative_tensor_core_kernels_in_subprocess(env_var):
+    """The kernel choice (and, for the CTA-pair kernel, the packed weight layout) is fixed per process by an environment
+    variable, so the alternatives are exercised in a child process: MOBODY_TC_PAIR=1 = experimental CTA-pair kernel for
+    the tensor-core modes; MOBODY_TC_DUO=0 = single-tile kernel for the single-pass bf16 mode."""
+    import subprocess
+    import sys
+    k, v = env_var.split("=")
+    env = dict(os.environ, **{k: v})
+    sel = "golden and (bf16x2 or bf16)" if k == "MOBODY_TC_PAIR" else "golden and bf16"
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-k", sel, "-p", "no:cacheprovider"],
+                       env=env, capture_output=True, text=True, timeout=300, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
