@@ -147,7 +147,8 @@ class MOBODY(object):
         [obs | act | next_obs | reward | terminal | penalty] (the slab the multi-GPU all-gather ships).
         sync=True: one host read at the end (row counts + reward sum); the returned dict holds [M, .] column views of
         the slab.  sync=False: nothing is read back; the dict holds capacity-sized views (rows >= kept are
-        unspecified) and info carries device tensors only (``kept_dev``, ``counts_dev``, ``stats_dev``).
+        unspecified) and info carries device tensors only (``kept_dev``, ``counts_dev``, ``stats_dev`` — views of the
+        cached workspace: consume them on the stream before the next rollout of the same shape overwrites them).
         Returns (dict of CUDA tensors, info) or (None, None) when rollout_length == 0."""
         if rollout_length == 0:
             return None, None                                    # mobody.py:602-603
