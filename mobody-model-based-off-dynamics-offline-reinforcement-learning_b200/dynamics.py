@@ -119,12 +119,19 @@ class MOBODYEnsembleDynamics(object):
     def _cached_params(self, kind, module, build):
         """Pointer struct of a module's live parameters, rebuilt only when a parameter's storage moved (building it
         costs ~0.1 ms of host time for the 26 ensemble tensors; the check costs a few microseconds)."""
-        ptrs = [p.data_ptr() for p in module.parameters()]
         ent = self._param_cache.get((kind, id(module)))
-        if ent is not None and ent[0] == ptrs:
-            return ent[1], ent[2]
+        if ent is not None:
+            ent[4] += 1
+            # walking the module tree costs more than everything else in a launch: the parameter list itself is re-read
+            # only every 64th call (a Parameter object replaced by hand is picked up then; .to() / load_state_dict / in-place
+            # optimiser steps keep the objects and are caught by the pointer comparison below on every call)
+            params = ent[3] if ent[4] & 63 else list(module.parameters())
+            if [p.data_ptr() for p in params] == ent[0]:
+                ent[3] = params
+                return ent[1], ent[2]
         struct, keep = build(module)
-        self._param_cache[(kind, id(module))] = (ptrs, struct, keep)
+        params = list(module.parameters())
+        self._param_cache[(kind, id(module))] = [[p.data_ptr() for p in params], struct, keep, params, 0]
         return struct, keep
 
     def fill_step_desc(self, d, B, S, dev, *, policy=None, max_action=1.0, use_penalty=True, use_trg=True):

@@ -35,3 +35,19 @@ for pr in (18944, 37888, 56832):
     print(f"rollout(host) PIPE_ROWS={pr} ms", timeit(quiet(lambda: ag.rollout(obs_host, 1))))
 ag.PIPE_ROWS = 10**9
 print("rollout(host) unpipelined ms", timeit(quiet(lambda: ag.rollout(obs_host, 1))))
+
+# host-side cost of one asynchronous rollout_device call (Python + ctypes + launches), GPU idle in between
+import cProfile, pstats
+ag.PIPE_ROWS = 37888
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(50):
+    ag.rollout_device(x, 1, sync=False)
+host = (time.perf_counter() - t0) / 50 * 1e3
+torch.cuda.synchronize()
+print("host time per rollout_device(sync=False) call ms", host)
+pr = cProfile.Profile(); pr.enable()
+for _ in range(50):
+    ag.rollout_device(x, 1, sync=False)
+pr.disable(); torch.cuda.synchronize()
+pstats.Stats(pr).sort_stats("cumulative").print_stats(14)
