@@ -60,7 +60,7 @@ __device__ __forceinline__ void act8(const uint32_t* x, const float* b, float (&
 // result is already the next layer's operand word: 2.5 instructions and half an SFU op per element (fp32 path: ~5.6 / 1).
 __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   uint32_t d;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));   // saturates at +-65504 instead of producing inf
   return d;
 }
 __device__ __forceinline__ void unpack_f16x2(uint32_t w, float& lo, float& hi) {

@@ -6,6 +6,7 @@ import pytest
 import torch
 
 from helpers import cuda_agent, cuda_dynamics, rel_err
+from oracle import mobody_oracle as M
 
 pytestmark = pytest.mark.gpu
 
@@ -93,3 +94,43 @@ def test_pipelined_host_rollout_equals_single_pass(precision, capsys):
     for k in ("obss", "actions", "next_obss", "rewards", "terminals", "penalty"):
         assert not tr[k].is_cuda and tuple(tr[k].shape) == tuple(ref[k].shape), k
         assert torch.equal(tr[k], ref[k].cpu()), k
+
+
+def test_full_size_rollout_properties_and_sampled_oracle_parity():
+    """BASELINE configs[1] size (100 000 start states, obs 17 / act 6, one step, production Philox draws): size-independent
+    properties — run-to-run bit determinism, independence from how the rows are sharded (three shards with their global
+    row offsets == one pass), output ranges and counts — and parity of a random sample of rows against the CPU oracle fed
+    the same Philox draws (noise from oracle.philox, member picks from the elite slots)."""
+    from oracle.philox import rollout_noise, rollout_elite_slot
+    S, A, B = 17, 6, 100_000
+    dyn, p = cuda_dynamics(S, A, 1, "halfcheetah", 5.0, precision="bf16x2")
+    dyn.seed = 77
+    ag, st = cuda_agent(S, A, 1, env_filter=1e9)
+    ag.dynamics = dyn
+    rng = np.random.default_rng(100)
+    obs_np = (0.3 * rng.standard_normal((B, S))).astype(np.float32)
+    obs = torch.from_numpy(obs_np).cuda()
+    a, ia = ag.rollout_device(obs, 1)
+    pa = ia["packed"][:ia["kept"]].clone()
+    b, ib = ag.rollout_device(obs, 1)
+    assert ia["kept"] == ib["kept"] == B and ia["num_transitions"] == B
+    assert torch.equal(pa, ib["packed"][:B])                                   # bit-deterministic
+    cuts = [0, 33_333, 70_001, B]
+    parts = [ag.rollout_device(obs[lo:hi].contiguous(), 1, row0=lo)[1] for lo, hi in zip(cuts[:-1], cuts[1:])]
+    assert torch.equal(torch.cat([q["packed"][:q["kept"]] for q in parts], 0), pa)    # shard invariant, order preserved
+    term, pen = pa[:, 2 * S + A + 1], pa[:, 2 * S + A + 2]
+    assert bool(((term == 0) | (term == 1)).all()) and bool((pen >= 0).all()) and bool(torch.isfinite(pa).all())
+    assert torch.equal(pa[:, :S], obs)                                         # the obs columns are the start states, in order
+    rows = np.sort(rng.choice(B, 256, replace=False))
+    eps_sel = rollout_noise(77, 0, rows, S)
+    members = p["elites"].numpy()[rollout_elite_slot(77, 0, rows, 5)]
+    eps = np.zeros((7, len(rows), S), np.float32); eps[members, np.arange(len(rows))] = eps_sel
+    so = torch.from_numpy(obs_np[rows])
+    act = M.policy_forward(st.policy, so, 1.0)
+    ref = M.step(p, so, act, torch.from_numpy(eps), members, 1, 5.0)
+    got = pa[torch.from_numpy(rows).cuda()].cpu().numpy()
+    assert rel_err(got[:, S:S + A], act.numpy()) < 1e-4
+    assert rel_err(got[:, S + A:2 * S + A], ref["next_obs"].numpy()) < 1e-4
+    assert rel_err(got[:, 2 * S + A:2 * S + A + 1], ref["reward"].numpy()) < 1e-4
+    assert rel_err(got[:, 2 * S + A + 2:2 * S + A + 3], ref["penalty"].numpy()) < 1e-4
+    assert np.array_equal(got[:, 2 * S + A + 1] != 0, ref["terminal"][:, 0])
