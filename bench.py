@@ -30,7 +30,6 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -113,6 +112,32 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": self.n, "source": "nvml" if self.nv else "nvidia-smi"}
 
 
+AGENT_CFG = dict(max_action=1.0, hidden_sizes=256, gamma=0.99, tau=0.005, update_interval=2, actor_lr=3e-4, critic_lr=3e-4,
+                 gaussian_noise_std=1.0, weight=2.5, penalty_type="none", penalty_coef=0.1, mopo=0, latent_reward=0, advantage=0,
+                 q_weighted=1, scale_Q=1, bc_coef=1.0, fake_batch_scale=0.5, src_ratio=1, trg_ratio=1, filter_bad_rollout=1,
+                 env_filter=ENV_FILTER, src_rollout_length=1, trg_rollout_length=1, use_src_sa_to_get_target_next_state=1,
+                 rollout_from_src=0)
+
+
+def build_dynamics(mb, s_dim, a_dim, precision, dev, seed=1):
+    """Random-init ensemble of the reference architecture (MOBODYModule's own initialiser) behind the product API.
+    The GPU arm never touches oracle/: that package is test infrastructure (CPU-baseline legs only)."""
+    torch.manual_seed(seed)
+    model = mb.MOBODYModule(s_dim, a_dim, 256, 7, 5, device=dev, config={"mopo": 0, "latent_reward": 0})
+    with torch.no_grad():
+        for name, prm in model.named_parameters():
+            if name.endswith(".bias"):
+                prm.normal_(0.0, 0.1)                 # biases randomised so they matter (the reference zero-initialises them)
+    return mb.MOBODYEnsembleDynamics({"encoder_loss_coef": 1, "domain_loss_coef": 0, "cycle_loss_coef": 0}, model, None, None,
+                                     mb.get_termination_fn(TASK), penalty_coef=COEF, precision=precision)
+
+
+def build_agent(mb, s_dim, a_dim, dev, seed=1, **overrides):
+    torch.manual_seed(seed + 100)
+    cfg = dict(AGENT_CFG, state_dim=s_dim, action_dim=a_dim); cfg.update(overrides)
+    return mb.MOBODY(cfg, dev)
+
+
 def cpu_rollout_rate(n_rows, threads, repeats=1):
     """Oracle (CPU restatement of MOBODY.rollout, proven equal to the reference) on host cores."""
     from oracle import mobody_oracle as M
@@ -169,9 +194,8 @@ def cpu_train_rate(batch, threads, steps=5):
 
 def gpu_train_rate(mb, dev, batch, steps=300, s_dim=None, a_dim=None):
     """MOBODY.train steady state through the public API: device-resident buffers, Philox indices, fused step."""
-    from helpers import cuda_agent
     s_dim, a_dim = s_dim or S, a_dim or A
-    ag, _ = cuda_agent(s_dim, a_dim, 2, penalty_type="none")
+    ag = build_agent(mb, s_dim, a_dim, dev, seed=2)
     src, tar = mb.ReplayBuffer(s_dim, a_dim, dev), mb.ReplayBuffer(s_dim, a_dim, dev)
     src.convert_D4RL(synth_buffer_dict(200_000, 1, s_dim, a_dim)); tar.convert_D4RL(synth_buffer_dict(20_000, 2, s_dim, a_dim))
     ag.fake_replay_buffer.convert_D4RL(synth_buffer_dict(50_000, 3, s_dim, a_dim))
@@ -238,11 +262,10 @@ def main():
         dist.barrier()
     import mobody_b200 as mb
     from mobody_b200 import _ffi
-    from helpers import cuda_agent, cuda_dynamics
     enabled = list(getattr(_ffi, "ENABLED_PRECISIONS", ("fp32",)))
     prec = args.precision if args.precision != "auto" else ("bf16x2" if "bf16x2" in enabled else "fp32")
-    dyn, _ = cuda_dynamics(S, A, 1, ENV, COEF, precision=prec)
-    ag, _ = cuda_agent(S, A, 1, env_filter=ENV_FILTER)
+    dyn = build_dynamics(mb, S, A, prec, dev)
+    ag = build_agent(mb, S, A, dev)
     ag.dynamics = dyn
     Bn = args.rows
     obs_host = torch.from_numpy(synth_obs(Bn, 100 + rank)).pin_memory()
@@ -335,7 +358,7 @@ def main():
     for lp in ("fp16", "bf16"):
         if lp == prec or lp not in enabled:
             continue
-        dyn_l, _ = cuda_dynamics(S, A, 1, ENV, COEF, precision=lp)
+        dyn_l = build_dynamics(mb, S, A, lp, dev)
         lt = []
         for it in range(W + args.steps):
             flush.zero_()
@@ -374,8 +397,9 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"fp32": "f32", "bf16x2": "bf16x2 (hi+lo split, fp32-parity)", "bf16": "bf16", "fp16": "f16"}[prec], "data": "synthetic",
-        "config": {"workload": f"halfcheetah-gravity S{S}/A{A} rollout_length={T}, {Bn} start states per GPU (BASELINE configs[1])",
-                   "ensemble": 7, "hidden": 256, "precision": prec, "l2": "flushed between timed iterations (256 MiB memset, inside the timed region)",
+        "config": {"workload": f"halfcheetah-gravity S{S}/A{A} rollout_length={T}, {Bn} start states per GPU, 7-member ensemble, hidden 256 "
+                               f"(BASELINE configs[1])",
+                   "precision": prec, "l2": "flushed between timed iterations (256 MiB memset, inside the timed region)",
                    "parallelism": f"dp{world} (start states sharded; NCCL all-gather of transitions)" if world > 1 else "single GPU"},
         "e2e": {"value": e2e_trans / e2e_s, "unit": UNIT, "h2d_bytes_per_step": Bn * S * 4, "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": args.steps * (T + (T - 1) * 4 + 1 + 3 + 2),   # per rollout: init, T steps, (T-1) x (3 compact + advance), 3 compact, pack, stats
