@@ -214,6 +214,35 @@ def gpu_train_rate(mb, dev, batch, steps=300, s_dim=None, a_dim=None):
     return steps / (e0.elapsed_time(e1) * 1e-3), steps / wall
 
 
+def hbm_stage_rates(mb, dev, hbm_peak, n=2_000_000):
+    """Achieved HBM GB/s of the byte-moving stages of the path at a size well beyond L2 (2 M rows x 176 B): replay-buffer
+    sampling (Philox draw + random row gather), ring insert, and the row packing of convert_D4RL / add_batch."""
+    from mobody_b200 import _ffi
+    buf = mb.ReplayBuffer(S, A, dev, max_size=n)
+    buf.size = n
+    RW, lib, st = buf.RW, _ffi.lib(), _ffi.stream_ptr(dev)
+    out = torch.empty(n, RW, dtype=torch.float32, device=dev)
+    cols = [torch.randn(n, w, device=dev) for w in (S, A, S)] + [torch.randn(n, device=dev), torch.zeros(n, device=dev)]
+
+    def timed(fn, reps=5):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e-3
+    row_bytes = RW * 4
+    res = {}
+    t = timed(lambda: buf.sample_rows(n, out=out))
+    res["sample_rows (Philox draw + random gather)"] = (n * (2 * row_bytes + 16)) / t / 1e9      # rows read + written, int64 index written + read
+    t = timed(lambda: buf.add_packed(out, n))
+    res["ring_insert"] = (n * 2 * row_bytes) / t / 1e9
+    t = timed(lambda: _ffi.check(lib.mobody_pack_rows(*[_ffi.ptr(c) for c in cols], n, S, A, 1, _ffi.ptr(out), st)))
+    res["pack_rows"] = (n * ((2 * S + A + 2) * 4 + row_bytes)) / t / 1e9
+    return {k: {"GB/s": round(v, 1), "frac_of_hbm_peak": round(v / hbm_peak, 3)} for k, v in res.items()}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -417,6 +446,8 @@ def main():
             "kernel_ms": ms, "achieved": la, "frac": la / peak, "transitions_per_s": Bn / (ms * 1e-3),
             "tolerance": {"fp16": "5e-3 relative (the stated looser bound of north_star for reduced-precision GEMMs; measured <= 4.6e-3)",
                           "bf16": "2e-2 relative (measured <= 1.6e-2)"}[lp]}
+    if not args.no_train:
+        line["hbm_stages"] = hbm_stage_rates(mb, dev, pk["hbm_gbs"])
     if upd_wall is not None:
         line["train"] = {"metric": "Q-weighted BC updates/sec", "value": upd_wall, "unit": "updates/s", "device_only": upd_dev,
                          "config": {"workload": f"MOBODY.train steady state, batch 128 (128 src + 128 tar + 64 fake rows), S{S}/A{A}",

@@ -53,17 +53,24 @@ __global__ void sample_rows_kernel(SampleJobs j, int rw4) {
 __global__ void pack_rows_kernel(const float* __restrict__ s, const float* __restrict__ a, const float* __restrict__ ns,
                                  const float* __restrict__ r, const float* __restrict__ d, long long n, int S, int A,
                                  int rw, int done_is_terminal, float* __restrict__ out) {
+  const int rw4 = rw >> 2;                                  // one thread per 16-byte group of an output row (128-bit stores)
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = n * rw;
+  const long long total = n * rw4;
   for (; t < total; t += (long long)gridDim.x * blockDim.x) {
-    long long i = t / rw; int c = (int)(t - i * rw);
-    float v = 0.f;
-    if (c < S) v = s[i * S + c];
-    else if (c < S + A) v = a[i * A + (c - S)];
-    else if (c < 2 * S + A) v = ns[i * S + (c - S - A)];
-    else if (c == 2 * S + A) v = r[i];
-    else if (c == 2 * S + A + 1) v = done_is_terminal ? 1.0f - d[i] : d[i];
-    out[t] = v;
+    const long long i = t / rw4; const int c0 = (int)(t - i * rw4) * 4;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c0 + j;
+      float x = 0.f;
+      if (c < S) x = __ldg(s + i * S + c);
+      else if (c < S + A) x = __ldg(a + i * A + (c - S));
+      else if (c < 2 * S + A) x = __ldg(ns + i * S + (c - S - A));
+      else if (c == 2 * S + A) x = __ldg(r + i);
+      else if (c == 2 * S + A + 1) x = done_is_terminal ? 1.0f - __ldg(d + i) : __ldg(d + i);
+      v[j] = x;
+    }
+    reinterpret_cast<float4*>(out)[t] = make_float4(v[0], v[1], v[2], v[3]);
   }
 }
 
@@ -299,7 +306,7 @@ void mb_philox_indices_launch(int64_t* idx, long long n, unsigned long long seed
 void mb_pack_rows_launch(const float* s, const float* a, const float* ns, const float* r, const float* d, long long n,
                          int S, int A, int rw, int done_is_terminal, float* out, cudaStream_t st) {
   if (n <= 0) return;
-  buf::pack_rows_kernel<<<grid_for(n * rw, buf::NT), buf::NT, 0, st>>>(s, a, ns, r, d, n, S, A, rw, done_is_terminal, out);
+  buf::pack_rows_kernel<<<grid_for(n * (rw / 4), buf::NT), buf::NT, 0, st>>>(s, a, ns, r, d, n, S, A, rw, done_is_terminal, out);
 }
 void mb_ring_insert_launch(const float* src, long long n_cap, const int* n_dev, int rw, long long ptr, long long cap,
                            float* dst, cudaStream_t st) {
