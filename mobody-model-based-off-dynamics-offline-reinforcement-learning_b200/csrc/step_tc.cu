@@ -17,11 +17,13 @@
 //    place in SMEM.  All groups work on the same 32-column chunk (8 columns per warp), so chunks are
 //    announced in order (one mbarrier per chunk) and the next layer's MMAs trail the epilogue by one chunk:
 //    tensor pipe and epilogue overlap inside a single row tile.
-//  A CTA-pair (cta_group::2) variant of this kernel lives on branch `cta-pair`: correct but slower here
-//  (the chain is latency-, not SMEM-bandwidth-bound); see DESIGN.md.
+//  Siblings: step_duo.cu (two tiles in flight per CTA; the single-pass fp16 / bf16 modes run there) and step_pair.cu
+//  (experimental CTA-pair / cta_group::2 variant: correct, slower — its cross-CTA hand-offs are software); DESIGN.md 4.1.
 //
-// Precision: NS = 1 -> single bf16 pass (bound 2e-2; the fp16 single-pass mode lives in step_duo.cu); NS = 2 -> bf16 hi+lo split of both
-// operands, 3 MMAs per K step (hi*hi + lo*hi + hi*lo), ~2^-16 per product: inside the 1e-4 bound.
+// Precision: NS = 2 -> bf16 hi+lo split of both operands, 3 MMAs per K step (hi*hi + lo*hi + hi*lo), ~2^-16 per
+// product: inside the 1e-4 bound (the default mode).  NS = 1 -> single bf16 pass (bound 2e-2; used when the two-tile
+// kernel does not fit or MOBODY_TC_DUO=0).  Biases come from a shared-memory ring staged by the producer warp; swish
+// layers are packed pre-scaled (tc_layout.h: tc_swish_scales) so the epilogue needs no multiply before the SFU op.
 #include "common.cuh"
 #include "philox.cuh"
 #include "term.cuh"
