@@ -7,7 +7,6 @@ they only own parameters — the hot path hands their device pointers to the CUD
 """
 import copy
 import ctypes as C
-from collections import defaultdict
 
 import numpy as np
 import torch

@@ -1,7 +1,7 @@
 """BASELINE.json configs as concrete synthetic runs: one line of JSON per config with the
 transitions/s of MOBODY.rollout_device (device resident, nothing read back inside the timed loop), rows per step and
 kept fraction.  Single GPU; the sharded configs are run at their per-GPU share."""
-import sys, os, json, time
+import sys, os, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch

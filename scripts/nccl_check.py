@@ -10,7 +10,6 @@ import numpy as np, torch, torch.distributed as dist
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-import mobody_b200 as mb
 from mobody_b200 import parallel as P
 from helpers import cuda_agent, cuda_dynamics
 

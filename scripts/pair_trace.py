@@ -3,7 +3,7 @@
 import sys, os, ctypes
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
-import numpy as np, torch
+import torch
 from helpers import cuda_dynamics, cuda_agent
 from mobody_b200 import _ffi
 from mobody_b200.dynamics import StepWorkspace

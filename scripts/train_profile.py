@@ -2,7 +2,7 @@
 import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
-import numpy as np, torch
+import torch
 import bench
 import mobody_b200 as mb
 from helpers import cuda_agent
