@@ -34,6 +34,8 @@ struct CriticArgs {
   float* Dq[2][2];     // [net][layer] dLoss/d(pre-activation), [N][256]
   float* d3[2];        // [net] dLoss/dq_k, [N]
   float* part;         // [n_tiles][4]: sum (q1-y)^2, sum (q2-y)^2, sum q1, sum q2
+  float* Hp[2];        // relu activations of pi(s), [N][256]      (phase 1 role 3: the actor's forward does not depend on
+  float* api;          // pi(s), [N][A]                             the critic update, so it rides along with it)
 };
 
 struct ActorArgs {
@@ -89,7 +91,8 @@ __device__ __forceinline__ void head_backward(float* __restrict__ X1, const floa
   __syncthreads();
 }
 
-// ---- critic phase 1: role 0 = pi(s') (:190), roles 1, 2 = Q_k(s, a) forward with stored activations (:196) ----
+// ---- critic phase 1: role 0 = pi(s') (:190), roles 1, 2 = Q_k(s, a) forward with stored activations (:196),
+//      role 3 = pi(s) with stored activations for the actor update that follows (:315; same policy parameters) ----
 template <int RPT>
 __global__ void __launch_bounds__(NT, 1) critic_fwd_kernel(CriticArgs a) {
   constexpr int TM = 8 * RPT;
@@ -101,10 +104,18 @@ __global__ void __launch_bounds__(NT, 1) critic_fwd_kernel(CriticArgs a) {
     const int r = i / ldi, j = i - r * ldi;
     const float* x = a.X + (size_t)(row0 + r) * a.rw;
     in_s[i] = role == 0 ? ((r < rows && j < S) ? x[S + A + j] : 0.f)        // [s', 0]
+            : role == 3 ? ((r < rows && j < S) ? x[j] : 0.f)                 // [s, 0]
                         : ((r < rows && j < S + A) ? x[j] : 0.f);            // [s, a, 0]
   }
   __syncthreads();
-  if (role == 0) {
+  if (role == 3) {
+    big_layer_mma<true, RPT>(in_s, ldi, S, a.pi.w[0], a.pi.b[0], X0, ACT_RELU);
+    store_tile<TM>(X0, a.Hp[0], row0, rows);
+    big_layer_mma<true, RPT>(X0, H, H, a.pi.w[1], a.pi.b[1], X1, ACT_RELU);
+    store_tile<TM>(X1, a.Hp[1], row0, rows);
+    small_layer<true, RPT>(X1, H, H, a.pi.w[2], H, a.pi.b[2], A, in_s, ldi, ACT_TANH, a.max_action);
+    for (int i = tid; i < rows * A; i += NT) { const int r = i / A, j = i - r * A; a.api[(size_t)(row0 + r) * A + j] = in_s[r * ldi + j]; }
+  } else if (role == 0) {
     big_layer_mma<true, RPT>(in_s, ldi, S, a.pi.w[0], a.pi.b[0], X0, ACT_RELU);
     big_layer_mma<true, RPT>(X0, H, H, a.pi.w[1], a.pi.b[1], X1, ACT_RELU);
     small_layer<true, RPT>(X1, H, H, a.pi.w[2], H, a.pi.b[2], A, in_s, ldi, ACT_TANH, a.max_action);
@@ -186,37 +197,8 @@ __global__ void __launch_bounds__(NT, 1) critic_bwd_kernel(CriticArgs a) {
   if (tid < 2) a.part[blockIdx.x * 4 + 2 * tid + k] = redbuf[tid] + redbuf[2 + tid];     // [0..1] = sq err of Q1, Q2; [2..3] = sum q
 }
 
-// ---- actor phase 1: role 0 = pi(s) with stored activations (:315); roles 1, 2 = q_hat_k = Q_k(s_t, a_t) on true rows (:249-251) ----
-template <int RPT>
-__global__ void __launch_bounds__(NT, 1) actor_fwd_kernel(ActorArgs a) {
-  constexpr int TM = 8 * RPT;
-  extern __shared__ __align__(16) float sm[];
-  const int S = a.S, A = a.A, ldi = rup16(S + A);
-  float* X0 = sm; float* X1 = X0 + TM * H; float* in_s = X1 + TM * H; float* qa = in_s + TM * ldi;
-  const int tid = threadIdx.x, row0 = blockIdx.x * TM, rows = min(TM, a.N - row0), role = blockIdx.y;
-  if (role != 0 && row0 >= a.n_true) return;
-  for (int i = tid; i < TM * ldi; i += NT) {
-    const int r = i / ldi, j = i - r * ldi;
-    in_s[i] = (r < rows && j < (role == 0 ? S : S + A)) ? a.X[(size_t)(row0 + r) * a.rw + j] : 0.f;
-  }
-  __syncthreads();
-  if (role == 0) {
-    big_layer_mma<true, RPT>(in_s, ldi, S, a.pi.w[0], a.pi.b[0], X0, ACT_RELU);
-    store_tile<TM>(X0, a.Hp[0], row0, rows);
-    big_layer_mma<true, RPT>(X0, H, H, a.pi.w[1], a.pi.b[1], X1, ACT_RELU);
-    store_tile<TM>(X1, a.Hp[1], row0, rows);
-    small_layer<true, RPT>(X1, H, H, a.pi.w[2], H, a.pi.b[2], A, in_s, ldi, ACT_TANH, a.max_action);
-    for (int i = tid; i < rows * A; i += NT) { const int r = i / A, j = i - r * A; a.api[(size_t)(row0 + r) * A + j] = in_s[r * ldi + j]; }
-  } else {
-    const int k = role - 1;
-    big_layer_mma<true, RPT>(in_s, ldi, S + A, a.q[k].w[0], a.q[k].b[0], X0, ACT_RELU);
-    big_layer_mma<true, RPT>(X0, H, H, a.q[k].w[1], a.q[k].b[1], X1, ACT_RELU);
-    q_head<TM>(X1, a.q[k].w[2], a.q[k].b[2], qa);
-    if (tid < rows && row0 + tid < a.n_true) a.qh[k][row0 + tid] = qa[tid];
-  }
-}
-
-// ---- actor phase 2: role k = Q_k(s, pi(s)) and d Q_k / d action with Q frozen (:316-317, 555-556) ----
+// ---- actor: roles 0, 1 = Q_k(s, pi(s)) and d Q_k / d action with Q frozen (:316-317, 555-556);
+//      roles 2, 3 = q_hat_k = Q_k(s_t, a_t) on the true rows (no grad, :249-251).  pi(s) was computed next to the critic. ----
 template <int RPT>
 __global__ void __launch_bounds__(NT, 1) actor_q_kernel(ActorArgs a) {
   constexpr int TM = 8 * RPT;
@@ -224,18 +206,27 @@ __global__ void __launch_bounds__(NT, 1) actor_q_kernel(ActorArgs a) {
   const int S = a.S, A = a.A, ldi = rup16(S + A);
   float* X0 = sm; float* X1 = X0 + TM * H; float* sap_s = X1 + TM * H;
   float* qa = sap_s + TM * ldi; float* ones = qa + TM; float* gk = ones + TM;      // gk [TM][A]
-  const int tid = threadIdx.x, row0 = blockIdx.x * TM, rows = min(TM, a.N - row0), k = blockIdx.y;
+  const int tid = threadIdx.x, row0 = blockIdx.x * TM, rows = min(TM, a.N - row0), k = blockIdx.y & 1;
+  const bool qhat = blockIdx.y >= 2;
+  if (qhat && row0 >= a.n_true) return;
   for (int i = tid; i < TM * ldi; i += NT) {
     const int r = i / ldi, j = i - r * ldi;
     float v = 0.f;
     if (r < rows) {
-      if (j < S) v = a.X[(size_t)(row0 + r) * a.rw + j];
-      else if (j < S + A) v = a.api[(size_t)(row0 + r) * A + (j - S)];
+      if (j < S || (qhat && j < S + A)) v = a.X[(size_t)(row0 + r) * a.rw + j];          // [s, a_t] for q_hat
+      else if (j < S + A) v = a.api[(size_t)(row0 + r) * A + (j - S)];                    // [s, pi(s)]
     }
     sap_s[i] = v;
   }
   if (tid < TM) ones[tid] = 1.0f;
   __syncthreads();
+  if (qhat) {
+    big_layer_mma<true, RPT>(sap_s, ldi, S + A, a.q[k].w[0], a.q[k].b[0], X0, ACT_RELU);
+    big_layer_mma<true, RPT>(X0, H, H, a.q[k].w[1], a.q[k].b[1], X1, ACT_RELU);
+    q_head<TM>(X1, a.q[k].w[2], a.q[k].b[2], qa);
+    if (tid < rows && row0 + tid < a.n_true) a.qh[k][row0 + tid] = qa[tid];
+    return;
+  }
   big_layer_mma<true, RPT>(sap_s, ldi, S + A, a.q[k].w[0], a.q[k].b[0], X0, ACT_RELU);
   big_layer_mma<true, RPT>(X0, H, H, a.q[k].w[1], a.q[k].b[1], X1, ACT_RELU);
   q_head<TM>(X1, a.q[k].w[2], a.q[k].b[2], qa);
@@ -606,7 +597,7 @@ const char* mb_train_critic_launch(const trn::CriticArgs& a, cudaStream_t st) {
   if (const char* e = set_smem(k1, bytes)) return e;
   if (const char* e = set_smem(k2, bytes)) return e;
   if (const char* e = set_smem(k3, bytes)) return e;
-  k1<<<dim3(ntiles, 3), simt::NT, bytes, st>>>(a);
+  k1<<<dim3(ntiles, 4), simt::NT, bytes, st>>>(a);
   k2<<<dim3(ntiles, 2), simt::NT, bytes, st>>>(a);
   k3<<<dim3(ntiles, 2), simt::NT, bytes, st>>>(a);
   return nullptr;
@@ -614,12 +605,9 @@ const char* mb_train_critic_launch(const trn::CriticArgs& a, cudaStream_t st) {
 const char* mb_train_actor_launch(const trn::ActorArgs& a, cudaStream_t st) {
   const int tm = pick_tm(a.N), ntiles = (a.N + tm - 1) / tm;
   const size_t bytes = (2 * (size_t)tm * simt::H + (size_t)tm * simt::rup16(a.S + a.A) + 2 * tm + (size_t)tm * a.A + 8) * sizeof(float);
-  auto k1 = tm == 64 ? trn::actor_fwd_kernel<8> : trn::actor_fwd_kernel<2>;
   auto k2 = tm == 64 ? trn::actor_q_kernel<8> : trn::actor_q_kernel<2>;
-  if (const char* e = set_smem(k1, bytes)) return e;
   if (const char* e = set_smem(k2, bytes)) return e;
-  k1<<<dim3(ntiles, 3), simt::NT, bytes, st>>>(a);
-  k2<<<dim3(ntiles, 2), simt::NT, bytes, st>>>(a);
+  k2<<<dim3(ntiles, 4), simt::NT, bytes, st>>>(a);
   return nullptr;
 }
 const char* mb_train_actor_scalars_launch(const trn::ActorScalarArgs& a, cudaStream_t st) {
@@ -703,6 +691,7 @@ const char* mb_train_step_launch(const mobody_train_desc& d, cudaStream_t st) {
     c.d3[k] = ws + w.d3[k];
   }
   c.gamma = d.gamma; c.max_action = d.max_action; c.part = ws + w.part; c.a2 = ws + w.a2;
+  c.Hp[0] = ws + w.Hp[0]; c.Hp[1] = ws + w.Hp[1]; c.api = ws + w.api;
   for (int k = 0; k < 2; ++k) { c.qk[k] = ws + w.qk[k]; c.qtk[k] = ws + w.qtk[k]; }
   if (const char* e = mb_train_critic_launch(c, st)) return e;
   // ---- critic weight gradients + Adam + Polyak ----
