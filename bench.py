@@ -138,6 +138,17 @@ def build_agent(mb, s_dim, a_dim, dev, seed=1, **overrides):
     return mb.MOBODY(cfg, dev)
 
 
+def cpu_model():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cpu_rollout_rate(n_rows, threads, repeats=1):
     """Oracle (CPU restatement of MOBODY.rollout, proven equal to the reference) on host cores."""
     from oracle import mobody_oracle as M
@@ -467,9 +478,13 @@ def main():
                                              "sample": "oracle.train_step incl. 3 buffer gathers, 5 steps after 2 warm-up"}
         n = min(Bn, 100_000)                   # the whole workload (~1.3 s per pass on 16 cores), best of 3 after a warm-up
         rate, dt = cpu_rollout_rate(n, cores, repeats=3)
+        rate1, _ = cpu_rollout_rate(10_000, 1, repeats=1)      # the reference pins torch to ONE thread (train_mobody.py:3-5, 50-51)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"oracle.rollout (CPU restatement of MOBODY.rollout) on {n} of {Bn} start states, "
-                                          f"best of 3 after 1 warm-up, torch threads={cores}"}
+                                          f"best of 3 after 1 warm-up, torch threads={cores}",
+                                "single_thread": {"value": rate1, "unit": UNIT, "cores": 1,
+                                                  "sample": "same, 10000 start states, torch threads=1 (the reference's own setting)"},
+                                "cpu_model": cpu_model()}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
