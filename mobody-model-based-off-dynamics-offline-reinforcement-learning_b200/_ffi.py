@@ -9,7 +9,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmobody_b200.so")
+# MOBODY_B200_LIB selects another build of the same library (kernel A/B experiments, scripts/build_variant.py)
+LIB_PATH = os.environ.get("MOBODY_B200_LIB") or os.path.join(_HERE, "libmobody_b200.so")
 
 N_DYN_LAYERS = 13
 DYN_LAYER_NAMES = ("zs1", "zs2", "zs3", "za_src1", "za_src2", "za_trg1", "za_trg2",

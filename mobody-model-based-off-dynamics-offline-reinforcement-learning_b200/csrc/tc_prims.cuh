@@ -179,17 +179,24 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-// ---------------- bf16 split helpers (integer pipe only: no F2FP / XU traffic) ----------------
+// ---------------- bf16 split helpers ----------------
 // hi = top 16 bits of v (truncation; exact, so v - hi is exact in fp32 and has the sign of v),
-// lo = bf16(v - hi) rounded half-away.  hi+lo carries ~16 significand bits of v (error <= 2^-16 |v|);
+// lo = bf16(v - hi) rounded to nearest (one F2FP for two values; MOBODY_LO_F2FP=0: integer add + byte permute, half-away).  hi+lo carries ~16 significand bits of v (error <= 2^-16 |v|);
 // the rounding of lo is unbiased, the truncation of hi is fully compensated by lo.
 // Packing two values into one 32-bit word is a byte permute (low half = first value).
+#ifndef MOBODY_LO_F2FP
+#define MOBODY_LO_F2FP 1   // 1: pack the lo plane with one F2FP (cvt.rn.bf16x2.f32) instead of two adds + a byte permute
+#endif
 __device__ __forceinline__ void split2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
   const uint32_t u0 = __float_as_uint(v0), u1 = __float_as_uint(v1);
   hi = __byte_perm(u0, u1, 0x7632);
+#if MOBODY_LO_F2FP
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(v1 - __uint_as_float(u1 & 0xFFFF0000u)), "f"(v0 - __uint_as_float(u0 & 0xFFFF0000u)));
+#else
   const uint32_t l0 = __float_as_uint(v0 - __uint_as_float(u0 & 0xFFFF0000u)) + 0x8000u;
   const uint32_t l1 = __float_as_uint(v1 - __uint_as_float(u1 & 0xFFFF0000u)) + 0x8000u;
   lo = __byte_perm(l0, l1, 0x7632);
+#endif
 }
 __device__ __forceinline__ uint32_t pack_bf16(float v0, float v1) {
   return __byte_perm(__float_as_uint(v0) + 0x8000u, __float_as_uint(v1) + 0x8000u, 0x7632);

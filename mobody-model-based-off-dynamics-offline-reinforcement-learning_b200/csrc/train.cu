@@ -357,52 +357,207 @@ __global__ void __launch_bounds__(NT, 1) policy_bwd_kernel(PolicyBwdArgs a) {
 }
 
 // ---------------- weight gradients: dW[o][i] = sum_r D[r][o] X[r][i], db[o] = sum_r D[r][o] ----------------
+// One launch covers every Linear of a phase (job = layer of a network), row range split `nsplit` ways; the partial sums
+// of the splits are added in a fixed order by adam_kernel, so the result does not depend on the schedule.
+// Layers with O a multiple of 128 (the 256-wide ones: > 99 % of the work) run on warp-level 3xTF32 tensor-core MMA
+// (wgrad_mma_tile); the one- / A-output heads run on the FMA pipe (wgrad_narrow_tile).
 struct WgradJob { const float* D; int ldD; const float* X; int ldX; float* dW; float* db; int O, I; };
 struct WgradArgs { WgradJob job[6]; int njobs, N, nsplit; };
-constexpr int WT_O = 64, WT_I = 64, WT_R = 32;
-__global__ void __launch_bounds__(256) wgrad_kernel(WgradArgs a) {
-  const WgradJob jb = a.job[blockIdx.z];
-  const int tiles_i = (jb.I + WT_I - 1) / WT_I, tiles_o = (jb.O + WT_O - 1) / WT_O;
-  if ((int)blockIdx.x >= tiles_i * tiles_o) return;
-  const int o0 = (blockIdx.x / tiles_i) * WT_O, i0 = (blockIdx.x % tiles_i) * WT_I;
-  const int split = blockIdx.y;
-  const int rbeg = (int)((long long)a.N * split / a.nsplit), rend = (int)((long long)a.N * (split + 1) / a.nsplit);
-  __shared__ float Ds[WT_R][WT_O + 1], Xs[WT_R][WT_I + 1];
-  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;     // 16 x 16 threads, 4 x 4 outputs each
-  float acc[4][4] = {}, bacc[4] = {};
-  for (int r0 = rbeg; r0 < rend; r0 += WT_R) {
-    for (int t = tid; t < WT_R * WT_O; t += 256) {
-      int rr = t / WT_O, c = t - rr * WT_O;
-      Ds[rr][c] = (r0 + rr < rend && o0 + c < jb.O) ? jb.D[(size_t)(r0 + rr) * jb.ldD + o0 + c] : 0.f;
+constexpr int WM_O = 128, WM_I = 64, WM_R = 32, WM_PD = WM_O + 8, WM_PX = WM_I + 8;   // pitches = 8 mod 32 words: conflict-free fragments
+constexpr size_t WGRAD_SMEM = (size_t)2 * 2 * WM_R * (WM_PD + WM_PX) * sizeof(uint32_t);   // two stages of {hi, lo} x {D, X} planes (106 496 B)
+__host__ __device__ inline bool wgrad_use_mma(int O) { return O % WM_O == 0; }
+__host__ __device__ inline int wgrad_tiles(int O, int I) {
+  return wgrad_use_mma(O) ? (O / WM_O) * ((I + WM_I - 1) / WM_I) : ((O + 7) / 8) * ((I + 255) / 256);
+}
+
+// Heads with few outputs (the Q head: O = 1, the policy head: O = A, the classifier head: O = 2): a tile is 8 outputs x
+// 256 input columns; the eight warps take the rows of the split round-robin (a lane owns 2 x 4 columns: coalesced 128-bit
+// loads of X, broadcast loads of D) and their partial sums are added through shared memory in warp order.
+constexpr int WN_O = 8, WN_I = 256;
+static_assert(WGRAD_SMEM >= (size_t)(8 * WN_O * WN_I + 8 * WN_O) * sizeof(float), "narrow-head reduction buffer");
+__device__ __forceinline__ void wgrad_narrow_tile(const WgradJob& jb, int tile, int split, int rbeg, int rend, float* red) {
+  const int tiles_i = (jb.I + WN_I - 1) / WN_I;
+  const int o0 = (tile / tiles_i) * WN_O, i0 = (tile % tiles_i) * WN_I;
+  const int no = min(WN_O, jb.O - o0);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int c0 = i0 + 4 * lane, c1 = c0 + 128;
+  const bool v0 = c0 < jb.I, v1 = c1 < jb.I;                  // I and ldX are multiples of 4 (checked at launch)
+  float acc[WN_O][8], bs[WN_O];
+#pragma unroll
+  for (int u = 0; u < WN_O; ++u) {
+    bs[u] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[u][j] = 0.f;
+  }
+#pragma unroll 2
+  for (int r = rbeg + warp; r < rend; r += 8) {
+    const float* x = jb.X + (size_t)r * jb.ldX;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 xa = v0 ? __ldg(reinterpret_cast<const float4*>(x + c0)) : z, xb = v1 ? __ldg(reinterpret_cast<const float4*>(x + c1)) : z;
+    const float* d = jb.D + (size_t)r * jb.ldD + o0;
+#pragma unroll
+    for (int u = 0; u < WN_O; ++u) {
+      const float dv = u < no ? __ldg(d + u) : 0.f;
+      bs[u] += dv;
+      acc[u][0] = fmaf(dv, xa.x, acc[u][0]); acc[u][1] = fmaf(dv, xa.y, acc[u][1]); acc[u][2] = fmaf(dv, xa.z, acc[u][2]); acc[u][3] = fmaf(dv, xa.w, acc[u][3]);
+      acc[u][4] = fmaf(dv, xb.x, acc[u][4]); acc[u][5] = fmaf(dv, xb.y, acc[u][5]); acc[u][6] = fmaf(dv, xb.z, acc[u][6]); acc[u][7] = fmaf(dv, xb.w, acc[u][7]);
     }
-    for (int t = tid; t < WT_R * WT_I; t += 256) {
-      int rr = t / WT_I, c = t - rr * WT_I;
-      Xs[rr][c] = (r0 + rr < rend && i0 + c < jb.I) ? jb.X[(size_t)(r0 + rr) * jb.ldX + i0 + c] : 0.f;
+  }
+  float* redb = red + 8 * WN_O * WN_I;
+#pragma unroll
+  for (int u = 0; u < WN_O; ++u) {
+    float* p = red + (size_t)(warp * WN_O + u) * WN_I + 4 * lane;
+    *reinterpret_cast<float4*>(p) = make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
+    *reinterpret_cast<float4*>(p + 128) = make_float4(acc[u][4], acc[u][5], acc[u][6], acc[u][7]);
+    if (lane == 0) redb[warp * WN_O + u] = bs[u];
+  }
+  __syncthreads();
+  const size_t poff = (size_t)split * jb.O * jb.I;
+  for (int u = 0; u < no; ++u) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += red[(size_t)(w * WN_O + u) * WN_I + tid];
+    if (i0 + tid < jb.I) jb.dW[poff + (size_t)(o0 + u) * jb.I + i0 + tid] = sum;
+  }
+  if (i0 == 0 && tid < no) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += redb[w * WN_O + tid];
+    jb.db[(size_t)split * jb.O + o0 + tid] = sum;
+  }
+}
+
+// 128 (o) x 64 (i) tile of one row split on mma.sync.m16n8k8 TF32 with both operands split hi + lo ("3xTF32":
+// lo*hi + hi*lo + hi*hi, fp32-class accuracy).  D and X are [row][.] in memory, i.e. k-major for both operands: a chunk of
+// 32 rows is loaded with 128-bit loads (next chunk in flight in registers while this one is multiplied), split ONCE
+// while it is staged, and the fragments are read with 64- / 128-bit shared loads through permuted operand slots:
+//   m-slot g, g+8 of a 16-row m-tile = output rows 2g, 2g+1 (one 64-bit load = one register pair of the A fragment).
+// 8 warps = 4 (o) x 2 (i), warp tile 32 x 32 = 2 m-tiles x 4 n-tiles, 24 MMAs per 8 rows.
+__device__ __forceinline__ void wgrad_mma_tile(const WgradJob& jb, int tile, int split, int rbeg, int rend, uint32_t* sm) {
+  constexpr uint32_t STAGE_WORDS = 2 * WM_R * (WM_PD + WM_PX);     // one stage = {Dh, Dl, Xh, Xl}; two stages alternate
+  const int tiles_i = (jb.I + WM_I - 1) / WM_I;
+  const int o0 = (tile / tiles_i) * WM_O, i0 = (tile % tiles_i) * WM_I;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int wo = (warp >> 1) * 32, wi = (warp & 1) * 32;
+  const int dc4 = tid & 31, dr = tid >> 5;          // D staging: columns 4 dc4 .. +3, rows dr + 8 j (j < 4)
+  const int xc4 = tid & 15, xr = tid >> 4;          // X staging: columns 4 xc4 .. +3, rows xr + 16 j (j < 2)
+  const bool xcol_ok = i0 + 4 * xc4 < ((jb.I + 3) & ~3);     // a row of X is readable up to roundup4(I) (<= ldX)
+  float4 pd[4], px[2];
+  auto fetch = [&](int r0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = r0 + dr + 8 * j;
+      pd[j] = r < rend ? __ldg(reinterpret_cast<const float4*>(jb.D + (size_t)r * jb.ldD + o0 + 4 * dc4)) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    __syncthreads();
-#pragma unroll 4
-    for (int rr = 0; rr < WT_R; ++rr) {
-      float d[4], x[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { d[u] = Ds[rr][ty * 4 + u]; x[u] = Xs[rr][tx * 4 + u]; }
+    for (int j = 0; j < 2; ++j) {
+      const int r = r0 + xr + 16 * j;
+      px[j] = (r < rend && xcol_ok) ? __ldg(reinterpret_cast<const float4*>(jb.X + (size_t)r * jb.ldX + i0 + 4 * xc4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto stage = [&](const float4& v, uint32_t* hp, uint32_t* lp) {
+    uint4 h, l;
+    simt::split_tf32(v.x, h.x, l.x); simt::split_tf32(v.y, h.y, l.y); simt::split_tf32(v.z, h.z, l.z); simt::split_tf32(v.w, h.w, l.w);
+    *reinterpret_cast<uint4*>(hp) = h; *reinterpret_cast<uint4*>(lp) = l;
+  };
+  float acc[2][4][4], bsum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        bacc[u] += d[u];
+  for (int m = 0; m < 2; ++m)
 #pragma unroll
-        for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(d[u], x[v], acc[u][v]);
+    for (int n = 0; n < 4; ++n)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[m][n][j] = 0.f;
+  auto stage_chunk = [&](uint32_t* base) {          // split the fetched chunk into the hi / lo planes of one stage
+    uint32_t (*Dh)[WM_PD] = reinterpret_cast<uint32_t (*)[WM_PD]>(base);
+    uint32_t (*Dl)[WM_PD] = Dh + WM_R;
+    uint32_t (*Xh)[WM_PX] = reinterpret_cast<uint32_t (*)[WM_PX]>(base + 2 * WM_R * WM_PD);
+    uint32_t (*Xl)[WM_PX] = Xh + WM_R;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      stage(pd[j], &Dh[dr + 8 * j][4 * dc4], &Dl[dr + 8 * j][4 * dc4]);
+      bsum[0] += pd[j].x; bsum[1] += pd[j].y; bsum[2] += pd[j].z; bsum[3] += pd[j].w;
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) stage(px[j], &Xh[xr + 16 * j][4 * xc4], &Xl[xr + 16 * j][4 * xc4]);
+  };
+  // chunk c is multiplied out of stage c & 1 while chunk c + 1 is split into the other stage and chunk c + 2 is in
+  // flight in registers: one barrier per chunk
+  if (rbeg < rend) {
+    fetch(rbeg);
+    stage_chunk(sm);
+    if (rbeg + WM_R < rend) fetch(rbeg + WM_R);
+  }
+  __syncthreads();
+  int cur = 0;
+  for (int r0 = rbeg; r0 < rend; r0 += WM_R, cur ^= 1) {
+    const uint32_t* base = sm + cur * STAGE_WORDS;
+    const uint32_t (*Dh)[WM_PD] = reinterpret_cast<const uint32_t (*)[WM_PD]>(base);
+    const uint32_t (*Dl)[WM_PD] = Dh + WM_R;
+    const uint32_t (*Xh)[WM_PX] = reinterpret_cast<const uint32_t (*)[WM_PX]>(base + 2 * WM_R * WM_PD);
+    const uint32_t (*Xl)[WM_PX] = Xh + WM_R;
+#pragma unroll
+    for (int ks = 0; ks < WM_R / 8; ++ks) {
+      const int k = ks * 8 + t;
+      uint32_t bh[4][2], bl[4][2];                 // scalar loads: (b0, b1) of a tile land in adjacent registers, no moves
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        bh[nt][0] = Xh[k][wi + nt * 8 + g]; bh[nt][1] = Xh[k + 4][wi + nt * 8 + g];
+        bl[nt][0] = Xl[k][wi + nt * 8 + g]; bl[nt][1] = Xl[k + 4][wi + nt * 8 + g];
+      }
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        const int oc = wo + m * 16 + 2 * g;
+        const uint2 h0 = *reinterpret_cast<const uint2*>(&Dh[k][oc]), h1 = *reinterpret_cast<const uint2*>(&Dh[k + 4][oc]);
+        const uint2 l0 = *reinterpret_cast<const uint2*>(&Dl[k][oc]), l1 = *reinterpret_cast<const uint2*>(&Dl[k + 4][oc]);
+        const uint32_t ah[4] = {h0.x, h0.y, h1.x, h1.y}, al[4] = {l0.x, l0.y, l1.x, l1.y};
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          simt::mma_tf32_1688(acc[m][nt], al, bh[nt][0], bh[nt][1]);
+          simt::mma_tf32_1688(acc[m][nt], ah, bl[nt][0], bl[nt][1]);
+          simt::mma_tf32_1688(acc[m][nt], ah, bh[nt][0], bh[nt][1]);
+        }
       }
     }
+    if (r0 + WM_R < rend) {
+      stage_chunk(sm + (cur ^ 1) * STAGE_WORDS);    // last read as the multiplicand of chunk c - 1, before the previous barrier
+      if (r0 + 2 * WM_R < rend) fetch(r0 + 2 * WM_R);
+    }
     __syncthreads();
   }
+  // C fragment: j = 0, 1 -> row 2g, columns 2t, 2t+1 of n-tile nt;  j = 2, 3 -> row 2g+1
   const size_t poff = (size_t)split * jb.O * jb.I;
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int o = o0 + ty * 4 + u;
-    if (o >= jb.O) continue;
+  for (int m = 0; m < 2; ++m)
 #pragma unroll
-    for (int v = 0; v < 4; ++v) { const int i = i0 + tx * 4 + v; if (i < jb.I) jb.dW[poff + (size_t)o * jb.I + i] = acc[u][v]; }
-    if (i0 == 0 && tx == 0) jb.db[(size_t)split * jb.O + o] = bacc[u];
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int o = o0 + wo + m * 16 + 2 * g + (j >> 1), i = i0 + wi + nt * 8 + 2 * t + (j & 1);
+        if (i < jb.I) jb.dW[poff + (size_t)o * jb.I + i] = acc[m][nt][j];
+      }
+  if (i0 == 0) {                                     // bias gradient: column sums of D, eight row classes added in order
+    float* red = reinterpret_cast<float*>(sm);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) red[dr * WM_O + 4 * dc4 + c] = bsum[c];
+    __syncthreads();
+    if (tid < WM_O) {
+      float b = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) b += red[q * WM_O + tid];
+      jb.db[(size_t)split * jb.O + o0 + tid] = b;
+    }
   }
+}
+
+__global__ void __launch_bounds__(256, 2) wgrad_kernel(WgradArgs a) {
+  extern __shared__ __align__(16) uint32_t wg_sm[];
+  const WgradJob jb = a.job[blockIdx.z];
+  if ((int)blockIdx.x >= wgrad_tiles(jb.O, jb.I)) return;
+  const int split = blockIdx.y;
+  const long long chunks = (a.N + WM_R - 1) / WM_R;               // splits are whole 32-row chunks, spread evenly
+  const int rbeg = (int)(chunks * split / a.nsplit) * WM_R, rend = min(a.N, (int)(chunks * (split + 1) / a.nsplit) * WM_R);
+  if (wgrad_use_mma(jb.O)) wgrad_mma_tile(jb, blockIdx.x, split, rbeg, rend, wg_sm);
+  else wgrad_narrow_tile(jb, blockIdx.x, split, rbeg, rend, reinterpret_cast<float*>(wg_sm));
 }
 
 // ---------------- fused Adam (+ Polyak target update) over a table of tensors ----------------
@@ -630,10 +785,14 @@ const char* mb_train_policy_bwd_launch(const trn::PolicyBwdArgs& a, cudaStream_t
 const char* mb_train_wgrad_launch(const trn::WgradArgs& a, cudaStream_t st) {
   int maxt = 1;
   for (int j = 0; j < a.njobs; ++j) {
-    int t = ((a.job[j].O + trn::WT_O - 1) / trn::WT_O) * ((a.job[j].I + trn::WT_I - 1) / trn::WT_I);
+    const trn::WgradJob& jb = a.job[j];
+    if (trn::wgrad_use_mma(jb.O) && ((jb.ldD | jb.ldX) & 3)) return "weight gradient: operand rows must be 16-byte aligned";
+    if (!trn::wgrad_use_mma(jb.O) && (jb.O > 32 || ((jb.I | jb.ldX) & 3))) return "weight gradient: unsupported head shape";
+    const int t = trn::wgrad_tiles(jb.O, jb.I);
     if (t > maxt) maxt = t;
   }
-  trn::wgrad_kernel<<<dim3(maxt, a.nsplit, a.njobs), 256, 0, st>>>(a);
+  if (const char* e = set_smem(trn::wgrad_kernel, trn::WGRAD_SMEM)) return e;
+  trn::wgrad_kernel<<<dim3(maxt, a.nsplit, a.njobs), 256, trn::WGRAD_SMEM, st>>>(a);
   return nullptr;
 }
 const char* mb_train_adam_launch(const trn::AdamArgs& a, cudaStream_t st) {

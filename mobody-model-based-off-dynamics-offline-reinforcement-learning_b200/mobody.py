@@ -69,6 +69,27 @@ class Classifier(nn.Module):                                   # mobody.py:11-33
         self.sas_classifier = MLPNetwork(2 * state_dim + action_dim, 2, hidden_size)
 
 
+
+_SM_COUNT = {}
+
+
+def _wgrad_splits(n_rows, tiles_per_launch, device):
+    """Row splits of the weight-gradient launches.  A launch runs ``tiles * nsplit`` CTAs of 128 x 64 outputs, two per
+    SM, each walking its rows in chunks of 32: pick the split count (<= 64) that minimises rounds x chunks per CTA
+    summed over the launches of an update (tiles: critic 2 x (8 + 2), actor 8 + 2), i.e. avoid a nearly empty last
+    round.  Any value gives the same result up to fp32 summation order; the order is fixed for a given value."""
+    key = str(device)
+    if key not in _SM_COUNT:
+        _SM_COUNT[key] = torch.cuda.get_device_properties(device).multi_processor_count
+    slots, chunks = 2 * _SM_COUNT[key], (n_rows + 31) // 32
+    best, best_cost = 1, None
+    for n in range(1, min(64, chunks) + 1):
+        per = (chunks + n - 1) // n
+        cost = sum(((t * n + slots - 1) // slots) for t in tiles_per_launch) * per
+        if best_cost is None or cost < best_cost:
+            best, best_cost = n, cost
+    return best
+
 class MOBODY(object):
     def __init__(self, config, device, target_entropy=None):   # mobody.py:91-135
         self.config, self.device = config, torch.device(device)
@@ -288,7 +309,7 @@ class MOBODY(object):
         cfg = self.config
         S, A = cfg["state_dim"], cfg["action_dim"]
         N = rows.shape[0]
-        nsplit = max(1, min(16, (N + 63) // 64))
+        nsplit = _wgrad_splits(N, (20,), self.device)
         lib = _ffi.lib()
         need = int(lib.mobody_classifier_workspace_bytes(N, S, A, nsplit))
         if self._cls_ws is None or self._cls_ws.numel() < need:
@@ -355,7 +376,7 @@ class MOBODY(object):
             raise NotImplementedError("mobody_b200 implements the default advantage=0, scale_Q=1, q_weighted=1 update")
         S, A = cfg["state_dim"], cfg["action_dim"]
         N = rows.shape[0]
-        nsplit = max(1, min(16, (N + 63) // 64))    # row splits of the weight-gradient GEMMs (partials summed in Adam, fixed order)
+        nsplit = _wgrad_splits(N, (20, 10), self.device)   # row splits of the weight-gradient GEMMs (partials summed in Adam, fixed order)
         lib = _ffi.lib()
         need = int(lib.mobody_train_workspace_bytes(N, S, A, nsplit))
         if self._train_ws is None or self._train_ws.numel() < need:
