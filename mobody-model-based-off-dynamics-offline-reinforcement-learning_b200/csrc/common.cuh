@@ -48,6 +48,33 @@ struct StepArgs {
   float* mean;             // [E,B,S] (info['samples']); always written
 };
 
+// ---- programmatic dependent launch (PDL): the launch-bound kernel chains (train step, small rollouts) let the next
+// kernel's CTAs become resident while this one drains.  Every kernel of a chain calls mb_pdl_begin() first:
+// launch_dependents = "the next grid may start launching", wait = "block until every grid this one depends on has
+// completed and its writes are visible" -- so no kernel touches global memory before its predecessors are done.
+__device__ __forceinline__ void mb_pdl_begin() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#ifdef __CUDACC__
+#include <cstdlib>
+#include <utility>
+inline bool mb_pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("MOBODY_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t mb_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = mb_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+#endif
+
 __device__ __forceinline__ float mb_swish(float x) {
   // x * sigmoid(x); ex2.approx + rcp.approx are ~1-2 ulp, far inside the 1e-4 parity bound
   return __fdividef(x, 1.0f + __expf(-x));

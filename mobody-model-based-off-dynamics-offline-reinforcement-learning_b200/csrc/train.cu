@@ -95,6 +95,7 @@ __device__ __forceinline__ void head_backward(float* __restrict__ X1, const floa
 //      role 3 = pi(s) with stored activations for the actor update that follows (:315; same policy parameters) ----
 template <int RPT>
 __global__ void __launch_bounds__(NT, 1) critic_fwd_kernel(CriticArgs a) {
+  mb_pdl_begin();
   constexpr int TM = 8 * RPT;
   extern __shared__ __align__(16) float sm[];
   const int S = a.S, A = a.A, ldi = rup16(S + A);
@@ -134,6 +135,7 @@ __global__ void __launch_bounds__(NT, 1) critic_fwd_kernel(CriticArgs a) {
 // ---- critic phase 2: role k = Q'_k(s', pi(s')) (no grad, :191-193) ----
 template <int RPT>
 __global__ void __launch_bounds__(NT, 1) critic_tgt_kernel(CriticArgs a) {
+  mb_pdl_begin();
   constexpr int TM = 8 * RPT;
   extern __shared__ __align__(16) float sm[];
   const int S = a.S, A = a.A, ldi = rup16(S + A);
@@ -158,6 +160,7 @@ __global__ void __launch_bounds__(NT, 1) critic_tgt_kernel(CriticArgs a) {
 // ---- critic phase 3: role k = TD target, mse gradient of Q_k and backward to the pre-activations (:194-207) ----
 template <int RPT>
 __global__ void __launch_bounds__(NT, 1) critic_bwd_kernel(CriticArgs a) {
+  mb_pdl_begin();
   constexpr int TM = 8 * RPT;
   extern __shared__ __align__(16) float sm[];
   const int S = a.S, A = a.A;
@@ -201,6 +204,7 @@ __global__ void __launch_bounds__(NT, 1) critic_bwd_kernel(CriticArgs a) {
 //      roles 2, 3 = q_hat_k = Q_k(s_t, a_t) on the true rows (no grad, :249-251).  pi(s) was computed next to the critic. ----
 template <int RPT>
 __global__ void __launch_bounds__(NT, 1) actor_q_kernel(ActorArgs a) {
+  mb_pdl_begin();
   constexpr int TM = 8 * RPT;
   extern __shared__ __align__(16) float sm[];
   const int S = a.S, A = a.A, ldi = rup16(S + A);
@@ -280,6 +284,7 @@ __device__ float block_minmax(float v, float* sh, bool is_max) {
   return sh[32];
 }
 __global__ void __launch_bounds__(1024) actor_scalar_kernel(ActorScalarArgs a) {
+  mb_pdl_begin();
   __shared__ float sh[33];
   float s_abs = 0.f, s_q = 0.f;
   for (int i = threadIdx.x; i < a.N; i += blockDim.x) { float q = fminf(a.qv[0][i], a.qv[1][i]); s_abs += fabsf(q); s_q += q; }
@@ -317,6 +322,7 @@ struct ActorGradArgs {
   int N, n_true, S, A, rw; float bc_coef, max_action; float* d3p;
 };
 __global__ void actor_grad_kernel(ActorGradArgs a) {
+  mb_pdl_begin();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.N * a.A) return;
   const int r = i / a.A, j = i - r * a.A;
@@ -337,6 +343,7 @@ __global__ void actor_grad_kernel(ActorGradArgs a) {
 struct PolicyBwdArgs { const float* d3p; int N, A; MlpPtrs pi; const float* Hp[2]; float* Dp[2]; };
 template <int RPT>
 __global__ void __launch_bounds__(NT, 1) policy_bwd_kernel(PolicyBwdArgs a) {
+  mb_pdl_begin();
   constexpr int TM = 8 * RPT;
   extern __shared__ __align__(16) float sm[];
   float* X0 = sm; float* X1 = X0 + TM * H; float* Wst = X1 + TM * H;
@@ -550,6 +557,7 @@ __device__ __forceinline__ void wgrad_mma_tile(const WgradJob& jb, int tile, int
 }
 
 __global__ void __launch_bounds__(256, 2) wgrad_kernel(WgradArgs a) {
+  mb_pdl_begin();
   extern __shared__ __align__(16) uint32_t wg_sm[];
   const WgradJob jb = a.job[blockIdx.z];
   if ((int)blockIdx.x >= wgrad_tiles(jb.O, jb.I)) return;
@@ -564,10 +572,17 @@ __global__ void __launch_bounds__(256, 2) wgrad_kernel(WgradArgs a) {
 struct AdamJob { float* p; const float* g; float* m; float* v; float* tgt; int n; };
 struct AdamArgs { AdamJob job[12]; int njobs, nsplit; float lr_over_bc1, inv_sqrt_bc2, b1, b2, eps, tau; };
 __global__ void adam_kernel(AdamArgs a) {
+  mb_pdl_begin();
   const AdamJob jb = a.job[blockIdx.y];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < jb.n; i += gridDim.x * blockDim.x) {
-    float g = 0.f;
-    for (int s = 0; s < a.nsplit; ++s) g += jb.g[(size_t)s * jb.n + i];      // fixed order over the row splits
+    float g = 0.f;                                                          // fixed order over the row splits;
+    int s = 0;                                                              // loads batched four at a time (L2 latency)
+    for (; s + 4 <= a.nsplit; s += 4) {
+      const float g0 = jb.g[(size_t)s * jb.n + i], g1 = jb.g[(size_t)(s + 1) * jb.n + i];
+      const float g2 = jb.g[(size_t)(s + 2) * jb.n + i], g3 = jb.g[(size_t)(s + 3) * jb.n + i];
+      g += g0; g += g1; g += g2; g += g3;
+    }
+    for (; s < a.nsplit; ++s) g += jb.g[(size_t)s * jb.n + i];
     const float m = a.b1 * jb.m[i] + (1.0f - a.b1) * g;
     const float v = a.b2 * jb.v[i] + (1.0f - a.b2) * g * g;
     jb.m[i] = m; jb.v[i] = v;
@@ -602,6 +617,7 @@ __device__ __forceinline__ void softmax2(float z0, float z1, float& p0, float& p
 
 template <int RPT>
 __global__ void __launch_bounds__(NT, 1) classifier_kernel(ClsArgs a) {
+  mb_pdl_begin();
   constexpr int TM = 8 * RPT;
   extern __shared__ __align__(16) float sm[];
   const int S = a.S, A = a.A;
@@ -681,6 +697,7 @@ __global__ void __launch_bounds__(NT, 1) classifier_kernel(ClsArgs a) {
 }
 
 __global__ void cls_scalar_kernel(const float* __restrict__ part, int ntiles, int N, float* __restrict__ out) {
+  mb_pdl_begin();
   if (threadIdx.x < 2) {
     float s = 0.f;
     for (int t = 0; t < ntiles; ++t) s += part[t * 2 + threadIdx.x];
@@ -691,6 +708,7 @@ __global__ void cls_scalar_kernel(const float* __restrict__ part, int ntiles, in
 // reward relabel (mobody.py:364-378): rows[i].reward += coef * clamp(log-ratio of the twice-softmaxed outputs, -10, 10)
 struct RelabelArgs { float* X; long long n; int S, A, rw; MlpPtrs net[2]; float coef; float* pen_out; };
 __global__ void __launch_bounds__(NT, 1) dara_relabel_kernel(RelabelArgs a) {
+  mb_pdl_begin();
   constexpr int RPT = 8, TM = 64;
   extern __shared__ __align__(16) float sm[];
   const int S = a.S, A = a.A;
@@ -752,9 +770,9 @@ const char* mb_train_critic_launch(const trn::CriticArgs& a, cudaStream_t st) {
   if (const char* e = set_smem(k1, bytes)) return e;
   if (const char* e = set_smem(k2, bytes)) return e;
   if (const char* e = set_smem(k3, bytes)) return e;
-  k1<<<dim3(ntiles, 4), simt::NT, bytes, st>>>(a);
-  k2<<<dim3(ntiles, 2), simt::NT, bytes, st>>>(a);
-  k3<<<dim3(ntiles, 2), simt::NT, bytes, st>>>(a);
+  mb_launch(k1, dim3(ntiles, 4), dim3(simt::NT), bytes, st, a);
+  mb_launch(k2, dim3(ntiles, 2), dim3(simt::NT), bytes, st, a);
+  mb_launch(k3, dim3(ntiles, 2), dim3(simt::NT), bytes, st, a);
   return nullptr;
 }
 const char* mb_train_actor_launch(const trn::ActorArgs& a, cudaStream_t st) {
@@ -762,16 +780,16 @@ const char* mb_train_actor_launch(const trn::ActorArgs& a, cudaStream_t st) {
   const size_t bytes = (2 * (size_t)tm * simt::H + (size_t)tm * simt::rup16(a.S + a.A) + 2 * tm + (size_t)tm * a.A + 8) * sizeof(float);
   auto k2 = tm == 64 ? trn::actor_q_kernel<8> : trn::actor_q_kernel<2>;
   if (const char* e = set_smem(k2, bytes)) return e;
-  k2<<<dim3(ntiles, 4), simt::NT, bytes, st>>>(a);
+  mb_launch(k2, dim3(ntiles, 4), dim3(simt::NT), bytes, st, a);
   return nullptr;
 }
 const char* mb_train_actor_scalars_launch(const trn::ActorScalarArgs& a, cudaStream_t st) {
-  trn::actor_scalar_kernel<<<1, 1024, 0, st>>>(a);
+  mb_launch(trn::actor_scalar_kernel, dim3(1), dim3(1024), 0, st, a);
   return nullptr;
 }
 const char* mb_train_actor_grad_launch(const trn::ActorGradArgs& a, cudaStream_t st) {
   int n = a.N * a.A;
-  trn::actor_grad_kernel<<<(n + 255) / 256, 256, 0, st>>>(a);
+  mb_launch(trn::actor_grad_kernel, dim3((n + 255) / 256), dim3(256), 0, st, a);
   return nullptr;
 }
 const char* mb_train_policy_bwd_launch(const trn::PolicyBwdArgs& a, cudaStream_t st) {
@@ -779,7 +797,7 @@ const char* mb_train_policy_bwd_launch(const trn::PolicyBwdArgs& a, cudaStream_t
   size_t bytes = (2 * (size_t)tm * simt::H + (size_t)tm * simt::rup16(a.A)) * sizeof(float);
   auto kern = tm == 64 ? trn::policy_bwd_kernel<8> : trn::policy_bwd_kernel<2>;
   if (const char* e = set_smem(kern, bytes)) return e;
-  kern<<<(a.N + tm - 1) / tm, simt::NT, bytes, st>>>(a);
+  mb_launch(kern, dim3((a.N + tm - 1) / tm), dim3(simt::NT), bytes, st, a);
   return nullptr;
 }
 const char* mb_train_wgrad_launch(const trn::WgradArgs& a, cudaStream_t st) {
@@ -792,14 +810,14 @@ const char* mb_train_wgrad_launch(const trn::WgradArgs& a, cudaStream_t st) {
     if (t > maxt) maxt = t;
   }
   if (const char* e = set_smem(trn::wgrad_kernel, trn::WGRAD_SMEM)) return e;
-  trn::wgrad_kernel<<<dim3(maxt, a.nsplit, a.njobs), 256, trn::WGRAD_SMEM, st>>>(a);
+  mb_launch(trn::wgrad_kernel, dim3(maxt, a.nsplit, a.njobs), dim3(256), trn::WGRAD_SMEM, st, a);
   return nullptr;
 }
 const char* mb_train_adam_launch(const trn::AdamArgs& a, cudaStream_t st) {
   int maxn = 1;
   for (int j = 0; j < a.njobs; ++j) if (a.job[j].n > maxn) maxn = a.job[j].n;
-  int gx = (maxn + 255) / 256; if (gx > 64) gx = 64;
-  trn::adam_kernel<<<dim3(gx, a.njobs), 256, 0, st>>>(a);
+  int gx = (maxn + 255) / 256; if (gx > 256) gx = 256;
+  mb_launch(trn::adam_kernel, dim3(gx, a.njobs), dim3(256), 0, st, a);
   return nullptr;
 }
 
@@ -953,8 +971,8 @@ const char* mb_classifier_step_launch(const mobody_classifier_desc& d, cudaStrea
   auto kern = tm == 64 ? trn::classifier_kernel<8> : trn::classifier_kernel<2>;
   if (const char* e = set_smem(kern, bytes)) return e;
   const int ntiles = (N + tm - 1) / tm;
-  kern<<<ntiles, simt::NT, bytes, st>>>(c);
-  trn::cls_scalar_kernel<<<1, 32, 0, st>>>(c.part, ntiles, N, ws + w.scal);
+  mb_launch(kern, dim3(ntiles), dim3(simt::NT), bytes, st, c);
+  mb_launch(trn::cls_scalar_kernel, dim3(1), dim3(32), 0, st, (const float*)c.part, ntiles, N, ws + w.scal);
   const int K[2] = {2 * S + A, S + A};
   trn::WgradArgs g{}; g.N = N; g.nsplit = ns; g.njobs = 6;
   for (int k = 0; k < 2; ++k) {
@@ -988,6 +1006,6 @@ const char* mb_dara_relabel_launch(float* rows, long long n, int S, int A, int r
   if (const char* e = set_smem(trn::dara_relabel_kernel, bytes)) return e;
   long long tiles = (n + 63) / 64;
   int grid = (int)(tiles < 148 * 4 ? tiles : 148 * 4);
-  trn::dara_relabel_kernel<<<grid, simt::NT, bytes, st>>>(a);
+  mb_launch(trn::dara_relabel_kernel, dim3(grid), dim3(simt::NT), bytes, st, a);
   return nullptr;
 }
