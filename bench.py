@@ -468,7 +468,7 @@ def main():
     if upd_wall is not None:
         line["train"] = {"metric": "Q-weighted BC updates/sec", "value": upd_wall, "unit": "updates/s", "device_only": upd_dev,
                          "config": {"workload": f"MOBODY.train steady state, batch 128 (128 src + 128 tar + 64 fake rows), S{S}/A{A}",
-                                    "launches_per_update": 12, "dtype": "f32 (3xTF32 tensor-core MMA for the 256-wide layers, fp32 elsewhere)"},
+                                    "launches_per_update": 10, "dtype": "f32 (3xTF32 tensor-core MMA for the 256-wide layers, fp32 elsewhere)"},
                          "batch4096_S27A8": {"value": big_wall, "device_only": big_dev, "unit": "updates/s",
                                              "workload": "MOBODY.train steady state, batch 4096 (4096 src + 4096 tar + 2048 fake rows), S27/A8 (BASELINE configs[3])"}}
     if not args.no_cpu_baseline:

@@ -47,6 +47,11 @@ struct ActorArgs {
   float* qv[2];        // Q_k(s, pi(s)), [N]
   float* gak[2];       // d Q_k / d action, [N][A]
   float* qh[2];        // Q_k(s_t, a_t), [n_true]
+  // the last CTA to finish reduces the batch scalars the backward needs (fixed order; see actor_finish)
+  const float* part; int ntiles_c;   // critic tile partials [ntiles_c][4]
+  float weight;
+  float* out;          // scalars [16]
+  int* counter;        // zeroed by the critic's Adam launch of the same update
 };
 
 template <int TMv>
@@ -200,56 +205,10 @@ __global__ void __launch_bounds__(NT, 1) critic_bwd_kernel(CriticArgs a) {
   if (tid < 2) a.part[blockIdx.x * 4 + 2 * tid + k] = redbuf[tid] + redbuf[2 + tid];     // [0..1] = sq err of Q1, Q2; [2..3] = sum q
 }
 
-// ---- actor: roles 0, 1 = Q_k(s, pi(s)) and d Q_k / d action with Q frozen (:316-317, 555-556);
-//      roles 2, 3 = q_hat_k = Q_k(s_t, a_t) on the true rows (no grad, :249-251).  pi(s) was computed next to the critic. ----
-template <int RPT>
-__global__ void __launch_bounds__(NT, 1) actor_q_kernel(ActorArgs a) {
-  mb_pdl_begin();
-  constexpr int TM = 8 * RPT;
-  extern __shared__ __align__(16) float sm[];
-  const int S = a.S, A = a.A, ldi = rup16(S + A);
-  float* X0 = sm; float* X1 = X0 + TM * H; float* sap_s = X1 + TM * H;
-  float* qa = sap_s + TM * ldi; float* ones = qa + TM; float* gk = ones + TM;      // gk [TM][A]
-  const int tid = threadIdx.x, row0 = blockIdx.x * TM, rows = min(TM, a.N - row0), k = blockIdx.y & 1;
-  const bool qhat = blockIdx.y >= 2;
-  if (qhat && row0 >= a.n_true) return;
-  for (int i = tid; i < TM * ldi; i += NT) {
-    const int r = i / ldi, j = i - r * ldi;
-    float v = 0.f;
-    if (r < rows) {
-      if (j < S || (qhat && j < S + A)) v = a.X[(size_t)(row0 + r) * a.rw + j];          // [s, a_t] for q_hat
-      else if (j < S + A) v = a.api[(size_t)(row0 + r) * A + (j - S)];                    // [s, pi(s)]
-    }
-    sap_s[i] = v;
-  }
-  if (tid < TM) ones[tid] = 1.0f;
-  __syncthreads();
-  if (qhat) {
-    big_layer_mma<true, RPT>(sap_s, ldi, S + A, a.q[k].w[0], a.q[k].b[0], X0, ACT_RELU);
-    big_layer_mma<true, RPT>(X0, H, H, a.q[k].w[1], a.q[k].b[1], X1, ACT_RELU);
-    q_head<TM>(X1, a.q[k].w[2], a.q[k].b[2], qa);
-    if (tid < rows && row0 + tid < a.n_true) a.qh[k][row0 + tid] = qa[tid];
-    return;
-  }
-  big_layer_mma<true, RPT>(sap_s, ldi, S + A, a.q[k].w[0], a.q[k].b[0], X0, ACT_RELU);
-  big_layer_mma<true, RPT>(X0, H, H, a.q[k].w[1], a.q[k].b[1], X1, ACT_RELU);
-  q_head<TM>(X1, a.q[k].w[2], a.q[k].b[2], qa);
-  head_backward<TM>(X1, a.q[k].w[2], ones);
-  big_layer_mma<false, RPT>(X1, H, H, a.q[k].w[1], nullptr, X0, ACT_MASK);
-  // d q / d a_j = sum_n dH1[n] * W1[n][S+j]
-  small_layer<false, RPT>(X0, H, H, a.q[k].w[0] + S, S + A, nullptr, A, gk, A, ACT_NONE, 1.f);
-  for (int i = tid; i < rows * A; i += NT) a.gak[k][(size_t)row0 * A + i] = gk[i];
-  if (tid < rows) a.qv[k][row0 + tid] = qa[tid];
-}
-
-// Scalars of the actor loss (single CTA, fixed-order reductions):
-//   out[0] = mean|qpi| (N rows)  out[1] = mean qpi  out[2] = mean|qhat| (n_true rows)
-//   out[3] = p_w = weight / mean|qpi|   out[4] = bc loss  out[5] = policy loss
-//   out[6..8] = mean / min / max of exp_adv   out[9] = q loss   out[10] = mean q1   (critic tile partials)
-struct ActorScalarArgs {
-  const float* qv[2]; const float* qh[2]; const float* api; const float* X; const float* part; int ntiles;   // twin outputs; min taken here
-  int N, n_true, S, A, rw; float weight, bc_coef; float* out;
-};
+// Batch scalars of the actor loss that the backward needs, reduced by the LAST CTA of actor_q_kernel to finish (every CTA
+// bumps a counter after its results are globally visible; no float atomics, so the sums have a fixed order):
+//   out[0] = q loss   out[1] = mean q1   (critic tile partials)      out[4] = mean q(s, pi(s))   out[5] = mean|q(s, pi(s))|
+//   out[9] = p_w = weight / mean|q|   out[10] = mean|q_hat|          (out[2, 3, 6..8] come from policy_bwd_kernel)
 __device__ float block_sum(float v, float* sh) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
@@ -283,64 +242,87 @@ __device__ float block_minmax(float v, float* sh, bool is_max) {
   __syncthreads();
   return sh[32];
 }
-__global__ void __launch_bounds__(1024) actor_scalar_kernel(ActorScalarArgs a) {
-  mb_pdl_begin();
-  __shared__ float sh[33];
-  float s_abs = 0.f, s_q = 0.f;
-  for (int i = threadIdx.x; i < a.N; i += blockDim.x) { float q = fminf(a.qv[0][i], a.qv[1][i]); s_abs += fabsf(q); s_q += q; }
-  const float mean_abs = block_sum(s_abs, sh) / (float)a.N;
+__device__ void actor_finish(const ActorArgs& a, float* sh) {
+  __shared__ int last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(a.counter, 1) == (int)(gridDim.x * gridDim.y) - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float s_abs = 0.f, s_q = 0.f, s_h = 0.f;
+  for (int i = threadIdx.x; i < a.N; i += blockDim.x) { const float q = fminf(__ldcg(a.qv[0] + i), __ldcg(a.qv[1] + i)); s_abs += fabsf(q); s_q += q; }
+  for (int i = threadIdx.x; i < a.n_true; i += blockDim.x) s_h += fabsf(fminf(__ldcg(a.qh[0] + i), __ldcg(a.qh[1] + i)));
+  const float mean_abs = block_sum(s_abs, sh) / (float)a.N;                 // mobody.py:318
   const float mean_q = block_sum(s_q, sh) / (float)a.N;
-  float s_h = 0.f;
-  for (int i = threadIdx.x; i < a.n_true; i += blockDim.x) s_h += fabsf(fminf(a.qh[0][i], a.qh[1][i]));
-  const float mean_h = block_sum(s_h, sh) / (float)a.n_true;
-  float s_w = 0.f, w_min = 3.4e38f, w_max = -3.4e38f, s_bc = 0.f;
-  for (int i = threadIdx.x; i < a.n_true; i += blockDim.x) {
-    const float w = fminf(expf(3.0f * (fminf(a.qh[0][i], a.qh[1][i]) / mean_h)), 100.0f);      // :252-258
-    s_w += w; w_min = fminf(w_min, w); w_max = fmaxf(w_max, w);
-    const float* x = a.X + (size_t)i * a.rw + a.S;
-    float e = 0.f;
-    for (int j = 0; j < a.A; ++j) { float d = a.api[(size_t)i * a.A + j] - x[j]; e += d * d; }
-    s_bc += w * e;
-  }
-  const float mean_w = block_sum(s_w, sh) / (float)a.n_true;
-  const float bc = block_sum(s_bc, sh) / (float)((size_t)a.n_true * a.A);   // mean over rows AND action dims (:271)
-  const float wmn = block_minmax(w_min, sh, false), wmx = block_minmax(w_max, sh, true);
+  const float mean_h = block_sum(s_h, sh) / (float)a.n_true;                // :252
+  float l = 0.f, q1s = 0.f;
+  for (int t = threadIdx.x; t < a.ntiles_c; t += blockDim.x) { l += a.part[t * 4] + a.part[t * 4 + 1]; q1s += a.part[t * 4 + 2]; }
+  l = block_sum(l, sh); q1s = block_sum(q1s, sh);
   if (threadIdx.x == 0) {
-    float l = 0.f, q1s = 0.f;
-    for (int t = 0; t < a.ntiles; ++t) { l += a.part[t * 4] + a.part[t * 4 + 1]; q1s += a.part[t * 4 + 2]; }
     a.out[0] = l / (float)a.N; a.out[1] = q1s / (float)a.N;                 // mse(q1,y) + mse(q2,y) (:207)
-    const float pw = a.weight / mean_abs;                                   // :318
-    a.out[2] = pw * (-mean_q) + a.bc_coef * bc;                             // :321, 330
-    a.out[3] = bc; a.out[4] = mean_q; a.out[5] = mean_abs;
-    a.out[6] = mean_w; a.out[7] = wmn; a.out[8] = wmx; a.out[9] = pw; a.out[10] = mean_h;
+    a.out[4] = mean_q; a.out[5] = mean_abs; a.out[9] = a.weight / mean_abs; a.out[10] = mean_h;
   }
 }
 
-// d loss / d (pre-tanh policy output) for every row: [N][A]
-struct ActorGradArgs {
-  const float* scal; const float* gak[2]; const float* qv[2]; const float* api; const float* qh[2]; const float* X;
-  int N, n_true, S, A, rw; float bc_coef, max_action; float* d3p;
-};
-__global__ void actor_grad_kernel(ActorGradArgs a) {
+// ---- actor: roles 0, 1 = Q_k(s, pi(s)) and d Q_k / d action with Q frozen (:316-317, 555-556);
+//      roles 2, 3 = q_hat_k = Q_k(s_t, a_t) on the true rows (no grad, :249-251).  pi(s) was computed next to the critic. ----
+template <int RPT>
+__global__ void __launch_bounds__(NT, 1) actor_q_kernel(ActorArgs a) {
   mb_pdl_begin();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.N * a.A) return;
-  const int r = i / a.A, j = i - r * a.A;
-  const float pw = a.scal[9], mean_h = a.scal[10];
-  const float ap = a.api[i];
-  const float ga = a.qv[0][r] <= a.qv[1][r] ? a.gak[0][i] : a.gak[1][i];   // torch.min(q1, q2): gradient follows the smaller one
-  float g = -pw / (float)a.N * ga;                                          // d [pw * mean(-q)] / d a
-  if (r < a.n_true) {
-    const float w = fminf(expf(3.0f * (fminf(a.qh[0][r], a.qh[1][r]) / mean_h)), 100.0f);
-    const float at = a.X[(size_t)r * a.rw + a.S + j];
-    g += a.bc_coef * w * 2.0f * (ap - at) / (float)((size_t)a.n_true * a.A);
+  constexpr int TM = 8 * RPT;
+  extern __shared__ __align__(16) float sm[];
+  const int S = a.S, A = a.A, ldi = rup16(S + A);
+  float* X0 = sm; float* X1 = X0 + TM * H; float* sap_s = X1 + TM * H;
+  float* qa = sap_s + TM * ldi; float* ones = qa + TM; float* gk = ones + TM;      // gk [TM][A]
+  const int tid = threadIdx.x, row0 = blockIdx.x * TM, rows = min(TM, a.N - row0), k = blockIdx.y & 1;
+  const bool qhat = blockIdx.y >= 2;
+  if (qhat && row0 >= a.n_true) { actor_finish(a, sm); return; }
+  for (int i = tid; i < TM * ldi; i += NT) {
+    const int r = i / ldi, j = i - r * ldi;
+    float v = 0.f;
+    if (r < rows) {
+      if (j < S || (qhat && j < S + A)) v = a.X[(size_t)(row0 + r) * a.rw + j];          // [s, a_t] for q_hat
+      else if (j < S + A) v = a.api[(size_t)(row0 + r) * A + (j - S)];                    // [s, pi(s)]
+    }
+    sap_s[i] = v;
   }
-  const float t = ap / a.max_action;                                        // tanh(u)
-  a.d3p[i] = g * a.max_action * (1.0f - t * t);
+  if (tid < TM) ones[tid] = 1.0f;
+  __syncthreads();
+  if (qhat) {
+    big_layer_mma<true, RPT>(sap_s, ldi, S + A, a.q[k].w[0], a.q[k].b[0], X0, ACT_RELU);
+    big_layer_mma<true, RPT>(X0, H, H, a.q[k].w[1], a.q[k].b[1], X1, ACT_RELU);
+    q_head<TM>(X1, a.q[k].w[2], a.q[k].b[2], qa);
+    if (tid < rows && row0 + tid < a.n_true) a.qh[k][row0 + tid] = qa[tid];
+    actor_finish(a, sm);
+    return;
+  }
+  big_layer_mma<true, RPT>(sap_s, ldi, S + A, a.q[k].w[0], a.q[k].b[0], X0, ACT_RELU);
+  big_layer_mma<true, RPT>(X0, H, H, a.q[k].w[1], a.q[k].b[1], X1, ACT_RELU);
+  q_head<TM>(X1, a.q[k].w[2], a.q[k].b[2], qa);
+  head_backward<TM>(X1, a.q[k].w[2], ones);
+  big_layer_mma<false, RPT>(X1, H, H, a.q[k].w[1], nullptr, X0, ACT_MASK);
+  // d q / d a_j = sum_n dH1[n] * W1[n][S+j]
+  small_layer<false, RPT>(X0, H, H, a.q[k].w[0] + S, S + A, nullptr, A, gk, A, ACT_NONE, 1.f);
+  for (int i = tid; i < rows * A; i += NT) a.gak[k][(size_t)row0 * A + i] = gk[i];
+  if (tid < rows) a.qv[k][row0 + tid] = qa[tid];
+  actor_finish(a, sm);
 }
 
-// Policy backward to the pre-activations: dH2 = (d3p W3) * 1[H2>0], dH1 = (dH2 W2) * 1[H1>0]
-struct PolicyBwdArgs { const float* d3p; int N, A; MlpPtrs pi; const float* Hp[2]; float* Dp[2]; };
+// Policy backward.  Prologue = d loss / d (pre-tanh policy output) of the tile's rows (mobody.py:321-330: the
+// -p_w mean(min Q) term through dQ/da of the smaller twin, plus the Q-weighted BC term on the true rows), written to
+// d3p for the weight gradient of the last layer; then dH2 = (d3p W3) * 1[H2>0], dH1 = (dH2 W2) * 1[H1>0].
+// Logging scalars (exp-advantage weight statistics, BC loss, policy loss) are tile partials reduced by the last CTA:
+//   out[2] = policy loss   out[3] = bc loss   out[6..8] = mean / min / max of the exp-advantage weights
+struct PolicyBwdArgs {
+  int N, n_true, S, A, rw; MlpPtrs pi; const float* Hp[2]; float* Dp[2];
+  const float* gak[2]; const float* qv[2]; const float* qh[2]; const float* api; const float* X;
+  float bc_coef, max_action;
+  float* d3p;          // [N][A]
+  float* part;         // [ntiles][4]: sum w, min w, max w, sum w * |pi(s) - a|^2
+  float* out;          // scalars [16]; [9] = p_w and [10] = mean|q_hat| were written by actor_q_kernel
+  int* counter;
+};
 template <int RPT>
 __global__ void __launch_bounds__(NT, 1) policy_bwd_kernel(PolicyBwdArgs a) {
   mb_pdl_begin();
@@ -349,18 +331,70 @@ __global__ void __launch_bounds__(NT, 1) policy_bwd_kernel(PolicyBwdArgs a) {
   float* X0 = sm; float* X1 = X0 + TM * H; float* Wst = X1 + TM * H;
   const int lda = rup16(a.A);
   float* d3 = Wst;                                       // [TM][lda]
+  float* wrow = d3 + TM * lda;                           // [TM] exp-advantage weight of a true row
+  float* red = wrow + TM;                                // [40]
   const int tid = threadIdx.x, row0 = blockIdx.x * TM, rows = min(TM, a.N - row0);
+  const float pw = a.out[9], mean_h = a.out[10];
+  float w_s = 0.f, w_mn = 3.4e38f, w_mx = -3.4e38f, w_e = 0.f;
+  if (tid < TM) {
+    const int r = row0 + tid;
+    float w = 0.f;
+    if (tid < rows && r < a.n_true) {
+      w = fminf(expf(3.0f * (fminf(a.qh[0][r], a.qh[1][r]) / mean_h)), 100.0f);           // :252-258
+      const float* x = a.X + (size_t)r * a.rw + a.S;
+      float e = 0.f;
+      for (int j = 0; j < a.A; ++j) { const float d = a.api[(size_t)r * a.A + j] - x[j]; e += d * d; }
+      w_s = w; w_mn = w; w_mx = w; w_e = w * e;
+    }
+    wrow[tid] = w;
+  }
+  __syncthreads();
   for (int i = tid; i < TM * lda; i += NT) {
-    int r = i / lda, j = i - r * lda;
-    d3[i] = (r < rows && j < a.A) ? a.d3p[(size_t)(row0 + r) * a.A + j] : 0.f;
+    const int rl = i / lda, j = i - rl * lda, r = row0 + rl;
+    float g3 = 0.f;
+    if (rl < rows && j < a.A) {
+      const size_t e = (size_t)r * a.A + j;
+      const float ap = a.api[e];
+      const float ga = a.qv[0][r] <= a.qv[1][r] ? a.gak[0][e] : a.gak[1][e];   // torch.min(q1, q2): gradient follows the smaller one
+      float g = -pw / (float)a.N * ga;                                          // d [pw * mean(-q)] / d a
+      if (r < a.n_true) g += a.bc_coef * wrow[rl] * 2.0f * (ap - a.X[(size_t)r * a.rw + a.S + j]) / (float)((size_t)a.n_true * a.A);
+      const float t = ap / a.max_action;                                        // tanh(u)
+      g3 = g * a.max_action * (1.0f - t * t);
+      a.d3p[e] = g3;
+    }
+    d3[i] = g3;
   }
   load_tile<TM>(X1, a.Hp[1], row0, rows);
   load_tile<TM>(X0, a.Hp[0], row0, rows);
+  // tile partials of the logging scalars (rows of a tile sit in the first TM threads: warps 0 .. TM/32 - 1, or half a warp)
+  w_s = block_sum(w_s, red); w_e = block_sum(w_e, red);
+  w_mn = block_minmax(w_mn, red, false); w_mx = block_minmax(w_mx, red, true);
+  if (tid == 0) { float* p = a.part + (size_t)blockIdx.x * 4; p[0] = w_s; p[1] = w_mn; p[2] = w_mx; p[3] = w_e; }
   __syncthreads();
   big_layer_mma<false, RPT>(d3, lda, a.A, a.pi.w[2], nullptr, X1, ACT_MASK);    // W3 is [A][256]: dH2[r][i] = sum_j d3[r][j] W3[j][i]
   store_tile<TM>(X1, a.Dp[1], row0, rows);
   big_layer_mma<false, RPT>(X1, H, H, a.pi.w[1], nullptr, X0, ACT_MASK);
   store_tile<TM>(X0, a.Dp[0], row0, rows);
+  // last CTA: logging scalars in tile order
+  __shared__ int last;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) last = atomicAdd(a.counter, 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float s_w = 0.f, s_e = 0.f, mn = 3.4e38f, mx = -3.4e38f;
+  for (int t = tid; t < (int)gridDim.x; t += NT) {
+    const float* p = a.part + (size_t)t * 4;
+    s_w += __ldcg(p); mn = fminf(mn, __ldcg(p + 1)); mx = fmaxf(mx, __ldcg(p + 2)); s_e += __ldcg(p + 3);
+  }
+  s_w = block_sum(s_w, red); s_e = block_sum(s_e, red);
+  mn = block_minmax(mn, red, false); mx = block_minmax(mx, red, true);
+  if (tid == 0) {
+    const float bc = s_e / (float)((size_t)a.n_true * a.A);                   // mean over rows AND action dims (:271)
+    a.out[2] = pw * (-a.out[4]) + a.bc_coef * bc;                             // :321, 330
+    a.out[3] = bc; a.out[6] = s_w / (float)a.n_true; a.out[7] = mn; a.out[8] = mx;
+  }
 }
 
 // ---------------- weight gradients: dW[o][i] = sum_r D[r][o] X[r][i], db[o] = sum_r D[r][o] ----------------
@@ -570,9 +604,10 @@ __global__ void __launch_bounds__(256, 2) wgrad_kernel(WgradArgs a) {
 
 // ---------------- fused Adam (+ Polyak target update) over a table of tensors ----------------
 struct AdamJob { float* p; const float* g; float* m; float* v; float* tgt; int n; };
-struct AdamArgs { AdamJob job[12]; int njobs, nsplit; float lr_over_bc1, inv_sqrt_bc2, b1, b2, eps, tau; };
+struct AdamArgs { AdamJob job[12]; int njobs, nsplit; float lr_over_bc1, inv_sqrt_bc2, b1, b2, eps, tau; int* zero2; };   // zero2: the actor phase's two "last CTA" counters
 __global__ void adam_kernel(AdamArgs a) {
   mb_pdl_begin();
+  if (a.zero2 && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 2) a.zero2[threadIdx.x] = 0;
   const AdamJob jb = a.job[blockIdx.y];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < jb.n; i += gridDim.x * blockDim.x) {
     float g = 0.f;                                                          // fixed order over the row splits;
@@ -750,9 +785,6 @@ __global__ void __launch_bounds__(NT, 1) dara_relabel_kernel(RelabelArgs a) {
 }  // namespace trn
 
 // ---------------- host launchers ----------------
-static size_t tile_smem(int tm, int S, int A, int extra_floats) {
-  return (2 * (size_t)tm * simt::H + 2 * (size_t)tm * simt::rup16(S + A) + extra_floats) * sizeof(float);
-}
 // Row tile: 64 rows per CTA for large batches; 16 for small ones so that a 320-row batch still spreads over 20 SMs.
 static int pick_tm(int N) { return N >= 148 * 32 ? 64 : 16; }
 template <typename K> static const char* set_smem(K kern, size_t bytes) {
@@ -783,18 +815,9 @@ const char* mb_train_actor_launch(const trn::ActorArgs& a, cudaStream_t st) {
   mb_launch(k2, dim3(ntiles, 4), dim3(simt::NT), bytes, st, a);
   return nullptr;
 }
-const char* mb_train_actor_scalars_launch(const trn::ActorScalarArgs& a, cudaStream_t st) {
-  mb_launch(trn::actor_scalar_kernel, dim3(1), dim3(1024), 0, st, a);
-  return nullptr;
-}
-const char* mb_train_actor_grad_launch(const trn::ActorGradArgs& a, cudaStream_t st) {
-  int n = a.N * a.A;
-  mb_launch(trn::actor_grad_kernel, dim3((n + 255) / 256), dim3(256), 0, st, a);
-  return nullptr;
-}
 const char* mb_train_policy_bwd_launch(const trn::PolicyBwdArgs& a, cudaStream_t st) {
   const int tm = pick_tm(a.N);
-  size_t bytes = (2 * (size_t)tm * simt::H + (size_t)tm * simt::rup16(a.A)) * sizeof(float);
+  size_t bytes = (2 * (size_t)tm * simt::H + (size_t)tm * simt::rup16(a.A) + tm + 40) * sizeof(float);
   auto kern = tm == 64 ? trn::policy_bwd_kernel<8> : trn::policy_bwd_kernel<2>;
   if (const char* e = set_smem(kern, bytes)) return e;
   mb_launch(kern, dim3((a.N + tm - 1) / tm), dim3(simt::NT), bytes, st, a);
@@ -823,7 +846,7 @@ const char* mb_train_adam_launch(const trn::AdamArgs& a, cudaStream_t st) {
 
 // ---------------- whole train step (C ABI: mobody_train_step) ----------------
 struct TrainWs {   // float offsets into the workspace
-  size_t Hq[2][2], Dq[2][2], d3[2], part, Hp[2], Dp[2], api, a2, qk[2], qtk[2], qv[2], qh[2], gak[2], d3p, scal, gq[2][6], gp[6], total;
+  size_t Hq[2][2], Dq[2][2], d3[2], part, Hp[2], Dp[2], api, a2, qk[2], qtk[2], qv[2], qh[2], gak[2], d3p, scal, part2, cnt, gq[2][6], gp[6], total;
   int ntiles;
 };
 static TrainWs train_ws(int N, int S, int A, int nsplit) {
@@ -837,7 +860,7 @@ static TrainWs train_ws(int N, int S, int A, int nsplit) {
   for (int l = 0; l < 2; ++l) { w.Hp[l] = take(act); w.Dp[l] = take(act); }
   w.api = take((size_t)N * A); w.a2 = take((size_t)N * A); w.d3p = take((size_t)N * A);
   for (int k = 0; k < 2; ++k) { w.qk[k] = take(N); w.qtk[k] = take(N); w.qv[k] = take(N); w.qh[k] = take(N); w.gak[k] = take((size_t)N * A); }
-  w.scal = take(16);
+  w.scal = take(16); w.part2 = take((size_t)w.ntiles * 4); w.cnt = take(4);
   const size_t qn[6] = {(size_t)256 * (S + A), 256, 256 * 256, 256, 256, 1};       // w1 b1 w2 b2 w3 b3
   const size_t pn[6] = {(size_t)256 * S, 256, 256 * 256, 256, (size_t)A * 256, (size_t)A};
   for (int k = 0; k < 2; ++k) for (int t = 0; t < 6; ++t) w.gq[k][t] = take(qn[t] * nsplit);
@@ -880,6 +903,7 @@ const char* mb_train_step_launch(const mobody_train_desc& d, cudaStream_t st) {
   }
   if (const char* e = mb_train_wgrad_launch(g, st)) return e;
   trn::AdamArgs ad{}; ad.nsplit = ns; ad.b1 = 0.9f; ad.b2 = 0.999f; ad.eps = 1e-8f; ad.tau = d.tau; ad.njobs = 12;
+  ad.zero2 = reinterpret_cast<int*>(ws + w.cnt);
   {
     const double bc1 = 1.0 - pow(0.9, (double)d.t_q), bc2 = 1.0 - pow(0.999, (double)d.t_q);
     ad.lr_over_bc1 = (float)(d.critic_lr / bc1); ad.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
@@ -898,13 +922,14 @@ const char* mb_train_step_launch(const mobody_train_desc& d, cudaStream_t st) {
   ac.q[0] = as_ptrs(d.q1); ac.q[1] = as_ptrs(d.q2); ac.max_action = d.max_action;
   ac.Hp[0] = ws + w.Hp[0]; ac.Hp[1] = ws + w.Hp[1]; ac.api = ws + w.api;
   for (int k = 0; k < 2; ++k) { ac.qv[k] = ws + w.qv[k]; ac.qh[k] = ws + w.qh[k]; ac.gak[k] = ws + w.gak[k]; }
+  ac.part = ws + w.part; ac.ntiles_c = (N + pick_tm(N) - 1) / pick_tm(N); ac.weight = d.weight; ac.out = ws + w.scal;
+  ac.counter = reinterpret_cast<int*>(ws + w.cnt);
   if (const char* e = mb_train_actor_launch(ac, st)) return e;
-  trn::ActorScalarArgs sc{{ac.qv[0], ac.qv[1]}, {ac.qh[0], ac.qh[1]}, ac.api, d.rows, ws + w.part, (N + pick_tm(N) - 1) / pick_tm(N), N, d.n_true, S, A, d.row_width, d.weight, d.bc_coef, ws + w.scal};
-  if (const char* e = mb_train_actor_scalars_launch(sc, st)) return e;
-  trn::ActorGradArgs ag{ws + w.scal, {ac.gak[0], ac.gak[1]}, {ac.qv[0], ac.qv[1]}, ac.api, {ac.qh[0], ac.qh[1]}, d.rows, N, d.n_true, S, A, d.row_width, d.bc_coef, d.max_action, ws + w.d3p};
-  if (const char* e = mb_train_actor_grad_launch(ag, st)) return e;
-  trn::PolicyBwdArgs pb{}; pb.d3p = ws + w.d3p; pb.N = N; pb.A = A; pb.pi = ac.pi;
+  trn::PolicyBwdArgs pb{}; pb.N = N; pb.n_true = d.n_true; pb.S = S; pb.A = A; pb.rw = d.row_width; pb.pi = ac.pi;
   pb.Hp[0] = ac.Hp[0]; pb.Hp[1] = ac.Hp[1]; pb.Dp[0] = ws + w.Dp[0]; pb.Dp[1] = ws + w.Dp[1];
+  for (int k = 0; k < 2; ++k) { pb.gak[k] = ac.gak[k]; pb.qv[k] = ac.qv[k]; pb.qh[k] = ac.qh[k]; }
+  pb.api = ac.api; pb.X = d.rows; pb.bc_coef = d.bc_coef; pb.max_action = d.max_action;
+  pb.d3p = ws + w.d3p; pb.part = ws + w.part2; pb.out = ws + w.scal; pb.counter = reinterpret_cast<int*>(ws + w.cnt) + 1;
   if (const char* e = mb_train_policy_bwd_launch(pb, st)) return e;
   trn::WgradArgs gp{}; gp.N = N; gp.nsplit = ns; gp.njobs = 3;
   gp.job[0] = {pb.Dp[0], 256, d.rows, d.row_width, ws + w.gp[0], ws + w.gp[1], 256, S};
