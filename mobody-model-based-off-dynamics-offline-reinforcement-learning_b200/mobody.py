@@ -125,6 +125,7 @@ class MOBODY(object):
         self._roll_ws = {}                                       # (T, B, S, A) -> rollout scratch
         self._host_slabs, self._host_turn = [None, None], 0      # pinned staging of rollout() results
         self._pipe_streams, self._pipe_hdr = None, None          # side streams / pinned header of the pipelined rollout()
+        self._pipe_plan_cache = None                             # (key, per-chunk launch plan)
 
     def select_action(self, state, policy, cuda=False):          # mobody.py:138-144
         with torch.no_grad():
@@ -258,47 +259,94 @@ class MOBODY(object):
             c0 += w
         return res, {"num_transitions": n_tr, "reward_mean": rsum / max(n_tr, 1)}
 
+    PIPE_FIRST = 148 * 128        # first chunk: one wave, so the first kernel starts after a short H2D
+
+    def _pipe_bounds(self, B):
+        """Chunk boundaries of a pipelined one-step rollout: a one-wave first chunk (little H2D exposed before the first
+        kernel), two-wave chunks after it, and the sub-wave remainder as its own last chunk (little D2H exposed after the
+        last kernel).  Whole waves per chunk: chunking adds no partially filled round to the step kernel."""
+        bounds, lo = [0], min(self.PIPE_FIRST, B)
+        while lo < B:
+            bounds.append(lo)
+            lo += self.PIPE_ROWS
+        bounds.append(B)
+        wave = 148 * 128
+        tail = (B - bounds[-2]) % wave
+        if 0 < tail < B - bounds[-2] and tail <= wave // 2:
+            bounds.insert(-1, B - tail)                           # split the sub-wave remainder off the last chunk
+        return bounds
+
+    def _pipe_plan(self, B, S, A, W, use_trg, bounds):
+        """Per-chunk launch plan of the pipelined rollout (device input / output buffers, workspace, a filled
+        mobody_rollout_desc, an event), cached while nothing it points to changes: a chunk then costs one H2D
+        enqueue, ONE C-ABI call and two 8-byte D2H enqueues of host time."""
+        dev, dyn = self.device, self.dynamics
+        probe = _ffi.StepDesc()
+        # also (re)builds the packed weight images on the caller's stream, before the side streams fork from it
+        keep0 = dyn.fill_step_desc(probe, 1, S, dev, policy=self.policy.network, max_action=self.policy.max_action, use_trg=use_trg)
+        filt, env_filter = int(bool(self.config.get("filter_bad_rollout", 1))), float(self.config.get("env_filter", 0.0))
+        key = (tuple(bounds), S, A, bool(use_trg), probe.precision, probe.dyn_pack, probe.policy_pack,
+               C.addressof(probe.dyn.contents), C.addressof(probe.policy.contents), probe.elites, probe.n_elites,
+               probe.penalty_coef, probe.term_kind, probe.seed, probe.max_action, filt, env_filter)
+        if self._pipe_plan_cache is not None and self._pipe_plan_cache[0] == key:
+            return self._pipe_plan_cache[1]
+        plan = []
+        for c in range(len(bounds) - 1):
+            lo, hi = bounds[c], bounds[c + 1]
+            n = hi - lo
+            ws = self._rollout_workspace(1, n, S, A, 1 + (c & 1))
+            x = torch.empty(n, S, dtype=torch.float32, device=dev)
+            packed = torch.empty(n, W, dtype=torch.float32, device=dev)
+            d = _ffi.RolloutDesc()
+            keep = dyn.fill_step_desc(d.step, n, S, dev, policy=self.policy.network, max_action=self.policy.max_action, use_trg=use_trg)
+            d.step.obs, d.step.mean, d.step.raw_reward = _ffi.ptr(x), _ffi.ptr(ws["mean"]), _ffi.ptr(ws["raw"])
+            d.step.step, d.step.row0 = 0, int(lo)
+            d.T, d.filter_bad_rollout, d.env_filter = 1, filt, env_filter
+            d.eps_all, d.idx_all = None, None
+            for k in ("obss", "acts", "nexts", "rews", "pens", "terms", "row_ids", "counts", "pos", "scratch", "stats", "ticket"):
+                setattr(d, k, _ffi.ptr(ws[k]))
+            d.packed = _ffi.ptr(packed)
+            plan.append(dict(lo=lo, hi=hi, x=x, packed=packed, desc=d, ref=C.byref(d), keep=(keep, keep0, ws),
+                             kept_dev=ws["counts"][2:3], stats_dev=ws["stats"][:2], ev=torch.cuda.Event()))
+        self._pipe_plan_cache = (key, plan)
+        return plan
+
     def _rollout_pipelined(self, init_obss, use_trg, S, A, W):
-        dev = self.device
+        dev, lib = self.device, _ffi.lib()
         if not torch.is_tensor(init_obss):
             init_obss = torch.as_tensor(np.asarray(init_obss, dtype=np.float32))
         B = init_obss.shape[0]
-        bounds = list(range(0, B, self.PIPE_ROWS)) + [B]
-        if bounds[-1] - bounds[-2] < self.PIPE_ROWS // 4 and len(bounds) > 2:
-            bounds.pop(-2)                                        # fold a short tail into the previous chunk
+        bounds = self._pipe_bounds(B)
         n = len(bounds) - 1
         if self._pipe_streams is None:
             self._pipe_streams = [torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)]   # 2 compute + 1 D2H
-        if self._pipe_hdr is None or self._pipe_hdr.shape[0] < n:
-            self._pipe_hdr = torch.empty(max(n, 8), 4, dtype=torch.float64, pin_memory=True)
+        if self._pipe_hdr is None or self._pipe_hdr[0].shape[0] < n:
+            self._pipe_hdr = (torch.zeros(max(n, 8), 1, dtype=torch.int32).pin_memory(),      # kept rows per chunk
+                              torch.zeros(max(n, 8), 2, dtype=torch.float64).pin_memory())    # [reward sum, produced]
+        hdr_kept, hdr_stats = self._pipe_hdr
         cur = torch.cuda.current_stream(dev)
-        # (re)build the packed weight images on the caller's stream, before the side streams fork from it
-        self.dynamics.fill_step_desc(_ffi.StepDesc(), 1, S, dev, policy=self.policy.network, max_action=self.policy.max_action,
-                                     use_trg=use_trg)
+        plan = self._pipe_plan(B, S, A, W, use_trg, bounds)
         ready = torch.cuda.Event(); ready.record(cur)
         host = self._host_slab(B, W)
-        chunks = []
-        for c in range(n):
+        for c, ch in enumerate(plan):
             st = self._pipe_streams[c & 1]
-            lo, hi = bounds[c], bounds[c + 1]
             with torch.cuda.stream(st):
                 st.wait_event(ready)
-                x = init_obss[lo:hi].to(device=dev, dtype=torch.float32, non_blocking=True)
-                out, info = self.rollout_device(x, 1, use_trg, row0=lo, sync=False, ws_slot=1 + (c & 1))
-                # [kept, produced, reward sum] of this chunk -> pinned header row (8-byte D2H, stream ordered)
-                self._pipe_hdr[c, 0:1].copy_(info["kept_dev"].double(), non_blocking=True)
-                self._pipe_hdr[c, 1:3].copy_(info["stats_dev"].flip(0), non_blocking=True)
-                ev = torch.cuda.Event(); ev.record(st)
-            chunks.append((st, ev, info["packed"], x))
+                ch["x"].copy_(init_obss[ch["lo"]:ch["hi"]], non_blocking=True)
+                _ffi.check(lib.mobody_rollout(ch["ref"], C.c_void_p(st.cuda_stream)))
+                # [kept | reward sum, produced] of this chunk -> pinned header rows (stream-ordered 4- and 16-byte D2H)
+                hdr_kept[c].copy_(ch["kept_dev"], non_blocking=True)
+                hdr_stats[c].copy_(ch["stats_dev"], non_blocking=True)
+                ch["ev"].record(st)
         off, n_tr, rsum = 0, 0, 0.0
-        for c, (st, ev, packed, _x) in enumerate(chunks):
-            ev.synchronize()                                      # chunk c is done; later chunks keep the GPU busy
-            m = int(self._pipe_hdr[c, 0]); n_tr += int(self._pipe_hdr[c, 1]); rsum += float(self._pipe_hdr[c, 2])
-            with torch.cuda.stream(self._pipe_streams[2]):     # dedicated copy stream: never queued behind a later chunk's kernels
-                host[off:off + m].copy_(packed[:m], non_blocking=True)
+        copy_stream = self._pipe_streams[2]                       # dedicated copy stream: never queued behind a later chunk's kernels
+        for c, ch in enumerate(plan):
+            ch["ev"].synchronize()                                # chunk c is done; later chunks keep the GPU busy
+            m = int(hdr_kept[c, 0]); rsum += float(hdr_stats[c, 0]); n_tr += int(hdr_stats[c, 1])
+            with torch.cuda.stream(copy_stream):
+                host[off:off + m].copy_(ch["packed"][:m], non_blocking=True)
             off += m
-        for st in self._pipe_streams:
-            st.synchronize()
+        copy_stream.synchronize()
         return host[:off], n_tr, rsum, off
 
     # ------------------------------------------------------------------ DARA domain classifier
