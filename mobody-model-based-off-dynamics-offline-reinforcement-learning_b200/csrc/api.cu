@@ -185,7 +185,7 @@ int mobody_sample_rows(const mobody_sample_job* jobs, int njobs, int row_width, 
 
 int mobody_pack_rows(const float* s, const float* a, const float* ns, const float* r, const float* d, long long n,
                      int S, int A, int done_is_terminal, float* out_rows, void* stream) {
-  if (n < 0 || S < 1 || A < 1) return fail(MOBODY_ERR_ARG, "mobody_pack_rows: bad arguments");
+  if (n < 0 || S < 1 || A < 1 || S > 1024 || A > 1024) return fail(MOBODY_ERR_ARG, "mobody_pack_rows: bad arguments");
   if (n > 0 && (!s || !a || !ns || !r || !d || !out_rows)) return fail(MOBODY_ERR_ARG, "mobody_pack_rows: null pointer");
   mb_pack_rows_launch(s, a, ns, r, d, n, S, A, mobody_row_width(S, A), done_is_terminal, out_rows, (cudaStream_t)stream);
   return check_launch("mobody_pack_rows");

@@ -73,15 +73,17 @@ class Classifier(nn.Module):                                   # mobody.py:11-33
 _SM_COUNT = {}
 
 
-def _wgrad_splits(n_rows, tiles_per_launch, device):
+def _wgrad_splits(n_rows, tiles_per_launch, device, sm_count=None):
     """Row splits of the weight-gradient launches.  A launch runs ``tiles * nsplit`` CTAs of 128 x 64 outputs, two per
     SM, each walking its rows in chunks of 32: pick the split count (<= 64) that minimises rounds x chunks per CTA
     summed over the launches of an update (tiles: critic 2 x (8 + 2), actor 8 + 2), i.e. avoid a nearly empty last
     round.  Any value gives the same result up to fp32 summation order; the order is fixed for a given value."""
-    key = str(device)
-    if key not in _SM_COUNT:
-        _SM_COUNT[key] = torch.cuda.get_device_properties(device).multi_processor_count
-    slots, chunks = 2 * _SM_COUNT[key], (n_rows + 31) // 32
+    if sm_count is None:
+        key = str(device)
+        if key not in _SM_COUNT:
+            _SM_COUNT[key] = torch.cuda.get_device_properties(device).multi_processor_count
+        sm_count = _SM_COUNT[key]
+    slots, chunks = 2 * sm_count, (n_rows + 31) // 32
     best, best_cost = 1, None
     for n in range(1, min(64, chunks) + 1):
         per = (chunks + n - 1) // n
@@ -415,16 +417,18 @@ class MOBODY(object):
         del k0, k1
 
     # ------------------------------------------------------------------ train step
-    def train_on_rows(self, rows, n_true):
+    def train_on_rows(self, rows, n_true, *, nsplit=None):
         """One fused critic + Polyak + actor update on packed batch rows [N, RW] (device, rows ordered
         src, tar, fake; the first ``n_true`` rows are the src+tar rows of the BC term).  Asynchronous:
-        losses land in ``self._scalars`` (device).  mobody.py:541-573."""
+        losses land in ``self._scalars`` (device).  mobody.py:541-573.
+        ``nsplit`` overrides the row-split count of the weight-gradient GEMMs (1..64; tests)."""
         cfg = self.config
         if cfg.get("advantage", 0) or not cfg.get("scale_Q", 1) or not cfg.get("q_weighted", 1):
             raise NotImplementedError("mobody_b200 implements the default advantage=0, scale_Q=1, q_weighted=1 update")
         S, A = cfg["state_dim"], cfg["action_dim"]
         N = rows.shape[0]
-        nsplit = _wgrad_splits(N, (20, 10), self.device)   # row splits of the weight-gradient GEMMs (partials summed in Adam, fixed order)
+        if nsplit is None:
+            nsplit = _wgrad_splits(N, (20, 10), self.device)   # row splits of the weight-gradient GEMMs (partials summed in Adam, fixed order)
         lib = _ffi.lib()
         need = int(lib.mobody_train_workspace_bytes(N, S, A, nsplit))
         if self._train_ws is None or self._train_ws.numel() < need:

@@ -132,3 +132,36 @@ def test_train_end_to_end_with_refresh_runs():
     ag3.dynamics = ag.dynamics
     ag3.train(src, tar, 128, None, None)
     assert ag3._t_cls == 1 and ag3.fake_replay_buffer.size == 50000 + 2000 + 50000 + 50100
+
+
+@pytest.mark.parametrize("S,A,N,n_true", [(17, 6, 77, 64), (27, 8, 1500, 1200)])
+def test_weight_gradient_row_splits_agree(S, A, N, n_true):
+    """The weight-gradient GEMMs (3xTF32 tensor-core tiles + narrow heads) split the rows `nsplit` ways and Adam adds the
+    partial sums in split order: any split count -- one, a ragged one, more splits than 32-row chunks (empty splits) --
+    must give the same update up to fp32 summation order, and the same count must give it bit for bit."""
+    from mobody_b200 import _ffi
+    rng = np.random.default_rng(7 * N)
+    RW = _ffi.lib().mobody_row_width(S, A)
+    rows = np.zeros((N, RW), np.float32)
+    rows[:, :2 * S + A] = rng.standard_normal((N, 2 * S + A)).astype(np.float32)
+    rows[:, S:S + A] = rng.uniform(-1, 1, (N, A)).astype(np.float32)
+    rows[:, 2 * S + A] = rng.standard_normal(N).astype(np.float32)
+    rows[:, 2 * S + A + 1] = (rng.random(N) > 0.1).astype(np.float32)
+    rows_d = torch.from_numpy(rows).cuda()
+
+    def run(nsplit):
+        ag, _ = cuda_agent(S, A, 55)
+        for _ in range(2):
+            ag.train_on_rows(rows_d, n_true, nsplit=nsplit)
+        torch.cuda.synchronize()
+        return {f"{g}.{k}": v.detach().cpu().numpy().copy() for g, m in (("pi", ag.policy), ("q", ag.q_funcs), ("qt", ag.target_q_funcs))
+                for k, v in m.state_dict().items()}
+
+    base = run(1)
+    again = run(1)
+    for k in base:
+        assert np.array_equal(base[k], again[k]), k                        # fixed summation order: bit-reproducible
+    for nsplit in (3, 7, 64):
+        other = run(nsplit)
+        for k in base:
+            adam_close(other[k], base[k], 3e-4, 2, (nsplit, k))
