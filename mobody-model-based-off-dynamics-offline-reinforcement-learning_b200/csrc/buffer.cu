@@ -50,43 +50,27 @@ __global__ void sample_rows_kernel(SampleJobs j, int rw4) {
 }
 
 // Pack separate [n,S],[n,A],[n,S],[n,1],[n,1] arrays into rows; done_is_terminal: store 1 - d (utils.py:73).
-// A CTA walks tiles of 64 rows: every source's slice of the tile is one contiguous run, read with fully coalesced
-// loads and scattered into a [64][rw] shared-memory image of the packed rows (pad columns zeroed once), which then
-// leaves as one contiguous run of 128-bit stores.  Both HBM sides are sequential; the row / column of a source
-// element comes from a multiply-high by a precomputed reciprocal (exact for the < 2^13 elements of a slice).
-constexpr int PK_R = 64;
-__device__ __forceinline__ void pack_stage(float* __restrict__ tile, const float* __restrict__ src, int count, int w, uint32_t magic,
-                                           int rw, int col0, bool one_minus) {
-  for (int e = threadIdx.x; e < count; e += blockDim.x) {
-    const int i = w == 1 ? e : (int)__umulhi((uint32_t)e, magic), c = e - i * w;       // ceil(2^32 / 1) does not fit 32 bits
-    const float v = __ldg(src + e);
-    tile[i * rw + col0 + c] = one_minus ? 1.0f - v : v;
-  }
-}
-__global__ void __launch_bounds__(256) pack_rows_kernel(const float* __restrict__ s, const float* __restrict__ a, const float* __restrict__ ns,
-                                                        const float* __restrict__ r, const float* __restrict__ d, long long n, int S, int A,
-                                                        int rw, int done_is_terminal, float* __restrict__ out) {
-  extern __shared__ __align__(16) float pk_tile[];           // [PK_R][rw]
-  const int used = 2 * S + A + 2, rw4 = rw >> 2;
-  const uint32_t mS = (uint32_t)((0x100000000ull + S - 1) / S), mA = (uint32_t)((0x100000000ull + A - 1) / A);
-  for (int t = threadIdx.x; t < PK_R * (rw - used); t += blockDim.x) {
-    const int i = t / (rw - used), c = t - i * (rw - used);
-    pk_tile[i * rw + used + c] = 0.f;
-  }
-  for (long long i0 = (long long)blockIdx.x * PK_R; i0 < n; i0 += (long long)gridDim.x * PK_R) {
-    const int rows = (int)min((long long)PK_R, n - i0);
-    pack_stage(pk_tile, s + i0 * S, rows * S, S, mS, rw, 0, false);
-    pack_stage(pk_tile, a + i0 * A, rows * A, A, mA, rw, S, false);
-    pack_stage(pk_tile, ns + i0 * S, rows * S, S, mS, rw, S + A, false);
-    for (int e = threadIdx.x; e < rows; e += blockDim.x) {
-      pk_tile[e * rw + 2 * S + A] = __ldg(r + i0 + e);
-      const float dv = __ldg(d + i0 + e);
-      pk_tile[e * rw + 2 * S + A + 1] = done_is_terminal ? 1.0f - dv : dv;
+__global__ void pack_rows_kernel(const float* __restrict__ s, const float* __restrict__ a, const float* __restrict__ ns,
+                                 const float* __restrict__ r, const float* __restrict__ d, long long n, int S, int A,
+                                 int rw, int done_is_terminal, float* __restrict__ out) {
+  const int rw4 = rw >> 2;                                  // one thread per 16-byte group of an output row (128-bit stores)
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = n * rw4;
+  for (; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long i = t / rw4; const int c0 = (int)(t - i * rw4) * 4;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c0 + j;
+      float x = 0.f;
+      if (c < S) x = __ldg(s + i * S + c);
+      else if (c < S + A) x = __ldg(a + i * A + (c - S));
+      else if (c < 2 * S + A) x = __ldg(ns + i * S + (c - S - A));
+      else if (c == 2 * S + A) x = __ldg(r + i);
+      else if (c == 2 * S + A + 1) x = done_is_terminal ? 1.0f - __ldg(d + i) : __ldg(d + i);
+      v[j] = x;
     }
-    __syncthreads();
-    float4* o = reinterpret_cast<float4*>(out + i0 * rw);
-    for (int t = threadIdx.x; t < rows * rw4; t += blockDim.x) o[t] = reinterpret_cast<const float4*>(pk_tile)[t];
-    __syncthreads();
+    reinterpret_cast<float4*>(out)[t] = make_float4(v[0], v[1], v[2], v[3]);
   }
 }
 
@@ -322,11 +306,7 @@ void mb_philox_indices_launch(int64_t* idx, long long n, unsigned long long seed
 void mb_pack_rows_launch(const float* s, const float* a, const float* ns, const float* r, const float* d, long long n,
                          int S, int A, int rw, int done_is_terminal, float* out, cudaStream_t st) {
   if (n <= 0) return;
-  const long long tiles = (n + buf::PK_R - 1) / buf::PK_R;
-  const unsigned grid = (unsigned)(tiles < 148 * 8 ? tiles : 148 * 8);         // 8 resident CTAs per SM walk the tiles
-  const size_t smem = (size_t)buf::PK_R * rw * sizeof(float);                  // 11 KB at obs 17 / act 6; a launch error beyond 227 KB
-  cudaFuncSetAttribute(buf::pack_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  buf::pack_rows_kernel<<<grid, 256, smem, st>>>(s, a, ns, r, d, n, S, A, rw, done_is_terminal, out);
+  buf::pack_rows_kernel<<<grid_for(n * (rw / 4), buf::NT), buf::NT, 0, st>>>(s, a, ns, r, d, n, S, A, rw, done_is_terminal, out);
 }
 void mb_ring_insert_launch(const float* src, long long n_cap, const int* n_dev, int rw, long long ptr, long long cap,
                            float* dst, cudaStream_t st) {
