@@ -196,7 +196,7 @@ typedef struct mobody_train_desc {
   mobody_mlp_state policy_m, policy_v, q1_m, q1_v, q2_m, q2_v;  /* Adam first / second moments              */
   int t_q, t_pi;                 /* optimiser step counts AFTER this step (1-based), for bias correction    */
   float gamma, tau, critic_lr, actor_lr, weight, bc_coef, max_action;
-  int nsplit;                    /* row splits of the weight-gradient GEMMs (1 for small batches)           */
+  int nsplit;                    /* row splits of the weight-gradient GEMMs, 1..64 (any value: same update up to fp32 summation order) */
   void* workspace; long long workspace_bytes;   /* device scratch >= mobody_train_workspace_bytes(...)       */
   float* scalars_out;            /* device float[16]                                                        */
 } mobody_train_desc;

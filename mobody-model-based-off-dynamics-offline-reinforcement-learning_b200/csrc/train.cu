@@ -99,7 +99,7 @@ __device__ __forceinline__ void head_backward(float* __restrict__ X1, const floa
 // ---- critic phase 1: role 0 = pi(s') (:190), roles 1, 2 = Q_k(s, a) forward with stored activations (:196),
 //      role 3 = pi(s) with stored activations for the actor update that follows (:315; same policy parameters) ----
 template <int RPT>
-__global__ void __launch_bounds__(NT, 1) critic_fwd_kernel(CriticArgs a) {
+__global__ void __launch_bounds__(NT, RPT == 4 ? 2 : 1) critic_fwd_kernel(CriticArgs a) {
   mb_pdl_begin();
   constexpr int TM = 8 * RPT;
   extern __shared__ __align__(16) float sm[];
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(NT, 1) critic_fwd_kernel(CriticArgs a) {
 
 // ---- critic phase 2: role k = Q'_k(s', pi(s')) (no grad, :191-193) ----
 template <int RPT>
-__global__ void __launch_bounds__(NT, 1) critic_tgt_kernel(CriticArgs a) {
+__global__ void __launch_bounds__(NT, RPT == 4 ? 2 : 1) critic_tgt_kernel(CriticArgs a) {
   mb_pdl_begin();
   constexpr int TM = 8 * RPT;
   extern __shared__ __align__(16) float sm[];
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(NT, 1) critic_tgt_kernel(CriticArgs a) {
 
 // ---- critic phase 3: role k = TD target, mse gradient of Q_k and backward to the pre-activations (:194-207) ----
 template <int RPT>
-__global__ void __launch_bounds__(NT, 1) critic_bwd_kernel(CriticArgs a) {
+__global__ void __launch_bounds__(NT, RPT == 4 ? 2 : 1) critic_bwd_kernel(CriticArgs a) {
   mb_pdl_begin();
   constexpr int TM = 8 * RPT;
   extern __shared__ __align__(16) float sm[];
@@ -268,7 +268,7 @@ __device__ void actor_finish(const ActorArgs& a, float* sh) {
 // ---- actor: roles 0, 1 = Q_k(s, pi(s)) and d Q_k / d action with Q frozen (:316-317, 555-556);
 //      roles 2, 3 = q_hat_k = Q_k(s_t, a_t) on the true rows (no grad, :249-251).  pi(s) was computed next to the critic. ----
 template <int RPT>
-__global__ void __launch_bounds__(NT, 1) actor_q_kernel(ActorArgs a) {
+__global__ void __launch_bounds__(NT, RPT == 4 ? 2 : 1) actor_q_kernel(ActorArgs a) {
   mb_pdl_begin();
   constexpr int TM = 8 * RPT;
   extern __shared__ __align__(16) float sm[];
@@ -324,7 +324,7 @@ struct PolicyBwdArgs {
   int* counter;
 };
 template <int RPT>
-__global__ void __launch_bounds__(NT, 1) policy_bwd_kernel(PolicyBwdArgs a) {
+__global__ void __launch_bounds__(NT, RPT == 4 ? 2 : 1) policy_bwd_kernel(PolicyBwdArgs a) {
   mb_pdl_begin();
   constexpr int TM = 8 * RPT;
   extern __shared__ __align__(16) float sm[];
@@ -651,7 +651,7 @@ __device__ __forceinline__ void softmax2(float z0, float z1, float& p0, float& p
 }
 
 template <int RPT>
-__global__ void __launch_bounds__(NT, 1) classifier_kernel(ClsArgs a) {
+__global__ void __launch_bounds__(NT, RPT == 4 ? 2 : 1) classifier_kernel(ClsArgs a) {
   mb_pdl_begin();
   constexpr int TM = 8 * RPT;
   extern __shared__ __align__(16) float sm[];
@@ -785,8 +785,13 @@ __global__ void __launch_bounds__(NT, 1) dara_relabel_kernel(RelabelArgs a) {
 }  // namespace trn
 
 // ---------------- host launchers ----------------
-// Row tile: 64 rows per CTA for large batches; 16 for small ones so that a 320-row batch still spreads over 20 SMs.
-static int pick_tm(int N) { return N >= 148 * 32 ? 64 : 16; }
+// Row tile: 16 rows per CTA for small batches so that a 320-row batch still spreads over 20 SMs; 32 rows for large ones,
+// two CTAs per SM (128 registers, 70 KB shared memory each): 16 warps per SM hide the L2 / HMMA latencies that one 64-row
+// CTA per SM (8 warps) exposes -- batch 4096: 1 025 -> 1 304 updates/s.  MOBODY_TRAIN_TM=64 selects the old tiling (A/B).
+static int pick_tm(int N) {
+  static const int big = [] { const char* e = getenv("MOBODY_TRAIN_TM"); const int v = e ? atoi(e) : 32; return v == 64 ? 64 : 32; }();
+  return N >= 148 * 32 ? big : 16;
+}
 template <typename K> static const char* set_smem(K kern, size_t bytes) {
   if (bytes > 227 * 1024) return "train step: shared memory budget exceeded for this (S, A)";
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) return "cudaFuncSetAttribute failed";
@@ -796,9 +801,9 @@ template <typename K> static const char* set_smem(K kern, size_t bytes) {
 const char* mb_train_critic_launch(const trn::CriticArgs& a, cudaStream_t st) {
   const int tm = pick_tm(a.N), ntiles = (a.N + tm - 1) / tm;
   const size_t bytes = (2 * (size_t)tm * simt::H + (size_t)tm * simt::rup16(a.S + a.A) + 2 * tm + 8) * sizeof(float);
-  auto k1 = tm == 64 ? trn::critic_fwd_kernel<8> : trn::critic_fwd_kernel<2>;
-  auto k2 = tm == 64 ? trn::critic_tgt_kernel<8> : trn::critic_tgt_kernel<2>;
-  auto k3 = tm == 64 ? trn::critic_bwd_kernel<8> : trn::critic_bwd_kernel<2>;
+  auto k1 = tm == 64 ? trn::critic_fwd_kernel<8> : tm == 32 ? trn::critic_fwd_kernel<4> : trn::critic_fwd_kernel<2>;
+  auto k2 = tm == 64 ? trn::critic_tgt_kernel<8> : tm == 32 ? trn::critic_tgt_kernel<4> : trn::critic_tgt_kernel<2>;
+  auto k3 = tm == 64 ? trn::critic_bwd_kernel<8> : tm == 32 ? trn::critic_bwd_kernel<4> : trn::critic_bwd_kernel<2>;
   if (const char* e = set_smem(k1, bytes)) return e;
   if (const char* e = set_smem(k2, bytes)) return e;
   if (const char* e = set_smem(k3, bytes)) return e;
@@ -810,7 +815,7 @@ const char* mb_train_critic_launch(const trn::CriticArgs& a, cudaStream_t st) {
 const char* mb_train_actor_launch(const trn::ActorArgs& a, cudaStream_t st) {
   const int tm = pick_tm(a.N), ntiles = (a.N + tm - 1) / tm;
   const size_t bytes = (2 * (size_t)tm * simt::H + (size_t)tm * simt::rup16(a.S + a.A) + 2 * tm + (size_t)tm * a.A + 8) * sizeof(float);
-  auto k2 = tm == 64 ? trn::actor_q_kernel<8> : trn::actor_q_kernel<2>;
+  auto k2 = tm == 64 ? trn::actor_q_kernel<8> : tm == 32 ? trn::actor_q_kernel<4> : trn::actor_q_kernel<2>;
   if (const char* e = set_smem(k2, bytes)) return e;
   mb_launch(k2, dim3(ntiles, 4), dim3(simt::NT), bytes, st, a);
   return nullptr;
@@ -818,7 +823,7 @@ const char* mb_train_actor_launch(const trn::ActorArgs& a, cudaStream_t st) {
 const char* mb_train_policy_bwd_launch(const trn::PolicyBwdArgs& a, cudaStream_t st) {
   const int tm = pick_tm(a.N);
   size_t bytes = (2 * (size_t)tm * simt::H + (size_t)tm * simt::rup16(a.A) + tm + 40) * sizeof(float);
-  auto kern = tm == 64 ? trn::policy_bwd_kernel<8> : trn::policy_bwd_kernel<2>;
+  auto kern = tm == 64 ? trn::policy_bwd_kernel<8> : tm == 32 ? trn::policy_bwd_kernel<4> : trn::policy_bwd_kernel<2>;
   if (const char* e = set_smem(kern, bytes)) return e;
   mb_launch(kern, dim3((a.N + tm - 1) / tm), dim3(simt::NT), bytes, st, a);
   return nullptr;
@@ -993,7 +998,7 @@ const char* mb_classifier_step_launch(const mobody_classifier_desc& d, cudaStrea
   c.part = ws + w.part;
   const int tm = pick_tm(N);
   const size_t bytes = (2 * (size_t)tm * simt::H + (size_t)tm * simt::rup16(2 * S + A) + 4 * tm + 8) * sizeof(float);
-  auto kern = tm == 64 ? trn::classifier_kernel<8> : trn::classifier_kernel<2>;
+  auto kern = tm == 64 ? trn::classifier_kernel<8> : tm == 32 ? trn::classifier_kernel<4> : trn::classifier_kernel<2>;
   if (const char* e = set_smem(kern, bytes)) return e;
   const int ntiles = (N + tm - 1) / tm;
   mb_launch(kern, dim3(ntiles), dim3(simt::NT), bytes, st, c);

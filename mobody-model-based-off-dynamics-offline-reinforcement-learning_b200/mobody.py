@@ -368,8 +368,11 @@ class MOBODY(object):
         d = _ffi.ClassifierDesc()
         d.rows, d.N, d.S, d.A, d.row_width = _ffi.ptr(rows), N, S, A, rows.shape[1]
         d.label = _ffi.ptr(label)
-        d.noise_sas = _ffi.ptr(None if noise_sas is None else _ffi.f32(noise_sas, self.device))
-        d.noise_sa = _ffi.ptr(None if noise_sa is None else _ffi.f32(noise_sa, self.device))
+        # injected draws: the device copies must stay referenced until the launch is enqueued (a dropped temporary's block
+        # is handed to the very next allocation by the caching allocator)
+        noise_sas = None if noise_sas is None else _ffi.f32(noise_sas, self.device)
+        noise_sa = None if noise_sa is None else _ffi.f32(noise_sa, self.device)
+        d.noise_sas, d.noise_sa = _ffi.ptr(noise_sas), _ffi.ptr(noise_sa)
         d.noise_std, d.seed, d.draw = float(self.classifier.gaussian_noise_std), int(cfg.get("seed", 0)), self._t_cls
         cl = self.classifier
         d.sas, d.sa = _ffi.mlp_state(_ffi.mlp_tensors(cl.sas_classifier)), _ffi.mlp_state(_ffi.mlp_tensors(cl.sa_classifier))
