@@ -1,5 +1,6 @@
 """Smallest end-to-end case for compute-sanitizer: one fused step per precision, one 2-step rollout, one train step,
-one classifier step.  Run as:  compute-sanitizer --tool memcheck python scripts/sanitize_case.py"""
+one classifier step, small, ragged and large (32-row-tile) batches.  Run plain (prints finite losses) or under
+compute-sanitizer --tool memcheck where the pool allows it."""
 import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -25,7 +26,10 @@ for b, n in ((src, 4000), (tar, 1000), (ag.fake_replay_buffer, 2000)):
                  "terminals": np.zeros((n, 1), np.float32)})
 ag.total_it = 1
 ag.train(src, tar, 64)
+ag.train(src, tar, 2048)            # 5 120 rows: 32-row tiles (two CTAs per SM), tensor-core weight gradients, 27 row splits
+ag.train(src, tar, 31)              # ragged: 77 rows
 ag.update_classifier(src, tar, 64)
+ag.update_classifier(src, tar, 2500)
 ag.dara_relabel(src)
 torch.cuda.synchronize()
 print("ok", ag.loss_scalars()["q_loss"])
