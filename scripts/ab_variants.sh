@@ -1,4 +1,5 @@
-for v in base f p2 p2f p4 p4f; do
+# A/B of library variants on the rollout (build them first: python scripts/build_variant.py NAME -D...):  bash scripts/ab_variants.sh
+for v in "$@"; do
   export MOBODY_B200_LIB=$PWD/variants/$v/libmobody_b200.so
   echo "=== $v" >> gpurun_out/ab1.log
   python scripts/tc_debug.py 2>&1 | grep "^bf16x2" >> gpurun_out/ab1.log
