@@ -165,3 +165,50 @@ def test_weight_gradient_row_splits_agree(S, A, N, n_true):
         other = run(nsplit)
         for k in base:
             adam_close(other[k], base[k], 3e-4, 2, (nsplit, k))
+
+
+_PARAM_DIGEST = r"""
+import hashlib, sys, os
+sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+import numpy as np, torch
+from helpers import cuda_agent
+from mobody_b200 import _ffi
+h = hashlib.sha256()
+for S, A, N, n_true, steps in ((17, 6, 320, 256, 30), (27, 8, 5120, 4096, 6)):
+    rng = np.random.default_rng(N)
+    RW = _ffi.lib().mobody_row_width(S, A)
+    rows = np.zeros((N, RW), np.float32)
+    rows[:, :2 * S + A + 1] = rng.standard_normal((N, 2 * S + A + 1)).astype(np.float32)
+    rows[:, S:S + A] = rng.uniform(-1, 1, (N, A)).astype(np.float32)
+    rows[:, 2 * S + A + 1] = (rng.random(N) > 0.1).astype(np.float32)
+    rows_d = torch.from_numpy(rows).cuda()
+    ag, _ = cuda_agent(S, A, 9)
+    for _ in range(steps):
+        ag.train_on_rows(rows_d, n_true)
+    torch.cuda.synchronize()
+    for m in (ag.policy, ag.q_funcs, ag.target_q_funcs):
+        for v in m.state_dict().values():
+            h.update(v.detach().cpu().numpy().tobytes())
+    h.update(np.asarray(list(ag.loss_scalars().values()), np.float32).tobytes())
+print("DIGEST", h.hexdigest())
+"""
+
+
+def test_launch_mode_and_tiling_switches_in_subprocess():
+    """The update is a chain of kernels with fixed-order reductions, so how the chain is LAUNCHED must not change a bit of
+    it: programmatic dependent launch on / off (MOBODY_PDL) give identical parameters and losses after 30 small-batch and
+    6 large-batch updates (a missing grid dependency would show up as a difference).  The 64-row tiling
+    (MOBODY_TRAIN_TM=64) changes summation order only; here it is only required to run (its parity is the same kernels'
+    parity at another template argument, covered by the small-batch cases)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def digest(**env):
+        r = subprocess.run([sys.executable, "-c", _PARAM_DIGEST], env=dict(os.environ, **env), capture_output=True, text=True,
+                           timeout=300, cwd=root)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        return [ln.split()[1] for ln in r.stdout.splitlines() if ln.startswith("DIGEST")][0]
+
+    assert digest(MOBODY_PDL="1") == digest(MOBODY_PDL="0")
+    assert len(digest(MOBODY_TRAIN_TM="64")) == 64
