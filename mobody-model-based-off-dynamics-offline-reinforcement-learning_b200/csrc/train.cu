@@ -785,12 +785,14 @@ __global__ void __launch_bounds__(NT, 1) dara_relabel_kernel(RelabelArgs a) {
 }  // namespace trn
 
 // ---------------- host launchers ----------------
-// Row tile: 16 rows per CTA for small batches so that a 320-row batch still spreads over 20 SMs; 32 rows for large ones,
+// Row tile: 16 rows per CTA for small batches so that a 320-row batch still spreads over 20 SMs; 32 rows once the 16-row
+// tiles would exceed one CTA per SM (>= 2 368 rows; measured cross-over between 1 280 and 2 560 rows, MOBODY_TRAIN_TM_ROWS),
 // two CTAs per SM (128 registers, 70 KB shared memory each): 16 warps per SM hide the L2 / HMMA latencies that one 64-row
 // CTA per SM (8 warps) exposes -- batch 4096: 1 025 -> 1 304 updates/s.  MOBODY_TRAIN_TM=64 selects the old tiling (A/B).
 static int pick_tm(int N) {
   static const int big = [] { const char* e = getenv("MOBODY_TRAIN_TM"); const int v = e ? atoi(e) : 32; return v == 64 ? 64 : 32; }();
-  return N >= 148 * 32 ? big : 16;
+  static const int min_rows = [] { const char* e = getenv("MOBODY_TRAIN_TM_ROWS"); return e ? atoi(e) : 148 * 16; }();
+  return N >= min_rows ? big : 16;
 }
 template <typename K> static const char* set_smem(K kern, size_t bytes) {
   if (bytes > 227 * 1024) return "train step: shared memory budget exceeded for this (S, A)";
