@@ -359,7 +359,7 @@ class MOBODY(object):
         cfg = self.config
         S, A = cfg["state_dim"], cfg["action_dim"]
         N = rows.shape[0]
-        nsplit = _wgrad_splits(N, (20,), self.device)
+        nsplit = _wgrad_splits(N, (16 + 2 * ((2 * S + A + 63) // 64) + 2 * ((S + A + 63) // 64),), self.device)
         lib = _ffi.lib()
         need = int(lib.mobody_classifier_workspace_bytes(N, S, A, nsplit))
         if self._cls_ws is None or self._cls_ws.numel() < need:
@@ -431,7 +431,9 @@ class MOBODY(object):
         S, A = cfg["state_dim"], cfg["action_dim"]
         N = rows.shape[0]
         if nsplit is None:
-            nsplit = _wgrad_splits(N, (20, 10), self.device)   # row splits of the weight-gradient GEMMs (partials summed in Adam, fixed order)
+            # row splits of the weight-gradient GEMMs (partials summed in Adam, fixed order); 128 x 64 tiles per split:
+            # critic 2 x (256 x 256 -> 8, 256 x (S+A) -> 2 per 64 columns), actor 8 + 2 per 64 columns of S
+            nsplit = _wgrad_splits(N, (2 * (8 + 2 * ((S + A + 63) // 64)), 8 + 2 * ((S + 63) // 64)), self.device)
         lib = _ffi.lib()
         need = int(lib.mobody_train_workspace_bytes(N, S, A, nsplit))
         if self._train_ws is None or self._train_ws.numel() < need:
