@@ -148,12 +148,20 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
   lo = __float_as_uint(v - __uint_as_float(hi)) + 0x1000u;
 }
 
+// [rows][256] activation tiles in shared memory are stored SWIZZLED: the 16-byte group index of a column is XORed with a
+// 3-bit function of the row, so that (a) the two rows a quarter-warp reads in one 128-bit A-fragment load and (b) the
+// eight rows a warp writes in one C-fragment store fall into different banks (row pitch 1 KB = same banks otherwise:
+// 2-way conflicts on every A load, 8-way on every epilogue store).  XOR within a 128-byte segment: an involution that
+// keeps float2 / float4 groups intact.  Every accessor of such a tile goes through swz().
+__device__ __forceinline__ int swz(int r, int c) { return c ^ ((((r & 1) << 2) | ((r >> 1) & 3)) << 2); }
+
 // Operand slots are permuted so that every global / shared load is a 128-bit vector (the contraction does not care
 // which actual k sits in which k-slot as long as A and B agree, and the epilogue knows which column an n-slot is):
 //   k16 block, thread (g, t): actual k = kb + 4t + i, i = 0..3; MMA #0 takes i = 0 (slot t) and 1 (slot t+4), MMA #1
 //   takes i = 2, 3.  A: one LDS.128 per row.  B, nn.Linear [out][in] (WT): one LDG.128 per n-tile along k.
 //   B, [k][256] row-major (!WT): n-slot g of tile nt is column n0 + 4g + nt, one LDG.128 along n per actual k.
-template <bool WT, int RPT = 8>
+// SWX: Xs is a swizzled [rows][256] tile (ldx = H); otherwise a plain staging buffer.  Ys is always a swizzled tile.
+template <bool WT, int RPT = 8, bool SWX = false>
 __device__ void big_layer_mma(const float* __restrict__ Xs, int ldx, int K, const float* __restrict__ Wg,
                               const float* __restrict__ bias, float* __restrict__ Ys, int act) {
   constexpr int MT = RPT / 2;                                  // 16-row m-tiles of the 8*RPT-row tile
@@ -210,8 +218,9 @@ __device__ void big_layer_mma(const float* __restrict__ Xs, int ldx, int K, cons
     const int k0 = blk * 16 + 4 * t;
 #pragma unroll
     for (int m = 0; m < MT; ++m) {
-      const float4 x0 = *reinterpret_cast<const float4*>(Xs + (size_t)(m * 16 + g) * ldx + k0);
-      const float4 x1 = *reinterpret_cast<const float4*>(Xs + (size_t)(m * 16 + g + 8) * ldx + k0);
+      const int r0 = m * 16 + g, r1 = r0 + 8;
+      const float4 x0 = *reinterpret_cast<const float4*>(Xs + (size_t)r0 * ldx + (SWX ? swz(r0, k0) : k0));
+      const float4 x1 = *reinterpret_cast<const float4*>(Xs + (size_t)r1 * ldx + (SWX ? swz(r1, k0) : k0));
       const float xr0[4] = {x0.x, x0.y, x0.z, x0.w}, xr1[4] = {x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
       for (int h2 = 0; h2 < 2; ++h2) {                          // the two k8 MMAs of the block: i = 2 h2, 2 h2 + 1
@@ -241,7 +250,8 @@ __device__ void big_layer_mma(const float* __restrict__ Xs, int ldx, int K, cons
       for (int j = 0; j < 4; ++j) {                             // C fragment: row g + 8 (j >> 1), n-slot 2t + (j & 1)
         const int slot = 2 * t + (j & 1);
         const int c = WT ? (n0 + nt * 8 + slot) : (n0 + 4 * slot + nt);
-        float* p = Ys + (size_t)(m * 16 + g + 8 * (j >> 1)) * H + c;
+        const int row = m * 16 + g + 8 * (j >> 1);
+        float* p = Ys + (size_t)row * H + swz(row, c);
         const float a = acc[m][nt][j];
         if (act == ACT_MASK) *p = (*p > 0.f) ? a : 0.f;
         else *p = apply_act(a + __ldg(bias + c), act, 1.f);
@@ -250,31 +260,32 @@ __device__ void big_layer_mma(const float* __restrict__ Xs, int ldx, int K, cons
 }
 
 // Narrow layers (N <= 32 or so): one thread per (row, column).  W is [K][ldw] (or [N][K] if WT).
-template <bool WT, int RPT = 8>
+template <bool WT, int RPT = 8, bool SWZ = false>
 __device__ void small_layer(const float* __restrict__ Xs, int ldx, int K, const float* __restrict__ Wg, int ldw,
                             const float* __restrict__ bias, int N, float* __restrict__ Ys, int ldy, int act,
                             float scale) {
   for (int idx = threadIdx.x; idx < 8 * RPT * N; idx += NT) {
     int r = idx / N, n = idx - r * N;
     const float* x = Xs + (size_t)r * ldx;
+    auto xi = [&](int k) { return SWZ ? swz(r, k) : k; };     // k is a multiple of 4 in the unrolled loops: the group stays intact
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
     int k = 0;
     if (!WT) {
       const float* w = Wg + n;
       for (; k + 4 <= K; k += 4) {
-        a0 = fmaf(x[k], __ldg(w + (size_t)k * ldw), a0);
-        a1 = fmaf(x[k + 1], __ldg(w + (size_t)(k + 1) * ldw), a1);
-        a2 = fmaf(x[k + 2], __ldg(w + (size_t)(k + 2) * ldw), a2);
-        a3 = fmaf(x[k + 3], __ldg(w + (size_t)(k + 3) * ldw), a3);
+        a0 = fmaf(x[xi(k)], __ldg(w + (size_t)k * ldw), a0);
+        a1 = fmaf(x[xi(k) + 1], __ldg(w + (size_t)(k + 1) * ldw), a1);
+        a2 = fmaf(x[xi(k) + 2], __ldg(w + (size_t)(k + 2) * ldw), a2);
+        a3 = fmaf(x[xi(k) + 3], __ldg(w + (size_t)(k + 3) * ldw), a3);
       }
-      for (; k < K; ++k) a0 = fmaf(x[k], __ldg(w + (size_t)k * ldw), a0);
+      for (; k < K; ++k) a0 = fmaf(x[xi(k)], __ldg(w + (size_t)k * ldw), a0);
     } else {
       const float* w = Wg + (size_t)n * ldw;
       for (; k + 4 <= K; k += 4) {
-        a0 = fmaf(x[k], __ldg(w + k), a0); a1 = fmaf(x[k + 1], __ldg(w + k + 1), a1);
-        a2 = fmaf(x[k + 2], __ldg(w + k + 2), a2); a3 = fmaf(x[k + 3], __ldg(w + k + 3), a3);
+        a0 = fmaf(x[xi(k)], __ldg(w + k), a0); a1 = fmaf(x[xi(k) + 1], __ldg(w + k + 1), a1);
+        a2 = fmaf(x[xi(k) + 2], __ldg(w + k + 2), a2); a3 = fmaf(x[xi(k) + 3], __ldg(w + k + 3), a3);
       }
-      for (; k < K; ++k) a0 = fmaf(x[k], __ldg(w + k), a0);
+      for (; k < K; ++k) a0 = fmaf(x[xi(k)], __ldg(w + k), a0);
     }
     float v = ((a0 + a1) + (a2 + a3)) + (bias ? __ldg(bias + n) : 0.0f);
     Ys[(size_t)r * ldy + n] = apply_act(v, act, scale);

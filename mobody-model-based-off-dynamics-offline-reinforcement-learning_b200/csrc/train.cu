@@ -56,18 +56,18 @@ struct ActorArgs {
 
 template <int TMv>
 __device__ __forceinline__ void store_tile(const float* __restrict__ Xs, float* __restrict__ g, int row0, int rows) {
-  // [64][256] smem tile -> global [N][256], 128-bit stores
+  // swizzled [TM][256] smem tile -> global [N][256] (plain), 128-bit stores
   for (int i = threadIdx.x; i < rows * (H / 4); i += NT) {
     int r = i / (H / 4), c = i - r * (H / 4);
-    reinterpret_cast<float4*>(g + (size_t)(row0 + r) * H)[c] = reinterpret_cast<const float4*>(Xs + r * H)[c];
+    reinterpret_cast<float4*>(g + (size_t)(row0 + r) * H)[c] = *reinterpret_cast<const float4*>(Xs + r * H + swz(r, 4 * c));
   }
 }
 template <int TMv>
 __device__ __forceinline__ void load_tile(float* __restrict__ Xs, const float* __restrict__ g, int row0, int rows) {
   for (int i = threadIdx.x; i < TMv * (H / 4); i += NT) {
     int r = i / (H / 4), c = i - r * (H / 4);
-    reinterpret_cast<float4*>(Xs + r * H)[c] = r < rows ? reinterpret_cast<const float4*>(g + (size_t)(row0 + r) * H)[c]
-                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(Xs + r * H + swz(r, 4 * c)) = r < rows ? reinterpret_cast<const float4*>(g + (size_t)(row0 + r) * H)[c]
+                                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
 
@@ -79,7 +79,7 @@ __device__ __forceinline__ void q_head(const float* __restrict__ X1, const float
   const int r = threadIdx.x / TPR, q = threadIdx.x % TPR;
   const float* x = X1 + r * H;
   float s = 0.f;
-  for (int k = q; k < H; k += TPR) s = fmaf(x[k], __ldg(w + k), s);
+  for (int k = q; k < H; k += TPR) s = fmaf(x[swz(r, k)], __ldg(w + k), s);
 #pragma unroll
   for (int o = 1; o < TPR; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if (q == 0) out[r] = s + __ldg(b);
@@ -90,7 +90,7 @@ __device__ __forceinline__ void q_head(const float* __restrict__ X1, const float
 template <int TMv>
 __device__ __forceinline__ void head_backward(float* __restrict__ X1, const float* __restrict__ w, const float* __restrict__ g) {
   for (int i = threadIdx.x; i < TMv * H; i += NT) {
-    int r = i >> 8, n = i & 255;
+    int r = i >> 8, n = swz(r, i & 255);                        // i is a physical position; n its logical column
     X1[i] = X1[i] > 0.f ? g[r] * __ldg(w + n) : 0.f;
   }
   __syncthreads();
@@ -117,20 +117,20 @@ __global__ void __launch_bounds__(NT, RPT == 4 ? 2 : 1) critic_fwd_kernel(Critic
   if (role == 3) {
     big_layer_mma<true, RPT>(in_s, ldi, S, a.pi.w[0], a.pi.b[0], X0, ACT_RELU);
     store_tile<TM>(X0, a.Hp[0], row0, rows);
-    big_layer_mma<true, RPT>(X0, H, H, a.pi.w[1], a.pi.b[1], X1, ACT_RELU);
+    big_layer_mma<true, RPT, true>(X0, H, H, a.pi.w[1], a.pi.b[1], X1, ACT_RELU);
     store_tile<TM>(X1, a.Hp[1], row0, rows);
-    small_layer<true, RPT>(X1, H, H, a.pi.w[2], H, a.pi.b[2], A, in_s, ldi, ACT_TANH, a.max_action);
+    small_layer<true, RPT, true>(X1, H, H, a.pi.w[2], H, a.pi.b[2], A, in_s, ldi, ACT_TANH, a.max_action);
     for (int i = tid; i < rows * A; i += NT) { const int r = i / A, j = i - r * A; a.api[(size_t)(row0 + r) * A + j] = in_s[r * ldi + j]; }
   } else if (role == 0) {
     big_layer_mma<true, RPT>(in_s, ldi, S, a.pi.w[0], a.pi.b[0], X0, ACT_RELU);
-    big_layer_mma<true, RPT>(X0, H, H, a.pi.w[1], a.pi.b[1], X1, ACT_RELU);
-    small_layer<true, RPT>(X1, H, H, a.pi.w[2], H, a.pi.b[2], A, in_s, ldi, ACT_TANH, a.max_action);
+    big_layer_mma<true, RPT, true>(X0, H, H, a.pi.w[1], a.pi.b[1], X1, ACT_RELU);
+    small_layer<true, RPT, true>(X1, H, H, a.pi.w[2], H, a.pi.b[2], A, in_s, ldi, ACT_TANH, a.max_action);
     for (int i = tid; i < rows * A; i += NT) { const int r = i / A, j = i - r * A; a.a2[(size_t)(row0 + r) * A + j] = in_s[r * ldi + j]; }
   } else {
     const int k = role - 1;
     big_layer_mma<true, RPT>(in_s, ldi, S + A, a.q[k].w[0], a.q[k].b[0], X0, ACT_RELU);
     store_tile<TM>(X0, a.Hq[k][0], row0, rows);
-    big_layer_mma<true, RPT>(X0, H, H, a.q[k].w[1], a.q[k].b[1], X1, ACT_RELU);
+    big_layer_mma<true, RPT, true>(X0, H, H, a.q[k].w[1], a.q[k].b[1], X1, ACT_RELU);
     store_tile<TM>(X1, a.Hq[k][1], row0, rows);
     q_head<TM>(X1, a.q[k].w[2], a.q[k].b[2], qa);
     if (tid < rows) a.qk[k][row0 + tid] = qa[tid];
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(NT, RPT == 4 ? 2 : 1) critic_tgt_kernel(Critic
   }
   __syncthreads();
   big_layer_mma<true, RPT>(in_s, ldi, S + A, a.qt[k].w[0], a.qt[k].b[0], X0, ACT_RELU);
-  big_layer_mma<true, RPT>(X0, H, H, a.qt[k].w[1], a.qt[k].b[1], X1, ACT_RELU);
+  big_layer_mma<true, RPT, true>(X0, H, H, a.qt[k].w[1], a.qt[k].b[1], X1, ACT_RELU);
   q_head<TM>(X1, a.qt[k].w[2], a.qt[k].b[2], qa);
   if (tid < rows) a.qtk[k][row0 + tid] = qa[tid];
 }
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(NT, RPT == 4 ? 2 : 1) critic_bwd_kernel(Critic
   __syncthreads();
   head_backward<TM>(X1, a.q[k].w[2], g3);                     // dH2 (masked)
   store_tile<TM>(X1, a.Dq[k][1], row0, rows);
-  big_layer_mma<false, RPT>(X1, H, H, a.q[k].w[1], nullptr, X0, ACT_MASK);   // dH1 = (dH2 W2) * 1[H1>0], in place on H1
+  big_layer_mma<false, RPT, true>(X1, H, H, a.q[k].w[1], nullptr, X0, ACT_MASK);   // dH1 = (dH2 W2) * 1[H1>0], in place on H1
   store_tile<TM>(X0, a.Dq[k][0], row0, rows);
   // tile partial sums in a fixed order (deterministic): threads 0..TM-1 hold one row each
   if (tid < 4) redbuf[tid] = 0.f;
@@ -291,19 +291,19 @@ __global__ void __launch_bounds__(NT, RPT == 4 ? 2 : 1) actor_q_kernel(ActorArgs
   __syncthreads();
   if (qhat) {
     big_layer_mma<true, RPT>(sap_s, ldi, S + A, a.q[k].w[0], a.q[k].b[0], X0, ACT_RELU);
-    big_layer_mma<true, RPT>(X0, H, H, a.q[k].w[1], a.q[k].b[1], X1, ACT_RELU);
+    big_layer_mma<true, RPT, true>(X0, H, H, a.q[k].w[1], a.q[k].b[1], X1, ACT_RELU);
     q_head<TM>(X1, a.q[k].w[2], a.q[k].b[2], qa);
     if (tid < rows && row0 + tid < a.n_true) a.qh[k][row0 + tid] = qa[tid];
     actor_finish(a, sm);
     return;
   }
   big_layer_mma<true, RPT>(sap_s, ldi, S + A, a.q[k].w[0], a.q[k].b[0], X0, ACT_RELU);
-  big_layer_mma<true, RPT>(X0, H, H, a.q[k].w[1], a.q[k].b[1], X1, ACT_RELU);
+  big_layer_mma<true, RPT, true>(X0, H, H, a.q[k].w[1], a.q[k].b[1], X1, ACT_RELU);
   q_head<TM>(X1, a.q[k].w[2], a.q[k].b[2], qa);
   head_backward<TM>(X1, a.q[k].w[2], ones);
-  big_layer_mma<false, RPT>(X1, H, H, a.q[k].w[1], nullptr, X0, ACT_MASK);
+  big_layer_mma<false, RPT, true>(X1, H, H, a.q[k].w[1], nullptr, X0, ACT_MASK);
   // d q / d a_j = sum_n dH1[n] * W1[n][S+j]
-  small_layer<false, RPT>(X0, H, H, a.q[k].w[0] + S, S + A, nullptr, A, gk, A, ACT_NONE, 1.f);
+  small_layer<false, RPT, true>(X0, H, H, a.q[k].w[0] + S, S + A, nullptr, A, gk, A, ACT_NONE, 1.f);
   for (int i = tid; i < rows * A; i += NT) a.gak[k][(size_t)row0 * A + i] = gk[i];
   if (tid < rows) a.qv[k][row0 + tid] = qa[tid];
   actor_finish(a, sm);
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(NT, RPT == 4 ? 2 : 1) policy_bwd_kernel(Policy
   __syncthreads();
   big_layer_mma<false, RPT>(d3, lda, a.A, a.pi.w[2], nullptr, X1, ACT_MASK);    // W3 is [A][256]: dH2[r][i] = sum_j d3[r][j] W3[j][i]
   store_tile<TM>(X1, a.Dp[1], row0, rows);
-  big_layer_mma<false, RPT>(X1, H, H, a.pi.w[1], nullptr, X0, ACT_MASK);
+  big_layer_mma<false, RPT, true>(X1, H, H, a.pi.w[1], nullptr, X0, ACT_MASK);
   store_tile<TM>(X0, a.Dp[0], row0, rows);
   // last CTA: logging scalars in tile order
   __shared__ int last;
@@ -685,9 +685,9 @@ __global__ void __launch_bounds__(NT, RPT == 4 ? 2 : 1) classifier_kernel(ClsArg
     __syncthreads();
     big_layer_mma<true, RPT>(in_s, ld, K, a.net[k].w[0], a.net[k].b[0], X0, ACT_RELU);
     store_tile<TM>(X0, a.Hc[k][0], row0, rows);
-    big_layer_mma<true, RPT>(X0, H, H, a.net[k].w[1], a.net[k].b[1], X1, ACT_RELU);
+    big_layer_mma<true, RPT, true>(X0, H, H, a.net[k].w[1], a.net[k].b[1], X1, ACT_RELU);
     store_tile<TM>(X1, a.Hc[k][1], row0, rows);
-    small_layer<true, RPT>(X1, H, H, a.net[k].w[2], H, a.net[k].b[2], 2, z_s, 2, ACT_NONE, 1.f);
+    small_layer<true, RPT, true>(X1, H, H, a.net[k].w[2], H, a.net[k].b[2], 2, z_s, 2, ACT_NONE, 1.f);
     if (tid < TM) {
       float g0 = 0.f, g1 = 0.f;
       if (tid < rows) {
@@ -708,13 +708,13 @@ __global__ void __launch_bounds__(NT, RPT == 4 ? 2 : 1) classifier_kernel(ClsArg
     {   // relu backward of the 2-output head: dH2[r][n] = H2 > 0 ? g0 W3[0][n] + g1 W3[1][n] : 0
       const float* w3 = a.net[k].w[2];
       for (int i = tid; i < TM * H; i += NT) {
-        const int r = i >> 8, n = i & 255;
+        const int r = i >> 8, n = swz(r, i & 255);
         X1[i] = X1[i] > 0.f ? g_s[2 * r] * __ldg(w3 + n) + g_s[2 * r + 1] * __ldg(w3 + H + n) : 0.f;
       }
       __syncthreads();
     }
     store_tile<TM>(X1, a.Dc[k][1], row0, rows);
-    big_layer_mma<false, RPT>(X1, H, H, a.net[k].w[1], nullptr, X0, ACT_MASK);
+    big_layer_mma<false, RPT, true>(X1, H, H, a.net[k].w[1], nullptr, X0, ACT_MASK);
     store_tile<TM>(X0, a.Dc[k][0], row0, rows);
     __syncthreads();
   }
@@ -761,8 +761,8 @@ __global__ void __launch_bounds__(NT, 1) dara_relabel_kernel(RelabelArgs a) {
       }
       __syncthreads();
       big_layer_mma<true, RPT>(in_s, ld, K, a.net[k].w[0], a.net[k].b[0], X0, ACT_RELU);
-      big_layer_mma<true, RPT>(X0, H, H, a.net[k].w[1], a.net[k].b[1], X1, ACT_RELU);
-      small_layer<true, RPT>(X1, H, H, a.net[k].w[2], H, a.net[k].b[2], 2, z_s + k * 2 * TM, 2, ACT_NONE, 1.f);
+      big_layer_mma<true, RPT, true>(X0, H, H, a.net[k].w[1], a.net[k].b[1], X1, ACT_RELU);
+      small_layer<true, RPT, true>(X1, H, H, a.net[k].w[2], H, a.net[k].b[2], 2, z_s + k * 2 * TM, 2, ACT_NONE, 1.f);
     }
     if (tid < rows) {
       float lp[2][2];
