@@ -16,8 +16,12 @@ N_DYN_LAYERS = 13
 DYN_LAYER_NAMES = ("zs1", "zs2", "zs3", "za_src1", "za_src2", "za_trg1", "za_trg2",
                    "transition1", "transition2", "transition3",
                    "reward_model1", "reward_model2", "reward_model3")
-PREC = {"fp32": 0, "bf16x2": 1, "bf16": 2, "fp16": 3}
-ENABLED_PRECISIONS = ("fp32", "bf16x2", "bf16", "fp16")
+# fp32: CUDA-core kernel; bf16x2: tcgen05 hi+lo split, inside the 1e-4 bound (default); fp16: tcgen05 single pass, inside the
+# stated looser bound 5e-3.  The library's single-pass bf16 mode (code 2, measured 1.6e-2) is outside every stated bound:
+# it is a kernel-development diagnostic and is not offered here.
+PREC = {"fp32": 0, "bf16x2": 1, "fp16": 3}
+ENABLED_PRECISIONS = ("fp32", "bf16x2", "fp16")
+ABI_VERSION = 2
 KEEP_U8_ZERO, KEEP_F32_LE, KEEP_F32_LT, KEEP_U8_VALID = 0, 1, 2, 3
 
 
@@ -31,7 +35,7 @@ class MlpParams(C.Structure):
 
 class StepDesc(C.Structure):
     _fields_ = [
-        ("precision", C.c_int), ("B", C.c_int), ("S", C.c_int), ("A", C.c_int),
+        ("precision", C.c_int), ("B", C.c_int), ("S", C.c_int), ("A", C.c_int), ("obs_ld", C.c_int), ("act_ld", C.c_int),
         ("n_rows_dev", C.c_void_p), ("row_ids", C.c_void_p),
         ("obs", C.c_void_p), ("act", C.c_void_p),
         ("policy", C.POINTER(MlpParams)), ("max_action", C.c_float),
@@ -104,6 +108,7 @@ def lib():
         L.mobody_compact_scratch_ints.argtypes = [C.c_longlong]
         L.mobody_row_width.argtypes = [C.c_int, C.c_int]
         L.mobody_step.argtypes = [C.POINTER(StepDesc), C.c_void_p]
+        L.mobody_rollout_stats_doubles.restype = C.c_int
         L.mobody_rollout.argtypes = [C.POINTER(RolloutDesc), C.c_void_p]
         L.mobody_policy_forward.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(MlpParams), C.c_float,
                                             C.c_void_p, C.c_void_p]
@@ -114,6 +119,8 @@ def lib():
         L.mobody_pack_rows.argtypes = [C.c_void_p] * 5 + [C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.mobody_ring_insert.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_longlong, C.c_longlong,
                                          C.c_void_p, C.c_void_p]
+        L.mobody_ring_insert_transitions.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_longlong,
+                                                     C.c_void_p, C.c_void_p]
         L.mobody_compact.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_float, C.c_longlong, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p]
         L.mobody_gather_pos.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p,
@@ -121,10 +128,11 @@ def lib():
         L.mobody_gather_pos_i64.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]
         L.mobody_dyn_pack_bytes.restype = C.c_longlong
         L.mobody_dyn_pack_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
-        L.mobody_dyn_pack.argtypes = [C.POINTER(DynParams), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.mobody_dyn_pack.argtypes = [C.POINTER(DynParams), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.mobody_mlp_pack_bytes.restype = C.c_longlong
         L.mobody_mlp_pack_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
-        L.mobody_mlp_pack.argtypes = [C.POINTER(MlpParams), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.mobody_mlp_pack.argtypes = [C.POINTER(MlpParams), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.mobody_par_penalty.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]
         L.mobody_train_workspace_bytes.restype = C.c_longlong
         L.mobody_train_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
         L.mobody_train_step.argtypes = [C.POINTER(TrainDesc), C.c_void_p]
@@ -134,8 +142,7 @@ def lib():
         L.mobody_dara_relabel.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.POINTER(MlpParams),
                                           C.POINTER(MlpParams), C.c_float, C.c_void_p, C.c_void_p]
         L.mobody_selftest_umma.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
-        L.mobody_selftest_umma2.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
-        if L.mobody_abi_version() != 1:
+        if L.mobody_abi_version() != ABI_VERSION:
             raise RuntimeError("mobody_b200: ABI version mismatch between _ffi.py and libmobody_b200.so")
         _lib = L
     return _lib
@@ -197,11 +204,6 @@ def mlp_tensors(mlp):
     """[w0, b0, w1, b1, w2, b2] parameter tensors (detached views of the live storage) of an MLPNetwork."""
     net = mlp.network
     return [t.detach() for li in (0, 2, 4) for t in (net[li].weight, net[li].bias)]
-
-
-def params_version(tensors):
-    """Cheap change detector for packed weight images: storage pointers + in-place version counters."""
-    return tuple((t.data_ptr(), t._version) for t in tensors)
 
 
 def mlp_params(mlp):

@@ -15,7 +15,19 @@ from . import _ffi
 
 
 class ReplayBuffer(object):
-    def __init__(self, state_dim, action_dim, device, max_size=int(1e6), seed=0, index_source="philox"):
+    _streams = 0          # buffers created so far in this process: default Philox streams are distinct per buffer
+
+    @staticmethod
+    def stream_seed(seed, stream):
+        """32-bit Philox key of index stream ``stream`` (an int or a role name) under run seed ``seed``: buffers of one run
+        draw from independent streams, like the reference's successive np.random.randint calls (utils.py:128)."""
+        if isinstance(stream, str):
+            stream = int.from_bytes(stream.encode()[:4].ljust(4, b"\0"), "little")
+        x = (int(seed) * 0x9E3779B1 + int(stream) * 0x85EBCA77 + 0x165667B1) & 0xFFFFFFFF
+        x ^= x >> 15; x = (x * 0x2C1B3C6D) & 0xFFFFFFFF; x ^= x >> 12; x = (x * 0x297A2D39) & 0xFFFFFFFF; x ^= x >> 15
+        return x
+
+    def __init__(self, state_dim, action_dim, device, max_size=int(1e6), seed=None, index_source="philox"):
         self.S, self.A = int(state_dim), int(action_dim)
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -24,6 +36,9 @@ class ReplayBuffer(object):
         self.max_size, self.ptr, self.size = int(max_size), 0, 0
         self._rows = torch.zeros(self.max_size, self.RW, dtype=torch.float32, device=self.device)
         self.mobile = 0
+        if seed is None:                       # a stream of its own: src / tar / fake samples are independent
+            ReplayBuffer._streams += 1
+            seed = ReplayBuffer.stream_seed(0, ReplayBuffer._streams)
         self.seed, self._draw = int(seed), 0
         self.index_source = index_source       # "philox" (device) | "numpy" (np.random.randint, like the reference)
 
@@ -75,6 +90,28 @@ class ReplayBuffer(object):
         rows = self._pack(batch["obss"], batch["actions"], batch["next_obss"], batch["rewards"], batch["terminals"], True)
         self.add_packed(rows, rows.shape[0])
 
+    def add_rollout_slab(self, packed, n):
+        """add_batch (utils.py:43-92) of the first ``n`` rows of a rollout slab [obs | act | next_obs | reward | terminal |
+        penalty] (MOBODY.rollout_device): one kernel converts the row layout (not_done = 1 - terminal) and ring-inserts."""
+        n = int(n)
+        if n == 0:
+            return
+        if n > self.max_size:
+            raise ValueError(f"add_batch of {n} rows exceeds buffer capacity {self.max_size}")
+        if packed.shape[1] != 2 * self.S + self.A + 3 or not packed.is_contiguous():
+            raise ValueError("rollout slab must be contiguous [M, 2S+A+3]")
+        _ffi.check(_ffi.lib().mobody_ring_insert_transitions(_ffi.ptr(packed), n, None, self.S, self.A, self.ptr, self.max_size,
+                                                             _ffi.ptr(self._rows), _ffi.stream_ptr(self.device)))
+        self._advance(n)
+
+    def _advance(self, n):
+        end = min(self.ptr + n, self.max_size)
+        used = end - self.ptr
+        self.ptr = end % self.max_size
+        self.size = min(self.size + used, self.max_size)
+        if self.ptr == 0:
+            self.ptr = n - used
+
     def add_packed(self, rows, n, n_dev=None):
         """Ring insert of ``n`` packed device rows (single wrap, like the reference).  ``n`` is the host
         count used for ptr/size bookkeeping; ``n_dev`` optionally bounds the copy on the device."""
@@ -86,12 +123,7 @@ class ReplayBuffer(object):
             raise ValueError(f"add_batch of {n} rows exceeds buffer capacity {self.max_size}")
         _ffi.check(_ffi.lib().mobody_ring_insert(_ffi.ptr(rows), n, _ffi.ptr(n_dev), self.RW, self.ptr, self.max_size,
                                                  _ffi.ptr(self._rows), _ffi.stream_ptr(self.device)))
-        end = min(self.ptr + n, self.max_size)
-        used = end - self.ptr
-        self.ptr = end % self.max_size
-        self.size = min(self.size + used, self.max_size)
-        if self.ptr == 0:
-            self.ptr = n - used
+        self._advance(n)
 
     # ---- sampling ----
     def draw_indices(self, batch_size, ind=None):
@@ -131,5 +163,7 @@ class ReplayBuffer(object):
         n = int(np.asarray(dataset["observations"]).shape[0])
         rows = self._pack(dataset["observations"], dataset["actions"], dataset["next_observations"],
                           np.asarray(dataset["rewards"]).reshape(-1), np.asarray(dataset["terminals"]).reshape(-1), True)
+        # the dataset becomes the storage: capacity follows it, so a later add() / add_batch() (the online modes,
+        # train_mobody.py:693, 743) wraps inside the allocation instead of running past it
         self._rows = rows
-        self.size = n
+        self.size, self.max_size, self.ptr = n, max(n, 1), 0

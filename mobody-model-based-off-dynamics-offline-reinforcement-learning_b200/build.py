@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmobody_b200.so")
-SOURCES = ["api.cu", "step_simt.cu", "buffer.cu", "tc_selftest.cu", "step_tc.cu", "step_pair.cu", "step_duo.cu", "train.cu"]
+SOURCES = ["api.cu", "step_simt.cu", "buffer.cu", "tc_selftest.cu", "step_tc.cu", "step_duo.cu", "train.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 
@@ -28,19 +28,24 @@ def _stale(target, deps):
 def build(verbose=False, force=False):
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     hdrs.append(os.path.join(os.path.dirname(HERE), "include", "mobody_b200.h"))
-    objs = []
+    objs, jobs = [], []
     os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
     for src in SOURCES:
         sp = os.path.join(CSRC, src)
         obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
         if force or _stale(obj, [sp] + hdrs):
-            cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", sp, "-o", obj]
-            r = subprocess.run(cmd, capture_output=True, text=True)
+            jobs.append((src, [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", sp, "-o", obj]))
+        objs.append(obj)
+    if jobs:   # translation units are independent: compile them side by side
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
+            results = list(ex.map(lambda j: (j[0], subprocess.run(j[1], capture_output=True, text=True)), jobs))
+        for src, r in results:
             if verbose or r.returncode:
                 sys.stderr.write(r.stdout + r.stderr)
-            if r.returncode:
-                raise RuntimeError(f"nvcc failed on {src}")
-        objs.append(obj)
+        bad = [src for src, r in results if r.returncode]
+        if bad:
+            raise RuntimeError(f"nvcc failed on {', '.join(bad)}")
     if force or _stale(LIB, objs):
         cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-lcudart"]
         r = subprocess.run(cmd, capture_output=True, text=True)

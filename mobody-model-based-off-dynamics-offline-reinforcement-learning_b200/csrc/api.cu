@@ -34,15 +34,14 @@ void mb_rollout_pack_launch(const float* obss, const float* acts, const float* n
 void mb_rollout_stats_launch(const float* rews, const unsigned char* terms, long long n, double* partial, unsigned int* ticket,
                              double* stats, cudaStream_t st);
 
-const char* mb_tc_dyn_pack(const DynPtrs& dp, int S, int A, int ns, int fp16, unsigned char* blob, cudaStream_t st);
-const char* mb_tc_mlp_pack(const MlpPtrs& mp, int din, int dout, int ns, int fp16, unsigned char* blob, cudaStream_t st);
+const char* mb_tc_dyn_pack(const DynPtrs& dp, int S, int A, int ns, int fp16, unsigned char* blob, unsigned long long* state, cudaStream_t st);
+const char* mb_tc_mlp_pack(const MlpPtrs& mp, int din, int dout, int ns, int fp16, unsigned char* blob, unsigned long long* state, cudaStream_t st);
 const char* mb_tc_step_launch(const StepArgs& a, const unsigned char* dynb, const unsigned char* polb, int ns, cudaStream_t st);
-int mb_tc_use_pair();
 const char* mb_tc_duo_step_launch(const StepArgs& a, const unsigned char* dynb, const unsigned char* polb, int fp16, cudaStream_t st, bool* launched);
-const char* mb_tc_pair_step_launch(const StepArgs& a, const unsigned char* dynb, const unsigned char* polb, int ns, cudaStream_t st);
 const char* mb_umma_selftest_launch(const float* A, const float* B, int K, int N, int nsplit, float* D, cudaStream_t st);
-
-const char* mb_umma2_selftest_launch(const float* A, const float* B, int K, int N, int nsplit, float* D, cudaStream_t st);
+void mb_ring_insert_transitions_launch(const float* packed, long long n_cap, const int* n_dev, int S, int A, int rw, long long ptr, long long cap,
+                                        float* dst, cudaStream_t st);
+void mb_par_penalty_launch(float* rows, int n, int S, int A, int rw, const float* pred, float coef, float* mean_out, cudaStream_t st);
 
 void mb_tc_set_trace(long long* buf);
 long long mb_train_workspace_bytes(int N, int S, int A, int nsplit);
@@ -91,6 +90,8 @@ int mobody_step(const mobody_step_desc* d, void* stream) {
   memset(&a, 0, sizeof(a));
   a.obs = d->obs; a.act = d->policy ? nullptr : d->act; a.eps = d->eps; a.idx = d->idx; a.elites = d->elites;
   a.n_elites = d->n_elites; a.B = d->B; a.S = d->S; a.A = d->A; a.n_rows_dev = d->n_rows_dev; a.row_ids = d->row_ids;
+  a.obs_ld = d->obs_ld ? d->obs_ld : d->S; a.act_ld = d->act_ld ? d->act_ld : d->A;
+  if (a.obs_ld < d->S || a.act_ld < d->A) return fail(MOBODY_ERR_ARG, "mobody_step: obs_ld / act_ld smaller than S / A");
   a.use_trg = d->use_trg; a.use_penalty = d->use_penalty; a.term_kind = d->term_kind;
   a.coef = d->penalty_coef; a.max_action = d->max_action; a.seed = d->seed; a.row0 = d->row0; a.step = d->step;
   a.act_out = d->act_out; a.next_obs = d->next_obs; a.reward = d->reward; a.raw_reward = d->raw_reward;
@@ -106,7 +107,6 @@ int mobody_step(const mobody_step_desc* d, void* stream) {
     case MOBODY_PREC_FP16: {
       if (!d->dyn_pack) return fail(MOBODY_ERR_ARG, "mobody_step: tensor-core precision needs dyn_pack (mobody_dyn_pack)");
       if (d->policy && !d->policy_pack) return fail(MOBODY_ERR_ARG, "mobody_step: fused policy needs policy_pack (mobody_mlp_pack)");
-      if (mb_tc_use_pair()) return fail(MOBODY_ERR_UNSUPPORTED, "mobody_step: the fp16 mode is not available with MOBODY_TC_PAIR=1");
       bool launched = false;
       err = mb_tc_duo_step_launch(a, (const unsigned char*)d->dyn_pack, d->policy ? (const unsigned char*)d->policy_pack : nullptr, 1,
                                   (cudaStream_t)stream, &launched);
@@ -116,10 +116,8 @@ int mobody_step(const mobody_step_desc* d, void* stream) {
     case MOBODY_PREC_BF16:
       if (!d->dyn_pack) return fail(MOBODY_ERR_ARG, "mobody_step: tensor-core precision needs dyn_pack (mobody_dyn_pack)");
       if (d->policy && !d->policy_pack) return fail(MOBODY_ERR_ARG, "mobody_step: fused policy needs policy_pack (mobody_mlp_pack)");
-      {   // default: one CTA per 128-row tile; MOBODY_TC_PAIR=1 selects the experimental CTA-pair kernel (two tiles in flight)
-        auto launch = mb_tc_use_pair() ? mb_tc_pair_step_launch : mb_tc_step_launch;   // the packed images are laid out for it
-        if (d->precision == MOBODY_PREC_BF16 && !mb_tc_use_pair()) {
-          // single bf16 plane: two row tiles fit in one SM -> the two-tiles-in-flight kernel (MOBODY_TC_DUO=0 disables it)
+      {   // one CTA per 128-row tile; the single bf16 plane (diagnostic mode) fits two row tiles per SM -> two-tiles-in-flight kernel
+        if (d->precision == MOBODY_PREC_BF16) {
           static int duo = -1;
           if (duo < 0) { const char* e = getenv("MOBODY_TC_DUO"); duo = (e && atoi(e) == 0) ? 0 : 1; }
           if (duo) {
@@ -130,8 +128,8 @@ int mobody_step(const mobody_step_desc* d, void* stream) {
             if (launched) return check_launch("mobody_step");
           }
         }
-        err = launch(a, (const unsigned char*)d->dyn_pack, d->policy ? (const unsigned char*)d->policy_pack : nullptr,
-                     d->precision == MOBODY_PREC_BF16X2 ? 2 : 1, (cudaStream_t)stream);
+        err = mb_tc_step_launch(a, (const unsigned char*)d->dyn_pack, d->policy ? (const unsigned char*)d->policy_pack : nullptr,
+                                d->precision == MOBODY_PREC_BF16X2 ? 2 : 1, (cudaStream_t)stream);
       }
       break;
     default: return fail(MOBODY_ERR_UNSUPPORTED, "mobody_step: unknown precision mode");
@@ -202,6 +200,24 @@ int mobody_ring_insert(const float* src_rows, long long n_cap, const int* n_dev,
   return check_launch("mobody_ring_insert");
 }
 
+int mobody_ring_insert_transitions(const float* packed, long long n_cap, const int* n_dev, int S, int A, long long ptr,
+                                   long long cap, float* dst_rows, void* stream) {
+  if (n_cap < 0 || cap <= 0 || ptr < 0 || ptr >= cap || S < 1 || A < 1) return fail(MOBODY_ERR_ARG, "mobody_ring_insert_transitions: bad arguments");
+  if (n_cap > cap) return fail(MOBODY_ERR_ARG, "mobody_ring_insert_transitions: batch larger than buffer capacity");
+  if (n_cap > 0 && (!packed || !dst_rows)) return fail(MOBODY_ERR_ARG, "mobody_ring_insert_transitions: null pointer");
+  mb_ring_insert_transitions_launch(packed, n_cap, n_dev, S, A, mobody_row_width(S, A), ptr, cap, dst_rows, (cudaStream_t)stream);
+  return check_launch("mobody_ring_insert_transitions");
+}
+
+int mobody_par_penalty(float* rows, int n, int S, int A, int row_width, const float* pred_next, float coef,
+                       float* mean_out, void* stream) {
+  if (n < 0 || S < 1 || A < 1 || row_width != mobody_row_width(S, A)) return fail(MOBODY_ERR_ARG, "mobody_par_penalty: bad arguments");
+  if (n > 0 && (!rows || !pred_next)) return fail(MOBODY_ERR_ARG, "mobody_par_penalty: null pointer");
+  if (n == 0) return MOBODY_OK;
+  mb_par_penalty_launch(rows, n, S, A, row_width, pred_next, coef, mean_out, (cudaStream_t)stream);
+  return check_launch("mobody_par_penalty");
+}
+
 long long mobody_compact_scratch_ints(long long n_cap) { return (n_cap + 1023) / 1024 + 1; }
 
 int mobody_compact(int keep_kind, const unsigned char* flags, const float* vals, float thr, long long n_cap,
@@ -230,6 +246,8 @@ int mobody_gather_pos_i64(const long long* src, const int* pos, const int* m_dev
   return check_launch("mobody_gather_pos_i64");
 }
 
+int mobody_rollout_stats_doubles(void) { return 2 + 2 * MB_STATS_BLOCKS; }
+
 int mobody_rollout(const mobody_rollout_desc* d, void* stream) {
   if (!d) return fail(MOBODY_ERR_ARG, "mobody_rollout: null descriptor");
   const mobody_step_desc& s0 = d->step;
@@ -237,6 +255,7 @@ int mobody_rollout(const mobody_rollout_desc* d, void* stream) {
   if (T < 1 || T > 200 || B < 0 || (long long)T * B > 0x7fffffffLL) return fail(MOBODY_ERR_ARG, "mobody_rollout: bad T / B");
   if (B == 0) return MOBODY_OK;
   if (!s0.policy) return fail(MOBODY_ERR_ARG, "mobody_rollout: the step template needs a policy (actions come from pi(s))");
+  if (s0.obs_ld && s0.obs_ld != S) return fail(MOBODY_ERR_ARG, "mobody_rollout: start states must be dense [B,S]");
   if (!s0.obs || !d->obss || !d->acts || !d->nexts || !d->rews || !d->pens || !d->terms || !d->row_ids || !d->counts || !d->pos ||
       !d->scratch || !d->stats || !d->ticket || !d->packed)
     return fail(MOBODY_ERR_ARG, "mobody_rollout: null workspace pointer");
@@ -248,7 +267,7 @@ int mobody_rollout(const mobody_rollout_desc* d, void* stream) {
   for (int t = 0; t < T; ++t) {
     mobody_step_desc s = s0;
     const size_t o = (size_t)t * B;
-    s.obs = d->obss + o * S; s.act = nullptr; s.act_out = d->acts + o * A; s.next_obs = d->nexts + o * S;
+    s.obs = d->obss + o * S; s.obs_ld = 0; s.act_ld = 0; s.act = nullptr; s.act_out = d->acts + o * A; s.next_obs = d->nexts + o * S;
     s.reward = d->rews + o; s.penalty = d->pens + o; s.terminal = d->terms + o;
     s.row_ids = d->row_ids + o; s.n_rows_dev = d->counts + t; s.step = s0.step + (unsigned)t;
     s.eps = d->eps_all ? d->eps_all + (size_t)t * MOBODY_E * B * S : nullptr;
@@ -325,13 +344,13 @@ long long mobody_dyn_pack_bytes(int S, int A, int precision) {
   return (long long)tc_dyn_layout(S, A, ns).total_bytes;
 }
 
-int mobody_dyn_pack(const mobody_dyn_params* dyn, int S, int A, int precision, void* blob, void* stream) {
+int mobody_dyn_pack(const mobody_dyn_params* dyn, int S, int A, int precision, void* blob, unsigned long long* state, void* stream) {
   int ns = nsplit_of(precision);
   if (!ns || !dyn || !blob || S < 2 || A < 1) return fail(MOBODY_ERR_ARG, "mobody_dyn_pack: bad arguments");
   DynPtrs dp; memcpy(&dp, dyn, sizeof(dp));
   for (int i = 0; i < L_COUNT; ++i)
     if (!dp.w[i] || !dp.b[i]) return fail(MOBODY_ERR_ARG, "mobody_dyn_pack: null parameter pointer");
-  const char* err = mb_tc_dyn_pack(dp, S, A, ns, precision == MOBODY_PREC_FP16, (unsigned char*)blob, (cudaStream_t)stream);
+  const char* err = mb_tc_dyn_pack(dp, S, A, ns, precision == MOBODY_PREC_FP16, (unsigned char*)blob, state, (cudaStream_t)stream);
   if (err) return fail(MOBODY_ERR_ARG, err);
   return check_launch("mobody_dyn_pack");
 }
@@ -342,11 +361,11 @@ long long mobody_mlp_pack_bytes(int din, int dout, int precision) {
   return (long long)tc_mlp_layout(din, dout, ns).total_bytes;
 }
 
-int mobody_mlp_pack(const mobody_mlp_params* mlp, int din, int dout, int precision, void* blob, void* stream) {
+int mobody_mlp_pack(const mobody_mlp_params* mlp, int din, int dout, int precision, void* blob, unsigned long long* state, void* stream) {
   int ns = nsplit_of(precision);
   if (!ns || !mlp || !blob || din < 1 || dout < 1) return fail(MOBODY_ERR_ARG, "mobody_mlp_pack: bad arguments");
   MlpPtrs mp; memcpy(&mp, mlp, sizeof(mp));
-  const char* err = mb_tc_mlp_pack(mp, din, dout, ns, precision == MOBODY_PREC_FP16, (unsigned char*)blob, (cudaStream_t)stream);
+  const char* err = mb_tc_mlp_pack(mp, din, dout, ns, precision == MOBODY_PREC_FP16, (unsigned char*)blob, state, (cudaStream_t)stream);
   if (err) return fail(MOBODY_ERR_ARG, err);
   return check_launch("mobody_mlp_pack");
 }
@@ -356,13 +375,6 @@ int mobody_selftest_umma(const float* A, const float* B, int K, int N, int nspli
   const char* err = mb_umma_selftest_launch(A, B, K, N, nsplit, D, (cudaStream_t)stream);
   if (err) return fail(MOBODY_ERR_ARG, err);
   return check_launch("mobody_selftest_umma");
-}
-
-int mobody_selftest_umma2(const float* A, const float* B, int K, int N, int nsplit, float* D, void* stream) {
-  if (!A || !B || !D) return fail(MOBODY_ERR_ARG, "mobody_selftest_umma2: null pointer");
-  const char* err = mb_umma2_selftest_launch(A, B, K, N, nsplit, D, (cudaStream_t)stream);
-  if (err) return fail(MOBODY_ERR_ARG, err);
-  return check_launch("mobody_selftest_umma2");
 }
 
 /* debug hook (not in the public header): device int64[80*8] receiving per-layer clock64 stamps of CTA 0 */

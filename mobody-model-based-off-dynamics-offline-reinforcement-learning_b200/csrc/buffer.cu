@@ -88,6 +88,24 @@ __global__ void ring_insert_kernel(const float4* __restrict__ src, long long n_c
   }
 }
 
+// add_batch straight from a rollout slab: packed row [obs | act | next_obs | reward | terminal | penalty] (W = 2S+A+3 floats)
+// -> buffer row [obs | act | next_obs | reward | 1 - terminal | 0-pad] (rw floats) at ring position (ptr + i) % cap.
+__global__ void ring_insert_transitions_kernel(const float* __restrict__ packed, long long n_cap, const int* __restrict__ n_dev,
+                                               int S, int A, int rw4, long long ptr, long long cap, float4* __restrict__ dst) {
+  const long long n = n_dev ? min((long long)*n_dev, n_cap) : n_cap;
+  const int W = 2 * S + A + 3, nd = 2 * S + A + 1;
+  const long long total = n * rw4;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long i = t / rw4; const int c0 = (int)(t - i * rw4) * 4;
+    const float* src = packed + i * W;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const int c = c0 + j; v[j] = c < nd ? src[c] : (c == nd ? 1.0f - src[nd] : 0.f); }
+    long long r = ptr + i; if (r >= cap) r -= cap;
+    dst[(size_t)r * rw4 + (c0 >> 2)] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
 // terminal[i] = term_fn(next_obs[i,:])   (terminal_funs.py via mobody_dynamics.py:237)
 __global__ void termination_kernel(const float* __restrict__ x, long long n, int S, int kind, unsigned char* __restrict__ out) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -284,6 +302,32 @@ __global__ void __launch_bounds__(SB) rollout_stats_kernel(const float* __restri
   }
 }
 
+// `par` reward penalty (mobody.py:428-434): reward[i] -= coef * mean_j (next_state[i,j] - pred[i,j])^2 on the first n batch
+// rows, in place; mean_out = batch mean of the penalty.  One CTA (n is a batch size): thread t owns rows t, t+1024, ...;
+// the per-thread sums are combined in a fixed tree, so the logged mean is deterministic.
+__global__ void __launch_bounds__(1024) par_penalty_kernel(float* __restrict__ rows, int n, int S, int A, int rw,
+                                                          const float* __restrict__ pred, float coef, float* __restrict__ mean_out) {
+  __shared__ float sh[1024];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += 1024) {
+    float* x = rows + (size_t)i * rw;
+    const float* ns = x + S + A;
+    const float* p = pred + (size_t)i * S;
+    float s = 0.f;
+    for (int j = 0; j < S; ++j) { const float d = ns[j] - p[j]; s = fmaf(d, d, s); }
+    const float pen = s / (float)S;
+    x[2 * S + A] -= coef * pen;
+    acc += pen;
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && mean_out) *mean_out = sh[0] / (float)n;
+}
+
 }  // namespace buf
 
 static inline int grid_for(long long work, int nt, int max_blocks = 148 * 16) {
@@ -337,6 +381,16 @@ void mb_gather_pos_i64_launch(const long long* src, const int* pos, const int* m
   buf::gather_pos_i64_kernel<<<grid_for(m_cap, buf::NT), buf::NT, 0, st>>>(src, pos, m_dev, m_cap, dst);
 }
 
+void mb_ring_insert_transitions_launch(const float* packed, long long n_cap, const int* n_dev, int S, int A, int rw, long long ptr, long long cap,
+                                        float* dst, cudaStream_t st) {
+  if (n_cap <= 0) return;
+  buf::ring_insert_transitions_kernel<<<grid_for(n_cap * (rw / 4), buf::NT), buf::NT, 0, st>>>(packed, n_cap, n_dev, S, A, rw / 4, ptr, cap,
+                                                                                             reinterpret_cast<float4*>(dst));
+}
+void mb_par_penalty_launch(float* rows, int n, int S, int A, int rw, const float* pred, float coef, float* mean_out, cudaStream_t st) {
+  buf::par_penalty_kernel<<<1, 1024, 0, st>>>(rows, n, S, A, rw, pred, coef, mean_out);
+}
+
 // ---- whole-rollout plumbing ----
 void mb_rollout_init_launch(long long* row_ids, unsigned long long row0, int B, int T, float* pens, unsigned char* terms,
                             int* counts, cudaStream_t st) {
@@ -357,7 +411,7 @@ void mb_rollout_pack_launch(const float* obss, const float* acts, const float* n
 // scratch: double[2 * MB_STATS_BLOCKS] partials followed by one unsigned ticket (zero-initialised once by the caller)
 void mb_rollout_stats_launch(const float* rews, const unsigned char* terms, long long n, double* partial, unsigned int* ticket,
                              double* stats, cudaStream_t st) {
-  int nb = (int)((n + 4095) / 4096); if (nb < 1) nb = 1; if (nb > 148) nb = 148;
+  int nb = (int)((n + 4095) / 4096); if (nb < 1) nb = 1; if (nb > MB_STATS_BLOCKS) nb = MB_STATS_BLOCKS;
   buf::rollout_stats_kernel<<<nb, buf::SB, 0, st>>>(rews, terms, n, partial, ticket, stats);
 }
 

@@ -7,6 +7,7 @@
 #define MB_E 7          // ensemble members (train_mobody.py:795; literal 7 in mobody_dynamics.py:218)
 #define MB_H 256        // hidden width (train_mobody.py:794)
 #define MB_LATENT 16    // latent_dim (mobody_module.py:95)
+#define MB_STATS_BLOCKS 148   // cap on the partial-sum blocks of rollout_stats_kernel (sizes mobody_rollout_desc.stats)
 #define MB_ZAH 32       // action-encoder hidden (mobody_module.py:110)
 
 enum MbLayer {
@@ -33,6 +34,7 @@ struct StepArgs {
   const int64_t* elites;   // [n_elites] device
   int n_elites;
   int B, S, A;             // B = row capacity (stride of eps/mean); live rows = *n_rows_dev if given
+  int obs_ld, act_ld;      // row strides of obs / act in floats (>= S / A; packed buffer rows are read in place)
   const int* n_rows_dev;   // nullable: live row count on device (rollout steps after compaction)
   const long long* row_ids;// nullable: global row id per row (Philox counter); default row0 + r
   int use_trg, use_penalty, term_kind;

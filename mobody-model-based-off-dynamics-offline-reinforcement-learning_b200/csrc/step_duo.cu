@@ -236,7 +236,7 @@ step_duo_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const 
     for (int u = 0; u < 2; ++u) {
       const size_t grow = row0_of(u) + r;
       const bool valid = grow < (size_t)live;
-      const float* orow = a.obs + grow * S;
+      const float* orow = a.obs + grow * a.obs_ld;
       unsigned char* As = small_of(u);
       for (int kg = group; kg < (int)cfg.obs_kp / 8; kg += 4) {
         float v[8];
@@ -245,7 +245,7 @@ step_duo_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const 
         put8(As, (uint32_t)kg * 2048u + (uint32_t)r * 16u, v);
       }
       if (!cfg.has_policy && group < 2) {
-        const float* arow = a.act + grow * A;
+        const float* arow = a.act + grow * a.act_ld;
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) { int j = group * 8 + i; v[i] = (valid && j < A) ? __ldg(arow + j) : 0.f; }
@@ -335,6 +335,7 @@ step_duo_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const 
       }
       {   // sas = [obs, act, next_obs, 0-pad] operand of the reward head (mobody_module.py:296); aliases obs/sa planes
         const float* actp = cfg.has_policy ? a.act_out : a.act;
+        const int act_ld = cfg.has_policy ? A : a.act_ld;
         unsigned char* As = small_of(u);
         for (int kg = group; kg < (int)cfg.sas_kp / 8; kg += 4) {
           float v[8];
@@ -343,8 +344,8 @@ step_duo_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const 
             const int k = kg * 8 + i;
             float t = 0.f;
             if (valid) {
-              if (k < S) t = __ldg(a.obs + grow * S + k);
-              else if (k < S + A) t = actp[grow * A + (k - S)];
+              if (k < S) t = __ldg(a.obs + grow * a.obs_ld + k);
+              else if (k < S + A) t = actp[grow * act_ld + (k - S)];
               else if (k < 2 * S + A) t = nobs_s[r * S + (k - S - A)];
             }
             v[i] = t;

@@ -65,12 +65,12 @@ step_kernel(StepArgs a, DynPtrs dp, MlpPtrs pol, int has_policy) {
   // ---- load obs tile (zero padded), action tile ----
   for (int i = tid; i < TM * m.ld_obs; i += NT) {
     int r = i / m.ld_obs, j = i - r * m.ld_obs;
-    m.obs[i] = (r < rows && j < S) ? a.obs[(size_t)(row0 + r) * S + j] : 0.0f;
+    m.obs[i] = (r < rows && j < S) ? a.obs[(size_t)(row0 + r) * a.obs_ld + j] : 0.0f;
   }
   if (!has_policy)
     for (int i = tid; i < TM * A; i += NT) {
-      int r = i / A;
-      m.act[i] = (r < rows) ? a.act[(size_t)row0 * A + i] : 0.0f;
+      int r = i / A, j = i - r * A;
+      m.act[i] = (r < rows) ? a.act[(size_t)(row0 + r) * a.act_ld + j] : 0.0f;
     }
   __syncthreads();
   if (has_policy) {   // Policy.forward: relu MLP, tanh * max_action  (mobody.py:35-72)

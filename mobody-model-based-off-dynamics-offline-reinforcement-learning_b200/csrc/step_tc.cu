@@ -17,8 +17,8 @@
 //    place in SMEM.  All groups work on the same 32-column chunk (8 columns per warp), so chunks are
 //    announced in order (one mbarrier per chunk) and the next layer's MMAs trail the epilogue by one chunk:
 //    tensor pipe and epilogue overlap inside a single row tile.
-//  Siblings: step_duo.cu (two tiles in flight per CTA; the single-pass fp16 / bf16 modes run there) and step_pair.cu
-//  (experimental CTA-pair / cta_group::2 variant: correct, slower — its cross-CTA hand-offs are software); DESIGN.md 4.1.
+//  Sibling: step_duo.cu (two tiles in flight per CTA; the single-pass fp16 mode runs there).  The CTA-pair experiment of
+//  round 1 (cta_group::2; correct, 3x slower) lives in scripts/experimental/ and is not part of the library; DESIGN.md 4.1.
 //
 // Precision: NS = 2 -> bf16 hi+lo split of both operands, 3 MMAs per K step (hi*hi + lo*hi + hi*lo), ~2^-16 per
 // product: inside the 1e-4 bound (the default mode).  NS = 1 -> single bf16 pass (bound 2e-2; used when the two-tile
@@ -234,7 +234,7 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
 
     // ---------------- prologue: obs (and given actions) -> bf16 operand planes ----------------
     {
-      const float* orow = a.obs + grow * S;
+      const float* orow = a.obs + grow * a.obs_ld;
       for (int kg = group; kg < (int)cfg.obs_kp / 8; kg += NG) {
         float v[8];
 #pragma unroll
@@ -242,7 +242,7 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
         store8<NS>(A_small, sp, (uint32_t)kg * 2048u + (uint32_t)r * 16u, v);
       }
       if (!cfg.has_policy && group < 2) {
-        const float* arow = a.act + grow * A;
+        const float* arow = a.act + grow * a.act_ld;
         float v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) { int j = group * 8 + i; v[i] = (valid && j < A) ? __ldg(arow + j) : 0.f; }
@@ -457,6 +457,7 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
     if (tracer && group == 0) cfg.trace[79 * 8 + 4] = clock64();
     {   // sas = [obs, act, next_obs, 0-pad] operand of the reward head (mobody_module.py:296); aliases obs/sa planes
       const float* actp = cfg.has_policy ? a.act_out : a.act;
+      const int act_ld = cfg.has_policy ? A : a.act_ld;
       for (int kg = group; kg < (int)cfg.sas_kp / 8; kg += NG) {
         float v[8];
 #pragma unroll
@@ -464,8 +465,8 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
           const int k = kg * 8 + i;
           float t = 0.f;
           if (valid) {
-            if (k < S) t = __ldg(a.obs + grow * S + k);
-            else if (k < S + A) t = actp[grow * A + (k - S)];
+            if (k < S) t = __ldg(a.obs + grow * a.obs_ld + k);
+            else if (k < S + A) t = actp[grow * act_ld + (k - S)];
             else if (k < 2 * S + A) t = nobs_s[r * S + (k - S - A)];
           }
           v[i] = t;
@@ -535,89 +536,129 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
 }
 
 // ---------------- weight packing: fp32 [K][N] (any strides) -> bf16 planes in UMMA B layout ----------------
-// pair = 0: [kstep s][plane p][kgroup g][n < Np][8 k]            (one CTA stages the whole K step with one bulk copy)
-// pair = 1: [kstep s][half h][plane p][kgroup g][n_local < Np/2][8 k]   (CTA h of a pair stages its half with one bulk copy)
-__global__ void pack_weight_kernel(const float* __restrict__ W, long long stride_k, long long stride_n, int K, int N, int Kp,
-                                   int Np, int ns, int pair, int fp16, float scale, __nv_bfloat16* __restrict__ out) {
-  const long long total = (long long)(Kp / 16) * ns * 2 * Np * 8;
-  const int nh = Np / 2;
+// image of one layer: [kstep s][plane p][kgroup g][n < Np][8 k]   (one CTA stages a whole K step with one bulk copy)
+__device__ __forceinline__ void pack_weight(const float* __restrict__ W, long long stride_k, long long stride_n, const TcGeom& g,
+                                            int ns, int fp16, float scale, __nv_bfloat16* __restrict__ out) {
+  const long long total = (long long)(g.Kp / 16) * ns * 2 * g.Np * 8;
   for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    int j = (int)(t & 7); long long u = t >> 3;
-    int n, g, p, s;
-    if (!pair) {
-      n = (int)(u % Np); u /= Np;
-      g = (int)(u & 1); u >>= 1;
-      p = (int)(u % ns); s = (int)(u / ns);
-    } else {
-      const int nl = (int)(u % nh); u /= nh;
-      g = (int)(u & 1); u >>= 1;
-      p = (int)(u % ns); u /= ns;
-      n = (int)(u & 1) * nh + nl; s = (int)(u >> 1);
-    }
-    int k = s * 16 + g * 8 + j;
-    float v = (k < K && n < N) ? W[k * stride_k + n * stride_n] * scale : 0.f;
+    const int j = (int)(t & 7); long long u = t >> 3;
+    const int n = (int)(u % g.Np); u /= g.Np;
+    const int kg = (int)(u & 1); u >>= 1;
+    const int p = (int)(u % ns), s = (int)(u / ns);
+    const int k = s * 16 + kg * 8 + j;
+    const float v = (k < g.K && n < g.N) ? W[k * stride_k + n * stride_n] * scale : 0.f;
     if (fp16) { reinterpret_cast<__half*>(out)[t] = __float2half_rn(v); continue; }     // single fp16 plane (ns == 1)
-    __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
     out[t] = (p == 0) ? h : __float2bfloat16_rn(v - __bfloat162float(h));
   }
 }
-__global__ void pack_bias_kernel(const float* __restrict__ b, long long stride, int N, int Np, float scale, float* __restrict__ out) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < Np) out[i] = (i < N) ? b[i * stride] * scale : 0.f;
+__device__ __forceinline__ void pack_bias(const float* __restrict__ b, long long stride, int N, int Np, float scale, float* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Np; i += gridDim.x * blockDim.x) out[i] = (i < N) ? b[i * stride] * scale : 0.f;
+}
+
+// ---------------- change detection for the packed images ----------------
+// state (device u64[4], zeroed once by the caller): [0] checksum of the parameters the image was packed from, [1] checksum
+// of the live parameters (accumulated by params_checksum_kernel, consumed and re-zeroed by the pack kernel), [2] image
+// valid flag, [3] ticket.  The checksum is position dependent (a value moved to another slot changes it) and is a sum of
+// 64-bit integers, so the atomics make it order independent: any write to the live fp32 parameters -- optimiser step,
+// load_state_dict, `.data.copy_()` (mobody_module.py:407-408), a raw pointer write -- is seen without asking the host.
+struct ChecksumArgs { const float* p[26]; unsigned int n[26]; int count; };
+__global__ void params_checksum_kernel(const ChecksumArgs a, unsigned long long* __restrict__ state) {
+  const int t = blockIdx.y;
+  const unsigned int n = a.n[t];
+  const uint32_t* x = reinterpret_cast<const uint32_t*>(a.p[t]);
+  unsigned long long h = 0;
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    h += (unsigned long long)(x[i] ^ (0x9E3779B9u * (uint32_t)(t + 1))) * (2ull * i + 1ull) + (unsigned long long)(t + 1);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+  if ((threadIdx.x & 31) == 0 && h) atomicAdd(state + 1, h);
+}
+// true -> this block must (re)pack.  Every block reads the two checksums first; the last block to finish commits.
+__device__ __forceinline__ bool pack_needed(const unsigned long long* state) {
+  if (!state) return true;
+  return !(state[2] != 0ull && state[0] == state[1]);
+}
+__device__ __forceinline__ void pack_commit(unsigned long long* state, unsigned long long cur) {
+  if (!state) return;
+  __shared__ bool last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(state + 3, 1ull) == (unsigned long long)gridDim.x * gridDim.y - 1ull;
+  __syncthreads();
+  if (last && threadIdx.x == 0) { state[0] = cur; state[1] = 0ull; state[2] = 1ull; state[3] = 0ull; }
+}
+
+// mobody_dyn_pack as ONE launch: blockIdx.y = member * 13 + job; jobs 0..11 = the MMA layers (weights + bias), job 12 =
+// reward_model3's column 0 and bias (the epilogue dot of the reward head)
+__device__ void pack_dyn_job(const DynPtrs& dp, int S, int A, int ns, int fp16, unsigned char* __restrict__ blob) {
+  const int e = blockIdx.y / (PK_COUNT + 1), i = blockIdx.y % (PK_COUNT + 1);
+  const TcDynLayout L = tc_dyn_layout(S, A, ns);
+  float* bias = reinterpret_cast<float*>(blob + L.bias_base) + (size_t)e * L.member_b_floats;
+  double so, si;
+  tc_swish_scales(ns, &so, &si);
+  if (i == PK_COUNT) {                                   // consumes reward_model2's swish: carries the input scale
+    float* o = bias + L.b_off[PK_COUNT];
+    pack_bias(dp.w[L_R3] + (size_t)e * MB_H * 2, 2, MB_H, MB_H, (float)si, o);
+    pack_bias(dp.b[L_R3] + (size_t)e * 2, 1, 1, 16, 1.0f, o + MB_H);
+    return;
+  }
+  const int src[PK_COUNT] = {L_ZS1, L_ZS2, L_ZS3, L_ZASRC1, L_ZASRC2, L_ZATRG1, L_ZATRG2, L_T1, L_T2, L_T3, L_R1, L_R2};
+  const float wscale = (float)((tc_out_is_swish(i) ? so : 1.0) * (tc_in_is_swish(i) ? si : 1.0));
+  const float bscale = (float)(tc_out_is_swish(i) ? so : 1.0);
+  const TcGeom g = tc_dyn_geom(i, S, A);
+  const int nfull = (i == PK_ZS3 || i == PK_ZASRC2 || i == PK_ZATRG2) ? 32 : g.N;     // mu half of 32 columns
+  pack_weight(dp.w[src[i]] + (size_t)e * g.K * nfull, nfull, 1, g, ns, fp16, wscale,
+              reinterpret_cast<__nv_bfloat16*>(blob + (size_t)e * L.member_w_bytes + L.w_off[i]));
+  pack_bias(dp.b[src[i]] + (size_t)e * nfull, 1, g.N, g.Np, bscale, bias + L.b_off[i]);
+}
+__global__ void pack_dyn_kernel(const DynPtrs dp, int S, int A, int ns, int fp16, unsigned char* __restrict__ blob,
+                                unsigned long long* __restrict__ state) {
+  const unsigned long long cur = state ? state[1] : 0ull;
+  if (pack_needed(state)) pack_dyn_job(dp, S, A, ns, fp16, blob);
+  pack_commit(state, cur);
+}
+
+// mobody_mlp_pack as one launch: blockIdx.y = layer.  nn.Linear weight is [out][in]: stride_k = 1, stride_n = K
+__global__ void pack_mlp_kernel(const MlpPtrs mp, int din, int dout, int ns, int fp16, unsigned char* __restrict__ blob,
+                                unsigned long long* __restrict__ state) {
+  const unsigned long long cur = state ? state[1] : 0ull;
+  if (pack_needed(state)) {
+    const TcMlpLayout L = tc_mlp_layout(din, dout, ns);
+    const int i = blockIdx.y;
+    pack_weight(mp.w[i], 1, L.g[i].K, L.g[i], ns, fp16, 1.0f, reinterpret_cast<__nv_bfloat16*>(blob + L.w_off[i]));
+    pack_bias(mp.b[i], 1, L.g[i].N, L.g[i].Np, 1.0f, reinterpret_cast<float*>(blob + L.bias_base) + L.b_off[i]);
+  }
+  pack_commit(state, cur);
 }
 
 }  // namespace tcs
 
-// Which kernel the packed images feed: the one-CTA-per-tile kernel (default) or the experimental CTA-pair kernel
-// (MOBODY_TC_PAIR=1; correct, but its software cross-CTA hand-offs are slower than what it saves — see DESIGN.md).
-int mb_tc_use_pair() {
-  static int pair = -1;
-  if (pair < 0) { const char* e = getenv("MOBODY_TC_PAIR"); pair = (e && atoi(e) == 1) ? 1 : 0; }
-  return pair;
-}
-
-static inline void launch_pack_w(const float* W, long long sk, long long sn, const TcGeom& g, int ns, int fp16, float scale, unsigned char* out, cudaStream_t st) {
-  long long total = (long long)(g.Kp / 16) * ns * 2 * g.Np * 8;
-  int grid = (int)((total + 255) / 256); if (grid > 1184) grid = 1184;
-  tcs::pack_weight_kernel<<<grid, 256, 0, st>>>(W, sk, sn, g.K, g.N, g.Kp, g.Np, ns, mb_tc_use_pair(), fp16, scale, reinterpret_cast<__nv_bfloat16*>(out));
-}
-
-// mobody_dyn_pack: all 7 members x 12 MMA layers + biases + reward_model3 vector
-const char* mb_tc_dyn_pack(const DynPtrs& dp, int S, int A, int ns, int fp16, unsigned char* blob, cudaStream_t st) {
+const char* mb_tc_dyn_pack(const DynPtrs& dp, int S, int A, int ns, int fp16, unsigned char* blob, unsigned long long* state, cudaStream_t st) {
   if (fp16 && ns != 1) return "dyn_pack: fp16 is a single-plane format";
   if (ns != 1 && ns != 2) return "dyn_pack: nsplit must be 1 or 2";
-  const TcDynLayout L = tc_dyn_layout(S, A, ns);
-  static const int src[PK_COUNT] = {L_ZS1, L_ZS2, L_ZS3, L_ZASRC1, L_ZASRC2, L_ZATRG1, L_ZATRG2, L_T1, L_T2, L_T3, L_R1, L_R2};
-  float* bias = reinterpret_cast<float*>(blob + L.bias_base);
-  double so, si;
-  tc_swish_scales(ns, &so, &si);
-  for (int e = 0; e < MB_E; ++e)
-    for (int i = 0; i < PK_COUNT; ++i) {
-      const float wscale = (float)((tc_out_is_swish(i) ? so : 1.0) * (tc_in_is_swish(i) ? si : 1.0));
-      const float bscale = (float)(tc_out_is_swish(i) ? so : 1.0);
-      const TcGeom g = tc_dyn_geom(i, S, A);
-      const int nfull = (i == PK_ZS3 || i == PK_ZASRC2 || i == PK_ZATRG2) ? 32 : g.N;     // mu half of 32 columns
-      const float* W = dp.w[src[i]] + (size_t)e * g.K * nfull;
-      launch_pack_w(W, nfull, 1, g, ns, fp16, wscale, blob + (size_t)e * L.member_w_bytes + L.w_off[i], st);
-      tcs::pack_bias_kernel<<<(g.Np + 127) / 128, 128, 0, st>>>(dp.b[src[i]] + (size_t)e * nfull, 1, g.N, g.Np, bscale,
-                                                                bias + (size_t)e * L.member_b_floats + L.b_off[i]);
+  if (state) {
+    tcs::ChecksumArgs c{}; c.count = 2 * L_COUNT;
+    for (int l = 0; l < L_COUNT; ++l) {
+      int in, out; tc_dyn_full_dims(l, S, A, &in, &out);
+      c.p[2 * l] = dp.w[l]; c.n[2 * l] = (unsigned)(MB_E * in * out);
+      c.p[2 * l + 1] = dp.b[l]; c.n[2 * l + 1] = (unsigned)(MB_E * out);
     }
-  for (int e = 0; e < MB_E; ++e) {   // reward_model3: column 0 of [256][2] and bias[0]
-    float* o = bias + (size_t)e * L.member_b_floats + L.b_off[PK_COUNT];
-    tcs::pack_bias_kernel<<<2, 128, 0, st>>>(dp.w[L_R3] + (size_t)e * MB_H * 2, 2, MB_H, MB_H, (float)si, o);   // consumes reward_model2's swish
-    tcs::pack_bias_kernel<<<1, 32, 0, st>>>(dp.b[L_R3] + (size_t)e * 2, 1, 1, 16, 1.0f, o + MB_H);
+    tcs::params_checksum_kernel<<<dim3(16, c.count), 256, 0, st>>>(c, state);
   }
+  tcs::pack_dyn_kernel<<<dim3(32, MB_E * (PK_COUNT + 1)), 256, 0, st>>>(dp, S, A, ns, fp16, blob, state);
   return nullptr;
 }
 
-const char* mb_tc_mlp_pack(const MlpPtrs& mp, int din, int dout, int ns, int fp16, unsigned char* blob, cudaStream_t st) {
+const char* mb_tc_mlp_pack(const MlpPtrs& mp, int din, int dout, int ns, int fp16, unsigned char* blob, unsigned long long* state, cudaStream_t st) {
   if (ns != 1 && ns != 2) return "mlp_pack: nsplit must be 1 or 2";
-  const TcMlpLayout L = tc_mlp_layout(din, dout, ns);
-  float* bias = reinterpret_cast<float*>(blob + L.bias_base);
-  for (int i = 0; i < 3; ++i) {   // nn.Linear weight is [out][in]: stride_k = 1, stride_n = K
-    launch_pack_w(mp.w[i], 1, L.g[i].K, L.g[i], ns, fp16, 1.0f, blob + L.w_off[i], st);
-    tcs::pack_bias_kernel<<<(L.g[i].Np + 127) / 128, 128, 0, st>>>(mp.b[i], 1, L.g[i].N, L.g[i].Np, 1.0f, bias + L.b_off[i]);
+  if (state) {
+    tcs::ChecksumArgs c{}; c.count = 6;
+    const int K[3] = {din, 256, 256}, N[3] = {256, 256, dout};
+    for (int l = 0; l < 3; ++l) { c.p[2 * l] = mp.w[l]; c.n[2 * l] = (unsigned)(K[l] * N[l]); c.p[2 * l + 1] = mp.b[l]; c.n[2 * l + 1] = (unsigned)N[l]; }
+    tcs::params_checksum_kernel<<<dim3(16, c.count), 256, 0, st>>>(c, state);
   }
+  tcs::pack_mlp_kernel<<<dim3(32, 3), 256, 0, st>>>(mp, din, dout, ns, fp16, blob, state);
   return nullptr;
 }
 

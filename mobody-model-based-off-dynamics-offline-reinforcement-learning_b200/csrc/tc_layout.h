@@ -78,6 +78,13 @@ static inline __host__ __device__ bool tc_in_is_swish(int pk) {
   return pk == PK_ZS2 || pk == PK_ZS3 || pk == PK_ZASRC2 || pk == PK_ZATRG2 || pk == PK_T2 || pk == PK_T3 || pk == PK_R2;
 }
 
+// Full (unpadded, both halves) shape of live parameter tensor `layer` (MbLayer order, common.cuh): weight [E][in][out], bias [E][1][out].
+static inline __host__ __device__ void tc_dyn_full_dims(int layer, int S, int A, int* in, int* out) {
+  const int I[13] = {S, 256, 256, 16 + A, 32, 16 + A, 32, 16, 256, 256, 2 * S + A, 256, 256};
+  const int O[13] = {256, 256, 32, 32, 32, 32, 32, 256, 256, S, 256, 256, 2};
+  *in = I[layer]; *out = O[layer];
+}
+
 #define TC_R3_FLOATS 272   // reward_model3 column 0 (256) + its bias at [256], padded
 
 struct TcDynLayout {

@@ -84,36 +84,42 @@ class MOBODYEnsembleDynamics(object):
         if self.precision == "auto":
             S_, A_ = getattr(model, "obs_dim", 0), getattr(model, "action_dim", 0)
             self.precision = "bf16x2" if (2 <= S_ <= 64 and 1 <= A_ <= 16) else "fp32"
+        if self.precision not in _ffi.PREC:
+            raise ValueError(f"precision {self.precision!r}: choose one of {_ffi.ENABLED_PRECISIONS} (single-pass bf16 is outside "
+                             "the stated error bounds and is not a product mode)")
         self.seed = int(seed)
         self._draw = 0        # Philox step counter for stand-alone step() calls in production mode
-        self._dyn_pack = None  # (version key, blob) of the tensor-core weight image
-        self._pol_pack = {}    # id(policy module) -> (version key, blob)
+        self._packs = {}       # image slot -> (blob, device-side change-detector state) of a tensor-core weight image
         self._param_cache = {}  # (kind, id(module)) -> (parameters, data_ptrs, pointer struct, keep-alive list)
 
     # ------------------------------------------------------------------
+    def _packed_image(self, slot, n_bytes, dev):
+        """(blob, state) of a packed tensor-core weight image.  ``state`` is the library's device-side change detector
+        (u64[4], zeroed once): mobody_*_pack checksums the live parameters on the device and re-packs only when they
+        differ from what the image was built from, so the image follows ANY write to the parameters -- an optimiser
+        step, load_state_dict, or a ``.data.copy_()`` that bumps no autograd version counter (MOBODYModule.load_save,
+        mobody_module.py:407-408) -- with no host synchronisation."""
+        ent = self._packs.get(slot)
+        if ent is None or ent[0].numel() != n_bytes or ent[0].device != dev:
+            ent = (torch.empty(n_bytes, dtype=torch.uint8, device=dev), torch.zeros(4, dtype=torch.int64, device=dev))
+            if len(self._packs) >= 16:
+                self._packs.pop(next(iter(self._packs)))
+            self._packs[slot] = ent
+        return ent
+
     def _packed_dynamics(self, dp, keep):
-        """bf16-plane UMMA image of the ensemble weights; re-packed when any parameter changed."""
-        key = (self.precision,) + _ffi.params_version(keep)
-        if self._dyn_pack is None or self._dyn_pack[0] != key:
-            S, A, prec = self.model.obs_dim, self.model.action_dim, _ffi.PREC[self.precision]
-            dev = keep[0].device
-            n = int(_ffi.lib().mobody_dyn_pack_bytes(S, A, prec))
-            blob = torch.empty(n, dtype=torch.uint8, device=dev)
-            _ffi.check(_ffi.lib().mobody_dyn_pack(C.byref(dp), S, A, prec, _ffi.ptr(blob), _ffi.stream_ptr(dev)))
-            self._dyn_pack = (key, blob)
-        return self._dyn_pack[1]
+        S, A, prec = self.model.obs_dim, self.model.action_dim, _ffi.PREC[self.precision]
+        dev = keep[0].device
+        blob, state = self._packed_image(("dyn", self.precision), int(_ffi.lib().mobody_dyn_pack_bytes(S, A, prec)), dev)
+        _ffi.check(_ffi.lib().mobody_dyn_pack(C.byref(dp), S, A, prec, _ffi.ptr(blob), _ffi.ptr(state), _ffi.stream_ptr(dev)))
+        return blob
 
     def _packed_policy(self, policy, mp, keep):
-        key = (self.precision, getattr(policy, "_b200_epoch", 0)) + _ffi.params_version(keep)
-        ent = self._pol_pack.get(id(policy))
-        if ent is None or ent[0] != key:
-            S, A, prec = self.model.obs_dim, self.model.action_dim, _ffi.PREC[self.precision]
-            dev = keep[0].device
-            n = int(_ffi.lib().mobody_mlp_pack_bytes(S, A, prec))
-            blob = ent[1] if ent is not None and ent[1].numel() == n else torch.empty(n, dtype=torch.uint8, device=dev)
-            _ffi.check(_ffi.lib().mobody_mlp_pack(C.byref(mp), S, A, prec, _ffi.ptr(blob), _ffi.stream_ptr(dev)))
-            self._pol_pack[id(policy)] = (key, blob)
-        return self._pol_pack[id(policy)][1]
+        S, A, prec = self.model.obs_dim, self.model.action_dim, _ffi.PREC[self.precision]
+        dev = keep[0].device
+        blob, state = self._packed_image(("pol", id(policy), self.precision), int(_ffi.lib().mobody_mlp_pack_bytes(S, A, prec)), dev)
+        _ffi.check(_ffi.lib().mobody_mlp_pack(C.byref(mp), S, A, prec, _ffi.ptr(blob), _ffi.ptr(state), _ffi.stream_ptr(dev)))
+        return blob
 
     # ------------------------------------------------------------------
     def _cached_params(self, kind, module, build):
@@ -166,16 +172,23 @@ class MOBODYEnsembleDynamics(object):
     def launch_step(self, obs, act, ws: StepWorkspace, *, policy=None, max_action=1.0, use_penalty=True,
                     use_trg=True, eps=None, idx=None, n_rows_dev=None, row_ids=None, step=0, row0=0):
         """Enqueue the fused step on the current stream; no host synchronisation.
-        obs [B,S] (B = capacity), act [B,A] or None with ``policy`` (an MLPNetwork-like module)."""
+        obs [B,S] (B = capacity), act [B,A] or None with ``policy`` (an MLPNetwork-like module).  obs / act may be
+        column views of wider rows (e.g. the state / action columns of packed replay-buffer rows): the row stride is
+        passed to the kernel, nothing is copied."""
         dev = obs.device
         B, S = obs.shape
         A = self.model.action_dim
+        for t in (obs, act):
+            if t is not None and (t.dtype != torch.float32 or not t.is_cuda or (t.shape[0] > 1 and t.stride(1) != 1) or t.shape[1] < 1):
+                raise RuntimeError("mobody_b200: step inputs must be fp32 CUDA tensors with unit column stride")
         d = _ffi.StepDesc()
         keep = self.fill_step_desc(d, B, S, dev, policy=policy, max_action=max_action, use_penalty=use_penalty, use_trg=use_trg)  # noqa: F841
         if policy is not None and ws.act is None:
             ws.act = torch.empty(B, A, dtype=torch.float32, device=dev)
         d.n_rows_dev, d.row_ids = _ffi.ptr(n_rows_dev), _ffi.ptr(row_ids)
-        d.obs, d.act = _ffi.ptr(obs), _ffi.ptr(act)
+        d.obs, d.act = obs.data_ptr(), (None if act is None else act.data_ptr())
+        d.obs_ld = obs.stride(0) if B > 1 else S
+        d.act_ld = (act.stride(0) if B > 1 else A) if act is not None else A
         d.eps, d.idx = _ffi.ptr(eps), _ffi.ptr(idx)
         d.step, d.row0 = int(step), int(row0)
         d.act_out = _ffi.ptr(ws.act)
@@ -193,8 +206,7 @@ class MOBODYEnsembleDynamics(object):
     def load(self, load_path: str) -> None:
         import os
         self.model.load_state_dict(torch.load(os.path.join(load_path, "dynamics.pth"), map_location=self.model.elites.device))
-        self.obs_scaler.load_scaler(load_path)
-        self._dyn_pack = None                                     # packed tensor-core image is rebuilt on the next step
+        self.obs_scaler.load_scaler(load_path)                   # (the packed tensor-core image follows by checksum)
 
     @torch.no_grad()
     def step(self, obs, action, use_penalty=True, use_trg=True, *, eps=None, idx=None

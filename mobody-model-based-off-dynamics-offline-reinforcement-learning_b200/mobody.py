@@ -53,12 +53,20 @@ class Policy(nn.Module):                                       # mobody.py:60-72
                                                     float(self.max_action), _ffi.ptr(out), _ffi.stream_ptr(x.device)))
         return out
 
+    def forward_autograd(self, x):
+        """Same function through torch ops (differentiable): used only by the non-default update branches."""
+        return torch.tanh(self.network(x)) * self.max_action
+
 
 class DoubleQFunc(nn.Module):                                  # mobody.py:74-83
     def __init__(self, state_dim, action_dim, hidden_size=256):
         super().__init__()
         self.network1 = MLPNetwork(state_dim + action_dim, 1, hidden_size)
         self.network2 = MLPNetwork(state_dim + action_dim, 1, hidden_size)
+
+    def forward(self, state, action):                          # torch ops: non-default update branches only
+        x = torch.cat((state, action), dim=1)
+        return self.network1(x), self.network2(x)
 
 
 class Classifier(nn.Module):                                   # mobody.py:11-33 (domain classifier of DARA / DARC)
@@ -73,16 +81,39 @@ class Classifier(nn.Module):                                   # mobody.py:11-33
 _SM_COUNT = {}
 
 
+def _sm_count(device):
+    key = str(device)
+    if key not in _SM_COUNT:
+        _SM_COUNT[key] = torch.cuda.get_device_properties(device).multi_processor_count
+    return _SM_COUNT[key]
+
+
+def _adam(params, lr):
+    """torch.optim.Adam with its per-parameter state created up front (mobody.py:127-135).  The fused kernels update
+    ``exp_avg`` / ``exp_avg_sq`` of this state IN PLACE, so ``state_dict()`` is the reference's optimizer checkpoint and the
+    torch-path branches continue from the same moments."""
+    opt = torch.optim.Adam(params, lr=lr)
+    for g in opt.param_groups:
+        for prm in g["params"]:
+            opt.state[prm] = {"step": torch.tensor(0.0), "exp_avg": torch.zeros_like(prm), "exp_avg_sq": torch.zeros_like(prm)}
+    return opt
+
+
+def _storage_idle(t):
+    """True when nothing but ``t`` itself references its storage (no view handed out earlier is still alive)."""
+    try:
+        return torch._C._storage_Use_Count(t.untyped_storage()._cdata) <= 2
+    except Exception:       # no such hook in this torch build: treat the slab as busy (allocate a fresh one)
+        return False
+
+
 def _wgrad_splits(n_rows, tiles_per_launch, device, sm_count=None):
     """Row splits of the weight-gradient launches.  A launch runs ``tiles * nsplit`` CTAs of 128 x 64 outputs, two per
     SM, each walking its rows in chunks of 32: pick the split count (<= 64) that minimises rounds x chunks per CTA
     summed over the launches of an update (tiles: critic 2 x (8 + 2), actor 8 + 2), i.e. avoid a nearly empty last
     round.  Any value gives the same result up to fp32 summation order; the order is fixed for a given value."""
     if sm_count is None:
-        key = str(device)
-        if key not in _SM_COUNT:
-            _SM_COUNT[key] = torch.cuda.get_device_properties(device).multi_processor_count
-        sm_count = _SM_COUNT[key]
+        sm_count = _sm_count(device)
     slots, chunks = 2 * sm_count, (n_rows + 31) // 32
     best, best_cost = 1, None
     for n in range(1, min(64, chunks) + 1):
@@ -91,6 +122,24 @@ def _wgrad_splits(n_rows, tiles_per_launch, device, sm_count=None):
         if best_cost is None or cost < best_cost:
             best, best_cost = n, cost
     return best
+
+def pipe_bounds(B, wave, first=None, rows=None):
+    """Chunk boundaries of a pipelined one-step rollout of B start states on a device whose full wave is ``wave`` rows
+    (SM count x 128-row tiles): a one-wave first chunk (little H2D exposed before the first kernel), two-wave chunks after
+    it, and the sub-wave remainder as its own last chunk (little D2H exposed after the last kernel).  Whole waves per
+    chunk: chunking adds no partially filled round to the step kernel."""
+    first = wave if first is None else first
+    rows = 2 * wave if rows is None else rows
+    bounds, lo = [0], min(first, B)
+    while lo < B:
+        bounds.append(lo)
+        lo += rows
+    bounds.append(B)
+    tail = (B - bounds[-2]) % wave
+    if 0 < tail < B - bounds[-2] and tail <= wave // 2:
+        bounds.insert(-1, B - tail)                           # split the sub-wave remainder off the last chunk
+    return bounds
+
 
 class MOBODY(object):
     def __init__(self, config, device, target_entropy=None):   # mobody.py:91-135
@@ -102,7 +151,8 @@ class MOBODY(object):
         self.discount, self.tau = config["gamma"], config["tau"]
         self.update_interval = config.get("update_interval", 2)   # read but unused by the reference too
         S, A = config["state_dim"], config["action_dim"]
-        self.fake_replay_buffer = ReplayBuffer(S, A, self.device)
+        self.seed = int(config.get("seed", 0))
+        self.fake_replay_buffer = ReplayBuffer(S, A, self.device, seed=ReplayBuffer.stream_seed(self.seed, "fake"))
         self.penalty_type = config.get("penalty_type", "par")
         self.total_it = 0
         self.q_funcs = DoubleQFunc(S, A).to(self.device)
@@ -113,21 +163,70 @@ class MOBODY(object):
         self.policy = Policy(S, A, config["max_action"]).to(self.device)
         self.classifier = Classifier(S, A, 256, config.get("gaussian_noise_std", 1.0)).to(self.device)   # :134
         self.dynamics = None                                     # injected by the caller (train_mobody.py:888)
-        # Adam moments of the fused train step (torch.optim.Adam equivalents of mobody.py:127-131)
-        z = lambda mlp: [torch.zeros_like(t) for t in _ffi.mlp_tensors(mlp)]      # noqa: E731
-        self._adam = {"pi": (z(self.policy.network), z(self.policy.network)),
-                      "q1": (z(self.q_funcs.network1), z(self.q_funcs.network1)),
-                      "q2": (z(self.q_funcs.network2), z(self.q_funcs.network2))}
-        self._adam["sas"] = (z(self.classifier.sas_classifier), z(self.classifier.sas_classifier))
-        self._adam["sa"] = (z(self.classifier.sa_classifier), z(self.classifier.sa_classifier))
-        self._t_q = self._t_pi = self._t_cls = 0
+        # the reference's four optimizers (mobody.py:127-135).  The fused kernels own the Adam arithmetic; these objects
+        # own the moments (updated in place by the kernels) and serve the checkpoint files and the torch-path branches.
+        self._opts = {"q": _adam(self.q_funcs.parameters(), config["critic_lr"]),
+                      "v": _adam(self.v_func.parameters(), config["critic_lr"]),
+                      "pi": _adam(self.policy.parameters(), config["actor_lr"]),
+                      "cls": _adam(self.classifier.parameters(), config["actor_lr"])}
+        self._t_q = self._t_pi = self._t_cls = 0                 # steps taken by the fused kernels (host counters) ...
+        self._steps_dirty = set()                                # ... flushed into the optimizers' ``step`` tensors on access
+        self._moment_cache = {}
         self._cls_ws, self._cls_scalars = None, torch.zeros(2, dtype=torch.float32, device=self.device)
         self._train_ws = None
         self._scalars = torch.zeros(16, dtype=torch.float32, device=self.device)
+        self._par_mean = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._par_ws = None
         self._roll_ws = {}                                       # (T, B, S, A) -> rollout scratch
-        self._host_slabs, self._host_turn = [None, None], 0      # pinned staging of rollout() results
+        self._host_slabs = []                                    # pinned staging slabs of rollout() results (reused when idle)
         self._pipe_streams, self._pipe_hdr = None, None          # side streams / pinned header of the pipelined rollout()
         self._pipe_plan_cache = None                             # (key, per-chunk launch plan)
+        sm = _sm_count(self.device)
+        self.PIPE_FIRST = sm * 128      # first chunk of a pipelined rollout(): one wave of 128-row tiles, so the first kernel starts after a short H2D
+        self.PIPE_ROWS = 2 * sm * 128   # later chunks: two full waves
+        self._wave = sm * 128
+
+    # ------------------------------------------------------------------ optimizers (mobody.py:127-135)
+    _OPT_COUNTER = {"q": "_t_q", "pi": "_t_pi", "cls": "_t_cls"}
+
+    def _optimizer(self, name):
+        """The torch optimizer ``name`` with its ``step`` tensors brought up to date with the fused kernels' counters."""
+        opt = self._opts[name]
+        if name in self._steps_dirty:
+            t = float(getattr(self, self._OPT_COUNTER[name]))
+            for st in opt.state.values():
+                st["step"].fill_(t)
+            self._steps_dirty.discard(name)
+        return opt
+
+    q_optimizer = property(lambda self: self._optimizer("q"))
+    v_optimizer = property(lambda self: self._optimizer("v"))
+    policy_optimizer = property(lambda self: self._optimizer("pi"))
+    classifier_optimizer = property(lambda self: self._optimizer("cls"))
+
+    def _pull_steps(self, name):
+        """After torch stepped (or loaded) optimizer ``name``: adopt its step count and its (possibly new) moment tensors."""
+        opt = self._opts[name]
+        steps = [int(st["step"]) for st in opt.state.values()]
+        setattr(self, self._OPT_COUNTER[name], max(steps) if steps else 0)
+        self._steps_dirty.discard(name)
+        self._moment_cache.pop(name, None)
+
+    def _moments(self, name, modules):
+        """[(exp_avg list, exp_avg_sq list) per MLP] of optimizer ``name`` in mlp_tensors order (the kernels' operand order)."""
+        ent = self._moment_cache.get(name)
+        if ent is None:
+            opt = self._opts[name]
+            ent = []
+            for mlp in modules:
+                prm = [t for li in (0, 2, 4) for t in (mlp.network[li].weight, mlp.network[li].bias)]
+                ent.append(([opt.state[q]["exp_avg"] for q in prm], [opt.state[q]["exp_avg_sq"] for q in prm]))
+            for m_list, v_list in ent:
+                for t in m_list + v_list:
+                    if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
+                        raise RuntimeError("mobody_b200: Adam moments must be contiguous fp32 CUDA tensors")
+            self._moment_cache[name] = ent
+        return ent
 
     def select_action(self, state, policy, cuda=False):          # mobody.py:138-144
         with torch.no_grad():
@@ -150,7 +249,7 @@ class MOBODY(object):
                       counts=torch.zeros(T + 2, dtype=torch.int32, device=dev),
                       pos=torch.empty(max(T * B, 1), dtype=torch.int32, device=dev),
                       scratch=torch.empty(int(_ffi.lib().mobody_compact_scratch_ints(T * B)), dtype=torch.int32, device=dev),
-                      stats=torch.zeros(2 + 2 * 148, dtype=torch.float64, device=dev),
+                      stats=torch.zeros(int(_ffi.lib().mobody_rollout_stats_doubles()), dtype=torch.float64, device=dev),
                       ticket=torch.zeros(1, dtype=torch.int32, device=dev))
             if len(self._roll_ws) >= 8:                       # a handful of shapes per run (50 000 / 2 000 starts)
                 self._roll_ws.pop(next(iter(self._roll_ws)))
@@ -158,14 +257,25 @@ class MOBODY(object):
         return ws
 
     @torch.no_grad()
+    def _take_draws(self, T, step0=None):
+        """Philox step counters of a T-step rollout: by default the dynamics object's monotonically increasing draw
+        counter (every rollout / step call consumes fresh noise and member picks, like the reference's torch.normal /
+        np.random.choice), or an explicit base ``step0`` (tests, replays) that leaves the counter alone."""
+        if step0 is not None:
+            return int(step0)
+        base = self.dynamics._draw
+        self.dynamics._draw += int(T)
+        return base
+
     def rollout_device(self, init_obss, rollout_length, use_trg=True, *, eps=None, idx=None, row0=0, out_packed=None,
-                       sync=True, ws_slot=0):
+                       sync=True, ws_slot=0, step0=None):
         """T-step imagined rollout entirely on the device (mobody.py:596-657 without its per-step D2H copies and
         host masks): ONE C-ABI call (mobody_rollout) enqueues the T fused steps, the compactions between them, the
         concatenation + penalty filter and the packing of the kept transitions.
 
         eps: optional [T,7,B,S] / idx: optional [T,B] injected draws (step t uses the first B_t rows, exactly what
         the reference consumes when fed the same arrays).
+        step0: explicit Philox step counter of the first step (default: the dynamics' running draw counter, advanced by T).
         out_packed: optional preallocated [>= T*B, 2S+A+3] CUDA tensor receiving the kept transitions as rows
         [obs | act | next_obs | reward | terminal | penalty] (the slab the multi-GPU all-gather ships).
         sync=True: one host read at the end (row counts + reward sum); the returned dict holds [M, .] column views of
@@ -193,7 +303,7 @@ class MOBODY(object):
             keep = dyn.fill_step_desc(d.step, B, S, dev, policy=self.policy.network, max_action=self.policy.max_action,  # noqa: F841
                                       use_trg=use_trg)
             d.step.obs, d.step.mean, d.step.raw_reward = _ffi.ptr(init_obss), _ffi.ptr(ws["mean"]), _ffi.ptr(ws["raw"])
-            d.step.step, d.step.row0 = 0, int(row0)
+            d.step.step, d.step.row0 = self._take_draws(T, step0), int(row0)
             d.T, d.filter_bad_rollout = T, int(bool(self.config.get("filter_bad_rollout", 1)))
             d.env_filter = float(self.config.get("env_filter", 0.0))
             d.eps_all, d.idx_all = _ffi.ptr(eps), _ffi.ptr(idx)
@@ -221,16 +331,17 @@ class MOBODY(object):
         return out, info
 
     def _host_slab(self, rows, W):
-        """Pinned staging slab for rollout() results, double-buffered: the CPU tensors a rollout() call returns stay
-        valid until the second-next rollout() call (the reference's only consumer, add_batch, copies immediately)."""
-        self._host_turn ^= 1
-        slab = self._host_slabs[self._host_turn]
-        if slab is None or slab.shape[0] < rows or slab.shape[1] != W:
-            slab = torch.empty(max(rows, 1), W, dtype=torch.float32, pin_memory=True)
-            self._host_slabs[self._host_turn] = slab
+        """Pinned staging slab for a rollout() result.  The CPU tensors rollout() returns are views of the slab and own it
+        for as long as any of them is alive (like the reference's fresh tensors, mobody.py:641-657): a slab is reused only
+        when its storage is referenced by nobody else; otherwise a new one is allocated and the busy one is left to its
+        holder.  A caller that drops each result before the second-next call (train()'s add_batch copies immediately)
+        cycles through two slabs with no allocation."""
+        for slab in self._host_slabs:
+            if slab.shape[1] == W and slab.shape[0] >= rows and _storage_idle(slab):
+                return slab
+        slab = torch.empty(max(rows, 1), W, dtype=torch.float32, pin_memory=True)
+        self._host_slabs = [t for t in self._host_slabs if not _storage_idle(t)][-3:] + [slab]   # idle leftovers are too small: drop them
         return slab
-
-    PIPE_ROWS = 2 * 148 * 128     # start states per pipelined chunk: two full waves of 128-row tiles on 148 SMs
 
     def rollout(self, init_obss, rollout_length, use_trg=True, **kw):
         """Reference signature and return convention (mobody.py:596-657): dict of CPU tensors + info.
@@ -261,22 +372,8 @@ class MOBODY(object):
             c0 += w
         return res, {"num_transitions": n_tr, "reward_mean": rsum / max(n_tr, 1)}
 
-    PIPE_FIRST = 148 * 128        # first chunk: one wave, so the first kernel starts after a short H2D
-
     def _pipe_bounds(self, B):
-        """Chunk boundaries of a pipelined one-step rollout: a one-wave first chunk (little H2D exposed before the first
-        kernel), two-wave chunks after it, and the sub-wave remainder as its own last chunk (little D2H exposed after the
-        last kernel).  Whole waves per chunk: chunking adds no partially filled round to the step kernel."""
-        bounds, lo = [0], min(self.PIPE_FIRST, B)
-        while lo < B:
-            bounds.append(lo)
-            lo += self.PIPE_ROWS
-        bounds.append(B)
-        wave = 148 * 128
-        tail = (B - bounds[-2]) % wave
-        if 0 < tail < B - bounds[-2] and tail <= wave // 2:
-            bounds.insert(-1, B - tail)                           # split the sub-wave remainder off the last chunk
-        return bounds
+        return pipe_bounds(B, self._wave, self.PIPE_FIRST, self.PIPE_ROWS)
 
     def _pipe_plan(self, B, S, A, W, use_trg, bounds):
         """Per-chunk launch plan of the pipelined rollout (device input / output buffers, workspace, a filled
@@ -289,7 +386,7 @@ class MOBODY(object):
         filt, env_filter = int(bool(self.config.get("filter_bad_rollout", 1))), float(self.config.get("env_filter", 0.0))
         key = (tuple(bounds), S, A, bool(use_trg), probe.precision, probe.dyn_pack, probe.policy_pack,
                C.addressof(probe.dyn.contents), C.addressof(probe.policy.contents), probe.elites, probe.n_elites,
-               probe.penalty_coef, probe.term_kind, probe.seed, probe.max_action, filt, env_filter)
+               probe.penalty_coef, probe.term_kind, probe.seed, probe.max_action, filt, env_filter, self._wave)
         if self._pipe_plan_cache is not None and self._pipe_plan_cache[0] == key:
             return self._pipe_plan_cache[1]
         plan = []
@@ -302,7 +399,7 @@ class MOBODY(object):
             d = _ffi.RolloutDesc()
             keep = dyn.fill_step_desc(d.step, n, S, dev, policy=self.policy.network, max_action=self.policy.max_action, use_trg=use_trg)
             d.step.obs, d.step.mean, d.step.raw_reward = _ffi.ptr(x), _ffi.ptr(ws["mean"]), _ffi.ptr(ws["raw"])
-            d.step.step, d.step.row0 = 0, int(lo)
+            d.step.step, d.step.row0 = 0, int(lo)                 # .step is patched per call (fresh Philox draws)
             d.T, d.filter_bad_rollout, d.env_filter = 1, filt, env_filter
             d.eps_all, d.idx_all = None, None
             for k in ("obss", "acts", "nexts", "rews", "pens", "terms", "row_ids", "counts", "pos", "scratch", "stats", "ticket"):
@@ -328,6 +425,7 @@ class MOBODY(object):
         hdr_kept, hdr_stats = self._pipe_hdr
         cur = torch.cuda.current_stream(dev)
         plan = self._pipe_plan(B, S, A, W, use_trg, bounds)
+        draw = self._take_draws(1)
         ready = torch.cuda.Event(); ready.record(cur)
         host = self._host_slab(B, W)
         for c, ch in enumerate(plan):
@@ -335,6 +433,7 @@ class MOBODY(object):
             with torch.cuda.stream(st):
                 st.wait_event(ready)
                 ch["x"].copy_(init_obss[ch["lo"]:ch["hi"]], non_blocking=True)
+                ch["desc"].step.step = draw
                 _ffi.check(lib.mobody_rollout(ch["ref"], C.c_void_p(st.cuda_stream)))
                 # [kept | reward sum, produced] of this chunk -> pinned header rows (stream-ordered 4- and 16-byte D2H)
                 hdr_kept[c].copy_(ch["kept_dev"], non_blocking=True)
@@ -364,7 +463,7 @@ class MOBODY(object):
         need = int(lib.mobody_classifier_workspace_bytes(N, S, A, nsplit))
         if self._cls_ws is None or self._cls_ws.numel() < need:
             self._cls_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-        self._t_cls += 1
+        self._t_cls += 1; self._steps_dirty.add("cls")
         d = _ffi.ClassifierDesc()
         d.rows, d.N, d.S, d.A, d.row_width = _ffi.ptr(rows), N, S, A, rows.shape[1]
         d.label = _ffi.ptr(label)
@@ -376,8 +475,9 @@ class MOBODY(object):
         d.noise_std, d.seed, d.draw = float(self.classifier.gaussian_noise_std), int(cfg.get("seed", 0)), self._t_cls
         cl = self.classifier
         d.sas, d.sa = _ffi.mlp_state(_ffi.mlp_tensors(cl.sas_classifier)), _ffi.mlp_state(_ffi.mlp_tensors(cl.sa_classifier))
-        d.sas_m, d.sas_v = _ffi.mlp_state(self._adam["sas"][0]), _ffi.mlp_state(self._adam["sas"][1])
-        d.sa_m, d.sa_v = _ffi.mlp_state(self._adam["sa"][0]), _ffi.mlp_state(self._adam["sa"][1])
+        (sa_m, sa_v), (sas_m, sas_v) = self._moments("cls", (cl.sa_classifier, cl.sas_classifier))
+        d.sas_m, d.sas_v = _ffi.mlp_state(sas_m), _ffi.mlp_state(sas_v)
+        d.sa_m, d.sa_v = _ffi.mlp_state(sa_m), _ffi.mlp_state(sa_v)
         d.t, d.lr, d.nsplit = self._t_cls, float(cfg["actor_lr"]), nsplit           # Adam(lr=actor_lr), mobody.py:135
         d.workspace, d.workspace_bytes, d.scalars_out = _ffi.ptr(self._cls_ws), self._cls_ws.numel(), _ffi.ptr(self._cls_scalars)
         _ffi.check(lib.mobody_classifier_step(C.byref(d), _ffi.stream_ptr(self.device)))
@@ -426,8 +526,9 @@ class MOBODY(object):
         losses land in ``self._scalars`` (device).  mobody.py:541-573.
         ``nsplit`` overrides the row-split count of the weight-gradient GEMMs (1..64; tests)."""
         cfg = self.config
-        if cfg.get("advantage", 0) or not cfg.get("scale_Q", 1) or not cfg.get("q_weighted", 1):
-            raise NotImplementedError("mobody_b200 implements the default advantage=0, scale_Q=1, q_weighted=1 update")
+        if not self._fused_update_ok():
+            raise RuntimeError("train_on_rows is the fused default update (advantage=0, scale_Q=1, q_weighted=1); "
+                               "train() routes the other branches through the torch path")
         S, A = cfg["state_dim"], cfg["action_dim"]
         N = rows.shape[0]
         if nsplit is None:
@@ -439,15 +540,18 @@ class MOBODY(object):
         if self._train_ws is None or self._train_ws.numel() < need:
             self._train_ws = torch.empty(need, dtype=torch.uint8, device=self.device)
         self._t_q += 1; self._t_pi += 1
+        self._steps_dirty.update(("q", "pi"))
         d = _ffi.TrainDesc()
         d.rows, d.N, d.n_true, d.S, d.A, d.row_width = _ffi.ptr(rows), N, int(n_true), S, A, rows.shape[1]
         qt = self.target_q_funcs
         d.policy = _ffi.mlp_state(_ffi.mlp_tensors(self.policy.network))
         d.q1, d.q2 = _ffi.mlp_state(_ffi.mlp_tensors(self.q_funcs.network1)), _ffi.mlp_state(_ffi.mlp_tensors(self.q_funcs.network2))
         d.q1_target, d.q2_target = _ffi.mlp_state(_ffi.mlp_tensors(qt.network1)), _ffi.mlp_state(_ffi.mlp_tensors(qt.network2))
-        d.policy_m, d.policy_v = _ffi.mlp_state(self._adam["pi"][0]), _ffi.mlp_state(self._adam["pi"][1])
-        d.q1_m, d.q1_v = _ffi.mlp_state(self._adam["q1"][0]), _ffi.mlp_state(self._adam["q1"][1])
-        d.q2_m, d.q2_v = _ffi.mlp_state(self._adam["q2"][0]), _ffi.mlp_state(self._adam["q2"][1])
+        ((pi_m, pi_v),) = self._moments("pi", (self.policy.network,))
+        (q1_m, q1_v), (q2_m, q2_v) = self._moments("q", (self.q_funcs.network1, self.q_funcs.network2))
+        d.policy_m, d.policy_v = _ffi.mlp_state(pi_m), _ffi.mlp_state(pi_v)
+        d.q1_m, d.q1_v = _ffi.mlp_state(q1_m), _ffi.mlp_state(q1_v)
+        d.q2_m, d.q2_v = _ffi.mlp_state(q2_m), _ffi.mlp_state(q2_v)
         d.t_q, d.t_pi = self._t_q, self._t_pi
         d.gamma, d.tau = float(self.discount), float(self.tau)
         d.critic_lr, d.actor_lr = float(cfg["critic_lr"]), float(cfg["actor_lr"])
@@ -455,9 +559,8 @@ class MOBODY(object):
         d.nsplit, d.workspace, d.workspace_bytes = nsplit, _ffi.ptr(self._train_ws), self._train_ws.numel()
         d.scalars_out = _ffi.ptr(self._scalars)
         _ffi.check(lib.mobody_train_step(C.byref(d), _ffi.stream_ptr(self.device)))
-        # parameters were updated in place behind autograd's version counters: bump the epoch that the
-        # tensor-core weight images (dynamics._packed_policy) are keyed on
-        self.policy.network._b200_epoch = getattr(self.policy.network, "_b200_epoch", 0) + 1
+        # (parameters were updated in place behind autograd's version counters; the packed tensor-core image of the
+        # policy follows them through the library's device-side checksum, dynamics._packed_image)
         return self._scalars
 
     def loss_scalars(self):
@@ -466,9 +569,35 @@ class MOBODY(object):
         return dict(q_loss=v[0], q1_mean=v[1], pi_loss=v[2], bc_loss=v[3], q_policy=v[4], q_abs_mean=v[5],
                     w_mean=v[6], w_min=v[7], w_max=v[8], p_w=v[9])
 
+    def _fused_update_ok(self):
+        cfg = self.config
+        return not cfg.get("advantage", 0) and bool(cfg.get("scale_Q", 1)) and bool(cfg.get("q_weighted", 1))
+
+    def _par_penalty(self, rows, n_src, writer, eps=None, idx=None):
+        """``penalty_type == 'par'`` (mobody.py:428-434): src_reward -= penalty_coef * mean((s' - s'_model)^2, 1), where
+        s'_model is a dynamics step on the batch's (s, a).  Two launches, no host synchronisation: the fused step reads the
+        state / action columns of the packed batch rows in place, and ``mobody_par_penalty`` rewrites the reward column."""
+        if n_src <= 0:
+            return
+        cfg, dyn = self.config, self.dynamics
+        S, A = cfg["state_dim"], cfg["action_dim"]
+        if self._par_ws is None or self._par_ws.next_obs.shape[0] != n_src:
+            self._par_ws = StepWorkspace(n_src, S, A, self.device)
+        if eps is not None:
+            eps = _ffi.f32(eps, self.device)
+        if idx is not None:
+            idx = torch.as_tensor(np.asarray(idx) if not torch.is_tensor(idx) else idx).to(device=self.device, dtype=torch.int64).contiguous()
+        dyn.launch_step(rows[:n_src, :S], rows[:n_src, S:S + A], self._par_ws, eps=eps, idx=idx, step=dyn._draw)
+        dyn._draw += 1
+        _ffi.check(_ffi.lib().mobody_par_penalty(_ffi.ptr(rows), n_src, S, A, rows.shape[1], _ffi.ptr(self._par_ws.next_obs),
+                                                 float(cfg["penalty_coef"]), _ffi.ptr(self._par_mean), _ffi.stream_ptr(self.device)))
+        if writer is not None and self.total_it % 100 == 0:                                           # :432-433
+            writer.add_scalar("train/reward_penalty_par", float(self._par_mean), global_step=self.total_it)
+
     def train(self, src_replay_buffer, tar_replay_buffer, batch_size=128, writer=None, wandbrun=None, *, _inject=None):
-        """Reference signature (mobody.py:347-578).  ``_inject`` optionally supplies the buffer indices the
-        reference would draw with np.random.randint, as a dict {src, tar, fake, src_init, tar_init}."""
+        """Reference signature (mobody.py:347-578).  ``_inject`` optionally scripts the draws the reference would make
+        (parity tests): buffer indices {src, tar, fake, src_init, tar_init} (np.random.randint) and the noise / member
+        indices of its dynamics calls {par_eps, par_idx, src_eps, src_idx, tar_eps, tar_idx, sa_eps, sa_idx}."""
         cfg = self.config
         self.total_it += 1
         self.src_replay_buffer, self.tar_replay_buffer = src_replay_buffer, tar_replay_buffer
@@ -479,15 +608,15 @@ class MOBODY(object):
                     print(loss_sa, loss_sas)
             self.dara_relabel(src_replay_buffer)
         inj = _inject or {}
-        S, A = cfg["state_dim"], cfg["action_dim"]
         n_src, n_tar = int(cfg["src_ratio"] * batch_size), int(cfg["trg_ratio"] * batch_size)
         n_fake = int(cfg["fake_batch_scale"] * batch_size) if cfg["fake_batch_scale"] != 0 else 0
         RW = src_replay_buffer.RW
         rows = torch.empty(n_src + n_tar + n_fake, RW, dtype=torch.float32, device=self.device)
         refresh = (self.total_it - 1) % 5000 == 0
-        fused = (not inj and not refresh and self.penalty_type != "par" and n_fake and
-                 all(b.index_source == "philox" and b.size > 0 for b in (src_replay_buffer, tar_replay_buffer, self.fake_replay_buffer)))
-        if fused:   # the three buffer samples of this step (:399, 400, 524) as ONE launch: Philox draw + 128-bit row gather
+        par = self.penalty_type == "par"
+        one_launch = (not inj and not refresh and n_fake and
+                      all(b.index_source == "philox" and b.size > 0 for b in (src_replay_buffer, tar_replay_buffer, self.fake_replay_buffer)))
+        if one_launch:   # the three buffer samples of this step (:399, 400, 524) as ONE launch: Philox draw + 128-bit row gather
             jobs = (_ffi.SampleJob * 3)()
             for jb, (b, n, lo) in zip(jobs, ((src_replay_buffer, n_src, 0), (tar_replay_buffer, n_tar, n_src),
                                              (self.fake_replay_buffer, n_fake, n_src + n_tar))):
@@ -495,21 +624,95 @@ class MOBODY(object):
                 jb.out = rows.data_ptr() + 4 * RW * lo
                 b._draw += 1
             _ffi.check(_ffi.lib().mobody_sample_rows(jobs, 3, RW, _ffi.stream_ptr(self.device)))
+            if par:
+                self._par_penalty(rows, n_src, writer)                                                # :428-434
+        else:
+            src_replay_buffer.sample_rows(n_src, inj.get("src"), out=rows[:n_src])                    # :399
+            tar_replay_buffer.sample_rows(n_tar, inj.get("tar"), out=rows[n_src:n_src + n_tar])       # :400
+            if par:
+                self._par_penalty(rows, n_src, writer, inj.get("par_eps"), inj.get("par_idx"))
+            if refresh:                                                                               # :441-513
+                self.refresh_fake_buffer(src_replay_buffer, tar_replay_buffer, inj, batch_size)
+            if n_fake:
+                self.fake_replay_buffer.sample_rows(n_fake, inj.get("fake"), out=rows[n_src + n_tar:])   # :524
+        if self._fused_update_ok():
             self.train_on_rows(rows, n_src + n_tar)
             self._train_side_effects(writer, wandbrun)
-            return
-        src_replay_buffer.sample_rows(n_src, inj.get("src"), out=rows[:n_src])                        # :399
-        tar_replay_buffer.sample_rows(n_tar, inj.get("tar"), out=rows[n_src:n_src + n_tar])           # :400
-        if self.penalty_type == "par":                                                                # :428-434
-            s, a_, ns = rows[:n_src, :S].contiguous(), rows[:n_src, S:S + A].contiguous(), rows[:n_src, S + A:2 * S + A]
-            pred, _, _, _ = self.dynamics.step(s, a_)
-            rows[:n_src, 2 * S + A] -= cfg["penalty_coef"] * ((ns - pred) ** 2).mean(1)
-        if (self.total_it - 1) % 5000 == 0:                                                           # :441-475 refresh
-            self.refresh_fake_buffer(src_replay_buffer, tar_replay_buffer, inj, batch_size)
-        if n_fake:
-            self.fake_replay_buffer.sample_rows(n_fake, inj.get("fake"), out=rows[n_src + n_tar:])    # :524
-        self.train_on_rows(rows, n_src + n_tar)
-        self._train_side_effects(writer, wandbrun)
+        else:
+            self._train_torch_path(rows, n_src + n_tar, writer, wandbrun)
+
+    def _train_torch_path(self, rows, n_true, writer, wandbrun):
+        """The update branches the fused kernels do not cover -- ``advantage=1`` (value-function baseline, mobody.py:210-242,
+        533-539), ``scale_Q=0`` (update_policy_1, :278-310) and ``q_weighted=0`` (:262-263) -- run through torch autograd on
+        the same device-resident batch rows and the same torch.optim.Adam objects (whose moments the fused kernels share),
+        as SURVEY section 2 #4 asks ("must keep working via the unchanged PyTorch path").  Off by default in every shipped
+        config; not a performance path."""
+        cfg = self.config
+        S, A = cfg["state_dim"], cfg["action_dim"]
+        state, action, next_state = rows[:, :S], rows[:, S:S + A], rows[:, S + A:2 * S + A]
+        reward, not_done = rows[:, 2 * S + A:2 * S + A + 1], rows[:, 2 * S + A + 1:2 * S + A + 2]
+        t_state, t_action = state[:n_true], action[:n_true]
+        log = writer is not None and self.total_it % 5000 == 0
+        q_opt, pi_opt = self.q_optimizer, self.policy_optimizer        # (properties: step tensors flushed)
+        if cfg.get("advantage", 0):                                                                   # :210-242, 533-537
+            with torch.no_grad():
+                qt = torch.min(*self.target_q_funcs(state, action))
+            v = self.v_func(state)
+            adv = qt - v
+            if log:
+                writer.add_scalar("train/adv", adv.mean(), self.total_it)
+                writer.add_scalar("train/value", v.mean(), self.total_it)
+            v_loss = torch.mean(torch.abs(0.7 - (adv < 0).float()) * adv ** 2)                        # asymmetric_l2_loss(adv, 0.7), :85-86
+            self.v_optimizer.zero_grad(); v_loss.backward(); self.v_optimizer.step()
+        with torch.no_grad():                                                                         # :189-195 / :210-216
+            if cfg.get("advantage", 0):
+                q_target = self.v_func(next_state)
+            else:
+                q_target = torch.min(*self.target_q_funcs(next_state, self.policy.forward_autograd(next_state)))
+            y = reward + not_done * self.discount * q_target
+        q1, q2 = self.q_funcs(state, action)
+        if log:
+            writer.add_scalar("train/q1", q1.mean(), self.total_it)
+            if wandbrun is not None:
+                wandbrun.log({"train/q1": q1.mean()}, step=self.total_it, commit=False)
+        q_loss = torch.nn.functional.mse_loss(q1, y) + torch.nn.functional.mse_loss(q2, y)
+        q_opt.zero_grad(); q_loss.backward(); q_opt.step()                                           # :546-548
+        with torch.no_grad():                                                                         # update_target, :183-187
+            for tp, qp in zip(self.target_q_funcs.parameters(), self.q_funcs.parameters()):
+                tp.data.copy_(self.tau * qp.data + (1.0 - self.tau) * tp.data)
+        for prm in self.q_funcs.parameters():
+            prm.requires_grad = False
+        qv = torch.min(*self.q_funcs(state, self.policy.forward_autograd(state)))                    # :279-281 / :315-317
+        p_w = cfg["weight"] / qv.abs().mean().detach() if cfg.get("scale_Q", 1) else 1.0
+        pi_loss = p_w * (-qv).mean()
+        pred = self.policy.forward_autograd(t_state)                                                  # bc_loss, :246-276
+        with torch.no_grad():
+            qb = torch.min(*self.q_funcs(t_state, t_action))
+            adv = qb - self.v_func(t_state) if cfg.get("advantage", 0) else qb / qb.abs().mean()
+            exp_adv = torch.exp(3 * adv).clamp(max=100.0)
+        if cfg.get("q_weighted", 1):
+            if self.total_it % 1000 == 0:
+                print(torch.mean(exp_adv), torch.min(exp_adv), torch.max(exp_adv))
+            bc = torch.mean(exp_adv * (pred - t_action) ** 2)
+        else:
+            bc = torch.mean((pred - t_action) ** 2)
+        if log:
+            writer.add_scalar("train/exp_adv", exp_adv.mean() if cfg.get("q_weighted", 1) else 1.0, self.total_it)
+            writer.add_scalar("train/bc_loss", bc, self.total_it)
+        pi_loss = pi_loss + cfg.get("bc_coef", 1.0) * bc
+        if log:
+            with torch.no_grad():
+                q_beh = torch.min(*self.q_funcs(state, action))
+            writer.add_scalar("train/q_behavior", q_beh.mean(), self.total_it)
+            writer.add_scalar("train/q_policy", qv.mean(), self.total_it)
+            writer.add_scalar("train/policy_loss", pi_loss, self.total_it)
+            if wandbrun is not None:
+                wandbrun.log({"train/q_behavior": q_beh.mean(), "train/q_policy": qv.mean(), "train/policy_loss": pi_loss}, step=self.total_it)
+        pi_opt.zero_grad(); pi_loss.backward(); pi_opt.step()                                         # :571-573
+        for prm in self.q_funcs.parameters():
+            prm.requires_grad = True
+        self._pull_steps("q"); self._pull_steps("pi")
+        self._scalars[0], self._scalars[2] = q_loss.detach(), pi_loss.detach()
 
     def _train_side_effects(self, writer, wandbrun):
         cfg = self.config
@@ -529,23 +732,42 @@ class MOBODY(object):
 
     def refresh_fake_buffer(self, src_buf, tar_buf, inj=None, batch_size=128):
         """Synthetic-data refresh (mobody.py:441-475): two policy rollouts through the learned target dynamics and one
-        dynamics step on dataset (s, a) pairs, all inserted into the fake buffer without leaving the device."""
+        dynamics step on dataset (s, a) pairs, all inserted into the fake buffer without leaving the device.  Every
+        dynamics call takes fresh Philox draws (the dynamics' running draw counter) unless ``inj`` scripts them."""
         cfg, inj = self.config, inj or {}
         S, A = cfg["state_dim"], cfg["action_dim"]
+        lib, dev, fake = _ffi.lib(), self.device, self.fake_replay_buffer
         src_rows = src_buf.sample_rows(50000, inj.get("src_init"))                                    # :442 (sizes hard-coded there)
         tar_rows = tar_buf.sample_rows(2000, inj.get("tar_init"))                                     # :443
-        for init, T in ((src_rows[:, :S].contiguous(), cfg["src_rollout_length"]), (tar_rows[:, :S].contiguous(), cfg["trg_rollout_length"])):
-            out, info = self.rollout_device(init, T)                                                  # :444, 453
+        for tag, init, T in (("src", src_rows[:, :S].contiguous(), cfg["src_rollout_length"]),
+                             ("tar", tar_rows[:, :S].contiguous(), cfg["trg_rollout_length"])):
+            out, info = self.rollout_device(init, T, eps=inj.get(tag + "_eps"), idx=inj.get(tag + "_idx"))   # :444, 453
             if cfg.get("filter_bad_rollout", 1) and out is not None:
                 print("filtered rollout", info["kept"], info["num_transitions"])                     # :653
-            self.fake_replay_buffer.add_batch(out)
+            if out is not None:                                                                       # add_batch, :445, 454
+                fake.add_rollout_slab(info["packed"], info["kept"])
         if cfg.get("use_src_sa_to_get_target_next_state", 1):                                         # :460-475
-            s, a_ = src_rows[:, :S].contiguous(), src_rows[:, S:S + A].contiguous()
-            ws = StepWorkspace(s.shape[0], S, A, self.device)
-            self.dynamics.launch_step(s, a_, ws)
-            keep = (ws.penalty < cfg["env_filter"]).squeeze(1)                                        # strict < here (quirk 5)
-            self.fake_replay_buffer.add_batch({"obss": s[keep], "next_obss": ws.next_obs[keep], "actions": a_[keep],
-                                               "rewards": ws.reward[keep], "terminals": ws.terminal[keep].float()[:, None]})
+            n = src_rows.shape[0]
+            ws = StepWorkspace(n, S, A, dev)
+            eps, idx = inj.get("sa_eps"), inj.get("sa_idx")
+            if eps is not None:
+                eps = _ffi.f32(eps, dev)
+            if idx is not None:
+                idx = torch.as_tensor(np.asarray(idx) if not torch.is_tensor(idx) else idx).to(device=dev, dtype=torch.int64).contiguous()
+            self.dynamics.launch_step(src_rows[:, :S], src_rows[:, S:S + A], ws, eps=eps, idx=idx, step=self.dynamics._draw)
+            self.dynamics._draw += 1
+            # keep rows with penalty < env_filter (strict `<` here, `<=` in rollout(): mobody.py:468 vs :649) -- stable device
+            # compaction, then one gather of the kept rows into buffer layout [s | a | s'_model | r_model | 1 - terminal]
+            pos = torch.empty(n, dtype=torch.int32, device=dev)
+            cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+            scratch = torch.empty(int(lib.mobody_compact_scratch_ints(n)), dtype=torch.int32, device=dev)
+            _ffi.check(lib.mobody_compact(_ffi.KEEP_F32_LT, None, _ffi.ptr(ws.penalty), float(cfg["env_filter"]), n, None,
+                                          _ffi.ptr(scratch), _ffi.ptr(pos), _ffi.ptr(cnt), _ffi.stream_ptr(dev)))
+            rows = fake._pack(src_rows[:, :S], src_rows[:, S:S + A], ws.next_obs, ws.reward, ws.terminal.float(), True)
+            kept = torch.empty_like(rows)
+            _ffi.check(lib.mobody_gather_pos(_ffi.ptr(rows), fake.RW, fake.RW, _ffi.ptr(pos), _ffi.ptr(cnt), n, _ffi.ptr(kept), fake.RW,
+                                             _ffi.stream_ptr(dev)))
+            fake.add_packed(kept, int(cnt.item()))            # the host owns ptr / size (utils.py:68-92): one count read
         if cfg.get("rollout_from_src", 0):                                                            # :477-510
             if self.penalty_type != "dara":
                 self.update_classifier(src_buf, tar_buf, batch_size)
@@ -565,10 +787,30 @@ class MOBODY(object):
                 self.fake_replay_buffer.add_packed(rows, rows.shape[0])
 
     # ------------------------------------------------------------------ checkpoints
-    def save(self, filename):                                    # mobody.py:584-588 (optimizer files: see train step)
+    def save(self, filename):                                    # mobody.py:584-588: the reference's four files
         torch.save(self.q_funcs.state_dict(), filename + "_critic")
+        torch.save(self.q_optimizer.state_dict(), filename + "_critic_optimizer")
         torch.save(self.policy.state_dict(), filename + "_actor")
+        torch.save(self.policy_optimizer.state_dict(), filename + "_actor_optimizer")
 
     def load(self, filename):                                    # mobody.py:590-594
         self.q_funcs.load_state_dict(torch.load(filename + "_critic"))
+        self._opts["q"].load_state_dict(torch.load(filename + "_critic_optimizer"))
         self.policy.load_state_dict(torch.load(filename + "_actor"))
+        self._opts["pi"].load_state_dict(torch.load(filename + "_actor_optimizer"))
+        for name in ("q", "pi"):
+            self._adopt_loaded_state(name)
+
+    def _adopt_loaded_state(self, name):
+        """load_state_dict replaced the optimizer's state tensors: make sure every parameter has fused-kernel-ready
+        moments (a checkpoint written before the first step holds none) and adopt the step count."""
+        opt = self._opts[name]
+        for g in opt.param_groups:
+            for prm in g["params"]:
+                st = opt.state[prm]
+                if "exp_avg" not in st:
+                    st.update({"step": torch.tensor(0.0), "exp_avg": torch.zeros_like(prm), "exp_avg_sq": torch.zeros_like(prm)})
+                st["exp_avg"], st["exp_avg_sq"] = st["exp_avg"].contiguous().float(), st["exp_avg_sq"].contiguous().float()
+                if not torch.is_tensor(st["step"]):
+                    st["step"] = torch.tensor(float(st["step"]))
+        self._pull_steps(name)

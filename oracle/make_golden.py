@@ -237,6 +237,17 @@ def gen_train(S, A, B, seed, n_steps=3):
             flat = v.numpy().reshape(-1)
             out[f"post_{grp}_{k}_sub"] = flat[::37].copy()
             out[f"post_{grp}_{k}_sum"] = np.float64(flat.astype(np.float64).sum())
+    # optimizer checkpoints (mobody.py:585, 587: torch.save(optimizer.state_dict())): Adam moments per parameter index
+    import json
+    for grp, opt in (("q", pol.q_optimizer), ("pi", pol.policy_optimizer)):
+        sd = opt.state_dict()
+        out[f"opt_{grp}_groups"] = json.dumps([{k: v for k, v in g.items()} for g in sd["param_groups"]], sort_keys=True)
+        for i, stt in sd["state"].items():
+            out[f"opt_{grp}_{i}_step"] = np.float64(float(stt["step"]))
+            for mk in ("exp_avg", "exp_avg_sq"):
+                flat = stt[mk].numpy().reshape(-1)
+                out[f"opt_{grp}_{i}_{mk}_sub"] = flat[::37].copy()
+                out[f"opt_{grp}_{i}_{mk}_sum"] = np.float64(flat.astype(np.float64).sum())
     return out
 
 
@@ -315,6 +326,102 @@ def gen_classifier(S, A, B, seed, n_steps=3):
     return out
 
 
+def recipe_dataset(S, A, n, seed, env):
+    """Deterministic synthetic dataset rows (state, action, next_state, reward, not_done) from Philox recipes: a fixture
+    only has to store the seed.  States sit around the env's healthy set so rollouts survive a few steps."""
+    from oracle.philox import recipe_fill
+    hs = healthy(env, S).astype(np.float32)
+    return dict(state=hs[None] + recipe_fill((n, S), seed, 0.2), action=recipe_fill((n, A), seed + 1, 0.5).clip(-1, 1),
+                next_state=hs[None] + recipe_fill((n, S), seed + 2, 0.2), reward=recipe_fill((n, 1), seed + 3, 1.0),
+                not_done=np.ones((n, 1), np.float32))
+
+
+def refresh_draws(S, seed, T_src, T_tar, n_batch):
+    """Scripted draws of one MOBODY.train call at total_it == 1 with penalty_type='par' (mobody.py:428-475), as recipes:
+    uniform noise with unit variance stands in for torch.normal's N(0,1) (the reference only multiplies it by std)."""
+    from oracle.philox import recipe_fill, buffer_indices
+    d = dict(par_eps=recipe_fill((7, n_batch, S), seed + 10, 1.0), par_idx=buffer_indices(seed, 10, n_batch, 5),
+             src_eps=recipe_fill((T_src, 7, 50000, S), seed + 11, 1.0), src_idx=np.stack([buffer_indices(seed, 20 + t, 50000, 5) for t in range(T_src)]),
+             tar_eps=recipe_fill((T_tar, 7, 2000, S), seed + 12, 1.0), tar_idx=np.stack([buffer_indices(seed, 40 + t, 2000, 5) for t in range(T_tar)]),
+             sa_eps=recipe_fill((7, 50000, S), seed + 13, 1.0), sa_idx=buffer_indices(seed, 60, 50000, 5))
+    return d
+
+
+def gen_refresh(env="hopper", S=11, A=3, B=32, seed=51, n_src=3000, n_tar=500, T_src=2, T_tar=3, coef=1.0, h0=0.8, t3_gain=4.0,
+                env_filter=0.3615, par_coef=0.1):
+    """The synthetic-data refresh of MOBODY.train at total_it == 1 (mobody.py:441-475) run by the UNMODIFIED reference with
+    penalty_type='par': fake-buffer contents (every 53rd row + float64 column sums + ptr/size) after the call."""
+    _, _, _, _, ref_utils = _import_reference()
+    from oracle.philox import buffer_indices
+    dyn, _ = build_reference_dynamics(S, A, seed, env, coef, h0, t3_gain)
+    pol, ag, cfg = build_reference_agent(S, A, seed, dict(penalty_type="par", penalty_coef=par_coef, env_filter=env_filter,
+                                                            src_rollout_length=T_src, trg_rollout_length=T_tar))
+    pol.dynamics = dyn
+    bufs = {}
+    for nm, n, sd in (("src", n_src, seed * 100), ("tar", n_tar, seed * 100 + 50)):
+        b = ref_utils.ReplayBuffer(S, A, "cpu", max_size=n)
+        for f, v in recipe_dataset(S, A, n, sd, env).items():
+            getattr(b, f)[:n] = torch.from_numpy(v)
+        b.size = n; b.ptr = 0
+        bufs[nm] = b
+    dr = refresh_draws(S, seed, T_src, T_tar, B)
+    inds = [buffer_indices(seed, 1, B, n_src), buffer_indices(seed, 2, B, n_tar), buffer_indices(seed, 3, 50000, n_src),
+            buffer_indices(seed, 4, 2000, n_tar)]
+    eps_calls = [dr["par_eps"]] + [dr["src_eps"][t] for t in range(T_src)] + [dr["tar_eps"][t] for t in range(T_tar)] + [dr["sa_eps"]]
+    idx_calls = [dr["par_idx"]] + [dr["src_idx"][t] for t in range(T_src)] + [dr["tar_idx"][t] for t in range(T_tar)] + [dr["sa_idx"]]
+
+    class Stop(Exception):
+        pass
+
+    def randint_then_stop(c):          # the 5th randint call is fake_replay_buffer.sample: the refresh is over
+        raise Stop
+    with Inject(lambda c, shp: torch.from_numpy(eps_calls[c][:, :shp[1]].copy()), lambda c, n: idx_calls[c][:n], ind_list=inds) as inj, \
+            contextlib.redirect_stdout(None):
+        try:
+            pol.train(bufs["src"], bufs["tar"], B, None, None)
+        except IndexError:             # ind_list exhausted at the fake-buffer sample: everything before it has run
+            pass
+        assert inj.calls["normal"] == len(eps_calls) and inj.calls["choice"] == len(idx_calls), inj.calls
+    fb = pol.fake_replay_buffer
+    n = fb.size
+    rows = torch.cat([fb.state[:n], fb.action[:n], fb.next_state[:n], fb.reward[:n], fb.not_done[:n]], 1).numpy()
+    out = dict(env=env, S=S, A=A, B=B, seed=seed, n_src=n_src, n_tar=n_tar, T_src=T_src, T_tar=T_tar, coef=np.float32(coef),
+               h0=np.float64(h0), t3_gain=np.float64(t3_gain), env_filter=np.float32(env_filter), par_coef=np.float32(par_coef),
+               fake_size=n, fake_ptr=fb.ptr, col_sums=rows.astype(np.float64).sum(0), not_done_count=int(rows[:, -1].sum()))
+    # The same three dynamics calls once more WITHOUT the penalty filter, under the same scripted draws: every transition the
+    # block produced, its terminal flag and whether the block kept it.  A checker can then line rows up by (segment, step,
+    # start row) even when a reduced-precision run flips a row that sits on a threshold.  Applying the masks must
+    # reproduce the fake buffer the reference's train() call built above -- asserted here, so the fixture IS that call.
+    src_init = torch.from_numpy(recipe_dataset(S, A, n_src, seed * 100, env)["state"])[inds[2]]
+    src_act = torch.from_numpy(recipe_dataset(S, A, n_src, seed * 100, env)["action"])[inds[2]]
+    tar_init = torch.from_numpy(recipe_dataset(S, A, n_tar, seed * 100 + 50, env)["state"])[inds[3]]
+    pol.config["filter_bad_rollout"] = 0
+    rebuilt = []
+    for seg, init, T, eps_all, idx_all in (("src", src_init, T_src, dr["src_eps"], dr["src_idx"]), ("tar", tar_init, T_tar, dr["tar_eps"], dr["tar_idx"])):
+        with Inject(lambda c, shp: torch.from_numpy(eps_all[c][:, :shp[1]].copy()), lambda c, n_: idx_all[c][:n_]), contextlib.redirect_stdout(None):
+            tr, _ = pol.rollout(init, T, True)
+        allrows = torch.cat([tr["obss"], tr["actions"], tr["next_obss"], tr["rewards"], 1.0 - tr["terminals"]], 1).numpy()
+        keep = (tr["penalty"] <= env_filter).squeeze(1).numpy()                      # mobody.py:648-651
+        out.update({seg + "_n_all": len(allrows), seg + "_term": np.packbits(tr["terminals"].numpy().astype(bool).ravel()),
+                    seg + "_keep": np.packbits(keep), seg + "_sub_rows": allrows[::41].copy()})
+        rebuilt.append(allrows[keep])
+    with Inject(lambda c, shp: torch.from_numpy(dr["sa_eps"]), lambda c, n_: dr["sa_idx"]):
+        nobs, rew, term, info = dyn.step(src_init, src_act)
+    allrows = torch.cat([src_init, src_act, nobs, rew, 1.0 - torch.from_numpy(term.astype(np.float32))], 1).numpy()
+    keep = (info["penalty"] < env_filter).squeeze(1).numpy()                         # strict, mobody.py:468
+    out.update(sa_n_all=len(allrows), sa_term=np.packbits(term.ravel()), sa_keep=np.packbits(keep), sa_sub_rows=allrows[::41].copy())
+    rebuilt.append(allrows[keep])
+    assert np.array_equal(np.concatenate(rebuilt, 0), rows), "mask reconstruction differs from the reference's refresh block"
+    # the `par` reward penalty of the same call (mobody.py:428-434): the reference keeps it in a local, so it is re-derived
+    # here from the reference's own dynamics.step under the draws that call consumed
+    ds = recipe_dataset(S, A, n_src, seed * 100, env)
+    bs, ba, bns = (torch.from_numpy(ds[k])[inds[0]] for k in ("state", "action", "next_state"))
+    with Inject(lambda c, shp: torch.from_numpy(dr["par_eps"]), lambda c, n_: dr["par_idx"]):
+        pred, _, _, _ = dyn.step(bs, ba)
+    out["par_penalty"] = torch.mean((bns - pred) ** 2, axis=1, keepdims=True).numpy()
+    return out
+
+
 def gen_checkpoint_keys():
     """Key -> shape of every checkpoint file the reference writes for this path: dynamics.pth
     (MOBODYModule.state_dict, mobody_dynamics.py:1158-1160), <name>_actor / <name>_critic (mobody.py:584-588) and the
@@ -351,6 +458,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "train_S17A6_B32.npz"), **gen_train(17, 6, 32, 31))
     np.savez_compressed(os.path.join(OUT, "train_S11A3_B16.npz"), **gen_train(11, 3, 16, 32, n_steps=2))
     np.savez_compressed(os.path.join(OUT, "classifier_S17A6_B32.npz"), **gen_classifier(17, 6, 32, 41))
+    np.savez_compressed(os.path.join(OUT, "refresh_hopper.npz"), **gen_refresh())
     import json
     with open(os.path.join(OUT, "checkpoint_keys.json"), "w") as f:
         json.dump(gen_checkpoint_keys(), f, indent=0, sort_keys=True)

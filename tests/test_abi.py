@@ -35,7 +35,7 @@ def test_every_declared_symbol_is_exported(libpath):
 def test_abi_version_and_pure_host_calls(libpath):
     from mobody_b200 import _ffi
     L = _ffi.lib()
-    assert L.mobody_abi_version() == 1
+    assert L.mobody_abi_version() == 2 == _ffi.ABI_VERSION
     assert L.mobody_row_width(17, 6) == 44 and L.mobody_row_width(11, 3) == 28 and L.mobody_row_width(27, 8) == 64
     assert L.mobody_compact_scratch_ints(1) == 2 and L.mobody_compact_scratch_ints(1025) == 3
 
@@ -60,7 +60,9 @@ def test_argument_errors_are_reported_not_raised_across_abi(libpath):
     sj = (_ffi.SampleJob * 1)()
     sj[0].n, sj[0].size = 4, 0
     assert L.mobody_sample_rows(sj, 1, 44, None) == -1 and b"empty buffer" in L.mobody_last_error()
-    assert L.mobody_dyn_pack_bytes(17, 6, 3) == L.mobody_dyn_pack_bytes(17, 6, 2) > 0      # fp16 and bf16 images have the same size
+    assert 2 * L.mobody_dyn_pack_bytes(17, 6, 3) > L.mobody_dyn_pack_bytes(17, 6, 1) > L.mobody_dyn_pack_bytes(17, 6, 3) > 0   # one fp16 plane vs bf16 hi+lo
+    assert L.mobody_par_penalty(None, 4, 17, 6, 40, None, 1.0, None, None) == -1 and b"bad arguments" in L.mobody_last_error()   # wrong row width
+    assert L.mobody_rollout_stats_doubles() >= 4
     assert L.mobody_dyn_pack_bytes(17, 6, 0) == 0                                           # fp32 mode has no packed image
     with pytest.raises(RuntimeError, match="mobody_b200"):
         _ffi.check(-1)

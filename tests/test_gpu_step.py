@@ -1,7 +1,7 @@
 """GPU parity of the fused step against (a) reference-generated golden vectors and (b) the CPU oracle.
 
 Tolerances (north_star): termination masks and indices bit-exact; fp32 outputs <= 1e-4 relative
-(fp32 and bf16x2 modes); single-pass modes: fp16 within the stated looser bound 5e-3, bf16 within 2e-2.
+(fp32 and bf16x2 modes); single-pass fp16 mode: within the stated looser bound 5e-3.
 rel = |a-b| / (|b| + 1e-3).
 """
 import glob
@@ -15,7 +15,7 @@ from helpers import cuda_dynamics, rel_err
 from oracle import mobody_oracle as M
 
 pytestmark = pytest.mark.gpu
-TOL = {"fp32": 1e-4, "bf16x2": 1e-4, "bf16": 2e-2, "fp16": 5e-3}   # single-pass GEMMs: fp16 meets the stated looser bound 5e-3; bf16 is looser (2e-2)
+TOL = {"fp32": 1e-4, "bf16x2": 1e-4, "fp16": 5e-3}   # single-pass fp16 GEMMs meet the stated looser bound 5e-3
 
 
 def precisions():
@@ -135,17 +135,31 @@ def test_policy_forward_matches_oracle():
         assert isinstance(a1, np.ndarray) and a1.shape == (A,)
 
 
-@pytest.mark.parametrize("env_var", ["MOBODY_TC_PAIR=1", "MOBODY_TC_DUO=0"])
-def test_alternative_tensor_core_kernels_in_subprocess(env_var):
-    """The kernel choice (and, for the CTA-pair kernel, the packed weight layout) is fixed per process by an environment
-    variable, so the alternatives are exercised in a child process: MOBODY_TC_PAIR=1 = experimental CTA-pair kernel for
-    the tensor-core modes; MOBODY_TC_DUO=0 = single-tile kernel for the single-pass bf16 mode."""
-    import subprocess
-    import sys
-    k, v = env_var.split("=")
-    env = dict(os.environ, **{k: v})
-    sel = "golden and (bf16x2 or bf16)" if k == "MOBODY_TC_PAIR" else "golden and bf16"
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-x", "-q", "-k", sel, "-p", "no:cacheprovider"],
-                       env=env, capture_output=True, text=True, timeout=300, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert " passed" in r.stdout
+def test_single_pass_bf16_is_not_a_product_precision():
+    """Single-pass bf16 (measured 1.6e-2) is outside north_star's bounds (1e-4; stated looser bound 5e-3): not selectable."""
+    import mobody_b200 as mb
+    from mobody_b200 import _ffi
+    assert "bf16" not in _ffi.PREC and "bf16" not in _ffi.ENABLED_PRECISIONS
+    with pytest.raises(ValueError, match="precision"):
+        cuda_dynamics(17, 6, 1, "halfcheetah", 1.0, precision="bf16")
+    assert mb.MOBODYEnsembleDynamics  # (import check)
+
+
+def test_step_reads_packed_buffer_rows_in_place():
+    """obs / act given as column views of packed replay-buffer rows (row stride RW): same result as dense copies."""
+    import mobody_b200 as mb
+    from mobody_b200.dynamics import StepWorkspace
+    S, A, B = 17, 6, 300
+    rng = np.random.default_rng(2)
+    buf = mb.ReplayBuffer(S, A, "cuda", max_size=B)
+    buf.convert_D4RL(dict(observations=rng.standard_normal((B, S)).astype(np.float32), actions=rng.uniform(-1, 1, (B, A)).astype(np.float32),
+                          next_observations=rng.standard_normal((B, S)).astype(np.float32), rewards=np.zeros(B, np.float32),
+                          terminals=np.zeros(B, bool)))
+    rows = buf._rows
+    for prec in precisions():
+        dyn, _ = cuda_dynamics(S, A, 3, "halfcheetah", 1.0, precision=prec)
+        w1, w2 = StepWorkspace(B, S, A, "cuda"), StepWorkspace(B, S, A, "cuda")
+        dyn.launch_step(rows[:, :S], rows[:, S:S + A], w1, step=3)
+        dyn.launch_step(rows[:, :S].contiguous(), rows[:, S:S + A].contiguous(), w2, step=3)
+        torch.cuda.synchronize()
+        assert torch.equal(w1.next_obs, w2.next_obs) and torch.equal(w1.reward, w2.reward) and torch.equal(w1.penalty, w2.penalty), prec

@@ -212,3 +212,125 @@ def test_launch_mode_and_tiling_switches_in_subprocess():
 
     assert digest(MOBODY_PDL="1") == digest(MOBODY_PDL="0")
     assert len(digest(MOBODY_TRAIN_TM="64")) == 64
+
+
+@pytest.mark.parametrize("name", ["train_S17A6_B32.npz"])
+def test_optimizer_checkpoints_match_reference_and_round_trip(golden_dir, name, tmp_path):
+    """MOBODY.save / load write and read the reference's FOUR files (mobody.py:584-594).  The optimizer files are
+    torch.optim.Adam.state_dict()s: after the golden's train steps the fused kernels' moments must equal the reference's
+    exp_avg / exp_avg_sq / step per parameter index and the param_groups must be the reference's; a saved agent must
+    resume bit-identically; and an optimizer file written by a stock torch.optim.Adam (what the reference writes) must load."""
+    import json
+    g = np.load(os.path.join(golden_dir, name))
+    S, A, B, seed, n_steps = (int(g[k]) for k in ("S", "A", "B", "seed", "n_steps"))
+    ag, _ = cuda_agent(S, A, seed)
+    bufs = _buffers(g, S, A)
+    ag.fake_replay_buffer = bufs["fake"]
+    ag.total_it = 1
+    inj = lambda it: {"src": g[f"ind{3 * it}"], "tar": g[f"ind{3 * it + 1}"], "fake": g[f"ind{3 * it + 2}"]}   # noqa: E731
+    for it in range(n_steps):
+        ag.train(bufs["src"], bufs["tar"], B, None, None, _inject=inj(it))
+    torch.cuda.synchronize()
+    for grp, opt in (("q", ag.q_optimizer), ("pi", ag.policy_optimizer)):
+        sd = opt.state_dict()
+        want_groups = json.loads(str(g[f"opt_{grp}_groups"]))
+        got_groups = json.loads(json.dumps(sd["param_groups"]))
+        assert got_groups == want_groups, grp                                   # same keys, lr, betas, eps, param indices
+        assert sorted(sd["state"]) == list(range(len(want_groups[0]["params"])))
+        for i, stt in sd["state"].items():
+            assert float(stt["step"]) == float(g[f"opt_{grp}_{i}_step"]) == n_steps
+            for mk, tol in (("exp_avg", 1e-4), ("exp_avg_sq", 2e-4)):
+                flat = stt[mk].cpu().numpy().reshape(-1)
+                want = g[f"opt_{grp}_{i}_{mk}_sub"]
+                scale = np.abs(want).mean() + 1e-30
+                bad = np.abs(flat[::37] - want) > tol * (np.abs(want) + scale)
+                assert bad.mean() <= 5e-3, (grp, i, mk, float(bad.mean()))        # (ReLU-edge outliers: see adam_close)
+    # round trip: save, load into a fresh agent, continue both with the same batch -> bit-identical parameters
+    fn = str(tmp_path / "ckpt")
+    ag.save(fn)
+    assert sorted(os.listdir(tmp_path)) == ["ckpt_actor", "ckpt_actor_optimizer", "ckpt_critic", "ckpt_critic_optimizer"]
+    ag2, _ = cuda_agent(S, A, seed + 1)                                          # different initial weights
+    ag2.load(fn)
+    ag2.target_q_funcs.load_state_dict(ag.target_q_funcs.state_dict())           # (targets are not checkpointed by the reference either)
+    assert ag2._t_q == ag._t_q == n_steps and ag2._t_pi == n_steps
+    rows = bufs["src"].sample_rows(80, np.arange(80))
+    ag.train_on_rows(rows, 64); ag2.train_on_rows(rows, 64)
+    torch.cuda.synchronize()
+    for m1, m2 in ((ag.policy, ag2.policy), (ag.q_funcs, ag2.q_funcs)):
+        for (k, v1), v2 in zip(m1.state_dict().items(), m2.state_dict().values()):
+            assert torch.equal(v1, v2), k
+    # a file written by stock torch.optim.Adam on the reference's module layout (mobody.py:585) loads and is used
+    import copy
+    ref_q = copy.deepcopy(ag.q_funcs).cpu()
+    ref_opt = torch.optim.Adam(ref_q.parameters(), lr=3e-4)
+    x = torch.randn(16, S + A)
+    (ref_q.network1(x).sum() + ref_q.network2(x).sum()).backward()
+    ref_opt.step(); ref_opt.step()
+    torch.save(ref_q.state_dict(), fn + "_critic"); torch.save(ref_opt.state_dict(), fn + "_critic_optimizer")
+    ag2.load(fn)
+    assert ag2._t_q == 2
+    m_ref = ref_opt.state_dict()["state"][2]["exp_avg"]
+    (q1_m, _), _ = ag2._moments("q", (ag2.q_funcs.network1, ag2.q_funcs.network2))
+    assert q1_m[2].is_cuda and torch.equal(q1_m[2].cpu(), m_ref)
+    ag2.train_on_rows(rows, 64)                                                  # continues from the loaded moments
+    torch.cuda.synchronize()
+    assert ag2._t_q == 3 and float(ag2.q_optimizer.state_dict()["state"][0]["step"]) == 3.0
+
+
+@pytest.mark.parametrize("override", [dict(advantage=1), dict(scale_Q=0), dict(q_weighted=0)])
+def test_non_default_update_branches_run_through_the_torch_path(override):
+    """advantage=1 / scale_Q=0 / q_weighted=0 (mobody.py:210-310, 533-559) are off in every shipped config; they must keep
+    working -- through torch autograd on the same device-resident rows and the same optimizers --
+    and must match the CPU oracle's restatement of the default math where the branch reduces to it."""
+    import mobody_b200 as mb
+    S, A, B = 11, 3, 64
+    rng = np.random.default_rng(3)
+    ag, st = cuda_agent(S, A, 21, **override)
+
+    def ds(n):
+        return dict(observations=rng.standard_normal((n, S)).astype(np.float32), actions=rng.uniform(-1, 1, (n, A)).astype(np.float32),
+                    next_observations=rng.standard_normal((n, S)).astype(np.float32), rewards=rng.standard_normal(n).astype(np.float32),
+                    terminals=(rng.random(n) < 0.1))
+    src, tar = mb.ReplayBuffer(S, A, "cuda"), mb.ReplayBuffer(S, A, "cuda")
+    src.convert_D4RL(ds(3000)); tar.convert_D4RL(ds(500)); ag.fake_replay_buffer.convert_D4RL(ds(800))
+    ag.total_it = 1
+    before = {k: v.clone() for k, v in ag.policy.state_dict().items()}
+    qb = {k: v.clone() for k, v in ag.q_funcs.state_dict().items()}
+    vb = {k: v.clone() for k, v in ag.v_func.state_dict().items()}
+    for _ in range(3):
+        ag.train(src, tar, B, None, None)
+    torch.cuda.synchronize()
+    assert ag._t_q == 3 and ag._t_pi == 3 and float(ag.q_optimizer.state_dict()["state"][0]["step"]) == 3.0
+    assert any(not torch.equal(v, before[k]) for k, v in ag.policy.state_dict().items())
+    assert any(not torch.equal(v, qb[k]) for k, v in ag.q_funcs.state_dict().items())
+    moved_v = any(not torch.equal(v, vb[k]) for k, v in ag.v_func.state_dict().items())
+    assert moved_v == bool(override.get("advantage", 0))                          # the value function trains only with advantage=1
+    assert all(bool(torch.isfinite(v).all()) for v in ag.policy.state_dict().values())
+    # switching back to the default config continues on the fused kernels from the same Adam state
+    ag.config.update(advantage=0, scale_Q=1, q_weighted=1)
+    ag.train(src, tar, B, None, None)
+    torch.cuda.synchronize()
+    assert ag._t_q == 4 and np.isfinite(list(ag.loss_scalars().values())).all()
+
+
+def test_torch_path_equals_fused_path_on_the_default_math():
+    """Cross-check of the two update paths: with the default flags forced through the torch path (autograd) one update must
+    give the parameters the fused kernels give (1e-4), which pins the torch path's formulas to the golden-checked ones."""
+    from mobody_b200 import _ffi
+    S, A, N, n_true = 17, 6, 320, 256
+    rng = np.random.default_rng(11)
+    RW = _ffi.lib().mobody_row_width(S, A)
+    rows = np.zeros((N, RW), np.float32)
+    rows[:, :2 * S + A + 1] = rng.standard_normal((N, 2 * S + A + 1)).astype(np.float32)
+    rows[:, S:S + A] = rng.uniform(-1, 1, (N, A)).astype(np.float32)
+    rows[:, 2 * S + A + 1] = (rng.random(N) > 0.1).astype(np.float32)
+    rows_d = torch.from_numpy(rows).cuda()
+    a1, _ = cuda_agent(S, A, 9)
+    a2, _ = cuda_agent(S, A, 9)
+    for _ in range(2):
+        a1.train_on_rows(rows_d, n_true)
+        a2._train_torch_path(rows_d, n_true, None, None)
+    torch.cuda.synchronize()
+    for m1, m2, tag in ((a1.policy, a2.policy, "pi"), (a1.q_funcs, a2.q_funcs, "q"), (a1.target_q_funcs, a2.target_q_funcs, "qt")):
+        for (k, v1), v2 in zip(m1.state_dict().items(), m2.state_dict().values()):
+            adam_close(v1.cpu().numpy(), v2.cpu().numpy(), 3e-4, 2, (tag, k))
