@@ -397,7 +397,7 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
     if (tracer && group == 0) cfg.trace[79 * 8 + 1] = clock64();
     float row_pmax = 0.f;
     for (int e0 = 0; e0 < MB_E; e0 += mbatch) {
-#pragma unroll 2
+#pragma unroll 1   // one code path for every element: a row's result must not depend on its position in the tile
       for (int i = etid; i < n_el; i += NEPI) {
         const int rr = i / S, j = i - rr * S;
         const size_t gr = (size_t)row0 + rr;
@@ -410,8 +410,8 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
           float ss = 0.f, mk = 0.f;
 #pragma unroll
           for (int e = 0; e < MB_E; ++e) {
-            const float d = mv[e] - mbar, dd = d * d;
-            ss += dd;
+            const float d = mv[e] - mbar, dd = __fmul_rn(d, d);    // explicit roundings (no contraction choices)
+            ss = __fadd_rn(ss, dd);
             if (e >= e0 && e < e0 + mbatch) dsq_s[(e - e0) * n_el + i] = (j < S - 1) ? dd : 0.f;   // quirk: last dim excluded (:246)
             if (e == member) mk = mv[e];
           }
@@ -423,7 +423,7 @@ step_tc_kernel(const StepArgs a, const unsigned char* __restrict__ dynb, const u
               const unsigned long long gid = a.row_ids ? (unsigned long long)a.row_ids[gr] : a.row0 + gr;
               ep = philox_normal1(philox_noise_block(a.seed, a.step, gid, (unsigned)(j >> 2)), j & 3);
             }
-            const float nv = mk + ep * sd;
+            const float nv = __fmaf_rn(ep, sd, mk);
             a.next_obs[(size_t)row0 * S + i] = nv;
             nobs_s[i] = nv;
           }
