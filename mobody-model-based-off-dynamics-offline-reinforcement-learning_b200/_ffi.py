@@ -58,6 +58,11 @@ class RolloutDesc(C.Structure):
     ]
 
 
+class PeerDesc(C.Structure):
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("base", C.c_void_p * 8), ("cap_rows", C.c_longlong), ("W", C.c_int),
+                ("epoch", C.c_uint), ("ctas", C.c_int)]
+
+
 class SampleJob(C.Structure):
     _fields_ = [("rows", C.c_void_p), ("n", C.c_longlong), ("size", C.c_uint), ("draw", C.c_uint), ("seed", C.c_ulonglong),
                 ("out", C.c_void_p)]
@@ -109,6 +114,14 @@ def lib():
         L.mobody_row_width.argtypes = [C.c_int, C.c_int]
         L.mobody_step.argtypes = [C.POINTER(StepDesc), C.c_void_p]
         L.mobody_rollout_stats_doubles.restype = C.c_int
+        L.mobody_rollout_push.argtypes = [C.POINTER(RolloutDesc), C.POINTER(PeerDesc), C.c_void_p]
+        L.mobody_peer_slot_floats.restype = C.c_longlong
+        L.mobody_peer_slot_floats.argtypes = [C.c_longlong, C.c_int]
+        L.mobody_peer_buffer_bytes.restype = C.c_longlong
+        L.mobody_peer_buffer_bytes.argtypes = [C.c_int, C.c_longlong, C.c_int]
+        L.mobody_peer_ack.argtypes = [C.POINTER(PeerDesc), C.c_uint, C.c_void_p]
+        L.mobody_peer_wait.argtypes = [C.POINTER(PeerDesc), C.c_void_p]
+        L.mobody_peer_slot.argtypes = [C.POINTER(PeerDesc), C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
         L.mobody_rollout.argtypes = [C.POINTER(RolloutDesc), C.c_void_p]
         L.mobody_policy_forward.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(MlpParams), C.c_float,
                                             C.c_void_p, C.c_void_p]

@@ -267,6 +267,23 @@ class MOBODY(object):
         self.dynamics._draw += int(T)
         return base
 
+    def _rollout_desc(self, init_obss, T, use_trg, ws, packed, eps=None, idx=None, row0=0, step0=None):
+        """A filled mobody_rollout_desc for start states ``init_obss`` [B,S] (device, contiguous) on workspace ``ws``.
+        ``packed`` None leaves the pack stage out (mobody_rollout_push does it, multi-GPU).  Returns (desc, keep-alive)."""
+        B, S = init_obss.shape
+        d = _ffi.RolloutDesc()
+        keep = self.dynamics.fill_step_desc(d.step, B, S, self.device, policy=self.policy.network, max_action=self.policy.max_action,
+                                            use_trg=use_trg)
+        d.step.obs, d.step.mean, d.step.raw_reward = _ffi.ptr(init_obss), _ffi.ptr(ws["mean"]), _ffi.ptr(ws["raw"])
+        d.step.step, d.step.row0 = self._take_draws(T, step0), int(row0)
+        d.T, d.filter_bad_rollout = T, int(bool(self.config.get("filter_bad_rollout", 1)))
+        d.env_filter = float(self.config.get("env_filter", 0.0))
+        d.eps_all, d.idx_all = _ffi.ptr(eps), _ffi.ptr(idx)
+        for k in ("obss", "acts", "nexts", "rews", "pens", "terms", "row_ids", "counts", "pos", "scratch", "stats", "ticket"):
+            setattr(d, k, _ffi.ptr(ws[k]))
+        d.packed = _ffi.ptr(packed)
+        return d, (keep, init_obss, eps, idx, ws, packed)
+
     def rollout_device(self, init_obss, rollout_length, use_trg=True, *, eps=None, idx=None, row0=0, out_packed=None,
                        sync=True, ws_slot=0, step0=None):
         """T-step imagined rollout entirely on the device (mobody.py:596-657 without its per-step D2H copies and
@@ -299,17 +316,7 @@ class MOBODY(object):
             idx = torch.as_tensor(np.asarray(idx) if not torch.is_tensor(idx) else idx).to(device=dev, dtype=torch.int64).contiguous()
         counts = ws["counts"]
         if B > 0:
-            d = _ffi.RolloutDesc()
-            keep = dyn.fill_step_desc(d.step, B, S, dev, policy=self.policy.network, max_action=self.policy.max_action,  # noqa: F841
-                                      use_trg=use_trg)
-            d.step.obs, d.step.mean, d.step.raw_reward = _ffi.ptr(init_obss), _ffi.ptr(ws["mean"]), _ffi.ptr(ws["raw"])
-            d.step.step, d.step.row0 = self._take_draws(T, step0), int(row0)
-            d.T, d.filter_bad_rollout = T, int(bool(self.config.get("filter_bad_rollout", 1)))
-            d.env_filter = float(self.config.get("env_filter", 0.0))
-            d.eps_all, d.idx_all = _ffi.ptr(eps), _ffi.ptr(idx)
-            for k in ("obss", "acts", "nexts", "rews", "pens", "terms", "row_ids", "counts", "pos", "scratch", "stats", "ticket"):
-                setattr(d, k, _ffi.ptr(ws[k]))
-            d.packed = _ffi.ptr(packed)
+            d, keep = self._rollout_desc(init_obss, T, use_trg, ws, packed, eps, idx, row0, step0)   # noqa: F841
             _ffi.check(_ffi.lib().mobody_rollout(C.byref(d), _ffi.stream_ptr(dev)))
         else:
             counts.zero_(); ws["stats"][:2].zero_()

@@ -6,7 +6,17 @@ with Philox draws keyed on the GLOBAL row id (results do not depend on the numbe
 exchange at the end assembles the transitions: a count all-gather plus an all-gather of padded
 per-rank slabs (an exact all-gather-v), concatenated rank-major.  No collective touches the data path
 of the rollout itself.  One process per GPU (torchrun); torch.distributed is plumbing only.
+
+Two assemblies of the per-rank results are offered:
+ * ``gather="p2p"`` (default on CUDA): the PACK stage of each rank's rollout stores its kept transitions straight into
+   slot ``rank`` of every rank's receive buffer through peer-mapped pointers (csrc/peer.cu: one kernel = gather + NVLink
+   stores + header + flag).  No collective kernel, no padding on the wire, the consumer waits on the device.
+ * ``gather="padded"`` / ``"padded_async"``: one NCCL all-gather of zero-padded slabs (round 1; kept as the fallback when
+   peer memory cannot be mapped, and for the CPU / gloo tests).
 """
+import ctypes as C
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -71,12 +81,168 @@ def allgather_slabs(slab, group=None, async_op=False):
     return out, out[:, -1, 0]
 
 
-def sharded_rollout(agent, init_obss, rollout_length, use_trg=True, *, group=None, gather=True, sharded_input=False):
+class PeerExchange:
+    """This rank's receive buffer, mapped by every rank of ``group``, plus the epoch bookkeeping of the push / wait / ack
+    protocol (include/mobody_b200.h: mobody_peer_desc).  torch only allocates the memory and carries the handles
+    (torch.distributed._symmetric_memory rendezvous, or legacy CUDA IPC through torch.multiprocessing.reductions); every
+    byte of the exchange is moved by rollout_pack_push_kernel."""
+
+    def __init__(self, cap_rows, W, device, group=None, mode=None):
+        from . import _ffi
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise RuntimeError("PeerExchange: at most 8 ranks (one NVSwitch box)")
+        self.cap_rows, self.W, self.device = int(cap_rows), int(W), torch.device(device)
+        lib = _ffi.lib()
+        self.slot_floats = int(lib.mobody_peer_slot_floats(self.cap_rows, self.W))
+        n_floats = int(lib.mobody_peer_buffer_bytes(self.world, self.cap_rows, self.W)) // 4
+        mode = mode or os.environ.get("MOBODY_PEER_MODE", "symm")
+        self.buf, self._keep, ptrs = None, None, None
+        if mode == "symm":
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                buf = symm_mem.empty(n_floats, dtype=torch.float32, device=self.device)
+                buf.zero_()
+                hdl = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
+                ptrs = [int(q) for q in hdl.buffer_ptrs]
+                self.buf, self._keep, self.mode = buf, hdl, "symmetric_memory"
+            except Exception as e:                                   # noqa: BLE001 -- fall through to legacy IPC
+                self._symm_error = repr(e)
+                mode = "ipc"
+        if mode == "ipc":
+            from torch.multiprocessing.reductions import reduce_tensor
+            buf = torch.zeros(n_floats, dtype=torch.float32, device=self.device)
+            fn, args = reduce_tensor(buf)
+            objs = [None] * self.world
+            dist.all_gather_object(objs, (fn, args), group=group)
+            peers, ptrs = [], []
+            for r, (f, a) in enumerate(objs):
+                if r == self.rank:
+                    peers.append(buf)
+                else:
+                    a = list(a); a[6] = self.device.index            # map the peer allocation into THIS device's context
+                    peers.append(f(*a))
+                ptrs.append(peers[-1].data_ptr())
+            self.buf, self._keep, self.mode = buf, peers, "cuda_ipc"
+        if ptrs is None:
+            raise RuntimeError(f"PeerExchange: unknown mode {mode!r}")
+        self.ptrs = ptrs
+        self.epoch = 0
+        self._push_done = [None, None]                               # event of the push kernel that last read workspace slot parity
+        self._side = torch.cuda.Stream(self.device)
+        self._descs = {}
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group)                                          # every buffer is zeroed before anyone pushes into it
+
+    def desc(self, epoch, ctas=0):
+        from . import _ffi
+        d = _ffi.PeerDesc()
+        d.world, d.rank, d.cap_rows, d.W, d.epoch, d.ctas = self.world, self.rank, self.cap_rows, self.W, int(epoch), int(ctas)
+        for r, q in enumerate(self.ptrs):
+            d.base[r] = q
+        return d
+
+    def views(self, epoch):
+        """(rows [world, cap_rows, W], header int32 [world, 5]) of the half that holds ``epoch`` in the local buffer."""
+        half = self.world * self.slot_floats
+        h = self.buf[(epoch & 1) * half:((epoch & 1) + 1) * half].view(self.world, self.slot_floats)
+        rows = h[:, :self.cap_rows * self.W].view(self.world, self.cap_rows, self.W)
+        hdr = h[:, self.cap_rows * self.W:self.cap_rows * self.W + 5].view(torch.int32)
+        return rows, hdr
+
+
+class GatheredRollout:
+    """Result of a p2p-gathered rollout: ``wait()`` makes the current stream wait (on the device) until every rank's rows have
+    landed; ``rows`` [world, cap, W] / ``header`` int32 [world, 5] are views of the local receive buffer, valid until the
+    second-next sharded_rollout call on this exchange (stream-ordered consumers are covered by the ack protocol)."""
+
+    def __init__(self, ex, epoch, widths, info):
+        self.ex, self.epoch, self.widths, self.info = ex, epoch, widths, info
+        self.rows, self.header = ex.views(epoch)
+        self._waited = False
+
+    def wait(self):
+        from . import _ffi
+        if not self._waited:
+            d = self.ex.desc(self.epoch)
+            _ffi.check(_ffi.lib().mobody_peer_wait(C.byref(d), _ffi.stream_ptr(self.ex.device)))
+            self._waited = True
+        return self
+
+    def counts(self):
+        """Host copy of the header: (kept per rank, produced transitions, reward sum).  One synchronising read."""
+        self.wait()
+        h = self.header.cpu()
+        kept = [int(v) for v in h[:, 0]]
+        produced = int(sum((int(h[r, 1]) & 0xFFFFFFFF) | (int(h[r, 2]) << 32) for r in range(h.shape[0])))
+        rsum = float(h[:, 3:5].contiguous().view(torch.float64).sum())
+        return kept, produced, rsum
+
+    def to_dict(self):
+        kept, produced, rsum = self.counts()
+        allp = torch.cat([self.rows[r, :kept[r]] for r in range(len(kept))], dim=0)
+        return unpack_transitions(allp, self.widths), {"num_transitions": produced, "reward_mean": rsum / max(produced, 1),
+                                                       "kept": int(sum(kept)), "kept_per_rank": kept, "exchange": self.ex.mode}
+
+
+def p2p_rollout(agent, local, T, use_trg, row0, cap, *, group=None, step0=None, exchange=None, ctas=0):
+    """This rank's shard rolled on the device with its PACK stage pushed to every rank (csrc/peer.cu).  Asynchronous: returns a
+    GatheredRollout handle; nothing is read back.  The push kernel runs on a side stream so that it overlaps whatever the
+    caller enqueues next (e.g. the next rollout); workspaces alternate with the exchange parity."""
+    from . import _ffi
+    lib, dev = _ffi.lib(), local.device
+    S, A = local.shape[1], agent.config["action_dim"]
+    W = 2 * S + A + 3
+    ex = exchange
+    if ex is None:
+        cache = agent.__dict__.setdefault("_peer_exchanges", {})
+        key = (int(cap), W, id(group))
+        ex = cache.get(key)
+        if ex is None:
+            ex = cache[key] = PeerExchange(cap, W, dev, group)
+    if cap > ex.cap_rows or W != ex.W:
+        raise ValueError("p2p_rollout: exchange is too small for this rollout")
+    ex.epoch += 1
+    e = ex.epoch
+    cur = torch.cuda.current_stream(dev)
+    pd = ex.desc(e, ctas)
+    if e > 2:    # everything enqueued on this stream so far has consumed epoch e - 2: peers may overwrite that half now
+        _ffi.check(lib.mobody_peer_ack(C.byref(pd), e - 2, _ffi.stream_ptr(dev)))
+    if ex._push_done[e & 1] is not None:
+        cur.wait_event(ex._push_done[e & 1])                         # the push of epoch e - 2 read the workspace we are about to reuse
+    B = local.shape[0]
+    local = _ffi.f32(local, dev)
+    ws = agent._rollout_workspace(T, B, S, A, 4 + (e & 1))
+    d, keep = agent._rollout_desc(local, T, use_trg, ws, None, row0=row0, step0=step0)
+    _ffi.check(lib.mobody_rollout(C.byref(d), _ffi.stream_ptr(dev)))
+    ev = torch.cuda.Event(); ev.record(cur)
+    with torch.cuda.stream(ex._side):
+        ex._side.wait_event(ev)
+        _ffi.check(lib.mobody_rollout_push(C.byref(d), C.byref(pd), C.c_void_p(ex._side.cuda_stream)))
+        done = torch.cuda.Event(); done.record(ex._side)
+    ex._push_done[e & 1] = done
+    ex._descs[e & 1] = (d, keep, pd)                                 # keep-alive until the slot is reused
+    info = {"kept_dev": ws["counts"][T + 1:T + 2], "counts_dev": ws["counts"], "stats_dev": ws["stats"][:2], "capacity": cap,
+            "world": ex.world, "exchange": ex.mode}
+    return GatheredRollout(ex, e, [S, A, S, 1, 1, 1], info)
+
+
+def _exchange_mode(agent):
+    for ex in getattr(agent, "_peer_exchanges", {}).values():
+        return ex.mode
+    return None
+
+
+def sharded_rollout(agent, init_obss, rollout_length, use_trg=True, *, group=None, gather=True, sharded_input=False, step0=None,
+                    exchange=None):
     """MOBODY.rollout over all ranks of ``group``.
 
     init_obss: the GLOBAL start states [B, S] (every rank passes the same tensor and takes its shard), or with
     ``sharded_input=True`` this rank's own shard (ranks must hold equal-sized shards; weak-scaling benches).
-    gather: False -> this rank's transitions only; "padded" -> ([world, cap+1, W] slabs, device counts, widths)
+    gather: False -> this rank's transitions only; "p2p" -> GatheredRollout handle (peer-memory push, asynchronous, see
+    p2p_rollout); "p2p_dict" -> the same, waited and compacted to a dict (one host read);
+    "padded" -> ([world, cap+1, W] slabs, device counts, widths)
     with no host synchronisation in the exchange; "padded_async" -> same plus the NCCL work handle, so the
     all-gather of step t overlaps the rollout of step t+1 (call .wait() before reading the slabs);
     True -> compact dict of the transitions of all ranks (rank-major).
@@ -90,12 +256,15 @@ def sharded_rollout(agent, init_obss, rollout_length, use_trg=True, *, group=Non
         local = init_obss[lo:hi]
         cap = shard_range(init_obss.shape[0], 0, world)[1] * T
     if not gather or T == 0:
-        return agent.rollout_device(local, T, use_trg, row0=lo)
+        return agent.rollout_device(local, T, use_trg, row0=lo, step0=step0)
+    if gather in ("p2p", "p2p_dict"):
+        res = p2p_rollout(agent, local, T, use_trg, lo, cap, group=group, step0=step0, exchange=exchange)
+        return res if gather == "p2p" else res.to_dict()
     S = local.shape[1]
     probe_w = getattr(agent, "config", {}).get("action_dim")
     W = 2 * S + probe_w + 3 if probe_w is not None else None
     if W is None or not local.is_cuda:       # generic path (CPU tests with a stand-in agent)
-        out, info = agent.rollout_device(local, T, use_trg, row0=lo)
+        out, info = agent.rollout_device(local, T, use_trg, row0=lo) if step0 is None else agent.rollout_device(local, T, use_trg, row0=lo, step0=step0)
         packed, widths = pack_transitions(out)
         allp, counts = allgather_transitions(packed, cap, group)
         stats = torch.tensor([info["num_transitions"], info["reward_mean"] * info["num_transitions"]], dtype=torch.float64,
@@ -105,7 +274,7 @@ def sharded_rollout(agent, init_obss, rollout_length, use_trg=True, *, group=Non
         return unpack_transitions(allp, widths), {"num_transitions": n, "reward_mean": float(stats[1].item()) / max(n, 1),
                                                   "kept": int(sum(counts)), "kept_per_rank": counts}
     slab = torch.empty(cap + 1, W, dtype=torch.float32, device=local.device)
-    out, info = agent.rollout_device(local, T, use_trg, row0=lo, out_packed=slab[:cap], sync=False)   # nothing read back
+    out, info = agent.rollout_device(local, T, use_trg, row0=lo, out_packed=slab[:cap], sync=False, step0=step0)   # nothing read back
     # in-band header row: kept rows (exact below 2^24), produced transitions, reward sum — written on the stream
     slab[cap, 0:1] = info["kept_dev"].float()
     slab[cap, 1:3] = info["stats_dev"].flip(0).float()
@@ -122,3 +291,50 @@ def sharded_rollout(agent, init_obss, rollout_length, use_trg=True, *, group=Non
     n = int(hdr[:, 1].sum())
     return unpack_transitions(allp, widths), {"num_transitions": n, "reward_mean": float(hdr[:, 2].sum()) / max(n, 1),
                                               "kept": int(sum(counts)), "kept_per_rank": counts}
+
+
+def self_check(agent, n_rows=10_007, group=None, rounds=5, seed=0):
+    """Correctness of the multi-rank assembly on live hardware: the transitions gathered from the ranks' shards must equal,
+    bit for bit, what THIS rank computes alone for all ``n_rows`` start states (Philox is keyed on the global row id, so a
+    row's result does not depend on its shard).  T = 1: same rows in the same order (rank-major == row order); T = 3: same
+    multiset (rank-major differs from the single-GPU step-major order only by a permutation).  The peer-memory exchange is
+    run ``rounds`` times back to back on fresh draws (both halves of the receive buffer, the ack hand-shake) and once
+    through the NCCL padded all-gather.  Collective: every rank must call it.  Returns {"ok": bool, ...}; never raises on a
+    mismatch (the caller reports it)."""
+    import numpy as np
+    dev = agent.device
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    S = agent.config["state_dim"]
+    g = torch.Generator().manual_seed(1234 + seed)
+    obs = (0.3 * torch.randn(n_rows, S, generator=g)).to(dev)          # same on every rank
+    res = {"world": world, "rows": n_rows}
+    ok = True
+    key = lambda m: m[np.lexsort(m.cpu().numpy().T[::-1])] if m.numel() else m    # noqa: E731
+    base = agent.dynamics._draw
+    ex_mode = None
+    for i in range(rounds):
+        T = 1 if i % 2 == 0 else 3
+        s0 = 1000 + 10 * i
+        full, fi = agent.rollout_device(obs, T, step0=s0)
+        want = fi["packed"][:fi["kept"]]
+        try:
+            out, info = sharded_rollout(agent, obs, T, group=group, gather="p2p_dict", step0=s0)
+            got = pack_transitions(out)[0]
+            ex_mode = info.get("exchange", ex_mode)
+            same = got.shape == want.shape and info["num_transitions"] == fi["num_transitions"] and info["kept"] == fi["kept"]
+            same = same and bool(torch.equal(got, want) if T == 1 else torch.equal(key(got), key(want)))
+        except Exception as e:                                            # noqa: BLE001
+            same, res["p2p_error"] = False, repr(e)
+        ok = ok and same
+    res["p2p"] = ok
+    full, fi = agent.rollout_device(obs, 1, step0=77)
+    (slabs, counts_dev, widths), _ = sharded_rollout(agent, obs, 1, group=group, gather="padded", step0=77)
+    cnt = [int(c) for c in counts_dev.cpu()]
+    nccl_ok = sum(cnt) == fi["kept"] and bool(torch.equal(torch.cat([slabs[r, :cnt[r]] for r in range(world)], 0), fi["packed"][:fi["kept"]]))
+    res["nccl"] = nccl_ok
+    agent.dynamics._draw = base
+    flag = torch.tensor([1.0 if ok else 0.0, 1.0 if nccl_ok else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    res["p2p"], res["nccl"] = bool(flag[0].item() == 1.0), bool(flag[1].item() == 1.0)
+    res["ok"] = res["p2p"] and res["nccl"]
+    return res

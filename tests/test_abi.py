@@ -80,7 +80,7 @@ def test_struct_layouts_match_header_via_gcc(libpath, tmp_path):
     structs = {"mobody_step_desc": _ffi.StepDesc, "mobody_train_desc": _ffi.TrainDesc,
                "mobody_dyn_params": _ffi.DynParams, "mobody_mlp_params": _ffi.MlpParams, "mobody_mlp_state": _ffi.MlpState,
                "mobody_rollout_desc": _ffi.RolloutDesc, "mobody_classifier_desc": _ffi.ClassifierDesc,
-               "mobody_sample_job": _ffi.SampleJob}
+               "mobody_sample_job": _ffi.SampleJob, "mobody_peer_desc": _ffi.PeerDesc}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void){']
     for cname, ct in structs.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
