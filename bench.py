@@ -3,7 +3,12 @@
 
 Workload at N=1: BASELINE.json configs[1] — halfcheetah-gravity shaped (obs 17 / act 6), 100 000 start
 states, rollout_length=1, 7-member ensemble, policy forward fused in.  At N>1 every rank rolls its own
-100 000 start states (weak scaling) and the synthetic transitions are all-gathered over NCCL.
+100 000 start states (weak scaling) and the pack stage of each rank's rollout pushes its transitions into
+every rank's receive buffer over peer memory (csrc/peer.cu; NCCL padded all-gather as the fallback).  The
+same run also reports a STRONG-scaling arm (BASELINE configs[2]: hopper, 1 000 000 start states,
+rollout_length=5, split over the N ranks) and, at N=1, one line per BASELINE config with its termination rate.
+Before the timed region every N>1 run verifies the exchange: the gathered transitions of a 10 007-row problem
+must equal, bit for bit, the single-GPU result (parallel.self_check) — reported as `exchange_check`.
 
 One "step" = one full rollout of the start states (policy + 7-member dynamics + reward ensemble +
 penalty + termination + penalty filter), exactly what MOBODY.rollout does per refresh.
@@ -66,6 +71,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, gpu):
         super().__init__(daemon=True)
         self.gpu, self.sm, self.mx, self.reasons, self._halt, self.n = gpu, [], [], set(), threading.Event(), 0
+        self.period = 0.005         # seconds between samples
         self.nv = None
         try:
             import pynvml
@@ -104,7 +110,7 @@ class ClockSampler(threading.Thread):
                 self.n += 1
             except Exception:
                 pass
-            self._halt.wait(0.005 if self.nv else 0.1)
+            self._halt.wait(self.period if self.nv else max(self.period, 0.1))
 
     def stop(self):
         self._halt.set(); self.join(timeout=6)
@@ -130,6 +136,92 @@ def build_dynamics(mb, s_dim, a_dim, precision, dev, seed=1):
                 prm.normal_(0.0, 0.1)                 # biases randomised so they matter (the reference zero-initialises them)
     return mb.MOBODYEnsembleDynamics({"encoder_loss_coef": 1, "domain_loss_coef": 0, "cycle_loss_coef": 0}, model, None, None,
                                      mb.get_termination_fn(TASK), penalty_coef=COEF, precision=precision)
+
+
+def build_config_dynamics(mb, env, s_dim, a_dim, dev, h0, gain, coef=1.0, precision="bf16x2", seed=3):
+    """Random-init ensemble (the reference module's own initialiser) whose decoder bias sits in the env's healthy set and
+    whose decoder weights are scaled so that a real share of the rows terminates at every step (SURVEY 8d recipe)."""
+    torch.manual_seed(seed)
+    model = mb.MOBODYModule(s_dim, a_dim, 256, 7, 5, device=dev, config={"mopo": 0, "latent_reward": 0})
+    with torch.no_grad():
+        for name, prm in model.named_parameters():
+            if name.endswith(".bias"):
+                prm.normal_(0.0, 0.1)
+        model.transition3.weight.mul_(gain)
+        model.transition3.bias.mul_(0.1)
+        model.transition3.bias[:, :, 0] += h0
+    task = {"hopper": "hopper-medium-v2", "ant": "ant-medium-v2", "walker2d": "walker2d-medium-v2", "halfcheetah": "halfcheetah-medium-v2"}[env]
+    return mb.MOBODYEnsembleDynamics({"encoder_loss_coef": 1, "domain_loss_coef": 0, "cycle_loss_coef": 0}, model, None, None,
+                                     mb.get_termination_fn(task), penalty_coef=coef, precision=precision)
+
+
+def config_obs(env, n, s_dim, seed, dev):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    x = 0.2 * torch.randn(n, s_dim, generator=g, device=dev)
+    x[:, 0] += {"hopper": 1.25, "walker2d": 1.25, "ant": 0.6, "halfcheetah": 0.0}[env]
+    return x
+
+
+def timed_rollouts(fn, reps):
+    """CUDA-event time of ``reps`` calls of ``fn`` (after one warm-up call) in seconds per call."""
+    fn(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / reps
+
+
+def baseline_config_lines(mb, dev):
+    """One entry per BASELINE.json config at its size (single GPU): transitions/s of the whole rollout (device timed), the
+    live rows entering every step and the share of rows that terminated -- compaction on shrinking batches is timed, not
+    assumed away."""
+    out = {}
+    cases = [("C1 walker2d-friction S17/A6 50k+2k starts T=1", "walker2d", 17, 6, [52_000], [1], 1.0, 4.0, 5.0),
+             ("C3 hopper-kinematic S11/A3 1M starts T=5", "hopper", 11, 3, [1_000_000], [5], 0.8, 4.0, 1.0),
+             ("C4 ant-friction S27/A8 50k starts T=5", "ant", 27, 8, [50_000], [5], 0.4, 4.0, 1.0),
+             ("C5 antmaze-umaze-style S29/A8 sweep", "ant", 29, 8, [10_000, 100_000, 1_000_000, 4_000_000], [1, 5], 0.35, 6.0, 1.0)]
+    for name, env, sd, ad, sizes, Ts, h0, gain, coef in cases:
+        dyn = build_config_dynamics(mb, env, sd, ad, dev, h0, gain, coef)
+        ag = build_agent(mb, sd, ad, dev, env_filter=1e9)
+        ag.dynamics = dyn
+        rows = []
+        for n in sizes:
+            obs = config_obs(env, n, sd, n, dev)
+            for T_ in Ts:
+                _, info = ag.rollout_device(obs, T_)
+                per = timed_rollouts(lambda: ag.rollout_device(obs, T_, sync=False), 3 if n * T_ >= 1_000_000 else 10)
+                cnt = info["rows_per_step"]
+                term = [round(1.0 - cnt[t + 1] / max(cnt[t], 1), 4) for t in range(len(cnt) - 1)]
+                rows.append({"start_states": n, "rollout_length": T_, "transitions": info["num_transitions"], "ms": per * 1e3,
+                             "transitions_per_s": info["num_transitions"] / per, "rows_per_step": cnt, "terminated_share_per_step": term})
+                ag._roll_ws.clear()
+            del obs
+        out[name] = rows if len(rows) > 1 else rows[0]
+        del ag, dyn
+        torch.cuda.empty_cache()
+    return out
+
+
+def step_kernel_traffic():
+    """roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the step kernel from an `ncu --set full`
+    capture of this bench command (profiles/step_kernel_traffic.json, written by scripts/ncu_traffic.py).  The record names
+    the sha256 of the kernel sources it was captured from; if the sources changed since, the number is stale -> None."""
+    import hashlib
+    try:
+        with open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json")) as f:
+            rec = json.load(f)
+        h = hashlib.sha256()
+        csrc = os.path.join(ROOT, "mobody-model-based-off-dynamics-offline-reinforcement-learning_b200", "csrc")
+        for fn in rec["sources"]:
+            with open(os.path.join(csrc, fn), "rb") as f:
+                h.update(f.read())
+        if h.hexdigest() != rec["sources_sha256"]:
+            return None, "stale (kernel sources changed since the ncu capture)"
+        return int(rec["dram_bytes_read"]) + int(rec["dram_bytes_write"]), rec.get("capture", "profiles/")
+    except Exception:
+        return None, "no ncu capture on record"
 
 
 def build_agent(mb, s_dim, a_dim, dev, seed=1, **overrides):
@@ -203,10 +295,11 @@ def cpu_train_rate(batch, threads, steps=5):
     return steps / (time.perf_counter() - t0)
 
 
-def gpu_train_rate(mb, dev, batch, steps=300, s_dim=None, a_dim=None):
+def gpu_train_rate(mb, dev, batch, steps=300, s_dim=None, a_dim=None, penalty_type="none", dynamics=None):
     """MOBODY.train steady state through the public API: device-resident buffers, Philox indices, fused step."""
     s_dim, a_dim = s_dim or S, a_dim or A
-    ag = build_agent(mb, s_dim, a_dim, dev, seed=2)
+    ag = build_agent(mb, s_dim, a_dim, dev, seed=2, penalty_type=penalty_type)
+    ag.dynamics = dynamics
     src, tar = mb.ReplayBuffer(s_dim, a_dim, dev), mb.ReplayBuffer(s_dim, a_dim, dev)
     src.convert_D4RL(synth_buffer_dict(200_000, 1, s_dim, a_dim)); tar.convert_D4RL(synth_buffer_dict(20_000, 2, s_dim, a_dim))
     ag.fake_replay_buffer.convert_D4RL(synth_buffer_dict(50_000, 3, s_dim, a_dim))
@@ -272,6 +365,57 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def strong_scaling_arm(mb, P, dev, dist, rank, world, steps):
+    """BASELINE configs[2]: hopper-kinematic, 1 000 000 start states, rollout_length 5, split over the ranks (strong scaling:
+    total work fixed).  Device-timed, max over ranks; transitions = what all ranks produced."""
+    env, sd, ad, total, T_ = "hopper", 11, 3, 1_000_000, 5
+    dyn = build_config_dynamics(mb, env, sd, ad, dev, 0.8, 4.0, 1.0)
+    ag = build_agent(mb, sd, ad, dev, env_filter=1e9)
+    ag.dynamics = dyn
+    lo, hi = P.shard_range(total, rank, world)
+    obs = config_obs(env, total, sd, 99, dev)[lo:hi].contiguous()          # same global states on every rank, this rank's range
+    produced = torch.zeros(1, dtype=torch.float64, device=dev)
+    pend = []
+
+    def one():
+        if dist is None:
+            _, info = ag.rollout_device(obs, T_, row0=lo, sync=False)
+            produced.add_(info["stats_dev"][1:2])
+        else:
+            h = P.p2p_rollout(ag, obs, T_, True, lo, P.shard_range(total, 0, world)[1] * T_)
+            produced.add_(h.info["stats_dev"][1:2])
+            pend.append(h)
+            if len(pend) > 1:
+                pend.pop(0).wait()
+    for _ in range(2):
+        one()
+    while pend:
+        pend.pop(0).wait()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    produced.zero_()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one()
+    while pend:
+        pend.pop(0).wait()
+    e1.record(); torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t = torch.tensor([e0.elapsed_time(e1), float(produced.item())], dtype=torch.float64, device=dev)
+    if dist is not None:
+        mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = t.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, n = float(mx[0]), float(sm[1])
+    else:
+        ms, n = float(t[0]), float(t[1])
+    return {"scaling": "strong", "workload": f"hopper-kinematic S{sd}/A{ad} rollout_length={T_}, {total} start states split over {world} GPU(s) (BASELINE configs[2])",
+            "value": n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps, "transitions_per_step": n / steps,
+            "start_states_per_gpu": hi - lo}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -282,6 +426,9 @@ def main():
     ap.add_argument("--rows", type=int, default=B_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the updates/sec measurement (short ncu runs)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the per-config lines and the strong-scaling arm (short ncu runs)")
+    ap.add_argument("--exchange", default=os.environ.get("MOBODY_EXCHANGE", "p2p"), choices=["p2p", "nccl"],
+                    help="N>1: peer-memory push (default) or the NCCL padded all-gather")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -301,7 +448,7 @@ def main():
     if dist is not None:
         dist.barrier()
     import mobody_b200 as mb
-    from mobody_b200 import _ffi
+    from mobody_b200 import _ffi, parallel as P
     enabled = list(getattr(_ffi, "ENABLED_PRECISIONS", ("fp32",)))
     prec = args.precision if args.precision != "auto" else ("bf16x2" if "bf16x2" in enabled else "fp32")
     dyn = build_dynamics(mb, S, A, prec, dev)
@@ -317,6 +464,17 @@ def main():
     obs_pool = [obs_dev] + [obs_dev.clone() for _ in range(n_pool - 1)]
     pool_i = [0]
 
+    # ---- N > 1: prove the exchange before timing it (gathered transitions == the single-GPU result, bit for bit) ----
+    exchange, check = "none", None
+    if dist is not None:
+        exchange = args.exchange
+        try:
+            check = P.self_check(ag, 10_007, rounds=4)
+            if exchange == "p2p" and not check["p2p"]:
+                exchange = "nccl"                                  # fall back, and say so in the line
+        except Exception as e:                                     # noqa: BLE001
+            check = {"ok": False, "error": repr(e)}
+            exchange = "nccl"
     pending = []
 
     def drain():
@@ -330,25 +488,27 @@ def main():
         x = obs_pool[pool_i[0] % n_pool]; pool_i[0] += 1
         if dist is None:
             o, info = ag.rollout_device(x, T, row0=rank * Bn, sync=False)
+        elif exchange == "p2p":
+            # shard = this rank's start states; the pack stage pushes the kept transitions into every rank's receive buffer
+            h = P.sharded_rollout(ag, x, T, sharded_input=True, gather="p2p")
+            info = h.info
+            pending.append(h)
+            if len(pending) > 1:
+                pending.pop(0).wait()                     # the exchange of step t-1 overlapped this step's rollout
         else:
-            # shard = this rank's start states; NCCL all-gather(v) of the synthetic transitions at the end
-            (o, counts_dev, widths, work), info = mb.parallel.sharded_rollout(ag, x, T, sharded_input=True, gather="padded_async")
+            (o, counts_dev, widths, work), info = P.sharded_rollout(ag, x, T, sharded_input=True, gather="padded_async")
             pending.append(work)
             if len(pending) > 1:
-                pending.pop(0).wait()                     # the all-gather of step t-1 overlapped this step's rollout
+                pending.pop(0).wait()
         produced.add_(info["stats_dev"][1:2])
-        return o, info
-
-    def exchange(out, info):
-        return None
 
     # ---- device-resident timing ----
     for _ in range(W):
-        o, i = one_rollout_device(); exchange(o, i)
+        one_rollout_device()
+    drain()
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
-    drain()
     sampler = ClockSampler(local_rank); sampler.start()
     torch.cuda.synchronize()
     produced.zero_()
@@ -356,8 +516,8 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        o, i = one_rollout_device(); exchange(o, i)
-    drain()                                               # every all-gather has completed before the closing event
+        one_rollout_device()
+    drain()                                               # every rank's rows of every step have landed before the closing event
     e1.record()
     torch.cuda.synchronize()
     if dist is not None:
@@ -369,25 +529,40 @@ def main():
     # ---- step-kernel-only timing for the roofline (same stream, events directly around the launch) ----
     from mobody_b200.dynamics import StepWorkspace
     ws = StepWorkspace(Bn, S, A, dev, want_act=True)
+    dyn.launch_step(obs_dev, None, ws, policy=ag.policy.network, max_action=1.0, step=0, row0=rank * Bn)   # (packs the weight images)
     kt = []
     for it in range(W + args.steps):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d = _ffi.StepDesc()
+        keep = dyn.fill_step_desc(d, Bn, S, dev, policy=ag.policy.network, max_action=1.0)     # noqa: F841 (image checksum passes run here, outside the events)
+        d.obs, d.step, d.row0, d.act_out = _ffi.ptr(obs_dev), it, rank * Bn, _ffi.ptr(ws.act)
+        d.next_obs, d.reward, d.raw_reward = _ffi.ptr(ws.next_obs), _ffi.ptr(ws.reward), _ffi.ptr(ws.raw_reward)
+        d.penalty, d.terminal, d.mean = _ffi.ptr(ws.penalty), _ffi.ptr(ws.terminal), _ffi.ptr(ws.mean)
         e0.record()
-        dyn.launch_step(obs_dev, None, ws, policy=ag.policy.network, max_action=1.0, step=it, row0=rank * Bn)
+        _ffi.check(_ffi.lib().mobody_step(d, _ffi.stream_ptr(dev)))
         e1.record()
         kt.append((e0, e1))
     torch.cuda.synchronize()
     k_ms = float(np.mean([a.elapsed_time(b) for a, b in kt[W:]]))
 
     # ---- end-to-end through the public API with host buffers ----
+    sampler.period = 0.02
     def one_rollout_e2e():
         import contextlib, io
         with contextlib.redirect_stdout(io.StringIO()):
-            tr, info = ag.rollout(obs_host, T)      # pinned HOST start states in, CPU tensors out (H2D + D2H inside)
-        return tr, info
-    for _ in range(2):
-        one_rollout_e2e()
+            if dist is None:
+                return ag.rollout(obs_host, T)      # pinned HOST start states in, CPU tensors out (H2D + D2H inside)
+            # N > 1: this rank's shard from HOST memory in, the transitions of ALL ranks out as CPU tensors (H2D + rollout +
+            # peer-memory exchange + D2H of the gathered rows inside)
+            return P.sharded_rollout_host(ag, obs_host, T) if exchange == "p2p" else e2e_nccl()
+
+    def e2e_nccl():
+        x = obs_host.to(dev, non_blocking=True)
+        out, info = P.sharded_rollout(ag, x, T, sharded_input=True, gather=True)
+        return {k: v.cpu() for k, v in out.items()}, info
+    for _ in range(3):                 # held like the timed loop holds them: both pinned result slabs exist before timing
+        tr, info = one_rollout_e2e()
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -396,14 +571,17 @@ def main():
         tr, info = one_rollout_e2e(); e2e_trans += info["num_transitions"]
         d2h = sum(v.numel() * v.element_size() for v in tr.values())
     torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        dist.barrier()
+    e2e_s = time.perf_counter() - t0           # (at N > 1 every rank's info already counts the whole job's transitions)
 
-    # ---- single-pass modes of the same step (looser stated bounds), reported next to the headline mode ----
+    # ---- single-pass fp16 mode of the same step (stated looser bound), reported next to the headline mode ----
     loose = {}
-    for lp in ("fp16", "bf16"):
+    for lp in ("fp16",):
         if lp == prec or lp not in enabled:
             continue
         dyn_l = build_dynamics(mb, S, A, lp, dev)
+        dyn_l.launch_step(obs_dev, None, ws, policy=ag.policy.network, max_action=1.0, step=0, row0=rank * Bn)
         lt = []
         for it in range(W + args.steps):
             flush.zero_()
@@ -414,61 +592,82 @@ def main():
             lt.append((e0, e1))
         torch.cuda.synchronize()
         loose[lp] = float(np.mean([a.elapsed_time(b) for a, b in lt[W:]]))
+    clocks = sampler.stop()
+    # ---- strong-scaling arm (BASELINE configs[2]) and, at N = 1, one line per BASELINE config ----
+    strong = cfg_lines = None
+    if not args.no_extras:
+        strong = strong_scaling_arm(mb, P, dev, dist, rank, world, min(args.steps, 5))
+        if world == 1:
+            cfg_lines = baseline_config_lines(mb, dev)
     # second BASELINE metric: Q-weighted BC updates/sec (one update = one steady-state MOBODY.train step)
     upd_dev = upd_wall = None
     big_dev = big_wall = None
+    par_dev = par_wall = None
     if rank == 0 and not args.no_train:
         upd_dev, upd_wall = gpu_train_rate(mb, dev, 128)
+        par_dev, par_wall = gpu_train_rate(mb, dev, 128, penalty_type="par", dynamics=dyn)     # the CLI default penalty: + one 128-row dynamics step per update
         big_dev, big_wall = gpu_train_rate(mb, dev, 4096, steps=40, s_dim=27, a_dim=8)     # BASELINE configs[3]: ant-shaped, batch 4096
-    clocks = sampler.stop()
 
     t = torch.tensor([dev_ms, e2e_s, float(n_trans), float(e2e_trans), k_ms], dtype=torch.float64, device=dev)
     if dist is not None:
         mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = t.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         dev_ms, e2e_s, k_ms = float(mx[0]), float(mx[1]), float(mx[4])
-        n_trans, e2e_trans = float(sm[2]), float(sm[3])
+        n_trans, e2e_trans = float(sm[2]), float(mx[3])
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
     pk, pk_src = peaks()
     flop = flop_per_transition(S, A)
-    split = {"fp32": 1, "bf16": 1, "fp16": 1, "bf16x2": 3}[prec]
+    split = {"fp32": 1, "fp16": 1, "bf16x2": 3}[prec]
     ach = flop * Bn / (k_ms * 1e-3) / 1e12
     peak = pk["bf16_tflops"]                               # kernel timed alone -> burst figure
     value = n_trans / (dev_ms * 1e-3)
+    traffic, traffic_src = step_kernel_traffic() if (Bn == 100_000 and prec == "bf16x2") else (None, "not captured for this workload")
+    # kernels launched per rollout: init, T steps (+2 image checksum/pack passes each), (T-1) x (3 compact + advance), 3 compact, pack (or pack+push), stats
+    launches_per_rollout = 1 + T * 1 + 4 + (T - 1) * 4 + 3 + 1 + 1 + (2 if world > 1 else 0)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": {"fp32": "f32", "bf16x2": "bf16x2 (hi+lo split, fp32-parity)", "bf16": "bf16", "fp16": "f16"}[prec], "data": "synthetic",
+        "dtype": {"fp32": "f32", "bf16x2": "bf16x2 (hi+lo split, fp32-parity)", "fp16": "f16"}[prec], "data": "synthetic",
         "config": {"workload": f"halfcheetah-gravity S{S}/A{A} rollout_length={T}, {Bn} start states per GPU, 7-member ensemble, hidden 256 "
                                f"(BASELINE configs[1])",
                    "precision": prec, "l2": f"inputs larger than L2: start states rotate over {n_pool} distinct buffers ({n_pool * Bn * S * 4 >> 20} MiB > 126 MB L2); "
                          "kernel-only timings flush L2 with a 256 MiB memset before each launch",
-                   "parallelism": f"dp{world} (start states sharded; NCCL all-gather of transitions)" if world > 1 else "single GPU"},
-        "e2e": {"value": e2e_trans / e2e_s, "unit": UNIT, "h2d_bytes_per_step": Bn * S * 4, "d2h_bytes_per_step": int(d2h)},
-        "gpu_launches": args.steps * (T + (T - 1) * 4 + 1 + 3 + 2),   # per rollout: init, T steps, (T-1) x (3 compact + advance), 3 compact, pack, stats
+                   "parallelism": (f"dp{world} (start states sharded; transitions assembled in every rank's buffer by "
+                                   f"{'peer-memory stores from the pack kernel' if exchange == 'p2p' else 'an NCCL all-gather of padded slabs'})")
+                                  if world > 1 else "single GPU"},
+        "e2e": {"value": e2e_trans / e2e_s, "unit": UNIT, "h2d_bytes_per_step": Bn * S * 4, "d2h_bytes_per_step": int(d2h),
+                "path": "MOBODY.rollout(host tensor)" if world == 1 else
+                        "parallel.sharded_rollout_host: host shard in, transitions of all ranks out as CPU tensors on every rank (exchange inside)"},
+        "gpu_launches": args.steps * launches_per_rollout,
         "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full (profiles/r01f_step_tc_ncu_full_selected.csv);
-                     # algorithmic I/O is 240 B x 100 000 = 24.0 MB (part of the outputs is still in L2 when the kernel ends)
-                     "traffic": 21497856 if (Bn == 100_000 and prec == "bf16x2") else None, "kernel": "fused rollout step", "kernel_ms": k_ms, "peak_source": pk_src + " bf16 burst",
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "kernel": "fused rollout step", "kernel_ms": k_ms, "peak_source": pk_src + " bf16 burst",
                      "mma_passes_per_gemm": split, "frac_of_mma_issued": ach * split / peak,
-                     "flop_per_transition": flop},
+                     "flop_per_transition": flop, "algorithmic_io_bytes": Bn * (3 * S + A + 3) * 4},
         "clocks": clocks, "wall_s": wall,
     }
+    if world > 1:
+        line["exchange"] = {"mode": exchange, "peer_memory": P._exchange_mode(ag), "check": check}
+    if strong is not None:
+        line["strong_scaling"] = strong
+    if cfg_lines is not None:
+        line["baseline_configs"] = cfg_lines
     for lp, ms in loose.items():
         la = flop * Bn / (ms * 1e-3) / 1e12
         line["roofline"][lp + "_single_pass"] = {
             "kernel_ms": ms, "achieved": la, "frac": la / peak, "transitions_per_s": Bn / (ms * 1e-3),
-            "tolerance": {"fp16": "5e-3 relative (the stated looser bound of north_star for reduced-precision GEMMs; measured <= 4.6e-3)",
-                          "bf16": "2e-2 relative (measured <= 1.6e-2)"}[lp]}
+            "tolerance": "5e-3 relative (the stated looser bound of north_star for reduced-precision GEMMs; measured <= 4.6e-3)"}
     if not args.no_train:
         line["hbm_stages"] = hbm_stage_rates(mb, dev, pk["hbm_gbs"])
     if upd_wall is not None:
         line["train"] = {"metric": "Q-weighted BC updates/sec", "value": upd_wall, "unit": "updates/s", "device_only": upd_dev,
                          "config": {"workload": f"MOBODY.train steady state, batch 128 (128 src + 128 tar + 64 fake rows), S{S}/A{A}",
                                     "launches_per_update": 10, "dtype": "f32 (3xTF32 tensor-core MMA for the 256-wide layers, fp32 elsewhere)"},
+                         "penalty_type_par": {"value": par_wall, "device_only": par_dev, "unit": "updates/s",
+                                              "workload": "same with penalty_type='par' (the CLI default): + one fused 128-row dynamics step and the reward shift per update, no host sync"},
                          "batch4096_S27A8": {"value": big_wall, "device_only": big_dev, "unit": "updates/s",
                                              "workload": "MOBODY.train steady state, batch 4096 (4096 src + 4096 tar + 2048 fake rows), S27/A8 (BASELINE configs[3])"}}
     if not args.no_cpu_baseline:

@@ -563,16 +563,35 @@ __device__ __forceinline__ void pack_bias(const float* __restrict__ b, long long
 // 64-bit integers, so the atomics make it order independent: any write to the live fp32 parameters -- optimiser step,
 // load_state_dict, `.data.copy_()` (mobody_module.py:407-408), a raw pointer write -- is seen without asking the host.
 struct ChecksumArgs { const float* p[26]; unsigned int n[26]; int count; };
-__global__ void params_checksum_kernel(const ChecksumArgs a, unsigned long long* __restrict__ state) {
+__global__ void __launch_bounds__(256) params_checksum_kernel(const ChecksumArgs a, unsigned long long* __restrict__ state) {
   const int t = blockIdx.y;
   const unsigned int n = a.n[t];
+  const unsigned int per = 256u * 8u;                               // elements per block per sweep: 8 independent loads per thread
+  if (blockIdx.x * per >= n) return;
   const uint32_t* x = reinterpret_cast<const uint32_t*>(a.p[t]);
+  const uint32_t salt = 0x9E3779B9u * (uint32_t)(t + 1);
   unsigned long long h = 0;
-  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    h += (unsigned long long)(x[i] ^ (0x9E3779B9u * (uint32_t)(t + 1))) * (2ull * i + 1ull) + (unsigned long long)(t + 1);
+  for (unsigned int base = blockIdx.x * per; base < n; base += gridDim.x * per) {
+    uint32_t v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const unsigned int i = base + k * 256u + threadIdx.x; v[k] = i < n ? x[i] : 0u; }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const unsigned int i = base + k * 256u + threadIdx.x;
+      if (i < n) h += (unsigned long long)(v[k] ^ salt) * (2ull * i + 1ull) + (unsigned long long)(t + 1);
+    }
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
-  if ((threadIdx.x & 31) == 0 && h) atomicAdd(state + 1, h);
+  __shared__ unsigned long long sh[8];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = h;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long s = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += sh[w];
+    if (s) atomicAdd(state + 1, s);
+  }
 }
 // true -> this block must (re)pack.  Every block reads the two checksums first; the last block to finish commits.
 __device__ __forceinline__ bool pack_needed(const unsigned long long* state) {
@@ -644,9 +663,9 @@ const char* mb_tc_dyn_pack(const DynPtrs& dp, int S, int A, int ns, int fp16, un
       c.p[2 * l] = dp.w[l]; c.n[2 * l] = (unsigned)(MB_E * in * out);
       c.p[2 * l + 1] = dp.b[l]; c.n[2 * l + 1] = (unsigned)(MB_E * out);
     }
-    tcs::params_checksum_kernel<<<dim3(16, c.count), 256, 0, st>>>(c, state);
+    tcs::params_checksum_kernel<<<dim3(64, c.count), 256, 0, st>>>(c, state);
   }
-  tcs::pack_dyn_kernel<<<dim3(32, MB_E * (PK_COUNT + 1)), 256, 0, st>>>(dp, S, A, ns, fp16, blob, state);
+  tcs::pack_dyn_kernel<<<dim3(8, MB_E * (PK_COUNT + 1)), 256, 0, st>>>(dp, S, A, ns, fp16, blob, state);
   return nullptr;
 }
 
@@ -656,7 +675,7 @@ const char* mb_tc_mlp_pack(const MlpPtrs& mp, int din, int dout, int ns, int fp1
     tcs::ChecksumArgs c{}; c.count = 6;
     const int K[3] = {din, 256, 256}, N[3] = {256, 256, dout};
     for (int l = 0; l < 3; ++l) { c.p[2 * l] = mp.w[l]; c.n[2 * l] = (unsigned)(K[l] * N[l]); c.p[2 * l + 1] = mp.b[l]; c.n[2 * l + 1] = (unsigned)N[l]; }
-    tcs::params_checksum_kernel<<<dim3(16, c.count), 256, 0, st>>>(c, state);
+    tcs::params_checksum_kernel<<<dim3(32, c.count), 256, 0, st>>>(c, state);
   }
   tcs::pack_mlp_kernel<<<dim3(32, 3), 256, 0, st>>>(mp, din, dout, ns, fp16, blob, state);
   return nullptr;

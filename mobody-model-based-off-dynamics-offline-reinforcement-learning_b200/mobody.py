@@ -347,6 +347,7 @@ class MOBODY(object):
             if slab.shape[1] == W and slab.shape[0] >= rows and _storage_idle(slab):
                 return slab
         slab = torch.empty(max(rows, 1), W, dtype=torch.float32, pin_memory=True)
+        self._slab_allocs = getattr(self, "_slab_allocs", 0) + 1
         self._host_slabs = [t for t in self._host_slabs if not _storage_idle(t)][-3:] + [slab]   # idle leftovers are too small: drop them
         return slab
 

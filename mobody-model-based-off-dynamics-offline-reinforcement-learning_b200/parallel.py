@@ -65,20 +65,20 @@ def allgather_transitions(packed, capacity, group=None):
 
 
 def allgather_slabs(slab, group=None, async_op=False):
-    """One collective for an exact all-gather-v: ``slab`` is [capacity + 1, W] with this rank's row count stored
-    in-band at slab[capacity, 0].  Returns ([world, capacity + 1, W], counts as a device float tensor[world]);
-    no host synchronisation."""
+    """One collective for an exact all-gather-v: ``slab`` is [capacity + 1, W] with this rank's header stored in-band in
+    the last row as INTEGER words (int32 kept rows, int32 produced transitions, float64 reward sum).  Returns
+    ([world, capacity + 1, W], kept rows as a device int32 tensor[world]); no host synchronisation."""
     world = dist.get_world_size(group)
     out = torch.empty((world,) + tuple(slab.shape), dtype=slab.dtype, device=slab.device)
     if slab.is_cuda:
         work = dist.all_gather_into_tensor(out, slab, group=group, async_op=async_op)
         if async_op:                        # NCCL runs on its own stream; work.wait() orders the caller's stream after it
-            return out, out[:, -1, 0], work
+            return out, out[:, -1, :1].view(torch.int32)[:, 0], work
     else:                                   # gloo (CPU tests)
         parts = [torch.empty_like(slab) for _ in range(world)]
         dist.all_gather(parts, slab, group=group)
         out = torch.stack(parts, 0)
-    return out, out[:, -1, 0]
+    return out, out[:, -1, :1].view(torch.int32)[:, 0]
 
 
 class PeerExchange:
@@ -173,7 +173,7 @@ class GatheredRollout:
     def counts(self):
         """Host copy of the header: (kept per rank, produced transitions, reward sum).  One synchronising read."""
         self.wait()
-        h = self.header.cpu()
+        h = self.header.contiguous().cpu()
         kept = [int(v) for v in h[:, 0]]
         produced = int(sum((int(h[r, 1]) & 0xFFFFFFFF) | (int(h[r, 2]) << 32) for r in range(h.shape[0])))
         rsum = float(h[:, 3:5].contiguous().view(torch.float64).sum())
@@ -228,6 +228,27 @@ def p2p_rollout(agent, local, T, use_trg, row0, cap, *, group=None, step0=None, 
     return GatheredRollout(ex, e, [S, A, S, 1, 1, 1], info)
 
 
+def sharded_rollout_host(agent, host_shard, rollout_length, use_trg=True, *, group=None, step0=None):
+    """MOBODY.rollout's host contract (mobody.py:596-657: start states in, dict of CPU tensors out) for start states sharded
+    over the ranks: THIS rank's shard [B_r, S] comes from (pinned) host memory, the transitions of ALL ranks come back as CPU
+    tensors on every rank, rank-major.  H2D of the shard, the rollout, the peer-memory exchange and the D2H of the gathered
+    rows all happen inside the call (equal shard sizes; weak-scaling e2e)."""
+    dev = agent.device
+    T = int(rollout_length)
+    x = host_shard.to(dev, non_blocking=True)
+    res = sharded_rollout(agent, x, T, use_trg, group=group, gather="p2p", sharded_input=True, step0=step0)
+    kept, produced, rsum = res.counts()                                   # waits for every rank's rows, one small D2H
+    W = res.rows.shape[2]
+    host = agent._host_slab(sum(kept), W)
+    off = 0
+    for r, m in enumerate(kept):
+        host[off:off + m].copy_(res.rows[r, :m], non_blocking=True)
+        off += m
+    torch.cuda.current_stream(dev).synchronize()
+    return unpack_transitions(host[:off], res.widths), {"num_transitions": produced, "reward_mean": rsum / max(produced, 1),
+                                                        "kept": off, "kept_per_rank": kept}
+
+
 def _exchange_mode(agent):
     for ex in getattr(agent, "_peer_exchanges", {}).values():
         return ex.mode
@@ -275,9 +296,11 @@ def sharded_rollout(agent, init_obss, rollout_length, use_trg=True, *, group=Non
                                                   "kept": int(sum(counts)), "kept_per_rank": counts}
     slab = torch.empty(cap + 1, W, dtype=torch.float32, device=local.device)
     out, info = agent.rollout_device(local, T, use_trg, row0=lo, out_packed=slab[:cap], sync=False, step0=step0)   # nothing read back
-    # in-band header row: kept rows (exact below 2^24), produced transitions, reward sum — written on the stream
-    slab[cap, 0:1] = info["kept_dev"].float()
-    slab[cap, 1:3] = info["stats_dev"].flip(0).float()
+    # in-band header row, integer words (exact at any size): int32 kept rows, int32 produced transitions, float64 reward sum
+    hdr = slab[cap, :4].view(torch.int32)
+    hdr[0:1] = info["kept_dev"]
+    hdr[1:2] = info["stats_dev"][1:2].to(torch.int32)
+    hdr[2:4] = info["stats_dev"][0:1].clone().view(torch.int32)        # the double's two words (the row need not be 8-byte aligned)
     widths = [S, probe_w, S, 1, 1, 1]
     if gather == "padded_async":
         slabs, counts_dev, work = allgather_slabs(slab, group, async_op=True)
@@ -285,11 +308,13 @@ def sharded_rollout(agent, init_obss, rollout_length, use_trg=True, *, group=Non
     slabs, counts_dev = allgather_slabs(slab, group)
     if gather == "padded":
         return (slabs, counts_dev, widths), dict(info, world=world, capacity=cap)
-    hdr = slabs[:, cap, :3].double().cpu()                             # the one host read of the exchange
-    counts = [int(c) for c in hdr[:, 0]]
+    hdr = slabs[:, cap, :4].contiguous().cpu()                         # the one host read of the exchange
+    hi = hdr.view(torch.int32)
+    counts = [int(c) for c in hi[:, 0]]
     allp = torch.cat([slabs[r, :counts[r]] for r in range(world)], dim=0)
-    n = int(hdr[:, 1].sum())
-    return unpack_transitions(allp, widths), {"num_transitions": n, "reward_mean": float(hdr[:, 2].sum()) / max(n, 1),
+    n = int(hi[:, 1].sum())
+    rsum = float(hi[:, 2:4].contiguous().view(torch.float64).sum())
+    return unpack_transitions(allp, widths), {"num_transitions": n, "reward_mean": rsum / max(n, 1),
                                               "kept": int(sum(counts)), "kept_per_rank": counts}
 
 
