@@ -609,7 +609,11 @@ def main():
         big_dev, big_wall = gpu_train_rate(mb, dev, 4096, steps=40, s_dim=27, a_dim=8)     # BASELINE configs[3]: ant-shaped, batch 4096
 
     t = torch.tensor([dev_ms, e2e_s, float(n_trans), float(e2e_trans), k_ms], dtype=torch.float64, device=dev)
+    per_rank = None
     if dist is not None:
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank = {"ms_per_step": [round(float(x[0]) / args.steps, 4) for x in allt], "step_kernel_ms": [round(float(x[4]), 4) for x in allt]}
         mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = t.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         dev_ms, e2e_s, k_ms = float(mx[0]), float(mx[1]), float(mx[4])
@@ -651,6 +655,7 @@ def main():
     }
     if world > 1:
         line["exchange"] = {"mode": exchange, "peer_memory": P._exchange_mode(ag), "check": check}
+        line["per_rank"] = per_rank
     if strong is not None:
         line["strong_scaling"] = strong
     if cfg_lines is not None:

@@ -194,30 +194,35 @@ typedef struct mobody_rollout_desc {
   float* packed;              /* device [T*B, 2S+A+3]                                                  */
 } mobody_rollout_desc;
 /* ---- multi-GPU assembly of the synthetic transitions over peer memory ----
- * Every rank owns a receive buffer that its peers have mapped (CUDA IPC / symmetric memory; the host side only exchanges
+ * Every rank owns a receive buffer that its peers have mapped (symmetric memory / CUDA IPC; the host side only exchanges
  * handles): two `halves` (parity of the exchange number) of `world` slots, each slot = [cap_rows][W] packed transitions
- * followed by one header row, and a flag block behind them.  mobody_rollout_push is the PACK stage of a rollout executed
- * with stores to slot `rank` of EVERY rank's buffer (its own included): one kernel gathers the kept transitions from the
- * rollout workspace and writes them over NVLink, then publishes the header {int32 kept, int64 produced, double reward
- * sum} and raises flag[rank] = epoch at every rank (system-scope release).  It replaces the NCCL all-gather of padded
- * slabs: no collective kernel, no padding on the wire.  A rank may overwrite half (epoch & 1) at a peer only after that
- * peer acknowledged epoch - 2 (mobody_peer_ack, stream-ordered after the peer's consumers); the push kernel waits for it.
- * mobody_peer_wait makes `stream` wait (device-side spin, no host involvement) until every rank's rows of `epoch` landed. */
+ * followed by one header row, and a flag block behind them.  A rank's rollout packs into slot `rank` of its OWN buffer
+ * (mobody_rollout with desc.packed = that slot); mobody_peer_push then streams exactly the kept rows into the same slot of
+ * every peer's buffer with 128-bit NVLink stores -- or with ONE NVSwitch-replicated multicast store per 16 bytes when a
+ * multicast mapping is given -- publishes the header {int32 kept, int64 produced, double reward sum} and raises
+ * flag[rank] = epoch at every rank (system-scope release).  It replaces the NCCL all-gather of padded slabs: no
+ * collective kernel, no padding on the wire, a few CTAs on a side stream beside the next rollout.  A rank may overwrite
+ * half (epoch & 1) at a peer only after that peer acknowledged epoch - 2 (mobody_peer_ack, stream-ordered after the
+ * peer's consumers); the push kernel waits for it.  mobody_peer_wait makes `stream` wait (device-side spin, no host
+ * involvement) until every rank's rows of `epoch` have landed. */
 #define MOBODY_MAX_PEERS 8
 typedef struct mobody_peer_desc {
   int world, rank;
   void* base[MOBODY_MAX_PEERS];   /* base[r]: rank r's receive buffer as mapped in THIS process (base[rank] is local)   */
+  void* multicast;                /* NULL, or the multicast mapping of the same buffers (NVLS)                          */
   long long cap_rows;             /* rows per slot (>= T*B of the largest shard)                                        */
   int W;                          /* floats per packed transition (2S+A+3)                                              */
   unsigned int epoch;             /* exchange number, 1, 2, 3, ... (monotone; same on every rank)                       */
-  int ctas;                       /* CTAs of the push kernel (0 = default): kept small, it runs beside the next rollout */
+  int ctas;                       /* CTAs of the push kernel (0 = default 8): kept small, it runs beside the next rollout */
 } mobody_peer_desc;
 long long mobody_peer_slot_floats(long long cap_rows, int W);     /* floats per slot incl. header row, padded to 16 B   */
 long long mobody_peer_buffer_bytes(int world, long long cap_rows, int W);   /* receive buffer: 2 halves + flag block    */
-int mobody_peer_ack(const mobody_peer_desc* p, unsigned int consumed_epoch, void* stream);
-int mobody_peer_wait(const mobody_peer_desc* p, void* stream);
 /* slot r of the half holding p->epoch in the LOCAL buffer: rows pointer and header pointer (host arithmetic only) */
 int mobody_peer_slot(const mobody_peer_desc* p, int r, float** rows, int** header);
+/* push slot `rank` (rows [0, *kept_dev)) of the local buffer to every peer; stats_dev = {reward sum, produced} doubles */
+int mobody_peer_push(const mobody_peer_desc* p, const int* kept_dev, const double* stats_dev, void* stream);
+int mobody_peer_ack(const mobody_peer_desc* p, unsigned int consumed_epoch, void* stream);
+int mobody_peer_wait(const mobody_peer_desc* p, void* stream);
 
 int mobody_rollout_stats_doubles(void);   /* size of mobody_rollout_desc.stats in doubles */
 int mobody_rollout(const mobody_rollout_desc* d, void* stream);

@@ -59,7 +59,7 @@ class RolloutDesc(C.Structure):
 
 
 class PeerDesc(C.Structure):
-    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("base", C.c_void_p * 8), ("cap_rows", C.c_longlong), ("W", C.c_int),
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("base", C.c_void_p * 8), ("multicast", C.c_void_p), ("cap_rows", C.c_longlong), ("W", C.c_int),
                 ("epoch", C.c_uint), ("ctas", C.c_int)]
 
 
@@ -114,7 +114,7 @@ def lib():
         L.mobody_row_width.argtypes = [C.c_int, C.c_int]
         L.mobody_step.argtypes = [C.POINTER(StepDesc), C.c_void_p]
         L.mobody_rollout_stats_doubles.restype = C.c_int
-        L.mobody_rollout_push.argtypes = [C.POINTER(RolloutDesc), C.POINTER(PeerDesc), C.c_void_p]
+        L.mobody_peer_push.argtypes = [C.POINTER(PeerDesc), C.c_void_p, C.c_void_p, C.c_void_p]
         L.mobody_peer_slot_floats.restype = C.c_longlong
         L.mobody_peer_slot_floats.argtypes = [C.c_longlong, C.c_int]
         L.mobody_peer_buffer_bytes.restype = C.c_longlong

@@ -48,7 +48,7 @@ long long mb_peer_buffer_bytes(int world, long long cap_rows, int W);
 const char* mb_peer_slot(const mobody_peer_desc* p, int r, float** rows, int** header);
 const char* mb_peer_ack_launch(const mobody_peer_desc* p, unsigned int consumed, cudaStream_t st);
 const char* mb_peer_wait_launch(const mobody_peer_desc* p, cudaStream_t st);
-const char* mb_rollout_push_launch(const mobody_rollout_desc* d, const mobody_peer_desc* p, cudaStream_t st);
+const char* mb_peer_push_launch(const mobody_peer_desc* p, const int* kept_dev, const double* stats_dev, cudaStream_t st);
 void mb_tc_set_trace(long long* buf);
 long long mb_train_workspace_bytes(int N, int S, int A, int nsplit);
 const char* mb_train_step_launch(const mobody_train_desc& d, cudaStream_t st);
@@ -263,7 +263,7 @@ int mobody_rollout(const mobody_rollout_desc* d, void* stream) {
   if (!s0.policy) return fail(MOBODY_ERR_ARG, "mobody_rollout: the step template needs a policy (actions come from pi(s))");
   if (s0.obs_ld && s0.obs_ld != S) return fail(MOBODY_ERR_ARG, "mobody_rollout: start states must be dense [B,S]");
   if (!s0.obs || !d->obss || !d->acts || !d->nexts || !d->rews || !d->pens || !d->terms || !d->row_ids || !d->counts || !d->pos ||
-      !d->scratch || !d->stats || !d->ticket)
+      !d->scratch || !d->stats || !d->ticket || !d->packed)
     return fail(MOBODY_ERR_ARG, "mobody_rollout: null workspace pointer");
   cudaStream_t st = (cudaStream_t)stream;
   if (s0.obs != d->obss &&
@@ -289,19 +289,15 @@ int mobody_rollout(const mobody_rollout_desc* d, void* stream) {
     mb_compact_launch(MOBODY_KEEP_F32_LE, nullptr, d->pens, d->env_filter, (long long)T * B, nullptr, d->scratch, d->pos, d->counts + T + 1, st);
   else
     mb_compact_launch(MOBODY_KEEP_U8_VALID, d->terms, nullptr, 0.f, (long long)T * B, nullptr, d->scratch, d->pos, d->counts + T + 1, st);
-  if (d->packed)     // NULL: the pack stage is mobody_rollout_push's (multi-GPU: rows go straight to every rank's slot)
-    mb_rollout_pack_launch(d->obss, d->acts, d->nexts, d->rews, d->terms, d->pens, S, A, d->pos, d->counts + T + 1, (long long)T * B,
-                           d->packed, st);
+  mb_rollout_pack_launch(d->obss, d->acts, d->nexts, d->rews, d->terms, d->pens, S, A, d->pos, d->counts + T + 1, (long long)T * B,
+                         d->packed, st);
   mb_rollout_stats_launch(d->rews, d->terms, (long long)T * B, d->stats + 2, d->ticket, d->stats, st);
   return check_launch("mobody_rollout");
 }
 
-int mobody_rollout_push(const mobody_rollout_desc* d, const mobody_peer_desc* p, void* stream) {
-  if (!d || !p) return fail(MOBODY_ERR_ARG, "mobody_rollout_push: null descriptor");
-  if (d->T < 1 || d->step.B < 1 || !d->obss || !d->acts || !d->nexts || !d->rews || !d->pens || !d->terms || !d->pos || !d->counts || !d->stats)
-    return fail(MOBODY_ERR_ARG, "mobody_rollout_push: the rollout descriptor's workspace is incomplete");
-  if (const char* e = mb_rollout_push_launch(d, p, (cudaStream_t)stream)) return fail(MOBODY_ERR_ARG, e);
-  return check_launch("mobody_rollout_push");
+int mobody_peer_push(const mobody_peer_desc* p, const int* kept_dev, const double* stats_dev, void* stream) {
+  if (const char* e = mb_peer_push_launch(p, kept_dev, stats_dev, (cudaStream_t)stream)) return fail(MOBODY_ERR_ARG, e);
+  return check_launch("mobody_peer_push");
 }
 long long mobody_peer_slot_floats(long long cap_rows, int W) { return (cap_rows < 1 || W < 5) ? 0 : mb_peer_slot_floats(cap_rows, W); }
 long long mobody_peer_buffer_bytes(int world, long long cap_rows, int W) {

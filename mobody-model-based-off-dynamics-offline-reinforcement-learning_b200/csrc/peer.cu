@@ -1,10 +1,11 @@
 // Multi-GPU assembly of the synthetic transitions over peer memory.
 //
 // The reference is single-GPU; when rollout start states are sharded over the GPUs of a box, every rank needs all
-// transitions in its own (device-resident) fake buffer.  Instead of an NCCL all-gather of padded slabs, the PACK stage of
-// the rollout writes the kept transitions straight into slot `rank` of every rank's receive buffer through peer-mapped
-// pointers (NVLink stores), and raises a flag there.  No collective kernel competes with the step kernel for SMs, no
-// padding travels, and the consumer waits on the device.
+// transitions in its own (device-resident) fake buffer.  Instead of an NCCL all-gather of padded slabs, a rank's rollout
+// packs its kept transitions straight into slot `rank` of its OWN receive buffer, and a narrow streaming kernel on a
+// high-priority side stream copies exactly those rows into the same slot of every peer's buffer through peer-mapped
+// pointers (NVLink stores; one NVSwitch-replicated multicast store when the fabric offers it), then raises a flag there.
+// Only kept rows travel, the copy overlaps the next rollout, and the consumer waits on the device.
 //
 // Receive buffer of one rank (mapped by all):  [half 0 | half 1 | flag block]
 //   half h    = world slots; slot r = [cap_rows][W] packed transitions of rank r + one header row
@@ -28,15 +29,22 @@ constexpr int FLAG_WORDS = 32;   // arrive[8] ack[8] ticket pad
 constexpr int ACK = 8, TICKET = 16;
 
 struct PushArgs {
-  const float *obss, *acts, *nexts, *rews, *pens; const unsigned char* terms; const int* pos; const int* m_dev; long long m_cap;
-  const double* stats; int S, A;
-  float* dst[MOBODY_MAX_PEERS];       // slot `rank` of half (epoch & 1) at every rank
+  const float* src;                   // local slot `rank` of half (epoch & 1): rows written by the rollout's pack kernel
+  const int* m_dev; long long m_cap; const double* stats;
+  float* dst[MOBODY_MAX_PEERS];       // the same slot at every rank (dst[rank] == src)
+  float* mc_dst;                      // the same slot through the multicast mapping (NVLS: one store reaches every rank), or nullptr
   unsigned* flags[MOBODY_MAX_PEERS];  // flag block of every rank
   int world, rank; unsigned epoch; long long cap_rows; int W;
 };
 
-// One kernel = gather of the kept transitions (stable compaction order `pos`) + NVLink stores to every rank + header + flag.
-__global__ void __launch_bounds__(512) rollout_pack_push_kernel(const PushArgs a) {
+__device__ __forceinline__ void st_multimem(float* p, const float4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// Streams this rank's packed transitions (contiguous, 128-bit) from its own slot to the same slot of every peer over
+// NVLink -- one unicast store per peer, or ONE multicast store replicated by the NVSwitch -- then publishes header + flag.
+// Deliberately narrow (a few CTAs on a high-priority stream): it is NVLink bound and runs beside the next rollout's step kernel.
+__global__ void __launch_bounds__(512) peer_push_kernel(const PushArgs a) {
   __shared__ bool last;
   // a peer's half (epoch & 1) may be overwritten once that peer has consumed epoch - 2 (its ack lands in OUR flag block)
   if ((int)threadIdx.x < a.world) {
@@ -45,29 +53,26 @@ __global__ void __launch_bounds__(512) rollout_pack_push_kernel(const PushArgs a
     while (ack[threadIdx.x] < need) __nanosleep(64);
   }
   __syncthreads();
-  const int W = a.W, S = a.S, A = a.A;
   const long long m = min((long long)*a.m_dev, a.m_cap);
-  const long long total = m * W, n4 = (total + 3) >> 2;
-  for (long long t4 = (long long)blockIdx.x * blockDim.x + threadIdx.x; t4 < n4; t4 += (long long)gridDim.x * blockDim.x) {
-    float v[4];
+  const long long n4 = (m * a.W + 3) >> 2;                        // the slot is padded to 16 bytes: the tail quad is in bounds
+  const float4* src = reinterpret_cast<const float4*>(a.src);
+  constexpr int U = 4;                                            // independent 128-bit loads in flight per thread
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; t0 < n4; t0 += U * stride) {
+    float4 q[U];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const long long t = t4 * 4 + k;
-      float x = 0.f;
-      if (t < total) {
-        const long long j = t / W; const int c = (int)(t - j * W);
-        const size_t p = (size_t)a.pos[j];
-        if (c < S) x = a.obss[p * S + c];
-        else if (c < S + A) x = a.acts[p * A + (c - S)];
-        else if (c < 2 * S + A) x = a.nexts[p * S + (c - S - A)];
-        else if (c == 2 * S + A) x = a.rews[p];
-        else if (c == 2 * S + A + 1) x = (float)a.terms[p];
-        else x = a.pens[p];
+    for (int u = 0; u < U; ++u) { const long long t = t0 + u * stride; if (t < n4) q[u] = __ldcs(src + t); }
+    if (a.mc_dst) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) { const long long t = t0 + u * stride; if (t < n4) st_multimem(a.mc_dst + 4 * t, q[u]); }
+    } else {
+      for (int r = 0; r < a.world; ++r) {
+        if (r == a.rank) continue;
+        float4* d = reinterpret_cast<float4*>(a.dst[r]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) { const long long t = t0 + u * stride; if (t < n4) d[t] = q[u]; }
       }
-      v[k] = x;
     }
-    const float4 q = make_float4(v[0], v[1], v[2], v[3]);
-    for (int r = 0; r < a.world; ++r) reinterpret_cast<float4*>(a.dst[r])[t4] = q;      // r == rank: the local copy
   }
   // publish: every CTA's stores are released at system scope before it takes a ticket; the last CTA writes header + flag
   __threadfence_system();
@@ -79,7 +84,7 @@ __global__ void __launch_bounds__(512) rollout_pack_push_kernel(const PushArgs a
   __threadfence_system();
   if ((int)threadIdx.x < a.world) {
     const int r = threadIdx.x;
-    int* h = reinterpret_cast<int*>(a.dst[r] + a.cap_rows * W);
+    int* h = reinterpret_cast<int*>(a.dst[r] + a.cap_rows * a.W);
     const long long produced = (long long)a.stats[1];
     h[0] = (int)m;
     h[1] = (int)(produced & 0xffffffffLL); h[2] = (int)(produced >> 32);
@@ -142,22 +147,22 @@ const char* mb_peer_wait_launch(const mobody_peer_desc* p, cudaStream_t st) {
   peer::peer_wait_kernel<<<1, 32, 0, st>>>(flags_of(p, p->rank), p->world, p->epoch);
   return nullptr;
 }
-const char* mb_rollout_push_launch(const mobody_rollout_desc* d, const mobody_peer_desc* p, cudaStream_t st) {
+const char* mb_peer_push_launch(const mobody_peer_desc* p, const int* kept_dev, const double* stats_dev, cudaStream_t st) {
   if (const char* e = check_peer(p)) return e;
-  const int S = d->step.S, A = d->step.A, T = d->T, B = d->step.B;
-  if (p->W != 2 * S + A + 3) return "peer W does not match 2S+A+3";
-  if ((long long)T * B > p->cap_rows) return "rollout capacity exceeds the peer slot";
+  if (!kept_dev || !stats_dev) return "null kept / stats pointer";
   const peer::Layout L = peer::layout(p->world, p->cap_rows, p->W);
+  const long long slot_off = (long long)(p->epoch & 1u) * L.half_floats + (long long)p->rank * L.slot_floats;
   peer::PushArgs a{};
-  a.obss = d->obss; a.acts = d->acts; a.nexts = d->nexts; a.rews = d->rews; a.pens = d->pens; a.terms = d->terms; a.pos = d->pos;
-  a.m_dev = d->counts + T + 1; a.m_cap = (long long)T * B; a.stats = d->stats; a.S = S; a.A = A;
+  a.m_dev = kept_dev; a.m_cap = p->cap_rows; a.stats = stats_dev;
   a.world = p->world; a.rank = p->rank; a.epoch = p->epoch; a.cap_rows = p->cap_rows; a.W = p->W;
   for (int r = 0; r < p->world; ++r) {
-    a.dst[r] = reinterpret_cast<float*>(p->base[r]) + (long long)(p->epoch & 1u) * L.half_floats + (long long)p->rank * L.slot_floats;
+    a.dst[r] = reinterpret_cast<float*>(p->base[r]) + slot_off;
     a.flags[r] = flags_of(p, r);
   }
-  int ctas = p->ctas > 0 ? p->ctas : 24;
+  a.src = a.dst[p->rank];
+  a.mc_dst = p->multicast ? reinterpret_cast<float*>(p->multicast) + slot_off : nullptr;
+  int ctas = p->ctas > 0 ? p->ctas : 8;
   if (ctas > 148) ctas = 148;
-  peer::rollout_pack_push_kernel<<<ctas, 512, 0, st>>>(a);
+  peer::peer_push_kernel<<<ctas, 512, 0, st>>>(a);
   return nullptr;
 }

@@ -269,7 +269,7 @@ class MOBODY(object):
 
     def _rollout_desc(self, init_obss, T, use_trg, ws, packed, eps=None, idx=None, row0=0, step0=None):
         """A filled mobody_rollout_desc for start states ``init_obss`` [B,S] (device, contiguous) on workspace ``ws``.
-        ``packed`` None leaves the pack stage out (mobody_rollout_push does it, multi-GPU).  Returns (desc, keep-alive)."""
+        ``packed``: destination of the pack stage (multi-GPU: this rank's slot of its receive buffer).  Returns (desc, keep-alive)."""
         B, S = init_obss.shape
         d = _ffi.RolloutDesc()
         keep = self.dynamics.fill_step_desc(d.step, B, S, self.device, policy=self.policy.network, max_action=self.policy.max_action,
@@ -281,6 +281,8 @@ class MOBODY(object):
         d.eps_all, d.idx_all = _ffi.ptr(eps), _ffi.ptr(idx)
         for k in ("obss", "acts", "nexts", "rews", "pens", "terms", "row_ids", "counts", "pos", "scratch", "stats", "ticket"):
             setattr(d, k, _ffi.ptr(ws[k]))
+        if T == 1:
+            d.obss = d.step.obs            # one step: the start states ARE obss[0] (aliasing skips the copy, include/mobody_b200.h)
         d.packed = _ffi.ptr(packed)
         return d, (keep, init_obss, eps, idx, ws, packed)
 
@@ -412,6 +414,7 @@ class MOBODY(object):
             d.eps_all, d.idx_all = None, None
             for k in ("obss", "acts", "nexts", "rews", "pens", "terms", "row_ids", "counts", "pos", "scratch", "stats", "ticket"):
                 setattr(d, k, _ffi.ptr(ws[k]))
+            d.obss = d.step.obs                                   # T == 1: no copy of the start states
             d.packed = _ffi.ptr(packed)
             plan.append(dict(lo=lo, hi=hi, x=x, packed=packed, desc=d, ref=C.byref(d), keep=(keep, keep0, ws),
                              kept_dev=ws["counts"][2:3], stats_dev=ws["stats"][:2], ev=torch.cuda.Event()))

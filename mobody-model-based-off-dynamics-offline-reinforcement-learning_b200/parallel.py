@@ -8,9 +8,10 @@ per-rank slabs (an exact all-gather-v), concatenated rank-major.  No collective 
 of the rollout itself.  One process per GPU (torchrun); torch.distributed is plumbing only.
 
 Two assemblies of the per-rank results are offered:
- * ``gather="p2p"`` (default on CUDA): the PACK stage of each rank's rollout stores its kept transitions straight into
-   slot ``rank`` of every rank's receive buffer through peer-mapped pointers (csrc/peer.cu: one kernel = gather + NVLink
-   stores + header + flag).  No collective kernel, no padding on the wire, the consumer waits on the device.
+ * ``gather="p2p"`` (default on CUDA): each rank's rollout packs its kept transitions into slot ``rank`` of its own receive
+   buffer, and a narrow kernel on a high-priority side stream streams exactly those rows into the same slot of every peer's
+   buffer through peer-mapped pointers (csrc/peer.cu: 128-bit NVLink stores, or one NVSwitch-replicated multicast store,
+   then header + flag).  No collective kernel, no padding on the wire, the consumer waits on the device.
  * ``gather="padded"`` / ``"padded_async"``: one NCCL all-gather of zero-padded slabs (round 1; kept as the fallback when
    peer memory cannot be mapped, and for the CPU / gloo tests).
 """
@@ -98,7 +99,7 @@ class PeerExchange:
         self.slot_floats = int(lib.mobody_peer_slot_floats(self.cap_rows, self.W))
         n_floats = int(lib.mobody_peer_buffer_bytes(self.world, self.cap_rows, self.W)) // 4
         mode = mode or os.environ.get("MOBODY_PEER_MODE", "symm")
-        self.buf, self._keep, ptrs = None, None, None
+        self.buf, self._keep, ptrs, self.multicast = None, None, None, 0
         if mode == "symm":
             try:
                 import torch.distributed._symmetric_memory as symm_mem
@@ -107,6 +108,9 @@ class PeerExchange:
                 hdl = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
                 ptrs = [int(q) for q in hdl.buffer_ptrs]
                 self.buf, self._keep, self.mode = buf, hdl, "symmetric_memory"
+                mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+                if mc and os.environ.get("MOBODY_PUSH_MULTICAST", "1") != "0":
+                    self.multicast = mc                              # NVLS: one store, replicated to every rank by the switch
             except Exception as e:                                   # noqa: BLE001 -- fall through to legacy IPC
                 self._symm_error = repr(e)
                 mode = "ipc"
@@ -130,7 +134,12 @@ class PeerExchange:
         self.ptrs = ptrs
         self.epoch = 0
         self._push_done = [None, None]                               # event of the push kernel that last read workspace slot parity
-        self._side = torch.cuda.Stream(self.device)
+        # the push kernel is short and bandwidth bound: a high-priority side stream lets its few CTAs take the first SMs that
+        # free up instead of queueing behind the next rollout's 700+ step tiles
+        prio = int(os.environ.get("MOBODY_PUSH_PRIO", "-1"))
+        self._side = torch.cuda.Stream(self.device, priority=prio)
+        self.ctas = int(os.environ.get("MOBODY_PUSH_CTAS", "0"))
+        self.overlap = os.environ.get("MOBODY_PUSH_OVERLAP", "1") != "0"
         self._descs = {}
         torch.cuda.synchronize(self.device)
         dist.barrier(group)                                          # every buffer is zeroed before anyone pushes into it
@@ -141,6 +150,7 @@ class PeerExchange:
         d.world, d.rank, d.cap_rows, d.W, d.epoch, d.ctas = self.world, self.rank, self.cap_rows, self.W, int(epoch), int(ctas)
         for r, q in enumerate(self.ptrs):
             d.base[r] = q
+        d.multicast = self.multicast or None
         return d
 
     def views(self, epoch):
@@ -187,7 +197,7 @@ class GatheredRollout:
 
 
 def p2p_rollout(agent, local, T, use_trg, row0, cap, *, group=None, step0=None, exchange=None, ctas=0):
-    """This rank's shard rolled on the device with its PACK stage pushed to every rank (csrc/peer.cu).  Asynchronous: returns a
+    """This rank's shard rolled on the device, packed into its own slot and pushed to every rank (csrc/peer.cu).  Asynchronous: returns a
     GatheredRollout handle; nothing is read back.  The push kernel runs on a side stream so that it overlaps whatever the
     caller enqueues next (e.g. the next rollout); workspaces alternate with the exchange parity."""
     from . import _ffi
@@ -206,25 +216,30 @@ def p2p_rollout(agent, local, T, use_trg, row0, cap, *, group=None, step0=None, 
     ex.epoch += 1
     e = ex.epoch
     cur = torch.cuda.current_stream(dev)
-    pd = ex.desc(e, ctas)
+    pd = ex.desc(e, ctas or ex.ctas)
     if e > 2:    # everything enqueued on this stream so far has consumed epoch e - 2: peers may overwrite that half now
         _ffi.check(lib.mobody_peer_ack(C.byref(pd), e - 2, _ffi.stream_ptr(dev)))
     if ex._push_done[e & 1] is not None:
-        cur.wait_event(ex._push_done[e & 1])                         # the push of epoch e - 2 read the workspace we are about to reuse
+        cur.wait_event(ex._push_done[e & 1])                         # the push of epoch e - 2 read the slot / counters we are about to reuse
     B = local.shape[0]
     local = _ffi.f32(local, dev)
     ws = agent._rollout_workspace(T, B, S, A, 4 + (e & 1))
-    d, keep = agent._rollout_desc(local, T, use_trg, ws, None, row0=row0, step0=step0)
+    rows, _ = ex.views(e)
+    d, keep = agent._rollout_desc(local, T, use_trg, ws, rows[ex.rank], row0=row0, step0=step0)   # packs into OUR slot of the local buffer
     _ffi.check(lib.mobody_rollout(C.byref(d), _ffi.stream_ptr(dev)))
-    ev = torch.cuda.Event(); ev.record(cur)
-    with torch.cuda.stream(ex._side):
+    kept_dev, stats_dev = ws["counts"][T + 1:T + 2], ws["stats"][:2]
+    if ex.overlap:
+        ev = torch.cuda.Event(); ev.record(cur)
         ex._side.wait_event(ev)
-        _ffi.check(lib.mobody_rollout_push(C.byref(d), C.byref(pd), C.c_void_p(ex._side.cuda_stream)))
+        _ffi.check(lib.mobody_peer_push(C.byref(pd), kept_dev.data_ptr(), stats_dev.data_ptr(), C.c_void_p(ex._side.cuda_stream)))
         done = torch.cuda.Event(); done.record(ex._side)
+    else:
+        _ffi.check(lib.mobody_peer_push(C.byref(pd), kept_dev.data_ptr(), stats_dev.data_ptr(), _ffi.stream_ptr(dev)))
+        done = torch.cuda.Event(); done.record(cur)
     ex._push_done[e & 1] = done
     ex._descs[e & 1] = (d, keep, pd)                                 # keep-alive until the slot is reused
-    info = {"kept_dev": ws["counts"][T + 1:T + 2], "counts_dev": ws["counts"], "stats_dev": ws["stats"][:2], "capacity": cap,
-            "world": ex.world, "exchange": ex.mode}
+    info = {"kept_dev": kept_dev, "counts_dev": ws["counts"], "stats_dev": stats_dev, "capacity": cap,
+            "world": ex.world, "exchange": ex.mode + ("+multicast" if ex.multicast else "")}
     return GatheredRollout(ex, e, [S, A, S, 1, 1, 1], info)
 
 
@@ -251,7 +266,7 @@ def sharded_rollout_host(agent, host_shard, rollout_length, use_trg=True, *, gro
 
 def _exchange_mode(agent):
     for ex in getattr(agent, "_peer_exchanges", {}).values():
-        return ex.mode
+        return ex.mode + ("+multicast" if ex.multicast else "")
     return None
 
 
