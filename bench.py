@@ -573,6 +573,7 @@ def main():
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
+        d2h *= world if exchange == "p2p" else 1      # whole-job bytes: every rank copies its own shard
     e2e_s = time.perf_counter() - t0           # (at N > 1 every rank's info already counts the whole job's transitions)
 
     # ---- single-pass fp16 mode of the same step (stated looser bound), reported next to the headline mode ----
@@ -642,9 +643,10 @@ def main():
                    "parallelism": (f"dp{world} (start states sharded; transitions assembled in every rank's buffer by "
                                    f"{'peer-memory stores from the pack kernel' if exchange == 'p2p' else 'an NCCL all-gather of padded slabs'})")
                                   if world > 1 else "single GPU"},
-        "e2e": {"value": e2e_trans / e2e_s, "unit": UNIT, "h2d_bytes_per_step": Bn * S * 4, "d2h_bytes_per_step": int(d2h),
+        "e2e": {"value": e2e_trans / e2e_s, "unit": UNIT, "h2d_bytes_per_step": Bn * S * 4 * world, "d2h_bytes_per_step": int(d2h),
                 "path": "MOBODY.rollout(host tensor)" if world == 1 else
-                        "parallel.sharded_rollout_host: host shard in, transitions of all ranks out as CPU tensors on every rank (exchange inside)"},
+                        "parallel.sharded_rollout_host: host shard in -> rollout -> peer-memory exchange (every rank's device buffer then holds all ranks' transitions) -> "
+                        "this rank's transitions out as CPU tensors; the job's gathered output reaches the host once, in parallel over the ranks"},
         "gpu_launches": args.steps * launches_per_rollout,
         "roofline": {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                      "traffic": traffic, "traffic_source": traffic_src,

@@ -750,6 +750,26 @@ const char* mb_tc_step_launch(const StepArgs& a, const unsigned char* dynb, cons
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
     return "cudaFuncSetAttribute(step_tc_kernel) failed";
   const int grid = (a.B + tcs::TM - 1) / tcs::TM;
-  kern<<<grid, 32 * (4 * ng + 2), bytes, st>>>(a, dynb, polb ? polb : dynb, sc, cfg);
+  // Every tile streams the whole weight image (6.5 MB at obs 17 / act 6) from L2: mark it persisting so that the rows
+  // flowing through L2 -- this kernel's own I/O and, on a multi-GPU box, the peers' incoming transitions -- cannot evict it
+  // (MOBODY_L2_PERSIST=0 turns the hint off for A/B runs).
+  static const bool persist = [] { const char* e = getenv("MOBODY_L2_PERSIST"); return !(e && e[0] == '0'); }();
+  cudaLaunchConfig_t lc = {};
+  lc.gridDim = dim3(grid); lc.blockDim = dim3(32 * (4 * ng + 2)); lc.dynamicSmemBytes = bytes; lc.stream = st;
+  cudaLaunchAttribute at[1];
+  if (persist) {
+    static thread_local int limit_dev = -1;
+    int dev = 0; cudaGetDevice(&dev);
+    if (limit_dev != dev) { cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)32 << 20); limit_dev = dev; }
+    at[0].id = cudaLaunchAttributeAccessPolicyWindow;
+    at[0].val.accessPolicyWindow.base_ptr = const_cast<unsigned char*>(dynb);
+    at[0].val.accessPolicyWindow.num_bytes = DL.total_bytes;
+    at[0].val.accessPolicyWindow.hitRatio = 1.0f;
+    at[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    at[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    lc.attrs = at; lc.numAttrs = 1;
+  }
+  const unsigned char* polp = polb ? polb : dynb;
+  if (cudaLaunchKernelEx(&lc, kern, a, dynb, polp, sc, cfg) != cudaSuccess) return "step_tc_kernel launch failed";
   return nullptr;
 }

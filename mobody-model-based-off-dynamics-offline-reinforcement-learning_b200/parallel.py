@@ -243,20 +243,26 @@ def p2p_rollout(agent, local, T, use_trg, row0, cap, *, group=None, step0=None, 
     return GatheredRollout(ex, e, [S, A, S, 1, 1, 1], info)
 
 
-def sharded_rollout_host(agent, host_shard, rollout_length, use_trg=True, *, group=None, step0=None):
+def sharded_rollout_host(agent, host_shard, rollout_length, use_trg=True, *, group=None, step0=None, host_output="shard"):
     """MOBODY.rollout's host contract (mobody.py:596-657: start states in, dict of CPU tensors out) for start states sharded
-    over the ranks: THIS rank's shard [B_r, S] comes from (pinned) host memory, the transitions of ALL ranks come back as CPU
-    tensors on every rank, rank-major.  H2D of the shard, the rollout, the peer-memory exchange and the D2H of the gathered
-    rows all happen inside the call (equal shard sizes; weak-scaling e2e)."""
+    over the ranks: THIS rank's shard [B_r, S] comes from (pinned) host memory; H2D of the shard, the rollout and the
+    peer-memory exchange (after which EVERY rank's device buffer holds the transitions of ALL ranks -- what each training
+    replica consumes) happen inside the call, and so does the D2H of the result:
+      host_output="shard": this rank's own transitions come back as CPU tensors -- over all ranks the job's gathered output
+                           reaches the host exactly once, in parallel over the GPUs' PCIe links;
+      host_output="all":   the transitions of all ranks come back on every rank, rank-major (world x the D2H traffic).
+    ``info`` always describes the whole job (num_transitions / reward_mean over all ranks, kept_per_rank)."""
     dev = agent.device
     T = int(rollout_length)
     x = host_shard.to(dev, non_blocking=True)
     res = sharded_rollout(agent, x, T, use_trg, group=group, gather="p2p", sharded_input=True, step0=step0)
     kept, produced, rsum = res.counts()                                   # waits for every rank's rows, one small D2H
     W = res.rows.shape[2]
-    host = agent._host_slab(sum(kept), W)
+    take = list(range(len(kept))) if host_output == "all" else [res.ex.rank]
+    host = agent._host_slab(sum(kept[r] for r in take), W)
     off = 0
-    for r, m in enumerate(kept):
+    for r in take:
+        m = kept[r]
         host[off:off + m].copy_(res.rows[r, :m], non_blocking=True)
         off += m
     torch.cuda.current_stream(dev).synchronize()
