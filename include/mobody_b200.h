@@ -292,6 +292,12 @@ int mobody_mlp_pack(const mobody_mlp_params* mlp, int din, int dout, int precisi
  * descriptors and TMEM read-back as the rollout kernel (nsplit 1 = bf16, 2 = bf16 hi+lo split). */
 int mobody_selftest_umma(const float* A, const float* B, int K, int N, int nsplit, float* D, void* stream);
 
+/* Test hook of the train step's tensor-core tiles (tcgen05.mma.kind::tf32, TF32 hi+lo split, 3 MMAs per K step):
+ * C[M][N] = A * B in fp32-class precision.  a_src / b_src: 0 = element (row, k) at src[row*ld + k], 1 = at src[k*ld + row]
+ * (row = m for A, n for B).  N <= 256. */
+int mobody_selftest_gemm(const float* A, const float* B, int M, int N, int K, int a_src, int b_src, int lda, int ldb,
+                         float* C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

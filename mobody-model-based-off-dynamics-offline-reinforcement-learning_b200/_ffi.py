@@ -154,6 +154,7 @@ def lib():
         L.mobody_classifier_step.argtypes = [C.POINTER(ClassifierDesc), C.c_void_p]
         L.mobody_dara_relabel.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.POINTER(MlpParams),
                                           C.POINTER(MlpParams), C.c_float, C.c_void_p, C.c_void_p]
+        L.mobody_selftest_gemm.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.mobody_selftest_umma.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         if L.mobody_abi_version() != ABI_VERSION:
             raise RuntimeError("mobody_b200: ABI version mismatch between _ffi.py and libmobody_b200.so")

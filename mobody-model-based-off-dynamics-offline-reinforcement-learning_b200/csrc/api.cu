@@ -49,6 +49,8 @@ const char* mb_peer_slot(const mobody_peer_desc* p, int r, float** rows, int** h
 const char* mb_peer_ack_launch(const mobody_peer_desc* p, unsigned int consumed, cudaStream_t st);
 const char* mb_peer_wait_launch(const mobody_peer_desc* p, cudaStream_t st);
 const char* mb_peer_push_launch(const mobody_peer_desc* p, const int* kept_dev, const double* stats_dev, cudaStream_t st);
+const char* mb_gemm_selftest_launch(const float* A, const float* B, int M, int N, int K, int a_src, int b_src, int lda, int ldb,
+                                    float* C, cudaStream_t st);
 void mb_tc_set_trace(long long* buf);
 long long mb_train_workspace_bytes(int N, int S, int A, int nsplit);
 const char* mb_train_step_launch(const mobody_train_desc& d, cudaStream_t st);
@@ -402,6 +404,13 @@ int mobody_selftest_umma(const float* A, const float* B, int K, int N, int nspli
   const char* err = mb_umma_selftest_launch(A, B, K, N, nsplit, D, (cudaStream_t)stream);
   if (err) return fail(MOBODY_ERR_ARG, err);
   return check_launch("mobody_selftest_umma");
+}
+
+int mobody_selftest_gemm(const float* A, const float* B, int M, int N, int K, int a_src, int b_src, int lda, int ldb, float* C, void* stream) {
+  if (!A || !B || !C) return fail(MOBODY_ERR_ARG, "mobody_selftest_gemm: null pointer");
+  const char* err = mb_gemm_selftest_launch(A, B, M, N, K, a_src, b_src, lda, ldb, C, (cudaStream_t)stream);
+  if (err) return fail(MOBODY_ERR_ARG, err);
+  return check_launch("mobody_selftest_gemm");
 }
 
 /* debug hook (not in the public header): device int64[80*8] receiving per-layer clock64 stamps of CTA 0 */

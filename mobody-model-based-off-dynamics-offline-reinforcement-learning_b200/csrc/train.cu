@@ -15,6 +15,7 @@
 // ranges whose partials are summed inside the fused Adam(+Polyak) kernel.
 #include "simt_layers.cuh"
 #include "philox.cuh"
+#include "umma_gemm.cuh"
 #include "../../include/mobody_b200.h"
 #include <math.h>
 
@@ -242,14 +243,7 @@ __device__ float block_minmax(float v, float* sh, bool is_max) {
   __syncthreads();
   return sh[32];
 }
-__device__ void actor_finish(const ActorArgs& a, float* sh) {
-  __shared__ int last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) last = atomicAdd(a.counter, 1) == (int)(gridDim.x * gridDim.y) - 1;
-  __syncthreads();
-  if (!last) return;
-  __threadfence();
+__device__ void actor_reduce(const ActorArgs& a, float* sh) {
   float s_abs = 0.f, s_q = 0.f, s_h = 0.f;
   for (int i = threadIdx.x; i < a.N; i += blockDim.x) { const float q = fminf(__ldcg(a.qv[0] + i), __ldcg(a.qv[1] + i)); s_abs += fabsf(q); s_q += q; }
   for (int i = threadIdx.x; i < a.n_true; i += blockDim.x) s_h += fabsf(fminf(__ldcg(a.qh[0] + i), __ldcg(a.qh[1] + i)));
@@ -263,6 +257,16 @@ __device__ void actor_finish(const ActorArgs& a, float* sh) {
     a.out[0] = l / (float)a.N; a.out[1] = q1s / (float)a.N;                 // mse(q1,y) + mse(q2,y) (:207)
     a.out[4] = mean_q; a.out[5] = mean_abs; a.out[9] = a.weight / mean_abs; a.out[10] = mean_h;
   }
+}
+__device__ void actor_finish(const ActorArgs& a, float* sh) {
+  __shared__ int last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(a.counter, 1) == (int)(gridDim.x * gridDim.y) - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  actor_reduce(a, sh);
 }
 
 // ---- actor: roles 0, 1 = Q_k(s, pi(s)) and d Q_k / d action with Q frozen (:316-317, 555-556);
@@ -782,6 +786,99 @@ __global__ void __launch_bounds__(NT, 1) dara_relabel_kernel(RelabelArgs a) {
   }
 }
 
+// ================= large-batch path: the update as a sequence of tcgen05 GEMM tiles (umma_gemm.cuh) =================
+// Element-wise glue between the GEMMs (everything else of the math lives in GEMM epilogues).
+
+// TD target, MSE gradient and the logging partials (mobody.py:189-207): one thread per row, 256-row blocks
+struct TdArgs { const float* X; int N, S, A, rw; float gamma; const float* qk[2]; const float* qtk[2]; float* d3[2]; float* part; };
+__global__ void __launch_bounds__(256) td_kernel(const TdArgs a) {
+  mb_pdl_begin();
+  __shared__ float sh[40];
+  const int r = blockIdx.x * 256 + threadIdx.x;
+  float e0 = 0.f, e1 = 0.f, s0 = 0.f, s1 = 0.f;
+  if (r < a.N) {
+    const float* x = a.X + (size_t)r * a.rw;
+    const float y = x[2 * a.S + a.A] + x[2 * a.S + a.A + 1] * a.gamma * fminf(a.qtk[0][r], a.qtk[1][r]);
+    const float q0 = a.qk[0][r], q1 = a.qk[1][r], d0 = q0 - y, d1 = q1 - y;
+    a.d3[0][r] = 2.0f * d0 / (float)a.N; a.d3[1][r] = 2.0f * d1 / (float)a.N;
+    e0 = d0 * d0; e1 = d1 * d1; s0 = q0; s1 = q1;
+  }
+  e0 = block_sum(e0, sh); e1 = block_sum(e1, sh); s0 = block_sum(s0, sh); s1 = block_sum(s1, sh);
+  if (threadIdx.x == 0) { float* p = a.part + (size_t)blockIdx.x * 4; p[0] = e0; p[1] = e1; p[2] = s0; p[3] = s1; }
+}
+
+// ReLU backward of a one-output head: dH2[k][r][n] = H2[k][r][n] > 0 ? g_k[r] * w3_k[n] : 0   (g == nullptr: g = 1, dQ/dH2)
+struct HeadBwdArgs { const float* H2[2]; const float* g[2]; const float* w3[2]; float* D[2]; int N; };
+__global__ void __launch_bounds__(256) head_bwd_kernel(const HeadBwdArgs a) {
+  mb_pdl_begin();
+  const int k = blockIdx.y;
+  const float4* h = reinterpret_cast<const float4*>(a.H2[k]);
+  const float4* w = reinterpret_cast<const float4*>(a.w3[k]);
+  float4* d = reinterpret_cast<float4*>(a.D[k]);
+  const long long total = (long long)a.N * (H / 4);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i >> 6), c = (int)(i & 63);
+    const float g = a.g[k] ? a.g[k][r] : 1.0f;
+    const float4 hv = h[i], wv = __ldg(w + c);
+    d[i] = make_float4(hv.x > 0.f ? g * wv.x : 0.f, hv.y > 0.f ? g * wv.y : 0.f, hv.z > 0.f ? g * wv.z : 0.f, hv.w > 0.f ? g * wv.w : 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(1024) actor_scalar_kernel(const ActorArgs a) {
+  mb_pdl_begin();
+  __shared__ float sh[40];
+  actor_reduce(a, sh);
+}
+
+// d loss / d (pre-tanh policy output) per row (mobody.py:321-330) + the logging scalars; 128 rows per block, last block reduces
+__global__ void __launch_bounds__(128) policy_grad_kernel(const PolicyBwdArgs a) {
+  mb_pdl_begin();
+  __shared__ float red[40];
+  __shared__ int last;
+  const int tid = threadIdx.x, r = blockIdx.x * 128 + tid;
+  const float pw = a.out[9], mean_h = a.out[10];
+  float w = 0.f, w_s = 0.f, w_mn = 3.4e38f, w_mx = -3.4e38f, w_e = 0.f;
+  if (r < a.N) {
+    if (r < a.n_true) {
+      w = fminf(expf(3.0f * (fminf(a.qh[0][r], a.qh[1][r]) / mean_h)), 100.0f);                 // :252-258
+      const float* x = a.X + (size_t)r * a.rw + a.S;
+      float e = 0.f;
+      for (int j = 0; j < a.A; ++j) { const float d = a.api[(size_t)r * a.A + j] - x[j]; e += d * d; }
+      w_s = w; w_mn = w; w_mx = w; w_e = w * e;
+    }
+    const bool first = a.qv[0][r] <= a.qv[1][r];                                                // torch.min(q1, q2): gradient follows the smaller one
+    for (int j = 0; j < a.A; ++j) {
+      const size_t e = (size_t)r * a.A + j;
+      const float ap = a.api[e];
+      float g = -pw / (float)a.N * (first ? a.gak[0][e] : a.gak[1][e]);
+      if (r < a.n_true) g += a.bc_coef * w * 2.0f * (ap - a.X[(size_t)r * a.rw + a.S + j]) / (float)((size_t)a.n_true * a.A);
+      const float t = ap / a.max_action;
+      a.d3p[e] = g * a.max_action * (1.0f - t * t);
+    }
+  }
+  w_s = block_sum(w_s, red); w_e = block_sum(w_e, red);
+  w_mn = block_minmax(w_mn, red, false); w_mx = block_minmax(w_mx, red, true);
+  if (tid == 0) { float* p = a.part + (size_t)blockIdx.x * 4; p[0] = w_s; p[1] = w_mn; p[2] = w_mx; p[3] = w_e; }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) last = atomicAdd(a.counter, 1) == (int)gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float s_w = 0.f, s_e = 0.f, mn = 3.4e38f, mx = -3.4e38f;
+  for (int t = tid; t < (int)gridDim.x; t += 128) {
+    const float* p = a.part + (size_t)t * 4;
+    s_w += __ldcg(p); mn = fminf(mn, __ldcg(p + 1)); mx = fmaxf(mx, __ldcg(p + 2)); s_e += __ldcg(p + 3);
+  }
+  s_w = block_sum(s_w, red); s_e = block_sum(s_e, red);
+  mn = block_minmax(mn, red, false); mx = block_minmax(mx, red, true);
+  if (tid == 0) {
+    const float bc = s_e / (float)((size_t)a.n_true * a.A);
+    a.out[2] = pw * (-a.out[4]) + a.bc_coef * bc;
+    a.out[3] = bc; a.out[6] = s_w / (float)a.n_true; a.out[7] = mn; a.out[8] = mx;
+  }
+}
+
 }  // namespace trn
 
 // ---------------- host launchers ----------------
@@ -853,7 +950,7 @@ const char* mb_train_adam_launch(const trn::AdamArgs& a, cudaStream_t st) {
 
 // ---------------- whole train step (C ABI: mobody_train_step) ----------------
 struct TrainWs {   // float offsets into the workspace
-  size_t Hq[2][2], Dq[2][2], d3[2], part, Hp[2], Dp[2], api, a2, qk[2], qtk[2], qv[2], qh[2], gak[2], d3p, scal, part2, cnt, gq[2][6], gp[6], total;
+  size_t Hq[2][2], Dq[2][2], d3[2], part, Hp[2], Dp[2], api, a2, qk[2], qtk[2], qv[2], qh[2], gak[2], d3p, scal, part2, cnt, gq[2][6], gp[6], T[2], total;
   int ntiles;
 };
 static TrainWs train_ws(int N, int S, int A, int nsplit) {
@@ -872,6 +969,7 @@ static TrainWs train_ws(int N, int S, int A, int nsplit) {
   const size_t pn[6] = {(size_t)256 * S, 256, 256 * 256, 256, (size_t)A * 256, (size_t)A};
   for (int k = 0; k < 2; ++k) for (int t = 0; t < 6; ++t) w.gq[k][t] = take(qn[t] * nsplit);
   for (int t = 0; t < 6; ++t) w.gp[t] = take(pn[t] * nsplit);
+  for (int l = 0; l < 2; ++l) w.T[l] = take(act);      // transient hidden activations of the tensor-core path (pi(s'), Q', q_hat)
   w.total = o;
   return w;
 }
@@ -879,11 +977,177 @@ long long mb_train_workspace_bytes(int N, int S, int A, int nsplit) { return (lo
 
 static MlpPtrs as_ptrs(const mobody_mlp_state& s) { MlpPtrs p; for (int i = 0; i < 3; ++i) { p.w[i] = s.w[i]; p.b[i] = s.b[i]; } return p; }
 
+// ---------------- large-batch update on tcgen05 (rows >= 2368: the GEMMs are throughput bound) ----------------
+const char* mb_gemm_launch(const ug::Args& a, cudaStream_t st);     // train_tc.cu
+
+static ug::Job gemm_job(const float* A, int lda, int a_src, const float* B, int ldb, int b_src, int M, int N, int K) {
+  ug::Job j{}; j.A = A; j.lda = lda; j.a_src = a_src; j.B = B; j.ldb = ldb; j.b_src = b_src; j.M = M; j.N = N; j.K = K;
+  j.epi = ug::EPI_STORE; j.scale = 1.f;
+  return j;
+}
+// forward layer: C = act(A W^T + b); nn.Linear weight [out][in] is the K-contiguous B operand
+static ug::Job fwd_job(const float* A, int lda, int M, int K, const float* W, const float* b, int Nout, float* C, bool relu = true) {
+  ug::Job j = gemm_job(A, lda, ug::SRC_KCONTIG, W, K, ug::SRC_KCONTIG, M, Nout, K);
+  j.bias = b; j.relu = relu ? 1 : 0; j.C = C; j.ldc = Nout;
+  return j;
+}
+// backward-data through a Linear + ReLU: C = (D W) * 1[mask > 0]; the weight is read "k = out, n = in"
+static ug::Job bwd_job(const float* D, int ldd, int M, int Kout, const float* W, int ldw, int Nin, const float* mask, float* C) {
+  ug::Job j = gemm_job(D, ldd, ug::SRC_KCONTIG, W, ldw, ug::SRC_RCONTIG, M, Nin, Kout);
+  j.epi = mask ? ug::EPI_MASK : ug::EPI_STORE; j.mask = mask; j.ldmask = Nin; j.C = C; j.ldc = Nin;
+  return j;
+}
+// weight gradient: dW[o][i] = sum_r D[r][o] X[r][i] (+ db[o] = sum_r D[r][o]); both operands are row-contiguous in k = r
+static ug::Job wgrad_job(const float* D, int ldd, int O, const float* X, int ldx, int I, int rows, float* dW, float* db) {
+  ug::Job j = gemm_job(D, ldd, ug::SRC_RCONTIG, X, ldx, ug::SRC_RCONTIG, O, I, rows);
+  j.epi = ug::EPI_PART; j.C = dW; j.db = db;
+  return j;
+}
+template <typename... J> static const char* run_gemms(cudaStream_t st, int nsplit, J... jobs) {
+  ug::Args a{}; a.nsplit = nsplit;
+  const ug::Job list[] = {jobs...};
+  a.njobs = (int)sizeof...(jobs);
+  for (int i = 0; i < a.njobs; ++i) a.job[i] = list[i];
+  return mb_gemm_launch(a, st);
+}
+
+static const char* mb_train_step_tc_launch(const mobody_train_desc& d, const TrainWs& w, cudaStream_t st) {
+  const int N = d.N, nt = d.n_true, S = d.S, A = d.A, rw = d.row_width, ns = d.nsplit, SA = S + A;
+  float* ws = (float*)d.workspace;
+  const float* X = d.rows;
+  const MlpPtrs pi = as_ptrs(d.policy), q[2] = {as_ptrs(d.q1), as_ptrs(d.q2)}, qt[2] = {as_ptrs(d.q1_target), as_ptrs(d.q2_target)};
+  float* Hq[2][2]; float* Dq[2][2]; float* T[2] = {ws + w.T[0], ws + w.T[1]};
+  for (int k = 0; k < 2; ++k) for (int l = 0; l < 2; ++l) { Hq[k][l] = ws + w.Hq[k][l]; Dq[k][l] = ws + w.Dq[k][l]; }
+  float* Hp[2] = {ws + w.Hp[0], ws + w.Hp[1]}; float* Dp[2] = {ws + w.Dp[0], ws + w.Dp[1]};
+  float* api = ws + w.api; float* a2 = ws + w.a2; float* d3p = ws + w.d3p;
+  float* qk[2] = {ws + w.qk[0], ws + w.qk[1]}; float* qtk[2] = {ws + w.qtk[0], ws + w.qtk[1]};
+  float* qv[2] = {ws + w.qv[0], ws + w.qv[1]}; float* qh[2] = {ws + w.qh[0], ws + w.qh[1]};
+  float* gak[2] = {ws + w.gak[0], ws + w.gak[1]}; float* d3[2] = {ws + w.d3[0], ws + w.d3[1]};
+  const char* e;
+  // ---- critic forward.  layer 1 of pi(s'), Q1(s,a), Q2(s,a), pi(s) side by side; then layer 2 (+ Q heads); then the policy tails ----
+  if ((e = run_gemms(st, 1, fwd_job(X + SA, rw, N, S, pi.w[0], pi.b[0], 256, T[0]), fwd_job(X, rw, N, SA, q[0].w[0], q[0].b[0], 256, Hq[0][0]),
+                     fwd_job(X, rw, N, SA, q[1].w[0], q[1].b[0], 256, Hq[1][0]), fwd_job(X, rw, N, S, pi.w[0], pi.b[0], 256, Hp[0])))) return e;
+  {
+    ug::Job j1 = fwd_job(Hq[0][0], 256, N, 256, q[0].w[1], q[0].b[1], 256, Hq[0][1]), j2 = fwd_job(Hq[1][0], 256, N, 256, q[1].w[1], q[1].b[1], 256, Hq[1][1]);
+    j1.epi = j2.epi = ug::EPI_HEAD; j1.w3 = q[0].w[2]; j1.b3 = q[0].b[2]; j1.out1 = qk[0]; j2.w3 = q[1].w[2]; j2.b3 = q[1].b[2]; j2.out1 = qk[1];
+    if ((e = run_gemms(st, 1, fwd_job(T[0], 256, N, 256, pi.w[1], pi.b[1], 256, T[1]), j1, j2, fwd_job(Hp[0], 256, N, 256, pi.w[1], pi.b[1], 256, Hp[1])))) return e;
+  }
+  {
+    ug::Job t1 = fwd_job(T[1], 256, N, 256, pi.w[2], pi.b[2], A, a2, false), t2 = fwd_job(Hp[1], 256, N, 256, pi.w[2], pi.b[2], A, api, false);
+    t1.epi = t2.epi = ug::EPI_TANH; t1.scale = t2.scale = d.max_action;
+    if ((e = run_gemms(st, 1, t1, t2))) return e;
+  }
+  // ---- target critics on (s', pi(s')): the input is [s' | a2], read from two sources ----
+  {
+    ug::Job j1 = fwd_job(X + SA, rw, N, SA, qt[0].w[0], qt[0].b[0], 256, T[0]), j2 = fwd_job(X + SA, rw, N, SA, qt[1].w[0], qt[1].b[0], 256, T[1]);
+    j1.A2 = j2.A2 = a2; j1.lda2 = j2.lda2 = A; j1.ksplit = j2.ksplit = S;
+    if ((e = run_gemms(st, 1, j1, j2))) return e;
+    // layer 2 + head in place is not possible (C would overwrite A of another tile's... no: tiles own their rows) -> no C store at all
+    ug::Job h1 = fwd_job(T[0], 256, N, 256, qt[0].w[1], qt[0].b[1], 256, nullptr), h2 = fwd_job(T[1], 256, N, 256, qt[1].w[1], qt[1].b[1], 256, nullptr);
+    h1.epi = h2.epi = ug::EPI_HEAD; h1.w3 = qt[0].w[2]; h1.b3 = qt[0].b[2]; h1.out1 = qtk[0]; h2.w3 = qt[1].w[2]; h2.b3 = qt[1].b[2]; h2.out1 = qtk[1];
+    if ((e = run_gemms(st, 1, h1, h2))) return e;
+  }
+  // ---- TD target + MSE gradient, head backward, backward-data ----
+  {
+    trn::TdArgs t{X, N, S, A, rw, d.gamma, {qk[0], qk[1]}, {qtk[0], qtk[1]}, {d3[0], d3[1]}, ws + w.part};
+    mb_launch(trn::td_kernel, dim3((N + 255) / 256), dim3(256), 0, st, t);
+    trn::HeadBwdArgs hb{{Hq[0][1], Hq[1][1]}, {d3[0], d3[1]}, {q[0].w[2], q[1].w[2]}, {Dq[0][1], Dq[1][1]}, N};
+    mb_launch(trn::head_bwd_kernel, dim3(296, 2), dim3(256), 0, st, hb);
+    if ((e = run_gemms(st, 1, bwd_job(Dq[0][1], 256, N, 256, q[0].w[1], 256, 256, Hq[0][0], Dq[0][0]),
+                       bwd_job(Dq[1][1], 256, N, 256, q[1].w[1], 256, 256, Hq[1][0], Dq[1][0])))) return e;
+  }
+  // ---- critic weight gradients (row-split partials) + Adam + Polyak ----
+  const mobody_mlp_state* qs[2] = {&d.q1, &d.q2};
+  const mobody_mlp_state* qts[2] = {&d.q1_target, &d.q2_target};
+  const mobody_mlp_state* qm[2] = {&d.q1_m, &d.q2_m};
+  const mobody_mlp_state* qvv[2] = {&d.q1_v, &d.q2_v};
+  if ((e = run_gemms(st, ns, wgrad_job(Dq[0][1], 256, 256, Hq[0][0], 256, 256, N, ws + w.gq[0][2], ws + w.gq[0][3]),
+                     wgrad_job(Dq[1][1], 256, 256, Hq[1][0], 256, 256, N, ws + w.gq[1][2], ws + w.gq[1][3]),
+                     wgrad_job(Dq[0][0], 256, 256, X, rw, SA, N, ws + w.gq[0][0], ws + w.gq[0][1]),
+                     wgrad_job(Dq[1][0], 256, 256, X, rw, SA, N, ws + w.gq[1][0], ws + w.gq[1][1])))) return e;
+  {
+    trn::WgradArgs g{}; g.N = N; g.nsplit = ns; g.njobs = 2;
+    for (int k = 0; k < 2; ++k) g.job[k] = {d3[k], 1, Hq[k][1], 256, ws + w.gq[k][4], ws + w.gq[k][5], 1, 256};
+    if ((e = mb_train_wgrad_launch(g, st))) return e;
+  }
+  trn::AdamArgs ad{}; ad.nsplit = ns; ad.b1 = 0.9f; ad.b2 = 0.999f; ad.eps = 1e-8f; ad.tau = d.tau; ad.njobs = 12;
+  ad.zero2 = reinterpret_cast<int*>(ws + w.cnt);
+  {
+    const double bc1 = 1.0 - pow(0.9, (double)d.t_q), bc2 = 1.0 - pow(0.999, (double)d.t_q);
+    ad.lr_over_bc1 = (float)(d.critic_lr / bc1); ad.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+    const int qn[6] = {256 * SA, 256, 256 * 256, 256, 256, 1};
+    for (int k = 0; k < 2; ++k)
+      for (int t = 0; t < 6; ++t) {
+        const int li = t >> 1; const bool isw = (t & 1) == 0;
+        ad.job[6 * k + t] = {isw ? qs[k]->w[li] : qs[k]->b[li], ws + w.gq[k][t], isw ? qm[k]->w[li] : qm[k]->b[li],
+                             isw ? qvv[k]->w[li] : qvv[k]->b[li], isw ? qts[k]->w[li] : qts[k]->b[li], qn[t]};
+      }
+  }
+  if ((e = mb_train_adam_launch(ad, st))) return e;
+  // ---- actor: Q_k(s, pi(s)) with the UPDATED, frozen critics (activations kept for the backward), q_hat_k on the true rows ----
+  {
+    ug::Job j1 = fwd_job(X, rw, N, SA, q[0].w[0], q[0].b[0], 256, Hq[0][0]), j2 = fwd_job(X, rw, N, SA, q[1].w[0], q[1].b[0], 256, Hq[1][0]);
+    j1.A2 = j2.A2 = api; j1.lda2 = j2.lda2 = A; j1.ksplit = j2.ksplit = S;
+    if ((e = run_gemms(st, 1, j1, j2, fwd_job(X, rw, nt, SA, q[0].w[0], q[0].b[0], 256, T[0]), fwd_job(X, rw, nt, SA, q[1].w[0], q[1].b[0], 256, T[1])))) return e;
+    ug::Job h[4] = {fwd_job(Hq[0][0], 256, N, 256, q[0].w[1], q[0].b[1], 256, Hq[0][1]), fwd_job(Hq[1][0], 256, N, 256, q[1].w[1], q[1].b[1], 256, Hq[1][1]),
+                    fwd_job(T[0], 256, nt, 256, q[0].w[1], q[0].b[1], 256, nullptr), fwd_job(T[1], 256, nt, 256, q[1].w[1], q[1].b[1], 256, nullptr)};
+    for (int i = 0; i < 4; ++i) { h[i].epi = ug::EPI_HEAD; h[i].w3 = q[i & 1].w[2]; h[i].b3 = q[i & 1].b[2]; h[i].out1 = i < 2 ? qv[i] : qh[i - 2]; }
+    if ((e = run_gemms(st, 1, h[0], h[1], h[2], h[3]))) return e;
+  }
+  trn::ActorArgs ac{};
+  ac.X = X; ac.N = N; ac.n_true = nt; ac.S = S; ac.A = A; ac.rw = rw; ac.max_action = d.max_action;
+  for (int k = 0; k < 2; ++k) { ac.qv[k] = qv[k]; ac.qh[k] = qh[k]; ac.gak[k] = gak[k]; }
+  ac.part = ws + w.part; ac.ntiles_c = (N + 255) / 256; ac.weight = d.weight; ac.out = ws + w.scal;
+  ac.counter = reinterpret_cast<int*>(ws + w.cnt);
+  mb_launch(trn::actor_scalar_kernel, dim3(1), dim3(1024), 0, st, ac);
+  {   // dQ_k / d action: head backward with unit gradient, backward-data through layers 2 and 1 (action columns of W1 only)
+    trn::HeadBwdArgs hb{{Hq[0][1], Hq[1][1]}, {nullptr, nullptr}, {q[0].w[2], q[1].w[2]}, {Dq[0][1], Dq[1][1]}, N};
+    mb_launch(trn::head_bwd_kernel, dim3(296, 2), dim3(256), 0, st, hb);
+    if ((e = run_gemms(st, 1, bwd_job(Dq[0][1], 256, N, 256, q[0].w[1], 256, 256, Hq[0][0], Dq[0][0]),
+                       bwd_job(Dq[1][1], 256, N, 256, q[1].w[1], 256, 256, Hq[1][0], Dq[1][0])))) return e;
+    if ((e = run_gemms(st, 1, bwd_job(Dq[0][0], 256, N, 256, q[0].w[0] + S, SA, A, nullptr, gak[0]),
+                       bwd_job(Dq[1][0], 256, N, 256, q[1].w[0] + S, SA, A, nullptr, gak[1])))) return e;
+  }
+  trn::PolicyBwdArgs pb{}; pb.N = N; pb.n_true = nt; pb.S = S; pb.A = A; pb.rw = rw; pb.pi = pi;
+  for (int k = 0; k < 2; ++k) { pb.gak[k] = gak[k]; pb.qv[k] = qv[k]; pb.qh[k] = qh[k]; }
+  pb.api = api; pb.X = X; pb.bc_coef = d.bc_coef; pb.max_action = d.max_action;
+  pb.d3p = d3p; pb.part = ws + w.part2; pb.out = ws + w.scal; pb.counter = reinterpret_cast<int*>(ws + w.cnt) + 1;
+  mb_launch(trn::policy_grad_kernel, dim3((N + 127) / 128), dim3(128), 0, st, pb);
+  // ---- policy backward-data: dH2 = (d3 W3) * 1[H2 > 0], dH1 = (dH2 W2) * 1[H1 > 0]; weight gradients; Adam ----
+  if ((e = run_gemms(st, 1, bwd_job(d3p, A, N, A, pi.w[2], 256, 256, Hp[1], Dp[1])))) return e;
+  if ((e = run_gemms(st, 1, bwd_job(Dp[1], 256, N, 256, pi.w[1], 256, 256, Hp[0], Dp[0])))) return e;
+  if ((e = run_gemms(st, ns, wgrad_job(Dp[1], 256, 256, Hp[0], 256, 256, N, ws + w.gp[2], ws + w.gp[3]),
+                     wgrad_job(Dp[0], 256, 256, X, rw, S, N, ws + w.gp[0], ws + w.gp[1])))) return e;
+  {
+    trn::WgradArgs g{}; g.N = N; g.nsplit = ns; g.njobs = 1;
+    g.job[0] = {d3p, A, Hp[1], 256, ws + w.gp[4], ws + w.gp[5], A, 256};
+    if ((e = mb_train_wgrad_launch(g, st))) return e;
+  }
+  trn::AdamArgs ap{}; ap.nsplit = ns; ap.b1 = 0.9f; ap.b2 = 0.999f; ap.eps = 1e-8f; ap.tau = 0.f; ap.njobs = 6;
+  {
+    const double bc1 = 1.0 - pow(0.9, (double)d.t_pi), bc2 = 1.0 - pow(0.999, (double)d.t_pi);
+    ap.lr_over_bc1 = (float)(d.actor_lr / bc1); ap.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
+    const int pn[6] = {256 * S, 256, 256 * 256, 256, A * 256, A};
+    for (int t = 0; t < 6; ++t) {
+      const int li = t >> 1; const bool isw = (t & 1) == 0;
+      ap.job[t] = {isw ? d.policy.w[li] : d.policy.b[li], ws + w.gp[t], isw ? d.policy_m.w[li] : d.policy_m.b[li],
+                   isw ? d.policy_v.w[li] : d.policy_v.b[li], nullptr, pn[t]};
+    }
+  }
+  if ((e = mb_train_adam_launch(ap, st))) return e;
+  if (d.scalars_out) cudaMemcpyAsync(d.scalars_out, ws + w.scal, 16 * sizeof(float), cudaMemcpyDeviceToDevice, st);
+  return nullptr;
+}
+
 const char* mb_train_step_launch(const mobody_train_desc& d, cudaStream_t st) {
   const int N = d.N, S = d.S, A = d.A, ns = d.nsplit;
   if (N < 1 || d.n_true < 1 || d.n_true > N || S < 1 || S > 128 || A < 1 || A > 32 || ns < 1 || ns > 64) return "train step: bad N/n_true/S/A/nsplit";
   const TrainWs w = train_ws(N, S, A, ns);
   if (!d.workspace || d.workspace_bytes < (long long)w.total * 4) return "train step: workspace too small";
+  // large batches: every contraction as tcgen05 GEMM tiles (MOBODY_TRAIN_TC=0 keeps the mma.sync path for A/B runs)
+  static const bool use_tc = [] { const char* e = getenv("MOBODY_TRAIN_TC"); return !(e && e[0] == '0'); }();
+  static const int tc_rows = [] { const char* e = getenv("MOBODY_TRAIN_TC_ROWS"); return e ? atoi(e) : 148 * 16; }();
+  if (use_tc && N >= tc_rows) return mb_train_step_tc_launch(d, w, st);
   float* ws = (float*)d.workspace;
   const mobody_mlp_state* qs[2] = {&d.q1, &d.q2};
   const mobody_mlp_state* qts[2] = {&d.q1_target, &d.q2_target};

@@ -107,14 +107,14 @@ def _storage_idle(t):
         return False
 
 
-def _wgrad_splits(n_rows, tiles_per_launch, device, sm_count=None):
+def _wgrad_splits(n_rows, tiles_per_launch, device, sm_count=None, ctas_per_sm=2):
     """Row splits of the weight-gradient launches.  A launch runs ``tiles * nsplit`` CTAs of 128 x 64 outputs, two per
     SM, each walking its rows in chunks of 32: pick the split count (<= 64) that minimises rounds x chunks per CTA
     summed over the launches of an update (tiles: critic 2 x (8 + 2), actor 8 + 2), i.e. avoid a nearly empty last
     round.  Any value gives the same result up to fp32 summation order; the order is fixed for a given value."""
     if sm_count is None:
         sm_count = _sm_count(device)
-    slots, chunks = 2 * sm_count, (n_rows + 31) // 32
+    slots, chunks = ctas_per_sm * sm_count, (n_rows + 31) // 32
     best, best_cost = 1, None
     for n in range(1, min(64, chunks) + 1):
         per = (chunks + n - 1) // n
@@ -185,6 +185,8 @@ class MOBODY(object):
         self.PIPE_FIRST = sm * 128      # first chunk of a pipelined rollout(): one wave of 128-row tiles, so the first kernel starts after a short H2D
         self.PIPE_ROWS = 2 * sm * 128   # later chunks: two full waves
         self._wave = sm * 128
+        import os
+        self.TC_TRAIN_ROWS = int(os.environ.get("MOBODY_TRAIN_TC_ROWS", sm * 16)) if os.environ.get("MOBODY_TRAIN_TC", "1") != "0" else 1 << 62
 
     # ------------------------------------------------------------------ optimizers (mobody.py:127-135)
     _OPT_COUNTER = {"q": "_t_q", "pi": "_t_pi", "cls": "_t_cls"}
@@ -545,7 +547,10 @@ class MOBODY(object):
         if nsplit is None:
             # row splits of the weight-gradient GEMMs (partials summed in Adam, fixed order); 128 x 64 tiles per split:
             # critic 2 x (256 x 256 -> 8, 256 x (S+A) -> 2 per 64 columns), actor 8 + 2 per 64 columns of S
-            nsplit = _wgrad_splits(N, (2 * (8 + 2 * ((S + A + 63) // 64)), 8 + 2 * ((S + 63) // 64)), self.device)
+            if N >= self.TC_TRAIN_ROWS:   # tcgen05 path: 128 x 256 GEMM tiles, one CTA per SM; critic launch 4 jobs x 2 tiles, actor 2 x 2
+                nsplit = _wgrad_splits(N, (8, 4), self.device, ctas_per_sm=1)
+            else:
+                nsplit = _wgrad_splits(N, (2 * (8 + 2 * ((S + A + 63) // 64)), 8 + 2 * ((S + 63) // 64)), self.device)
         lib = _ffi.lib()
         need = int(lib.mobody_train_workspace_bytes(N, S, A, nsplit))
         if self._train_ws is None or self._train_ws.numel() < need:
