@@ -16,19 +16,23 @@
 #pragma once
 #include "common.cuh"
 #include "tc_prims.cuh"
+#include <stdio.h>
 
 namespace ug {
 
 constexpr int BM = 128;          // rows of C per CTA (UMMA M)
-constexpr int KC = 32;           // K per pipeline stage = 4 UMMA K steps of 8
+constexpr int KC = 16;           // K per pipeline stage = 2 UMMA K steps of 8 (two stages of a 128 x 256 tile = 96 KB: two CTAs per SM)
 constexpr int NT = 256;          // threads per CTA
 
 enum { SRC_KCONTIG = 0, SRC_RCONTIG = 1 };
+// Epilogue kinds.  EPI_STORE and EPI_HEAD share one compiled epilogue (a job without w3 has no head), the others are their own
+// instantiations: the epilogue body is unrolled per 32 x 32 block, so every variant compiled into it is paid in issue slots.
 enum { EPI_STORE = 0,   // C = act(acc + bias)                       -> C[m][n]
        EPI_MASK = 1,    // C = mask[m][n] > 0 ? acc : 0              -> C[m][n]          (ReLU backward)
        EPI_HEAD = 2,    // h = relu(acc + bias); out1[m] = h . w3 + b3; optional C = h     (Q network tail)
        EPI_TANH = 3,    // C = tanh(acc + bias) * scale              -> C[m][n]          (policy tail)
        EPI_PART = 4 };  // C[split][m][n] = acc, db[split][m] = row sums of the A operand (weight gradient partials)
+__host__ __device__ constexpr int epi_class(int epi) { return epi == EPI_HEAD ? EPI_STORE : epi; }
 
 struct Job {
   const float* A; int lda; const float* A2; int lda2; int ksplit;     // A2: columns k >= ksplit of a KCONTIG A come from A2[m][k - ksplit]
@@ -71,18 +75,25 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
 // bytes) or 32 rows x 1 kgroup (RCONTIG: 128-byte coalesced reads per k, 128-byte contiguous writes per quarter-warp).
 template <int R>
 struct Operand {
-  static constexpr int U = R / 32;
+  static constexpr int KG = KC / 4;                 // 16-byte k groups per chunk (4)
+  static constexpr int U = R * KG / NT;             // units of (row, kgroup) per thread
   float v[U][4];
 
+  // KCONTIG: warp-iteration b covers rows 8b .. 8b+7 x all 4 kgroups (lane & 7 = row, lane >> 3 = kgroup)
+  // RCONTIG: warp-iteration b covers 32 rows x 1 kgroup: kgroup = warp & 3, rows 32 (2u + (warp >> 2)) + lane
+  __device__ __forceinline__ void where(int mode, int u, int& row, int& kg) const {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (mode == SRC_KCONTIG) { row = (warp * U + u) * 8 + (lane & 7); kg = lane >> 3; }
+    else { row = (2 * u + (warp >> 2)) * 32 + lane; kg = warp & 3; }
+  }
   __device__ __forceinline__ void load(const float* __restrict__ src, int ld, int mode, int row0, int rows, int k0, int kend,
                                        const float* __restrict__ src2, int ld2, int ksplit, float* rowsum) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (mode == SRC_KCONTIG) {
       const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && src2 == nullptr;
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int b = warp * U + u;                                     // 8-row x 4-kgroup block
-        const int row = (b >> 1) * 8 + (lane & 7), k = k0 + ((b & 1) * 4 + (lane >> 3)) * 4;
+        int row, kg; where(mode, u, row, kg);
+        const int k = k0 + kg * 4;
         const bool rok = row < rows;
         const float* p = src + (size_t)(row0 + row) * ld + k;
         if (vec && rok && k + 4 <= kend) {
@@ -100,7 +111,8 @@ struct Operand {
     } else {
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const int row = u * 32 + lane, k = k0 + warp * 4;               // warp = kgroup
+        int row, kg; where(mode, u, row, kg);
+        const int k = k0 + kg * 4;
         const bool rok = row < rows;
         float s = 0.f;
 #pragma unroll
@@ -113,22 +125,24 @@ struct Operand {
     }
   }
   __device__ __forceinline__ void store(unsigned char* hi_plane, int mode) const {
-    constexpr uint32_t plane = (uint32_t)R * (KC / 4) * 16;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr uint32_t plane = (uint32_t)R * KG * 16;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      int row, kg;
-      if (mode == SRC_KCONTIG) { const int b = warp * U + u; row = (b >> 1) * 8 + (lane & 7); kg = (b & 1) * 4 + (lane >> 3); }
-      else { row = u * 32 + lane; kg = warp; }
+      int row, kg; where(mode, u, row, kg);
       put_unit(hi_plane, plane, (uint32_t)kg * (R * 16) + (uint32_t)row * 16, v[u]);
     }
   }
 };
 
 // NP = padded N of the tile (B rows staged): 256 for the hidden layers, 64 for the narrow ones.
-template <int NP>
-__global__ void __launch_bounds__(NT, 1) gemm_kernel(const __grid_constant__ Args args) {
+// A_SRC / B_SRC are compile-time (every job of a launch shares them): the kernel is a straight line of unrolled code that
+// each CTA walks once, so its size is instruction-fetch time -- dead operand paths are not compiled in.
+template <int NP, int A_SRC, int B_SRC, int EPI>
+__global__ void __launch_bounds__(NT, 2) gemm_kernel(const __grid_constant__ Args args) {
   mb_pdl_begin();
+#ifdef UG_TRACE
+  long long t_[6]; t_[0] = clock64();
+#endif
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t bar_free[2], bar_done;
   __shared__ uint32_t tmem_slot;
@@ -156,28 +170,33 @@ __global__ void __launch_bounds__(NT, 1) gemm_kernel(const __grid_constant__ Arg
   tc::tc_fence_after();
   const uint32_t tmem = tmem_slot;
 
+#ifdef UG_TRACE
+  t_[1] = clock64();
+#endif
   Operand<BM> oa; Operand<NP> ob;
   float rowsum[Operand<BM>::U];
 #pragma unroll
   for (int u = 0; u < Operand<BM>::U; ++u) rowsum[u] = 0.f;
-  float* rs = (jb.epi == EPI_PART && jb.db) ? rowsum : nullptr;
+  float* rs = (A_SRC == SRC_RCONTIG && EPI == EPI_PART && jb.db) ? rowsum : nullptr;
   const int nrows_b = jb.N;                                             // valid rows of the B operand (n < N)
-  if (nchunks > 0) {
-    oa.load(jb.A, jb.lda, jb.a_src, m0, rows, kbeg, kend, jb.A2, jb.lda2, jb.ksplit, rs);
-    ob.load(jb.B, jb.ldb, jb.b_src, 0, nrows_b, kbeg, kend, nullptr, 0, 0, nullptr);
-  }
   const uint32_t idesc = make_idesc_tf32(BM, NP);
-  for (int c = 0; c < nchunks; ++c) {
+  // software pipeline with ONE load site and ONE store site: iteration c stores chunk c (fetched during iteration c - 1),
+  // fetches chunk c + 1 into registers and issues the MMAs of chunk c; c = -1 is the prologue fetch
+#pragma unroll 1
+  for (int c = -1; c < nchunks; ++c) {
     const int buf = c & 1;
     unsigned char* st = smem + (size_t)buf * STAGE;
-    if (c >= 2) tc::mbar_wait(&bar_free[buf], (uint32_t)(((c >> 1) - 1) & 1));      // the MMAs that read this stage are done
-    oa.store(st, jb.a_src);
-    ob.store(st + 2 * A_PLANE, jb.b_src);
+    if (c >= 0) {
+      if (c >= 2) tc::mbar_wait(&bar_free[buf], (uint32_t)(((c >> 1) - 1) & 1));    // the MMAs that read this stage are done
+      oa.store(st, A_SRC);
+      ob.store(st + 2 * A_PLANE, B_SRC);
+    }
     if (c + 1 < nchunks) {                                              // next chunk's global loads fly during this chunk's MMAs
       const int k0 = kbeg + (c + 1) * KC;
-      oa.load(jb.A, jb.lda, jb.a_src, m0, rows, k0, kend, jb.A2, jb.lda2, jb.ksplit, rs);
-      ob.load(jb.B, jb.ldb, jb.b_src, 0, nrows_b, k0, kend, nullptr, 0, 0, nullptr);
+      oa.load(jb.A, jb.lda, A_SRC, m0, rows, k0, kend, jb.A2, jb.lda2, jb.ksplit, rs);
+      ob.load(jb.B, jb.ldb, B_SRC, 0, nrows_b, k0, kend, nullptr, 0, 0, nullptr);
     }
+    if (c < 0) continue;
     tc::fence_proxy_async_smem();
     __syncthreads();
     if (tid == 0) {
@@ -196,78 +215,123 @@ __global__ void __launch_bounds__(NT, 1) gemm_kernel(const __grid_constant__ Arg
       if (c + 1 == nchunks) tc::umma_commit(&bar_done);
     }
   }
+#ifdef UG_TRACE
+  t_[2] = clock64();
+#endif
   if (nchunks > 0) tc::mbar_wait(&bar_done, 0);
   tc::tc_fence_after();
+#ifdef UG_TRACE
+  t_[3] = clock64();
+#endif
 
-  // ---------------- epilogue: warp w reads TMEM lane quadrant w & 3, column half w >> 2 ----------------
+  // ---------------- epilogue ----------------
+  // Warp w owns TMEM lane quadrant q = w & 3 (32 rows) and every second 32-column block (w >> 2).  tcgen05.ld hands each
+  // lane one ROW; global memory wants lanes along COLUMNS, so every 32 x 32 block is transposed through shared memory (the
+  // operand stages are free now; pitch 36 floats: 128-bit stores and loads, conflict-free both ways) and all global
+  // traffic -- ReLU mask in, C out -- is 128 contiguous bytes per row.
   const int q = warp & 3, half = warp >> 2;
-  const int r = q * 32 + lane, m = m0 + r;
-  const bool valid = r < rows;
-  constexpr int CH = 16;                                                // columns per tcgen05.ld
-  constexpr int NCH = NP / CH;
+  float* tb = reinterpret_cast<float*>(smem) + warp * (32 * 36);
   const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
-  float head = 0.f;
-  for (int ch = half; ch < NCH; ch += 2) {
-    uint32_t x[CH];
-    if (nchunks > 0) { tc::tmem_ld16(taddr + (uint32_t)(ch * CH), x); tc::tmem_ld_wait(); }
+  const int cl = (lane & 7) * 4, rl = lane >> 3;                        // coalesced phase: lane -> (row rl + 4 it, columns cl .. cl + 3)
+  const int ldc = EPI == EPI_PART ? jb.N : jb.ldc;
+  float* cbase = jb.C ? jb.C + (EPI == EPI_PART ? (size_t)blockIdx.z * jb.M * jb.N : 0) + (size_t)(m0 + q * 32 + rl) * ldc : nullptr;
+  // fast path: whole 4-column groups, 16-byte aligned rows (every 256-wide tensor of the update)
+  const bool fast = (jb.N & 3) == 0 && (!jb.C || ((ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(jb.C) & 15) == 0)) &&
+                    (EPI != EPI_MASK || ((jb.ldmask & 3) == 0 && (reinterpret_cast<uintptr_t>(jb.mask) & 15) == 0)) &&
+                    (!jb.bias || (reinterpret_cast<uintptr_t>(jb.bias) & 15) == 0) && (!jb.w3 || (reinterpret_cast<uintptr_t>(jb.w3) & 15) == 0);
+  float head[8];
+#pragma unroll
+  for (int it = 0; it < 8; ++it) head[it] = 0.f;
+  for (int cb = half; cb * 32 < NP; cb += 2) {
+    const int n0 = cb * 32, n = n0 + cl;
+    if (n0 >= jb.N) break;
+    const bool colok = n + 4 <= jb.N;
+    float4 mkv[8];                                                      // ReLU-mask block: all 8 loads in flight before anything waits
+    if (EPI == EPI_MASK && fast) {
+      const float* mrow = jb.mask + (size_t)(m0 + q * 32 + rl) * jb.ldmask + n;
+#pragma unroll
+      for (int it = 0; it < 8; ++it)
+        mkv[it] = (q * 32 + it * 4 + rl < rows && colok) ? __ldg(reinterpret_cast<const float4*>(mrow + (size_t)it * 4 * jb.ldmask)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    uint32_t x[32];
+    if (nchunks > 0) { tc::tmem_ld32(taddr + (uint32_t)n0, x); tc::tmem_ld_wait(); }
     else {
 #pragma unroll
-      for (int j = 0; j < CH; ++j) x[j] = 0u;
+      for (int jj = 0; jj < 32; ++jj) x[jj] = 0u;
     }
-    const int n0 = ch * CH;
-    if (jb.epi == EPI_PART) {
-      if (valid) {
-        float* dst = jb.C + ((size_t)blockIdx.z * jb.M + m) * jb.N + n0;
 #pragma unroll
-        for (int j = 0; j < CH; ++j) if (n0 + j < jb.N) dst[j] = __uint_as_float(x[j]);
+    for (int jj = 0; jj < 32; jj += 4)
+      *reinterpret_cast<uint4*>(tb + lane * 36 + jj) = make_uint4(x[jj], x[jj + 1], x[jj + 2], x[jj + 3]);
+    __syncwarp();
+    if (fast) {
+      float4 bq = make_float4(0.f, 0.f, 0.f, 0.f), wq = bq;
+      if (colok) {
+        if (jb.bias) bq = __ldg(reinterpret_cast<const float4*>(jb.bias + n));
+        if (EPI == EPI_STORE && jb.w3) wq = __ldg(reinterpret_cast<const float4*>(jb.w3 + n));
       }
-      continue;
-    }
-    float v[CH];
 #pragma unroll
-    for (int j = 0; j < CH; ++j) {
-      const int n = n0 + j;
-      float t = __uint_as_float(x[j]);
-      if (jb.bias && n < jb.N) t += __ldg(jb.bias + n);
-      if (jb.epi == EPI_MASK) t = (valid && n < jb.N && __ldg(jb.mask + (size_t)m * jb.ldmask + n) > 0.f) ? t : 0.f;
-      else if (jb.epi == EPI_TANH) t = tanhf(t) * jb.scale;
-      else if (jb.relu) t = fmaxf(t, 0.f);
-      v[j] = t;
-    }
-    if (jb.epi == EPI_HEAD) {
-#pragma unroll
-      for (int j = 0; j < CH; ++j) if (n0 + j < jb.N) head = fmaf(v[j], __ldg(jb.w3 + n0 + j), head);
-    }
-    if (jb.C && valid) {
-      float* dst = jb.C + (size_t)m * jb.ldc + n0;
-      if (n0 + CH <= jb.N && (jb.ldc & 3) == 0) {
-#pragma unroll
-        for (int j = 0; j < CH; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < CH; ++j) if (n0 + j < jb.N) dst[j] = v[j];
+      for (int it = 0; it < 8; ++it) {
+        const int rr = it * 4 + rl;
+        float4 v = *reinterpret_cast<const float4*>(tb + rr * 36 + cl);
+        if (EPI == EPI_MASK) {
+          v.x = mkv[it].x > 0.f ? v.x : 0.f; v.y = mkv[it].y > 0.f ? v.y : 0.f; v.z = mkv[it].z > 0.f ? v.z : 0.f; v.w = mkv[it].w > 0.f ? v.w : 0.f;
+        } else if (EPI != EPI_PART) {
+          v.x += bq.x; v.y += bq.y; v.z += bq.z; v.w += bq.w;
+          if (EPI == EPI_TANH) { v.x = tanhf(v.x) * jb.scale; v.y = tanhf(v.y) * jb.scale; v.z = tanhf(v.z) * jb.scale; v.w = tanhf(v.w) * jb.scale; }
+          else if (jb.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+          if (EPI == EPI_STORE) head[it] = fmaf(v.x, wq.x, fmaf(v.y, wq.y, fmaf(v.z, wq.z, fmaf(v.w, wq.w, head[it]))));
+        }
+        if (cbase && colok && q * 32 + rr < rows) *reinterpret_cast<float4*>(cbase + (size_t)it * 4 * ldc + n) = v;
+      }
+    } else {   // ragged / unaligned outputs (narrow heads, the 35-column first-layer gradients): compact scalar loop
+#pragma unroll 1
+      for (int e = lane; e < 32 * 32; e += 32) {
+        const int rr = e >> 5, c = e & 31, nn = n0 + c, r = q * 32 + rr;
+        if (nn >= jb.N || r >= rows) continue;
+        float t = tb[rr * 36 + c];
+        if (EPI == EPI_MASK) t = __ldg(jb.mask + (size_t)(m0 + r) * jb.ldmask + nn) > 0.f ? t : 0.f;
+        else if (EPI != EPI_PART) {
+          if (jb.bias) t += __ldg(jb.bias + nn);
+          if (EPI == EPI_TANH) t = tanhf(t) * jb.scale;
+          else if (jb.relu) t = fmaxf(t, 0.f);
+        }
+        if (jb.C) jb.C[(EPI == EPI_PART ? (size_t)blockIdx.z * jb.M * jb.N : 0) + (size_t)(m0 + r) * ldc + nn] = t;
       }
     }
+    __syncwarp();
   }
-  if (jb.epi == EPI_HEAD) {                                             // the two column halves of a row meet in shared memory
-    red[half * BM + r] = head;
+  if (EPI == EPI_STORE && jb.w3) {   // a row's dot product: 8 lanes (column groups) of this warp, then the two column halves through shared memory
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      float h = head[it];
+      h += __shfl_xor_sync(0xffffffffu, h, 1); h += __shfl_xor_sync(0xffffffffu, h, 2); h += __shfl_xor_sync(0xffffffffu, h, 4);
+      if ((lane & 7) == 0) red[half * BM + q * 32 + it * 4 + rl] = h;
+    }
     __syncthreads();
-    if (half == 0 && valid) jb.out1[m] = red[r] + red[BM + r] + __ldg(jb.b3);
+    if (tid < rows) jb.out1[m0 + tid] = red[tid] + red[BM + tid] + __ldg(jb.b3);
   }
-  if (jb.epi == EPI_PART && jb.db && jb.a_src == SRC_RCONTIG) {         // bias gradient: row sums of A (= column sums of D), fixed order
+  if (A_SRC == SRC_RCONTIG && EPI == EPI_PART && jb.db) {         // bias gradient: row sums of A (= column sums of D), fixed order
 #pragma unroll
-    for (int u = 0; u < Operand<BM>::U; ++u) red[warp * BM + u * 32 + lane] = rowsum[u];
+    for (int u = 0; u < Operand<BM>::U; ++u) red[(warp & 3) * BM + (2 * u + (warp >> 2)) * 32 + lane] = rowsum[u];   // [kgroup][row]
     __syncthreads();
     if (tid < rows) {
       float s = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) s += red[w * BM + tid];
+      for (int w = 0; w < 4; ++w) s += red[w * BM + tid];
       jb.db[(size_t)blockIdx.z * jb.M + m0 + tid] = s;
     }
   }
+#ifdef UG_TRACE
+  t_[4] = clock64();
+#endif
   tc::tc_fence_before();
   __syncthreads();
   if (warp == 0) tc::tmem_dealloc(tmem, TCOLS);
+#ifdef UG_TRACE
+  t_[5] = clock64();
+  if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+    printf("UG_TRACE NP=%d K=%d chunks=%d epi=%d: setup %lld loop %lld drain %lld epilogue %lld dealloc %lld\n", NP, jb.K, nchunks, jb.epi, t_[1]-t_[0], t_[2]-t_[1], t_[3]-t_[2], t_[4]-t_[3], t_[5]-t_[4]);
+#endif
 }
 
 }  // namespace ug
