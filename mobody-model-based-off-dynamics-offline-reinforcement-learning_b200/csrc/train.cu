@@ -950,7 +950,7 @@ const char* mb_train_adam_launch(const trn::AdamArgs& a, cudaStream_t st) {
 
 // ---------------- whole train step (C ABI: mobody_train_step) ----------------
 struct TrainWs {   // float offsets into the workspace
-  size_t Hq[2][2], Dq[2][2], d3[2], part, Hp[2], Dp[2], api, a2, qk[2], qtk[2], qv[2], qh[2], gak[2], d3p, scal, part2, cnt, gq[2][6], gp[6], T[2], total;
+  size_t Hq[2][2], Dq[2][2], d3[2], part, Hp[2], Dp[2], api, a2, qk[2], qtk[2], qv[2], qh[2], gak[2], d3p, scal, part2, cnt, gq[2][6], gp[6], T[2], img[17], total;
   int ntiles;
 };
 static TrainWs train_ws(int N, int S, int A, int nsplit) {
@@ -970,6 +970,11 @@ static TrainWs train_ws(int N, int S, int A, int nsplit) {
   for (int k = 0; k < 2; ++k) for (int t = 0; t < 6; ++t) w.gq[k][t] = take(qn[t] * nsplit);
   for (int t = 0; t < 6; ++t) w.gp[t] = take(pn[t] * nsplit);
   for (int l = 0; l < 2; ++l) w.T[l] = take(act);      // transient hidden activations of the tensor-core path (pi(s'), Q', q_hat)
+  {   // packed TF32 hi/lo weight images of the tensor-core path (umma_gemm.cuh: SRC_PACKED); slots: see mb_train_step_tc_launch
+    const int ik[17] = {S, 256, 256, S + A, S + A, 256, 256, S + A, S + A, 256, 256, 256, 256, A, 256, 256, 256};
+    const int inp[17] = {256, 256, 64, 256, 256, 256, 256, 256, 256, 256, 256, 256, 256, 256, 256, 64, 64};
+    for (int i = 0; i < 17; ++i) w.img[i] = take(ug::packed_floats(ik[i], inp[i]));
+  }
   w.total = o;
   return w;
 }
@@ -1003,6 +1008,11 @@ static ug::Job wgrad_job(const float* D, int ldd, int O, const float* X, int ldx
   j.epi = ug::EPI_PART; j.C = dW; j.db = db;
   return j;
 }
+static ug::Job packed(ug::Job j, const float* image) { j.B = image; j.b_src = ug::SRC_PACKED; return j; }
+const char* mb_pack_b_launch(const ug::PackArgs& a, cudaStream_t st);     // train_tc.cu
+static ug::PackJob pack_job(const float* src, int ld, int mode, int N, int K, int NP, float* dst) {
+  return ug::PackJob{src, ld, mode, N, K, NP, reinterpret_cast<uint32_t*>(dst)};
+}
 template <typename... J> static const char* run_gemms(cudaStream_t st, int nsplit, J... jobs) {
   ug::Args a{}; a.nsplit = nsplit;
   const ug::Job list[] = {jobs...};
@@ -1024,28 +1034,57 @@ static const char* mb_train_step_tc_launch(const mobody_train_desc& d, const Tra
   float* qv[2] = {ws + w.qv[0], ws + w.qv[1]}; float* qh[2] = {ws + w.qh[0], ws + w.qh[1]};
   float* gak[2] = {ws + w.gak[0], ws + w.gak[1]}; float* d3[2] = {ws + w.d3[0], ws + w.d3[1]};
   const char* e;
+  // ---- weight images: every weight matrix the GEMMs use as a B operand, split into TF32 hi / lo planes ONCE (one launch) ----
+  // slots: 0-2 pi W1 W2 W3 (forward) | 3,4 Q_k W1 | 5,6 Q_k W2 | 7,8 Q'_k W1 | 9,10 Q'_k W2 | 11,12 Q_k W2 (backward) |
+  //        13 pi W3 (backward) | 14 pi W2 (backward) | 15,16 action columns of Q_k W1 (backward)
+  static const bool use_img = [] { const char* v = getenv("MOBODY_TRAIN_PACKED"); return !(v && v[0] == '0'); }();
+  float* img[17];
+  for (int i = 0; i < 17; ++i) img[i] = ws + w.img[i];
+  auto P = [&](ug::Job j, int slot) { return use_img ? packed(j, img[slot]) : j; };
+  auto pack_q = [&](ug::PackArgs& pa, bool with_slices) {
+    for (int k = 0; k < 2; ++k) {
+      pa.job[pa.njobs++] = pack_job(q[k].w[0], SA, ug::SRC_KCONTIG, 256, SA, 256, img[3 + k]);
+      pa.job[pa.njobs++] = pack_job(q[k].w[1], 256, ug::SRC_KCONTIG, 256, 256, 256, img[5 + k]);
+      pa.job[pa.njobs++] = pack_job(q[k].w[1], 256, ug::SRC_RCONTIG, 256, 256, 256, img[11 + k]);
+      if (with_slices) pa.job[pa.njobs++] = pack_job(q[k].w[0] + S, SA, ug::SRC_RCONTIG, A, 256, 64, img[15 + k]);
+    }
+  };
+  if (use_img) {
+    ug::PackArgs pa{};
+    pa.job[pa.njobs++] = pack_job(pi.w[0], S, ug::SRC_KCONTIG, 256, S, 256, img[0]);
+    pa.job[pa.njobs++] = pack_job(pi.w[1], 256, ug::SRC_KCONTIG, 256, 256, 256, img[1]);
+    pa.job[pa.njobs++] = pack_job(pi.w[2], 256, ug::SRC_KCONTIG, A, 256, 64, img[2]);
+    pa.job[pa.njobs++] = pack_job(pi.w[2], 256, ug::SRC_RCONTIG, 256, A, 256, img[13]);
+    pa.job[pa.njobs++] = pack_job(pi.w[1], 256, ug::SRC_RCONTIG, 256, 256, 256, img[14]);
+    for (int k = 0; k < 2; ++k) {
+      pa.job[pa.njobs++] = pack_job(qt[k].w[0], SA, ug::SRC_KCONTIG, 256, SA, 256, img[7 + k]);
+      pa.job[pa.njobs++] = pack_job(qt[k].w[1], 256, ug::SRC_KCONTIG, 256, 256, 256, img[9 + k]);
+    }
+    pack_q(pa, false);
+    if ((e = mb_pack_b_launch(pa, st))) return e;
+  }
   // ---- critic forward.  layer 1 of pi(s'), Q1(s,a), Q2(s,a), pi(s) side by side; then layer 2 (+ Q heads); then the policy tails ----
-  if ((e = run_gemms(st, 1, fwd_job(X + SA, rw, N, S, pi.w[0], pi.b[0], 256, T[0]), fwd_job(X, rw, N, SA, q[0].w[0], q[0].b[0], 256, Hq[0][0]),
-                     fwd_job(X, rw, N, SA, q[1].w[0], q[1].b[0], 256, Hq[1][0]), fwd_job(X, rw, N, S, pi.w[0], pi.b[0], 256, Hp[0])))) return e;
+  if ((e = run_gemms(st, 1, P(fwd_job(X + SA, rw, N, S, pi.w[0], pi.b[0], 256, T[0]), 0), P(fwd_job(X, rw, N, SA, q[0].w[0], q[0].b[0], 256, Hq[0][0]), 3),
+                     P(fwd_job(X, rw, N, SA, q[1].w[0], q[1].b[0], 256, Hq[1][0]), 4), P(fwd_job(X, rw, N, S, pi.w[0], pi.b[0], 256, Hp[0]), 0)))) return e;
   {
     ug::Job j1 = fwd_job(Hq[0][0], 256, N, 256, q[0].w[1], q[0].b[1], 256, Hq[0][1]), j2 = fwd_job(Hq[1][0], 256, N, 256, q[1].w[1], q[1].b[1], 256, Hq[1][1]);
     j1.epi = j2.epi = ug::EPI_HEAD; j1.w3 = q[0].w[2]; j1.b3 = q[0].b[2]; j1.out1 = qk[0]; j2.w3 = q[1].w[2]; j2.b3 = q[1].b[2]; j2.out1 = qk[1];
-    if ((e = run_gemms(st, 1, fwd_job(T[0], 256, N, 256, pi.w[1], pi.b[1], 256, T[1]), j1, j2, fwd_job(Hp[0], 256, N, 256, pi.w[1], pi.b[1], 256, Hp[1])))) return e;
+    if ((e = run_gemms(st, 1, P(fwd_job(T[0], 256, N, 256, pi.w[1], pi.b[1], 256, T[1]), 1), P(j1, 5), P(j2, 6), P(fwd_job(Hp[0], 256, N, 256, pi.w[1], pi.b[1], 256, Hp[1]), 1)))) return e;
   }
   {
     ug::Job t1 = fwd_job(T[1], 256, N, 256, pi.w[2], pi.b[2], A, a2, false), t2 = fwd_job(Hp[1], 256, N, 256, pi.w[2], pi.b[2], A, api, false);
     t1.epi = t2.epi = ug::EPI_TANH; t1.scale = t2.scale = d.max_action;
-    if ((e = run_gemms(st, 1, t1, t2))) return e;
+    if ((e = run_gemms(st, 1, P(t1, 2), P(t2, 2)))) return e;
   }
   // ---- target critics on (s', pi(s')): the input is [s' | a2], read from two sources ----
   {
     ug::Job j1 = fwd_job(X + SA, rw, N, SA, qt[0].w[0], qt[0].b[0], 256, T[0]), j2 = fwd_job(X + SA, rw, N, SA, qt[1].w[0], qt[1].b[0], 256, T[1]);
     j1.A2 = j2.A2 = a2; j1.lda2 = j2.lda2 = A; j1.ksplit = j2.ksplit = S;
-    if ((e = run_gemms(st, 1, j1, j2))) return e;
+    if ((e = run_gemms(st, 1, P(j1, 7), P(j2, 8)))) return e;
     // layer 2 + head in place is not possible (C would overwrite A of another tile's... no: tiles own their rows) -> no C store at all
     ug::Job h1 = fwd_job(T[0], 256, N, 256, qt[0].w[1], qt[0].b[1], 256, nullptr), h2 = fwd_job(T[1], 256, N, 256, qt[1].w[1], qt[1].b[1], 256, nullptr);
     h1.epi = h2.epi = ug::EPI_HEAD; h1.w3 = qt[0].w[2]; h1.b3 = qt[0].b[2]; h1.out1 = qtk[0]; h2.w3 = qt[1].w[2]; h2.b3 = qt[1].b[2]; h2.out1 = qtk[1];
-    if ((e = run_gemms(st, 1, h1, h2))) return e;
+    if ((e = run_gemms(st, 1, P(h1, 9), P(h2, 10)))) return e;
   }
   // ---- TD target + MSE gradient, head backward, backward-data ----
   {
@@ -1053,8 +1092,8 @@ static const char* mb_train_step_tc_launch(const mobody_train_desc& d, const Tra
     mb_launch(trn::td_kernel, dim3((N + 255) / 256), dim3(256), 0, st, t);
     trn::HeadBwdArgs hb{{Hq[0][1], Hq[1][1]}, {d3[0], d3[1]}, {q[0].w[2], q[1].w[2]}, {Dq[0][1], Dq[1][1]}, N};
     mb_launch(trn::head_bwd_kernel, dim3(296, 2), dim3(256), 0, st, hb);
-    if ((e = run_gemms(st, 1, bwd_job(Dq[0][1], 256, N, 256, q[0].w[1], 256, 256, Hq[0][0], Dq[0][0]),
-                       bwd_job(Dq[1][1], 256, N, 256, q[1].w[1], 256, 256, Hq[1][0], Dq[1][0])))) return e;
+    if ((e = run_gemms(st, 1, P(bwd_job(Dq[0][1], 256, N, 256, q[0].w[1], 256, 256, Hq[0][0], Dq[0][0]), 11),
+                       P(bwd_job(Dq[1][1], 256, N, 256, q[1].w[1], 256, 256, Hq[1][0], Dq[1][0]), 12)))) return e;
   }
   // ---- critic weight gradients (row-split partials) + Adam + Polyak ----
   const mobody_mlp_state* qs[2] = {&d.q1, &d.q2};
@@ -1084,15 +1123,20 @@ static const char* mb_train_step_tc_launch(const mobody_train_desc& d, const Tra
       }
   }
   if ((e = mb_train_adam_launch(ad, st))) return e;
+  if (use_img) {   // the critics just changed: their images again (+ the action columns of W1 for dQ/da)
+    ug::PackArgs pa{};
+    pack_q(pa, true);
+    if ((e = mb_pack_b_launch(pa, st))) return e;
+  }
   // ---- actor: Q_k(s, pi(s)) with the UPDATED, frozen critics (activations kept for the backward), q_hat_k on the true rows ----
   {
     ug::Job j1 = fwd_job(X, rw, N, SA, q[0].w[0], q[0].b[0], 256, Hq[0][0]), j2 = fwd_job(X, rw, N, SA, q[1].w[0], q[1].b[0], 256, Hq[1][0]);
     j1.A2 = j2.A2 = api; j1.lda2 = j2.lda2 = A; j1.ksplit = j2.ksplit = S;
-    if ((e = run_gemms(st, 1, j1, j2, fwd_job(X, rw, nt, SA, q[0].w[0], q[0].b[0], 256, T[0]), fwd_job(X, rw, nt, SA, q[1].w[0], q[1].b[0], 256, T[1])))) return e;
+    if ((e = run_gemms(st, 1, P(j1, 3), P(j2, 4), P(fwd_job(X, rw, nt, SA, q[0].w[0], q[0].b[0], 256, T[0]), 3), P(fwd_job(X, rw, nt, SA, q[1].w[0], q[1].b[0], 256, T[1]), 4)))) return e;
     ug::Job h[4] = {fwd_job(Hq[0][0], 256, N, 256, q[0].w[1], q[0].b[1], 256, Hq[0][1]), fwd_job(Hq[1][0], 256, N, 256, q[1].w[1], q[1].b[1], 256, Hq[1][1]),
                     fwd_job(T[0], 256, nt, 256, q[0].w[1], q[0].b[1], 256, nullptr), fwd_job(T[1], 256, nt, 256, q[1].w[1], q[1].b[1], 256, nullptr)};
     for (int i = 0; i < 4; ++i) { h[i].epi = ug::EPI_HEAD; h[i].w3 = q[i & 1].w[2]; h[i].b3 = q[i & 1].b[2]; h[i].out1 = i < 2 ? qv[i] : qh[i - 2]; }
-    if ((e = run_gemms(st, 1, h[0], h[1], h[2], h[3]))) return e;
+    if ((e = run_gemms(st, 1, P(h[0], 5), P(h[1], 6), P(h[2], 5), P(h[3], 6)))) return e;
   }
   trn::ActorArgs ac{};
   ac.X = X; ac.N = N; ac.n_true = nt; ac.S = S; ac.A = A; ac.rw = rw; ac.max_action = d.max_action;
@@ -1103,10 +1147,10 @@ static const char* mb_train_step_tc_launch(const mobody_train_desc& d, const Tra
   {   // dQ_k / d action: head backward with unit gradient, backward-data through layers 2 and 1 (action columns of W1 only)
     trn::HeadBwdArgs hb{{Hq[0][1], Hq[1][1]}, {nullptr, nullptr}, {q[0].w[2], q[1].w[2]}, {Dq[0][1], Dq[1][1]}, N};
     mb_launch(trn::head_bwd_kernel, dim3(296, 2), dim3(256), 0, st, hb);
-    if ((e = run_gemms(st, 1, bwd_job(Dq[0][1], 256, N, 256, q[0].w[1], 256, 256, Hq[0][0], Dq[0][0]),
-                       bwd_job(Dq[1][1], 256, N, 256, q[1].w[1], 256, 256, Hq[1][0], Dq[1][0])))) return e;
-    if ((e = run_gemms(st, 1, bwd_job(Dq[0][0], 256, N, 256, q[0].w[0] + S, SA, A, nullptr, gak[0]),
-                       bwd_job(Dq[1][0], 256, N, 256, q[1].w[0] + S, SA, A, nullptr, gak[1])))) return e;
+    if ((e = run_gemms(st, 1, P(bwd_job(Dq[0][1], 256, N, 256, q[0].w[1], 256, 256, Hq[0][0], Dq[0][0]), 11),
+                       P(bwd_job(Dq[1][1], 256, N, 256, q[1].w[1], 256, 256, Hq[1][0], Dq[1][0]), 12)))) return e;
+    if ((e = run_gemms(st, 1, P(bwd_job(Dq[0][0], 256, N, 256, q[0].w[0] + S, SA, A, nullptr, gak[0]), 15),
+                       P(bwd_job(Dq[1][0], 256, N, 256, q[1].w[0] + S, SA, A, nullptr, gak[1]), 16)))) return e;
   }
   trn::PolicyBwdArgs pb{}; pb.N = N; pb.n_true = nt; pb.S = S; pb.A = A; pb.rw = rw; pb.pi = pi;
   for (int k = 0; k < 2; ++k) { pb.gak[k] = gak[k]; pb.qv[k] = qv[k]; pb.qh[k] = qh[k]; }
@@ -1114,8 +1158,8 @@ static const char* mb_train_step_tc_launch(const mobody_train_desc& d, const Tra
   pb.d3p = d3p; pb.part = ws + w.part2; pb.out = ws + w.scal; pb.counter = reinterpret_cast<int*>(ws + w.cnt) + 1;
   mb_launch(trn::policy_grad_kernel, dim3((N + 127) / 128), dim3(128), 0, st, pb);
   // ---- policy backward-data: dH2 = (d3 W3) * 1[H2 > 0], dH1 = (dH2 W2) * 1[H1 > 0]; weight gradients; Adam ----
-  if ((e = run_gemms(st, 1, bwd_job(d3p, A, N, A, pi.w[2], 256, 256, Hp[1], Dp[1])))) return e;
-  if ((e = run_gemms(st, 1, bwd_job(Dp[1], 256, N, 256, pi.w[1], 256, 256, Hp[0], Dp[0])))) return e;
+  if ((e = run_gemms(st, 1, P(bwd_job(d3p, A, N, A, pi.w[2], 256, 256, Hp[1], Dp[1]), 13)))) return e;
+  if ((e = run_gemms(st, 1, P(bwd_job(Dp[1], 256, N, 256, pi.w[1], 256, 256, Hp[0], Dp[0]), 14)))) return e;
   if ((e = run_gemms(st, ns, wgrad_job(Dp[1], 256, 256, Hp[0], 256, 256, N, ws + w.gp[2], ws + w.gp[3]),
                      wgrad_job(Dp[0], 256, 256, X, rw, S, N, ws + w.gp[0], ws + w.gp[1])))) return e;
   {

@@ -13,6 +13,8 @@
 // Operand sources (element (row, k) of a K-major operand plane; row = m for A, n for B):
 //   SRC_KCONTIG : src[row * ld + k]      (activations, nn.Linear weight used "forward")
 //   SRC_RCONTIG : src[k * ld + row]      (weight used "backward", and both operands of a weight gradient)
+//   SRC_PACKED  : (B only) a weight matrix split ONCE per update into its hi / lo planes, already in the stage layout
+//                 [chunk][plane][kgroup][n][4 k]: one cp.async.bulk per chunk replaces two thirds of the per-chunk ALU work
 #pragma once
 #include "common.cuh"
 #include "tc_prims.cuh"
@@ -24,7 +26,8 @@ constexpr int BM = 128;          // rows of C per CTA (UMMA M)
 constexpr int KC = 16;           // K per pipeline stage = 2 UMMA K steps of 8 (two stages of a 128 x 256 tile = 96 KB: two CTAs per SM)
 constexpr int NT = 256;          // threads per CTA
 
-enum { SRC_KCONTIG = 0, SRC_RCONTIG = 1 };
+enum { SRC_KCONTIG = 0, SRC_RCONTIG = 1,
+       SRC_PACKED = 2 };   // B only: pre-split TF32 hi/lo image in stage layout (pack_b_kernel), streamed by TMA bulk copies
 // Epilogue kinds.  EPI_STORE and EPI_HEAD share one compiled epilogue (a job without w3 has no head), the others are their own
 // instantiations: the epilogue body is unrolled per 32 x 32 block, so every variant compiled into it is paid in issue slots.
 enum { EPI_STORE = 0,   // C = act(acc + bias)                       -> C[m][n]
@@ -144,9 +147,10 @@ __global__ void __launch_bounds__(NT, 2) gemm_kernel(const __grid_constant__ Arg
   long long t_[6]; t_[0] = clock64();
 #endif
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ uint64_t bar_free[2], bar_done;
+  __shared__ uint64_t bar_free[2], bar_done, bar_fullb[2];
   __shared__ uint32_t tmem_slot;
   __shared__ float red[8 * BM];
+  __shared__ __align__(16) float bias_s[256], w3_s[256];     // epilogue vectors, fetched while the main loop runs
   const Job& jb = args.job[blockIdx.y];
   const int m0 = blockIdx.x * BM;
   if (m0 >= jb.M) return;
@@ -163,7 +167,14 @@ __global__ void __launch_bounds__(NT, 2) gemm_kernel(const __grid_constant__ Arg
   }
   const int nchunks = kend > kbeg ? (kend - kbeg + KC - 1) / KC : 0;
 
-  if (tid == 0) { tc::mbar_init(&bar_free[0], 1); tc::mbar_init(&bar_free[1], 1); tc::mbar_init(&bar_done, 1); tc::mbar_fence_init(); }
+  if (tid == 0) {
+    tc::mbar_init(&bar_free[0], 1); tc::mbar_init(&bar_free[1], 1); tc::mbar_init(&bar_done, 1);
+    tc::mbar_init(&bar_fullb[0], 1); tc::mbar_init(&bar_fullb[1], 1); tc::mbar_fence_init();
+  }
+  if (EPI == EPI_STORE || EPI == EPI_TANH) {
+    bias_s[tid] = (jb.bias && tid < jb.N) ? __ldg(jb.bias + tid) : 0.f;
+    w3_s[tid] = (EPI == EPI_STORE && jb.w3 && tid < jb.N) ? __ldg(jb.w3 + tid) : 0.f;
+  }
   if (warp == 0) tc::tmem_alloc(&tmem_slot, TCOLS);
   tc::tc_fence_before();
   __syncthreads();
@@ -189,17 +200,25 @@ __global__ void __launch_bounds__(NT, 2) gemm_kernel(const __grid_constant__ Arg
     if (c >= 0) {
       if (c >= 2) tc::mbar_wait(&bar_free[buf], (uint32_t)(((c >> 1) - 1) & 1));    // the MMAs that read this stage are done
       oa.store(st, A_SRC);
-      ob.store(st + 2 * A_PLANE, B_SRC);
+      if (B_SRC != SRC_PACKED) ob.store(st + 2 * A_PLANE, B_SRC);
     }
     if (c + 1 < nchunks) {                                              // next chunk's global loads fly during this chunk's MMAs
       const int k0 = kbeg + (c + 1) * KC;
       oa.load(jb.A, jb.lda, A_SRC, m0, rows, k0, kend, jb.A2, jb.lda2, jb.ksplit, rs);
-      ob.load(jb.B, jb.ldb, B_SRC, 0, nrows_b, k0, kend, nullptr, 0, 0, nullptr);
+      if (B_SRC != SRC_PACKED) ob.load(jb.B, jb.ldb, B_SRC, 0, nrows_b, k0, kend, nullptr, 0, 0, nullptr);
+    }
+    if (B_SRC == SRC_PACKED && tid == 32 && c + 1 < nchunks) {          // TMA: chunk c + 1 of the packed weight image -> the other stage
+      const int nb = (c + 1) & 1;
+      if (c + 1 >= 2) tc::mbar_wait(&bar_free[nb], (uint32_t)((((c + 1) >> 1) - 1) & 1));
+      tc::mbar_arrive_expect_tx(&bar_fullb[nb], 2 * B_PLANE);
+      tc::bulk_g2s(smem + (size_t)nb * STAGE + 2 * A_PLANE, reinterpret_cast<const unsigned char*>(jb.B) + (size_t)(kbeg / KC + c + 1) * (2 * B_PLANE),
+                   2 * B_PLANE, &bar_fullb[nb]);
     }
     if (c < 0) continue;
     tc::fence_proxy_async_smem();
     __syncthreads();
     if (tid == 0) {
+      if (B_SRC == SRC_PACKED) tc::mbar_wait(&bar_fullb[buf], (uint32_t)((c >> 1) & 1));
       tc::tc_fence_after();
       const uint32_t a0 = tc::smem_u32(st), b0 = a0 + 2 * A_PLANE;
 #pragma unroll
@@ -237,8 +256,7 @@ __global__ void __launch_bounds__(NT, 2) gemm_kernel(const __grid_constant__ Arg
   float* cbase = jb.C ? jb.C + (EPI == EPI_PART ? (size_t)blockIdx.z * jb.M * jb.N : 0) + (size_t)(m0 + q * 32 + rl) * ldc : nullptr;
   // fast path: whole 4-column groups, 16-byte aligned rows (every 256-wide tensor of the update)
   const bool fast = (jb.N & 3) == 0 && (!jb.C || ((ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(jb.C) & 15) == 0)) &&
-                    (EPI != EPI_MASK || ((jb.ldmask & 3) == 0 && (reinterpret_cast<uintptr_t>(jb.mask) & 15) == 0)) &&
-                    (!jb.bias || (reinterpret_cast<uintptr_t>(jb.bias) & 15) == 0) && (!jb.w3 || (reinterpret_cast<uintptr_t>(jb.w3) & 15) == 0);
+                    (EPI != EPI_MASK || ((jb.ldmask & 3) == 0 && (reinterpret_cast<uintptr_t>(jb.mask) & 15) == 0));
   float head[8];
 #pragma unroll
   for (int it = 0; it < 8; ++it) head[it] = 0.f;
@@ -265,10 +283,7 @@ __global__ void __launch_bounds__(NT, 2) gemm_kernel(const __grid_constant__ Arg
     __syncwarp();
     if (fast) {
       float4 bq = make_float4(0.f, 0.f, 0.f, 0.f), wq = bq;
-      if (colok) {
-        if (jb.bias) bq = __ldg(reinterpret_cast<const float4*>(jb.bias + n));
-        if (EPI == EPI_STORE && jb.w3) wq = __ldg(reinterpret_cast<const float4*>(jb.w3 + n));
-      }
+      if (EPI == EPI_STORE || EPI == EPI_TANH) { bq = *reinterpret_cast<const float4*>(bias_s + n); wq = *reinterpret_cast<const float4*>(w3_s + n); }
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const int rr = it * 4 + rl;
@@ -291,7 +306,7 @@ __global__ void __launch_bounds__(NT, 2) gemm_kernel(const __grid_constant__ Arg
         float t = tb[rr * 36 + c];
         if (EPI == EPI_MASK) t = __ldg(jb.mask + (size_t)(m0 + r) * jb.ldmask + nn) > 0.f ? t : 0.f;
         else if (EPI != EPI_PART) {
-          if (jb.bias) t += __ldg(jb.bias + nn);
+          t += bias_s[nn];
           if (EPI == EPI_TANH) t = tanhf(t) * jb.scale;
           else if (jb.relu) t = fmaxf(t, 0.f);
         }
@@ -334,4 +349,9 @@ __global__ void __launch_bounds__(NT, 2) gemm_kernel(const __grid_constant__ Arg
 #endif
 }
 
+// ---- packed B images: a weight matrix split once per update into TF32 hi / lo planes, in the stage layout of gemm_kernel<NP> ----
+// image[chunk][plane][kgroup 0..3][n 0..NP)[4 k]; logical B[n][k] = src[n * ld + k] (mode SRC_KCONTIG) or src[k * ld + n] (SRC_RCONTIG)
+struct PackJob { const float* src; int ld, mode, N, K, NP; uint32_t* dst; };
+struct PackArgs { PackJob job[16]; int njobs; };
+__host__ __device__ inline size_t packed_floats(int K, int NP) { return (size_t)((K + KC - 1) / KC) * 2 * (KC / 4) * NP * 4; }
 }  // namespace ug
