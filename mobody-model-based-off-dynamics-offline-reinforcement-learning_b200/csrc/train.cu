@@ -824,6 +824,47 @@ __global__ void __launch_bounds__(256) head_bwd_kernel(const HeadBwdArgs a) {
   }
 }
 
+// Narrow tails with 256 inputs and A <= 32 outputs per row (policy head: tanh(h W3^T + b) * max_action; dQ/da = dH1 W1[:, S:]):
+// one warp per row, the A x 256 weight slice in shared memory, lanes along the 256 inputs (two 128-bit loads each).
+struct RowDotJob { const float* X; const float* W; int ldw, wt; const float* b; float* out; int M; };    // wt = 0: W[j][k] (ld = ldw); 1: W[k][j]
+struct RowDotArgs { RowDotJob job[4]; int njobs, A; float scale; int tanh_act; };
+__global__ void __launch_bounds__(256) rowdot_kernel(const RowDotArgs a) {
+  mb_pdl_begin();
+  extern __shared__ __align__(16) float wsm[];                      // [A][256]
+  const RowDotJob& jb = a.job[blockIdx.y];
+  for (int i = threadIdx.x; i < a.A * H; i += 256) {
+    const int j = i >> 8, k = i & 255;
+    wsm[i] = jb.wt ? __ldg(jb.W + (size_t)k * jb.ldw + j) : __ldg(jb.W + (size_t)j * jb.ldw + k);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int step = gridDim.x * 8;
+  int m = blockIdx.x * 8 + warp;
+  float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0;
+  if (m < jb.M) { x0 = __ldg(reinterpret_cast<const float4*>(jb.X + (size_t)m * H) + lane); x1 = __ldg(reinterpret_cast<const float4*>(jb.X + (size_t)m * H) + 32 + lane); }
+  for (; m < jb.M; m += step) {
+    float4 n0 = x0, n1 = x1;                                         // next row in flight while this one is reduced
+    if (m + step < jb.M) {
+      n0 = __ldg(reinterpret_cast<const float4*>(jb.X + (size_t)(m + step) * H) + lane);
+      n1 = __ldg(reinterpret_cast<const float4*>(jb.X + (size_t)(m + step) * H) + 32 + lane);
+    }
+    float mine = 0.f;
+    for (int j = 0; j < a.A; ++j) {
+      const float4 w0 = *(reinterpret_cast<const float4*>(wsm + j * H) + lane), w1 = *(reinterpret_cast<const float4*>(wsm + j * H) + 32 + lane);
+      float s = x0.x * w0.x + x0.y * w0.y + x0.z * w0.z + x0.w * w0.w + x1.x * w1.x + x1.y * w1.y + x1.z * w1.z + x1.w * w1.w;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == j) mine = s;
+    }
+    if (lane < a.A) {
+      float t = mine + (jb.b ? __ldg(jb.b + lane) : 0.f);
+      if (a.tanh_act) t = tanhf(t) * a.scale;
+      jb.out[(size_t)m * a.A + lane] = t;
+    }
+    x0 = n0; x1 = n1;
+  }
+}
+
 __global__ void __launch_bounds__(1024) actor_scalar_kernel(const ActorArgs a) {
   mb_pdl_begin();
   __shared__ float sh[40];
@@ -1072,9 +1113,9 @@ static const char* mb_train_step_tc_launch(const mobody_train_desc& d, const Tra
     if ((e = run_gemms(st, 1, P(fwd_job(T[0], 256, N, 256, pi.w[1], pi.b[1], 256, T[1]), 1), P(j1, 5), P(j2, 6), P(fwd_job(Hp[0], 256, N, 256, pi.w[1], pi.b[1], 256, Hp[1]), 1)))) return e;
   }
   {
-    ug::Job t1 = fwd_job(T[1], 256, N, 256, pi.w[2], pi.b[2], A, a2, false), t2 = fwd_job(Hp[1], 256, N, 256, pi.w[2], pi.b[2], A, api, false);
-    t1.epi = t2.epi = ug::EPI_TANH; t1.scale = t2.scale = d.max_action;
-    if ((e = run_gemms(st, 1, P(t1, 2), P(t2, 2)))) return e;
+    trn::RowDotArgs rd{}; rd.njobs = 2; rd.A = A; rd.scale = d.max_action; rd.tanh_act = 1;
+    rd.job[0] = {T[1], pi.w[2], 256, 0, pi.b[2], a2, N}; rd.job[1] = {Hp[1], pi.w[2], 256, 0, pi.b[2], api, N};
+    mb_launch(trn::rowdot_kernel, dim3(296, 2), dim3(256), (size_t)A * 256 * sizeof(float), st, rd);
   }
   // ---- target critics on (s', pi(s')): the input is [s' | a2], read from two sources ----
   {
@@ -1103,12 +1144,9 @@ static const char* mb_train_step_tc_launch(const mobody_train_desc& d, const Tra
   if ((e = run_gemms(st, ns, wgrad_job(Dq[0][1], 256, 256, Hq[0][0], 256, 256, N, ws + w.gq[0][2], ws + w.gq[0][3]),
                      wgrad_job(Dq[1][1], 256, 256, Hq[1][0], 256, 256, N, ws + w.gq[1][2], ws + w.gq[1][3]),
                      wgrad_job(Dq[0][0], 256, 256, X, rw, SA, N, ws + w.gq[0][0], ws + w.gq[0][1]),
-                     wgrad_job(Dq[1][0], 256, 256, X, rw, SA, N, ws + w.gq[1][0], ws + w.gq[1][1])))) return e;
-  {
-    trn::WgradArgs g{}; g.N = N; g.nsplit = ns; g.njobs = 2;
-    for (int k = 0; k < 2; ++k) g.job[k] = {d3[k], 1, Hq[k][1], 256, ws + w.gq[k][4], ws + w.gq[k][5], 1, 256};
-    if ((e = mb_train_wgrad_launch(g, st))) return e;
-  }
+                     wgrad_job(Dq[1][0], 256, 256, X, rw, SA, N, ws + w.gq[1][0], ws + w.gq[1][1]),
+                     wgrad_job(d3[0], 1, 1, Hq[0][1], 256, 256, N, ws + w.gq[0][4], ws + w.gq[0][5]),     // the one-output heads: one
+                     wgrad_job(d3[1], 1, 1, Hq[1][1], 256, 256, N, ws + w.gq[1][4], ws + w.gq[1][5])))) return e;   // (mostly empty) tile each
   trn::AdamArgs ad{}; ad.nsplit = ns; ad.b1 = 0.9f; ad.b2 = 0.999f; ad.eps = 1e-8f; ad.tau = d.tau; ad.njobs = 12;
   ad.zero2 = reinterpret_cast<int*>(ws + w.cnt);
   {
@@ -1149,8 +1187,10 @@ static const char* mb_train_step_tc_launch(const mobody_train_desc& d, const Tra
     mb_launch(trn::head_bwd_kernel, dim3(296, 2), dim3(256), 0, st, hb);
     if ((e = run_gemms(st, 1, P(bwd_job(Dq[0][1], 256, N, 256, q[0].w[1], 256, 256, Hq[0][0], Dq[0][0]), 11),
                        P(bwd_job(Dq[1][1], 256, N, 256, q[1].w[1], 256, 256, Hq[1][0], Dq[1][0]), 12)))) return e;
-    if ((e = run_gemms(st, 1, P(bwd_job(Dq[0][0], 256, N, 256, q[0].w[0] + S, SA, A, nullptr, gak[0]), 15),
-                       P(bwd_job(Dq[1][0], 256, N, 256, q[1].w[0] + S, SA, A, nullptr, gak[1]), 16)))) return e;
+    trn::RowDotArgs rd{}; rd.njobs = 2; rd.A = A; rd.scale = 1.f; rd.tanh_act = 0;
+    for (int k = 0; k < 2; ++k) rd.job[k] = {Dq[k][0], q[k].w[0] + S, SA, 0, nullptr, gak[k], N};     // W1 is [256 out][S+A in]: gak[m][j] = sum_n dH1[m][n] W1[n][S+j]
+    for (int k = 0; k < 2; ++k) rd.job[k].wt = 1;
+    mb_launch(trn::rowdot_kernel, dim3(296, 2), dim3(256), (size_t)A * 256 * sizeof(float), st, rd);
   }
   trn::PolicyBwdArgs pb{}; pb.N = N; pb.n_true = nt; pb.S = S; pb.A = A; pb.rw = rw; pb.pi = pi;
   for (int k = 0; k < 2; ++k) { pb.gak[k] = gak[k]; pb.qv[k] = qv[k]; pb.qh[k] = qh[k]; }
@@ -1161,12 +1201,8 @@ static const char* mb_train_step_tc_launch(const mobody_train_desc& d, const Tra
   if ((e = run_gemms(st, 1, P(bwd_job(d3p, A, N, A, pi.w[2], 256, 256, Hp[1], Dp[1]), 13)))) return e;
   if ((e = run_gemms(st, 1, P(bwd_job(Dp[1], 256, N, 256, pi.w[1], 256, 256, Hp[0], Dp[0]), 14)))) return e;
   if ((e = run_gemms(st, ns, wgrad_job(Dp[1], 256, 256, Hp[0], 256, 256, N, ws + w.gp[2], ws + w.gp[3]),
-                     wgrad_job(Dp[0], 256, 256, X, rw, S, N, ws + w.gp[0], ws + w.gp[1])))) return e;
-  {
-    trn::WgradArgs g{}; g.N = N; g.nsplit = ns; g.njobs = 1;
-    g.job[0] = {d3p, A, Hp[1], 256, ws + w.gp[4], ws + w.gp[5], A, 256};
-    if ((e = mb_train_wgrad_launch(g, st))) return e;
-  }
+                     wgrad_job(Dp[0], 256, 256, X, rw, S, N, ws + w.gp[0], ws + w.gp[1]),
+                     wgrad_job(d3p, A, A, Hp[1], 256, 256, N, ws + w.gp[4], ws + w.gp[5])))) return e;
   trn::AdamArgs ap{}; ap.nsplit = ns; ap.b1 = 0.9f; ap.b2 = 0.999f; ap.eps = 1e-8f; ap.tau = 0.f; ap.njobs = 6;
   {
     const double bc1 = 1.0 - pow(0.9, (double)d.t_pi), bc2 = 1.0 - pow(0.999, (double)d.t_pi);

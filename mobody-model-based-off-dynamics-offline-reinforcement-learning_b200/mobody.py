@@ -547,8 +547,8 @@ class MOBODY(object):
         if nsplit is None:
             # row splits of the weight-gradient GEMMs (partials summed in Adam, fixed order); 128 x 64 tiles per split:
             # critic 2 x (256 x 256 -> 8, 256 x (S+A) -> 2 per 64 columns), actor 8 + 2 per 64 columns of S
-            if N >= self.TC_TRAIN_ROWS:   # tcgen05 path: 128 x 256 GEMM tiles, one CTA per SM; critic launch 4 jobs x 2 tiles, actor 2 x 2
-                nsplit = _wgrad_splits(N, (8, 4), self.device, ctas_per_sm=1)
+            if N >= self.TC_TRAIN_ROWS:   # tcgen05 path: 128 x 256 GEMM tiles, two CTAs per SM; critic launch 4 x 2 + 2 x 1 tiles, actor 2 x 2 + 1
+                nsplit = _wgrad_splits(N, (10, 5), self.device, ctas_per_sm=2)
             else:
                 nsplit = _wgrad_splits(N, (2 * (8 + 2 * ((S + A + 63) // 64)), 8 + 2 * ((S + 63) // 64)), self.device)
         lib = _ffi.lib()
