@@ -482,10 +482,34 @@ def main():
             pending.pop(0).wait()
 
     produced = torch.zeros(1, dtype=torch.float64, device=dev)   # transitions produced by this rank (device accumulator)
+    # N = 1: consecutive rollouts are independent, so they alternate between the agent's two rollout streams (own workspace
+    # each): the last, 72 %-idle round of one step kernel (782 tiles on 148 SMs) runs beside the first round of the next.
+    two_streams = dist is None and os.environ.get("MOBODY_BENCH_STREAMS", "2") != "1"
+    side = ag.rollout_streams() if two_streams else None
+    produced_side = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(2)]
+
+    def fork_streams():
+        if side:
+            ag.verify_images()
+            for st in side:
+                st.wait_stream(torch.cuda.current_stream(dev))
+
+    def join_streams():
+        if side:
+            for st in side:
+                torch.cuda.current_stream(dev).wait_stream(st)
+            produced.add_(produced_side[0]).add_(produced_side[1])
+            produced_side[0].zero_(); produced_side[1].zero_()
 
     def one_rollout_device():
         """One rollout with nothing read back by the host (counts stay on the device; read once after the timed region)."""
-        x = obs_pool[pool_i[0] % n_pool]; pool_i[0] += 1
+        i = pool_i[0]
+        x = obs_pool[i % n_pool]; pool_i[0] += 1
+        if side:
+            with torch.cuda.stream(side[i & 1]):
+                o, info = ag.rollout_device(x, T, row0=rank * Bn, sync=False, ws_slot=10 + (i & 1), verify_images=False)
+                produced_side[i & 1].add_(info["stats_dev"][1:2])
+            return
         if dist is None:
             o, info = ag.rollout_device(x, T, row0=rank * Bn, sync=False)
         elif exchange == "p2p":
@@ -503,9 +527,11 @@ def main():
         produced.add_(info["stats_dev"][1:2])
 
     # ---- device-resident timing ----
+    fork_streams()
     for _ in range(W):
         one_rollout_device()
     drain()
+    join_streams()
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -515,9 +541,11 @@ def main():
     wall0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    fork_streams()
     for _ in range(args.steps):
         one_rollout_device()
     drain()                                               # every rank's rows of every step have landed before the closing event
+    join_streams()
     e1.record()
     torch.cuda.synchronize()
     if dist is not None:
@@ -640,6 +668,8 @@ def main():
                                f"(BASELINE configs[1])",
                    "precision": prec, "l2": f"inputs larger than L2: start states rotate over {n_pool} distinct buffers ({n_pool * Bn * S * 4 >> 20} MiB > 126 MB L2); "
                          "kernel-only timings flush L2 with a 256 MiB memset before each launch",
+                   "streams": "consecutive (independent) rollouts alternate between two CUDA streams: one step kernel's partial last round overlaps the next one's first"
+                              if two_streams else "one stream",
                    "parallelism": (f"dp{world} (start states sharded; transitions assembled in every rank's buffer by "
                                    f"{'peer-memory stores from the pack kernel' if exchange == 'p2p' else 'an NCCL all-gather of padded slabs'})")
                                   if world > 1 else "single GPU"},

@@ -107,18 +107,20 @@ class MOBODYEnsembleDynamics(object):
             self._packs[slot] = ent
         return ent
 
-    def _packed_dynamics(self, dp, keep):
+    def _packed_dynamics(self, dp, keep, verify=True):
         S, A, prec = self.model.obs_dim, self.model.action_dim, _ffi.PREC[self.precision]
         dev = keep[0].device
         blob, state = self._packed_image(("dyn", self.precision), int(_ffi.lib().mobody_dyn_pack_bytes(S, A, prec)), dev)
-        _ffi.check(_ffi.lib().mobody_dyn_pack(C.byref(dp), S, A, prec, _ffi.ptr(blob), _ffi.ptr(state), _ffi.stream_ptr(dev)))
+        if verify:
+            _ffi.check(_ffi.lib().mobody_dyn_pack(C.byref(dp), S, A, prec, _ffi.ptr(blob), _ffi.ptr(state), _ffi.stream_ptr(dev)))
         return blob
 
-    def _packed_policy(self, policy, mp, keep):
+    def _packed_policy(self, policy, mp, keep, verify=True):
         S, A, prec = self.model.obs_dim, self.model.action_dim, _ffi.PREC[self.precision]
         dev = keep[0].device
         blob, state = self._packed_image(("pol", id(policy), self.precision), int(_ffi.lib().mobody_mlp_pack_bytes(S, A, prec)), dev)
-        _ffi.check(_ffi.lib().mobody_mlp_pack(C.byref(mp), S, A, prec, _ffi.ptr(blob), _ffi.ptr(state), _ffi.stream_ptr(dev)))
+        if verify:
+            _ffi.check(_ffi.lib().mobody_mlp_pack(C.byref(mp), S, A, prec, _ffi.ptr(blob), _ffi.ptr(state), _ffi.stream_ptr(dev)))
         return blob
 
     # ------------------------------------------------------------------
@@ -140,9 +142,11 @@ class MOBODYEnsembleDynamics(object):
         self._param_cache[(kind, id(module))] = [[p.data_ptr() for p in params], struct, keep, params, 0]
         return struct, keep
 
-    def fill_step_desc(self, d, B, S, dev, *, policy=None, max_action=1.0, use_penalty=True, use_trg=True):
+    def fill_step_desc(self, d, B, S, dev, *, policy=None, max_action=1.0, use_penalty=True, use_trg=True, verify_images=True):
         """Fill the call-invariant half of a mobody_step_desc (shapes, parameter pointers, packed weight images,
-        penalty/termination/elite settings).  Returns the tensors/structs that must outlive the launch."""
+        penalty/termination/elite settings).  Returns the tensors/structs that must outlive the launch.
+        ``verify_images=False`` skips the device-side check / re-pack of the packed weight images: for calls that run
+        CONCURRENTLY on several streams (the check is stateful), after one verified call on the stream they forked from."""
         A = self.model.action_dim
         d.precision = _ffi.PREC[self.precision]
         d.B, d.S, d.A = B, S, A
@@ -152,12 +156,12 @@ class MOBODYEnsembleDynamics(object):
             mp, k = self._cached_params("pol", policy, _ffi.mlp_params); keep += k; keep.append(mp)
             d.policy = C.pointer(mp)
             if tensor_core:
-                d.policy_pack = _ffi.ptr(self._packed_policy(policy, mp, k))
+                d.policy_pack = _ffi.ptr(self._packed_policy(policy, mp, k, verify_images))
         d.max_action = float(max_action)
         dp, k = self._cached_params("dyn", self.model, _ffi.dyn_params); keep += k; keep.append(dp)
         d.dyn = C.pointer(dp)
         if tensor_core:
-            d.dyn_pack = _ffi.ptr(self._packed_dynamics(dp, k))
+            d.dyn_pack = _ffi.ptr(self._packed_dynamics(dp, k, verify_images))
         d.use_trg, d.use_penalty = int(bool(use_trg)), int(bool(use_penalty))
         d.penalty_coef = float(self._penalty_coef)
         d.term_kind = self.terminal_fn.kind
@@ -170,7 +174,7 @@ class MOBODYEnsembleDynamics(object):
         return keep
 
     def launch_step(self, obs, act, ws: StepWorkspace, *, policy=None, max_action=1.0, use_penalty=True,
-                    use_trg=True, eps=None, idx=None, n_rows_dev=None, row_ids=None, step=0, row0=0):
+                    use_trg=True, eps=None, idx=None, n_rows_dev=None, row_ids=None, step=0, row0=0, verify_images=True):
         """Enqueue the fused step on the current stream; no host synchronisation.
         obs [B,S] (B = capacity), act [B,A] or None with ``policy`` (an MLPNetwork-like module).  obs / act may be
         column views of wider rows (e.g. the state / action columns of packed replay-buffer rows): the row stride is
@@ -182,7 +186,8 @@ class MOBODYEnsembleDynamics(object):
             if t is not None and (t.dtype != torch.float32 or not t.is_cuda or (t.shape[0] > 1 and t.stride(1) != 1) or t.shape[1] < 1):
                 raise RuntimeError("mobody_b200: step inputs must be fp32 CUDA tensors with unit column stride")
         d = _ffi.StepDesc()
-        keep = self.fill_step_desc(d, B, S, dev, policy=policy, max_action=max_action, use_penalty=use_penalty, use_trg=use_trg)  # noqa: F841
+        keep = self.fill_step_desc(d, B, S, dev, policy=policy, max_action=max_action, use_penalty=use_penalty, use_trg=use_trg,  # noqa: F841
+                                   verify_images=verify_images)
         if policy is not None and ws.act is None:
             ws.act = torch.empty(B, A, dtype=torch.float32, device=dev)
         d.n_rows_dev, d.row_ids = _ffi.ptr(n_rows_dev), _ffi.ptr(row_ids)

@@ -269,13 +269,13 @@ class MOBODY(object):
         self.dynamics._draw += int(T)
         return base
 
-    def _rollout_desc(self, init_obss, T, use_trg, ws, packed, eps=None, idx=None, row0=0, step0=None):
+    def _rollout_desc(self, init_obss, T, use_trg, ws, packed, eps=None, idx=None, row0=0, step0=None, verify_images=True):
         """A filled mobody_rollout_desc for start states ``init_obss`` [B,S] (device, contiguous) on workspace ``ws``.
         ``packed``: destination of the pack stage (multi-GPU: this rank's slot of its receive buffer).  Returns (desc, keep-alive)."""
         B, S = init_obss.shape
         d = _ffi.RolloutDesc()
         keep = self.dynamics.fill_step_desc(d.step, B, S, self.device, policy=self.policy.network, max_action=self.policy.max_action,
-                                            use_trg=use_trg)
+                                            use_trg=use_trg, verify_images=verify_images)
         d.step.obs, d.step.mean, d.step.raw_reward = _ffi.ptr(init_obss), _ffi.ptr(ws["mean"]), _ffi.ptr(ws["raw"])
         d.step.step, d.step.row0 = self._take_draws(T, step0), int(row0)
         d.T, d.filter_bad_rollout = T, int(bool(self.config.get("filter_bad_rollout", 1)))
@@ -288,8 +288,24 @@ class MOBODY(object):
         d.packed = _ffi.ptr(packed)
         return d, (keep, init_obss, eps, idx, ws, packed)
 
+    def verify_images(self, use_trg=True):
+        """Bring the packed tensor-core weight images up to date on the CURRENT stream (device-side checksum, re-pack when the
+        parameters changed).  Call once before enqueueing several rollouts with ``verify_images=False`` on other streams."""
+        probe = _ffi.StepDesc()
+        return self.dynamics.fill_step_desc(probe, 1, self.config["state_dim"], self.device, policy=self.policy.network,
+                                            max_action=self.policy.max_action, use_trg=use_trg)
+
+    def rollout_streams(self):
+        """Two side streams for INDEPENDENT rollouts.  A rollout of B start states is ceil(B / 128) tiles on the device's SMs
+        (100 000 states on 148 SMs: 5.28 rounds, the sixth 72 % idle); enqueued on alternating streams -- each with its own
+        ``ws_slot``, after one verify_images() on the stream they fork from -- the tail round of one rollout runs beside the
+        first round of the next.  The refresh block uses them for its three independent dynamics calls."""
+        if getattr(self, "_roll_streams", None) is None:
+            self._roll_streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+        return self._roll_streams
+
     def rollout_device(self, init_obss, rollout_length, use_trg=True, *, eps=None, idx=None, row0=0, out_packed=None,
-                       sync=True, ws_slot=0, step0=None):
+                       sync=True, ws_slot=0, step0=None, verify_images=True):
         """T-step imagined rollout entirely on the device (mobody.py:596-657 without its per-step D2H copies and
         host masks): ONE C-ABI call (mobody_rollout) enqueues the T fused steps, the compactions between them, the
         concatenation + penalty filter and the packing of the kept transitions.
@@ -320,7 +336,7 @@ class MOBODY(object):
             idx = torch.as_tensor(np.asarray(idx) if not torch.is_tensor(idx) else idx).to(device=dev, dtype=torch.int64).contiguous()
         counts = ws["counts"]
         if B > 0:
-            d, keep = self._rollout_desc(init_obss, T, use_trg, ws, packed, eps, idx, row0, step0)   # noqa: F841
+            d, keep = self._rollout_desc(init_obss, T, use_trg, ws, packed, eps, idx, row0, step0, verify_images)   # noqa: F841
             _ffi.check(_ffi.lib().mobody_rollout(C.byref(d), _ffi.stream_ptr(dev)))
         else:
             counts.zero_(); ws["stats"][:2].zero_()
@@ -755,35 +771,58 @@ class MOBODY(object):
         lib, dev, fake = _ffi.lib(), self.device, self.fake_replay_buffer
         src_rows = src_buf.sample_rows(50000, inj.get("src_init"))                                    # :442 (sizes hard-coded there)
         tar_rows = tar_buf.sample_rows(2000, inj.get("tar_init"))                                     # :443
-        for tag, init, T in (("src", src_rows[:, :S].contiguous(), cfg["src_rollout_length"]),
-                             ("tar", tar_rows[:, :S].contiguous(), cfg["trg_rollout_length"])):
-            out, info = self.rollout_device(init, T, eps=inj.get(tag + "_eps"), idx=inj.get(tag + "_idx"))   # :444, 453
-            if cfg.get("filter_bad_rollout", 1) and out is not None:
-                print("filtered rollout", info["kept"], info["num_transitions"])                     # :653
-            if out is not None:                                                                       # add_batch, :445, 454
-                fake.add_rollout_slab(info["packed"], info["kept"])
+        # The three dynamics calls of the block are independent: they run on two side streams (the tail round of one
+        # overlaps the first round of the next, rollout_streams()); the inserts follow in the reference's order.
+        cur = torch.cuda.current_stream(dev)
+        self.verify_images()
+        fork = torch.cuda.Event(); fork.record(cur)
+        s0, s1 = self.rollout_streams()
+        runs = {}
+        for tag, st, rows_, T, slot in (("src", s0, src_rows, cfg["src_rollout_length"], 8), ("tar", s1, tar_rows, cfg["trg_rollout_length"], 9)):
+            with torch.cuda.stream(st):
+                st.wait_event(fork)
+                runs[tag] = self.rollout_device(rows_[:, :S].contiguous(), T, eps=inj.get(tag + "_eps"), idx=inj.get(tag + "_idx"),
+                                                sync=False, ws_slot=slot, verify_images=False)                # :444, 453
+        sa = None
         if cfg.get("use_src_sa_to_get_target_next_state", 1):                                         # :460-475
-            n = src_rows.shape[0]
-            ws = StepWorkspace(n, S, A, dev)
-            eps, idx = inj.get("sa_eps"), inj.get("sa_idx")
-            if eps is not None:
-                eps = _ffi.f32(eps, dev)
-            if idx is not None:
-                idx = torch.as_tensor(np.asarray(idx) if not torch.is_tensor(idx) else idx).to(device=dev, dtype=torch.int64).contiguous()
-            self.dynamics.launch_step(src_rows[:, :S], src_rows[:, S:S + A], ws, eps=eps, idx=idx, step=self.dynamics._draw)
-            self.dynamics._draw += 1
-            # keep rows with penalty < env_filter (strict `<` here, `<=` in rollout(): mobody.py:468 vs :649) -- stable device
-            # compaction, then one gather of the kept rows into buffer layout [s | a | s'_model | r_model | 1 - terminal]
-            pos = torch.empty(n, dtype=torch.int32, device=dev)
-            cnt = torch.zeros(1, dtype=torch.int32, device=dev)
-            scratch = torch.empty(int(lib.mobody_compact_scratch_ints(n)), dtype=torch.int32, device=dev)
-            _ffi.check(lib.mobody_compact(_ffi.KEEP_F32_LT, None, _ffi.ptr(ws.penalty), float(cfg["env_filter"]), n, None,
-                                          _ffi.ptr(scratch), _ffi.ptr(pos), _ffi.ptr(cnt), _ffi.stream_ptr(dev)))
-            rows = fake._pack(src_rows[:, :S], src_rows[:, S:S + A], ws.next_obs, ws.reward, ws.terminal.float(), True)
-            kept = torch.empty_like(rows)
-            _ffi.check(lib.mobody_gather_pos(_ffi.ptr(rows), fake.RW, fake.RW, _ffi.ptr(pos), _ffi.ptr(cnt), n, _ffi.ptr(kept), fake.RW,
-                                             _ffi.stream_ptr(dev)))
-            fake.add_packed(kept, int(cnt.item()))            # the host owns ptr / size (utils.py:68-92): one count read
+            with torch.cuda.stream(s1):
+                n = src_rows.shape[0]
+                ws = StepWorkspace(n, S, A, dev)
+                eps, idx = inj.get("sa_eps"), inj.get("sa_idx")
+                if eps is not None:
+                    eps = _ffi.f32(eps, dev)
+                if idx is not None:
+                    idx = torch.as_tensor(np.asarray(idx) if not torch.is_tensor(idx) else idx).to(device=dev, dtype=torch.int64).contiguous()
+                self.dynamics.launch_step(src_rows[:, :S], src_rows[:, S:S + A], ws, eps=eps, idx=idx, step=self.dynamics._draw,
+                                          verify_images=False)
+                self.dynamics._draw += 1
+                # keep rows with penalty < env_filter (strict `<` here, `<=` in rollout(): mobody.py:468 vs :649) -- stable device
+                # compaction, then one gather of the kept rows into buffer layout [s | a | s'_model | r_model | 1 - terminal]
+                pos = torch.empty(n, dtype=torch.int32, device=dev)
+                cnt = torch.zeros(1, dtype=torch.int32, device=dev)
+                scratch = torch.empty(int(lib.mobody_compact_scratch_ints(n)), dtype=torch.int32, device=dev)
+                _ffi.check(lib.mobody_compact(_ffi.KEEP_F32_LT, None, _ffi.ptr(ws.penalty), float(cfg["env_filter"]), n, None,
+                                              _ffi.ptr(scratch), _ffi.ptr(pos), _ffi.ptr(cnt), _ffi.stream_ptr(dev)))
+                rows = fake._pack(src_rows[:, :S], src_rows[:, S:S + A], ws.next_obs, ws.reward, ws.terminal.float(), True)
+                kept = torch.empty_like(rows)
+                _ffi.check(lib.mobody_gather_pos(_ffi.ptr(rows), fake.RW, fake.RW, _ffi.ptr(pos), _ffi.ptr(cnt), n, _ffi.ptr(kept), fake.RW,
+                                                 _ffi.stream_ptr(dev)))
+                sa = (kept, cnt, (ws, pos, scratch, rows, eps, idx))
+        cur.wait_stream(s0); cur.wait_stream(s1)
+        for tag in ("src", "tar"):
+            out, info = runs[tag]
+            if out is None:
+                continue
+            info["packed"].record_stream(cur)
+            T = int(cfg["src_rollout_length"] if tag == "src" else cfg["trg_rollout_length"])
+            host = torch.cat([info["counts_dev"].double(), info["stats_dev"]]).cpu()                  # one small read per rollout
+            kept_n, produced = int(host[T + 1]), int(host[T + 3])
+            if cfg.get("filter_bad_rollout", 1):
+                print("filtered rollout", kept_n, produced)                                           # :653
+            fake.add_rollout_slab(info["packed"], kept_n)                                             # add_batch, :445, 454
+        if sa is not None:
+            sa[0].record_stream(cur)
+            fake.add_packed(sa[0], int(sa[1].item()))         # the host owns ptr / size (utils.py:68-92): one count read
         if cfg.get("rollout_from_src", 0):                                                            # :477-510
             if self.penalty_type != "dara":
                 self.update_classifier(src_buf, tar_buf, batch_size)
