@@ -39,9 +39,11 @@ const char* mb_gemm_launch(const ug::Args& a, cudaStream_t st) {
   } else if (as == SRC_KCONTIG && bs == SRC_KCONTIG) {   // forward layers
     if (ec == EPI_STORE) return launch_np<0, 0, EPI_STORE>(a, max_m, narrow, st);
     if (ec == EPI_TANH) return launch_np<0, 0, EPI_TANH>(a, max_m, narrow, st);
+    if (ec == EPI_DSWISH) return launch_np<0, 0, EPI_DSWISH>(a, max_m, narrow, st);   // ensemble layers backward: W[e][in][out] is K-contiguous in `out`
   } else if (as == SRC_KCONTIG && bs == SRC_RCONTIG) {   // backward-data
     if (ec == EPI_MASK) return launch_np<0, 1, EPI_MASK>(a, max_m, narrow, st);
     if (ec == EPI_STORE) return launch_np<0, 1, EPI_STORE>(a, max_m, narrow, st);
+    if (ec == EPI_SWISH) return launch_np<0, 1, EPI_SWISH>(a, max_m, narrow, st);     // ensemble layers forward
   } else if (as == SRC_RCONTIG && bs == SRC_RCONTIG) {   // weight gradients (and the test hook)
     if (ec == EPI_PART) return launch_np<1, 1, EPI_PART>(a, max_m, narrow, st);
     if (ec == EPI_STORE) return launch_np<1, 1, EPI_STORE>(a, max_m, narrow, st);

@@ -34,7 +34,9 @@ enum { EPI_STORE = 0,   // C = act(acc + bias)                       -> C[m][n]
        EPI_MASK = 1,    // C = mask[m][n] > 0 ? acc : 0              -> C[m][n]          (ReLU backward)
        EPI_HEAD = 2,    // h = relu(acc + bias); out1[m] = h . w3 + b3; optional C = h     (Q network tail)
        EPI_TANH = 3,    // C = tanh(acc + bias) * scale              -> C[m][n]          (policy tail)
-       EPI_PART = 4 };  // C[split][m][n] = acc, db[split][m] = row sums of the A operand (weight gradient partials)
+       EPI_PART = 4,    // C[split][m][n] = acc, db[split][m] = row sums of the A operand (weight gradient partials)
+       EPI_SWISH = 5,   // x = acc + bias -> pre[m][n] (kept for the backward pass); C = x * sigmoid(x)   (ensemble layers, dynfit.cu)
+       EPI_DSWISH = 6 };// C = acc * swish'(mask[m][n]), mask = the layer's stored pre-activation         (Swish backward)
 __host__ __device__ constexpr int epi_class(int epi) { return epi == EPI_HEAD ? EPI_STORE : epi; }
 
 struct Job {
@@ -45,12 +47,15 @@ struct Job {
   const float* bias; const float* mask; int ldmask;
   const float* w3; const float* b3;
   float* C; int ldc; float* out1; float* db; float scale;
+  float* pre;                                                           // EPI_SWISH: pre-activation copy, same pitch as C (may be null)
 };
 struct Args { Job job[8]; int njobs, nsplit; };
 
 __host__ __device__ inline int rup16(int x) { return (x + 15) & ~15; }
 __host__ __device__ inline size_t stage_bytes(int np) { return (size_t)2 * (BM + np) * (KC / 4) * 16; }   // hi + lo planes of A and B
 
+__device__ __forceinline__ float swish_f(float x) { return x / (1.f + expf(-x)); }
+__device__ __forceinline__ float dswish_f(float x) { const float s = 1.f / (1.f + expf(-x)); return s * (1.f + x * (1.f - s)); }
 __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) {
   hi = __float_as_uint(v) & 0xFFFFE000u;                               // exactly a TF32 value
   lo = __float_as_uint(v - __uint_as_float(hi)) + 0x1000u;             // the MMA truncates: pre-round the residual
@@ -171,7 +176,7 @@ __global__ void __launch_bounds__(NT, 2) gemm_kernel(const __grid_constant__ Arg
     tc::mbar_init(&bar_free[0], 1); tc::mbar_init(&bar_free[1], 1); tc::mbar_init(&bar_done, 1);
     tc::mbar_init(&bar_fullb[0], 1); tc::mbar_init(&bar_fullb[1], 1); tc::mbar_fence_init();
   }
-  if (EPI == EPI_STORE || EPI == EPI_TANH) {
+  if (EPI == EPI_STORE || EPI == EPI_TANH || EPI == EPI_SWISH) {
     bias_s[tid] = (jb.bias && tid < jb.N) ? __ldg(jb.bias + tid) : 0.f;
     w3_s[tid] = (EPI == EPI_STORE && jb.w3 && tid < jb.N) ? __ldg(jb.w3 + tid) : 0.f;
   }
@@ -255,8 +260,11 @@ __global__ void __launch_bounds__(NT, 2) gemm_kernel(const __grid_constant__ Arg
   const int ldc = EPI == EPI_PART ? jb.N : jb.ldc;
   float* cbase = jb.C ? jb.C + (EPI == EPI_PART ? (size_t)blockIdx.z * jb.M * jb.N : 0) + (size_t)(m0 + q * 32 + rl) * ldc : nullptr;
   // fast path: whole 4-column groups, 16-byte aligned rows (every 256-wide tensor of the update)
+  constexpr bool MASKED = EPI == EPI_MASK || EPI == EPI_DSWISH;
   const bool fast = (jb.N & 3) == 0 && (!jb.C || ((ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(jb.C) & 15) == 0)) &&
-                    (EPI != EPI_MASK || ((jb.ldmask & 3) == 0 && (reinterpret_cast<uintptr_t>(jb.mask) & 15) == 0));
+                    (!MASKED || ((jb.ldmask & 3) == 0 && (reinterpret_cast<uintptr_t>(jb.mask) & 15) == 0)) &&
+                    (EPI != EPI_SWISH || !jb.pre || (reinterpret_cast<uintptr_t>(jb.pre) & 15) == 0);
+  float* pbase = (EPI == EPI_SWISH && jb.pre) ? jb.pre + (size_t)(m0 + q * 32 + rl) * ldc : nullptr;
   float head[8];
 #pragma unroll
   for (int it = 0; it < 8; ++it) head[it] = 0.f;
@@ -265,7 +273,7 @@ __global__ void __launch_bounds__(NT, 2) gemm_kernel(const __grid_constant__ Arg
     if (n0 >= jb.N) break;
     const bool colok = n + 4 <= jb.N;
     float4 mkv[8];                                                      // ReLU-mask block: all 8 loads in flight before anything waits
-    if (EPI == EPI_MASK && fast) {
+    if (MASKED && fast) {
       const float* mrow = jb.mask + (size_t)(m0 + q * 32 + rl) * jb.ldmask + n;
 #pragma unroll
       for (int it = 0; it < 8; ++it)
@@ -283,13 +291,19 @@ __global__ void __launch_bounds__(NT, 2) gemm_kernel(const __grid_constant__ Arg
     __syncwarp();
     if (fast) {
       float4 bq = make_float4(0.f, 0.f, 0.f, 0.f), wq = bq;
-      if (EPI == EPI_STORE || EPI == EPI_TANH) { bq = *reinterpret_cast<const float4*>(bias_s + n); wq = *reinterpret_cast<const float4*>(w3_s + n); }
+      if (EPI == EPI_STORE || EPI == EPI_TANH || EPI == EPI_SWISH) { bq = *reinterpret_cast<const float4*>(bias_s + n); wq = *reinterpret_cast<const float4*>(w3_s + n); }
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const int rr = it * 4 + rl;
         float4 v = *reinterpret_cast<const float4*>(tb + rr * 36 + cl);
         if (EPI == EPI_MASK) {
           v.x = mkv[it].x > 0.f ? v.x : 0.f; v.y = mkv[it].y > 0.f ? v.y : 0.f; v.z = mkv[it].z > 0.f ? v.z : 0.f; v.w = mkv[it].w > 0.f ? v.w : 0.f;
+        } else if (EPI == EPI_DSWISH) {
+          v.x *= dswish_f(mkv[it].x); v.y *= dswish_f(mkv[it].y); v.z *= dswish_f(mkv[it].z); v.w *= dswish_f(mkv[it].w);
+        } else if (EPI == EPI_SWISH) {
+          v.x += bq.x; v.y += bq.y; v.z += bq.z; v.w += bq.w;
+          if (pbase && colok && q * 32 + rr < rows) *reinterpret_cast<float4*>(pbase + (size_t)it * 4 * ldc + n) = v;
+          v.x = swish_f(v.x); v.y = swish_f(v.y); v.z = swish_f(v.z); v.w = swish_f(v.w);
         } else if (EPI != EPI_PART) {
           v.x += bq.x; v.y += bq.y; v.z += bq.z; v.w += bq.w;
           if (EPI == EPI_TANH) { v.x = tanhf(v.x) * jb.scale; v.y = tanhf(v.y) * jb.scale; v.z = tanhf(v.z) * jb.scale; v.w = tanhf(v.w) * jb.scale; }
@@ -305,7 +319,12 @@ __global__ void __launch_bounds__(NT, 2) gemm_kernel(const __grid_constant__ Arg
         if (nn >= jb.N || r >= rows) continue;
         float t = tb[rr * 36 + c];
         if (EPI == EPI_MASK) t = __ldg(jb.mask + (size_t)(m0 + r) * jb.ldmask + nn) > 0.f ? t : 0.f;
-        else if (EPI != EPI_PART) {
+        else if (EPI == EPI_DSWISH) t *= dswish_f(__ldg(jb.mask + (size_t)(m0 + r) * jb.ldmask + nn));
+        else if (EPI == EPI_SWISH) {
+          t += bias_s[nn];
+          if (jb.pre) jb.pre[(size_t)(m0 + r) * ldc + nn] = t;
+          t = swish_f(t);
+        } else if (EPI != EPI_PART) {
           t += bias_s[nn];
           if (EPI == EPI_TANH) t = tanhf(t) * jb.scale;
           else if (jb.relu) t = fmaxf(t, 0.f);
