@@ -318,6 +318,43 @@ def gpu_train_rate(mb, dev, batch, steps=300, s_dim=None, a_dim=None, penalty_ty
     return steps / (e0.elapsed_time(e1) * 1e-3), steps / wall
 
 
+def fit_batch_data(B, seed=5):
+    rng = np.random.default_rng(seed)
+    s = (0.3 * rng.standard_normal((7, B, S))).astype(np.float32)
+    return [s, rng.uniform(-1, 1, (7, B, A)).astype(np.float32), (s + 0.1 * rng.standard_normal((7, B, S))).astype(np.float32),
+            rng.standard_normal((7, B, 1)).astype(np.float32)]
+
+
+def gpu_fit_rate(mb, dev, dyn, B=256, n_batches=40, epochs=5):
+    """Dynamics fitting (MOBODYEnsembleDynamics.learn, 7 x B rows per mini-batch): optimiser steps/s through learn() on
+    device-resident epoch tensors (one scalar read-back per learn() call)."""
+    data = [torch.from_numpy(np.concatenate([x] * n_batches, 1)).to(dev) for x in fit_batch_data(B)]
+    dyn.learn(True, *data, B, 0.01)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter(); e0.record()
+    for _ in range(epochs):
+        dyn.learn(True, *data, B, 0.01)
+    e1.record(); torch.cuda.synchronize()
+    return epochs * n_batches / (e0.elapsed_time(e1) * 1e-3), epochs * n_batches / (time.perf_counter() - t0)
+
+
+def cpu_fit_rate(threads, B=256, steps=3):
+    """Oracle fitting step (autograd restatement of learn(), proven equal to the reference) on host cores."""
+    from oracle import mobody_oracle as M
+    torch.set_num_threads(threads)
+    p = M.make_dynamics_params(S, A, 1)
+    names = [n + sfx for n in M.fit_trained_layers(True) for sfx in (".weight", ".bias")]
+    m = {k: torch.zeros_like(p[k]) for k in names}; v = {k: torch.zeros_like(p[k]) for k in names}
+    data = [torch.from_numpy(x) for x in fit_batch_data(B)]
+    t0 = None
+    for it in range(steps + 1):
+        if it == 1:
+            t0 = time.perf_counter()
+        M.fit_step(p, m, v, {n: it + 1 for n in M.fit_trained_layers(True)}, *data, torch.randn(6, 7, B, 16), torch.randn(7, B, S), True)
+    return steps / (time.perf_counter() - t0)
+
+
 def hbm_stage_rates(mb, dev, hbm_peak, n=2_000_000):
     """Achieved HBM GB/s of the byte-moving stages of the path at a size well beyond L2 (2 M rows x 176 B): replay-buffer
     sampling (Philox draw + random row gather), ring insert, and the row packing of convert_D4RL / add_batch."""
@@ -707,9 +744,16 @@ def main():
                                               "workload": "same with penalty_type='par' (the CLI default): + one fused 128-row dynamics step and the reward shift per update, no host sync"},
                          "batch4096_S27A8": {"value": big_wall, "device_only": big_dev, "unit": "updates/s",
                                              "workload": "MOBODY.train steady state, batch 4096 (4096 src + 4096 tar + 2048 fake rows), S27/A8 (BASELINE configs[3])"}}
+    if upd_wall is not None:
+        fit_dev, fit_wall = gpu_fit_rate(mb, dev, dyn)
+        line["train"]["dynamics_fit"] = {"metric": "dynamics fitting steps/sec", "value": fit_wall, "device_only": fit_dev, "unit": "steps/s",
+                                         "workload": f"MOBODYEnsembleDynamics.learn, 7 members x 256 rows per mini-batch, S{S}/A{A} "
+                                                     "(3 losses + backward + Adam = one C-ABI call, 43 launches)"}
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         if upd_wall is not None:
+            line["train"]["dynamics_fit"]["cpu_baseline"] = {"value": cpu_fit_rate(cores), "unit": "steps/s", "cores": cores, "kind": "port",
+                                                             "sample": "oracle.fit_step (autograd + Adam), 3 steps after 1 warm-up"}
             line["train"]["cpu_baseline"] = {"value": cpu_train_rate(128, cores), "unit": "updates/s", "cores": cores, "kind": "port",
                                              "sample": "oracle.train_step incl. 3 buffer gathers, 5 steps after 2 warm-up"}
         n = min(Bn, 100_000)                   # the whole workload (~1.3 s per pass on 16 cores), best of 3 after a warm-up

@@ -275,6 +275,41 @@ int mobody_classifier_step(const mobody_classifier_desc* d, void* stream);
 int mobody_dara_relabel(float* rows, long long n, int S, int A, int row_width, const mobody_mlp_params* sas,
                         const mobody_mlp_params* sa, float penalty_coef, float* penalty_out, void* stream);
 
+/* ---- dynamics fitting step ----
+ * One mini-batch of MOBODYEnsembleDynamics.learn (algo/dynamics/mobody_dynamics.py:594-653): encoder_loss (:300-329,
+ * incl. get_kl_loss :330-333), transition_loss (:336-347), reward_loss (:349-386), loss.backward() and the
+ * torch.optim.Adam step (train_mobody.py:801-804: lr = dynamics_lr, default betas / eps, no weight decay), for the default
+ * configuration (no_vae = 0, latent_reward = 0, inverse_sep_reward_loss = 0, mopo = 0).  Batches are per ensemble member
+ * (the reference indexes a bootstrapped [7, B, .] view, :607-610).  Trained layers: zs1-3, transition1-3, reward_model1-3
+ * and za_trg1-2 (use_trg) or za_src1-2; every other parameter of MOBODYModule receives no gradient in the reference and is
+ * left untouched (its Adam state is never created there).  Parameters and moments are updated IN PLACE.
+ * eps_latent: the six torch.randn_like draws of MOBODYModule.reparameterize in the reference's call order
+ *   [0] encoder_decoder(s) [1] encoder_decoder(s') [2] encode_state(s) [3] encode_state(s') under no_grad
+ *   [4] forward_*(s, a) of transition_loss [5] forward_*(s, a) of reward_loss;  eps_next: randn_like(mean) of reward_loss (:354).
+ * Both NULL -> Philox draws keyed on (seed, draw).
+ * scalars_out (device float[8]): [0] loss [1] transition_loss [2] encoder_loss [3] recon_loss [4] kl_loss [5] reward_loss. */
+typedef struct mobody_dyn_state { float* w[MOBODY_N_DYN_LAYERS]; float* b[MOBODY_N_DYN_LAYERS]; } mobody_dyn_state;   /* writable twin of mobody_dyn_params */
+typedef struct mobody_dynfit_desc {
+  int S, A, B;                    /* B = rows per ensemble member                                                  */
+  int use_trg;                    /* 1: target-domain batch (za_trg*, encoder weight 5x, reward weight 1); 0: source (za_src*, 1x, 0.01) */
+  const float* obs; const float* act; const float* next_obs; const float* reward;   /* device fp32 [7,B,S] [7,B,A] [7,B,S] [7,B,1] */
+  long long member_stride;        /* rows between consecutive members in the four batch tensors (0 = B: contiguous); lets a batch be a
+                                     row window [:, lo:lo+B] of epoch tensors [7,N,.] without a copy (:607-610)     */
+  const float* eps_latent;        /* [6,7,B,16] or NULL                                                            */
+  const float* eps_next;          /* [7,B,S] or NULL                                                               */
+  unsigned long long seed; unsigned int draw;
+  float encoder_coef;             /* weight of encoder_loss in the total: (use_trg ? 5 : 1) * config['encoder_loss_coef'] (:623-626) */
+  float reward_coef;              /* use_trg ? 1 : 0.01 (:381-384)                                                 */
+  mobody_dyn_state params, adam_m, adam_v;
+  int t_shared, t_action;         /* Adam step counts AFTER this step (1-based): shared layers / this domain's action encoder */
+  float lr;
+  int nsplit;                     /* K splits of the weight-gradient GEMMs, 1..16                                  */
+  void* workspace; long long workspace_bytes;   /* >= mobody_dynfit_workspace_bytes(B, S, A, nsplit), 16-byte aligned */
+  float* scalars_out;
+} mobody_dynfit_desc;
+long long mobody_dynfit_workspace_bytes(int B, int S, int A, int nsplit);
+int mobody_dynfit_step(const mobody_dynfit_desc* d, void* stream);
+
 /* ---- tensor-core weight images (precision MOBODY_PREC_BF16X2 / MOBODY_PREC_FP16) ----
  * The reference keeps weights as fp32 nn.Parameters (mobody_module.py:371-391, mobody.py:35-48); the
  * tcgen05 path consumes them as 16-bit planes in the UMMA shared-memory layout (one launch per image).

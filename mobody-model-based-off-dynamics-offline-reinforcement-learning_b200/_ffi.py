@@ -95,6 +95,22 @@ class ClassifierDesc(C.Structure):
     ]
 
 
+class DynState(C.Structure):
+    _fields_ = [("w", C.c_void_p * N_DYN_LAYERS), ("b", C.c_void_p * N_DYN_LAYERS)]
+
+
+class DynFitDesc(C.Structure):
+    _fields_ = [
+        ("S", C.c_int), ("A", C.c_int), ("B", C.c_int), ("use_trg", C.c_int),
+        ("obs", C.c_void_p), ("act", C.c_void_p), ("next_obs", C.c_void_p), ("reward", C.c_void_p), ("member_stride", C.c_longlong),
+        ("eps_latent", C.c_void_p), ("eps_next", C.c_void_p), ("seed", C.c_ulonglong), ("draw", C.c_uint),
+        ("encoder_coef", C.c_float), ("reward_coef", C.c_float),
+        ("params", DynState), ("adam_m", DynState), ("adam_v", DynState),
+        ("t_shared", C.c_int), ("t_action", C.c_int), ("lr", C.c_float), ("nsplit", C.c_int),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong), ("scalars_out", C.c_void_p),
+    ]
+
+
 _lib = None
 
 
@@ -154,6 +170,9 @@ def lib():
         L.mobody_classifier_step.argtypes = [C.POINTER(ClassifierDesc), C.c_void_p]
         L.mobody_dara_relabel.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.POINTER(MlpParams),
                                           C.POINTER(MlpParams), C.c_float, C.c_void_p, C.c_void_p]
+        L.mobody_dynfit_workspace_bytes.restype = C.c_longlong
+        L.mobody_dynfit_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int]
+        L.mobody_dynfit_step.argtypes = [C.POINTER(DynFitDesc), C.c_void_p]
         L.mobody_selftest_gemm.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.mobody_selftest_umma.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         if L.mobody_abi_version() != ABI_VERSION:

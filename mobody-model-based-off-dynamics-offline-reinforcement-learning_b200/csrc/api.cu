@@ -60,6 +60,9 @@ const char* mb_classifier_step_launch(const mobody_classifier_desc& d, cudaStrea
 const char* mb_dara_relabel_launch(float* rows, long long n, int S, int A, int rw, const MlpPtrs& sas, const MlpPtrs& sa,
                                    float coef, float* pen_out, cudaStream_t st);
 
+long long mb_dynfit_workspace_bytes(int B, int S, int A, int nsplit);
+const char* mb_dynfit_step_launch(const mobody_dynfit_desc& d, cudaStream_t st);
+
 static thread_local char g_err[512] = "";
 
 static int fail(int code, const char* msg) {
@@ -335,6 +338,25 @@ int mobody_train_step(const mobody_train_desc* d, void* stream) {
   const char* err = mb_train_step_launch(*d, (cudaStream_t)stream);
   if (err) return fail(MOBODY_ERR_UNSUPPORTED, err);
   return check_launch("mobody_train_step");
+}
+
+long long mobody_dynfit_workspace_bytes(int B, int S, int A, int nsplit) {
+  if (B < 1 || S < 1 || A < 1 || nsplit < 1) return 0;
+  return mb_dynfit_workspace_bytes(B, S, A, nsplit);
+}
+
+int mobody_dynfit_step(const mobody_dynfit_desc* d, void* stream) {
+  if (!d || !d->obs || !d->act || !d->next_obs || !d->reward) return fail(MOBODY_ERR_ARG, "mobody_dynfit_step: null descriptor / batch pointer");
+  if (d->B < 1 || d->S < 1 || d->A < 1) return fail(MOBODY_ERR_ARG, "mobody_dynfit_step: B >= 1, S >= 1, A >= 1");
+  if ((d->eps_latent == nullptr) != (d->eps_next == nullptr)) return fail(MOBODY_ERR_ARG, "mobody_dynfit_step: inject both noise tensors or neither");
+  for (int i = 0; i < MOBODY_N_DYN_LAYERS; ++i)
+    if (!d->params.w[i] || !d->params.b[i] || !d->adam_m.w[i] || !d->adam_m.b[i] || !d->adam_v.w[i] || !d->adam_v.b[i])
+      return fail(MOBODY_ERR_ARG, "mobody_dynfit_step: null parameter / moment pointer");
+  if (d->t_shared < 1 || d->t_action < 1) return fail(MOBODY_ERR_ARG, "mobody_dynfit_step: optimiser step counts are 1-based");
+  if (!d->workspace || !d->scalars_out) return fail(MOBODY_ERR_ARG, "mobody_dynfit_step: null workspace / scalars_out");
+  const char* err = mb_dynfit_step_launch(*d, (cudaStream_t)stream);
+  if (err) return fail(MOBODY_ERR_UNSUPPORTED, err);
+  return check_launch("mobody_dynfit_step");
 }
 
 long long mobody_classifier_workspace_bytes(int N, int S, int A, int nsplit) {

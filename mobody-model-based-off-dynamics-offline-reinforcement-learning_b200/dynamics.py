@@ -1,8 +1,8 @@
 """MOBODYEnsembleDynamics.step as one fused CUDA launch.
 
 Mirror of algo/dynamics/mobody_dynamics.py:83-265 (identity StandardScaler + ``step``).  The model
-fitting half of that class (``train``/``learn``/``validate``, :300-1270) is out of scope
-(SURVEY.md §2 #3): this class drops in for the *rollout* use of the dynamics object.
+fitting half of that class (``learn`` / ``validate`` / ``select_elites`` / ``train``, :300-1156) lives in
+dynamics_fit.py (one C-ABI call per mini-batch).
 """
 import ctypes as C
 from typing import Callable, Dict, Optional, Tuple
@@ -11,6 +11,7 @@ import numpy as np
 import torch
 
 from . import _ffi
+from .dynamics_fit import DynamicsFitting
 from .terminal_funs import TerminationFn
 
 
@@ -59,7 +60,7 @@ class StepWorkspace:
         self.act = torch.empty(B, A, **f) if want_act else None
 
 
-class MOBODYEnsembleDynamics(object):
+class MOBODYEnsembleDynamics(DynamicsFitting):
     def __init__(self, config, model, optim=None, scaler=None,
                  terminal_fn: Optional[Callable] = None, penalty_coef: float = 0.0,
                  uncertainty_mode: str = "pairwise-diff", precision: Optional[str] = None, seed: int = 0) -> None:

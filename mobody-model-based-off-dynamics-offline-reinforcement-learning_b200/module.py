@@ -4,9 +4,9 @@ Same class / parameter names and shapes as the reference
 (algo/dynamics/mobody_module.py:51-214, 371-416) so ``dynamics.pth`` state_dicts load unchanged
 and ``train_mobody.py:791-799`` can construct it.  The nn.Module only *owns* the parameters;
 the inference hot path (MOBODYEnsembleDynamics.step) hands their device pointers to the fused
-CUDA kernels.  ``forward_trg`` / ``forward_src`` / ``encode_reward`` stay differentiable torch
-code because the reference's model-fitting loop (out of scope) back-propagates
-through them; they are not on the rollout path.
+CUDA kernels; the fitting step (dynamics_fit.py) updates them in place.  ``forward_trg`` /
+``forward_src`` / ``encode_reward`` stay as plain torch code for callers that want autograd
+through the model and for the once-per-epoch ``validate``; they are not on the rollout path.
 """
 from typing import List, Optional, Tuple, Union
 

@@ -422,6 +422,75 @@ def gen_refresh(env="hopper", S=11, A=3, B=32, seed=51, n_src=3000, n_tar=500, T
     return out
 
 
+FIT_SAMPLE = 1536      # elements kept per tensor in the dynamics-fitting fixtures (evenly strided)
+
+
+def fit_sample_index(n):
+    return np.unique(np.linspace(0, n - 1, min(n, FIT_SAMPLE)).astype(np.int64))
+
+
+def gen_dynfit(S, A, B, seed, calls=(True, True, False)):
+    """MOBODYEnsembleDynamics.learn (mobody_dynamics.py:594-653) of the UNMODIFIED reference, one mini-batch per call, on
+    one model + torch.optim.Adam (train_mobody.py:801-804) across the calls; `calls` = use_trg_data per call.  The
+    torch.randn_like draws (six reparameterize calls + reward_loss's randn_like(mean), in that order) are scripted and
+    recorded; `.to('cuda')` is a no-op (CPU run).  Kept: the returned loss scalars per call, and evenly strided samples of
+    every trained tensor's value / exp_avg / exp_avg_sq after the last call (+ exp_avg after the first: 0.1 * gradient)."""
+    dyn, p0 = build_reference_dynamics(S, A, seed, "hopper" if S == 11 else "walker2d", 1.0)
+    dyn.config.update(no_vae=0, inverse_sep_reward_loss=0, latent_reward=0, train_together=0)
+    dyn.encoder_loss_coef = 1
+    dyn.optim = torch.optim.Adam(dyn.model.parameters(), lr=1e-3)
+    dyn.total_steps = 0
+    rng = np.random.default_rng(seed)
+    out = dict(S=S, A=A, B=B, seed=seed, calls=np.asarray(calls, dtype=np.int64))
+    real_to, real_randn_like = torch.Tensor.to, torch.randn_like
+    names = [n for n in O.dynamics_layer_shapes(S, A)]
+    for c, use_trg in enumerate(calls):
+        s = (HEALTHY["hopper" if S == 11 else "walker2d"](S)[None, None, :] + 0.3 * rng.standard_normal((7, B, S))).astype(np.float32)
+        a = rng.uniform(-1, 1, (7, B, A)).astype(np.float32)
+        ns = (s + 0.1 * rng.standard_normal((7, B, S))).astype(np.float32)
+        r = rng.standard_normal((7, B, 1)).astype(np.float32)
+        eps_l = rng.standard_normal((6, 7, B, 16)).astype(np.float32)
+        eps_n = rng.standard_normal((7, B, S)).astype(np.float32)
+        draws = [torch.from_numpy(eps_l[k]) for k in range(6)] + [torch.from_numpy(eps_n)]
+        count = [0]
+
+        def randn_like(x, **kw):
+            d = draws[count[0]]; count[0] += 1
+            assert tuple(d.shape) == tuple(x.shape), (count[0], d.shape, x.shape)
+            return d.clone()
+
+        def to(self, *args, **kw):
+            if args and isinstance(args[0], str) and args[0].startswith("cuda"):
+                return self
+            return real_to(self, *args, **kw)
+        torch.randn_like, torch.Tensor.to = randn_like, to
+        try:
+            res = dyn.learn(bool(use_trg), *(torch.from_numpy(x) for x in (s, a, ns, r)), B, 0.01)
+        finally:
+            torch.randn_like, torch.Tensor.to = real_randn_like, real_to
+        assert count[0] == 7, count
+        out.update({f"c{c}_obs": s, f"c{c}_act": a, f"c{c}_next_obs": ns, f"c{c}_reward": r, f"c{c}_eps_latent": eps_l,
+                    f"c{c}_eps_next": eps_n, f"c{c}_losses": np.asarray(res, dtype=np.float64)})   # loss, transition, encoder, recon, kl
+        if c == 0:
+            for n in names:
+                for sfx in ("weight", "bias"):
+                    st = dyn.optim.state.get(getattr(getattr(dyn.model, n), sfx))
+                    if st:
+                        out[f"first_m_{n}.{sfx}"] = st["exp_avg"].numpy().ravel()[fit_sample_index(st["exp_avg"].numel())].copy()
+    for n in names:
+        for sfx in ("weight", "bias"):
+            t = getattr(getattr(dyn.model, n), sfx)
+            idx = fit_sample_index(t.numel())
+            out[f"p_{n}.{sfx}"] = t.detach().numpy().ravel()[idx].copy()
+            st = dyn.optim.state.get(t)
+            out[f"has_state_{n}.{sfx}"] = np.int64(bool(st))
+            if st:
+                out[f"m_{n}.{sfx}"] = st["exp_avg"].numpy().ravel()[idx].copy()
+                out[f"v_{n}.{sfx}"] = st["exp_avg_sq"].numpy().ravel()[idx].copy()
+                out[f"t_{n}.{sfx}"] = np.int64(int(st["step"]))
+    return out
+
+
 def gen_checkpoint_keys():
     """Key -> shape of every checkpoint file the reference writes for this path: dynamics.pth
     (MOBODYModule.state_dict, mobody_dynamics.py:1158-1160), <name>_actor / <name>_critic (mobody.py:584-588) and the
@@ -459,6 +528,8 @@ def main():
     np.savez_compressed(os.path.join(OUT, "train_S11A3_B16.npz"), **gen_train(11, 3, 16, 32, n_steps=2))
     np.savez_compressed(os.path.join(OUT, "classifier_S17A6_B32.npz"), **gen_classifier(17, 6, 32, 41))
     np.savez_compressed(os.path.join(OUT, "refresh_hopper.npz"), **gen_refresh())
+    np.savez_compressed(os.path.join(OUT, "dynfit_S11A3_B24.npz"), **gen_dynfit(11, 3, 24, 51))
+    np.savez_compressed(os.path.join(OUT, "dynfit_S17A6_B40.npz"), **gen_dynfit(17, 6, 40, 52, calls=(True,)))
     import json
     with open(os.path.join(OUT, "checkpoint_keys.json"), "w") as f:
         json.dump(gen_checkpoint_keys(), f, indent=0, sort_keys=True)

@@ -446,3 +446,76 @@ def dara_reward_penalty(p, s, a, s2):
     sa_lp = torch.log(torch.softmax(sa_logits, -1) + 1e-10)
     pen = sas_lp[:, 1:] - sa_lp[:, 1:] - sas_lp[:, :1] + sa_lp[:, :1]
     return pen.clamp(-10, 10)
+
+
+# --------------------------------------------------------------------------
+# dynamics fitting step
+# --------------------------------------------------------------------------
+FIT_LAYERS_SHARED = ("zs1", "zs2", "zs3", "transition1", "transition2", "transition3",
+                     "reward_model1", "reward_model2", "reward_model3")
+
+
+def fit_trained_layers(use_trg):
+    """Layers that receive a gradient in MOBODYEnsembleDynamics.learn (mobody_dynamics.py:594-653): the other domain's
+    action encoder and the action decoders are never touched, so torch.optim.Adam never creates state for them."""
+    return FIT_LAYERS_SHARED + (("za_trg1", "za_trg2") if use_trg else ("za_src1", "za_src2"))
+
+
+def _reparam(mu, logvar, eps):
+    """mobody_module.py:237-243 in training mode, with the randn_like draw injected."""
+    return mu + eps * torch.exp(0.5 * logvar)
+
+
+def _kl(mu, logvar):
+    """get_kl_loss, mobody_dynamics.py:330-333."""
+    return 0.05 * (-0.5 * (1 + logvar - mu.pow(2) - logvar.exp()).mean(dim=(1, 2))).sum()
+
+
+def fit_losses(p, s, a, ns, r, eps_latent, eps_next, use_trg, encoder_loss_coef=1.0):
+    """The loss of one learn() mini-batch for the default configuration (no_vae = 0, latent_reward = 0,
+    inverse_sep_reward_loss = 0): encoder_loss (:300-329) + transition_loss (:336-347) + reward_loss (:349-386),
+    combined as in :616-641.  s, ns [E,B,S]; a [E,B,A]; r [E,B,1]; eps_latent [6,E,B,16] = the reparameterize draws in
+    call order; eps_next [E,B,S] = randn_like(mean) of reward_loss.  Returns (loss, transition, encoder, recon, kl, reward)."""
+    def enc(x, k):
+        mu, lv = encode_state(p, x)
+        return _reparam(mu, lv, eps_latent[k]), mu, lv
+    # encoder_loss
+    z1, mu_s, lv_s = enc(s, 0)
+    rec_s = encode_transition(p, z1)                                        # encoder_decoder(state)
+    z2, mu_n, lv_n = enc(ns, 1)
+    rec_n = encode_transition(p, z2)                                        # encoder_decoder(next_state)
+    recon = ((rec_s - s) ** 2).mean(dim=(1, 2)).sum() + ((rec_n - ns) ** 2).mean(dim=(1, 2)).sum()
+    kl = _kl(mu_s, lv_s) + _kl(mu_n, lv_n)
+    z3, _, _ = enc(s, 2)
+    zl = z3 + encode_action(p, z3, a, use_trg)
+    with torch.no_grad():
+        z4, _, _ = enc(ns, 3)
+    encoder = 100 * recon + kl + ((zl - z4) ** 2).mean(dim=(1, 2)).sum()
+    # transition_loss
+    z5, _, _ = enc(s, 4)
+    mean5 = encode_transition(p, z5 + encode_action(p, z5, a, use_trg))
+    transition = ((mean5 - ns) ** 2).mean(dim=(1, 2)).sum()
+    # reward_loss
+    z6, _, _ = enc(s, 5)
+    mean6 = encode_transition(p, z6 + encode_action(p, z6, a, use_trg))
+    fake = mean6 + eps_next * torch.std(mean6, dim=0, keepdim=True)
+    r1, _ = encode_reward(p, s, a, fake)
+    r2, _ = encode_reward(p, s, a, ns)
+    reward = ((r1 - r) ** 2).mean(dim=(1, 2)).sum() + ((r2 - r) ** 2).mean(dim=(1, 2)).sum()
+    if not use_trg:
+        reward = 0.01 * reward
+    loss = transition + (5 if use_trg else 1) * encoder_loss_coef * encoder + reward
+    return loss, transition, encoder, recon, kl, reward
+
+
+def fit_step(p, m, v, t, s, a, ns, r, eps_latent, eps_next, use_trg, lr=1e-3, encoder_loss_coef=1.0):
+    """One optimiser step of learn() (:643-647): autograd of fit_losses + torch.optim.Adam on the layers that received a
+    gradient.  p, m, v: dicts of tensors updated in place; t: dict layer name -> step count after this step."""
+    names = [n + sfx for n in fit_trained_layers(use_trg) for sfx in (".weight", ".bias")]
+    leaves = {k: p[k].clone().requires_grad_(True) for k in names}
+    q = dict(p); q.update(leaves)
+    out = fit_losses(q, s, a, ns, r, eps_latent, eps_next, use_trg, encoder_loss_coef)
+    grads = torch.autograd.grad(out[0], [leaves[k] for k in names])
+    for k, g in zip(names, grads):
+        adam_update({k: p[k]}, {k: g}, m, v, t[k.split(".")[0]], lr)
+    return [float(x.detach()) for x in out], dict(zip(names, grads))

@@ -55,6 +55,8 @@ def test_argument_errors_are_reported_not_raised_across_abi(libpath):
     rd.T = 2
     assert L.mobody_rollout(ctypes.byref(rd), None) == -1 and b"policy" in L.mobody_last_error()
     assert L.mobody_classifier_step(None, None) == -1
+    assert L.mobody_dynfit_step(None, None) == -1 and b"null descriptor" in L.mobody_last_error()
+    assert L.mobody_dynfit_workspace_bytes(256, 17, 6, 4) > L.mobody_dynfit_workspace_bytes(128, 17, 6, 4) > 0
     assert L.mobody_dara_relabel(None, 5, 17, 6, 44, None, None, 1.0, None, None) == -1
     assert L.mobody_sample_rows(None, 3, 44, None) == -1
     sj = (_ffi.SampleJob * 1)()
@@ -80,7 +82,8 @@ def test_struct_layouts_match_header_via_gcc(libpath, tmp_path):
     structs = {"mobody_step_desc": _ffi.StepDesc, "mobody_train_desc": _ffi.TrainDesc,
                "mobody_dyn_params": _ffi.DynParams, "mobody_mlp_params": _ffi.MlpParams, "mobody_mlp_state": _ffi.MlpState,
                "mobody_rollout_desc": _ffi.RolloutDesc, "mobody_classifier_desc": _ffi.ClassifierDesc,
-               "mobody_sample_job": _ffi.SampleJob, "mobody_peer_desc": _ffi.PeerDesc}
+               "mobody_sample_job": _ffi.SampleJob, "mobody_peer_desc": _ffi.PeerDesc,
+               "mobody_dyn_state": _ffi.DynState, "mobody_dynfit_desc": _ffi.DynFitDesc}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', 'int main(void){']
     for cname, ct in structs.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')

@@ -178,3 +178,48 @@ def test_philox_normals_are_normal():
     assert s.min() == 0 and s.max() == 4 and np.all(np.abs(np.bincount(s) / 50000 - 0.2) < 0.01)
     i = buffer_indices(1, 2, 10000, 777)
     assert i.min() >= 0 and i.max() < 777
+
+
+def fit_replay(g, step_fn):
+    """Drive ``step_fn(call, use_trg, batch, eps_latent, eps_next, t)`` through the calls of a dynfit fixture; t = per-layer
+    Adam step counts AFTER the call.  Shared by the oracle test here and the CUDA test (tests/test_gpu_dynfit.py)."""
+    counts = {}
+    for c, use_trg in enumerate(g["calls"]):
+        for n in M.fit_trained_layers(bool(use_trg)):
+            counts[n] = counts.get(n, 0) + 1
+        batch = [g[f"c{c}_{k}"] for k in ("obs", "act", "next_obs", "reward")]
+        step_fn(c, bool(use_trg), batch, g[f"c{c}_eps_latent"], g[f"c{c}_eps_next"], dict(counts))
+    return counts
+
+
+@pytest.mark.parametrize("name", ["dynfit_S11A3_B24", "dynfit_S17A6_B40"])
+def test_dynamics_fitting_step_matches_reference(golden_dir, name):
+    """oracle.fit_step == the reference's learn() (mobody_dynamics.py:594-653) under the same scripted randn_like draws:
+    returned loss scalars per call, Adam state and parameters after the last call (sampled elements)."""
+    from oracle.make_golden import fit_sample_index
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    S, A = int(g["S"]), int(g["A"])
+    p = M.make_dynamics_params(S, A, int(g["seed"]), healthy_state=HEALTHY["hopper" if S == 11 else "walker2d"](S))
+    m, v, first_m = {}, {}, {}
+
+    def step(c, use_trg, batch, el, en, t):
+        for n in M.fit_trained_layers(use_trg):
+            for sfx in (".weight", ".bias"):
+                m.setdefault(n + sfx, torch.zeros_like(p[n + sfx])); v.setdefault(n + sfx, torch.zeros_like(p[n + sfx]))
+        losses, _ = M.fit_step(p, m, v, t, *(torch.from_numpy(x) for x in batch), torch.from_numpy(el), torch.from_numpy(en), use_trg)
+        np.testing.assert_allclose(losses[:5], g[f"c{c}_losses"], rtol=2e-5)
+        if c == 0:
+            first_m.update({k: x.clone() for k, x in m.items()})
+    counts = fit_replay(g, step)
+    for n in M.dynamics_layer_shapes(S, A):
+        for sfx in (".weight", ".bias"):
+            k = n + sfx
+            idx = fit_sample_index(p[k].numel())
+            assert bool(g["has_state_" + k]) == (k in m)
+            np.testing.assert_allclose(p[k].numpy().ravel()[idx], g["p_" + k], rtol=1e-5, atol=2e-6)
+            if k in m:
+                assert int(g["t_" + k]) == counts[n]
+                np.testing.assert_allclose(m[k].numpy().ravel()[idx], g["m_" + k], rtol=2e-4, atol=1e-7)
+                np.testing.assert_allclose(v[k].numpy().ravel()[idx], g["v_" + k], rtol=4e-4, atol=1e-12)
+            if "first_m_" + k in g.files:
+                np.testing.assert_allclose(first_m[k].numpy().ravel()[idx], g["first_m_" + k], rtol=2e-4, atol=1e-7)
