@@ -514,16 +514,28 @@ def main():
             exchange = "nccl"
     pending = []
 
+    def wait_on_own_stream(h):
+        # a p2p handle is waited for on the stream its rollout ran on: the ack of epoch e - 2 (enqueued with rollout e on
+        # that same stream) is then ordered after it
+        if isinstance(h, tuple):
+            with torch.cuda.stream(h[1]):
+                h[0].wait()
+        else:
+            h.wait()
+
     def drain():
         while pending:
-            pending.pop(0).wait()
+            wait_on_own_stream(pending.pop(0))
 
     produced = torch.zeros(1, dtype=torch.float64, device=dev)   # transitions produced by this rank (device accumulator)
-    # N = 1: consecutive rollouts are independent, so they alternate between the agent's two rollout streams (own workspace
+    # Consecutive rollouts are independent, so they alternate between the agent's two rollout streams (own workspace
     # each): the last, 72 %-idle round of one step kernel (782 tiles on 148 SMs) runs beside the first round of the next.
-    two_streams = dist is None and os.environ.get("MOBODY_BENCH_STREAMS", "2") != "1"
+    # N > 1 (peer-memory exchange): epoch parity = stream, see parallel.p2p_rollout.
+    two_streams = (dist is None or exchange == "p2p") and os.environ.get("MOBODY_BENCH_STREAMS", "2") != "1"
     side = ag.rollout_streams() if two_streams else None
     produced_side = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(2)]
+    last_handle = [None]
+    last_epoch = [None]     # (epoch parity) xor (stream index) of the first two-stream exchange: constant afterwards
 
     def fork_streams():
         if side:
@@ -542,10 +554,23 @@ def main():
         """One rollout with nothing read back by the host (counts stay on the device; read once after the timed region)."""
         i = pool_i[0]
         x = obs_pool[i % n_pool]; pool_i[0] += 1
-        if side:
+        if side and dist is None:
             with torch.cuda.stream(side[i & 1]):
                 o, info = ag.rollout_device(x, T, row0=rank * Bn, sync=False, ws_slot=10 + (i & 1), verify_images=False)
                 produced_side[i & 1].add_(info["stats_dev"][1:2])
+            return
+        if side:
+            st = side[i & 1]
+            with torch.cuda.stream(st):
+                h = P.sharded_rollout(ag, x, T, sharded_input=True, gather="p2p", verify_images=False)
+                if last_epoch[0] is None:
+                    last_epoch[0] = (h.epoch ^ i) & 1
+                assert ((h.epoch ^ i) & 1) == last_epoch[0], "exchange epoch parity and stream fell out of step"
+                produced_side[i & 1].add_(h.info["stats_dev"][1:2])
+            last_handle[0] = h
+            pending.append((h, st))
+            if len(pending) > 1:
+                wait_on_own_stream(pending.pop(0))
             return
         if dist is None:
             o, info = ag.rollout_device(x, T, row0=rank * Bn, sync=False)
@@ -590,6 +615,15 @@ def main():
     wall = time.perf_counter() - wall0
     dev_ms = e0.elapsed_time(e1)
     n_trans = float(produced.item())
+    if last_handle[0] is not None and check is not None:
+        # the last timed step, as every rank received it: the headers in MY receive buffer must add up to what the ranks
+        # say they produced (device counters, all-reduced) -- the two-stream pipeline delivered complete results
+        h = last_handle[0]
+        kept_r, produced_all, _ = h.counts()
+        mine = torch.stack([h.info["stats_dev"][1], h.info["kept_dev"][0].double()])
+        dist.all_reduce(mine)
+        check["timed_last_step"] = {"produced": produced_all, "kept": int(sum(kept_r)),
+                                    "ok": bool(int(mine[0].item()) == produced_all and int(mine[1].item()) == sum(kept_r))}
 
     # ---- step-kernel-only timing for the roofline (same stream, events directly around the launch) ----
     from mobody_b200.dynamics import StepWorkspace

@@ -196,10 +196,14 @@ class GatheredRollout:
                                                        "kept": int(sum(kept)), "kept_per_rank": kept, "exchange": self.ex.mode}
 
 
-def p2p_rollout(agent, local, T, use_trg, row0, cap, *, group=None, step0=None, exchange=None, ctas=0):
+def p2p_rollout(agent, local, T, use_trg, row0, cap, *, group=None, step0=None, exchange=None, ctas=0, verify_images=True):
     """This rank's shard rolled on the device, packed into its own slot and pushed to every rank (csrc/peer.cu).  Asynchronous: returns a
     GatheredRollout handle; nothing is read back.  The push kernel runs on a side stream so that it overlaps whatever the
-    caller enqueues next (e.g. the next rollout); workspaces alternate with the exchange parity."""
+    caller enqueues next (e.g. the next rollout); workspaces alternate with the exchange parity.
+    Consecutive calls may be enqueued on TWO alternating streams (epoch parity = stream), so that one rollout's partial last
+    round of tiles overlaps the next rollout's first: everything keyed on the parity (workspace, receive-buffer half, the
+    ack of epoch e - 2) then lives on one stream -- the caller must enqueue ``wait()`` of a handle on the stream it was
+    produced on, and verify the weight images once before the fork (``verify_images=False`` here)."""
     from . import _ffi
     lib, dev = _ffi.lib(), local.device
     S, A = local.shape[1], agent.config["action_dim"]
@@ -225,7 +229,7 @@ def p2p_rollout(agent, local, T, use_trg, row0, cap, *, group=None, step0=None, 
     local = _ffi.f32(local, dev)
     ws = agent._rollout_workspace(T, B, S, A, 4 + (e & 1))
     rows, _ = ex.views(e)
-    d, keep = agent._rollout_desc(local, T, use_trg, ws, rows[ex.rank], row0=row0, step0=step0)   # packs into OUR slot of the local buffer
+    d, keep = agent._rollout_desc(local, T, use_trg, ws, rows[ex.rank], row0=row0, step0=step0, verify_images=verify_images)   # packs into OUR slot of the local buffer
     _ffi.check(lib.mobody_rollout(C.byref(d), _ffi.stream_ptr(dev)))
     kept_dev, stats_dev = ws["counts"][T + 1:T + 2], ws["stats"][:2]
     if ex.overlap:
@@ -277,7 +281,7 @@ def _exchange_mode(agent):
 
 
 def sharded_rollout(agent, init_obss, rollout_length, use_trg=True, *, group=None, gather=True, sharded_input=False, step0=None,
-                    exchange=None):
+                    exchange=None, verify_images=True):
     """MOBODY.rollout over all ranks of ``group``.
 
     init_obss: the GLOBAL start states [B, S] (every rank passes the same tensor and takes its shard), or with
@@ -300,7 +304,7 @@ def sharded_rollout(agent, init_obss, rollout_length, use_trg=True, *, group=Non
     if not gather or T == 0:
         return agent.rollout_device(local, T, use_trg, row0=lo, step0=step0)
     if gather in ("p2p", "p2p_dict"):
-        res = p2p_rollout(agent, local, T, use_trg, lo, cap, group=group, step0=step0, exchange=exchange)
+        res = p2p_rollout(agent, local, T, use_trg, lo, cap, group=group, step0=step0, exchange=exchange, verify_images=verify_images)
         return res if gather == "p2p" else res.to_dict()
     S = local.shape[1]
     probe_w = getattr(agent, "config", {}).get("action_dim")
