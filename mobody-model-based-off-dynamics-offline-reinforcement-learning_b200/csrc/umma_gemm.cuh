@@ -189,37 +189,42 @@ __global__ void __launch_bounds__(NT, 2) gemm_kernel(const __grid_constant__ Arg
 #ifdef UG_TRACE
   t_[1] = clock64();
 #endif
-  Operand<BM> oa; Operand<NP> ob;
+  Operand<BM> oa0, oa1; Operand<NP> ob0, ob1;                           // chunk c lives in register set c & 1
   float rowsum[Operand<BM>::U];
 #pragma unroll
   for (int u = 0; u < Operand<BM>::U; ++u) rowsum[u] = 0.f;
   float* rs = (A_SRC == SRC_RCONTIG && EPI == EPI_PART && jb.db) ? rowsum : nullptr;
   const int nrows_b = jb.N;                                             // valid rows of the B operand (n < N)
   const uint32_t idesc = make_idesc_tf32(BM, NP);
-  // software pipeline with ONE load site and ONE store site: iteration c stores chunk c (fetched during iteration c - 1),
-  // fetches chunk c + 1 into registers and issues the MMAs of chunk c; c = -1 is the prologue fetch
-#pragma unroll 1
-  for (int c = -1; c < nchunks; ++c) {
+  // Software pipeline, global loads TWO chunks ahead: step c stores chunk c (fetched during step c - 2) into stage c & 1,
+  // fetches chunk c + 2 into the registers it just freed and issues the MMAs of chunk c -- a DRAM / L2 round trip is
+  // covered by two steps instead of one.  The packed B image of chunk c + 1 is requested AFTER the step's barrier, by a thread
+  // that is not the MMA issuer: its wait for the MMAs of chunk c - 1 (which free that stage) no longer holds back the
+  // barrier, so chunk c's MMAs are queued while chunk c - 1's still run.
+  // (Measured and not kept, round 2: a ninth warp as dedicated MMA issuer with per-stage "full" mbarriers instead of the
+  // barrier, with two stages of K = 16 or four of K = 8 -- 2 145 / 2 120 updates/s at batch 4096 against 2 244 for this loop.
+  // A clock64 trace of the phases shows where a tile's ~45 k cycles go: the tensor pipe needs 12.6 k (96 MMAs of 128 x 256 x 8 at
+  // 131 cycles), the operand path ~400 - 700 per K = 16 chunk in store + load issue + proxy fence, the chain "MMAs done -> free
+  // barrier -> bulk copy -> full barrier" ~830 cycles whatever the copy size, and the epilogue 8 - 16 k.)
+  auto fetch = [&](Operand<BM>& a, Operand<NP>& b, int c) {
+    const int k0 = kbeg + c * KC;
+    a.load(jb.A, jb.lda, A_SRC, m0, rows, k0, kend, jb.A2, jb.lda2, jb.ksplit, rs);
+    if (B_SRC != SRC_PACKED) b.load(jb.B, jb.ldb, B_SRC, 0, nrows_b, k0, kend, nullptr, 0, 0, nullptr);
+  };
+  auto tma_b = [&](int c) {                                             // chunk c of the packed weight image -> stage c & 1
+    const int nb = c & 1;
+    if (c >= 2) tc::mbar_wait(&bar_free[nb], (uint32_t)(((c >> 1) - 1) & 1));
+    tc::mbar_arrive_expect_tx(&bar_fullb[nb], 2 * B_PLANE);
+    tc::bulk_g2s(smem + (size_t)nb * STAGE + 2 * A_PLANE, reinterpret_cast<const unsigned char*>(jb.B) + (size_t)(kbeg / KC + c) * (2 * B_PLANE),
+                 2 * B_PLANE, &bar_fullb[nb]);
+  };
+  auto step = [&](Operand<BM>& a, Operand<NP>& b, int c) {
     const int buf = c & 1;
     unsigned char* st = smem + (size_t)buf * STAGE;
-    if (c >= 0) {
-      if (c >= 2) tc::mbar_wait(&bar_free[buf], (uint32_t)(((c >> 1) - 1) & 1));    // the MMAs that read this stage are done
-      oa.store(st, A_SRC);
-      if (B_SRC != SRC_PACKED) ob.store(st + 2 * A_PLANE, B_SRC);
-    }
-    if (c + 1 < nchunks) {                                              // next chunk's global loads fly during this chunk's MMAs
-      const int k0 = kbeg + (c + 1) * KC;
-      oa.load(jb.A, jb.lda, A_SRC, m0, rows, k0, kend, jb.A2, jb.lda2, jb.ksplit, rs);
-      if (B_SRC != SRC_PACKED) ob.load(jb.B, jb.ldb, B_SRC, 0, nrows_b, k0, kend, nullptr, 0, 0, nullptr);
-    }
-    if (B_SRC == SRC_PACKED && tid == 32 && c + 1 < nchunks) {          // TMA: chunk c + 1 of the packed weight image -> the other stage
-      const int nb = (c + 1) & 1;
-      if (c + 1 >= 2) tc::mbar_wait(&bar_free[nb], (uint32_t)((((c + 1) >> 1) - 1) & 1));
-      tc::mbar_arrive_expect_tx(&bar_fullb[nb], 2 * B_PLANE);
-      tc::bulk_g2s(smem + (size_t)nb * STAGE + 2 * A_PLANE, reinterpret_cast<const unsigned char*>(jb.B) + (size_t)(kbeg / KC + c + 1) * (2 * B_PLANE),
-                   2 * B_PLANE, &bar_fullb[nb]);
-    }
-    if (c < 0) continue;
+    if (c >= 2) tc::mbar_wait(&bar_free[buf], (uint32_t)(((c >> 1) - 1) & 1));      // the MMAs that read this stage are done
+    a.store(st, A_SRC);
+    if (B_SRC != SRC_PACKED) b.store(st + 2 * A_PLANE, B_SRC);
+    if (c + 2 < nchunks) fetch(a, b, c + 2);
     tc::fence_proxy_async_smem();
     __syncthreads();
     if (tid == 0) {
@@ -237,7 +242,14 @@ __global__ void __launch_bounds__(NT, 2) gemm_kernel(const __grid_constant__ Arg
       }
       tc::umma_commit(&bar_free[buf]);
       if (c + 1 == nchunks) tc::umma_commit(&bar_done);
-    }
+    } else if (B_SRC == SRC_PACKED && tid == 32 && c + 1 < nchunks) tma_b(c + 1);
+  };
+  if (nchunks > 0) { fetch(oa0, ob0, 0); if (B_SRC == SRC_PACKED && tid == 32) tma_b(0); }
+  if (nchunks > 1) fetch(oa1, ob1, 1);
+#pragma unroll 1
+  for (int c = 0; c < nchunks; c += 2) {
+    step(oa0, ob0, c);
+    if (c + 1 < nchunks) step(oa1, ob1, c + 1);
   }
 #ifdef UG_TRACE
   t_[2] = clock64();
