@@ -6,6 +6,7 @@
 //     [ state(S) | action(A) | next_state(S) | reward | not_done | 0-pad ]
 // so that sample() is a 128-bit-vectorised row gather and add_batch() a row scatter.
 #include "common.cuh"
+#include <stdlib.h>
 #include "philox.cuh"
 #include "term.cuh"
 #include "../../include/mobody_b200.h"
@@ -71,6 +72,61 @@ __global__ void pack_rows_kernel(const float* __restrict__ s, const float* __res
       v[j] = x;
     }
     reinterpret_cast<float4*>(out)[t] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// Same, for 16-byte aligned sources: a tile of TR rows is a CONTIGUOUS range of each source array, so the tile is fetched with
+// 128-bit loads straight down each array (all of a thread's loads in flight before the first use), assembled as the row
+// image in shared memory and written out as one contiguous run of 128-bit stores.  (The per-16-byte-group kernel above reads
+// with 4-byte loads from five places per store: 0.49 of the HBM peak at 2 M rows; this one is bound by bytes in flight.)
+constexpr int PACK_TR = 64;
+template <int NV>     // NV = 128-bit loads per thread per source array (compile-time so they are all issued before use)
+__device__ __forceinline__ void pack_src(const float* __restrict__ src, int len, int w, int col0, int rw, float* img, bool flip) {
+  const int nv = len >> 2;
+  float4 v[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int i = threadIdx.x + k * blockDim.x;
+    v[k] = i < nv ? __ldg(reinterpret_cast<const float4*>(src) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int i = threadIdx.x + k * blockDim.x;
+    if (i < nv) {
+      const float x[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+      int row = (4 * i) / w, col = (4 * i) - row * w;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        img[row * rw + col0 + col] = flip ? 1.0f - x[j] : x[j];
+        if (++col == w) { col = 0; ++row; }
+      }
+    }
+  }
+  for (int e = (nv << 2) + threadIdx.x; e < len; e += blockDim.x) {      // (only a ragged last tile has a tail)
+    const float x = __ldg(src + e);
+    img[(e / w) * rw + col0 + e % w] = flip ? 1.0f - x : x;
+  }
+}
+template <int NVS, int NVA>
+__global__ void __launch_bounds__(256) pack_rows_tile_kernel(const float* __restrict__ s, const float* __restrict__ a, const float* __restrict__ ns,
+                                                             const float* __restrict__ r, const float* __restrict__ d, long long n, int S, int A,
+                                                             int rw, int done_is_terminal, float* __restrict__ out) {
+  extern __shared__ __align__(16) float img[];                          // [PACK_TR][rw]
+  const long long tiles = (n + PACK_TR - 1) / PACK_TR;
+  for (int e = threadIdx.x; e < PACK_TR * rw; e += blockDim.x) img[e] = 0.f;     // the pad columns stay zero
+  for (long long t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const long long r0 = t * PACK_TR;
+    const int rows = (int)min((long long)PACK_TR, n - r0);
+    __syncthreads();                                                    // the previous tile's stores have read the image
+    pack_src<NVS>(s + r0 * S, rows * S, S, 0, rw, img, false);
+    pack_src<NVA>(a + r0 * A, rows * A, A, S, rw, img, false);
+    pack_src<NVS>(ns + r0 * S, rows * S, S, S + A, rw, img, false);
+    pack_src<1>(r + r0, rows, 1, 2 * S + A, rw, img, false);
+    pack_src<1>(d + r0, rows, 1, 2 * S + A + 1, rw, img, done_is_terminal != 0);
+    __syncthreads();
+    float4* dst = reinterpret_cast<float4*>(out + r0 * rw);
+    const float4* src = reinterpret_cast<const float4*>(img);
+    for (int i = threadIdx.x; i < rows * (rw >> 2); i += blockDim.x) dst[i] = src[i];
   }
 }
 
@@ -350,6 +406,23 @@ void mb_philox_indices_launch(int64_t* idx, long long n, unsigned long long seed
 void mb_pack_rows_launch(const float* s, const float* a, const float* ns, const float* r, const float* d, long long n,
                          int S, int A, int rw, int done_is_terminal, float* out, cudaStream_t st) {
   if (n <= 0) return;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(ns) |
+                         reinterpret_cast<uintptr_t>(r) | reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  const size_t smem = (size_t)buf::PACK_TR * rw * sizeof(float);
+  static const int threads = [] { const char* e = getenv("MOBODY_PACK_THREADS"); return e && atoi(e) >= 32 && atoi(e) <= 256 ? atoi(e) : 128; }();   // measured: 128 x 16 CTAs per SM 0.91 of the HBM peak, 256 x 8: 0.73
+  static const int per_sm = [] { const char* e = getenv("MOBODY_PACK_CTAS"); return e && atoi(e) > 0 ? atoi(e) : 16; }();
+  const int nvs = (buf::PACK_TR / 4 * S + threads - 1) / threads, nva = (buf::PACK_TR / 4 * A + threads - 1) / threads;   // 128-bit loads per thread per array
+  if (aligned && n >= 4096 && smem <= 48 * 1024 && nvs <= 8 && nva <= 4) {
+    const long long tiles = (n + buf::PACK_TR - 1) / buf::PACK_TR;
+    const unsigned grid = (unsigned)(tiles < 148LL * per_sm ? tiles : 148LL * per_sm);
+#define MB_PACK(NS_, NA_) buf::pack_rows_tile_kernel<NS_, NA_><<<grid, threads, smem, st>>>(s, a, ns, r, d, n, S, A, rw, done_is_terminal, out)
+    if (nvs <= 1 && nva <= 1) MB_PACK(1, 1);
+    else if (nvs <= 2 && nva <= 1) MB_PACK(2, 1);
+    else if (nvs <= 4 && nva <= 2) MB_PACK(4, 2);
+    else MB_PACK(8, 4);
+#undef MB_PACK
+    return;
+  }
   buf::pack_rows_kernel<<<grid_for(n * (rw / 4), buf::NT), buf::NT, 0, st>>>(s, a, ns, r, d, n, S, A, rw, done_is_terminal, out);
 }
 void mb_ring_insert_launch(const float* src, long long n_cap, const int* n_dev, int rw, long long ptr, long long cap,

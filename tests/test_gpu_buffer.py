@@ -132,3 +132,27 @@ def test_fused_sample_rows_equals_separate_draw_and_gather():
     _ffi.check(_ffi.lib().mobody_sample_rows(jobs, 3, RW, _ffi.stream_ptr(torch.device("cuda"))))
     want = torch.cat([b.sample_rows(n) for b, n in zip(bufs, ns)], 0)
     assert torch.equal(rows, want)
+
+
+@pytest.mark.parametrize("S,A,n", [(17, 6, 100_003), (11, 3, 4096), (27, 8, 65_537), (29, 8, 9_999), (64, 32, 5_000), (17, 6, 4_095)])
+def test_pack_rows_tile_path_bit_exact(S, A, n):
+    """convert_D4RL / add_batch row packing (utils.py:43-92, 173-193) at sizes that take the 128-bit tile kernel (n >= 4096,
+    aligned sources), with ragged last tiles, both done conventions, and the unaligned-source fallback: bit-exact vs torch.cat."""
+    import mobody_b200 as mb
+    from mobody_b200 import _ffi
+    g = torch.Generator(device="cuda").manual_seed(S * 7 + A)
+    s, a, ns = (torch.randn(n, w, device="cuda", generator=g) for w in (S, A, S))
+    r = torch.randn(n, device="cuda", generator=g); d = (torch.rand(n, device="cuda", generator=g) < 0.1).float()
+    buf = mb.ReplayBuffer(S, A, "cuda", max_size=8)
+    for flip in (True, False):
+        got = buf._pack(s, a, ns, r, d, flip)
+        want = torch.zeros(n, buf.RW, device="cuda")
+        want[:, :S], want[:, S:S + A], want[:, S + A:2 * S + A] = s, a, ns
+        want[:, 2 * S + A], want[:, 2 * S + A + 1] = r, (1.0 - d if flip else d)
+        assert torch.equal(got, want)
+    # a source that is not 16-byte aligned (a view starting one float into an allocation) takes the scalar kernel: same result
+    s_un = torch.empty(n * S + 1, device="cuda")[1:].view(n, S).copy_(s)
+    assert s_un.data_ptr() % 16 != 0
+    out = torch.empty(n, buf.RW, device="cuda")
+    _ffi.check(_ffi.lib().mobody_pack_rows(s_un.data_ptr(), _ffi.ptr(a), _ffi.ptr(ns), _ffi.ptr(r), _ffi.ptr(d), n, S, A, 1, _ffi.ptr(out), _ffi.stream_ptr(s.device)))
+    assert torch.equal(out, buf._pack(s, a, ns, r, d, True))
