@@ -20,6 +20,7 @@
 #include "philox.cuh"
 #include "../../include/mobody_b200.h"
 #include <math.h>
+#include <stdlib.h>
 
 const char* mb_gemm_launch(const ug::Args& a, cudaStream_t st);     // train_tc.cu
 
@@ -352,6 +353,27 @@ static void layer_table(LayerDef* ly, int S, int A, int use_trg) {
 static Dims make_dims(int B, int S, int A) { return Dims{S, A, B, r4(S), L + A, r4(L + A), 2 * S + A, r4(2 * S + A)}; }
 }  // namespace dfit
 
+// The eleven weight-gradient launches depend only on their layer's output gradient and input activation, not on each other or
+// on the backward-data chain: they run on a side stream (fork by event after the kernel that produces the gradient, join
+// before Adam), so the chain of dependent launches is 32 long instead of 43.  MOBODY_DYNFIT_SIDE=0 keeps one stream.
+namespace dfit {
+struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork[11] = {}, join = nullptr; bool ok = false, tried = false; };
+static SideStream& side_stream() {
+  static SideStream per_dev[64];
+  int dev = 0; cudaGetDevice(&dev);
+  SideStream& ss = per_dev[dev & 63];
+  if (!ss.tried) {
+    ss.tried = true;
+    const char* e = getenv("MOBODY_DYNFIT_SIDE");
+    if (!(e && e[0] == '0') && cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking) == cudaSuccess) {
+      ss.ok = cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) == cudaSuccess;
+      for (int i = 0; i < 11 && ss.ok; ++i) ss.ok = cudaEventCreateWithFlags(&ss.fork[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+  }
+  return ss;
+}
+}  // namespace dfit
+
 long long mb_dynfit_workspace_bytes(int B, int S, int A, int nsplit) {
   dfit::Ws w; dfit::LayerDef ly[11]; dfit::layer_table(ly, S, A, 1);
   return (long long)dfit::carve(w, nullptr, dfit::make_dims(B, S, A), nsplit, ly, true);
@@ -378,6 +400,13 @@ const char* mb_dynfit_step_launch(const mobody_dynfit_desc& dsc, cudaStream_t st
 #define EW(kern, n) do { const long long nb_ = ((long long)(n) + 255) / 256; \
     if (mb_launch(kern, dim3((unsigned)(nb_ < 1 ? 1 : (nb_ > 1184 ? 1184 : nb_))), dim3(256), 0, st, fa) != cudaSuccess) return #kern " launch failed"; } while (0)
 #define GEMM(args) do { if ((err = mb_gemm_launch(args, st))) return err; } while (0)
+  SideStream& ss = side_stream();
+  // weight gradient of layer li: on the side stream, after everything enqueued on `st` so far (its operands are complete)
+#define WGRAD(li, ...) do { \
+    if (ss.ok) { \
+      if (cudaEventRecord(ss.fork[li], st) != cudaSuccess || cudaStreamWaitEvent(ss.s, ss.fork[li], 0) != cudaSuccess) return "dynfit: side-stream fork failed"; \
+      if ((err = mb_gemm_launch(wgrad(li, __VA_ARGS__), ss.s))) return err; \
+    } else if ((err = mb_gemm_launch(wgrad(li, __VA_ARGS__), st))) return err; } while (0)
 
   // ---- GEMM job builders: one job per ensemble member ----
   auto fwd = [&](int li, const float* X, int ldx, int rows, float* C, int ldc, float* pre) {
@@ -442,34 +471,35 @@ const char* mb_dynfit_step_launch(const mobody_dynfit_desc& dsc, cudaStream_t st
   if (mb_launch(loss_kernel, dim3(E), dim3(256), 0, st, fa) != cudaSuccess) return "loss_kernel launch failed";
   if (mb_launch(finish_kernel, dim3(1), dim3(32), 0, st, fa) != cudaSuccess) return "finish_kernel launch failed";
   // ---------------- backward: reward head ----------------
-  GEMM(wgrad(10, w.dR, 4, w.V2, H, 2 * B));
+  WGRAD(10, w.dR, 4, w.V2, H, 2 * B);
   GEMM(bwd(10, w.dR, 4, 2 * B, w.PV2, H, w.PV2));           // PV2 <- dL/d(pre of r2)
-  GEMM(wgrad(9, w.PV2, H, w.V1, H, 2 * B));
+  WGRAD(9, w.PV2, H, w.V1, H, 2 * B);
   GEMM(bwd(9, w.PV2, H, 2 * B, w.PV1, H, w.PV1));           // PV1 <- dL/d(pre of r1)
-  GEMM(wgrad(8, w.PV1, H, w.RIn, d.RI4, 2 * B));
+  WGRAD(8, w.PV1, H, w.RIn, d.RI4, 2 * B);
   GEMM(bwd(8, w.PV1, H, 2 * B, w.dRIn, d.RI4, nullptr));
   EW(dfake_kernel, (long long)B * S);
   // ---------------- transition head ----------------
-  GEMM(wgrad(7, w.dM, d.S4, w.U2, H, 4 * B));
+  WGRAD(7, w.dM, d.S4, w.U2, H, 4 * B);
   GEMM(bwd(7, w.dM, d.S4, 4 * B, w.PU2, H, w.PU2));
-  GEMM(wgrad(6, w.PU2, H, w.U1, H, 4 * B));
+  WGRAD(6, w.PU2, H, w.U1, H, 4 * B);
   GEMM(bwd(6, w.PU2, H, 4 * B, w.PU1, H, w.PU1));
-  GEMM(wgrad(5, w.PU1, H, w.TrIn, L, 4 * B));
+  WGRAD(5, w.PU1, H, w.TrIn, L, 4 * B);
   GEMM(bwd(5, w.PU1, H, 4 * B, w.dTrIn, L, nullptr));
   EW(dza_kernel, (long long)E * 2 * B * 32);
   // ---------------- action encoder ----------------
-  GEMM(wgrad(4, w.dZA, 32, w.G, ZH, 3 * B));
+  WGRAD(4, w.dZA, 32, w.G, ZH, 3 * B);
   GEMM(bwd(4, w.dZA, 32, 3 * B, w.PG, ZH, w.PG));
-  GEMM(wgrad(3, w.PG, ZH, w.ZAin, d.LA4, 3 * B));
+  WGRAD(3, w.PG, ZH, w.ZAin, d.LA4, 3 * B);
   GEMM(bwd(3, w.PG, ZH, 3 * B, w.dZAin, d.LA4, nullptr));
   EW(do3_kernel, (long long)E * B * L);
   // ---------------- trunk ----------------
-  GEMM(wgrad(2, w.dO3, 32, w.H2, H, 2 * B));
+  WGRAD(2, w.dO3, 32, w.H2, H, 2 * B);
   GEMM(bwd(2, w.dO3, 32, 2 * B, w.P2, H, w.P2));
-  GEMM(wgrad(1, w.P2, H, w.H1, H, 2 * B));
+  WGRAD(1, w.P2, H, w.H1, H, 2 * B);
   GEMM(bwd(1, w.P2, H, 2 * B, w.P1, H, w.P1));
-  GEMM(wgrad(0, w.P1, H, w.X0, d.S4, 2 * B));
+  WGRAD(0, w.P1, H, w.X0, d.S4, 2 * B);
   // ---------------- Adam ----------------
+  if (ss.ok && (cudaEventRecord(ss.join, ss.s) != cudaSuccess || cudaStreamWaitEvent(st, ss.join, 0) != cudaSuccess)) return "dynfit: side-stream join failed";
   AdamArgs aa{}; aa.nsplit = ns; aa.b1 = 0.9f; aa.b2 = 0.999f; aa.eps = 1e-8f;
   for (int i = 0; i < 11; ++i) {
     const int t = (i == 3 || i == 4) ? dsc.t_action : dsc.t_shared;
@@ -486,5 +516,6 @@ const char* mb_dynfit_step_launch(const mobody_dynfit_desc& dsc, cudaStream_t st
   if (mb_launch(adam_kernel, dim3(64, aa.njobs), dim3(256), 0, st, aa) != cudaSuccess) return "dynfit adam_kernel launch failed";
 #undef EW
 #undef GEMM
+#undef WGRAD
   return nullptr;
 }

@@ -289,7 +289,9 @@ __global__ void __launch_bounds__(NT, 2) gemm_kernel(const __grid_constant__ Arg
       const float* mrow = jb.mask + (size_t)(m0 + q * 32 + rl) * jb.ldmask + n;
 #pragma unroll
       for (int it = 0; it < 8; ++it)
-        mkv[it] = (q * 32 + it * 4 + rl < rows && colok) ? __ldg(reinterpret_cast<const float4*>(mrow + (size_t)it * 4 * jb.ldmask)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        mkv[it] = !(q * 32 + it * 4 + rl < rows && colok) ? make_float4(0.f, 0.f, 0.f, 0.f)
+                  : EPI == EPI_DSWISH ? *reinterpret_cast<const float4*>(mrow + (size_t)it * 4 * jb.ldmask)     // may alias C (in place): coherent load
+                                      : __ldg(reinterpret_cast<const float4*>(mrow + (size_t)it * 4 * jb.ldmask));
     }
     uint32_t x[32];
     if (nchunks > 0) { tc::tmem_ld32(taddr + (uint32_t)n0, x); tc::tmem_ld_wait(); }
@@ -331,7 +333,7 @@ __global__ void __launch_bounds__(NT, 2) gemm_kernel(const __grid_constant__ Arg
         if (nn >= jb.N || r >= rows) continue;
         float t = tb[rr * 36 + c];
         if (EPI == EPI_MASK) t = __ldg(jb.mask + (size_t)(m0 + r) * jb.ldmask + nn) > 0.f ? t : 0.f;
-        else if (EPI == EPI_DSWISH) t *= dswish_f(__ldg(jb.mask + (size_t)(m0 + r) * jb.ldmask + nn));
+        else if (EPI == EPI_DSWISH) t *= dswish_f(jb.mask[(size_t)(m0 + r) * jb.ldmask + nn]);
         else if (EPI == EPI_SWISH) {
           t += bias_s[nn];
           if (jb.pre) jb.pre[(size_t)(m0 + r) * ldc + nn] = t;

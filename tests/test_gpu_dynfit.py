@@ -158,3 +158,40 @@ def test_learn_validate_train_api():
     assert torch.equal(dyn.model.zs1.weight, dyn.model.zs1.saved_weight)  # load_save (:975)
     nobs, rew, term, info = dyn.step(src[0][:64], src[1][:64])           # the fitted model rolls (packed image follows by checksum)
     assert torch.isfinite(nobs).all() and nobs.shape == (64, S)
+
+
+_FIT_DIGEST = r"""
+import hashlib, sys, os
+sys.path.insert(0, "tests"); sys.path.insert(0, ".")
+import numpy as np, torch
+from helpers import cuda_dynamics
+S, A, N, B = 17, 6, 700, 256
+torch.manual_seed(0)          # the layers the recipe does not cover (action decoders, saved_* copies) are torch-initialised
+rng = np.random.default_rng(4)
+data = [torch.from_numpy(rng.standard_normal((7, N, w)).astype(np.float32)).cuda() for w in (S, A, S, 1)]
+dyn, _ = cuda_dynamics(S, A, 5, "walker2d", 1.0)
+for ep in range(2):
+    for trg in (True, False):
+        out = dyn.learn(trg, *data, B, 0.01)
+torch.cuda.synchronize()
+h = hashlib.sha256()
+for v in dyn.model.state_dict().values():
+    h.update(v.detach().cpu().numpy().tobytes())
+h.update(np.asarray(out, np.float64).tobytes())
+print("DIGEST", h.hexdigest())
+"""
+
+
+def test_side_stream_and_launch_mode_do_not_change_a_bit():
+    """The weight gradients run on a side stream and the chain is launched with programmatic dependent launch: neither may
+    change the result (12 optimiser steps over ragged mini-batches, both domains) -- a missing dependency would."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def digest(**env):
+        r = subprocess.run([sys.executable, "-c", _FIT_DIGEST], env=dict(os.environ, **env), capture_output=True, text=True, timeout=300, cwd=root)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        return [ln.split()[1] for ln in r.stdout.splitlines() if ln.startswith("DIGEST")][0]
+    base = digest(MOBODY_DYNFIT_SIDE="1", MOBODY_PDL="1")
+    assert base == digest(MOBODY_DYNFIT_SIDE="0", MOBODY_PDL="1") == digest(MOBODY_DYNFIT_SIDE="1", MOBODY_PDL="0")
