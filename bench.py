@@ -782,7 +782,7 @@ def main():
         fit_dev, fit_wall = gpu_fit_rate(mb, dev, dyn)
         line["train"]["dynamics_fit"] = {"metric": "dynamics fitting steps/sec", "value": fit_wall, "device_only": fit_dev, "unit": "steps/s",
                                          "workload": f"MOBODYEnsembleDynamics.learn, 7 members x 256 rows per mini-batch, S{S}/A{A} "
-                                                     "(3 losses + backward + Adam = one C-ABI call, 43 launches)"}
+                                                     "(3 losses + backward + Adam = one C-ABI call, 43 launches, weight gradients on a side stream)"}
     if not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         if upd_wall is not None:
