@@ -181,9 +181,11 @@ def baseline_config_lines(mb, dev):
     cases = [("C1 walker2d-friction S17/A6 50k+2k starts T=1", "walker2d", 17, 6, [52_000], [1], 1.0, 4.0, 5.0),
              ("C3 hopper-kinematic S11/A3 1M starts T=5", "hopper", 11, 3, [1_000_000], [5], 0.8, 4.0, 1.0),
              ("C4 ant-friction S27/A8 50k starts T=5", "ant", 27, 8, [50_000], [5], 0.4, 4.0, 1.0),
-             ("C5 antmaze-umaze-style S29/A8 sweep", "ant", 29, 8, [10_000, 100_000, 1_000_000, 4_000_000], [1, 5], 0.35, 6.0, 1.0)]
+             ("C5 antmaze-umaze-style S29/A8 sweep", "ant", 29, 8, [10_000, 100_000, 1_000_000, 4_000_000], [1, 5], 0.35, 6.0, 1.0),
+             # observations wider than the tensor-core kernel's 64 (Ant-v3's 111 dims): the fp32 CUDA-core step kernel
+             ("wide observations S111/A8 (Ant-v3) 100k starts T=1, fp32 CUDA-core step kernel", "ant", 111, 8, [100_000], [1], 0.6, 4.0, 1.0)]
     for name, env, sd, ad, sizes, Ts, h0, gain, coef in cases:
-        dyn = build_config_dynamics(mb, env, sd, ad, dev, h0, gain, coef)
+        dyn = build_config_dynamics(mb, env, sd, ad, dev, h0, gain, coef, precision="bf16x2" if sd <= 64 else "fp32")
         ag = build_agent(mb, sd, ad, dev, env_filter=1e9)
         ag.dynamics = dyn
         rows = []

@@ -1062,7 +1062,38 @@ template <typename... J> static const char* run_gemms(cudaStream_t st, int nspli
   return mb_gemm_launch(a, st);
 }
 
+// Launches of the large-batch update that do not depend on each other run on a side stream (fork by event, join by event):
+// the layer-2 / head weight gradients beside the backward-data GEMM that produces layer 1's error signal, the single-CTA
+// actor scalar reduction beside the dQ/da chain.  Same kernels, same partial-sum layout: bit-identical to the single-stream
+// chain (MOBODY_TRAIN_SIDE=0), tested.
+struct TrainSide { cudaStream_t s = nullptr; cudaEvent_t fork[4] = {}, join[3] = {}; bool ok = false, tried = false; };
+static TrainSide& train_side() {
+  static TrainSide per_dev[64];
+  int dev = 0; cudaGetDevice(&dev);
+  TrainSide& ss = per_dev[dev & 63];
+  if (!ss.tried) {
+    ss.tried = true;
+    const char* e = getenv("MOBODY_TRAIN_SIDE");
+    if (!(e && e[0] == '0') && cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking) == cudaSuccess) {
+      ss.ok = true;
+      for (int i = 0; i < 4 && ss.ok; ++i) ss.ok = cudaEventCreateWithFlags(&ss.fork[i], cudaEventDisableTiming) == cudaSuccess;
+      for (int i = 0; i < 3 && ss.ok; ++i) ss.ok = cudaEventCreateWithFlags(&ss.join[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+  }
+  return ss;
+}
+
 static const char* mb_train_step_tc_launch(const mobody_train_desc& d, const TrainWs& w, cudaStream_t st) {
+  TrainSide& side = train_side();
+  // fork(i): the side stream continues after everything enqueued on `st` so far; join(i): `st` waits for the side stream
+  auto fork = [&](int i) -> cudaStream_t {
+    if (!side.ok) return st;
+    if (cudaEventRecord(side.fork[i], st) != cudaSuccess || cudaStreamWaitEvent(side.s, side.fork[i], 0) != cudaSuccess) return st;
+    return side.s;
+  };
+  auto join = [&](int i) {
+    if (side.ok) { cudaEventRecord(side.join[i], side.s); cudaStreamWaitEvent(st, side.join[i], 0); }
+  };
   const int N = d.N, nt = d.n_true, S = d.S, A = d.A, rw = d.row_width, ns = d.nsplit, SA = S + A;
   float* ws = (float*)d.workspace;
   const float* X = d.rows;
@@ -1133,6 +1164,12 @@ static const char* mb_train_step_tc_launch(const mobody_train_desc& d, const Tra
     mb_launch(trn::td_kernel, dim3((N + 255) / 256), dim3(256), 0, st, t);
     trn::HeadBwdArgs hb{{Hq[0][1], Hq[1][1]}, {d3[0], d3[1]}, {q[0].w[2], q[1].w[2]}, {Dq[0][1], Dq[1][1]}, N};
     mb_launch(trn::head_bwd_kernel, dim3(296, 2), dim3(256), 0, st, hb);
+    // layer-2 and head weight gradients need only head_bwd's output: beside the backward-data GEMM
+    cudaStream_t s2 = fork(0);
+    if ((e = run_gemms(s2, ns, wgrad_job(Dq[0][1], 256, 256, Hq[0][0], 256, 256, N, ws + w.gq[0][2], ws + w.gq[0][3]),
+                       wgrad_job(Dq[1][1], 256, 256, Hq[1][0], 256, 256, N, ws + w.gq[1][2], ws + w.gq[1][3]),
+                       wgrad_job(d3[0], 1, 1, Hq[0][1], 256, 256, N, ws + w.gq[0][4], ws + w.gq[0][5]),     // the one-output heads: one
+                       wgrad_job(d3[1], 1, 1, Hq[1][1], 256, 256, N, ws + w.gq[1][4], ws + w.gq[1][5])))) return e;   // (mostly empty) tile each
     if ((e = run_gemms(st, 1, P(bwd_job(Dq[0][1], 256, N, 256, q[0].w[1], 256, 256, Hq[0][0], Dq[0][0]), 11),
                        P(bwd_job(Dq[1][1], 256, N, 256, q[1].w[1], 256, 256, Hq[1][0], Dq[1][0]), 12)))) return e;
   }
@@ -1141,12 +1178,9 @@ static const char* mb_train_step_tc_launch(const mobody_train_desc& d, const Tra
   const mobody_mlp_state* qts[2] = {&d.q1_target, &d.q2_target};
   const mobody_mlp_state* qm[2] = {&d.q1_m, &d.q2_m};
   const mobody_mlp_state* qvv[2] = {&d.q1_v, &d.q2_v};
-  if ((e = run_gemms(st, ns, wgrad_job(Dq[0][1], 256, 256, Hq[0][0], 256, 256, N, ws + w.gq[0][2], ws + w.gq[0][3]),
-                     wgrad_job(Dq[1][1], 256, 256, Hq[1][0], 256, 256, N, ws + w.gq[1][2], ws + w.gq[1][3]),
-                     wgrad_job(Dq[0][0], 256, 256, X, rw, SA, N, ws + w.gq[0][0], ws + w.gq[0][1]),
-                     wgrad_job(Dq[1][0], 256, 256, X, rw, SA, N, ws + w.gq[1][0], ws + w.gq[1][1]),
-                     wgrad_job(d3[0], 1, 1, Hq[0][1], 256, 256, N, ws + w.gq[0][4], ws + w.gq[0][5]),     // the one-output heads: one
-                     wgrad_job(d3[1], 1, 1, Hq[1][1], 256, 256, N, ws + w.gq[1][4], ws + w.gq[1][5])))) return e;   // (mostly empty) tile each
+  if ((e = run_gemms(st, ns, wgrad_job(Dq[0][0], 256, 256, X, rw, SA, N, ws + w.gq[0][0], ws + w.gq[0][1]),
+                     wgrad_job(Dq[1][0], 256, 256, X, rw, SA, N, ws + w.gq[1][0], ws + w.gq[1][1])))) return e;
+  join(0);
   trn::AdamArgs ad{}; ad.nsplit = ns; ad.b1 = 0.9f; ad.b2 = 0.999f; ad.eps = 1e-8f; ad.tau = d.tau; ad.njobs = 12;
   ad.zero2 = reinterpret_cast<int*>(ws + w.cnt);
   {
@@ -1181,7 +1215,7 @@ static const char* mb_train_step_tc_launch(const mobody_train_desc& d, const Tra
   for (int k = 0; k < 2; ++k) { ac.qv[k] = qv[k]; ac.qh[k] = qh[k]; ac.gak[k] = gak[k]; }
   ac.part = ws + w.part; ac.ntiles_c = (N + 255) / 256; ac.weight = d.weight; ac.out = ws + w.scal;
   ac.counter = reinterpret_cast<int*>(ws + w.cnt);
-  mb_launch(trn::actor_scalar_kernel, dim3(1), dim3(1024), 0, st, ac);
+  mb_launch(trn::actor_scalar_kernel, dim3(1), dim3(1024), 0, fork(1), ac);      // single CTA: beside the dQ/da chain below
   {   // dQ_k / d action: head backward with unit gradient, backward-data through layers 2 and 1 (action columns of W1 only)
     trn::HeadBwdArgs hb{{Hq[0][1], Hq[1][1]}, {nullptr, nullptr}, {q[0].w[2], q[1].w[2]}, {Dq[0][1], Dq[1][1]}, N};
     mb_launch(trn::head_bwd_kernel, dim3(296, 2), dim3(256), 0, st, hb);
@@ -1196,13 +1230,19 @@ static const char* mb_train_step_tc_launch(const mobody_train_desc& d, const Tra
   for (int k = 0; k < 2; ++k) { pb.gak[k] = gak[k]; pb.qv[k] = qv[k]; pb.qh[k] = qh[k]; }
   pb.api = api; pb.X = X; pb.bc_coef = d.bc_coef; pb.max_action = d.max_action;
   pb.d3p = d3p; pb.part = ws + w.part2; pb.out = ws + w.scal; pb.counter = reinterpret_cast<int*>(ws + w.cnt) + 1;
+  join(1);
   mb_launch(trn::policy_grad_kernel, dim3((N + 127) / 128), dim3(128), 0, st, pb);
   // ---- policy backward-data: dH2 = (d3 W3) * 1[H2 > 0], dH1 = (dH2 W2) * 1[H1 > 0]; weight gradients; Adam ----
-  if ((e = run_gemms(st, 1, P(bwd_job(d3p, A, N, A, pi.w[2], 256, 256, Hp[1], Dp[1]), 13)))) return e;
-  if ((e = run_gemms(st, 1, P(bwd_job(Dp[1], 256, N, 256, pi.w[1], 256, 256, Hp[0], Dp[0]), 14)))) return e;
-  if ((e = run_gemms(st, ns, wgrad_job(Dp[1], 256, 256, Hp[0], 256, 256, N, ws + w.gp[2], ws + w.gp[3]),
-                     wgrad_job(Dp[0], 256, 256, X, rw, S, N, ws + w.gp[0], ws + w.gp[1]),
-                     wgrad_job(d3p, A, A, Hp[1], 256, 256, N, ws + w.gp[4], ws + w.gp[5])))) return e;
+  {
+    cudaStream_t s2 = fork(2);                                           // head weight gradient beside the first backward-data GEMM
+    if ((e = run_gemms(s2, ns, wgrad_job(d3p, A, A, Hp[1], 256, 256, N, ws + w.gp[4], ws + w.gp[5])))) return e;
+    if ((e = run_gemms(st, 1, P(bwd_job(d3p, A, N, A, pi.w[2], 256, 256, Hp[1], Dp[1]), 13)))) return e;
+    s2 = fork(3);                                                        // layer 2's beside the second
+    if ((e = run_gemms(s2, ns, wgrad_job(Dp[1], 256, 256, Hp[0], 256, 256, N, ws + w.gp[2], ws + w.gp[3])))) return e;
+    if ((e = run_gemms(st, 1, P(bwd_job(Dp[1], 256, N, 256, pi.w[1], 256, 256, Hp[0], Dp[0]), 14)))) return e;
+    if ((e = run_gemms(st, ns, wgrad_job(Dp[0], 256, 256, X, rw, S, N, ws + w.gp[0], ws + w.gp[1])))) return e;
+    join(2);
+  }
   trn::AdamArgs ap{}; ap.nsplit = ns; ap.b1 = 0.9f; ap.b2 = 0.999f; ap.eps = 1e-8f; ap.tau = 0.f; ap.njobs = 6;
   {
     const double bc1 = 1.0 - pow(0.9, (double)d.t_pi), bc2 = 1.0 - pow(0.999, (double)d.t_pi);

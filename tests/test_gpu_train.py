@@ -210,7 +210,9 @@ def test_launch_mode_and_tiling_switches_in_subprocess():
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         return [ln.split()[1] for ln in r.stdout.splitlines() if ln.startswith("DIGEST")][0]
 
-    assert digest(MOBODY_PDL="1") == digest(MOBODY_PDL="0")
+    base = digest(MOBODY_PDL="1")
+    assert base == digest(MOBODY_PDL="0")
+    assert base == digest(MOBODY_TRAIN_SIDE="0")          # large-batch update: side-stream overlap on / off
     assert len(digest(MOBODY_TRAIN_TM="64")) == 64
 
 
