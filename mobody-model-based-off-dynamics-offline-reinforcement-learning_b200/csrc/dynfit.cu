@@ -303,22 +303,48 @@ __global__ void __launch_bounds__(256) do3_kernel(const FitArgs a) {
 // bias gradient); parameters are [e][in][out].
 struct AdamJob { float* p; float* m; float* v; const float* g; int in, out, is_bias; float lr_over_bc1, inv_sqrt_bc2; };
 struct AdamArgs { AdamJob job[22]; int njobs, nsplit; float b1, b2, eps; };
+__device__ __forceinline__ void adam_update(const AdamArgs& a, const AdamJob& jb, size_t i, float g) {
+  const float m0 = jb.m[i], m = m0 + (g - m0) * (1.0f - a.b1);              // exp_avg.lerp_(grad, 1 - beta1)
+  const float v = a.b2 * jb.v[i] + (1.0f - a.b2) * g * g;
+  jb.m[i] = m; jb.v[i] = v;
+  const float denom = sqrtf(v) * jb.inv_sqrt_bc2 + a.eps;
+  jb.p[i] = jb.p[i] - jb.lr_over_bc1 * (m / denom);
+}
+// Weights: 32 x 32 tiles through shared memory -- the gradient is read along `in` (its contiguous axis), the parameter and
+// its moments are touched along `out` (theirs); every access is a full 128-byte line.  block = (32, 8).
 __global__ void __launch_bounds__(256) adam_kernel(const __grid_constant__ AdamArgs a) {
   mb_pdl_begin();
   const AdamJob& jb = a.job[blockIdx.y];
-  const int per = jb.is_bias ? jb.out : jb.in * jb.out, n = E * per;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int e = i / per, r = i % per;
-    size_t goff, gstride;
-    if (jb.is_bias) { goff = (size_t)e * a.nsplit * jb.out + r; gstride = jb.out; }
-    else { const int ii = r / jb.out, o = r % jb.out; goff = ((size_t)e * a.nsplit * jb.out + o) * jb.in + ii; gstride = (size_t)jb.out * jb.in; }
-    float g = 0.f;
-    for (int s = 0; s < a.nsplit; ++s) g += jb.g[goff + (size_t)s * gstride];
-    const float m0 = jb.m[i], m = m0 + (g - m0) * (1.0f - a.b1);            // exp_avg.lerp_(grad, 1 - beta1)
-    const float v = a.b2 * jb.v[i] + (1.0f - a.b2) * g * g;
-    jb.m[i] = m; jb.v[i] = v;
-    const float denom = sqrtf(v) * jb.inv_sqrt_bc2 + a.eps;
-    jb.p[i] = jb.p[i] - jb.lr_over_bc1 * (m / denom);
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (jb.is_bias) {
+    const int n = E * jb.out;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+      const int e = i / jb.out, o = i % jb.out;
+      float g = 0.f;
+      for (int s = 0; s < a.nsplit; ++s) g += jb.g[((size_t)e * a.nsplit + s) * jb.out + o];
+      adam_update(a, jb, (size_t)i, g);
+    }
+    return;
+  }
+  __shared__ float tile[32][33];
+  const int to = (jb.out + 31) / 32, ti = (jb.in + 31) / 32, per = to * ti;
+  for (int t = blockIdx.x; t < E * per; t += gridDim.x) {
+    const int e = t / per, o0 = ((t % per) / ti) * 32, i0 = ((t % per) % ti) * 32;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {                                           // tile[o][i] <- sum over the K splits, lanes along `in`
+      const int o = o0 + ty + 8 * k, ii = i0 + tx;
+      float g = 0.f;
+      if (o < jb.out && ii < jb.in)
+        for (int s = 0; s < a.nsplit; ++s) g += jb.g[(((size_t)e * a.nsplit + s) * jb.out + o) * jb.in + ii];
+      tile[ty + 8 * k][tx] = g;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {                                           // lanes along `out`
+      const int ii = i0 + ty + 8 * k, o = o0 + tx;
+      if (ii < jb.in && o < jb.out) adam_update(a, jb, ((size_t)e * jb.in + ii) * jb.out + o, tile[tx][ty + 8 * k]);
+    }
+    __syncthreads();
   }
 }
 
@@ -357,7 +383,7 @@ static Dims make_dims(int B, int S, int A) { return Dims{S, A, B, r4(S), L + A, 
 // on the backward-data chain: they run on a side stream (fork by event after the kernel that produces the gradient, join
 // before Adam), so the chain of dependent launches is 32 long instead of 43.  MOBODY_DYNFIT_SIDE=0 keeps one stream.
 namespace dfit {
-struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork[11] = {}, join = nullptr; bool ok = false, tried = false; };
+struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork[12] = {}, join = nullptr; bool ok = false, tried = false; };
 static SideStream& side_stream() {
   static SideStream per_dev[64];
   int dev = 0; cudaGetDevice(&dev);
@@ -367,7 +393,7 @@ static SideStream& side_stream() {
     const char* e = getenv("MOBODY_DYNFIT_SIDE");
     if (!(e && e[0] == '0') && cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking) == cudaSuccess) {
       ss.ok = cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) == cudaSuccess;
-      for (int i = 0; i < 11 && ss.ok; ++i) ss.ok = cudaEventCreateWithFlags(&ss.fork[i], cudaEventDisableTiming) == cudaSuccess;
+      for (int i = 0; i < 12 && ss.ok; ++i) ss.ok = cudaEventCreateWithFlags(&ss.fork[i], cudaEventDisableTiming) == cudaSuccess;
     }
   }
   return ss;
@@ -468,8 +494,15 @@ const char* mb_dynfit_step_launch(const mobody_dynfit_desc& dsc, cudaStream_t st
   GEMM(fwd(10, w.V2, H, 2 * B, w.R, 4, nullptr));
   // ---------------- losses ----------------
   EW(lossgrad_kernel, (long long)E * 3 * B * S);
-  if (mb_launch(loss_kernel, dim3(E), dim3(256), 0, st, fa) != cudaSuccess) return "loss_kernel launch failed";
-  if (mb_launch(finish_kernel, dim3(1), dim3(32), 0, st, fa) != cudaSuccess) return "finish_kernel launch failed";
+  {   // the loss scalars feed nothing downstream: off the critical path (side stream; they only read forward results)
+    cudaStream_t ls = st;
+    if (ss.ok) {
+      if (cudaEventRecord(ss.fork[11], st) != cudaSuccess || cudaStreamWaitEvent(ss.s, ss.fork[11], 0) != cudaSuccess) return "dynfit: side-stream fork failed";
+      ls = ss.s;
+    }
+    if (mb_launch(loss_kernel, dim3(E), dim3(256), 0, ls, fa) != cudaSuccess) return "loss_kernel launch failed";
+    if (mb_launch(finish_kernel, dim3(1), dim3(32), 0, ls, fa) != cudaSuccess) return "finish_kernel launch failed";
+  }
   // ---------------- backward: reward head ----------------
   WGRAD(10, w.dR, 4, w.V2, H, 2 * B);
   GEMM(bwd(10, w.dR, 4, 2 * B, w.PV2, H, w.PV2));           // PV2 <- dL/d(pre of r2)
@@ -513,7 +546,7 @@ const char* mb_dynfit_step_launch(const mobody_dynfit_desc& dsc, cudaStream_t st
       j.lr_over_bc1 = (float)((double)dsc.lr / bc1); j.inv_sqrt_bc2 = (float)(1.0 / sqrt(bc2));
     }
   }
-  if (mb_launch(adam_kernel, dim3(64, aa.njobs), dim3(256), 0, st, aa) != cudaSuccess) return "dynfit adam_kernel launch failed";
+  if (mb_launch(adam_kernel, dim3(112, aa.njobs), dim3(256), 0, st, aa) != cudaSuccess) return "dynfit adam_kernel launch failed";
 #undef EW
 #undef GEMM
 #undef WGRAD
