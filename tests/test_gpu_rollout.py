@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import cuda_agent, cuda_dynamics, rel_err
+from helpers import cuda_agent, cuda_dynamics, rel_err, rel_err_strict
 from oracle import mobody_oracle as M
 
 pytestmark = pytest.mark.gpu
@@ -34,6 +34,7 @@ def test_rollout_matches_reference_golden(golden_dir, name, precision, capsys):
     for k in ("obss", "next_obss", "actions", "rewards", "terminals", "penalty"):
         assert not tr[k].is_cuda and tr[k].shape == g["out_" + k].shape, k   # CPU tensors, post-filter row count and order
         assert rel_err(tr[k].numpy(), g["out_" + k]) < 1e-4, k
+        assert rel_err_strict(tr[k].numpy(), g["out_" + k]) < 1e-4, k
     assert np.array_equal(tr["terminals"].numpy(), g["out_terminals"])      # masks bit-exact
     assert tr["rewards"].shape[1] == 1 and tr["terminals"].dtype == torch.float32
 

@@ -11,7 +11,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import cuda_dynamics, rel_err
+from helpers import cuda_dynamics, rel_err, rel_err_strict
 from oracle import mobody_oracle as M
 
 pytestmark = pytest.mark.gpu
@@ -31,6 +31,9 @@ def _check(prec, out, ref_next, ref_rew, ref_raw, ref_pen, ref_mean, ref_term, n
     assert rel_err(info["raw_reward"].cpu().numpy(), ref_raw) < tol
     assert rel_err(info["penalty"].cpu().numpy(), ref_pen) < tol
     assert rel_err(rew.cpu().numpy(), ref_rew) < tol
+    if prec in ("fp32", "bf16x2"):      # the fp32-parity modes: 1e-4 under the strict metric too
+        for got, want in ((info["samples"], ref_mean), (nobs, ref_next), (info["raw_reward"], ref_raw), (info["penalty"], ref_pen), (rew, ref_rew)):
+            assert rel_err_strict(got.cpu().numpy(), want) < 1e-4
     assert term.dtype == np.bool_ and term.shape == ref_term.shape
     if prec == "fp32" or near is None:
         assert np.array_equal(term, ref_term)
