@@ -514,6 +514,8 @@ def main():
         except Exception as e:                                     # noqa: BLE001
             check = {"ok": False, "error": repr(e)}
             exchange = "nccl"
+    if os.environ.get("MOBODY_PROBE_LATE"):        # timing experiments only (parallel.p2p_rollout): takes effect after the self-check
+        os.environ["MOBODY_PROBE"] = os.environ["MOBODY_PROBE_LATE"]
     pending = []
 
     def wait_on_own_stream(h):
@@ -617,7 +619,7 @@ def main():
     wall = time.perf_counter() - wall0
     dev_ms = e0.elapsed_time(e1)
     n_trans = float(produced.item())
-    if last_handle[0] is not None and check is not None:
+    if last_handle[0] is not None and check is not None and not os.environ.get("MOBODY_PROBE"):
         # the last timed step, as every rank received it: the headers in MY receive buffer must add up to what the ranks
         # say they produced (device counters, all-reduced) -- the two-stream pipeline delivered complete results
         h = last_handle[0]

@@ -221,6 +221,11 @@ long long mobody_peer_buffer_bytes(int world, long long cap_rows, int W);   /* r
 int mobody_peer_slot(const mobody_peer_desc* p, int r, float** rows, int** header);
 /* push slot `rank` (rows [0, *kept_dev)) of the local buffer to every peer; stats_dev = {reward sum, produced} doubles */
 int mobody_peer_push(const mobody_peer_desc* p, const int* kept_dev, const double* stats_dev, void* stream);
+/* Copy-engine variant of the push (no SM touches the payload): mobody_peer_header writes the header row of slot `rank` in the
+ * LOCAL buffer; the host side then ships the whole slot (cap_rows + 1 rows) to every peer with stream-ordered device-to-device
+ * copies and raises / awaits the flags with stream memory operations (cuStreamWriteValue32 / cuStreamWaitValue32 on the flag
+ * block: word r = arrive[r], word 8 + r = ack[r], the block starts mobody_peer_buffer_bytes(...) - 128 bytes into a buffer). */
+int mobody_peer_header(const mobody_peer_desc* p, const int* kept_dev, const double* stats_dev, void* stream);
 int mobody_peer_ack(const mobody_peer_desc* p, unsigned int consumed_epoch, void* stream);
 int mobody_peer_wait(const mobody_peer_desc* p, void* stream);
 

@@ -135,6 +135,7 @@ def lib():
         L.mobody_peer_slot_floats.argtypes = [C.c_longlong, C.c_int]
         L.mobody_peer_buffer_bytes.restype = C.c_longlong
         L.mobody_peer_buffer_bytes.argtypes = [C.c_int, C.c_longlong, C.c_int]
+        L.mobody_peer_header.argtypes = [C.POINTER(PeerDesc), C.c_void_p, C.c_void_p, C.c_void_p]
         L.mobody_peer_ack.argtypes = [C.POINTER(PeerDesc), C.c_uint, C.c_void_p]
         L.mobody_peer_wait.argtypes = [C.POINTER(PeerDesc), C.c_void_p]
         L.mobody_peer_slot.argtypes = [C.POINTER(PeerDesc), C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]

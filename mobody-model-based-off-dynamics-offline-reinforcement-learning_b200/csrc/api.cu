@@ -48,6 +48,7 @@ long long mb_peer_buffer_bytes(int world, long long cap_rows, int W);
 const char* mb_peer_slot(const mobody_peer_desc* p, int r, float** rows, int** header);
 const char* mb_peer_ack_launch(const mobody_peer_desc* p, unsigned int consumed, cudaStream_t st);
 const char* mb_peer_wait_launch(const mobody_peer_desc* p, cudaStream_t st);
+const char* mb_peer_header_launch(const mobody_peer_desc* p, const int* kept_dev, const double* stats_dev, cudaStream_t st);
 const char* mb_peer_push_launch(const mobody_peer_desc* p, const int* kept_dev, const double* stats_dev, cudaStream_t st);
 const char* mb_gemm_selftest_launch(const float* A, const float* B, int M, int N, int K, int a_src, int b_src, int lda, int ldb,
                                     float* C, cudaStream_t st);
@@ -307,6 +308,11 @@ int mobody_peer_push(const mobody_peer_desc* p, const int* kept_dev, const doubl
 long long mobody_peer_slot_floats(long long cap_rows, int W) { return (cap_rows < 1 || W < 5) ? 0 : mb_peer_slot_floats(cap_rows, W); }
 long long mobody_peer_buffer_bytes(int world, long long cap_rows, int W) {
   return (world < 1 || world > MOBODY_MAX_PEERS || cap_rows < 1 || W < 5) ? 0 : mb_peer_buffer_bytes(world, cap_rows, W);
+}
+int mobody_peer_header(const mobody_peer_desc* p, const int* kept_dev, const double* stats_dev, void* stream) {
+  const char* err = mb_peer_header_launch(p, kept_dev, stats_dev, (cudaStream_t)stream);
+  if (err) return fail(MOBODY_ERR_ARG, err);
+  return check_launch("mobody_peer_header");
 }
 int mobody_peer_slot(const mobody_peer_desc* p, int r, float** rows, int** header) {
   if (const char* e = mb_peer_slot(p, r, rows, header)) return fail(MOBODY_ERR_ARG, e);

@@ -95,6 +95,15 @@ __global__ void __launch_bounds__(512) peer_push_kernel(const PushArgs a) {
   if (threadIdx.x == 0) *ticket = 0u;
 }
 
+// Header of this rank's slot, written LOCALLY (the copy-engine push ships the whole slot, header row included)
+__global__ void peer_header_kernel(int* __restrict__ h, const int* __restrict__ m_dev, long long m_cap, const double* __restrict__ stats) {
+  if (threadIdx.x == 0) {
+    const long long m = min((long long)*m_dev, m_cap), produced = (long long)stats[1];
+    h[0] = (int)m; h[1] = (int)(produced & 0xffffffffLL); h[2] = (int)(produced >> 32);
+    h[3] = __double2loint(stats[0]); h[4] = __double2hiint(stats[0]);
+  }
+}
+
 __global__ void peer_wait_kernel(const unsigned* __restrict__ flags_local, int world, unsigned epoch) {
   if ((int)threadIdx.x < world) {
     const volatile unsigned* f = flags_local;
@@ -133,6 +142,14 @@ const char* mb_peer_slot(const mobody_peer_desc* p, int r, float** rows, int** h
   float* slot = reinterpret_cast<float*>(p->base[p->rank]) + (long long)(p->epoch & 1u) * L.half_floats + (long long)r * L.slot_floats;
   if (rows) *rows = slot;
   if (header) *header = reinterpret_cast<int*>(slot + p->cap_rows * p->W);
+  return nullptr;
+}
+const char* mb_peer_header_launch(const mobody_peer_desc* p, const int* kept_dev, const double* stats_dev, cudaStream_t st) {
+  if (const char* e = check_peer(p)) return e;
+  if (!kept_dev || !stats_dev) return "null kept / stats pointer";
+  float* rows; int* header;
+  if (const char* e = mb_peer_slot(p, p->rank, &rows, &header)) return e;
+  peer::peer_header_kernel<<<1, 32, 0, st>>>(header, kept_dev, p->cap_rows, stats_dev);
   return nullptr;
 }
 const char* mb_peer_ack_launch(const mobody_peer_desc* p, unsigned int consumed, cudaStream_t st) {

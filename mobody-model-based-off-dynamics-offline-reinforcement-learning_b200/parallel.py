@@ -24,6 +24,31 @@ import torch.distributed as dist
 KEYS = ("obss", "actions", "next_obss", "rewards", "terminals", "penalty")   # column order of a packed slab
 
 
+class _StreamMemOps:
+    """cuStreamWaitValue32 / cuStreamWriteValue32 (cuda-python): flags awaited and raised IN STREAM ORDER by the front end,
+    with no kernel -- a fused step kernel fills every SM completely (228 KB of shared memory), so even a one-warp flag kernel
+    has to wait for a tile to finish and then pushes that SM's next tile back."""
+
+    def __init__(self):
+        from cuda.bindings import driver as drv
+        self.drv = drv
+        self.geq = drv.CUstreamWaitValue_flags.CU_STREAM_WAIT_VALUE_GEQ
+        self.wdef = drv.CUstreamWriteValue_flags.CU_STREAM_WRITE_VALUE_DEFAULT
+
+    def _ok(self, res, what):
+        code = res[0] if isinstance(res, tuple) else res
+        if int(code) != 0:
+            raise RuntimeError(f"mobody_b200: {what} failed with CUresult {int(code)}")
+
+    def wait_geq(self, stream, addr, value):
+        self._ok(self.drv.cuStreamWaitValue32(self.drv.CUstream(int(stream.cuda_stream)), self.drv.CUdeviceptr(int(addr)), int(value), self.geq),
+                 "cuStreamWaitValue32")
+
+    def write(self, stream, addr, value):
+        self._ok(self.drv.cuStreamWriteValue32(self.drv.CUstream(int(stream.cuda_stream)), self.drv.CUdeviceptr(int(addr)), int(value), self.wdef),
+                 "cuStreamWriteValue32")
+
+
 def shard_range(n, rank, world):
     """Contiguous global-row range [lo, hi) of ``rank``: sizes differ by at most one, ranges tile [0, n)."""
     base, rem = divmod(int(n), int(world))
@@ -132,6 +157,27 @@ class PeerExchange:
         if ptrs is None:
             raise RuntimeError(f"PeerExchange: unknown mode {mode!r}")
         self.ptrs = ptrs
+        # every rank's buffer as a tensor in THIS process (device-to-device copies of whole slots: the copy-engine push)
+        if self.mode == "symmetric_memory":
+            self.peer_views = [self.buf if r == self.rank else self._keep.get_buffer(r, (n_floats,), torch.float32) for r in range(self.world)]
+        else:
+            self.peer_views = list(self._keep)
+        self.flags_off = int(lib.mobody_peer_buffer_bytes(self.world, self.cap_rows, self.W)) - 128     # arrive[8] | ack[8] | ticket | pad
+        # push = "dma": whole slots by the copy engines + stream memory operations for the flags (no SM involved);
+        #        "sm":  the narrow NVLink-store kernel (only the kept rows travel; one multicast store when the fabric offers it)
+        # Measured (100 000 rows per rank, two compute streams): N=2 dma 164.7 M vs sm 161.9 M transitions/s; N=4 304.5 vs 309.4;
+        # N=8 541.7 vs 590.6 -- N - 1 unicast copies of the slot against ONE multicast store stream.  Default: the copy engines for
+        # two ranks or when the fabric offers no multicast mapping, the multicast kernel otherwise.
+        self.push = os.environ.get("MOBODY_PUSH") or ("dma" if (self.world <= 2 or not self.multicast) else "sm")
+        self.memops = None
+        if self.push == "dma":
+            try:
+                self.memops = _StreamMemOps()
+                probe = torch.cuda.Stream(self.device)
+                self.memops.write(probe, self.ptrs[self.rank] + self.flags_off + 4 * 20, 0)            # a pad word of the local flag block
+                probe.synchronize()
+            except Exception as e:                                   # noqa: BLE001 -- no stream memory operations here: kernel push
+                self._memops_error, self.memops, self.push = repr(e), None, "sm"
         self.epoch = 0
         self._push_done = [None, None]                               # event of the push kernel that last read workspace slot parity
         # the push kernel is short and bandwidth bound: a high-priority side stream lets its few CTAs take the first SMs that
@@ -174,9 +220,17 @@ class GatheredRollout:
 
     def wait(self):
         from . import _ffi
+        if os.environ.get("MOBODY_PROBE", "") == "nopush":
+            return self
         if not self._waited:
-            d = self.ex.desc(self.epoch)
-            _ffi.check(_ffi.lib().mobody_peer_wait(C.byref(d), _ffi.stream_ptr(self.ex.device)))
+            ex = self.ex
+            if ex.push == "dma":
+                cur = torch.cuda.current_stream(ex.device)
+                for r in range(ex.world):
+                    ex.memops.wait_geq(cur, ex.ptrs[ex.rank] + ex.flags_off + 4 * r, self.epoch)
+            else:
+                d = ex.desc(self.epoch)
+                _ffi.check(_ffi.lib().mobody_peer_wait(C.byref(d), _ffi.stream_ptr(ex.device)))
             self._waited = True
         return self
 
@@ -221,8 +275,14 @@ def p2p_rollout(agent, local, T, use_trg, row0, cap, *, group=None, step0=None, 
     e = ex.epoch
     cur = torch.cuda.current_stream(dev)
     pd = ex.desc(e, ctas or ex.ctas)
-    if e > 2:    # everything enqueued on this stream so far has consumed epoch e - 2: peers may overwrite that half now
-        _ffi.check(lib.mobody_peer_ack(C.byref(pd), e - 2, _ffi.stream_ptr(dev)))
+    probe = os.environ.get("MOBODY_PROBE", "")    # timing experiments only: 'nopush' = rollout into the symmetric slot, nothing else
+    dma, mo = ex.push == "dma", ex.memops
+    if e > 2 and probe != "nopush":    # everything enqueued on this stream so far has consumed epoch e - 2: peers may overwrite that half now
+        if dma:
+            for r in range(ex.world):
+                mo.write(cur, ex.ptrs[r] + ex.flags_off + 32 + 4 * ex.rank, e - 2)
+        else:
+            _ffi.check(lib.mobody_peer_ack(C.byref(pd), e - 2, _ffi.stream_ptr(dev)))
     if ex._push_done[e & 1] is not None:
         cur.wait_event(ex._push_done[e & 1])                         # the push of epoch e - 2 read the slot / counters we are about to reuse
     B = local.shape[0]
@@ -232,7 +292,27 @@ def p2p_rollout(agent, local, T, use_trg, row0, cap, *, group=None, step0=None, 
     d, keep = agent._rollout_desc(local, T, use_trg, ws, rows[ex.rank], row0=row0, step0=step0, verify_images=verify_images)   # packs into OUR slot of the local buffer
     _ffi.check(lib.mobody_rollout(C.byref(d), _ffi.stream_ptr(dev)))
     kept_dev, stats_dev = ws["counts"][T + 1:T + 2], ws["stats"][:2]
-    if ex.overlap:
+    if probe == "nopush":
+        done = torch.cuda.Event(); done.record(cur)
+    elif dma:
+        # copy-engine push: header row written locally, then the whole slot goes to every peer as ONE device-to-device copy
+        # each, bracketed by stream memory operations (peer acked epoch e - 2 -> copy -> arrive flag = e).  No SM involved.
+        _ffi.check(lib.mobody_peer_header(C.byref(pd), kept_dev.data_ptr(), stats_dev.data_ptr(), _ffi.stream_ptr(dev)))
+        ev = torch.cuda.Event(); ev.record(cur)
+        side = ex._side
+        side.wait_event(ev)
+        off = (e & 1) * ex.world * ex.slot_floats + ex.rank * ex.slot_floats
+        src = ex.buf[off:off + ex.slot_floats]
+        with torch.cuda.stream(side):
+            for k in range(1, ex.world):
+                r = (ex.rank + k) % ex.world                          # staggered: at any moment every rank is written by one peer
+                if e > 2:
+                    mo.wait_geq(side, ex.ptrs[ex.rank] + ex.flags_off + 32 + 4 * r, e - 2)
+                ex.peer_views[r][off:off + ex.slot_floats].copy_(src, non_blocking=True)
+                mo.write(side, ex.ptrs[r] + ex.flags_off + 4 * ex.rank, e)
+            mo.write(side, ex.ptrs[ex.rank] + ex.flags_off + 4 * ex.rank, e)
+        done = torch.cuda.Event(); done.record(side)
+    elif ex.overlap:
         ev = torch.cuda.Event(); ev.record(cur)
         ex._side.wait_event(ev)
         _ffi.check(lib.mobody_peer_push(C.byref(pd), kept_dev.data_ptr(), stats_dev.data_ptr(), C.c_void_p(ex._side.cuda_stream)))
@@ -243,7 +323,7 @@ def p2p_rollout(agent, local, T, use_trg, row0, cap, *, group=None, step0=None, 
     ex._push_done[e & 1] = done
     ex._descs[e & 1] = (d, keep, pd)                                 # keep-alive until the slot is reused
     info = {"kept_dev": kept_dev, "counts_dev": ws["counts"], "stats_dev": stats_dev, "capacity": cap,
-            "world": ex.world, "exchange": ex.mode + ("+multicast" if ex.multicast else "")}
+            "world": ex.world, "exchange": ex.mode + ("+copy-engine push" if ex.push == "dma" else "+multicast" if ex.multicast else "")}
     return GatheredRollout(ex, e, [S, A, S, 1, 1, 1], info)
 
 
@@ -276,7 +356,7 @@ def sharded_rollout_host(agent, host_shard, rollout_length, use_trg=True, *, gro
 
 def _exchange_mode(agent):
     for ex in getattr(agent, "_peer_exchanges", {}).values():
-        return ex.mode + ("+multicast" if ex.multicast else "")
+        return ex.mode + ("+copy-engine push" if ex.push == "dma" else "+multicast" if ex.multicast else "")
     return None
 
 
