@@ -213,7 +213,7 @@ typedef struct mobody_peer_desc {
   long long cap_rows;             /* rows per slot (>= T*B of the largest shard)                                        */
   int W;                          /* floats per packed transition (2S+A+3)                                              */
   unsigned int epoch;             /* exchange number, 1, 2, 3, ... (monotone; same on every rank)                       */
-  int ctas;                       /* CTAs of the push kernel (0 = default 8): kept small, it runs beside the next rollout */
+  int ctas;                       /* CTAs of the push kernel (0 = default: 64 CTAs of 128 threads, small enough to sit beside a step tile) */
 } mobody_peer_desc;
 long long mobody_peer_slot_floats(long long cap_rows, int W);     /* floats per slot incl. header row, padded to 16 B   */
 long long mobody_peer_buffer_bytes(int world, long long cap_rows, int W);   /* receive buffer: 2 halves + flag block    */

@@ -13,6 +13,7 @@
 //   flag block = unsigned arrive[8] (arrive[r] = last epoch rank r delivered here), unsigned ack[8] (ack[r] = last epoch
 //               rank r has finished consuming in ITS buffer), unsigned ticket
 #include "common.cuh"
+#include <stdlib.h>
 #include "../../include/mobody_b200.h"
 
 namespace peer {
@@ -178,8 +179,12 @@ const char* mb_peer_push_launch(const mobody_peer_desc* p, const int* kept_dev, 
   }
   a.src = a.dst[p->rank];
   a.mc_dst = p->multicast ? reinterpret_cast<float*>(p->multicast) + slot_off : nullptr;
-  int ctas = p->ctas > 0 ? p->ctas : 8;
-  if (ctas > 148) ctas = 148;
-  peer::peer_push_kernel<<<ctas, 512, 0, st>>>(a);
+  // A fused step kernel leaves ~5 KB of shared memory and ~10 K registers per SM: a push CTA of 128 threads (40 registers,
+  // 1 KB of shared memory) fits BESIDE a step tile, a 512-thread one has to wait for a tile to finish and then holds that
+  // SM's next tile back for the length of the push (MOBODY_PUSH_THREADS / MOBODY_PUSH_CTAS for A/B runs).
+  static const int threads = [] { const char* e = getenv("MOBODY_PUSH_THREADS"); const int v = e ? atoi(e) : 0; return (v >= 32 && v <= 512) ? (v & ~31) : 128; }();
+  int ctas = p->ctas > 0 ? p->ctas : 64;        // measured: 128 x 64 vs 512 x 8: N=2 162.2 vs 160.7, N=8 591.4 vs 588.5 M transitions/s
+  if (ctas > 592) ctas = 592;
+  peer::peer_push_kernel<<<ctas, threads, 0, st>>>(a);
   return nullptr;
 }
