@@ -165,8 +165,8 @@ class PeerExchange:
         self.flags_off = int(lib.mobody_peer_buffer_bytes(self.world, self.cap_rows, self.W)) - 128     # arrive[8] | ack[8] | ticket | pad
         # push = "dma": whole slots by the copy engines + stream memory operations for the flags (no SM involved);
         #        "sm":  the narrow NVLink-store kernel (only the kept rows travel; one multicast store when the fabric offers it)
-        # Measured (100 000 rows per rank, two compute streams): N=2 dma 164.7 M vs sm 161.9 M transitions/s; N=4 304.5 vs 309.4;
-        # N=8 541.7 vs 590.6 -- N - 1 unicast copies of the slot against ONE multicast store stream.  Default: the copy engines for
+        # Measured (100 000 rows per rank, two compute streams): N=2 dma 161.9-164.7 M vs sm 160.7-162.4 M transitions/s (noise);
+        # N=4 304.5 vs 309.4; N=8 541.7 vs 590.6 -- N - 1 unicast copies of the slot against ONE multicast store stream.  Default: the copy engines for
         # two ranks or when the fabric offers no multicast mapping, the multicast kernel otherwise.
         self.push = os.environ.get("MOBODY_PUSH") or ("dma" if (self.world <= 2 or not self.multicast) else "sm")
         self.memops = None
