@@ -757,7 +757,12 @@ def main():
                      "traffic": traffic, "traffic_source": traffic_src,
                      "kernel": "fused rollout step", "kernel_ms": k_ms, "peak_source": pk_src + " bf16 burst",
                      "mma_passes_per_gemm": split, "frac_of_mma_issued": ach * split / peak,
-                     "flop_per_transition": flop, "algorithmic_io_bytes": Bn * (3 * S + A + 3) * 4},
+                     "flop_per_transition": flop, "algorithmic_io_bytes": Bn * (3 * S + A + 3) * 4,
+                     # the same algorithmic work over the whole timed loop (this rank's transitions / loop time): with two
+                     # streams the partial last round of one launch is filled by the next launch, which the single-launch
+                     # timing above cannot show
+                     "per_rollout_in_loop": {"ms": dev_ms / args.steps, "achieved": flop * (n_trans / world) / (dev_ms * 1e-3) / 1e12,
+                                             "frac": flop * (n_trans / world) / (dev_ms * 1e-3) / 1e12 / peak}},
         "clocks": clocks, "wall_s": wall,
     }
     if world > 1:
