@@ -991,7 +991,7 @@ const char* mb_train_adam_launch(const trn::AdamArgs& a, cudaStream_t st) {
 
 // ---------------- whole train step (C ABI: mobody_train_step) ----------------
 struct TrainWs {   // float offsets into the workspace
-  size_t Hq[2][2], Dq[2][2], d3[2], part, Hp[2], Dp[2], api, a2, qk[2], qtk[2], qv[2], qh[2], gak[2], d3p, scal, part2, cnt, gq[2][6], gp[6], T[2], img[17], total;
+  size_t Hq[2][2], Dq[2][2], d3[2], part, Hp[2], Dp[2], api, a2, qk[2], qtk[2], qv[2], qh[2], gak[2], d3p, scal, part2, cnt, gq[2][6], gp[6], T[2], img[17], pa[5], total;
   int ntiles;
 };
 static TrainWs train_ws(int N, int S, int A, int nsplit) {
@@ -1015,6 +1015,9 @@ static TrainWs train_ws(int N, int S, int A, int nsplit) {
     const int ik[17] = {S, 256, 256, S + A, S + A, 256, 256, S + A, S + A, 256, 256, 256, 256, A, 256, 256, 256};
     const int inp[17] = {256, 256, 64, 256, 256, 256, 256, 256, 256, 256, 256, 256, 256, 256, 256, 64, 64};
     for (int i = 0; i < 17; ++i) w.img[i] = take(ug::packed_floats(ik[i], inp[i]));
+    // packed A images of the five layer-1 outputs that feed a 256-deep layer (T0, T1, Hq[0][0], Hq[1][0], Hp[0]): emitted by the producing
+    // launch's epilogue, streamed by the consumer's TMA
+    for (int i = 0; i < 5; ++i) w.pa[i] = take((size_t)((N + 127) / 128) * ug::packed_a_tile_floats(256));
   }
   w.total = o;
   return w;
@@ -1113,6 +1116,16 @@ static const char* mb_train_step_tc_launch(const mobody_train_desc& d, const Tra
   float* img[17];
   for (int i = 0; i < 17; ++i) img[i] = ws + w.img[i];
   auto P = [&](ug::Job j, int slot) { return use_img ? packed(j, img[slot]) : j; };
+  // Activations as packed images too (the producing launch's epilogue emits the TF32 hi / lo stage image, the 256-deep consumer
+  // streams both operands by TMA from one thread): bit-identical, and SLOWER -- 2 050 against 2 260 updates/s at batch 4096: ten
+  // layer-1 jobs write 21 MB of image each and their consumers read it back (+420 MB of HBM traffic per update) for a K loop
+  // that was not the whole problem.  Opt-in (MOBODY_TRAIN_PACKED_A=1) for A/B runs.
+  static const bool use_pa = use_img && [] { const char* v = getenv("MOBODY_TRAIN_PACKED_A"); return v && v[0] == '1'; }();
+  float* pa[5];
+  for (int i = 0; i < 5; ++i) pa[i] = ws + w.pa[i];
+  enum { PA_T0 = 0, PA_T1, PA_Q0, PA_Q1, PA_P0 };
+  auto EMIT = [&](ug::Job j, int slot) { if (use_pa) j.apack = pa[slot]; return j; };                 // producer: also write the packed A image
+  auto FROM = [&](ug::Job j, int slot) { if (use_pa) { j.A = pa[slot]; j.a_src = ug::SRC_PACKED; } return j; };   // consumer: stream it
   auto pack_q = [&](ug::PackArgs& pa, bool with_slices) {
     for (int k = 0; k < 2; ++k) {
       pa.job[pa.njobs++] = pack_job(q[k].w[0], SA, ug::SRC_KCONTIG, 256, SA, 256, img[3 + k]);
@@ -1136,12 +1149,13 @@ static const char* mb_train_step_tc_launch(const mobody_train_desc& d, const Tra
     if ((e = mb_pack_b_launch(pa, st))) return e;
   }
   // ---- critic forward.  layer 1 of pi(s'), Q1(s,a), Q2(s,a), pi(s) side by side; then layer 2 (+ Q heads); then the policy tails ----
-  if ((e = run_gemms(st, 1, P(fwd_job(X + SA, rw, N, S, pi.w[0], pi.b[0], 256, T[0]), 0), P(fwd_job(X, rw, N, SA, q[0].w[0], q[0].b[0], 256, Hq[0][0]), 3),
-                     P(fwd_job(X, rw, N, SA, q[1].w[0], q[1].b[0], 256, Hq[1][0]), 4), P(fwd_job(X, rw, N, S, pi.w[0], pi.b[0], 256, Hp[0]), 0)))) return e;
+  if ((e = run_gemms(st, 1, EMIT(P(fwd_job(X + SA, rw, N, S, pi.w[0], pi.b[0], 256, T[0]), 0), PA_T0), EMIT(P(fwd_job(X, rw, N, SA, q[0].w[0], q[0].b[0], 256, Hq[0][0]), 3), PA_Q0),
+                     EMIT(P(fwd_job(X, rw, N, SA, q[1].w[0], q[1].b[0], 256, Hq[1][0]), 4), PA_Q1), EMIT(P(fwd_job(X, rw, N, S, pi.w[0], pi.b[0], 256, Hp[0]), 0), PA_P0)))) return e;
   {
     ug::Job j1 = fwd_job(Hq[0][0], 256, N, 256, q[0].w[1], q[0].b[1], 256, Hq[0][1]), j2 = fwd_job(Hq[1][0], 256, N, 256, q[1].w[1], q[1].b[1], 256, Hq[1][1]);
     j1.epi = j2.epi = ug::EPI_HEAD; j1.w3 = q[0].w[2]; j1.b3 = q[0].b[2]; j1.out1 = qk[0]; j2.w3 = q[1].w[2]; j2.b3 = q[1].b[2]; j2.out1 = qk[1];
-    if ((e = run_gemms(st, 1, P(fwd_job(T[0], 256, N, 256, pi.w[1], pi.b[1], 256, T[1]), 1), P(j1, 5), P(j2, 6), P(fwd_job(Hp[0], 256, N, 256, pi.w[1], pi.b[1], 256, Hp[1]), 1)))) return e;
+    if ((e = run_gemms(st, 1, FROM(P(fwd_job(T[0], 256, N, 256, pi.w[1], pi.b[1], 256, T[1]), 1), PA_T0), FROM(P(j1, 5), PA_Q0), FROM(P(j2, 6), PA_Q1),
+                       FROM(P(fwd_job(Hp[0], 256, N, 256, pi.w[1], pi.b[1], 256, Hp[1]), 1), PA_P0)))) return e;
   }
   {
     trn::RowDotArgs rd{}; rd.njobs = 2; rd.A = A; rd.scale = d.max_action; rd.tanh_act = 1;
@@ -1152,11 +1166,11 @@ static const char* mb_train_step_tc_launch(const mobody_train_desc& d, const Tra
   {
     ug::Job j1 = fwd_job(X + SA, rw, N, SA, qt[0].w[0], qt[0].b[0], 256, T[0]), j2 = fwd_job(X + SA, rw, N, SA, qt[1].w[0], qt[1].b[0], 256, T[1]);
     j1.A2 = j2.A2 = a2; j1.lda2 = j2.lda2 = A; j1.ksplit = j2.ksplit = S;
-    if ((e = run_gemms(st, 1, P(j1, 7), P(j2, 8)))) return e;
+    if ((e = run_gemms(st, 1, EMIT(P(j1, 7), PA_T0), EMIT(P(j2, 8), PA_T1)))) return e;
     // layer 2 + head in place is not possible (C would overwrite A of another tile's... no: tiles own their rows) -> no C store at all
     ug::Job h1 = fwd_job(T[0], 256, N, 256, qt[0].w[1], qt[0].b[1], 256, nullptr), h2 = fwd_job(T[1], 256, N, 256, qt[1].w[1], qt[1].b[1], 256, nullptr);
     h1.epi = h2.epi = ug::EPI_HEAD; h1.w3 = qt[0].w[2]; h1.b3 = qt[0].b[2]; h1.out1 = qtk[0]; h2.w3 = qt[1].w[2]; h2.b3 = qt[1].b[2]; h2.out1 = qtk[1];
-    if ((e = run_gemms(st, 1, P(h1, 9), P(h2, 10)))) return e;
+    if ((e = run_gemms(st, 1, FROM(P(h1, 9), PA_T0), FROM(P(h2, 10), PA_T1)))) return e;
   }
   // ---- TD target + MSE gradient, head backward, backward-data ----
   {
@@ -1204,11 +1218,12 @@ static const char* mb_train_step_tc_launch(const mobody_train_desc& d, const Tra
   {
     ug::Job j1 = fwd_job(X, rw, N, SA, q[0].w[0], q[0].b[0], 256, Hq[0][0]), j2 = fwd_job(X, rw, N, SA, q[1].w[0], q[1].b[0], 256, Hq[1][0]);
     j1.A2 = j2.A2 = api; j1.lda2 = j2.lda2 = A; j1.ksplit = j2.ksplit = S;
-    if ((e = run_gemms(st, 1, P(j1, 3), P(j2, 4), P(fwd_job(X, rw, nt, SA, q[0].w[0], q[0].b[0], 256, T[0]), 3), P(fwd_job(X, rw, nt, SA, q[1].w[0], q[1].b[0], 256, T[1]), 4)))) return e;
+    if ((e = run_gemms(st, 1, EMIT(P(j1, 3), PA_Q0), EMIT(P(j2, 4), PA_Q1), EMIT(P(fwd_job(X, rw, nt, SA, q[0].w[0], q[0].b[0], 256, T[0]), 3), PA_T0),
+                       EMIT(P(fwd_job(X, rw, nt, SA, q[1].w[0], q[1].b[0], 256, T[1]), 4), PA_T1)))) return e;
     ug::Job h[4] = {fwd_job(Hq[0][0], 256, N, 256, q[0].w[1], q[0].b[1], 256, Hq[0][1]), fwd_job(Hq[1][0], 256, N, 256, q[1].w[1], q[1].b[1], 256, Hq[1][1]),
                     fwd_job(T[0], 256, nt, 256, q[0].w[1], q[0].b[1], 256, nullptr), fwd_job(T[1], 256, nt, 256, q[1].w[1], q[1].b[1], 256, nullptr)};
     for (int i = 0; i < 4; ++i) { h[i].epi = ug::EPI_HEAD; h[i].w3 = q[i & 1].w[2]; h[i].b3 = q[i & 1].b[2]; h[i].out1 = i < 2 ? qv[i] : qh[i - 2]; }
-    if ((e = run_gemms(st, 1, P(h[0], 5), P(h[1], 6), P(h[2], 5), P(h[3], 6)))) return e;
+    if ((e = run_gemms(st, 1, FROM(P(h[0], 5), PA_Q0), FROM(P(h[1], 6), PA_Q1), FROM(P(h[2], 5), PA_T0), FROM(P(h[3], 6), PA_T1)))) return e;
   }
   trn::ActorArgs ac{};
   ac.X = X; ac.N = N; ac.n_true = nt; ac.S = S; ac.A = A; ac.rw = rw; ac.max_action = d.max_action;

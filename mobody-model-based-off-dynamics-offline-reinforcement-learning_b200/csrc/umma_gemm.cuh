@@ -27,7 +27,8 @@ constexpr int KC = 16;           // K per pipeline stage = 2 UMMA K steps of 8 (
 constexpr int NT = 256;          // threads per CTA
 
 enum { SRC_KCONTIG = 0, SRC_RCONTIG = 1,
-       SRC_PACKED = 2 };   // B only: pre-split TF32 hi/lo image in stage layout (pack_b_kernel), streamed by TMA bulk copies
+       SRC_PACKED = 2 };   // pre-split TF32 hi/lo image in stage layout, streamed by TMA bulk copies: B from pack_b_kernel, A from a
+                           // producing launch's epilogue (Job::apack); a packed A requires a packed B
 // Epilogue kinds.  EPI_STORE and EPI_HEAD share one compiled epilogue (a job without w3 has no head), the others are their own
 // instantiations: the epilogue body is unrolled per 32 x 32 block, so every variant compiled into it is paid in issue slots.
 enum { EPI_STORE = 0,   // C = act(acc + bias)                       -> C[m][n]
@@ -48,10 +49,13 @@ struct Job {
   const float* w3; const float* b3;
   float* C; int ldc; float* out1; float* db; float scale;
   float* pre;                                                           // EPI_SWISH: pre-activation copy, same pitch as C (may be null)
+  float* apack;   // EPI_STORE / EPI_HEAD: also emit the output tile as the NEXT layer's packed A image (TF32 hi / lo planes in stage layout,
+                  // [row tile][chunk][plane][kgroup][row][4 k]); a consumer with a_src = SRC_PACKED streams it by TMA -- no operand conversion
 };
 struct Args { Job job[8]; int njobs, nsplit; };
 
 __host__ __device__ inline int rup16(int x) { return (x + 15) & ~15; }
+__host__ __device__ inline size_t packed_a_tile_floats(int K) { return (size_t)((K + KC - 1) / KC) * 2 * BM * (KC / 4) * 4; }   // one 128-row tile of a packed A image
 __host__ __device__ inline size_t stage_bytes(int np) { return (size_t)2 * (BM + np) * (KC / 4) * 16; }   // hi + lo planes of A and B
 
 __device__ __forceinline__ float swish_f(float x) { return x / (1.f + expf(-x)); }
@@ -244,12 +248,49 @@ __global__ void __launch_bounds__(NT, 2) gemm_kernel(const __grid_constant__ Arg
       if (c + 1 == nchunks) tc::umma_commit(&bar_done);
     } else if (B_SRC == SRC_PACKED && tid == 32 && c + 1 < nchunks) tma_b(c + 1);
   };
+  if constexpr (A_SRC == SRC_PACKED) {
+    // Both operands arrive as packed images: ONE thread requests chunk c + 1 (A and B, one barrier) as soon as the MMAs of
+    // chunk c - 1 have left that stage, then issues the MMAs of chunk c.  No operand conversion, no block barrier in the loop.
+    static_assert(B_SRC == SRC_PACKED, "a packed A operand needs a packed B operand");
+    if (tid == 0) {
+      const unsigned char* aimg = reinterpret_cast<const unsigned char*>(jb.A) + (size_t)blockIdx.x * packed_a_tile_floats(jb.K) * 4;
+      auto tma_ab = [&](int c) {
+        const int nb = c & 1;
+        if (c >= 2) tc::mbar_wait(&bar_free[nb], (uint32_t)(((c >> 1) - 1) & 1));
+        tc::mbar_arrive_expect_tx(&bar_fullb[nb], 2 * A_PLANE + 2 * B_PLANE);
+        tc::bulk_g2s(smem + (size_t)nb * STAGE, aimg + (size_t)(kbeg / KC + c) * (2 * A_PLANE), 2 * A_PLANE, &bar_fullb[nb]);
+        tc::bulk_g2s(smem + (size_t)nb * STAGE + 2 * A_PLANE, reinterpret_cast<const unsigned char*>(jb.B) + (size_t)(kbeg / KC + c) * (2 * B_PLANE),
+                     2 * B_PLANE, &bar_fullb[nb]);
+      };
+      if (nchunks > 0) tma_ab(0);
+#pragma unroll 1
+      for (int c = 0; c < nchunks; ++c) {
+        if (c + 1 < nchunks) tma_ab(c + 1);
+        const int buf = c & 1;
+        tc::mbar_wait(&bar_fullb[buf], (uint32_t)((c >> 1) & 1));
+        tc::tc_fence_after();
+        const uint32_t a0 = tc::smem_u32(smem + (size_t)buf * STAGE), b0 = a0 + 2 * A_PLANE;
+#pragma unroll
+        for (int s2 = 0; s2 < KC / 8; ++s2) {
+          const uint32_t ao = a0 + (uint32_t)s2 * 2u * (BM * 16), bo = b0 + (uint32_t)s2 * 2u * (NP * 16);
+          const uint64_t ah = tc::make_smem_desc(ao, BM * 16, 128), al = tc::make_smem_desc(ao + A_PLANE, BM * 16, 128);
+          const uint64_t bh = tc::make_smem_desc(bo, NP * 16, 128), bl = tc::make_smem_desc(bo + B_PLANE, NP * 16, 128);
+          umma_tf32(tmem, al, bh, idesc, (c > 0 || s2 > 0) ? 1u : 0u);
+          umma_tf32(tmem, ah, bl, idesc, 1u);
+          umma_tf32(tmem, ah, bh, idesc, 1u);
+        }
+        tc::umma_commit(&bar_free[buf]);
+        if (c + 1 == nchunks) tc::umma_commit(&bar_done);
+      }
+    }
+  } else {
   if (nchunks > 0) { fetch(oa0, ob0, 0); if (B_SRC == SRC_PACKED && tid == 32) tma_b(0); }
   if (nchunks > 1) fetch(oa1, ob1, 1);
 #pragma unroll 1
   for (int c = 0; c < nchunks; c += 2) {
     step(oa0, ob0, c);
     if (c + 1 < nchunks) step(oa1, ob1, c + 1);
+  }
   }
 #ifdef UG_TRACE
   t_[2] = clock64();
@@ -298,6 +339,17 @@ __global__ void __launch_bounds__(NT, 2) gemm_kernel(const __grid_constant__ Arg
     else {
 #pragma unroll
       for (int jj = 0; jj < 32; ++jj) x[jj] = 0u;
+    }
+    if (EPI == EPI_STORE && jb.apack) {   // the next layer's packed A image: this lane's row, 8 k-groups of this block (coalesced along rows)
+      unsigned char* img = reinterpret_cast<unsigned char*>(jb.apack) + (size_t)blockIdx.x * packed_a_tile_floats(jb.N) * 4;
+#pragma unroll
+      for (int jj = 0; jj < 32; jj += 4) {
+        const int nn = n0 + jj;
+        float pv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const float t = __uint_as_float(x[jj + i]) + bias_s[nn + i]; pv[i] = jb.relu ? fmaxf(t, 0.f) : t; }
+        put_unit(img + (size_t)(nn / KC) * (2 * A_PLANE), A_PLANE, (uint32_t)((nn % KC) / 4) * (BM * 16) + (uint32_t)(q * 32 + lane) * 16, pv);
+      }
     }
 #pragma unroll
     for (int jj = 0; jj < 32; jj += 4)

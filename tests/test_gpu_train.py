@@ -213,6 +213,7 @@ def test_launch_mode_and_tiling_switches_in_subprocess():
     base = digest(MOBODY_PDL="1")
     assert base == digest(MOBODY_PDL="0")
     assert base == digest(MOBODY_TRAIN_SIDE="0")          # large-batch update: side-stream overlap on / off
+    assert base == digest(MOBODY_TRAIN_PACKED_A="1")      # ... activations streamed as pre-split images (opt-in) or converted on the fly
     assert len(digest(MOBODY_TRAIN_TM="64")) == 64
 
 
