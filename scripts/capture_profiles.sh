@@ -12,18 +12,8 @@ ncu --set full --clock-control none -k regex:"gemm_kernel|head_bwd|rowdot|adam_k
 python scripts/ncu_select.py gpurun_out/${tag}_train4096.ncu-rep gpurun_out/${tag}_train4096_ncu_full_selected.csv
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"^(critic|actor|policy|wgrad|adam|sample_rows|head_bwd|rowdot|td)_" -s 30 -c 22 --csv --log-file gpurun_out/${tag}_train128_launches.csv python scripts/train_profile.py 128 > gpurun_out/${tag}_ncu4.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"^(critic|actor|policy|wgrad|adam|sample_rows|head_bwd|rowdot|td|gemm|pack_b)_" -s 81 -c 54 --csv --log-file gpurun_out/${tag}_train4096_launches.csv python scripts/train_profile.py 4096 > gpurun_out/${tag}_ncu5.log 2>&1
-# dynamics fitting step: launch list of two mini-batches (43 launches each)
-cat > gpurun_out/_fit_profile.py <<'PY'
-import sys, os
-sys.path.insert(0, "."); sys.path.insert(0, "tests")
-import torch, bench
-import mobody_b200 as mb
-dev = torch.device("cuda:0")
-dyn = bench.build_dynamics(mb, bench.S, bench.A, "bf16x2", dev)
-data = [torch.from_numpy(x).to(dev) for x in bench.fit_batch_data(256)]
-for _ in range(4):
-    sc = dyn.fit_batch(True, *data)
-torch.cuda.synchronize(); print("ok", sc.cpu().tolist())
-PY
-python gpurun_out/_fit_profile.py > gpurun_out/${tag}_fit.log 2>&1 || exit 1
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"^(prep|reparam|combine|fake|lossgrad|loss|finish|dfake|dza|do3|adam|gemm)_kernel" -s 86 -c 86 --csv --log-file gpurun_out/${tag}_dynfit_launches.csv python gpurun_out/_fit_profile.py > gpurun_out/${tag}_ncu6.log 2>&1
+# dynamics fitting step: launch list of two mini-batches (43 launches each) + full capture of one mini-batch's GEMM tiles
+python scripts/fit_profile.py > gpurun_out/${tag}_fit.log 2>&1 || exit 1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"^(prep|reparam|combine|fake|lossgrad|loss|finish|dfake|dza|do3|adam|gemm)_kernel" -s 86 -c 86 --csv --log-file gpurun_out/${tag}_dynfit_launches.csv python scripts/fit_profile.py > gpurun_out/${tag}_ncu6.log 2>&1
+ncu --set full --clock-control none -k regex:"^gemm_kernel" -s 64 -c 32 -o gpurun_out/${tag}_dynfit -f python scripts/fit_profile.py > gpurun_out/${tag}_ncu7.log 2>&1
+python scripts/ncu_select.py gpurun_out/${tag}_dynfit.ncu-rep gpurun_out/${tag}_dynfit_ncu_full_selected.csv
