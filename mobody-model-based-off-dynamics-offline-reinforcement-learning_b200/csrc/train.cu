@@ -1281,7 +1281,9 @@ const char* mb_train_step_launch(const mobody_train_desc& d, cudaStream_t st) {
   if (!d.workspace || d.workspace_bytes < (long long)w.total * 4) return "train step: workspace too small";
   // large batches: every contraction as tcgen05 GEMM tiles (MOBODY_TRAIN_TC=0 keeps the mma.sync path for A/B runs)
   static const bool use_tc = [] { const char* e = getenv("MOBODY_TRAIN_TC"); return !(e && e[0] == '0'); }();
-  static const int tc_rows = [] { const char* e = getenv("MOBODY_TRAIN_TC_ROWS"); return e ? atoi(e) : 148 * 16; }();
+  // cross-over measured on the tuned tiles (S17/A6, updates/s tcgen05 vs mma.sync): 640 rows 4 540 vs 6 435, 1 280 rows 4 350 vs 4 220,
+  // 1 920 rows 3 920 vs 3 340, 2 560 rows 4 180 vs 3 600
+  static const int tc_rows = [] { const char* e = getenv("MOBODY_TRAIN_TC_ROWS"); return e ? atoi(e) : 1280; }();
   if (use_tc && N >= tc_rows) return mb_train_step_tc_launch(d, w, st);
   float* ws = (float*)d.workspace;
   const mobody_mlp_state* qs[2] = {&d.q1, &d.q2};

@@ -186,7 +186,7 @@ class MOBODY(object):
         self.PIPE_ROWS = 2 * sm * 128   # later chunks: two full waves
         self._wave = sm * 128
         import os
-        self.TC_TRAIN_ROWS = int(os.environ.get("MOBODY_TRAIN_TC_ROWS", sm * 16)) if os.environ.get("MOBODY_TRAIN_TC", "1") != "0" else 1 << 62
+        self.TC_TRAIN_ROWS = int(os.environ.get("MOBODY_TRAIN_TC_ROWS", 1280)) if os.environ.get("MOBODY_TRAIN_TC", "1") != "0" else 1 << 62
 
     # ------------------------------------------------------------------ optimizers (mobody.py:127-135)
     _OPT_COUNTER = {"q": "_t_q", "pi": "_t_pi", "cls": "_t_cls"}
