@@ -19,7 +19,7 @@ FIT_SHARED = ("zs1", "zs2", "zs3", "transition1", "transition2", "transition3", 
 class DynamicsFitting(object):
     """Mixed into MOBODYEnsembleDynamics."""
 
-    FIT_NSPLIT = 4
+    FIT_NSPLIT = 8            # K splits of the weight-gradient GEMMs (measured at 7 x 256 rows: 1 -> 1 215, 2 -> 1 541, 4 -> 1 754, 8 -> 1 830, 16 -> 1 780 steps/s)
 
     # ------------------------------------------------------------------ optimiser state
     def _fit_state(self):
