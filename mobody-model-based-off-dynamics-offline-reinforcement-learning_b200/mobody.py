@@ -107,18 +107,21 @@ def _storage_idle(t):
         return False
 
 
-def _wgrad_splits(n_rows, tiles_per_launch, device, sm_count=None, ctas_per_sm=2):
+def _wgrad_splits(n_rows, tiles_per_launch, device, sm_count=None, ctas_per_sm=2, cta_overhead=0.0, per_split=0.0):
     """Row splits of the weight-gradient launches.  A launch runs ``tiles * nsplit`` CTAs of 128 x 64 outputs, two per
     SM, each walking its rows in chunks of 32: pick the split count (<= 64) that minimises rounds x chunks per CTA
     summed over the launches of an update (tiles: critic 2 x (8 + 2), actor 8 + 2), i.e. avoid a nearly empty last
-    round.  Any value gives the same result up to fp32 summation order; the order is fixed for a given value."""
+    round.  Any value gives the same result up to fp32 summation order; the order is fixed for a given value.
+    ``cta_overhead`` (a CTA's fixed cost -- set-up, epilogue of a whole output tile -- in units of one 32-row chunk) and
+    ``per_split`` (what one more partial costs the Adam launches, same unit) make the model prefer fewer, longer splits:
+    used for the tcgen05 tiles, where they are measured (batch 4096: 27 splits 2 343, 54 splits 2 269, 16 splits 2 195 updates/s)."""
     if sm_count is None:
         sm_count = _sm_count(device)
     slots, chunks = ctas_per_sm * sm_count, (n_rows + 31) // 32
     best, best_cost = 1, None
     for n in range(1, min(64, chunks) + 1):
         per = (chunks + n - 1) // n
-        cost = sum(((t * n + slots - 1) // slots) for t in tiles_per_launch) * per
+        cost = sum(((t * n + slots - 1) // slots) for t in tiles_per_launch) * (per + cta_overhead) + per_split * n
         if best_cost is None or cost < best_cost:
             best, best_cost = n, cost
     return best
@@ -564,7 +567,7 @@ class MOBODY(object):
             # row splits of the weight-gradient GEMMs (partials summed in Adam, fixed order); 128 x 64 tiles per split:
             # critic 2 x (256 x 256 -> 8, 256 x (S+A) -> 2 per 64 columns), actor 8 + 2 per 64 columns of S
             if N >= self.TC_TRAIN_ROWS:   # tcgen05 path: 128 x 256 GEMM tiles, two CTAs per SM; critic launch 4 x 2 + 2 x 1 tiles, actor 2 x 2 + 1
-                nsplit = _wgrad_splits(N, (10, 5), self.device, ctas_per_sm=2)
+                nsplit = _wgrad_splits(N, (10, 5), self.device, ctas_per_sm=2, cta_overhead=4.0, per_split=0.36)
             else:
                 nsplit = _wgrad_splits(N, (2 * (8 + 2 * ((S + A + 63) // 64)), 8 + 2 * ((S + 63) // 64)), self.device)
         lib = _ffi.lib()
